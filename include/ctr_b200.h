@@ -1,0 +1,192 @@
+/* ctr_b200.h -- C-ABI of libctr_b200.so: sm_100a kernels for the torchctr embedding /
+ * feature-interaction hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers and sizes (no torch
+ * types), runs on the CUDA stream passed as the last argument (a `cudaStream_t`, spelled
+ * `void*` so that C callers need no CUDA headers), never allocates user-visible memory
+ * (scratch comes from a caller-provided workspace) and returns 0 or a negative
+ * `CTR_E_*` code; `ctr_last_error_string()` describes the last failure of the calling
+ * thread.  No C++ exception crosses the boundary.
+ *
+ * What each entry point replaces in the reference (paths relative to the torchctr repo):
+ *
+ *   ctr_emb_pool_fwd        torchctr/models/dnn.py:53-59  (mask, nn.Embedding gather,
+ *                           mask-multiply, sum(dim=1)) and the concat of dnn.py:61-67;
+ *                           with index_kind HASH also torchctr/utils.py:103-119 applied
+ *                           per element by torchctr/transformer.py:487-490; with
+ *                           index_kind REMAP also transformer.py:492-498.
+ *   ctr_hash_bucket_i64     torchctr/utils.py:103-119 (hash_bucket) on decimal ids.
+ *   ctr_emb_bwd_plan /      autograd of dnn.py:57-58 (aten::embedding_dense_backward) and
+ *   ctr_emb_bwd_apply       optimizer.step() at torchctr/trainer.py:303, restricted to the
+ *                           rows the batch touched; no dense [V, D] gradient exists.
+ *   ctr_rows_gather /       nn.Embedding.forward as used by DynamicEmbedding,
+ *   ctr_normal_fill_rows    torchctr/nn/embedding.py:69-87 (growth: N(0, std) new rows).
+ *   ctr_vocab_*             vocabulary fit / transform, transformer.py:451-498.
+ *   ctr_fm_fwd / ctr_fm_bwd FM second-order term (absent from the reference).
+ *   ctr_cross_*             DCN-v2 cross layer (absent from the reference).
+ */
+#ifndef CTR_B200_H
+#define CTR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTR_B200_ABI_VERSION 1
+#define CTR_MAX_FEATURES 40 /* features per launch group (kernel-parameter budget) */
+
+/* status codes */
+#define CTR_OK 0
+#define CTR_E_BADARG (-1)    /* null pointer, bad size, unsupported dim ...            */
+#define CTR_E_WORKSPACE (-2) /* workspace too small                                    */
+#define CTR_E_CUDA (-3)      /* a CUDA runtime call failed (see ctr_last_error_string) */
+#define CTR_E_UNSUPPORTED (-4)
+
+/* bits of the device-side status word (ctr_group_t.status, optional) */
+#define CTR_STATUS_INDEX_OOB 1u   /* a table index was >= num_rows (IndexError upstream) */
+#define CTR_STATUS_MAP_FULL 2u    /* vocabulary map ran out of slots                      */
+
+/* ctr_feature_t.index_kind */
+#define CTR_INDEX_DIRECT 0 /* ids are table rows                                          */
+#define CTR_INDEX_HASH 1   /* row = murmur3_32(decimal(id), seed) % num_rows               */
+#define CTR_INDEX_REMAP 2  /* row = vocab[id], unknown -> 0 (OOV)                          */
+
+/* ctr_feature_t.pooling */
+#define CTR_POOL_SUM 0
+#define CTR_POOL_MEAN 1 /* sum / max(#valid ids, 1): extension, not in the reference     */
+
+/* optimizer kinds for ctr_emb_bwd_apply */
+#define CTR_OPT_NONE 0            /* only emit unique rows + summed gradients               */
+#define CTR_OPT_SGD 1             /* torch.optim.SGD(lr)                                    */
+#define CTR_OPT_ADAGRAD 2         /* torch.optim.Adagrad(lr, eps) element-wise              */
+#define CTR_OPT_ROWWISE_ADAGRAD 3 /* one accumulator per row, += mean(g*g)                  */
+#define CTR_OPT_ADAM 4            /* torch.optim.SparseAdam (lazy Adam)                     */
+
+/* Device-resident open-addressing hash map: raw key (int64) -> table row (int32). */
+typedef struct ctr_vocab_map {
+    int64_t *keys;      /* [capacity], CTR_VOCAB_EMPTY where unused                        */
+    int32_t *rows;      /* [capacity]                                                      */
+    int64_t capacity;   /* power of two                                                    */
+} ctr_vocab_map_t;
+#define CTR_VOCAB_EMPTY INT64_MIN
+
+/* One sparse feature (= one table) of a launch group.  All pointers are device pointers. */
+typedef struct ctr_feature {
+    const int64_t *ids;      /* [B, L] row-major; negative = padding (dataset.py:54-57)     */
+    const float *id_weight;  /* [B, L] per-id multiplier or NULL                             */
+    float *table;            /* [num_rows, D] fp32, row-major                                */
+    float *state0;           /* optimizer state: Adagrad sum [V,D] | row-wise [V] | Adam m   */
+    float *state1;           /* Adam v [V,D] or NULL                                         */
+    float *bag_scale;        /* [B]: written by fwd, read by bwd when pooling == MEAN        */
+    const ctr_vocab_map_t *map; /* host pointer to a map descriptor, index_kind == REMAP     */
+    int64_t num_rows;        /* V (< 2^31)                                                   */
+    int32_t L;               /* id slots per bag                                             */
+    int32_t D;               /* embedding dim: multiple of 4 up to 128, or any D <= 32       */
+    int32_t out_col;         /* first column of this feature in the pooled / grad matrix     */
+    int32_t pooling;         /* CTR_POOL_*                                                   */
+    int32_t index_kind;      /* CTR_INDEX_*                                                  */
+    uint32_t hash_seed;
+} ctr_feature_t;
+
+/* A launch group: up to CTR_MAX_FEATURES features pooled for the same B bags into one
+ * row-major matrix out[B, out_stride] (the tower input of dnn.py:67), plus an optional
+ * dense block copied into columns [dense_col, dense_col + dense_width). */
+typedef struct ctr_group {
+    const ctr_feature_t *features; /* host array                                            */
+    int32_t num_features;
+    int32_t B;
+    float *out;              /* fwd: pooled output; bwd: gradient w.r.t. it                  */
+    int64_t out_stride;      /* floats per row of `out`                                      */
+    const float *dense;      /* [B, dense_width] or NULL                                     */
+    int32_t dense_width;
+    int32_t dense_col;
+    int32_t zero_from;       /* fwd: columns [zero_from, out_stride) are zero-filled; <0 = none */
+    uint32_t *status;        /* device status word (CTR_STATUS_*), may be NULL               */
+} ctr_group_t;
+
+typedef struct ctr_opt {
+    int32_t kind;            /* CTR_OPT_*                                                    */
+    float lr;                /* already decayed by the host if a schedule is used            */
+    float eps;
+    float beta1, beta2;      /* Adam                                                         */
+    int32_t step;            /* Adam bias-correction step (1-based)                          */
+} ctr_opt_t;
+
+const char *ctr_last_error_string(void);
+int ctr_abi_version(void);
+
+/* ---- lookup + pool ---------------------------------------------------------------- */
+int ctr_emb_pool_fwd(const ctr_group_t *group, void *stream);
+
+/* ids i64 [n] -> out i32 [n] = murmur3_32(decimal ASCII of id, seed) % buckets */
+int ctr_hash_bucket_i64(const int64_t *ids, int64_t n, uint32_t buckets, uint32_t seed, int32_t *out,
+                        void *stream);
+
+/* plain row gather out[i, :] = table[ids[i], :] (ids >= 0), used by DynamicEmbedding */
+int ctr_rows_gather(const int64_t *ids, int64_t n, const float *table, int64_t num_rows, int32_t D,
+                    float *out, uint32_t *status, void *stream);
+
+/* table[row0 .. row0 + n) ~ N(mean, std) from a counter-based generator (seed, row, col) */
+int ctr_normal_fill_rows(float *table, int64_t row0, int64_t n, int32_t D, float mean, float std,
+                         uint64_t seed, void *stream);
+
+/* min and max of an id tensor, written to out[0], out[1] (device) */
+int ctr_ids_minmax(const int64_t *ids, int64_t n, int64_t *out, void *stream);
+
+/* ---- backward: dedup/sort plan, then fused gradient scatter + optimizer ------------- */
+/* Bytes of workspace ctr_emb_bwd_plan needs for this group. */
+int64_t ctr_emb_bwd_workspace_bytes(const ctr_group_t *group);
+
+/* Sorts the (row, slot) pairs of the group and finds the runs of equal rows.  The plan
+ * lives inside `workspace` and stays valid until the workspace is reused.  It depends on
+ * the ids only, so it can be applied to several tables that share those ids. */
+int ctr_emb_bwd_plan(const ctr_group_t *group, void *workspace, int64_t workspace_bytes, void *stream);
+
+/* For every unique row touched: g = sum over its slots of coef * grad_out[bag, cols];
+ * then the optimizer update of that row, in place.  `group->out` is grad_out here and the
+ * features' `table/state/D/out_col` may differ from the ones the plan was built with
+ * (same ids, index mapping and num_rows).  Optional outputs (may be NULL):
+ *   uniq_feature i32 [U], uniq_row i32 [U], row_grad f32 [U, row_grad_stride], num_unique i64 [1]. */
+int ctr_emb_bwd_apply(const ctr_group_t *group, void *workspace, const ctr_opt_t *opt,
+                      int32_t *uniq_feature, int32_t *uniq_row, float *row_grad, int64_t row_grad_stride,
+                      int64_t *num_unique, void *stream);
+
+/* ---- vocabulary (dynamic growth) ---------------------------------------------------- */
+int64_t ctr_vocab_fit_workspace_bytes(int64_t n);
+/* keys i64 [n] (negative = padding): admit keys with batch count >= min_freq that are not in
+ * the map, give them rows next_row[0], next_row[0]+1, ... in order of first occurrence, and
+ * advance next_row[0] (device int64).  counts (i64 [>= final next_row], may be NULL) gets the
+ * batch count added for every key that is in the map after the call. */
+int ctr_vocab_fit(const ctr_vocab_map_t *map, const int64_t *keys, int64_t n, int32_t min_freq,
+                  int64_t *next_row, int64_t *counts, uint32_t *status, void *workspace,
+                  int64_t workspace_bytes, void *stream);
+/* keys -> rows (i32), unknown or negative -> oov_row */
+int ctr_vocab_transform(const ctr_vocab_map_t *map, const int64_t *keys, int64_t n, int32_t oov_row,
+                        int32_t *rows, void *stream);
+int ctr_vocab_clear(const ctr_vocab_map_t *map, void *stream);
+
+/* ---- feature interaction ------------------------------------------------------------- */
+/* x f32 [B, x_stride] holding F fields of D columns starting at column 0;
+ * out[b * out_stride] (+)= 0.5 * sum_d[(sum_f v)^2 - sum_f v^2] (+ sum of `first` [B, nfirst]). */
+int ctr_fm_fwd(const float *x, int64_t x_stride, int32_t B, int32_t F, int32_t D, const float *first,
+               int32_t nfirst, int64_t first_stride, float *out, int64_t out_stride, int32_t accumulate,
+               void *stream);
+/* gx[b, f*D+d] (+)= gout[b] * (sum_f' v[b,f',d] - v[b,f,d]);  gfirst[b, j] = gout[b] */
+int ctr_fm_bwd(const float *x, int64_t x_stride, int32_t B, int32_t F, int32_t D, const float *gout,
+               int64_t gout_stride, float *gx, int64_t gx_stride, int32_t accumulate, float *gfirst,
+               int32_t nfirst, int64_t gfirst_stride, void *stream);
+
+/* DCN-v2 cross epilogue: y = x0 * (u + bias) + x   (u = x W^T from the GEMM), all [B, d] */
+int ctr_cross_combine_fwd(const float *x0, const float *x, const float *u, const float *bias, int32_t B,
+                          int32_t d, int64_t stride, float *y, void *stream);
+/* given gy: gu = gy * x0 (its column sums are the bias gradient);  gx0 (+)= gy * (u + bias) */
+int ctr_cross_combine_bwd(const float *x0, const float *u, const float *bias, const float *gy, int32_t B,
+                          int32_t d, int64_t stride, float *gu, float *gx0, int32_t accumulate_gx0, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTR_B200_H */

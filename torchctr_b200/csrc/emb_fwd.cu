@@ -1,0 +1,334 @@
+// K1: fused index-map (direct | murmur3 hash | vocabulary remap) + row gather + segment pool.
+//
+// Replaces the per-feature loop of torchctr/models/dnn.py:53-59 (mask, nn.Embedding gather,
+// mask-multiply, sum over the sequence axis) and the concat of dnn.py:61-67: every feature of
+// a launch group is pooled straight into its column range of the tower-input matrix, the
+// dense block is copied beside it, and no [B, L, D] intermediate exists.
+//
+// Lane layout.  A row of D floats is covered by G lanes (float4 each when D % 4 == 0, one
+// float each otherwise).  A bag is owned by a team of T = clamp(pow2(L), G, 32) lanes =
+// R = T / G row slots.  Per chunk of T id slots every lane loads and maps ONE id (coalesced
+// 8-byte loads, one murmur3 / map probe per id), the mapped rows are exchanged by warp
+// shuffle, and each row slot issues its G row loads back to back (G independent 16-byte
+// loads in flight per lane).  Row slots are summed with xor-shuffles.  For single-id bags
+// (L == 1) a team takes K = min(G, 4) consecutive bags per trip instead, to keep the same
+// number of loads in flight.
+#include "common.cuh"
+
+namespace ctr {
+
+constexpr int kFwdThreads = 256;
+constexpr int kFwdWarps = kFwdThreads / kWarp;
+
+__device__ __forceinline__ void flag_status(uint32_t *status, uint32_t bit) {
+    if (status != nullptr) atomicOr(status, bit);
+}
+
+__device__ __forceinline__ float4 load_row_part(const DevFeature &f, int32_t row, int g_lane) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f.vec == 4) {
+        v = __ldg(reinterpret_cast<const float4 *>(f.table + (size_t)row * f.D) + g_lane);
+    } else {
+        v.x = __ldg(f.table + (size_t)row * f.D + g_lane);
+    }
+    return v;
+}
+
+__device__ __forceinline__ void store_out_part(const DevGroup &g, const DevFeature &f, int64_t bag, int g_lane,
+                                               float4 v) {
+    float *dst = g.out + bag * g.out_stride + f.out_col;
+    if (f.vec == 4) {
+        if (f.aligned) {
+            reinterpret_cast<float4 *>(dst)[g_lane] = v;
+        } else {
+            dst[4 * g_lane + 0] = v.x;
+            dst[4 * g_lane + 1] = v.y;
+            dst[4 * g_lane + 2] = v.z;
+            dst[4 * g_lane + 3] = v.w;
+        }
+    } else {
+        dst[g_lane] = v.x;
+    }
+}
+
+__global__ void __launch_bounds__(kFwdThreads) emb_pool_fwd_kernel(const __grid_constant__ DevGroup g) {
+    const int fi = blockIdx.y;
+    const int B = g.B;
+    if (fi == g.num_features) {  // dense block (dnn.py:61-67 concat) + zero padding columns
+        const int zero_w = g.zero_from >= 0 ? (int)(g.out_stride - g.zero_from) : 0;
+        const int w = g.dense_width + zero_w;
+        const int64_t total = (int64_t)B * w;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+             i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t b = i / w;
+            const int c = (int)(i - b * w);
+            if (c < g.dense_width)
+                g.out[b * g.out_stride + g.dense_col + c] = __ldg(g.dense + b * g.dense_width + c);
+            else
+                g.out[b * g.out_stride + g.zero_from + (c - g.dense_width)] = 0.f;
+        }
+        return;
+    }
+    const DevFeature &f = g.f[fi];
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = (int64_t)blockIdx.x * kFwdWarps + (threadIdx.x >> 5);
+    const int64_t total_warps = (int64_t)gridDim.x * kFwdWarps;
+    const int G = f.G;
+    const int L = f.L;
+    const bool mean = f.pooling == CTR_POOL_MEAN;
+
+    if (L == 1) {
+        const int K = G < 4 ? G : 4;
+        const int g_lane = lane & (G - 1);
+        const int team = lane / G;
+        const int bags_per_warp = (kWarp / G) * K;
+        const bool col_ok = g_lane * f.vec < f.D;
+        for (int64_t b0 = warp_global * bags_per_warp; b0 < B; b0 += total_warps * bags_per_warp) {
+            const int64_t team_bag0 = b0 + (int64_t)team * K;
+            int32_t row = -1;
+            float w = 1.f;
+            if (g_lane < K && team_bag0 + g_lane < B) {
+                const int64_t id = __ldg(f.ids + team_bag0 + g_lane);
+                row = map_index(f, id);
+                if (row == -2) { flag_status(g.status, CTR_STATUS_INDEX_OOB); row = -1; }
+                if (f.id_weight != nullptr && row >= 0) w = __ldg(f.id_weight + team_bag0 + g_lane);
+            }
+            float4 acc[4];
+            int32_t rk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int src = team * G + (k < K ? k : 0);
+                rk[k] = __shfl_sync(kFull, row, src);
+                const float wk = __shfl_sync(kFull, w, src);
+                acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < K && rk[k] >= 0 && col_ok) {
+                    const float4 v = load_row_part(f, rk[k], g_lane);
+                    acc[k] = make_float4(v.x * wk, v.y * wk, v.z * wk, v.w * wk);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int64_t bag = team_bag0 + k;
+                if (k < K && bag < B) {
+                    if (col_ok) store_out_part(g, f, bag, g_lane, acc[k]);
+                    if (mean && g_lane == 0) f.bag_scale[bag] = 1.f;
+                }
+            }
+        }
+        return;
+    }
+
+    int T = pow2_ceil(L);
+    T = T < G ? G : (T > kWarp ? kWarp : T);
+    const int t = lane & (T - 1);
+    const int team = lane / T;
+    const int teams_per_warp = kWarp / T;
+    const int slot = t / G;
+    const int g_lane = t & (G - 1);
+    const bool col_ok = g_lane * f.vec < f.D;
+    for (int64_t b0 = warp_global * teams_per_warp; b0 < B; b0 += total_warps * teams_per_warp) {
+        const int64_t bag = b0 + team;
+        const bool bag_ok = bag < B;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int cnt = 0;
+        for (int base = 0; base < L; base += T) {
+            const int pos = base + t;
+            int32_t row = -1;
+            float w = 1.f;
+            if (bag_ok && pos < L) {
+                const int64_t id = __ldg(f.ids + bag * L + pos);
+                row = map_index(f, id);
+                if (row == -2) { flag_status(g.status, CTR_STATUS_INDEX_OOB); row = -1; }
+                if (row >= 0) {
+                    ++cnt;
+                    if (f.id_weight != nullptr) w = __ldg(f.id_weight + bag * L + pos);
+                }
+            }
+            const int src0 = team * T + slot * G;
+#pragma unroll 4
+            for (int k = 0; k < G; ++k) {
+                const int32_t r = __shfl_sync(kFull, row, src0 + k);
+                const float wk = __shfl_sync(kFull, w, src0 + k);
+                if (r >= 0 && col_ok) {
+                    const float4 v = load_row_part(f, r, g_lane);
+                    acc.x = fmaf(wk, v.x, acc.x);
+                    acc.y = fmaf(wk, v.y, acc.y);
+                    acc.z = fmaf(wk, v.z, acc.z);
+                    acc.w = fmaf(wk, v.w, acc.w);
+                }
+            }
+        }
+        for (int off = G; off < T; off <<= 1) {
+            acc.x += __shfl_xor_sync(kFull, acc.x, off);
+            acc.y += __shfl_xor_sync(kFull, acc.y, off);
+            acc.z += __shfl_xor_sync(kFull, acc.z, off);
+            acc.w += __shfl_xor_sync(kFull, acc.w, off);
+        }
+        for (int off = 1; off < T; off <<= 1) cnt += __shfl_xor_sync(kFull, cnt, off);
+        if (bag_ok) {
+            float scale = 1.f;
+            if (mean) {
+                scale = 1.f / (float)(cnt > 1 ? cnt : 1);
+                if (t == 0) f.bag_scale[bag] = scale;
+                acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+            }
+            if (slot == 0 && col_ok) store_out_part(g, f, bag, g_lane, acc);
+        }
+    }
+}
+
+// ---- standalone index kernels ----------------------------------------------------------
+
+__global__ void hash_bucket_kernel(const int64_t *__restrict__ ids, int64_t n, uint32_t buckets, uint32_t seed,
+                                   int32_t *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (int32_t)(murmur3_decimal(ids[i], seed) % buckets);
+}
+
+__global__ void rows_gather_kernel(const int64_t *__restrict__ ids, int64_t n, const float *__restrict__ table,
+                                   int64_t num_rows, int D, float *__restrict__ out, uint32_t *status) {
+    // one thread per (row, 4-float piece) when D % 4 == 0, else per element
+    const int pieces = (D % 4 == 0) ? D / 4 : D;
+    const int64_t total = n * pieces;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / pieces;
+        const int p = (int)(i - r * pieces);
+        const int64_t id = __ldg(ids + r);
+        const bool ok = id >= 0 && id < num_rows;
+        if (!ok && p == 0) flag_status(status, CTR_STATUS_INDEX_OOB);
+        if (D % 4 == 0) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) v = __ldg(reinterpret_cast<const float4 *>(table + id * D) + p);
+            reinterpret_cast<float4 *>(out + r * D)[p] = v;
+        } else {
+            out[r * D + p] = ok ? __ldg(table + id * D + p) : 0.f;
+        }
+    }
+}
+
+// Counter-based normal generator: Philox-free, two rounds of mix64 -> Box-Muller.  Row/col
+// addressed so that growing a table in several steps gives the same rows as growing it once.
+__global__ void normal_fill_rows_kernel(float *table, int64_t row0, int64_t n, int D, float mean, float stdv,
+                                        uint64_t seed) {
+    const int64_t total = n * D;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = row0 + i / D;
+        const int c = (int)(i % D);
+        const uint64_t ctr = mix64(seed ^ mix64((uint64_t)r * 0x9e3779b97f4a7c15ull + (uint64_t)c + 1ull));
+        const uint32_t a = (uint32_t)(ctr >> 32), b = (uint32_t)ctr;
+        const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0, 1)
+        const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float z = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+        table[r * D + c] = mean + stdv * z;
+    }
+}
+
+__global__ void ids_minmax_kernel(const int64_t *__restrict__ ids, int64_t n, int64_t *out) {
+    long long lo = INT64_MAX, hi = INT64_MIN;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const long long v = ids[i];
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+    }
+    for (int off = 16; off; off >>= 1) {
+        const long long l2 = __shfl_xor_sync(kFull, lo, off), h2 = __shfl_xor_sync(kFull, hi, off);
+        lo = l2 < lo ? l2 : lo;
+        hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(reinterpret_cast<long long *>(out), lo);
+        atomicMax(reinterpret_cast<long long *>(out) + 1, hi);
+    }
+}
+
+__global__ void minmax_init_kernel(int64_t *out) {
+    out[0] = INT64_MAX;
+    out[1] = INT64_MIN;
+}
+
+static int grid_for(int64_t work_items, int threads, int cap) {
+    int64_t blocks = (work_items + threads - 1) / threads;
+    if (blocks < 1) blocks = 1;
+    if (blocks > cap) blocks = cap;
+    return (int)blocks;
+}
+
+}  // namespace ctr
+
+using namespace ctr;
+
+extern "C" int ctr_emb_pool_fwd(const ctr_group_t *group, void *stream) {
+    static thread_local DevGroup dg;
+    int rc = lower_group(group, &dg, /*need_tables=*/true, /*need_out=*/true);
+    if (rc != CTR_OK) return rc;
+    const int extra_w = dg.dense_width + (dg.zero_from >= 0 ? (int)(dg.out_stride - dg.zero_from) : 0);
+    if (dg.B == 0 || (dg.num_features == 0 && extra_w == 0)) return CTR_OK;
+    int64_t max_warps = 1;
+    for (int i = 0; i < dg.num_features; ++i) {
+        const DevFeature &f = dg.f[i];
+        int bags_per_warp;
+        if (f.L == 1) {
+            bags_per_warp = (kWarp / f.G) * (f.G < 4 ? f.G : 4);
+        } else {
+            int T = pow2_ceil(f.L);
+            T = T < f.G ? f.G : (T > kWarp ? kWarp : T);
+            bags_per_warp = kWarp / T;
+        }
+        const int64_t warps = (dg.B + bags_per_warp - 1) / bags_per_warp;
+        if (warps > max_warps) max_warps = warps;
+    }
+    if (extra_w > 0) {
+        const int64_t warps = ((int64_t)dg.B * extra_w + 4 * kWarp - 1) / (4 * kWarp);
+        if (warps > max_warps) max_warps = warps;
+    }
+    // enough blocks for every feature row of the grid to fill the machine a few times over
+    const int cap = kNumSMs * 8;
+    dim3 grid(grid_for(max_warps, kFwdWarps, cap), dg.num_features + (extra_w > 0 ? 1 : 0));
+    emb_pool_fwd_kernel<<<grid, kFwdThreads, 0, (cudaStream_t)stream>>>(dg);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int ctr_hash_bucket_i64(const int64_t *ids, int64_t n, uint32_t buckets, uint32_t seed, int32_t *out,
+                                   void *stream) {
+    CTR_REQUIRE(n >= 0 && buckets > 0, "n=%lld buckets=%u", (long long)n, buckets);
+    if (n == 0) return CTR_OK;
+    CTR_REQUIRE(ids != nullptr && out != nullptr, "null pointer");
+    hash_bucket_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(ids, n, buckets, seed, out);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int ctr_rows_gather(const int64_t *ids, int64_t n, const float *table, int64_t num_rows, int32_t D,
+                               float *out, uint32_t *status, void *stream) {
+    CTR_REQUIRE(n >= 0 && D >= 1 && num_rows >= 0, "bad sizes");
+    if (n == 0) return CTR_OK;
+    CTR_REQUIRE(ids != nullptr && table != nullptr && out != nullptr, "null pointer");
+    const int pieces = (D % 4 == 0) ? D / 4 : D;
+    rows_gather_kernel<<<grid_for(n * pieces, 256, kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(ids, n, table, num_rows,
+                                                                                              D, out, status);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int ctr_normal_fill_rows(float *table, int64_t row0, int64_t n, int32_t D, float mean, float stdv,
+                                    uint64_t seed, void *stream) {
+    CTR_REQUIRE(n >= 0 && D >= 1 && row0 >= 0, "bad sizes");
+    if (n == 0) return CTR_OK;
+    CTR_REQUIRE(table != nullptr, "null pointer");
+    normal_fill_rows_kernel<<<grid_for(n * D, 256, kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(table, row0, n, D, mean,
+                                                                                              stdv, seed);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int ctr_ids_minmax(const int64_t *ids, int64_t n, int64_t *out, void *stream) {
+    CTR_REQUIRE(n >= 0 && out != nullptr, "bad args");
+    minmax_init_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(out);
+    if (n > 0) {
+        CTR_REQUIRE(ids != nullptr, "null ids");
+        ids_minmax_kernel<<<grid_for(n, 256, kNumSMs * 4), 256, 0, (cudaStream_t)stream>>>(ids, n, out);
+    }
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}

@@ -1,0 +1,221 @@
+// K4: FM second-order interaction and the DCN-v2 cross-layer epilogue.
+//
+// Neither exists in the reference (torchctr/models/__init__.py exports only DNN); the
+// definitions are the ones of SURVEY.md section 8c / oracle/models.py:
+//   FM      out[b] = 0.5 * sum_d[(sum_f v[b,f,d])^2 - sum_f v[b,f,d]^2]   (+ first-order terms)
+//   cross   y = x0 * (x W^T + bias) + x
+// Both are HBM-bound element/row-wise work: a team of G lanes owns one sample, keeps the
+// per-column sums in registers and walks the F fields with all loads of a field group in
+// flight; the team reduction is a handful of xor-shuffles.
+#include "common.cuh"
+
+namespace ctr {
+
+struct FmArgs {
+    const float *x;
+    int64_t x_stride;
+    int B, F, D;
+    int vec, G;          // lanes per sample and floats per lane
+    const float *first;  // [B, nfirst] first-order terms (may be null)
+    int nfirst;
+    int64_t first_stride;
+    float *out;
+    int64_t out_stride;
+    int accumulate;
+    // backward
+    const float *gout;
+    int64_t gout_stride;
+    float *gx;
+    int64_t gx_stride;
+    float *gfirst;
+    int64_t gfirst_stride;
+};
+
+__device__ __forceinline__ float4 fm_load(const float *p, int vec) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec == 4) v = __ldg(reinterpret_cast<const float4 *>(p));
+    else v.x = __ldg(p);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) fm_fwd_kernel(const FmArgs a) {
+    const int G = a.G;
+    const int lane = threadIdx.x & 31;
+    const int g_lane = lane & (G - 1);
+    const bool col_ok = g_lane * a.vec < a.D;
+    const int64_t teams_total = (int64_t)gridDim.x * (256 / G);
+    const int64_t nb = ((int64_t)a.B + (kWarp / G) - 1) / (kWarp / G) * (kWarp / G);  // whole warps iterate together
+    for (int64_t b = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G; b < nb; b += teams_total) {
+        const bool ok = b < a.B;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+        if (ok && col_ok) {
+            const float *row = a.x + b * a.x_stride + g_lane * a.vec;
+#pragma unroll 8
+            for (int f = 0; f < a.F; ++f) {
+                const float4 v = fm_load(row + f * a.D, a.vec);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y);
+                q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+            }
+        }
+        float r = 0.5f * ((s.x * s.x - q.x) + (s.y * s.y - q.y) + (s.z * s.z - q.z) + (s.w * s.w - q.w));
+        if (ok && a.first != nullptr)
+            for (int j = g_lane; j < a.nfirst; j += G) r += __ldg(a.first + b * a.first_stride + j);
+        for (int off = 1; off < G; off <<= 1) r += __shfl_xor_sync(kFull, r, off);
+        if (ok && g_lane == 0) {
+            float *o = a.out + b * a.out_stride;
+            *o = a.accumulate ? *o + r : r;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) fm_bwd_kernel(const FmArgs a) {
+    const int G = a.G;
+    const int lane = threadIdx.x & 31;
+    const int g_lane = lane & (G - 1);
+    const bool col_ok = g_lane * a.vec < a.D;
+    const int64_t teams_total = (int64_t)gridDim.x * (256 / G);
+    for (int64_t b = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G; b < a.B; b += teams_total) {
+        const float go = __ldg(a.gout + b * a.gout_stride);
+        if (a.gfirst != nullptr)
+            for (int j = g_lane; j < a.nfirst; j += G) a.gfirst[b * a.gfirst_stride + j] = go;
+        if (!col_ok) continue;
+        const float *row = a.x + b * a.x_stride + g_lane * a.vec;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int f = 0; f < a.F; ++f) {
+            const float4 v = fm_load(row + f * a.D, a.vec);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        float *grow = a.gx + b * a.gx_stride + g_lane * a.vec;
+#pragma unroll 4
+        for (int f = 0; f < a.F; ++f) {
+            const float4 v = fm_load(row + f * a.D, a.vec);  // second touch: L1 / L2 hit
+            float4 gr = make_float4(go * (s.x - v.x), go * (s.y - v.y), go * (s.z - v.z), go * (s.w - v.w));
+            float *dst = grow + f * a.D;
+            if (a.vec == 4) {
+                float4 *d4 = reinterpret_cast<float4 *>(dst);
+                if (a.accumulate) {
+                    const float4 o = *d4;
+                    gr.x += o.x; gr.y += o.y; gr.z += o.z; gr.w += o.w;
+                }
+                *d4 = gr;
+            } else {
+                *dst = a.accumulate ? *dst + gr.x : gr.x;
+            }
+        }
+    }
+}
+
+static int fm_lower(FmArgs &a) {
+    CTR_REQUIRE(a.B >= 0 && a.F >= 1 && a.D >= 1, "bad FM shape B=%d F=%d D=%d", a.B, a.F, a.D);
+    CTR_REQUIRE(a.x != nullptr || a.B == 0, "x is null");
+    CTR_REQUIRE((int64_t)a.F * a.D <= a.x_stride, "F*D exceeds the row stride");
+    const bool v4 = a.D % 4 == 0 && a.x_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0 &&
+                    (a.gx == nullptr || (a.gx_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(a.gx) & 15u) == 0));
+    a.vec = v4 ? 4 : 1;
+    a.G = pow2_ceil(a.D / a.vec);
+    CTR_REQUIRE(a.G <= 32, "FM: D=%d too wide for one warp", a.D);
+    return CTR_OK;
+}
+
+// ---- DCN-v2 cross epilogue --------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    cross_combine_fwd_kernel(const float *__restrict__ x0, const float *__restrict__ x, const float *__restrict__ u,
+                             const float *__restrict__ bias, int B, int d, int64_t stride, float *__restrict__ y) {
+    const int64_t total = (int64_t)B * d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / d;
+        const int c = (int)(i - b * d);
+        const int64_t o = b * stride + c;
+        y[o] = fmaf(x0[o], u[o] + __ldg(bias + c), x[o]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    cross_combine_bwd_kernel(const float *__restrict__ x0, const float *__restrict__ u, const float *__restrict__ bias,
+                             const float *__restrict__ gy, int B, int d, int64_t stride, float *__restrict__ gu,
+                             float *__restrict__ gx0, int accumulate) {
+    const int64_t total = (int64_t)B * d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / d;
+        const int c = (int)(i - b * d);
+        const int64_t o = b * stride + c;
+        const float g = gy[o];
+        gu[o] = g * x0[o];
+        const float t = g * (u[o] + __ldg(bias + c));
+        gx0[o] = accumulate ? gx0[o] + t : t;
+    }
+}
+
+static int ew_grid(int64_t total) {
+    int64_t blocks = (total + 1023) / 1024;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    return blocks < 1 ? 1 : (int)blocks;
+}
+
+}  // namespace ctr
+
+using namespace ctr;
+
+extern "C" int ctr_fm_fwd(const float *x, int64_t x_stride, int32_t B, int32_t F, int32_t D, const float *first,
+                          int32_t nfirst, int64_t first_stride, float *out, int64_t out_stride, int32_t accumulate,
+                          void *stream) {
+    FmArgs a{};
+    a.x = x; a.x_stride = x_stride; a.B = B; a.F = F; a.D = D;
+    a.first = nfirst > 0 ? first : nullptr; a.nfirst = nfirst; a.first_stride = first_stride;
+    a.out = out; a.out_stride = out_stride; a.accumulate = accumulate;
+    int rc = fm_lower(a);
+    if (rc != CTR_OK) return rc;
+    if (B == 0) return CTR_OK;
+    CTR_REQUIRE(out != nullptr, "out is null");
+    CTR_REQUIRE(nfirst == 0 || first != nullptr, "first is null");
+    const int teams_per_block = 256 / a.G;
+    int64_t blocks = ((int64_t)B + teams_per_block - 1) / teams_per_block;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    fm_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int ctr_fm_bwd(const float *x, int64_t x_stride, int32_t B, int32_t F, int32_t D, const float *gout,
+                          int64_t gout_stride, float *gx, int64_t gx_stride, int32_t accumulate, float *gfirst,
+                          int32_t nfirst, int64_t gfirst_stride, void *stream) {
+    FmArgs a{};
+    a.x = x; a.x_stride = x_stride; a.B = B; a.F = F; a.D = D;
+    a.gout = gout; a.gout_stride = gout_stride; a.gx = gx; a.gx_stride = gx_stride; a.accumulate = accumulate;
+    a.gfirst = nfirst > 0 ? gfirst : nullptr; a.nfirst = nfirst; a.gfirst_stride = gfirst_stride;
+    int rc = fm_lower(a);
+    if (rc != CTR_OK) return rc;
+    if (B == 0) return CTR_OK;
+    CTR_REQUIRE(gout != nullptr && gx != nullptr, "null gradient pointer");
+    CTR_REQUIRE((int64_t)F * D <= gx_stride, "F*D exceeds the gradient row stride");
+    const int teams_per_block = 256 / a.G;
+    int64_t blocks = ((int64_t)B + teams_per_block - 1) / teams_per_block;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    fm_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int ctr_cross_combine_fwd(const float *x0, const float *x, const float *u, const float *bias, int32_t B,
+                                     int32_t d, int64_t stride, float *y, void *stream) {
+    CTR_REQUIRE(B >= 0 && d >= 1 && stride >= d, "bad cross shape");
+    if (B == 0) return CTR_OK;
+    CTR_REQUIRE(x0 && x && u && bias && y, "null pointer");
+    cross_combine_fwd_kernel<<<ew_grid((int64_t)B * d), 256, 0, (cudaStream_t)stream>>>(x0, x, u, bias, B, d, stride, y);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int ctr_cross_combine_bwd(const float *x0, const float *u, const float *bias, const float *gy, int32_t B,
+                                     int32_t d, int64_t stride, float *gu, float *gx0, int32_t accumulate_gx0,
+                                     void *stream) {
+    CTR_REQUIRE(B >= 0 && d >= 1 && stride >= d, "bad cross shape");
+    if (B == 0) return CTR_OK;
+    CTR_REQUIRE(x0 && u && bias && gy && gu && gx0, "null pointer");
+    cross_combine_bwd_kernel<<<ew_grid((int64_t)B * d), 256, 0, (cudaStream_t)stream>>>(x0, u, bias, gy, B, d, stride, gu,
+                                                                                     gx0, accumulate_gx0);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}

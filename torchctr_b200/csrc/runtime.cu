@@ -1,0 +1,106 @@
+// Error reporting and argument lowering shared by every entry point of libctr_b200.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace ctr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return CTR_E_CUDA;
+}
+
+int lower_group(const ctr_group_t *g, DevGroup *out, bool need_tables, bool need_out) {
+    CTR_REQUIRE(g != nullptr && out != nullptr, "group is null");
+    CTR_REQUIRE(g->num_features >= 0 && g->num_features <= CTR_MAX_FEATURES,
+                "num_features=%d outside [0, %d]", g->num_features, CTR_MAX_FEATURES);
+    CTR_REQUIRE(g->num_features == 0 || g->features != nullptr, "features is null");
+    CTR_REQUIRE(g->B >= 0, "B=%d is negative", g->B);
+    CTR_REQUIRE(!need_out || g->out != nullptr || g->B == 0, "out is null");
+    CTR_REQUIRE(g->dense_width >= 0, "dense_width is negative");
+    CTR_REQUIRE(g->dense_width == 0 || g->dense != nullptr, "dense is null but dense_width=%d", g->dense_width);
+    memset(out, 0, sizeof(*out));
+    out->num_features = g->num_features;
+    out->B = g->B;
+    out->out = g->out;
+    out->out_stride = g->out_stride;
+    out->dense = g->dense;
+    out->dense_width = g->dense_width;
+    out->dense_col = g->dense_col;
+    out->status = g->status;
+    out->zero_from = (g->zero_from >= 0 && g->zero_from < g->out_stride) ? g->zero_from : -1;
+    CTR_REQUIRE(g->dense_width == 0 || (g->dense_col >= 0 && g->dense_col + (int64_t)g->dense_width <= g->out_stride),
+                "dense block [%d, %d) outside out_stride=%lld", g->dense_col, g->dense_col + g->dense_width,
+                (long long)g->out_stride);
+    uint64_t base = 0;
+    for (int i = 0; i < g->num_features; ++i) {
+        const ctr_feature_t &s = g->features[i];
+        DevFeature &d = out->f[i];
+        CTR_REQUIRE(s.ids != nullptr || g->B == 0, "feature %d: ids is null", i);
+        CTR_REQUIRE(!need_tables || s.table != nullptr, "feature %d: table is null", i);
+        CTR_REQUIRE(s.num_rows > 0 && s.num_rows < (1ll << 31), "feature %d: num_rows=%lld outside [1, 2^31)", i,
+                    (long long)s.num_rows);
+        CTR_REQUIRE(s.L >= 1, "feature %d: L=%d must be >= 1", i, s.L);
+        CTR_REQUIRE((int64_t)s.L * g->B < (1ll << 32), "feature %d: B*L does not fit 32 bits", i);
+        CTR_REQUIRE(s.D >= 1 && ((s.D % 4 == 0 && s.D <= 128) || s.D <= 32),
+                    "feature %d: D=%d unsupported (multiple of 4 up to 128, or any D <= 32)", i, s.D);
+        CTR_REQUIRE(s.pooling == CTR_POOL_SUM || s.pooling == CTR_POOL_MEAN, "feature %d: bad pooling %d", i, s.pooling);
+        CTR_REQUIRE(s.out_col >= 0 && s.out_col + (int64_t)s.D <= g->out_stride,
+                    "feature %d: columns [%d, %d) outside out_stride=%lld", i, s.out_col, s.out_col + s.D,
+                    (long long)g->out_stride);
+        d.ids = s.ids;
+        d.id_weight = s.id_weight;
+        d.table = s.table;
+        d.state0 = s.state0;
+        d.state1 = s.state1;
+        d.bag_scale = s.bag_scale;
+        d.num_rows = (uint32_t)s.num_rows;
+        d.L = s.L;
+        d.D = s.D;
+        d.out_col = s.out_col;
+        d.pooling = s.pooling;
+        d.index_kind = s.index_kind;
+        d.hash_seed = s.hash_seed;
+        if (s.index_kind == CTR_INDEX_REMAP) {
+            CTR_REQUIRE(s.map != nullptr && s.map->keys != nullptr && s.map->rows != nullptr,
+                        "feature %d: REMAP needs a vocabulary map", i);
+            CTR_REQUIRE(s.map->capacity > 0 && (s.map->capacity & (s.map->capacity - 1)) == 0,
+                        "feature %d: map capacity must be a power of two", i);
+            d.map_keys = s.map->keys;
+            d.map_rows = s.map->rows;
+            d.map_mask = s.map->capacity - 1;
+        } else {
+            CTR_REQUIRE(s.index_kind == CTR_INDEX_DIRECT || s.index_kind == CTR_INDEX_HASH,
+                        "feature %d: bad index_kind %d", i, s.index_kind);
+        }
+        CTR_REQUIRE(s.pooling != CTR_POOL_MEAN || s.bag_scale != nullptr || g->B == 0,
+                    "feature %d: mean pooling needs bag_scale [B]", i);
+        d.vec = (s.D % 4 == 0) ? 4 : 1;
+        d.G = pow2_ceil(s.D / d.vec);
+        d.aligned = (d.vec == 4 && s.out_col % 4 == 0 && g->out_stride % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(g->out) & 15u) == 0)
+                        ? 1
+                        : 0;
+        if (d.vec == 4 && s.table != nullptr)
+            CTR_REQUIRE((reinterpret_cast<uintptr_t>(s.table) & 15u) == 0, "feature %d: table not 16-byte aligned", i);
+        d.row_base = (uint32_t)base;
+        base += (uint64_t)s.num_rows;
+        CTR_REQUIRE(base < 0xffffffffull, "group key space (sum of num_rows) must stay below 2^32-1; split the group");
+    }
+    return CTR_OK;
+}
+
+}  // namespace ctr
+
+extern "C" const char *ctr_last_error_string(void) { return ctr::g_err; }
+extern "C" int ctr_abi_version(void) { return CTR_B200_ABI_VERSION; }
