@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Headline benchmark: train samples/s of a Criteo-shape DeepFM (BASELINE.json configs[1]:
+26 sparse + 13 dense, emb dim 16, batch 65536) on N B200s, plus the embedding kernels'
+achieved HBM GB/s against the measured roofline, the end-to-end number through the public
+module API with host buffers, and the reference's CPU path timed beside it.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference        # the reference arithmetic on the host cores
+
+One JSON line on stdout (rank 0).  A "step" is forward + backward + optimizer update of one
+batch of synthetic Zipf(1.05) ids / N(0,1) dense / Bernoulli(0.25) labels.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# Criteo-like cardinalities: 3 tables >= 1e7, the rest 1e1 .. 2e6
+CRITEO_VOCABS = [10_000_000, 10_000_000, 10_000_000, 2_000_000, 1_000_000, 1_000_000, 500_000, 300_000,
+                 100_000, 100_000, 50_000, 20_000, 10_000, 10_000, 5_000, 5_000, 2_000, 2_000, 1_000, 1_000,
+                 1_000, 500, 100, 50, 20, 10]
+NUM_DENSE = 13
+EMB_DIM = 16
+HIDDEN = [256, 128, 64]
+ZIPF_A = 1.05
+LR = 0.01
+
+
+def feat_configs(vocabs=CRITEO_VOCABS, dim=EMB_DIM, num_dense=NUM_DENSE):
+    fc = [{"name": f"C{i + 1}", "type": "sparse", "num_embeddings": v, "emb_dim": dim} for i, v in enumerate(vocabs)]
+    fc += [{"name": f"I{i + 1}", "type": "dense"} for i in range(num_dense)]
+    return fc
+
+
+def zipf_ids(gen, n, V, a=ZIPF_A):
+    """Zipf(a)-distributed ranks in [0, V) by inverting the continuous CDF (bounded Zipf)."""
+    u = torch.rand(n, generator=gen, dtype=torch.float64)
+    s = 1.0 - a
+    x = ((V ** s - 1.0) * u + 1.0) ** (1.0 / s)
+    return (x.floor().long() - 1).clamp_(0, V - 1)
+
+
+def make_batch(seed, B, vocabs=CRITEO_VOCABS, num_dense=NUM_DENSE, pin=False):
+    gen = torch.Generator().manual_seed(seed)
+    feats = {}
+    for i, V in enumerate(vocabs):
+        feats[f"C{i + 1}"] = zipf_ids(gen, B, V).reshape(B, 1)
+    feats["dense_features"] = torch.randn(B, num_dense, generator=gen)
+    labels = (torch.rand(B, 1, generator=gen) < 0.25).float()
+    if pin:
+        feats = {k: v.pin_memory() for k, v in feats.items()}
+        labels = labels.pin_memory()
+    return feats, labels
+
+
+def batch_bytes(batch):
+    feats, labels = batch
+    return sum(v.numel() * v.element_size() for v in feats.values()) + labels.numel() * labels.element_size()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, B, budget_s):
+    """The reference arithmetic (oracle.models.OracleDeepFM == nn.Embedding + dense autograd +
+    dense torch.optim.Adagrad, the path torchctr/trainer.py:291-303 drives) on the host cores."""
+    from oracle import models as om
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    fc = feat_configs()
+    torch.manual_seed(0)
+    model = om.OracleDeepFM(fc, HIDDEN).train()
+    opt = torch.optim.Adagrad(model.parameters(), lr=LR)
+    batches = [make_batch(100 + i, B) for i in range(2)]
+
+    def step(i):
+        opt.zero_grad()
+        loss = model.training_step(batches[i % len(batches)], i)
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    t0 = time.perf_counter()
+    step(0)
+    first = time.perf_counter() - t0
+    warm_done = 1
+    while warm_done < warmup and (time.perf_counter() - t0) < 0.3 * budget_s:
+        step(warm_done); warm_done += 1
+    per = max((time.perf_counter() - t0) / warm_done, 1e-3)
+    k = max(1, min(steps, int((budget_s - (time.perf_counter() - t0)) / per)))
+    t1 = time.perf_counter()
+    for i in range(k):
+        step(warm_done + i)
+    dt = time.perf_counter() - t1
+    return {"value": B * k / dt, "steps": k, "warmup": warm_done, "ms_per_step": 1e3 * dt / k, "cores": threads,
+            "first_step_s": first, "B": B}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.batch
+    r = cpu_reference_run(args.steps, args.warmup, B, budget_s=150.0)
+    sample = (f"{r['steps']} steps (after {r['warmup']} warm-up) of B={B} samples each, full-size tables "
+              f"({sum(CRITEO_VOCABS)} rows x {EMB_DIM}), dense autograd + dense torch.optim.Adagrad, eager fp32 on CPU")
+    line = {
+        "impl": "reference", "metric": "train samples/s, Criteo-shape DeepFM", "value": r["value"], "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(B, 1),
+        "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(B, n_gpus):
+    return {"workload": "BASELINE configs[1]: DeepFM, 26 sparse (Zipf(1.05) ids, Criteo-like cardinalities, "
+                        f"{sum(CRITEO_VOCABS)} rows total) + 13 dense, emb dim 16, tower 256-128-64, Adagrad",
+            "batch_per_gpu": B, "global_batch": B * n_gpus, "emb_dim": EMB_DIM, "num_sparse": len(CRITEO_VOCABS),
+            "num_dense": NUM_DENSE, "table_rows": sum(CRITEO_VOCABS),
+            "l2": "inputs larger than L2: 2.4 GB of tables + 2.4 GB optimizer state, 4 distinct batches cycled"}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from torchctr_b200 import ops
+    from torchctr_b200.models import DeepFM
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    torch.backends.cuda.matmul.allow_tf32 = True        # tower GEMMs on tensor cores (TF32 in, fp32 accumulate)
+    torch.backends.cudnn.allow_tf32 = True
+
+    torch.manual_seed(0)
+    fc = feat_configs()
+    if world > 1:
+        from torchctr_b200.parallel import shard_model
+    model = DeepFM(fc, HIDDEN)
+    model = model.to(dev).train()
+    if world > 1:
+        model = shard_model(model, dist.group.WORLD)
+    opt = torch.optim.Adagrad(model.dense_parameters(), lr=LR)    # tower etc.; tables take the fused row update
+    model.bind_optimizer(opt, kind="adagrad")
+
+    nb = 4
+    host = [make_batch(1000 * rank + i, B, pin=True) for i in range(nb)]
+    resident = [({k: v.to(dev) for k, v in f.items()}, l.to(dev)) for f, l in host]
+    h2d = batch_bytes(host[0])
+
+    def step(batch, i):
+        opt.zero_grad(set_to_none=True)
+        loss = model.training_step(batch, i)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(batches, steps, read_loss):
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        t0.record()
+        for i in range(steps):
+            loss = step(batches[i % nb], i)
+            if read_loss:
+                loss.item()                              # device -> host read of the step's result
+        t1.record()
+        barrier()
+        wall = time.perf_counter() - w0
+        ms = t0.elapsed_time(t1)
+        if read_loss:
+            ms = max(ms, 1e3 * wall)                    # host-inclusive for the end-to-end leg
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for i in range(max(args.warmup, 3)):
+        step(resident[i % nb], i)
+    launches0 = ops.kernel_launches()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    with ops.KernelTimer() as kt:
+        ms = timed(resident, args.steps, read_loss=False)
+        spans = kt.summary()
+    launches = ops.kernel_launches() - launches0
+    clock_info = clocks.stop() if rank == 0 else None
+    # end to end: pinned host buffers in, loss out, every step
+    for i in range(3):
+        step(host[i % nb], i)
+    ms_e2e = timed(host, args.steps, read_loss=True)
+
+    value = B * world * args.steps / (ms / 1e3)
+    e2e = B * world * args.steps / (ms_e2e / 1e3)
+
+    # roofline of the embedding kernels: algorithmic bytes / CUDA-event time
+    S = B * len(CRITEO_VOCABS)
+    D = EMB_DIM
+    uniq = sum(int(torch.unique(f[f"C{i + 1}"]).numel()) for f, _ in resident for i in range(len(CRITEO_VOCABS))) / nb
+    peak, peak_src = measured_peak_hbm()
+    fwd_bytes = 8 * S + 4 * D * S + 4 * D * S            # ids + rows + pooled out   (D = 16 group)
+    upd_bytes = 8 * S + 4 * D * S + 16 * D * uniq        # ids + grad_out + Adagrad rmw of unique rows
+    kern = {}
+    for name, (calls, total_ms) in spans.items():
+        kern[name] = {"calls_per_step": calls / args.steps, "ms_per_step": total_ms / args.steps}
+    # two lookup groups per step (D=16 tables, D=1 first-order tables): scale bytes by the widths
+    fwd_bytes_all = fwd_bytes + (8 * S + 4 * S + 4 * S)
+    upd_bytes_all = upd_bytes + (8 * S + 4 * S + 16 * uniq)
+    roofline = None
+    if "emb_bwd_apply" in kern and "emb_pool_fwd" in kern:
+        cand = {"emb_bwd_apply (sparse grad scatter + fused Adagrad)": (upd_bytes_all, kern["emb_bwd_apply"]["ms_per_step"]),
+                "emb_pool_fwd (gather + pool + concat)": (fwd_bytes_all, kern["emb_pool_fwd"]["ms_per_step"])}
+        dom = max(cand, key=lambda k: cand[k][1])
+        for k, (bytes_, t) in cand.items():
+            kern[k.split(" ")[0]]["achieved_GBs"] = bytes_ / (t * 1e-3) / 1e9
+            kern[k.split(" ")[0]]["algorithmic_bytes_per_step"] = bytes_
+        b, t = cand[dom]
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": b / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": b / (t * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_step": b, "ms_per_step": t, "unique_rows_per_step": uniq}
+
+    line = {
+        "metric": "train samples/s, Criteo-shape DeepFM", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, world),
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "kernels": kern, "roofline": roofline, "clocks": clock_info,
+        "tower_matmul": "torch F.linear, TF32 tensor cores, fp32 accumulate",
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(3, 1, B, budget_s=40.0)
+            line["cpu_baseline"] = {
+                "value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                "sample": f"{r['steps']} steps of B={r['B']} samples, full-size tables, dense autograd + dense Adagrad "
+                          f"(oracle.models.OracleDeepFM, eager fp32 CPU)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

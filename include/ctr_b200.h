@@ -117,6 +117,8 @@ typedef struct ctr_opt {
 
 const char *ctr_last_error_string(void);
 int ctr_abi_version(void);
+/* number of kernels this library has launched since it was loaded (bench.py reports it) */
+int64_t ctr_kernel_launches(void);
 
 /* ---- lookup + pool ---------------------------------------------------------------- */
 int ctr_emb_pool_fwd(const ctr_group_t *group, void *stream);
@@ -166,6 +168,9 @@ int ctr_vocab_fit(const ctr_vocab_map_t *map, const int64_t *keys, int64_t n, in
 /* keys -> rows (i32), unknown or negative -> oov_row */
 int ctr_vocab_transform(const ctr_vocab_map_t *map, const int64_t *keys, int64_t n, int32_t oov_row,
                         int32_t *rows, void *stream);
+/* insert n distinct (key, row) pairs that are not in the map (rebuild after a capacity change) */
+int ctr_vocab_insert(const ctr_vocab_map_t *map, const int64_t *keys, const int32_t *rows, int64_t n,
+                     uint32_t *status, void *stream);
 int ctr_vocab_clear(const ctr_vocab_map_t *map, void *stream);
 
 /* ---- feature interaction ------------------------------------------------------------- */

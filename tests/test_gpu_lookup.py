@@ -1,0 +1,296 @@
+"""GPU parity tests of the lookup / backward / optimizer kernels, through the C ABI
+(torchctr_b200.ops -> libctr_b200.so), against the CPU oracle and the golden fixtures.
+
+Tolerances (BASELINE.json north_star): bit-exact for hashed / remapped indices, dedup and vocab
+growth; <= 1e-5 relative (fp32, relative to max|ref|) for pooled embeddings, gradients and updated rows.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def close(got, ref, rtol=RTOL):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    scale = max(float(ref.abs().max()), 1e-30)
+    err = float((got - ref).abs().max())
+    assert err <= rtol * scale, f"max abs err {err:.3e} > {rtol} * {scale:.3e}"
+
+
+def make_ids(gen, B, L, V, pad_frac=0.3, hot=0):
+    ids = torch.randint(0, V, (B, L), generator=gen)
+    if L > 1:
+        lens = torch.randint(0, L + 1, (B,), generator=gen)
+        ids[torch.arange(L).unsqueeze(0) >= lens.unsqueeze(1)] = -100
+    elif pad_frac:
+        ids[torch.rand(B, 1, generator=gen) < pad_frac * 0.2] = -100
+    if hot:
+        ids[:, 0] = torch.randint(0, hot, (B,), generator=gen)
+    return ids
+
+
+def run_fwd(specs_cpu, B, dense=None, dev="cuda"):
+    """specs_cpu: list of dict(ids, table, pooling, id_weight, index_kind, seed, num_rows).  Returns (out, layout)."""
+    from torchctr_b200 import ops
+    col, cols = 0, []
+    for s in specs_cpu:
+        cols.append(col)
+        col += s["table"].shape[1]
+    dense_col, width = col, col + (0 if dense is None else dense.shape[1])
+    stride = (width + 3) // 4 * 4
+    out = torch.full((B, stride), float("nan"), device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    feats = []
+    for s, c in zip(specs_cpu, cols):
+        feats.append(ops.FeatureSpec(
+            ids=s["ids"].to(dev), table=s["table"].to(dev).contiguous(), num_rows=s["table"].shape[0],
+            D=s["table"].shape[1], out_col=c, pooling=s.get("pooling", "sum"), index_kind=s.get("index_kind", "direct"),
+            hash_seed=s.get("seed", 0), id_weight=None if s.get("id_weight") is None else s["id_weight"].to(dev),
+            bag_scale=torch.empty(B, device=dev) if s.get("pooling") == "mean" else None))
+    call = ops.make_group(feats, B, out, stride, dense=None if dense is None else dense.to(dev), dense_col=dense_col,
+                          zero_from=width if stride > width else -1, status=status)
+    ops.emb_pool_fwd(call)
+    torch.cuda.synchronize()
+    return out, cols, width, feats, int(status.item())
+
+
+@pytest.mark.parametrize("D,L", [(16, 1), (16, 12), (16, 50), (16, 200), (9, 1), (9, 7), (32, 1), (32, 33), (64, 1),
+                                 (64, 20), (1, 1), (1, 5), (128, 3), (4, 2), (8, 1)])
+def test_pooled_forward_matches_oracle(D, L):
+    from oracle import embedding as oe
+    gen = torch.Generator().manual_seed(100 * D + L)
+    B, V = 301, 97
+    ids = make_ids(gen, B, L, V)
+    ids[3] = -100                                       # an empty bag -> zero vector
+    table = torch.randn(V, D, generator=gen)
+    for pooling in ("sum", "mean"):
+        out, cols, width, _, status = run_fwd([dict(ids=ids, table=table, pooling=pooling)], B)
+        assert status == 0
+        close(out[:, :D], oe.pooled_lookup(ids, table, pooling))
+        assert float(out[:, width:].abs().sum()) == 0.0     # padding columns are zero
+        assert float(out[3, :D].abs().sum()) == 0.0
+
+
+def test_forward_group_with_dense_and_weights():
+    from oracle import embedding as oe
+    gen = torch.Generator().manual_seed(7)
+    B = 1000
+    dims = [16, 16, 9, 16, 1, 32]
+    Ls = [1, 1, 1, 12, 1, 40]
+    specs, refs = [], []
+    for D, L in zip(dims, Ls):
+        V = 50 + D
+        ids = make_ids(gen, B, L, V)
+        table = torch.randn(V, D, generator=gen)
+        w = torch.rand(B, L, generator=gen) if L > 1 else None
+        specs.append(dict(ids=ids, table=table, id_weight=w, pooling="mean" if D == 32 else "sum"))
+        refs.append(oe.pooled_lookup(ids, table, "mean" if D == 32 else "sum", per_id_weight=w))
+    dense = torch.randn(B, 5, generator=gen)
+    out, cols, width, _, status = run_fwd(specs, B, dense=dense)
+    assert status == 0
+    ref = torch.cat(refs + [dense], dim=1)
+    close(out[:, :width], ref)
+    assert out.shape[1] % 4 == 0 and float(out[:, width:].abs().sum()) == 0.0
+
+
+def test_l1_lookup_is_bit_exact_copy_of_rows():
+    """Full BASELINE config-2 size: 26 single-id features, B=65536, D=16 -- a pure row copy."""
+    gen = torch.Generator().manual_seed(11)
+    B, F, D = 65536, 26, 16
+    specs = []
+    for f in range(F):
+        V = [1000, 50000, 2_000_000][f % 3]
+        specs.append(dict(ids=torch.randint(0, V, (B, 1), generator=gen), table=torch.randn(V, D, generator=gen)))
+    dense = torch.randn(B, 13, generator=gen)
+    out, cols, width, feats, status = run_fwd(specs, B, dense=dense)
+    assert status == 0 and width == 429 and out.shape[1] == 432
+    for f, c in zip(feats, cols):
+        assert torch.equal(out[:, c:c + D], f.table[f.ids[:, 0]])
+    assert torch.equal(out[:, 416:429].cpu(), dense)
+
+
+def test_out_of_range_id_sets_status_not_memory():
+    gen = torch.Generator().manual_seed(5)
+    ids = torch.randint(0, 10, (64, 3), generator=gen)
+    ids[5, 1] = 10                                           # == num_rows -> IndexError upstream
+    out, _, _, _, status = run_fwd([dict(ids=ids, table=torch.randn(10, 16, generator=gen))], 64)
+    assert status & 1
+
+
+def test_hash_bucket_matches_sklearn_golden(golden_dir):
+    from torchctr_b200 import ops
+    with open(os.path.join(golden_dir, "hash_golden.json")) as f:
+        rows = [r for r in json.load(f) if r["is_int"]]
+    for seed in sorted({r["seed"] for r in rows}):
+        for buckets in sorted({r["buckets"] for r in rows}):
+            sel = [r for r in rows if r["seed"] == seed and r["buckets"] == buckets]
+            ids = torch.tensor([r["v"] for r in sel], dtype=torch.int64, device="cuda")
+            got = ops.hash_bucket(ids, buckets, seed).cpu().numpy()
+            assert (got == np.array([r["bucket"] for r in sel], dtype=np.int32)).all()
+
+
+def test_hash_bucket_matches_oracle_on_random_ids():
+    from oracle import hashing as oh
+    from torchctr_b200 import ops
+    rng = np.random.default_rng(3)
+    ids = np.concatenate([rng.integers(0, 2 ** 31, 200000), rng.integers(-2 ** 62, 2 ** 62, 50000),
+                          np.array([0, 9, 10, 99, 100, 2 ** 31 - 1, -1, 2 ** 63 - 1, -2 ** 63, 10 ** 18, 10 ** 9, 999999999])])
+    for seed, buckets in ((0, 1000003), (12345, 2 ** 31 - 1), (2 ** 32 - 1, 100)):
+        got = ops.hash_bucket(torch.from_numpy(ids).cuda(), buckets, seed).cpu().numpy()
+        assert (got == oh.hash_bucket_ids(ids, buckets, seed)).all()
+    with pytest.raises(OverflowError):
+        ops.hash_bucket(torch.zeros(1, dtype=torch.int64, device="cuda"), 10, 2 ** 32)
+
+
+def test_hashed_lookup_fuses_hash_bucket():
+    from oracle import embedding as oe
+    from oracle import hashing as oh
+    gen = torch.Generator().manual_seed(21)
+    B, L, V, D = 500, 6, 1009, 16
+    raw = torch.randint(0, 2 ** 40, (B, L), generator=gen)
+    raw[torch.rand(B, L, generator=gen) < 0.3] = -100
+    table = torch.randn(V, D, generator=gen)
+    rows = torch.from_numpy(oh.hash_bucket_ids(raw.clamp(min=0).numpy(), V, 7)).long()
+    rows[raw < 0] = -100
+    out, *_ = run_fwd([dict(ids=raw, table=table, index_kind="hash", seed=7)], B)
+    close(out[:, :D], oe.pooled_lookup(rows, table))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_bwd(specs_cpu, B, grad_out, opt_kind="none", opt_kw=None, states=None, dev="cuda"):
+    from torchctr_b200 import ops
+    col, cols = 0, []
+    for s in specs_cpu:
+        cols.append(col)
+        col += s["table"].shape[1]
+    feats = []
+    for i, (s, c) in enumerate(zip(specs_cpu, cols)):
+        st = states[i] if states else (None, None)
+        feats.append(ops.FeatureSpec(
+            ids=s["ids"].to(dev), table=s["table"].to(dev).contiguous(), num_rows=s["table"].shape[0],
+            D=s["table"].shape[1], out_col=c, pooling=s.get("pooling", "sum"), index_kind=s.get("index_kind", "direct"),
+            hash_seed=s.get("seed", 0), id_weight=None if s.get("id_weight") is None else s["id_weight"].to(dev),
+            state0=None if st[0] is None else st[0].to(dev), state1=None if st[1] is None else st[1].to(dev),
+            bag_scale=None if s.get("bag_scale") is None else s["bag_scale"].to(dev)))
+    g = grad_out.to(dev).contiguous()
+    call = ops.make_group(feats, B, g, g.shape[1])
+    ws = torch.empty(ops.emb_bwd_workspace_bytes(call) + 256, dtype=torch.uint8, device=dev)
+    ops.emb_bwd_plan(call, ws)
+    S = sum(s["ids"].numel() for s in specs_cpu)
+    dmax = max(s["table"].shape[1] for s in specs_cpu)
+    uf = torch.full((S,), -1, dtype=torch.int32, device=dev)
+    ur = torch.full((S,), -1, dtype=torch.int32, device=dev)
+    rg = torch.zeros(S, dmax, device=dev)
+    nu = torch.zeros(1, dtype=torch.int64, device=dev)
+    ops.emb_bwd_apply(call, ws, ops.make_opt(opt_kind, **(opt_kw or {})), uf, ur, rg, nu)
+    torch.cuda.synchronize()
+    U = int(nu.item())
+    return feats, uf[:U].cpu(), ur[:U].cpu(), rg[:U].cpu(), U
+
+
+@pytest.mark.parametrize("B,hot", [(257, 0), (5000, 3), (20000, 1)])
+def test_backward_unique_rows_and_grads_match_oracle(B, hot):
+    from oracle import embedding as oe
+    gen = torch.Generator().manual_seed(B)
+    dims, Ls = [16, 16, 9, 1], [1, 12, 3, 1]
+    specs, col = [], 0
+    for D, L in zip(dims, Ls):
+        V = 40 + 3 * D
+        specs.append(dict(ids=make_ids(gen, B, L, V, hot=hot), table=torch.randn(V, D, generator=gen)))
+        col += D
+    gout = torch.randn(B, (col + 3) // 4 * 4, generator=gen)
+    feats, uf, ur, rg, U = run_bwd(specs, B, gout)
+    c = 0
+    total = 0
+    for i, s in enumerate(specs):
+        D = s["table"].shape[1]
+        rows, grads = oe.unique_row_grads(s["ids"], gout[:, c:c + D], s["table"].shape[0])
+        sel = uf == i
+        assert torch.equal(ur[sel].long(), rows)            # dedup is bit-exact, sorted
+        close(rg[sel][:, :D], grads)
+        total += rows.numel()
+        c += D
+    assert U == total
+
+
+def test_backward_mean_and_weights():
+    from oracle import embedding as oe
+    gen = torch.Generator().manual_seed(99)
+    B, L, V, D = 700, 9, 60, 16
+    ids = make_ids(gen, B, L, V)
+    w = torch.rand(B, L, generator=gen)
+    table = torch.randn(V, D, generator=gen)
+    gout = torch.randn(B, D, generator=gen)
+    scale = oe.bag_scale(ids, "mean")
+    feats, uf, ur, rg, U = run_bwd([dict(ids=ids, table=table, pooling="mean", id_weight=w, bag_scale=scale)], B, gout)
+    rows, grads = oe.unique_row_grads(ids, gout, V, "mean", per_id_weight=w)
+    assert torch.equal(ur.long(), rows)
+    close(rg, grads)
+
+
+def test_optimizers_match_torch_golden(golden_dir):
+    """Three steps of torch.optim.{Adagrad, SparseAdam, SGD} recorded from real torch (optim_golden.pt)."""
+    g = torch.load(os.path.join(golden_dir, "optim_golden.pt"))
+    V, D = g["w0"].shape
+    for kind, key, kw in (("adagrad", "adagrad", dict(lr=0.1, eps=1e-10)),
+                          ("adam", "sparse_adam", dict(lr=0.01, eps=1e-8, betas=(0.9, 0.999))),
+                          ("sgd", "sgd", dict(lr=0.1))):
+        w = g["w0"].clone().cuda()
+        s0 = torch.zeros(V, D, device="cuda")
+        s1 = torch.zeros(V, D, device="cuda")
+        for step, (ids, gout) in enumerate(g["steps"], start=1):
+            spec = dict(ids=ids, table=w)
+            feats, *_ = run_bwd([spec], ids.shape[0], gout, kind, dict(kw, step=step), states=[(s0, s1)])
+            w, s0, s1 = feats[0].table, feats[0].state0, feats[0].state1
+        close(w, g[key]["w"])
+        if kind == "adagrad":
+            close(s0, g[key]["sum"])
+        if kind == "adam":
+            close(s0, g[key]["exp_avg"])
+            close(s1, g[key]["exp_avg_sq"])
+
+
+def test_rowwise_adagrad_matches_oracle():
+    from oracle import embedding as oe
+    from oracle import optim as oo
+    gen = torch.Generator().manual_seed(4)
+    B, L, V, D = 3000, 4, 50, 16
+    ids = make_ids(gen, B, L, V, hot=2)
+    table = torch.randn(V, D, generator=gen)
+    gout = torch.randn(B, D, generator=gen)
+    st = torch.rand(V, generator=gen)
+    feats, *_ = run_bwd([dict(ids=ids, table=table)], B, gout, "rowwise_adagrad", dict(lr=0.05, eps=1e-10),
+                        states=[(st.clone(), None)])
+    rows, grads = oe.unique_row_grads(ids, gout, V)
+    w_ref, s_ref = table.clone(), st.clone()
+    oo.rowwise_adagrad_rows(w_ref, s_ref, rows, grads, 0.05, 1e-10)
+    close(feats[0].table, w_ref)
+    close(feats[0].state0, s_ref)
+
+
+def test_full_size_sgd_equals_index_add():
+    """Config-2 size (26 x 65536 ids, Zipf-like): fused SGD == table - lr * index_add(grad) on the GPU."""
+    gen = torch.Generator().manual_seed(2)
+    B, F, D = 65536, 26, 16
+    specs = []
+    for f in range(F):
+        V = [1000, 50000, 2_000_000][f % 3]
+        u = torch.rand(B, 1, generator=gen)
+        ids = (V ** u - 1).long().clamp(0, V - 1)             # log-uniform: hot head, long tail
+        specs.append(dict(ids=ids, table=torch.randn(V, D, generator=gen)))
+    gout = torch.randn(B, F * D, generator=gen)
+    feats, uf, ur, rg, U = run_bwd(specs, B, gout, "sgd", dict(lr=0.5))
+    g = gout.cuda()
+    nuniq = 0
+    for f, (s, ft) in enumerate(zip(specs, feats)):
+        ref = s["table"].cuda().index_add(0, s["ids"].cuda()[:, 0], g[:, f * D:(f + 1) * D], alpha=-0.5)
+        close(ft.table, ref, rtol=2e-5)                       # atomics in index_add: order differs
+        nuniq += int(torch.unique(s["ids"]).numel())
+    assert U == nuniq

@@ -1,0 +1,259 @@
+"""GPU parity tests at module level: DNN against the golden fixtures recorded from the real
+reference (tests/golden/dnn_golden.pt), DeepFM / DCN-v2 / FM against the oracle definitions,
+DynamicEmbedding against dynamic_golden.pt, the device vocabulary against oracle.vocab.
+
+Embedding-path tolerances are the north_star's 1e-5 (see test_gpu_lookup.py); quantities that
+pass through the fp32 cuBLAS tower GEMMs are compared at 1e-4 (GPU vs CPU GEMM summation order).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOWER_RTOL = 1e-4
+
+
+def close(got, ref, rtol):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    scale = max(float(ref.abs().max()), 1e-30)
+    err = float((got - ref).abs().max())
+    assert err <= rtol * scale, f"max abs err {err:.3e} > {rtol} * {scale:.3e}"
+
+
+def no_dropout(model):
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    return model
+
+
+@pytest.fixture(autouse=True)
+def _fp32_matmul():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def test_dnn_matches_reference_golden(golden_dir):
+    from torchctr_b200.models import DNN
+    g = torch.load(os.path.join(golden_dir, "dnn_golden.pt"))
+    model = no_dropout(DNN(g["feat_configs"], g["hidden_units"])).cuda()
+    model.load_state_dict(g["init_state"])                   # reference checkpoint loads unchanged
+    model.eval()
+    with torch.no_grad():
+        close(model(g["feats"]), g["eval_logits"], TOWER_RTOL)
+    # one Adagrad step: dense params through torch.optim, tables through the fused update
+    model.train()
+    opt = torch.optim.Adagrad(model.parameters(), lr=g["adagrad_lr"])
+    model.bind_optimizer(opt)
+    opt.zero_grad()
+    loss = model.training_step((g["feats"], g["labels"]), 0)
+    close(loss, g["train_loss"], TOWER_RTOL)
+    loss.backward()
+    for name, p in model.named_parameters():
+        if name.startswith("tower"):
+            close(p.grad, g["grads"][name], 5e-4)
+        else:
+            assert p.grad is None                            # no dense [V, D] gradient exists
+    opt.step()
+    after = model.state_dict()
+    for k, ref in g["after_adagrad_step"].items():
+        close(after[k], ref, 5e-4 if k.startswith("tower") else 2e-4)
+
+
+def test_dnn_sparse_grads_without_binding(golden_dir):
+    """No optimizer bound: backward hands autograd sparse gradients equal to the reference's dense ones."""
+    from torchctr_b200.models import DNN
+    g = torch.load(os.path.join(golden_dir, "dnn_golden.pt"))
+    model = no_dropout(DNN(g["feat_configs"], g["hidden_units"])).cuda()
+    model.load_state_dict(g["init_state"])
+    model.train()
+    model.training_step((g["feats"], g["labels"]), 0).backward()
+    for name, p in model.named_parameters():
+        if name.startswith("embeddings"):
+            assert p.grad.is_sparse
+            close(p.grad.to_dense(), g["grads"][name], 2e-4)
+
+
+def test_trainer_loop_trace_matches_reference(golden_dir):
+    """Six steps of the reference Trainer.fit (Adagrad) recorded in the fixture; here the same loop
+    (zero_grad / training_step / backward / step, trainer.py:291-303) over our model."""
+    from torchctr_b200.models import DNN
+    g = torch.load(os.path.join(golden_dir, "dnn_golden.pt"))
+    model = no_dropout(DNN(g["feat_configs"], g["hidden_units"])).cuda()
+    model.load_state_dict(g["init_state"])
+    opt = torch.optim.Adagrad(model.parameters(), lr=0.05)
+    model.bind_optimizer(opt)
+    model.train()
+    trace = []
+    for k, batch in enumerate(g["trainer_batches"]):
+        opt.zero_grad()
+        loss = model.training_step(batch, k)
+        trace.append(loss.item())
+        loss.backward()
+        opt.step()
+    close(torch.tensor(trace), g["trainer_loss_trace"], 2e-4)
+    final = model.state_dict()
+    for k, ref in g["trainer_final_state"].items():
+        if k.startswith("embeddings"):
+            close(final[k], ref, 1e-3)
+
+
+def _criteo_like(gen, B, F, V, D, nd):
+    fc = [{"name": f"c{i}", "type": "sparse", "num_embeddings": V + i, "emb_dim": D} for i in range(F)]
+    fc += [{"name": f"d{i}", "type": "dense"} for i in range(nd)]
+    feats = {f"c{i}": torch.randint(0, V + i, (B, 1), generator=gen) for i in range(F)}
+    feats["dense_features"] = torch.randn(B, nd, generator=gen)
+    labels = (torch.rand(B, 1, generator=gen) < 0.25).float()
+    return fc, feats, labels
+
+
+@pytest.mark.parametrize("which", ["deepfm", "dcnv2"])
+def test_deepfm_dcn_match_oracle(which):
+    from oracle import models as om
+    from torchctr_b200.models import DCNv2, DeepFM
+    gen = torch.Generator().manual_seed(8)
+    D = 16 if which == "deepfm" else 32
+    fc, feats, labels = _criteo_like(gen, 512, 6, 40, D, 3)
+    torch.manual_seed(0)
+    ref = no_dropout(om.OracleDeepFM(fc, [32, 16]) if which == "deepfm" else om.OracleDCNv2(fc, [32, 16], 3))
+    ours = no_dropout(DeepFM(fc, [32, 16]) if which == "deepfm" else DCNv2(fc, [32, 16], 3)).cuda()
+    ours.load_state_dict(ref.state_dict())
+    ref.train(); ours.train()
+    lr = 0.1
+    opt_ref = torch.optim.SGD(ref.parameters(), lr=lr)
+    opt = torch.optim.SGD(ours.parameters(), lr=lr)
+    ours.bind_optimizer(opt)
+    for step in range(2):
+        opt_ref.zero_grad(); opt.zero_grad()
+        l_ref = ref.training_step((feats, labels), step)
+        l = ours.training_step((feats, labels), step)
+        close(l, l_ref, TOWER_RTOL)
+        l_ref.backward(); l.backward()
+        opt_ref.step(); opt.step()
+    sd, sd_ref = ours.state_dict(), ref.state_dict()
+    for k in sd_ref:
+        close(sd[k], sd_ref[k], 5e-4)
+
+
+def test_fm_kernels_match_autograd():
+    from oracle.models import fm_second_order
+    from torchctr_b200.nn import fm_interaction
+    gen = torch.Generator().manual_seed(1)
+    for F, D, stride, nfirst in ((26, 16, 432, 26), (5, 9, 48, 0), (3, 32, 96, 3), (7, 4, 28, 7)):
+        B = 777
+        x = torch.zeros(B, stride)
+        x[:, :F * D] = torch.randn(B, F * D, generator=gen)
+        first = torch.randn(B, (nfirst + 3) // 4 * 4, generator=gen) if nfirst else None
+        xr = x.clone().requires_grad_(True)
+        fr = first.clone().requires_grad_(True) if nfirst else None
+        ref = fm_second_order(xr[:, :F * D].reshape(B, F, D))
+        if nfirst:
+            ref = ref + fr[:, :nfirst].sum(1, keepdim=True)
+        gout = torch.randn(B, 1, generator=gen)
+        ref.backward(gout)
+        xg = x.cuda().requires_grad_(True)
+        fg = first.cuda().requires_grad_(True) if nfirst else None
+        out = fm_interaction(xg, F, D, fg, nfirst)
+        out.backward(gout.cuda())
+        close(out, ref, 1e-5)
+        close(xg.grad, xr.grad, 1e-5)
+        if nfirst:
+            close(fg.grad, fr.grad, 1e-5)
+
+
+def test_dynamic_embedding_matches_reference_golden(golden_dir):
+    from torchctr_b200.nn import DynamicEmbedding
+    g = torch.load(os.path.join(golden_dir, "dynamic_golden.pt"))
+
+    class Two(torch.nn.Module):
+        def __init__(self, n1, n2):
+            super().__init__()
+            self.emb1 = DynamicEmbedding(n1, 5)
+            self.emb2 = DynamicEmbedding(n2, 5)
+
+    m = Two(5, 6).cuda()
+    with torch.no_grad():
+        m.emb1.weight.copy_(g["w_before"])
+    out = m.emb1(g["ids"].cuda())
+    assert tuple(m.emb1.weight.shape) == tuple(g["w_after"].shape) == (10, 5)      # grew to max id + 1
+    assert tuple(m.emb2.weight.shape) == (6, 5)
+    assert torch.equal(m.emb1.weight[:5].cpu(), g["w_before"])                    # old rows untouched
+    new = m.emb1.weight[5:].detach().cpu()
+    assert float(new.abs().max()) < 0.08 and float(new.std()) > 0.002               # ~ N(0, 0.01)
+    assert torch.equal(out.detach().cpu(), m.emb1.weight.detach().cpu()[g["ids"]])
+    assert out.shape == g["out"].shape
+    # state-dict merge: a smaller table grows to the checkpoint, a larger one keeps its tail rows
+    bigger = Two(8, 15).cuda()
+    tail = bigger.emb2.weight.detach()[6:].clone().cpu()
+    bigger.load_state_dict({k: v.clone() for k, v in g["state_dict"].items()})
+    assert tuple(bigger.emb1.weight.shape) == tuple(g["loaded_emb1"].shape)
+    assert tuple(bigger.emb2.weight.shape) == tuple(g["loaded_emb2"].shape)
+    assert torch.equal(bigger.emb1.weight.detach().cpu(), g["state_dict"]["emb1.weight"])
+    assert torch.equal(bigger.emb2.weight.detach().cpu()[:6], g["state_dict"]["emb2.weight"])
+    assert torch.equal(bigger.emb2.weight.detach().cpu()[6:], tail)
+    for name, bad in (("empty", torch.zeros(0, dtype=torch.long)), ("negative", torch.tensor([[1, -1]]))):
+        with pytest.raises(ValueError) as e:
+            m.emb1(bad.cuda())
+        assert str(e.value) == g["errors"][name]
+    # gradient flows through the gather as a sparse update
+    m.emb1(torch.tensor([[1, 1, 3]]).cuda()).sum().backward()
+    dense = m.emb1.weight.grad.to_dense().cpu()
+    assert torch.equal(dense[1], torch.full((5,), 2.0)) and torch.equal(dense[3], torch.ones(5)) and float(dense[0].abs().sum()) == 0
+
+
+def test_vocab_fit_transform_match_oracle():
+    from oracle.vocab import Vocab
+    from torchctr_b200.nn import VocabIndex
+    rng = np.random.default_rng(5)
+    for min_freq in (0, 2):
+        ref = Vocab(min_freq=min_freq)
+        dev = VocabIndex(capacity=256, min_freq=min_freq).cuda()      # small: forces a rebuild
+        for step in range(5):
+            keys = rng.zipf(1.3, size=(400, 5)).astype(np.int64) * 7919 + step
+            keys[rng.random(keys.shape) < 0.2] = -100
+            flat = keys[keys >= 0]
+            n_ref = ref.fit(flat)
+            dev.fit(torch.from_numpy(keys))
+            assert dev.num_embeddings() == n_ref
+            probe = np.concatenate([flat[:500], rng.integers(0, 10 ** 9, 100)])
+            got = dev.transform(torch.from_numpy(probe)).cpu().numpy()
+            assert (got == ref.transform(probe)).all()                # bit-exact rows, incl. first-occurrence order
+
+
+def test_model_with_growing_vocab_and_hashed_feature():
+    """raw ids end to end: a hashed feature and a vocabulary feature that grows while training."""
+    from oracle import embedding as oe
+    from oracle import hashing as oh
+    from oracle.vocab import Vocab
+    from torchctr_b200.models import DNN
+    fc = [{"name": "h", "type": "sparse", "num_embeddings": 101, "emb_dim": 16, "raw_ids": True, "hash_buckets": 101, "seed": 3},
+          {"name": "v", "type": "sparse", "num_embeddings": 1, "emb_dim": 16, "raw_ids": True, "islist": True},
+          {"name": "x", "type": "dense"}]
+    torch.manual_seed(0)
+    model = no_dropout(DNN(fc, [16])).cuda().train()
+    gen = torch.Generator().manual_seed(3)
+    ref_vocab = Vocab()
+    for step in range(3):
+        feats = {"h": torch.randint(0, 2 ** 33, (64, 1), generator=gen),
+                 "v": torch.randint(1000 * step, 1000 * step + 300, (64, 7), generator=gen),
+                 "dense_features": torch.randn(64, 1, generator=gen)}
+        feats["v"][torch.rand(64, 7, generator=gen) < 0.3] = -100
+        logits = model(feats)
+        n = ref_vocab.fit(feats["v"][feats["v"] >= 0].numpy())
+        assert model.embeddings["v"].num_embeddings == n == model.embeddings["v"].weight.shape[0]
+        # recompute the tower input on the CPU from the oracle's rows
+        hrows = torch.from_numpy(oh.hash_bucket_ids(feats["h"].numpy(), 101, 3)).long()
+        vrows = torch.from_numpy(ref_vocab.transform(feats["v"].numpy())).long()
+        vrows[feats["v"] < 0] = -100
+        x = torch.cat([oe.pooled_lookup(hrows, model.embeddings["h"].weight.detach().cpu()),
+                       oe.pooled_lookup(vrows, model.embeddings["v"].weight.detach().cpu()), feats["dense_features"]], 1)
+        with torch.no_grad():
+            ref_logits = torch.nn.functional.linear(x.cuda(), model.tower[0].weight, model.tower[0].bias)
+            got_first = model._first_linear(model._lookup(feats, feats["dense_features"], False), model.tower[0])
+        close(got_first, ref_logits, TOWER_RTOL)
+        logits.sum().backward()

@@ -59,6 +59,7 @@ _SIGNATURES = {
     # name: (restype, argtypes)
     "ctr_last_error_string": (C.c_char_p, []),
     "ctr_abi_version": (C.c_int, []),
+    "ctr_kernel_launches": (C.c_int64, []),
     "ctr_emb_pool_fwd": (C.c_int, [C.POINTER(Group), _P]),
     "ctr_hash_bucket_i64": (C.c_int, [_P, C.c_int64, C.c_uint32, C.c_uint32, _P, _P]),
     "ctr_rows_gather": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P, _P]),
@@ -70,6 +71,7 @@ _SIGNATURES = {
     "ctr_vocab_fit_workspace_bytes": (C.c_int64, [C.c_int64]),
     "ctr_vocab_fit": (C.c_int, [C.POINTER(VocabMap), _P, C.c_int64, C.c_int32, _P, _P, _P, _P, C.c_int64, _P]),
     "ctr_vocab_transform": (C.c_int, [C.POINTER(VocabMap), _P, C.c_int64, C.c_int32, _P, _P]),
+    "ctr_vocab_insert": (C.c_int, [C.POINTER(VocabMap), _P, _P, C.c_int64, _P, _P]),
     "ctr_vocab_clear": (C.c_int, [C.POINTER(VocabMap), _P]),
     "ctr_fm_fwd": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int64, _P,
                              C.c_int64, C.c_int32, _P]),

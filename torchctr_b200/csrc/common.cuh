@@ -14,6 +14,7 @@ constexpr int kNumSMs = 148;  // B200
 
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
+void note_launch();
 
 #define CTR_CUDA_OK(expr)                                     \
     do {                                                      \

@@ -343,7 +343,7 @@ extern "C" int ctr_emb_bwd_plan(const ctr_group_t *group, void *workspace, int64
     uint32_t *counters = reinterpret_cast<uint32_t *>(ws + p.counters);
     uint32_t *keys_a = reinterpret_cast<uint32_t *>(ws + p.keys_a), *keys_b = reinterpret_cast<uint32_t *>(ws + p.keys_b);
     uint32_t *vals_a = reinterpret_cast<uint32_t *>(ws + p.vals_a), *vals_b = reinterpret_cast<uint32_t *>(ws + p.vals_b);
-    reset_counters_kernel<<<1, 32, 0, stream>>>(counters);
+    note_launch(), reset_counters_kernel<<<1, 32, 0, stream>>>(counters);
     if (p.S > 0) {
         int64_t max_slots = 0;
         for (int i = 0; i < dg.num_features; ++i) {
@@ -353,7 +353,7 @@ extern "C" int ctr_emb_bwd_plan(const ctr_group_t *group, void *workspace, int64
         int64_t bx = (max_slots + 1023) / 1024;  // 4 slots per thread
         if (bx > kNumSMs * 8) bx = kNumSMs * 8;
         if (bx < 1) bx = 1;
-        emb_keygen_kernel<<<dim3((unsigned)bx, dg.num_features), 256, 0, stream>>>(dg, keys_a, vals_a);
+        note_launch(), emb_keygen_kernel<<<dim3((unsigned)bx, dg.num_features), 256, 0, stream>>>(dg, keys_a, vals_a);
         CTR_CUDA_OK(cudaGetLastError());
     }
     rc = radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, p.S, p.key_bits, reinterpret_cast<uint32_t *>(ws + p.counts),
@@ -432,8 +432,8 @@ extern "C" int ctr_emb_bwd_apply(const ctr_group_t *group, void *workspace, cons
     const int64_t cap = (int64_t)kNumSMs * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    emb_bwd_apply_kernel<<<(unsigned)blocks, kApplyThreads, 0, stream>>>(dg, a);
-    emb_bwd_apply_long_kernel<<<kNumSMs * 4, kApplyThreads, 0, stream>>>(dg, a);
+    note_launch(), emb_bwd_apply_kernel<<<(unsigned)blocks, kApplyThreads, 0, stream>>>(dg, a);
+    note_launch(), emb_bwd_apply_long_kernel<<<kNumSMs * 4, kApplyThreads, 0, stream>>>(dg, a);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }

@@ -284,7 +284,7 @@ extern "C" int ctr_emb_pool_fwd(const ctr_group_t *group, void *stream) {
     // enough blocks for every feature row of the grid to fill the machine a few times over
     const int cap = kNumSMs * 8;
     dim3 grid(grid_for(max_warps, kFwdWarps, cap), dg.num_features + (extra_w > 0 ? 1 : 0));
-    emb_pool_fwd_kernel<<<grid, kFwdThreads, 0, (cudaStream_t)stream>>>(dg);
+    note_launch(), emb_pool_fwd_kernel<<<grid, kFwdThreads, 0, (cudaStream_t)stream>>>(dg);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }
@@ -294,7 +294,7 @@ extern "C" int ctr_hash_bucket_i64(const int64_t *ids, int64_t n, uint32_t bucke
     CTR_REQUIRE(n >= 0 && buckets > 0, "n=%lld buckets=%u", (long long)n, buckets);
     if (n == 0) return CTR_OK;
     CTR_REQUIRE(ids != nullptr && out != nullptr, "null pointer");
-    hash_bucket_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(ids, n, buckets, seed, out);
+    note_launch(), hash_bucket_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(ids, n, buckets, seed, out);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }
@@ -305,7 +305,7 @@ extern "C" int ctr_rows_gather(const int64_t *ids, int64_t n, const float *table
     if (n == 0) return CTR_OK;
     CTR_REQUIRE(ids != nullptr && table != nullptr && out != nullptr, "null pointer");
     const int pieces = (D % 4 == 0) ? D / 4 : D;
-    rows_gather_kernel<<<grid_for(n * pieces, 256, kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(ids, n, table, num_rows,
+    note_launch(), rows_gather_kernel<<<grid_for(n * pieces, 256, kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(ids, n, table, num_rows,
                                                                                               D, out, status);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
@@ -316,7 +316,7 @@ extern "C" int ctr_normal_fill_rows(float *table, int64_t row0, int64_t n, int32
     CTR_REQUIRE(n >= 0 && D >= 1 && row0 >= 0, "bad sizes");
     if (n == 0) return CTR_OK;
     CTR_REQUIRE(table != nullptr, "null pointer");
-    normal_fill_rows_kernel<<<grid_for(n * D, 256, kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(table, row0, n, D, mean,
+    note_launch(), normal_fill_rows_kernel<<<grid_for(n * D, 256, kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(table, row0, n, D, mean,
                                                                                               stdv, seed);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
@@ -324,10 +324,10 @@ extern "C" int ctr_normal_fill_rows(float *table, int64_t row0, int64_t n, int32
 
 extern "C" int ctr_ids_minmax(const int64_t *ids, int64_t n, int64_t *out, void *stream) {
     CTR_REQUIRE(n >= 0 && out != nullptr, "bad args");
-    minmax_init_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(out);
+    note_launch(), minmax_init_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(out);
     if (n > 0) {
         CTR_REQUIRE(ids != nullptr, "null ids");
-        ids_minmax_kernel<<<grid_for(n, 256, kNumSMs * 4), 256, 0, (cudaStream_t)stream>>>(ids, n, out);
+        note_launch(), ids_minmax_kernel<<<grid_for(n, 256, kNumSMs * 4), 256, 0, (cudaStream_t)stream>>>(ids, n, out);
     }
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;

@@ -173,7 +173,7 @@ extern "C" int ctr_fm_fwd(const float *x, int64_t x_stride, int32_t B, int32_t F
     const int teams_per_block = 256 / a.G;
     int64_t blocks = ((int64_t)B + teams_per_block - 1) / teams_per_block;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    fm_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    note_launch(), fm_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }
@@ -193,7 +193,7 @@ extern "C" int ctr_fm_bwd(const float *x, int64_t x_stride, int32_t B, int32_t F
     const int teams_per_block = 256 / a.G;
     int64_t blocks = ((int64_t)B + teams_per_block - 1) / teams_per_block;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    fm_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    note_launch(), fm_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }
@@ -203,7 +203,7 @@ extern "C" int ctr_cross_combine_fwd(const float *x0, const float *x, const floa
     CTR_REQUIRE(B >= 0 && d >= 1 && stride >= d, "bad cross shape");
     if (B == 0) return CTR_OK;
     CTR_REQUIRE(x0 && x && u && bias && y, "null pointer");
-    cross_combine_fwd_kernel<<<ew_grid((int64_t)B * d), 256, 0, (cudaStream_t)stream>>>(x0, x, u, bias, B, d, stride, y);
+    note_launch(), cross_combine_fwd_kernel<<<ew_grid((int64_t)B * d), 256, 0, (cudaStream_t)stream>>>(x0, x, u, bias, B, d, stride, y);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }
@@ -214,7 +214,7 @@ extern "C" int ctr_cross_combine_bwd(const float *x0, const float *u, const floa
     CTR_REQUIRE(B >= 0 && d >= 1 && stride >= d, "bad cross shape");
     if (B == 0) return CTR_OK;
     CTR_REQUIRE(x0 && u && bias && gy && gu && gx0, "null pointer");
-    cross_combine_bwd_kernel<<<ew_grid((int64_t)B * d), 256, 0, (cudaStream_t)stream>>>(x0, u, bias, gy, B, d, stride, gu,
+    note_launch(), cross_combine_bwd_kernel<<<ew_grid((int64_t)B * d), 256, 0, (cudaStream_t)stream>>>(x0, u, bias, gy, B, d, stride, gu,
                                                                                      gx0, accumulate_gx0);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;

@@ -1,5 +1,6 @@
 // Error reporting and argument lowering shared by every entry point of libctr_b200.
 #include <stdarg.h>
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -104,3 +105,10 @@ int lower_group(const ctr_group_t *g, DevGroup *out, bool need_tables, bool need
 
 extern "C" const char *ctr_last_error_string(void) { return ctr::g_err; }
 extern "C" int ctr_abi_version(void) { return CTR_B200_ABI_VERSION; }
+
+// every kernel launch of the library passes through note_launch(): bench.py reports the count
+namespace ctr {
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace ctr
+extern "C" int64_t ctr_kernel_launches(void) { return (int64_t)ctr::g_launches.load(); }

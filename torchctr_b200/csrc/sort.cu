@@ -123,9 +123,9 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(In in, int64_t m, const
 template <class In, class Out>
 static int device_scan(In in, Out out, int64_t m, uint32_t *spine, cudaStream_t stream) {
     const int64_t nblk = scan_num_blocks(m);
-    scan_reduce_kernel<In><<<(unsigned)nblk, 256, 0, stream>>>(in, m, spine);
-    scan_spine_kernel<<<1, 256, 0, stream>>>(spine, nblk);
-    scan_apply_kernel<In, Out><<<(unsigned)nblk, 256, 0, stream>>>(in, m, spine, nblk, out);
+    note_launch(), scan_reduce_kernel<In><<<(unsigned)nblk, 256, 0, stream>>>(in, m, spine);
+    note_launch(), scan_spine_kernel<<<1, 256, 0, stream>>>(spine, nblk);
+    note_launch(), scan_apply_kernel<In, Out><<<(unsigned)nblk, 256, 0, stream>>>(in, m, spine, nblk, out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "device_scan");
     return CTR_OK;
@@ -150,7 +150,7 @@ __global__ void empty_runs_kernel(uint32_t *run_start, uint32_t *counters) {
 int find_runs(const uint32_t *sorted_keys, int64_t n, uint32_t *run_start, uint32_t *counters, uint32_t *spine,
               cudaStream_t stream) {
     if (n <= 0) {
-        empty_runs_kernel<<<1, 1, 0, stream>>>(run_start, counters);
+        note_launch(), empty_runs_kernel<<<1, 1, 0, stream>>>(run_start, counters);
         cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? CTR_OK : cuda_fail(e, "empty_runs_kernel");
     }
@@ -247,10 +247,10 @@ int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint3
     uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
     for (int p = 0; p < passes; ++p) {
         const int shift = p * kRadixBits;
-        radix_hist_kernel<<<(unsigned)ntiles, kSortThreads, 0, stream>>>(kin, n, shift, counts, ntiles);
+        note_launch(), radix_hist_kernel<<<(unsigned)ntiles, kSortThreads, 0, stream>>>(kin, n, shift, counts, ntiles);
         int rc = exclusive_scan_u32(counts, (int64_t)kRadix * ntiles, spine, stream);
         if (rc != CTR_OK) return rc;
-        radix_scatter_kernel<<<(unsigned)ntiles, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, counts, ntiles);
+        note_launch(), radix_scatter_kernel<<<(unsigned)ntiles, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, counts, ntiles);
         uint32_t *t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }

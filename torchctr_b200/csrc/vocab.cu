@@ -126,6 +126,28 @@ __global__ void vocab_transform_kernel(const int64_t *__restrict__ keys, int64_t
     }
 }
 
+// insert distinct (key, row) pairs that are not in the map yet (rebuild after a capacity change)
+__global__ void vocab_insert_kernel(const int64_t *__restrict__ keys, const int32_t *__restrict__ rows, int64_t n,
+                                    long long *mkeys, int32_t *mrows, int64_t mmask, uint32_t *status) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const long long key = keys[p];
+        if (key < 0) continue;
+        uint64_t slot = mix64((uint64_t)key) & (uint64_t)mmask;
+        bool placed = false;
+        for (int64_t probe = 0; probe <= mmask; ++probe) {
+            if (mkeys[slot] == CTR_VOCAB_EMPTY &&
+                atomicCAS(reinterpret_cast<unsigned long long *>(mkeys + slot), (unsigned long long)CTR_VOCAB_EMPTY,
+                          (unsigned long long)key) == (unsigned long long)CTR_VOCAB_EMPTY) {
+                mrows[slot] = rows[p];
+                placed = true;
+                break;
+            }
+            slot = (slot + 1) & (uint64_t)mmask;
+        }
+        if (!placed && status != nullptr) atomicOr(status, CTR_STATUS_MAP_FULL);
+    }
+}
+
 __global__ void vocab_clear_kernel(long long *mkeys, int32_t *mrows, int64_t cap) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
         mkeys[i] = CTR_VOCAB_EMPTY;
@@ -171,16 +193,16 @@ extern "C" int ctr_vocab_fit(const ctr_vocab_map_t *map, const int64_t *keys, in
     uint32_t *scount = reinterpret_cast<uint32_t *>(ws + l.scount), *sfirst = reinterpret_cast<uint32_t *>(ws + l.sfirst);
     uint32_t *pslot = reinterpret_cast<uint32_t *>(ws + l.pslot), *flag = reinterpret_cast<uint32_t *>(ws + l.flag);
     uint32_t *rank = reinterpret_cast<uint32_t *>(ws + l.rank), *spine = reinterpret_cast<uint32_t *>(ws + l.spine);
-    fit_init_kernel<<<grid1d(l.cap), 256, 0, stream>>>(skeys, scount, sfirst, l.cap);
-    fit_count_kernel<<<grid1d(n), 256, 0, stream>>>(keys, n, skeys, scount, sfirst, l.cap - 1, pslot);
-    fit_flag_kernel<<<grid1d(n), 256, 0, stream>>>(keys, n, scount, sfirst, pslot, map->keys, map->rows, map->capacity - 1,
+    note_launch(), fit_init_kernel<<<grid1d(l.cap), 256, 0, stream>>>(skeys, scount, sfirst, l.cap);
+    note_launch(), fit_count_kernel<<<grid1d(n), 256, 0, stream>>>(keys, n, skeys, scount, sfirst, l.cap - 1, pslot);
+    note_launch(), fit_flag_kernel<<<grid1d(n), 256, 0, stream>>>(keys, n, scount, sfirst, pslot, map->keys, map->rows, map->capacity - 1,
                                                   min_freq, reinterpret_cast<long long *>(counts), flag);
     rc = exclusive_scan_u32_to(flag, rank, n, spine, stream);
     if (rc != CTR_OK) return rc;
-    fit_insert_kernel<<<grid1d(n), 256, 0, stream>>>(keys, n, flag, rank, scount, pslot,
+    note_launch(), fit_insert_kernel<<<grid1d(n), 256, 0, stream>>>(keys, n, flag, rank, scount, pslot,
                                                     reinterpret_cast<long long *>(map->keys), map->rows, map->capacity - 1,
                                                     next_row, reinterpret_cast<long long *>(counts), status);
-    fit_advance_kernel<<<1, 1, 0, stream>>>(next_row, spine + scan_num_blocks(n));
+    note_launch(), fit_advance_kernel<<<1, 1, 0, stream>>>(next_row, spine + scan_num_blocks(n));
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }
@@ -192,8 +214,21 @@ extern "C" int ctr_vocab_transform(const ctr_vocab_map_t *map, const int64_t *ke
     CTR_REQUIRE(n >= 0, "n is negative");
     if (n == 0) return CTR_OK;
     CTR_REQUIRE(keys != nullptr && rows != nullptr, "null pointer");
-    vocab_transform_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(keys, n, map->keys, map->rows, map->capacity - 1,
+    note_launch(), vocab_transform_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(keys, n, map->keys, map->rows, map->capacity - 1,
                                                                        oov_row, rows);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int ctr_vocab_insert(const ctr_vocab_map_t *map, const int64_t *keys, const int32_t *rows, int64_t n,
+                                uint32_t *status, void *stream) {
+    int rc = check_map(map);
+    if (rc != CTR_OK) return rc;
+    CTR_REQUIRE(n >= 0, "n is negative");
+    if (n == 0) return CTR_OK;
+    CTR_REQUIRE(keys != nullptr && rows != nullptr, "null pointer");
+    note_launch(), vocab_insert_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(keys, rows, n, reinterpret_cast<long long *>(map->keys),
+                                                                    map->rows, map->capacity - 1, status);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }
@@ -201,7 +236,7 @@ extern "C" int ctr_vocab_transform(const ctr_vocab_map_t *map, const int64_t *ke
 extern "C" int ctr_vocab_clear(const ctr_vocab_map_t *map, void *stream) {
     int rc = check_map(map);
     if (rc != CTR_OK) return rc;
-    vocab_clear_kernel<<<grid1d(map->capacity), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long *>(map->keys),
+    note_launch(), vocab_clear_kernel<<<grid1d(map->capacity), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long *>(map->keys),
                                                                                map->rows, map->capacity);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;

@@ -1,0 +1,134 @@
+"""Shared model plumbing: tables from ``feat_configs``, fused lookup, reference-shaped tower.
+
+Mirrors the construction rules of ``torchctr/models/dnn.py:10-46`` (same attribute names, same
+module order, hence the same ``state_dict`` keys) and its step protocol (``:72-82``).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..nn.embedding import EmbeddingTable, PooledLookupGroup
+from ..nn.vocab import VocabIndex
+
+
+def split_feature_configs(feat_configs):
+    """(sparse configs, dense input width) -- dnn.py:17-29 incl. its error messages."""
+    sparse, dense_width = [], 0
+    for cfg in feat_configs:
+        kind = cfg["type"]
+        if kind == "sparse":
+            if "emb_dim" not in cfg:
+                raise ValueError("emb_dim must be specified for sparse features.")
+            sparse.append(cfg)
+        elif kind == "dense" and cfg.get("islist"):
+            dense_width += 3      # dnn.py:24-25: 3 dense inputs per dense sequence feature
+        elif kind == "dense":
+            dense_width += 1
+        else:
+            raise ValueError(f'Unsupported feature type: {cfg["type"]}')
+    return sparse, dense_width
+
+
+def make_tower(input_dim: int, hidden_units, p_drop: float = 0.5) -> nn.Sequential:
+    """[Linear, BatchNorm1d, ReLU, Dropout(0.5)] * k + Linear(., 1) -- dnn.py:35-46."""
+    layers, width = [], input_dim
+    for h in hidden_units:
+        layers += [nn.Linear(width, h), nn.BatchNorm1d(h), nn.ReLU(), nn.Dropout(p=p_drop)]
+        width = h
+    layers.append(nn.Linear(width, 1))
+    return nn.Sequential(*layers)
+
+
+def table_from_config(cfg) -> EmbeddingTable:
+    """Table for one sparse feature.  ``raw_ids: True`` (extension) means the batch carries raw
+    category ids rather than rows: with ``hash_buckets`` the murmur3 bucket of
+    ``torchctr/transformer.py:487-490`` is computed inside the lookup, without it the ids go
+    through a device vocabulary that grows while training (``transformer.py:451-498``)."""
+    kind, vocab = "direct", None
+    if cfg.get("raw_ids"):
+        if cfg.get("hash_buckets"):
+            kind = "hash"
+        else:
+            kind = "vocab"
+            vocab = VocabIndex(capacity=cfg.get("vocab_capacity", 1 << 16), min_freq=cfg.get("min_freq", 0))
+    return EmbeddingTable(cfg["num_embeddings"], cfg["emb_dim"], pooling=cfg.get("pooling", "sum"), index_kind=kind,
+                          hash_seed=cfg.get("seed", 0), vocab=vocab, use_id_weight=bool(cfg.get("use_weight", False)))
+
+
+class CTRModelBase(nn.Module):
+    """Holds ``feat_configs``, ``embeddings`` (ModuleDict of tables keyed by feature name) and the
+    fused lookup; subclasses add the interaction and the tower."""
+
+    def __init__(self, feat_configs):
+        super().__init__()
+        self.feat_configs = feat_configs
+        self._sparse, self._dense_width = split_feature_configs(feat_configs)
+        self.embeddings = nn.ModuleDict({c["name"]: table_from_config(c) for c in self._sparse})
+        self._names = [c["name"] for c in self._sparse]
+        self._sparse_width = sum(c["emb_dim"] for c in self._sparse)
+        self._lookup = PooledLookupGroup(self._names, self.embeddings)
+        self._groups = [self._lookup]
+
+    # ---- optimizer / ids checks -------------------------------------------------------------
+    def bind_optimizer(self, optimizer, kind: str | None = None):
+        """Fuse the table update into backward, following ``optimizer``'s hyper-parameters (the
+        optimizer itself keeps stepping the dense parameters; tables get no ``.grad``)."""
+        for g in self._groups:
+            g.bind_optimizer(optimizer, kind)
+        return self
+
+    def table_parameters(self):
+        """Parameters updated by the fused sparse optimizer (every EmbeddingTable weight)."""
+        from ..nn.embedding import EmbeddingTable
+        return [m.weight for m in self.modules() if isinstance(m, EmbeddingTable)]
+
+    def dense_parameters(self):
+        """Everything else: hand these to the torch optimizer when the tables are fused, so that it
+        does not allocate dense state for the tables."""
+        skip = {id(p) for p in self.table_parameters()}
+        return [p for p in self.parameters() if id(p) not in skip]
+
+    @staticmethod
+    def dense_block(feats):
+        parts = []
+        if "dense_features" in feats:
+            parts.append(feats["dense_features"])
+        if "seq_dense_features" in feats:
+            parts += list(feats["seq_dense_features"])       # dnn.py:64-65
+        if not parts:
+            return None
+        return parts[0] if len(parts) == 1 else torch.cat([p.to(parts[0].device) for p in parts], dim=-1)
+
+    def _first_linear(self, x: torch.Tensor, layer: nn.Linear) -> torch.Tensor:
+        """Linear over the 4-float-padded lookup output: the weight is zero-padded instead of
+        slicing (and copying) the activations."""
+        pad = x.shape[1] - layer.in_features
+        w = F.pad(layer.weight, (0, pad)) if pad else layer.weight
+        return F.linear(x, w, layer.bias)
+
+    def _run_tower(self, x: torch.Tensor) -> torch.Tensor:
+        h = self._first_linear(x, self.tower[0])
+        for layer in list(self.tower)[1:]:
+            h = layer(h)
+        return h
+
+    def _grow_vocabularies(self, feats):
+        if not self.training:
+            return
+        for name in self._names:
+            table = self.embeddings[name]
+            if table.index_kind == "vocab":
+                table.vocab.fit_and_grow(feats[name], table)
+
+    # ---- step protocol: dnn.py:72-82 ----------------------------------------------------------
+    def training_step(self, batch, batch_idx):
+        features, labels = batch
+        logits = self(features)
+        return F.binary_cross_entropy_with_logits(logits, labels.to(logits.device, non_blocking=True))
+
+    def validation_step(self, batch, batch_idx):
+        features, labels = batch
+        logits = self(features)
+        return F.binary_cross_entropy_with_logits(logits, labels.to(logits.device, non_blocking=True))

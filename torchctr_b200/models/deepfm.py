@@ -1,0 +1,41 @@
+"""``DeepFM`` on the fused lookup.  Not in the reference; definition of SURVEY.md 8c /
+``oracle.models.OracleDeepFM``:
+    logit = sum_f w1_f[id] + Linear(dense) + FM2(v) + tower(concat(v, dense))."""
+from __future__ import annotations
+
+import torch.nn as nn
+
+from ..nn.embedding import EmbeddingTable, PooledLookupGroup
+from ..nn.interaction import fm_interaction
+from .base import CTRModelBase, make_tower
+
+
+class DeepFM(CTRModelBase):
+    def __init__(self, feat_configs, hidden_units=[256, 128, 64]):
+        super().__init__(feat_configs)
+        dims = {c["emb_dim"] for c in self._sparse}
+        if len(dims) != 1:
+            raise ValueError("DeepFM needs one common emb_dim for the FM term")
+        self._dim = dims.pop()
+        self.linear_embeddings = nn.ModuleDict()
+        for c in self._sparse:
+            src = self.embeddings[c["name"]]
+            self.linear_embeddings[c["name"]] = EmbeddingTable(
+                c["num_embeddings"], 1, pooling=src.pooling, index_kind=src.index_kind, hash_seed=src.hash_seed,
+                vocab=src.vocab, use_id_weight=src.use_id_weight)
+        self._linear_lookup = PooledLookupGroup(self._names, self.linear_embeddings)
+        self._groups.append(self._linear_lookup)
+        self.linear_dense = nn.Linear(self._dense_width, 1) if self._dense_width else None
+        self.tower = make_tower(self._sparse_width + self._dense_width, list(hidden_units))
+
+    def forward(self, input_feats):
+        self._grow_vocabularies(input_feats)
+        dense = self.dense_block(input_feats)
+        x = self._lookup(input_feats, dense, self.training)                  # [B, pad4(F*D + Nd)]
+        first = self._linear_lookup(input_feats, None, self.training)        # [B, pad4(F)]
+        nf = len(self._names)
+        logit = fm_interaction(x, nf, self._dim, first, nf) + self._run_tower(x)
+        if self.linear_dense is not None:
+            c0 = self._sparse_width
+            logit = logit + self.linear_dense(x[:, c0:c0 + self._dense_width])
+        return logit

@@ -1,0 +1,15 @@
+"""``DNN`` -- drop-in for ``torchctr.models.DNN`` (``torchctr/models/dnn.py:10-82``)."""
+from __future__ import annotations
+
+from .base import CTRModelBase, make_tower
+
+
+class DNN(CTRModelBase):
+    def __init__(self, feat_configs, hidden_units=[256, 128, 64]):
+        super().__init__(feat_configs)
+        self.tower = make_tower(self._sparse_width + self._dense_width, list(hidden_units))
+
+    def forward(self, input_feats):
+        self._grow_vocabularies(input_feats)
+        x = self._lookup(input_feats, self.dense_block(input_feats), self.training)   # dnn.py:53-67 in one launch
+        return self._run_tower(x)                                                     # dnn.py:68

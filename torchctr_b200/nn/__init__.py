@@ -1,0 +1,7 @@
+from .embedding import EmbeddingTable, PooledLookupGroup, SparseOptimizerBinding, pooled_lookup
+from .dynamic import DynamicEmbedding
+from .vocab import VocabIndex
+from .interaction import CrossLayer, fm_interaction
+
+__all__ = ["EmbeddingTable", "DynamicEmbedding", "VocabIndex", "PooledLookupGroup", "SparseOptimizerBinding",
+           "pooled_lookup", "CrossLayer", "fm_interaction"]

@@ -1,0 +1,334 @@
+"""Embedding tables and the fused pooled lookup (host side of kernels K1 / K2).
+
+``EmbeddingTable`` is an ``nn.Embedding`` (same constructor, same ``weight`` parameter, same
+state-dict key) so models built from it load and save reference checkpoints
+(``torchctr/models/dnn.py:17-23``).  ``PooledLookupGroup`` turns the per-feature Python loop of
+``torchctr/models/dnn.py:53-67`` into ONE kernel launch that writes the tower input, and its
+backward into sort/dedup + fused sparse update (or sparse gradients when no optimizer is
+bound), so neither a ``[B, L, D]`` activation nor a dense ``[V, D]`` gradient exists.
+"""
+from __future__ import annotations
+
+import warnings
+
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops
+
+
+class EmbeddingTable(nn.Embedding):
+    """``nn.Embedding`` whose lookups run through libctr_b200.
+
+    Extra keyword arguments describe how raw ids reach table rows:
+    ``index_kind`` 'direct' (ids are rows, the reference's only mode at model level), 'hash'
+    (row = murmur3_32(str(id), seed) % num_embeddings, i.e. ``torchctr.utils.hash_bucket`` fused
+    into the lookup) or 'vocab' (row = VocabIndex[id], unknown -> 0); ``pooling`` 'sum' | 'mean'.
+    ``forward`` keeps ``nn.Embedding`` semantics (un-pooled gather).
+    """
+
+    def __init__(self, num_embeddings, embedding_dim, padding_idx=None, max_norm=None, norm_type=2.0,
+                 scale_grad_by_freq=False, sparse=False, _weight=None, *, pooling: str = "sum",
+                 index_kind: str = "direct", hash_seed: int = 0, vocab=None, use_id_weight: bool = False, **kw):
+        if max_norm is not None or scale_grad_by_freq or padding_idx is not None:
+            raise NotImplementedError("max_norm / scale_grad_by_freq / padding_idx are not supported by the fused "
+                                      "lookup (the reference models never set them, models/dnn.py:21)")
+        super().__init__(num_embeddings, embedding_dim, None, None, norm_type, False, sparse, _weight, **kw)
+        if pooling not in ("sum", "mean"):
+            raise ValueError(f"unknown pooling {pooling!r}")
+        if index_kind not in ("direct", "hash", "vocab"):
+            raise ValueError(f"unknown index_kind {index_kind!r}")
+        self.pooling = pooling
+        self.index_kind = index_kind
+        self.hash_seed = int(hash_seed)
+        self.vocab = vocab                       # VocabIndex module when index_kind == 'vocab'
+        self.use_id_weight = bool(use_id_weight)  # multiply rows by feats['<name>_weight'] (dataset.py:59-67)
+        self._opt_kind = None
+
+    # -- optimizer state lives with the table so that it is checkpointed with the model ------
+    def _ensure_state(self, kind: str, initial_accumulator_value: float = 0.0):
+        w = self.weight
+        if kind in ("adagrad", "adam") and getattr(self, "opt_state0", None) is None:
+            self.register_buffer("opt_state0", torch.full_like(w.data, initial_accumulator_value if kind == "adagrad" else 0.0))
+        if kind == "rowwise_adagrad" and getattr(self, "opt_state0", None) is None:
+            self.register_buffer("opt_state0", torch.full((w.shape[0],), initial_accumulator_value, device=w.device))
+        if kind == "adam" and getattr(self, "opt_state1", None) is None:
+            self.register_buffer("opt_state1", torch.zeros_like(w.data))
+        for name in ("opt_state0", "opt_state1"):          # follow the table if it grew / moved
+            buf = getattr(self, name, None)
+            if buf is not None and (buf.shape[0] != w.shape[0] or buf.device != w.device):
+                new = torch.zeros((w.shape[0],) + tuple(buf.shape[1:]), device=w.device)
+                n = min(buf.shape[0], w.shape[0])
+                new[:n] = buf[:n].to(w.device)
+                setattr(self, name, new)
+        self._opt_kind = kind
+
+    # -- growth (DynamicEmbedding._expand_embeddings, torchctr/nn/embedding.py:69-78) -----------
+    def grow_to(self, new_num_embeddings: int, std: float = 0.01) -> None:
+        """Append rows ~ N(0, std) up to ``new_num_embeddings``; existing rows keep their values.
+        The table sits in a capacity-managed store, so growth is amortised O(new rows)."""
+        old = self.num_embeddings
+        if new_num_embeddings <= old:
+            return
+        w = self.weight
+        store = getattr(self, "_store", None)
+        if store is None or store.data_ptr() != w.data_ptr() or store.shape[0] < new_num_embeddings:
+            cap = max(new_num_embeddings, old + old // 2 + 1024)
+            store = torch.empty(cap, self.embedding_dim, dtype=w.dtype, device=w.device)
+            store[:old] = w.data
+            self._store = store
+        seed = getattr(self, "_init_seed", None)
+        if seed is None:
+            seed = self._init_seed = torch.initial_seed()
+        ops.normal_fill_rows(store, old, new_num_embeddings - old, 0.0, std, seed)
+        self.weight = nn.Parameter(store[:new_num_embeddings], requires_grad=w.requires_grad)
+        self.num_embeddings = new_num_embeddings
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        key = prefix + "weight"
+        if getattr(self, "_store", None) is not None and key in destination and not keep_vars:
+            destination[key] = destination[key].clone()      # a view would drag the whole store into torch.save
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        for name in ("opt_state0", "opt_state1"):           # optional keys: absent in reference checkpoints
+            key = prefix + name
+            if key in state_dict and getattr(self, name, None) is None:
+                self.register_buffer(name, torch.empty_like(state_dict[key], device=self.weight.device))
+        before = len(missing_keys)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+        missing_keys[before:] = [k for k in missing_keys[before:] if not k.endswith(("opt_state0", "opt_state1"))]
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        """``nn.Embedding.forward``: ids of any shape (all >= 0) -> [..., D]."""
+        flat = input.reshape(-1, 1)
+        out = pooled_lookup([(self, flat, None)])
+        return out[:, : self.embedding_dim].reshape(*input.shape, self.embedding_dim)
+
+
+class SparseOptimizerBinding:
+    """Reads the hyper-parameters of a ``torch.optim`` optimizer every step, so the fused row
+    update follows the user's optimizer (and any lr scheduler) set up for the reference Trainer
+    (``torchctr/trainer.py:303``)."""
+
+    def __init__(self, optimizer: torch.optim.Optimizer, tables, kind: str | None = None):
+        self.optimizer = optimizer
+        self.tables = list(tables)
+        self.step = 0
+        ids = {id(t.weight) for t in self.tables}
+        self.group = None
+        for g in optimizer.param_groups:
+            if any(id(p) in ids for p in g["params"]):
+                self.group = g
+                break
+        if self.group is None:
+            self.group = optimizer.param_groups[0]
+        if kind is None:
+            name = type(optimizer).__name__.lower()
+            if name == "sgd":
+                kind = "sgd"
+            elif name == "adagrad":
+                kind = "adagrad"
+            elif name in ("sparseadam", "adam", "adamw"):
+                kind = "adam"
+                if name != "sparseadam":
+                    warnings.warn("torchctr_b200: dense Adam on embedding tables is applied as lazy Adam "
+                                  "(torch.optim.SparseAdam semantics: untouched rows do not decay)", stacklevel=3)
+            else:
+                raise ValueError(f"no fused row update for optimizer {type(optimizer).__name__}; "
+                                 "pass kind='sgd'|'adagrad'|'rowwise_adagrad'|'adam'")
+        self.kind = kind
+        g = self.group
+        if g.get("weight_decay", 0) or g.get("momentum", 0):
+            raise ValueError("fused table update supports neither weight_decay nor momentum "
+                             "(a touched-rows-only update cannot reproduce them)")
+
+    def next_opt(self) -> _lib.Opt:
+        self.step += 1
+        g = self.group
+        lr = float(g["lr"])
+        if self.kind in ("adagrad", "rowwise_adagrad"):
+            lr = lr / (1.0 + (self.step - 1) * float(g.get("lr_decay", 0.0)))
+        eps = float(g.get("eps", 1e-10 if self.kind != "adam" else 1e-8))
+        betas = g.get("betas", (0.9, 0.999))
+        return ops.make_opt(self.kind, lr, eps, (float(betas[0]), float(betas[1])), self.step)
+
+    def initial_accumulator_value(self) -> float:
+        return float(self.group.get("initial_accumulator_value", 0.0))
+
+
+class _Workspace:
+    """Grow-only device scratch shared by the groups of one device."""
+    _bufs: dict = {}
+
+    @classmethod
+    def get(cls, device, nbytes: int) -> torch.Tensor:
+        buf = cls._bufs.get(device)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
+            cls._bufs[device] = buf
+        return buf
+
+
+class _PooledLookupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, call, dense, *weights):
+        ctx.call = call
+        ctx.has_dense = dense is not None
+        return call.run_forward(dense, weights)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        call = ctx.call
+        wgrads = call.run_backward(grad_out)
+        gdense = None
+        if ctx.has_dense and ctx.needs_input_grad[1]:
+            gdense = grad_out[:, call.dense_col: call.dense_col + call.dense_width]
+        return (None, gdense, *wgrads)
+
+
+class _LookupCall:
+    """One forward/backward of a group of tables over one batch."""
+
+    def __init__(self, entries, dense_width, layout, binding, training):
+        # entries: [(table module, ids [B, L] i64, id_weight or None)]
+        self.entries = entries
+        self.layout = layout            # (out_cols, width, stride, dense_col)
+        self.out_cols, self.width, self.stride, self.dense_col = layout
+        self.dense_width = dense_width
+        self.binding = binding
+        self.training = training
+        self.B = entries[0][1].shape[0] if entries else 0
+        self.bag_scales = None
+        self.status = None
+
+    def _specs(self, tables_data, with_state):
+        specs = []
+        for i, (mod, ids, wgt) in enumerate(self.entries):
+            vocab = mod.vocab.handle() if mod.index_kind == "vocab" else None
+            specs.append(ops.FeatureSpec(
+                ids=ids, table=tables_data[i], num_rows=mod.num_embeddings, D=mod.embedding_dim,
+                out_col=self.out_cols[i], pooling=mod.pooling, index_kind=mod.index_kind, hash_seed=mod.hash_seed,
+                id_weight=wgt, vocab=vocab,
+                state0=getattr(mod, "opt_state0", None) if with_state else None,
+                state1=getattr(mod, "opt_state1", None) if with_state else None,
+                bag_scale=self.bag_scales[i]))
+        return specs
+
+    def run_forward(self, dense, weights):
+        dev = weights[0].device
+        B = self.B
+        out = torch.empty(B, self.stride, dtype=torch.float32, device=dev)
+        self.bag_scales = [torch.empty(B, dtype=torch.float32, device=dev) if m.pooling == "mean" else None
+                           for m, _, _ in self.entries]
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        zero_from = self.width if self.stride > self.width else -1
+        call = ops.make_group(self._specs([w.detach() for w in weights], False), B, out, self.stride,
+                              dense=dense, dense_col=self.dense_col, zero_from=zero_from, status=self.status)
+        ops.emb_pool_fwd(call)
+        return out
+
+    def run_backward(self, grad_out):
+        mods = [m for m, _, _ in self.entries]
+        needs = [m.weight.requires_grad for m in mods]
+        if not any(needs):
+            return [None] * len(mods)
+        if grad_out.stride(1) != 1 or grad_out.stride(0) != grad_out.shape[1]:
+            grad_out = grad_out.contiguous()
+        dev = grad_out.device
+        fused = self.binding is not None and self.training
+        if fused:
+            for m in mods:
+                m._ensure_state(self.binding.kind, self.binding.initial_accumulator_value())
+        tables = [m.weight.data for m in mods]
+        call = ops.make_group(self._specs(tables, fused), self.B, grad_out, grad_out.shape[1])
+        ws = _Workspace.get(dev, ops.emb_bwd_workspace_bytes(call))
+        ops.emb_bwd_plan(call, ws)
+        if fused:
+            ops.emb_bwd_apply(call, ws, self.binding.next_opt())
+            return [None] * len(mods)
+        # no optimizer bound: hand autograd sparse gradients (torch.optim SGD / Adagrad / SparseAdam accept them)
+        S = sum(ids.numel() for _, ids, _ in self.entries)
+        dmax = max(m.embedding_dim for m in mods)
+        uf = torch.empty(S, dtype=torch.int32, device=dev)
+        ur = torch.empty(S, dtype=torch.int32, device=dev)
+        rg = torch.empty(S, dmax, dtype=torch.float32, device=dev)
+        nu = torch.zeros(1, dtype=torch.int64, device=dev)
+        ops.emb_bwd_apply(call, ws, ops.make_opt("none"), uf, ur, rg, nu)
+        U = int(nu.item())
+        uf, ur, rg = uf[:U], ur[:U], rg[:U]
+        bounds = torch.searchsorted(uf, torch.arange(len(mods) + 1, dtype=torch.int32, device=dev)).tolist()
+        grads = []
+        for i, m in enumerate(mods):
+            if not needs[i]:
+                grads.append(None)
+                continue
+            lo, hi = bounds[i], bounds[i + 1]
+            grads.append(torch.sparse_coo_tensor(ur[lo:hi].long().unsqueeze(0), rg[lo:hi, : m.embedding_dim],
+                                                 size=tuple(m.weight.shape), is_coalesced=True))
+        return grads
+
+
+def _layout(entries, dense_width, align=4):
+    cols, col = [], 0
+    for m, _, _ in entries:
+        cols.append(col)
+        col += m.embedding_dim
+    dense_col = col
+    width = col + dense_width
+    stride = (width + align - 1) // align * align
+    return cols, width, stride, dense_col
+
+
+def pooled_lookup(entries, dense: torch.Tensor | None = None, binding: SparseOptimizerBinding | None = None,
+                  training: bool = False) -> torch.Tensor:
+    """Pools every (table, ids [B, L], id_weight) entry and concatenates them with ``dense``.
+
+    Returns f32 ``[B, stride]`` with ``stride`` = total width rounded up to 4 floats; columns past
+    the width are zero.  This is ``torchctr/models/dnn.py:53-67`` as one launch.
+    """
+    if not entries:
+        raise ValueError("pooled_lookup needs at least one table")
+    dev = entries[0][0].weight.device
+    if dev.type != "cuda":
+        raise RuntimeError("torchctr_b200 tables must live on a CUDA device: the lookup kernels have no CPU path")
+    prepared = []
+    for mod, ids, wgt in entries:
+        if ids.dim() == 1:
+            ids = ids.unsqueeze(1)
+        if ids.dim() != 2:
+            raise ValueError(f"ids must be [B] or [B, L], got {tuple(ids.shape)}")
+        if ids.dtype != torch.int64:
+            ids = ids.long()
+        ids = ids.to(dev, non_blocking=True).contiguous()
+        if wgt is not None:
+            wgt = wgt.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        prepared.append((mod, ids, wgt))
+    dense_width = 0
+    if dense is not None:
+        dense = dense.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        dense_width = dense.shape[1]
+    # a launch group carries at most MAX_FEATURES tables and a 32-bit key space
+    if len(prepared) <= _lib.MAX_FEATURES and sum(m.num_embeddings for m, _, _ in prepared) < 2 ** 32 - 1:
+        call = _LookupCall(prepared, dense_width, _layout(prepared, dense_width), binding, training)
+        return _PooledLookupFn.apply(call, dense, *[m.weight for m, _, _ in prepared])
+    raise NotImplementedError("split the features into several pooled_lookup calls "
+                              f"(more than {_lib.MAX_FEATURES} tables or >= 2^32 rows in one group)")
+
+
+class PooledLookupGroup:
+    """The sparse half of a model: tables in ``feat_configs`` order + the dense block."""
+
+    def __init__(self, names, tables: nn.ModuleDict):
+        self.names = list(names)
+        self.tables = tables
+        self.binding: SparseOptimizerBinding | None = None
+
+    def bind_optimizer(self, optimizer, kind: str | None = None):
+        self.binding = SparseOptimizerBinding(optimizer, [self.tables[n] for n in self.names], kind)
+        return self.binding
+
+    def __call__(self, feats: dict, dense: torch.Tensor | None, training: bool) -> torch.Tensor:
+        entries = [(self.tables[n], feats[n], feats.get(n + "_weight") if self.tables[n].use_id_weight else None)
+                   for n in self.names]
+        return pooled_lookup(entries, dense, self.binding, training)

@@ -1,0 +1,322 @@
+"""Tensor-level wrappers of the C ABI (``include/ctr_b200.h``).
+
+Each function takes CUDA tensors, checks dtypes / contiguity, and calls the matching
+``ctr_*`` entry point on the current torch CUDA stream.  Nothing here computes on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _lib
+from ._lib import (INDEX_DIRECT, INDEX_HASH, INDEX_REMAP, OPT_ADAGRAD, OPT_ADAM, OPT_NONE,  # noqa: F401
+                   OPT_ROWWISE_ADAGRAD, OPT_SGD, POOL_MEAN, POOL_SUM)
+
+_INDEX_KINDS = {"direct": INDEX_DIRECT, "hash": INDEX_HASH, "vocab": INDEX_REMAP, "remap": INDEX_REMAP}
+_POOLINGS = {"sum": POOL_SUM, "mean": POOL_MEAN}
+_OPT_KINDS = {"none": OPT_NONE, "sgd": OPT_SGD, "adagrad": OPT_ADAGRAD, "rowwise_adagrad": OPT_ROWWISE_ADAGRAD,
+              "adam": OPT_ADAM}
+
+
+def _chk(t, name, dtype, cuda=True):
+    if t is None:
+        return
+    if cuda:
+        _lib.require_cuda(t, name)
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+class VocabMapHandle:
+    """Device hash map raw key (int64) -> row (int32); owns nothing but references."""
+
+    def __init__(self, keys: torch.Tensor, rows: torch.Tensor):
+        _chk(keys, "map keys", torch.int64)
+        _chk(rows, "map rows", torch.int32)
+        cap = keys.numel()
+        if cap == 0 or cap & (cap - 1) or rows.numel() != cap:
+            raise ValueError("vocabulary map capacity must be a power of two and match rows")
+        self.keys, self.rows = keys, rows
+        self.struct = _lib.VocabMap(keys.data_ptr(), rows.data_ptr(), cap)
+
+
+@dataclass
+class FeatureSpec:
+    """One table of a launch group (mirrors ``ctr_feature_t``)."""
+    ids: torch.Tensor                       # i64 [B, L]
+    table: torch.Tensor | None              # f32 [V, D]
+    num_rows: int
+    D: int
+    out_col: int
+    pooling: str = "sum"
+    index_kind: str = "direct"
+    hash_seed: int = 0
+    id_weight: torch.Tensor | None = None   # f32 [B, L]
+    vocab: VocabMapHandle | None = None
+    state0: torch.Tensor | None = None
+    state1: torch.Tensor | None = None
+    bag_scale: torch.Tensor | None = None   # f32 [B]
+
+
+@dataclass
+class GroupCall:
+    """A lowered ``ctr_group_t`` plus the Python objects that keep its pointers alive."""
+    struct: _lib.Group
+    keep: list = field(default_factory=list)
+
+
+def make_group(features, B: int, out: torch.Tensor | None, out_stride: int, dense: torch.Tensor | None = None,
+               dense_col: int = 0, zero_from: int = -1, status: torch.Tensor | None = None) -> GroupCall:
+    n = len(features)
+    if n > _lib.MAX_FEATURES:
+        raise ValueError(f"a launch group holds at most {_lib.MAX_FEATURES} features, got {n}")
+    arr = (_lib.Feature * max(n, 1))()
+    keep = [arr, out, dense, status]
+    for i, f in enumerate(features):
+        _chk(f.ids, f"feature {i} ids", torch.int64)
+        if f.ids.dim() != 2 or f.ids.shape[0] != B:
+            raise ValueError(f"feature {i}: ids must be [B={B}, L], got {tuple(f.ids.shape)}")
+        _chk(f.table, f"feature {i} table", torch.float32)
+        _chk(f.id_weight, f"feature {i} id_weight", torch.float32)
+        _chk(f.state0, f"feature {i} state0", torch.float32)
+        _chk(f.state1, f"feature {i} state1", torch.float32)
+        _chk(f.bag_scale, f"feature {i} bag_scale", torch.float32)
+        if f.id_weight is not None and f.id_weight.shape != f.ids.shape:
+            raise ValueError(f"feature {i}: id_weight shape {tuple(f.id_weight.shape)} != ids {tuple(f.ids.shape)}")
+        if f.table is not None and tuple(f.table.shape) != (f.num_rows, f.D):
+            raise ValueError(f"feature {i}: table shape {tuple(f.table.shape)} != ({f.num_rows}, {f.D})")
+        s = arr[i]
+        s.ids = f.ids.data_ptr()
+        s.id_weight = _lib.ptr(f.id_weight)
+        s.table = _lib.ptr(f.table)
+        s.state0 = _lib.ptr(f.state0)
+        s.state1 = _lib.ptr(f.state1)
+        s.bag_scale = _lib.ptr(f.bag_scale)
+        s.map = C.pointer(f.vocab.struct) if f.vocab is not None else None
+        s.num_rows = f.num_rows
+        s.L = f.ids.shape[1]
+        s.D = f.D
+        s.out_col = f.out_col
+        s.pooling = _POOLINGS[f.pooling]
+        s.index_kind = _INDEX_KINDS[f.index_kind]
+        s.hash_seed = f.hash_seed & 0xFFFFFFFF
+        keep.append((f.ids, f.id_weight, f.table, f.state0, f.state1, f.bag_scale, f.vocab))
+    _chk(out, "out", torch.float32)
+    _chk(dense, "dense", torch.float32)
+    if status is not None:
+        _chk(status, "status", torch.int32)
+    g = _lib.Group()
+    g.features = arr
+    g.num_features = n
+    g.B = B
+    g.out = _lib.ptr(out)
+    g.out_stride = out_stride
+    g.dense = _lib.ptr(dense)
+    g.dense_width = 0 if dense is None else dense.shape[1]
+    g.dense_col = dense_col
+    g.zero_from = zero_from
+    g.status = _lib.ptr(status)
+    return GroupCall(g, keep)
+
+
+def _stream(t: torch.Tensor | None = None):
+    return _lib.stream_ptr(t.device if t is not None else None)
+
+
+class KernelTimer:
+    """Optional CUDA-event timing of the C-ABI calls on the launching stream (bench.py's roofline
+    numbers).  Off by default; ``with KernelTimer() as kt: ...; kt.summary()``."""
+    active = None
+
+    def __init__(self):
+        self.spans = {}
+
+    def __enter__(self):
+        KernelTimer.active = self
+        return self
+
+    def __exit__(self, *exc):
+        KernelTimer.active = None
+
+    def summary(self):
+        """name -> (calls, total ms); synchronises."""
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.spans.items()}
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        kt = KernelTimer.active
+        if kt is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+
+    def __exit__(self, *exc):
+        kt = KernelTimer.active
+        if kt is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            kt.spans.setdefault(self.name, []).append((self.start, end))
+
+
+def kernel_launches() -> int:
+    return int(_lib.lib().ctr_kernel_launches())
+
+
+def emb_pool_fwd(call: GroupCall) -> None:
+    with _timed("emb_pool_fwd"):
+        _lib.check(_lib.lib().ctr_emb_pool_fwd(C.byref(call.struct), _stream()), "ctr_emb_pool_fwd")
+
+
+def emb_bwd_workspace_bytes(call: GroupCall) -> int:
+    return _lib.check(_lib.lib().ctr_emb_bwd_workspace_bytes(C.byref(call.struct)), "ctr_emb_bwd_workspace_bytes")
+
+
+def emb_bwd_plan(call: GroupCall, workspace: torch.Tensor) -> None:
+    _chk(workspace, "workspace", torch.uint8)
+    with _timed("emb_bwd_plan"):
+        _lib.check(_lib.lib().ctr_emb_bwd_plan(C.byref(call.struct), workspace.data_ptr(), workspace.numel(), _stream()),
+                   "ctr_emb_bwd_plan")
+
+
+def make_opt(kind: str = "none", lr: float = 0.0, eps: float = 1e-10, betas=(0.9, 0.999), step: int = 1) -> _lib.Opt:
+    return _lib.Opt(_OPT_KINDS[kind], lr, eps, betas[0], betas[1], step)
+
+
+def emb_bwd_apply(call: GroupCall, workspace: torch.Tensor, opt: _lib.Opt, uniq_feature=None, uniq_row=None,
+                  row_grad=None, num_unique=None) -> None:
+    _chk(uniq_feature, "uniq_feature", torch.int32)
+    _chk(uniq_row, "uniq_row", torch.int32)
+    _chk(row_grad, "row_grad", torch.float32)
+    _chk(num_unique, "num_unique", torch.int64)
+    stride = 0 if row_grad is None else row_grad.shape[1]
+    with _timed("emb_bwd_apply"):
+        _lib.check(_lib.lib().ctr_emb_bwd_apply(C.byref(call.struct), workspace.data_ptr(), C.byref(opt),
+                                                _lib.ptr(uniq_feature), _lib.ptr(uniq_row), _lib.ptr(row_grad), stride,
+                                                _lib.ptr(num_unique), _stream()), "ctr_emb_bwd_apply")
+
+
+def hash_bucket(ids: torch.Tensor, buckets: int, seed: int = 0) -> torch.Tensor:
+    """``torchctr.utils.hash_bucket`` (utils.py:103-119) on a tensor of integer ids -> int32 buckets."""
+    _chk(ids, "ids", torch.int64)
+    if not 0 <= seed <= 0xFFFFFFFF:
+        raise OverflowError("seed must fit uint32")      # sklearn raises OverflowError too
+    if not 0 < buckets < 2 ** 31:
+        raise ValueError("buckets must be in [1, 2^31)")
+    out = torch.empty(ids.shape, dtype=torch.int32, device=ids.device)
+    _lib.check(_lib.lib().ctr_hash_bucket_i64(ids.data_ptr(), ids.numel(), buckets, seed, out.data_ptr(), _stream(ids)),
+               "ctr_hash_bucket_i64")
+    return out
+
+
+def rows_gather(ids: torch.Tensor, table: torch.Tensor, status: torch.Tensor | None = None) -> torch.Tensor:
+    _chk(ids, "ids", torch.int64)
+    _chk(table, "table", torch.float32)
+    out = torch.empty(*ids.shape, table.shape[1], dtype=torch.float32, device=table.device)
+    _lib.check(_lib.lib().ctr_rows_gather(ids.data_ptr(), ids.numel(), table.data_ptr(), table.shape[0], table.shape[1],
+                                          out.data_ptr(), _lib.ptr(status), _stream(table)), "ctr_rows_gather")
+    return out
+
+
+def normal_fill_rows(table: torch.Tensor, row0: int, n: int, mean: float, std: float, seed: int) -> None:
+    _chk(table, "table", torch.float32)
+    if row0 < 0 or row0 + n > table.shape[0]:
+        raise ValueError("row range outside the table")
+    _lib.check(_lib.lib().ctr_normal_fill_rows(table.data_ptr(), row0, n, table.shape[1], mean, std,
+                                               seed & 0xFFFFFFFFFFFFFFFF, _stream(table)), "ctr_normal_fill_rows")
+
+
+def ids_minmax(ids: torch.Tensor) -> torch.Tensor:
+    """Device tensor i64 [2] = (min, max) of ids."""
+    _chk(ids, "ids", torch.int64)
+    out = torch.empty(2, dtype=torch.int64, device=ids.device)
+    _lib.check(_lib.lib().ctr_ids_minmax(ids.data_ptr(), ids.numel(), out.data_ptr(), _stream(ids)), "ctr_ids_minmax")
+    return out
+
+
+def vocab_fit(vmap: VocabMapHandle, keys: torch.Tensor, next_row: torch.Tensor, min_freq: int = 0,
+              counts: torch.Tensor | None = None, status: torch.Tensor | None = None) -> None:
+    _chk(keys, "keys", torch.int64)
+    _chk(next_row, "next_row", torch.int64)
+    _chk(counts, "counts", torch.int64)
+    n = keys.numel()
+    nbytes = _lib.check(_lib.lib().ctr_vocab_fit_workspace_bytes(n))
+    ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=keys.device)
+    _lib.check(_lib.lib().ctr_vocab_fit(C.byref(vmap.struct), keys.data_ptr(), n, int(min_freq or 0), next_row.data_ptr(),
+                                        _lib.ptr(counts), _lib.ptr(status), ws.data_ptr(), ws.numel(), _stream(keys)),
+               "ctr_vocab_fit")
+
+
+def vocab_transform(vmap: VocabMapHandle, keys: torch.Tensor, oov_row: int = 0) -> torch.Tensor:
+    _chk(keys, "keys", torch.int64)
+    rows = torch.empty(keys.shape, dtype=torch.int32, device=keys.device)
+    _lib.check(_lib.lib().ctr_vocab_transform(C.byref(vmap.struct), keys.data_ptr(), keys.numel(), oov_row,
+                                              rows.data_ptr(), _stream(keys)), "ctr_vocab_transform")
+    return rows
+
+
+def vocab_insert(vmap: VocabMapHandle, keys: torch.Tensor, rows: torch.Tensor, status: torch.Tensor | None = None) -> None:
+    _chk(keys, "keys", torch.int64)
+    _chk(rows, "rows", torch.int32)
+    _lib.check(_lib.lib().ctr_vocab_insert(C.byref(vmap.struct), keys.data_ptr(), rows.data_ptr(), keys.numel(),
+                                           _lib.ptr(status), _stream(keys)), "ctr_vocab_insert")
+
+
+def vocab_clear(vmap: VocabMapHandle) -> None:
+    _lib.check(_lib.lib().ctr_vocab_clear(C.byref(vmap.struct), _stream(vmap.keys)), "ctr_vocab_clear")
+
+
+def fm_fwd(x: torch.Tensor, F: int, D: int, first: torch.Tensor | None = None, out: torch.Tensor | None = None,
+           accumulate: bool = False) -> torch.Tensor:
+    """x f32 [B, stride>=F*D] -> out f32 [B, 1] = FM second-order term (+ row sums of ``first`` [B, n])."""
+    _lib.require_cuda(x, "x")
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be f32 [B, *] with unit inner stride")
+    B = x.shape[0]
+    if out is None:
+        out = torch.empty(B, 1, dtype=torch.float32, device=x.device)
+    nfirst = 0 if first is None else first.shape[1]
+    if first is not None and (first.dtype != torch.float32 or first.stride(1) != 1):
+        raise ValueError("first must be f32 with unit inner stride")
+    _lib.check(_lib.lib().ctr_fm_fwd(x.data_ptr(), x.stride(0), B, F, D, _lib.ptr(first), nfirst,
+                                     0 if first is None else first.stride(0), out.data_ptr(), out.stride(0),
+                                     int(accumulate), _stream(x)), "ctr_fm_fwd")
+    return out
+
+
+def fm_bwd(x: torch.Tensor, F: int, D: int, gout: torch.Tensor, gx: torch.Tensor, accumulate: bool,
+           gfirst: torch.Tensor | None = None) -> None:
+    B = x.shape[0]
+    nfirst = 0 if gfirst is None else gfirst.shape[1]
+    _lib.check(_lib.lib().ctr_fm_bwd(x.data_ptr(), x.stride(0), B, F, D, gout.data_ptr(), gout.stride(0), gx.data_ptr(),
+                                     gx.stride(0), int(accumulate), _lib.ptr(gfirst), nfirst,
+                                     0 if gfirst is None else gfirst.stride(0), _stream(x)), "ctr_fm_bwd")
+
+
+def cross_combine_fwd(x0, x, u, bias) -> torch.Tensor:
+    for name, t in (("x0", x0), ("x", x), ("u", u)):
+        _chk(t, name, torch.float32)
+    _chk(bias, "bias", torch.float32)
+    B, d = x0.shape
+    y = torch.empty_like(x0)
+    _lib.check(_lib.lib().ctr_cross_combine_fwd(x0.data_ptr(), x.data_ptr(), u.data_ptr(), bias.data_ptr(), B, d, d,
+                                                y.data_ptr(), _stream(x0)), "ctr_cross_combine_fwd")
+    return y
+
+
+def cross_combine_bwd(x0, u, bias, gy, gx0: torch.Tensor, accumulate: bool) -> torch.Tensor:
+    for name, t in (("x0", x0), ("u", u), ("gy", gy), ("gx0", gx0)):
+        _chk(t, name, torch.float32)
+    B, d = x0.shape
+    gu = torch.empty_like(x0)
+    _lib.check(_lib.lib().ctr_cross_combine_bwd(x0.data_ptr(), u.data_ptr(), bias.data_ptr(), gy.data_ptr(), B, d, d,
+                                                gu.data_ptr(), gx0.data_ptr(), int(accumulate), _stream(x0)),
+               "ctr_cross_combine_bwd")
+    return gu
