@@ -109,10 +109,10 @@ typedef struct ctr_group {
 
 typedef struct ctr_opt {
     int32_t kind;            /* CTR_OPT_*                                                    */
-    float lr;                /* already decayed by the host if a schedule is used            */
-    float eps;
-    float beta1, beta2;      /* Adam                                                         */
     int32_t step;            /* Adam bias-correction step (1-based)                          */
+    double lr;               /* already decayed by the host if a schedule is used            */
+    double eps;
+    double beta1, beta2;     /* Adam (doubles: torch forms 1 - beta in double precision)     */
 } ctr_opt_t;
 
 const char *ctr_last_error_string(void);

@@ -54,15 +54,20 @@ def test_dnn_matches_reference_golden(golden_dir):
     loss = model.training_step((g["feats"], g["labels"]), 0)
     close(loss, g["train_loss"], TOWER_RTOL)
     loss.backward()
+    # a Linear bias in front of BatchNorm has a mathematically zero gradient: what the fixture holds there is
+    # rounding noise, which the first Adagrad step turns into +-lr -- such parameters are not comparable
+    noise = {n for n, gr in g["grads"].items() if float(gr.abs().max()) < 1e-6}
     for name, p in model.named_parameters():
         if name.startswith("tower"):
-            close(p.grad, g["grads"][name], 5e-4)
+            if name not in noise:
+                close(p.grad, g["grads"][name], 5e-4)
         else:
             assert p.grad is None                            # no dense [V, D] gradient exists
     opt.step()
     after = model.state_dict()
     for k, ref in g["after_adagrad_step"].items():
-        close(after[k], ref, 5e-4 if k.startswith("tower") else 2e-4)
+        if k not in noise:
+            close(after[k], ref, 5e-4 if k.startswith("tower") else 2e-4)
 
 
 def test_dnn_sparse_grads_without_binding(golden_dir):

@@ -50,8 +50,8 @@ class Group(C.Structure):
 
 
 class Opt(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("lr", C.c_float), ("eps", C.c_float), ("beta1", C.c_float),
-                ("beta2", C.c_float), ("step", C.c_int32)]
+    _fields_ = [("kind", C.c_int32), ("step", C.c_int32), ("lr", C.c_double), ("eps", C.c_double),
+                ("beta1", C.c_double), ("beta2", C.c_double)]
 
 
 _P = C.c_void_p

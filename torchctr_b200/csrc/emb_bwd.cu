@@ -7,8 +7,9 @@
 //          runs of equal keys (= unique rows) listed by a head-flag scan;
 //   apply  one team of lanes per unique row sums coef * grad_out[bag] over the run in slot
 //          order (deterministic), then applies SGD / Adagrad / row-wise Adagrad / lazy Adam
-//          to that row in place.  Runs longer than kLongRun (hot Zipf rows) are queued and
-//          reduced by a whole block each, with a fixed-order shared-memory tree.
+//          to that row in place.  Runs longer than kLongRun (hot Zipf rows) are queued, cut
+//          into chunks of kChunk positions that one block each reduces with a fixed-order
+//          shared-memory tree, and finished by a team that adds the chunk partials in order.
 #include "sort.cuh"
 
 namespace ctr {
@@ -22,10 +23,13 @@ struct PlanLayout {
     int key_bits;
     int sorted_in_b;     // which ping-pong buffer holds the sorted pairs
     // offsets in bytes from the workspace base
-    int64_t counters, keys_a, keys_b, vals_a, vals_b, counts, spine, run_start, long_list, total;
+    int64_t counters, keys_a, keys_b, vals_a, vals_b, counts, spine, run_start;
+    // apply-time scratch (rebuilt by every apply; sized by the group being applied)
+    int64_t long_list, long_cbase, chunk_q, partials, max_long, max_chunks, row_floats, total;
 };
-// counters (u32): [0] runs, [1] unique valid rows, [2] long-run queue length
+// counters (u32): [0] runs, [1] unique valid rows, [2] long-run queue length, [3] chunk queue length
 constexpr int kNumCounters = 8;
+constexpr int kChunk = 1024;   // sorted positions reduced by one block
 
 static int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
 
@@ -54,7 +58,15 @@ static PlanLayout plan_layout(const DevGroup &g) {
     const int64_t spine = scan_spine_elems(counts > S ? counts : S) + 8;
     p.spine = off; off = align256(off + spine * 4);
     p.run_start = off; off = align256(off + (S + 2) * 4);
-    p.long_list = off; off = align256(off + (S / kLongRun + 2) * 4);
+    int row_floats = 4;  // one float4 slot per lane of the widest row, whatever the lane width
+    for (int i = 0; i < g.num_features; ++i) row_floats = max(row_floats, g.f[i].G * 4);
+    p.row_floats = row_floats;
+    p.max_long = S / (kLongRun + 1) + 2;
+    p.max_chunks = p.max_long + S / kChunk + 2;
+    p.long_list = off; off = align256(off + p.max_long * 4);
+    p.long_cbase = off; off = align256(off + p.max_long * 4);
+    p.chunk_q = off; off = align256(off + p.max_chunks * 4);
+    p.partials = off; off = align256(off + p.max_chunks * row_floats * 4);
     p.total = off;
     return p;
 }
@@ -84,14 +96,18 @@ struct ApplyArgs {
     const uint32_t *vals;       // sorted with the keys: slot inside the feature (bag * L + l)
     const uint32_t *run_start;
     uint32_t *counters;
-    uint32_t *long_list;
+    uint32_t *long_list;        // [q] -> run
+    uint32_t *long_cbase;       // [q] -> first chunk of the run
+    uint32_t *chunk_q;          // [chunk] -> q
+    float *partials;            // [chunk, row_floats]
+    int row_floats;
     int32_t *uniq_feature;
     int32_t *uniq_row;
     float *row_grad;
     int64_t row_grad_stride;
     int64_t *num_unique;
     int kind;
-    float lr, eps, beta1, beta2, adam_step_size;
+    float lr, eps, one_minus_beta1, one_minus_beta2, adam_step_size;
     int team;                   // lanes per run in the short-run kernel (max G of the group)
 };
 
@@ -135,8 +151,8 @@ __device__ __forceinline__ float adagrad_elem(float w, float &s, float gr, float
     return w - lr * __fdiv_rn(gr, __fsqrt_rn(s) + eps);
 }
 __device__ __forceinline__ float adam_elem(float w, float &m, float &v, float gr, const ApplyArgs &a) {
-    m = m + (gr - m) * (1.f - a.beta1);
-    v = v + (gr * gr - v) * (1.f - a.beta2);
+    m = m + (gr - m) * a.one_minus_beta1;
+    v = v + (gr * gr - v) * a.one_minus_beta2;
     return w - a.adam_step_size * __fdiv_rn(m, __fsqrt_rn(v) + a.eps);
 }
 
@@ -230,8 +246,18 @@ __global__ void __launch_bounds__(kApplyThreads)
     const int64_t team_global = ((int64_t)blockIdx.x * kApplyThreads + threadIdx.x) / TG;
     for (int64_t run = team_global; run < num_runs; run += teams_total) {
         const uint32_t s = a.run_start[run], e = a.run_start[run + 1];
-        if (e - s > (uint32_t)kLongRun) {
-            if (t == 0) a.long_list[atomicAdd(&a.counters[2], 1u)] = (uint32_t)run;
+        if (e - s > (uint32_t)kLongRun) {  // hot row: hand it to the chunked block reduction
+            const uint32_t nch = (e - s + kChunk - 1) / kChunk;
+            uint32_t q = 0, cbase = 0;
+            if (t == 0) {
+                q = atomicAdd(&a.counters[2], 1u);
+                cbase = atomicAdd(&a.counters[3], nch);
+                a.long_list[q] = (uint32_t)run;
+                a.long_cbase[q] = cbase;
+            }
+            q = __shfl_sync(mask, q, team_in_warp * TG);
+            cbase = __shfl_sync(mask, cbase, team_in_warp * TG);
+            for (uint32_t c = t; c < nch; c += TG) a.chunk_q[cbase + c] = q;
             continue;
         }
         const uint32_t key = a.keys[s];
@@ -266,34 +292,52 @@ __global__ void __launch_bounds__(kApplyThreads)
     }
 }
 
-// Long runs: one block per queued run; 256 / G row slots stride the run, then a fixed-order tree.
+// Long runs, stage 1: one block per chunk of kChunk sorted positions.  256 / G row slots stride the
+// chunk four positions at a time (independent loads in flight), then a fixed-order shared-memory
+// tree leaves the chunk's partial sum in partials[chunk].
 __global__ void __launch_bounds__(kApplyThreads)
-    emb_bwd_apply_long_kernel(const __grid_constant__ DevGroup g, const __grid_constant__ ApplyArgs a) {
+    emb_bwd_chunk_kernel(const __grid_constant__ DevGroup g, const __grid_constant__ ApplyArgs a) {
     __shared__ float4 red[kApplyThreads];
-    const uint32_t nlong = a.counters[2];
-    for (uint32_t q = blockIdx.x; q < nlong; q += gridDim.x) {
+    const uint32_t nchunks = a.counters[3];
+    for (uint32_t ci = blockIdx.x; ci < nchunks; ci += gridDim.x) {
+        const uint32_t q = a.chunk_q[ci];
         const uint32_t run = a.long_list[q];
-        const uint32_t s = a.run_start[run], e = a.run_start[run + 1];
-        const uint32_t key = a.keys[s];
-        const int fi = find_feature(g, key);
-        const DevFeature &f = g.f[fi];
-        const uint32_t row = key - f.row_base;
+        const uint32_t c = ci - a.long_cbase[q];
+        const uint32_t s = a.run_start[run] + c * kChunk;
+        const uint32_t run_end = a.run_start[run + 1];
+        const uint32_t e = min(run_end, s + (uint32_t)kChunk);
+        const DevFeature &f = g.f[find_feature(g, a.keys[s])];
         const int G = f.G;
         const int g_lane = threadIdx.x & (G - 1);
-        const int slot_id = threadIdx.x / G;
-        const int nslots = kApplyThreads / G;
+        const uint32_t slot_id = threadIdx.x / G;
+        const uint32_t nslots = kApplyThreads / G;
         const bool col_ok = g_lane * f.vec < f.D;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (uint32_t p = s + slot_id; p < e; p += nslots) {
-            const uint32_t slot = a.vals[p];
-            const uint32_t bag = slot / (uint32_t)f.L;
-            const float c = slot_coef(f, slot, bag);
-            if (col_ok) {
-                const float4 v = load_grad_part(g, f, bag, g_lane);
-                acc.x = fmaf(c, v.x, acc.x);
-                acc.y = fmaf(c, v.y, acc.y);
-                acc.z = fmaf(c, v.z, acc.z);
-                acc.w = fmaf(c, v.w, acc.w);
+        for (uint32_t p0 = s + slot_id; p0 < e; p0 += 4 * nslots) {
+            uint32_t bag[4];
+            float coef[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t p = p0 + j * nslots;
+                bag[j] = 0; coef[j] = 0.f;
+                if (p < e) {
+                    const uint32_t slot = a.vals[p];
+                    bag[j] = slot / (uint32_t)f.L;
+                    coef[j] = slot_coef(f, slot, bag[j]);
+                }
+            }
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col_ok && p0 + j * nslots < e) v[j] = load_grad_part(g, f, bag[j], g_lane);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc.x = fmaf(coef[j], v[j].x, acc.x);
+                acc.y = fmaf(coef[j], v[j].y, acc.y);
+                acc.z = fmaf(coef[j], v[j].z, acc.z);
+                acc.w = fmaf(coef[j], v[j].w, acc.w);
             }
         }
         red[threadIdx.x] = acc;
@@ -307,11 +351,38 @@ __global__ void __launch_bounds__(kApplyThreads)
             }
             __syncthreads();
         }
-        if (threadIdx.x < 32) {  // first warp; lanes [0, G) hold the row
-            const float4 gr = red[threadIdx.x];
-            update_row(g, f, a, run, fi, row, (int)threadIdx.x, threadIdx.x < (unsigned)G && col_ok, gr, kFull, G);
-        }
+        if ((int)threadIdx.x < G) reinterpret_cast<float4 *>(a.partials + (size_t)ci * a.row_floats)[threadIdx.x] = red[threadIdx.x];
         __syncthreads();
+    }
+}
+
+// Long runs, stage 2: one team per queued run adds its chunk partials in chunk order and updates the row.
+__global__ void __launch_bounds__(kApplyThreads)
+    emb_bwd_long_finish_kernel(const __grid_constant__ DevGroup g, const __grid_constant__ ApplyArgs a) {
+    const int TG = a.team;
+    const int lane = threadIdx.x & 31;
+    const int t = lane & (TG - 1);
+    const int team_in_warp = lane / TG;
+    const unsigned mask = TG == 32 ? kFull : (((1u << TG) - 1u) << (team_in_warp * TG));
+    const uint32_t nlong = a.counters[2];
+    const int64_t teams_total = (int64_t)gridDim.x * (kApplyThreads / TG);
+    for (int64_t q = ((int64_t)blockIdx.x * kApplyThreads + threadIdx.x) / TG; q < nlong; q += teams_total) {
+        const uint32_t run = a.long_list[q];
+        const uint32_t s = a.run_start[run], e = a.run_start[run + 1];
+        const uint32_t nch = (e - s + kChunk - 1) / kChunk;
+        const uint32_t cbase = a.long_cbase[q];
+        const uint32_t key = a.keys[s];
+        const int fi = find_feature(g, key);
+        const DevFeature &f = g.f[fi];
+        const bool col_ok = t < f.G && t * f.vec < f.D;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < f.G) {
+            for (uint32_t c = 0; c < nch; ++c) {
+                const float4 v = reinterpret_cast<const float4 *>(a.partials + (size_t)(cbase + c) * a.row_floats)[t];
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        update_row(g, f, a, run, fi, key - f.row_base, t, col_ok, acc, mask, TG);
     }
 }
 
@@ -404,36 +475,41 @@ extern "C" int ctr_emb_bwd_apply(const ctr_group_t *group, void *workspace, cons
     a.run_start = reinterpret_cast<const uint32_t *>(ws + p.run_start);
     a.counters = reinterpret_cast<uint32_t *>(ws + p.counters);
     a.long_list = reinterpret_cast<uint32_t *>(ws + p.long_list);
+    a.long_cbase = reinterpret_cast<uint32_t *>(ws + p.long_cbase);
+    a.chunk_q = reinterpret_cast<uint32_t *>(ws + p.chunk_q);
+    a.partials = reinterpret_cast<float *>(ws + p.partials);
+    a.row_floats = (int)p.row_floats;
     a.uniq_feature = uniq_feature;
     a.uniq_row = uniq_row;
     a.row_grad = row_grad;
     a.row_grad_stride = row_grad_stride;
     a.num_unique = num_unique;
     a.kind = opt->kind;
-    a.lr = opt->lr;
-    a.eps = opt->eps;
-    a.beta1 = opt->beta1;
-    a.beta2 = opt->beta2;
+    a.lr = (float)opt->lr;
+    a.eps = (float)opt->eps;
+    a.one_minus_beta1 = (float)(1.0 - opt->beta1);   // torch forms 1 - beta in double, then rounds
+    a.one_minus_beta2 = (float)(1.0 - opt->beta2);
     a.team = team;
     if (opt->kind == CTR_OPT_ADAM) {
         CTR_REQUIRE(opt->step >= 1, "Adam step must be >= 1");
-        const double bc1 = 1.0 - pow((double)opt->beta1, (double)opt->step);
-        const double bc2 = 1.0 - pow((double)opt->beta2, (double)opt->step);
-        a.adam_step_size = (float)((double)opt->lr * sqrt(bc2) / bc1);
+        const double bc1 = 1.0 - pow(opt->beta1, (double)opt->step);
+        const double bc2 = 1.0 - pow(opt->beta2, (double)opt->step);
+        a.adam_step_size = (float)(opt->lr * sqrt(bc2) / bc1);
     }
     if (p.S == 0) {
         if (num_unique != nullptr) CTR_CUDA_OK(cudaMemsetAsync(num_unique, 0, sizeof(int64_t), stream));
         return CTR_OK;
     }
     // the long-run queue is rebuilt by every apply
-    CTR_CUDA_OK(cudaMemsetAsync(a.counters + 2, 0, sizeof(uint32_t), stream));
+    CTR_CUDA_OK(cudaMemsetAsync(a.counters + 2, 0, 2 * sizeof(uint32_t), stream));
     const int teams_per_block = kApplyThreads / team;
     int64_t blocks = (p.S + teams_per_block - 1) / teams_per_block;  // upper bound: one run per slot
     const int64_t cap = (int64_t)kNumSMs * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     note_launch(), emb_bwd_apply_kernel<<<(unsigned)blocks, kApplyThreads, 0, stream>>>(dg, a);
-    note_launch(), emb_bwd_apply_long_kernel<<<kNumSMs * 4, kApplyThreads, 0, stream>>>(dg, a);
+    note_launch(), emb_bwd_chunk_kernel<<<kNumSMs * 8, kApplyThreads, 0, stream>>>(dg, a);
+    note_launch(), emb_bwd_long_finish_kernel<<<kNumSMs, kApplyThreads, 0, stream>>>(dg, a);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }

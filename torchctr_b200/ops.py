@@ -187,7 +187,7 @@ def emb_bwd_plan(call: GroupCall, workspace: torch.Tensor) -> None:
 
 
 def make_opt(kind: str = "none", lr: float = 0.0, eps: float = 1e-10, betas=(0.9, 0.999), step: int = 1) -> _lib.Opt:
-    return _lib.Opt(_OPT_KINDS[kind], lr, eps, betas[0], betas[1], step)
+    return _lib.Opt(_OPT_KINDS[kind], step, lr, eps, betas[0], betas[1])
 
 
 def emb_bwd_apply(call: GroupCall, workspace: torch.Tensor, opt: _lib.Opt, uniq_feature=None, uniq_row=None,
