@@ -179,6 +179,62 @@ def workload_config(B, n_gpus):
             "l2": "inputs larger than L2: 2.4 GB of tables + 2.4 GB optimizer state, 4 distinct batches cycled"}
 
 
+def kernel_roofline(model, resident, B, dev, iters=12):
+    """Times ctr_emb_pool_fwd / ctr_emb_bwd_plan / ctr_emb_bwd_apply (fused Adagrad) of the D=16 table group one
+    launch at a time.  Algorithmic bytes per SURVEY.md 8(d): fwd 8S + 4DN + 4DB*F; update 8S + 4DB*F + 16DU."""
+    from torchctr_b200 import ops
+    from torchctr_b200.nn.embedding import _layout
+    names = model._names
+    tables = [model.embeddings[n] for n in names]
+    D = EMB_DIM
+    S = B * len(names)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    peak, peak_src = measured_peak_hbm()
+    acc = {"emb_pool_fwd": 0.0, "emb_bwd_plan": 0.0, "emb_bwd_apply": 0.0}
+    uniq_total = 0
+    for it in range(iters + 2):
+        feats, _ = resident[it % len(resident)]
+        entries = [(t, feats[n], None) for t, n in zip(tables, names)]
+        cols, width, stride, dense_col = _layout(entries, NUM_DENSE)
+        out = torch.empty(B, stride, device=dev)
+        gout = torch.randn(B, stride, device=dev)
+        specs = [ops.FeatureSpec(ids=feats[n], table=t.weight.data, num_rows=t.num_embeddings, D=D, out_col=c,
+                                 state0=t.opt_state0) for t, n, c in zip(tables, names, cols)]
+        fwd = ops.make_group(specs, B, out, stride, dense=feats["dense_features"], dense_col=dense_col, zero_from=width)
+        bwd = ops.make_group(specs, B, gout, stride)
+        ws = torch.empty(ops.emb_bwd_workspace_bytes(bwd) + 256, dtype=torch.uint8, device=dev)
+        opt = ops.make_opt("adagrad", lr=LR, eps=1e-10)
+        for name, fn in (("emb_pool_fwd", lambda: ops.emb_pool_fwd(fwd)), ("emb_bwd_plan", lambda: ops.emb_bwd_plan(bwd, ws)),
+                         ("emb_bwd_apply", lambda: ops.emb_bwd_apply(bwd, ws, opt))):
+            flush.fill_(it & 0xff)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                acc[name] += e0.elapsed_time(e1)
+        if it >= 2:
+            uniq_total += sum(int(torch.unique(feats[n]).numel()) for n in names)
+    U = uniq_total / iters
+    bytes_ = {"emb_pool_fwd": 8 * S + 4 * D * S + 4 * D * S, "emb_bwd_apply": 8 * S + 4 * D * S + 16 * D * U}
+    kern = {}
+    for name, total in acc.items():
+        ms = total / iters
+        kern[name] = {"ms_per_launch": ms}
+        if name in bytes_:
+            kern[name]["algorithmic_bytes"] = bytes_[name]
+            kern[name]["achieved_GBs"] = bytes_[name] / (ms * 1e-3) / 1e9
+            kern[name]["frac_of_peak"] = kern[name]["achieved_GBs"] / peak
+    dom = "emb_bwd_apply" if kern["emb_bwd_apply"]["ms_per_launch"] >= kern["emb_pool_fwd"]["ms_per_launch"] else "emb_pool_fwd"
+    k = kern[dom]
+    roofline = {"bound": "hbm", "kernel": dom + (" (sparse gradient reduce + fused Adagrad row update, 26 tables x D=16)"
+                                                 if dom == "emb_bwd_apply" else " (gather + pool + concat, 26 tables x D=16)"),
+                "achieved": k["achieved_GBs"], "peak": peak, "unit": "GB/s", "frac": k["frac_of_peak"], "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": k["algorithmic_bytes"],
+                "ms_per_launch": k["ms_per_launch"], "unique_rows_per_launch": U,
+                "timing": f"CUDA events around each launch on the launching stream, 256 MiB L2 flush before each, {iters} launches"}
+    return kern, roofline
+
+
 # ---------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
@@ -212,7 +268,7 @@ def run_ours(args):
     resident = [({k: v.to(dev) for k, v in f.items()}, l.to(dev)) for f, l in host]
     h2d = batch_bytes(host[0])
 
-    def step(batch, i):
+    def eager_step(batch, i):
         opt.zero_grad(set_to_none=True)
         loss = model.training_step(batch, i)
         loss.backward()
@@ -223,6 +279,18 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):                 # eager warm-up (also sizes workspaces / optimizer state)
+        eager_step(resident[i % nb], i)
+    launches_per_step = None
+    if args.no_graph:
+        step = eager_step
+    else:
+        from torchctr_b200.graph import GraphedTrainStep
+        l0 = ops.kernel_launches()
+        graphed = GraphedTrainStep(model, opt, resident[0], warmup=1)
+        launches_per_step = (ops.kernel_launches() - l0) // 2      # one eager warm-up + one captured step
+        step = lambda batch, i: graphed(batch)           # noqa: E731
 
     def timed(batches, steps, read_loss):
         barrier()
@@ -245,50 +313,26 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    for i in range(max(args.warmup, 3)):
+    for i in range(3):
         step(resident[i % nb], i)
     launches0 = ops.kernel_launches()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    with ops.KernelTimer() as kt:
-        ms = timed(resident, args.steps, read_loss=False)
-        spans = kt.summary()
-    launches = ops.kernel_launches() - launches0
-    clock_info = clocks.stop() if rank == 0 else None
+    ms = timed(resident, args.steps, read_loss=False)
+    launches = ops.kernel_launches() - launches0 if launches_per_step is None else launches_per_step * args.steps
     # end to end: pinned host buffers in, loss out, every step
     for i in range(3):
         step(host[i % nb], i)
     ms_e2e = timed(host, args.steps, read_loss=True)
+    clock_info = clocks.stop() if rank == 0 else None
 
     value = B * world * args.steps / (ms / 1e3)
     e2e = B * world * args.steps / (ms_e2e / 1e3)
 
-    # roofline of the embedding kernels: algorithmic bytes / CUDA-event time
-    S = B * len(CRITEO_VOCABS)
-    D = EMB_DIM
-    uniq = sum(int(torch.unique(f[f"C{i + 1}"]).numel()) for f, _ in resident for i in range(len(CRITEO_VOCABS))) / nb
-    peak, peak_src = measured_peak_hbm()
-    fwd_bytes = 8 * S + 4 * D * S + 4 * D * S            # ids + rows + pooled out   (D = 16 group)
-    upd_bytes = 8 * S + 4 * D * S + 16 * D * uniq        # ids + grad_out + Adagrad rmw of unique rows
-    kern = {}
-    for name, (calls, total_ms) in spans.items():
-        kern[name] = {"calls_per_step": calls / args.steps, "ms_per_step": total_ms / args.steps}
-    # two lookup groups per step (D=16 tables, D=1 first-order tables): scale bytes by the widths
-    fwd_bytes_all = fwd_bytes + (8 * S + 4 * S + 4 * S)
-    upd_bytes_all = upd_bytes + (8 * S + 4 * S + 16 * uniq)
-    roofline = None
-    if "emb_bwd_apply" in kern and "emb_pool_fwd" in kern:
-        cand = {"emb_bwd_apply (sparse grad scatter + fused Adagrad)": (upd_bytes_all, kern["emb_bwd_apply"]["ms_per_step"]),
-                "emb_pool_fwd (gather + pool + concat)": (fwd_bytes_all, kern["emb_pool_fwd"]["ms_per_step"])}
-        dom = max(cand, key=lambda k: cand[k][1])
-        for k, (bytes_, t) in cand.items():
-            kern[k.split(" ")[0]]["achieved_GBs"] = bytes_ / (t * 1e-3) / 1e9
-            kern[k.split(" ")[0]]["algorithmic_bytes_per_step"] = bytes_
-        b, t = cand[dom]
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": b / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": b / (t * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_step": b, "ms_per_step": t, "unique_rows_per_step": uniq}
+    # ---- kernel roofline: each embedding entry point timed alone, CUDA events on the launching stream,
+    # L2 flushed (256 MiB written) before every launch, on the step's real tensors
+    kern, roofline = kernel_roofline(model, resident, B, dev) if rank == 0 else ({}, None)
 
     line = {
         "metric": "train samples/s, Criteo-shape DeepFM", "value": value, "unit": "samples/s", "n_gpus": world,
@@ -296,7 +340,8 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, world),
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "kernels": kern, "roofline": roofline, "clocks": clock_info,
+        "gpu_launches": launches, "cuda_graph": not args.no_graph, "kernels": kern, "roofline": roofline,
+        "clocks": clock_info,
         "tower_matmul": "torch F.linear, TF32 tensor cores, fp32 accumulate",
     }
     if rank == 0:
@@ -319,6 +364,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

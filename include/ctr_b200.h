@@ -107,13 +107,24 @@ typedef struct ctr_group {
     uint32_t *status;        /* device status word (CTR_STATUS_*), may be NULL               */
 } ctr_group_t;
 
+/* Per-step scalars of the row update as the kernels consume them (fp32). */
+typedef struct ctr_hyper {
+    float lr, eps, one_minus_beta1, one_minus_beta2, adam_step_size;
+} ctr_hyper_t;
+
 typedef struct ctr_opt {
     int32_t kind;            /* CTR_OPT_*                                                    */
     int32_t step;            /* Adam bias-correction step (1-based)                          */
     double lr;               /* already decayed by the host if a schedule is used            */
     double eps;
     double beta1, beta2;     /* Adam (doubles: torch forms 1 - beta in double precision)     */
+    const ctr_hyper_t *device_hyper; /* optional DEVICE copy of ctr_opt_hyper()'s output, read by the kernels
+                                        at run time instead of the values above: lets a captured CUDA graph
+                                        follow lr schedules / Adam steps without re-capture               */
 } ctr_opt_t;
+
+/* host helper: the fp32 scalars the kernels use for `opt` (what device_hyper must hold) */
+void ctr_opt_hyper(const ctr_opt_t *opt, ctr_hyper_t *out);
 
 const char *ctr_last_error_string(void);
 int ctr_abi_version(void);

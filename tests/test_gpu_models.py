@@ -262,3 +262,47 @@ def test_model_with_growing_vocab_and_hashed_feature():
             got_first = model._first_linear(model._lookup(feats, feats["dense_features"], False), model.tower[0])
         close(got_first, ref_logits, TOWER_RTOL)
         logits.sum().backward()
+
+
+@pytest.mark.parametrize("opt_name", ["adagrad", "adam"])
+def test_graphed_train_step_equals_eager(opt_name):
+    """Whole-step CUDA graph replay == eager launches (same kernels), incl. Adam's step-dependent
+    scalars, which reach the kernels through the device hyper-parameter tensor."""
+    from torchctr_b200.graph import GraphedTrainStep
+    from torchctr_b200.models import DeepFM
+    gen = torch.Generator().manual_seed(17)
+    fc, f0, l0 = _criteo_like(gen, 1024, 5, 300, 16, 3)
+    batches = [(f0, l0)]
+    for _ in range(3):
+        feats = {k: (torch.randint(0, 300, v.shape, generator=gen) if v.dtype == torch.int64
+                     else torch.randn(v.shape, generator=gen)) for k, v in f0.items()}
+        batches.append((feats, (torch.rand(1024, 1, generator=gen) < 0.25).float()))
+    torch.manual_seed(1)
+    a = no_dropout(DeepFM(fc, [32, 16])).cuda().train()
+    b = no_dropout(DeepFM(fc, [32, 16])).cuda().train()
+    b.load_state_dict(a.state_dict())
+
+    def make_opt(m):
+        if opt_name == "adagrad":
+            o = torch.optim.Adagrad(m.dense_parameters(), lr=0.05)
+            m.bind_optimizer(o, kind="adagrad")
+        else:
+            o = torch.optim.Adam(m.dense_parameters(), lr=0.01, capturable=True)
+            m.bind_optimizer(o, kind="adam")
+        return o
+
+    oa, ob = make_opt(a), make_opt(b)
+    # the constructor runs `warmup` real steps on the example batch before capturing
+    graphed = GraphedTrainStep(b, ob, batches[0], warmup=1)
+    oa.zero_grad(); a.training_step(batches[0], 0).backward(); oa.step()
+    for i, batch in enumerate(batches):
+        oa.zero_grad()
+        la = a.training_step(batch, i)
+        la.backward()
+        oa.step()
+        lb = graphed(batch)
+        close(lb, la, 1e-5)
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        if sa[k].dtype.is_floating_point:
+            close(sb[k], sa[k], 1e-5)

@@ -51,7 +51,12 @@ class Group(C.Structure):
 
 class Opt(C.Structure):
     _fields_ = [("kind", C.c_int32), ("step", C.c_int32), ("lr", C.c_double), ("eps", C.c_double),
-                ("beta1", C.c_double), ("beta2", C.c_double)]
+                ("beta1", C.c_double), ("beta2", C.c_double), ("device_hyper", C.c_void_p)]
+
+
+class Hyper(C.Structure):
+    _fields_ = [("lr", C.c_float), ("eps", C.c_float), ("one_minus_beta1", C.c_float),
+                ("one_minus_beta2", C.c_float), ("adam_step_size", C.c_float)]
 
 
 _P = C.c_void_p
@@ -60,6 +65,7 @@ _SIGNATURES = {
     "ctr_last_error_string": (C.c_char_p, []),
     "ctr_abi_version": (C.c_int, []),
     "ctr_kernel_launches": (C.c_int64, []),
+    "ctr_opt_hyper": (None, [C.POINTER(Opt), C.POINTER(Hyper)]),
     "ctr_emb_pool_fwd": (C.c_int, [C.POINTER(Group), _P]),
     "ctr_hash_bucket_i64": (C.c_int, [_P, C.c_int64, C.c_uint32, C.c_uint32, _P, _P]),
     "ctr_rows_gather": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P, _P]),

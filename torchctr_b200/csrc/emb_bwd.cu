@@ -14,7 +14,8 @@
 
 namespace ctr {
 
-constexpr int kLongRun = 32;
+constexpr int kTeamRun = 8;    // runs up to this length: one team of lanes (short-run kernel)
+constexpr int kLongRun = 256;  // up to this length: one warp per run; longer: chunked block reduction
 constexpr int kApplyThreads = 256;
 
 // ---- workspace layout ---------------------------------------------------------------------
@@ -25,9 +26,9 @@ struct PlanLayout {
     // offsets in bytes from the workspace base
     int64_t counters, keys_a, keys_b, vals_a, vals_b, counts, spine, run_start;
     // apply-time scratch (rebuilt by every apply; sized by the group being applied)
-    int64_t long_list, long_cbase, chunk_q, partials, max_long, max_chunks, row_floats, total;
+    int64_t med_list, long_list, long_cbase, chunk_q, partials, max_med, max_long, max_chunks, row_floats, total;
 };
-// counters (u32): [0] runs, [1] unique valid rows, [2] long-run queue length, [3] chunk queue length
+// counters (u32): [0] runs, [1] unique valid rows, [2] long-run queue, [3] chunk queue, [4] medium-run queue
 constexpr int kNumCounters = 8;
 constexpr int kChunk = 1024;   // sorted positions reduced by one block
 
@@ -61,8 +62,10 @@ static PlanLayout plan_layout(const DevGroup &g) {
     int row_floats = 4;  // one float4 slot per lane of the widest row, whatever the lane width
     for (int i = 0; i < g.num_features; ++i) row_floats = max(row_floats, g.f[i].G * 4);
     p.row_floats = row_floats;
+    p.max_med = S / (kTeamRun + 1) + 2;
     p.max_long = S / (kLongRun + 1) + 2;
     p.max_chunks = p.max_long + S / kChunk + 2;
+    p.med_list = off; off = align256(off + p.max_med * 4);
     p.long_list = off; off = align256(off + p.max_long * 4);
     p.long_cbase = off; off = align256(off + p.max_long * 4);
     p.chunk_q = off; off = align256(off + p.max_chunks * 4);
@@ -96,6 +99,7 @@ struct ApplyArgs {
     const uint32_t *vals;       // sorted with the keys: slot inside the feature (bag * L + l)
     const uint32_t *run_start;
     uint32_t *counters;
+    uint32_t *med_list;         // [q] -> run (medium runs, one warp each)
     uint32_t *long_list;        // [q] -> run
     uint32_t *long_cbase;       // [q] -> first chunk of the run
     uint32_t *chunk_q;          // [chunk] -> q
@@ -107,7 +111,8 @@ struct ApplyArgs {
     int64_t row_grad_stride;
     int64_t *num_unique;
     int kind;
-    float lr, eps, one_minus_beta1, one_minus_beta2, adam_step_size;
+    ctr_hyper_t h;              // used when hyper_dev == nullptr
+    const ctr_hyper_t *hyper_dev;  // device copy read at run time (CUDA-graph replays see new values)
     int team;                   // lanes per run in the short-run kernel (max G of the group)
 };
 
@@ -151,9 +156,9 @@ __device__ __forceinline__ float adagrad_elem(float w, float &s, float gr, float
     return w - lr * __fdiv_rn(gr, __fsqrt_rn(s) + eps);
 }
 __device__ __forceinline__ float adam_elem(float w, float &m, float &v, float gr, const ApplyArgs &a) {
-    m = m + (gr - m) * a.one_minus_beta1;
-    v = v + (gr * gr - v) * a.one_minus_beta2;
-    return w - a.adam_step_size * __fdiv_rn(m, __fsqrt_rn(v) + a.eps);
+    m = m + (gr - m) * a.h.one_minus_beta1;
+    v = v + (gr * gr - v) * a.h.one_minus_beta2;
+    return w - a.h.adam_step_size * __fdiv_rn(m, __fsqrt_rn(v) + a.h.eps);
 }
 
 // Lanes [0, G) of a team hold the summed gradient of (feature f, row); mask names the team.
@@ -179,7 +184,7 @@ __device__ __forceinline__ void update_row(const DevGroup &g, const DevFeature &
         float sq = col_ok ? (f.vec == 4 ? gr.x * gr.x + gr.y * gr.y + gr.z * gr.z + gr.w * gr.w : gr.x * gr.x) : 0.f;
         for (int off = 1; off < team_lanes; off <<= 1) sq += __shfl_xor_sync(mask, sq, off);
         const float acc = f.state0[row] + sq / (float)f.D;
-        rowwise_denominator = __fsqrt_rn(acc) + a.eps;
+        rowwise_denominator = __fsqrt_rn(acc) + a.h.eps;
         __syncwarp(mask);
         if (g_lane == 0) f.state0[row] = acc;
     }
@@ -188,19 +193,19 @@ __device__ __forceinline__ void update_row(const DevGroup &g, const DevFeature &
     if (f.vec == 4) {
         float4 w = *reinterpret_cast<float4 *>(f.table + off);
         if (a.kind == CTR_OPT_SGD) {
-            w.x -= a.lr * gr.x; w.y -= a.lr * gr.y; w.z -= a.lr * gr.z; w.w -= a.lr * gr.w;
+            w.x -= a.h.lr * gr.x; w.y -= a.h.lr * gr.y; w.z -= a.h.lr * gr.z; w.w -= a.h.lr * gr.w;
         } else if (a.kind == CTR_OPT_ADAGRAD) {
             float4 s = *reinterpret_cast<float4 *>(f.state0 + off);
-            w.x = adagrad_elem(w.x, s.x, gr.x, a.lr, a.eps);
-            w.y = adagrad_elem(w.y, s.y, gr.y, a.lr, a.eps);
-            w.z = adagrad_elem(w.z, s.z, gr.z, a.lr, a.eps);
-            w.w = adagrad_elem(w.w, s.w, gr.w, a.lr, a.eps);
+            w.x = adagrad_elem(w.x, s.x, gr.x, a.h.lr, a.h.eps);
+            w.y = adagrad_elem(w.y, s.y, gr.y, a.h.lr, a.h.eps);
+            w.z = adagrad_elem(w.z, s.z, gr.z, a.h.lr, a.h.eps);
+            w.w = adagrad_elem(w.w, s.w, gr.w, a.h.lr, a.h.eps);
             *reinterpret_cast<float4 *>(f.state0 + off) = s;
         } else if (a.kind == CTR_OPT_ROWWISE_ADAGRAD) {
-            w.x -= a.lr * __fdiv_rn(gr.x, rowwise_denominator);
-            w.y -= a.lr * __fdiv_rn(gr.y, rowwise_denominator);
-            w.z -= a.lr * __fdiv_rn(gr.z, rowwise_denominator);
-            w.w -= a.lr * __fdiv_rn(gr.w, rowwise_denominator);
+            w.x -= a.h.lr * __fdiv_rn(gr.x, rowwise_denominator);
+            w.y -= a.h.lr * __fdiv_rn(gr.y, rowwise_denominator);
+            w.z -= a.h.lr * __fdiv_rn(gr.z, rowwise_denominator);
+            w.w -= a.h.lr * __fdiv_rn(gr.w, rowwise_denominator);
         } else {  // CTR_OPT_ADAM
             float4 m = *reinterpret_cast<float4 *>(f.state0 + off);
             float4 v = *reinterpret_cast<float4 *>(f.state1 + off);
@@ -215,13 +220,13 @@ __device__ __forceinline__ void update_row(const DevGroup &g, const DevFeature &
     } else {
         float w = f.table[off];
         if (a.kind == CTR_OPT_SGD) {
-            w -= a.lr * gr.x;
+            w -= a.h.lr * gr.x;
         } else if (a.kind == CTR_OPT_ADAGRAD) {
             float s = f.state0[off];
-            w = adagrad_elem(w, s, gr.x, a.lr, a.eps);
+            w = adagrad_elem(w, s, gr.x, a.h.lr, a.h.eps);
             f.state0[off] = s;
         } else if (a.kind == CTR_OPT_ROWWISE_ADAGRAD) {
-            w -= a.lr * __fdiv_rn(gr.x, rowwise_denominator);
+            w -= a.h.lr * __fdiv_rn(gr.x, rowwise_denominator);
         } else {
             float m = f.state0[off], v = f.state1[off];
             w = adam_elem(w, m, v, gr.x, a);
@@ -234,7 +239,9 @@ __device__ __forceinline__ void update_row(const DevGroup &g, const DevFeature &
 
 // Short runs: one team of a.team lanes per run.
 __global__ void __launch_bounds__(kApplyThreads)
-    emb_bwd_apply_kernel(const __grid_constant__ DevGroup g, const __grid_constant__ ApplyArgs a) {
+    emb_bwd_apply_kernel(const __grid_constant__ DevGroup g, const __grid_constant__ ApplyArgs a_in) {
+    ApplyArgs a = a_in;
+    if (a.hyper_dev != nullptr) a.h = *a.hyper_dev;
     const int TG = a.team;
     const int lane = threadIdx.x & 31;
     const int t = lane & (TG - 1);
@@ -246,6 +253,10 @@ __global__ void __launch_bounds__(kApplyThreads)
     const int64_t team_global = ((int64_t)blockIdx.x * kApplyThreads + threadIdx.x) / TG;
     for (int64_t run = team_global; run < num_runs; run += teams_total) {
         const uint32_t s = a.run_start[run], e = a.run_start[run + 1];
+        if (e - s > (uint32_t)kTeamRun && e - s <= (uint32_t)kLongRun) {  // medium run: one warp
+            if (t == 0) a.med_list[atomicAdd(&a.counters[4], 1u)] = (uint32_t)run;
+            continue;
+        }
         if (e - s > (uint32_t)kLongRun) {  // hot row: hand it to the chunked block reduction
             const uint32_t nch = (e - s + kChunk - 1) / kChunk;
             uint32_t q = 0, cbase = 0;
@@ -289,6 +300,64 @@ __global__ void __launch_bounds__(kApplyThreads)
             }
         }
         update_row(g, f, a, (uint32_t)run, fi, row, g_lane, col_ok, acc, mask, TG);
+    }
+}
+
+// Medium runs: one warp per queued run; 32 / G row slots stride the run four positions at a time,
+// xor-shuffles fold the slots, lanes [0, G) update the row.
+__global__ void __launch_bounds__(kApplyThreads)
+    emb_bwd_medium_kernel(const __grid_constant__ DevGroup g, const __grid_constant__ ApplyArgs a_in) {
+    ApplyArgs a = a_in;
+    if (a.hyper_dev != nullptr) a.h = *a.hyper_dev;
+    const int lane = threadIdx.x & 31;
+    const uint32_t nmed = a.counters[4];
+    const int64_t warps_total = (int64_t)gridDim.x * (kApplyThreads / kWarp);
+    for (int64_t q = (int64_t)blockIdx.x * (kApplyThreads / kWarp) + (threadIdx.x >> 5); q < nmed; q += warps_total) {
+        const uint32_t run = a.med_list[q];
+        const uint32_t s = a.run_start[run], e = a.run_start[run + 1];
+        const uint32_t key = a.keys[s];
+        const int fi = find_feature(g, key);
+        const DevFeature &f = g.f[fi];
+        const int G = f.G;
+        const int g_lane = lane & (G - 1);
+        const uint32_t slot_id = lane / G;
+        const uint32_t nslots = kWarp / G;
+        const bool col_ok = g_lane * f.vec < f.D;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t p0 = s + slot_id; p0 < e; p0 += 4 * nslots) {
+            uint32_t bag[4];
+            float coef[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t p = p0 + j * nslots;
+                bag[j] = 0; coef[j] = 0.f;
+                if (p < e) {
+                    const uint32_t slot = a.vals[p];
+                    bag[j] = slot / (uint32_t)f.L;
+                    coef[j] = slot_coef(f, slot, bag[j]);
+                }
+            }
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col_ok && p0 + j * nslots < e) v[j] = load_grad_part(g, f, bag[j], g_lane);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc.x = fmaf(coef[j], v[j].x, acc.x);
+                acc.y = fmaf(coef[j], v[j].y, acc.y);
+                acc.z = fmaf(coef[j], v[j].z, acc.z);
+                acc.w = fmaf(coef[j], v[j].w, acc.w);
+            }
+        }
+        for (int off = G; off < kWarp; off <<= 1) {
+            acc.x += __shfl_xor_sync(kFull, acc.x, off);
+            acc.y += __shfl_xor_sync(kFull, acc.y, off);
+            acc.z += __shfl_xor_sync(kFull, acc.z, off);
+            acc.w += __shfl_xor_sync(kFull, acc.w, off);
+        }
+        update_row(g, f, a, run, fi, key - f.row_base, lane, lane < G && col_ok, acc, kFull, G);
     }
 }
 
@@ -358,7 +427,9 @@ __global__ void __launch_bounds__(kApplyThreads)
 
 // Long runs, stage 2: one team per queued run adds its chunk partials in chunk order and updates the row.
 __global__ void __launch_bounds__(kApplyThreads)
-    emb_bwd_long_finish_kernel(const __grid_constant__ DevGroup g, const __grid_constant__ ApplyArgs a) {
+    emb_bwd_long_finish_kernel(const __grid_constant__ DevGroup g, const __grid_constant__ ApplyArgs a_in) {
+    ApplyArgs a = a_in;
+    if (a.hyper_dev != nullptr) a.h = *a.hyper_dev;
     const int TG = a.team;
     const int lane = threadIdx.x & 31;
     const int t = lane & (TG - 1);
@@ -389,6 +460,19 @@ __global__ void __launch_bounds__(kApplyThreads)
 }  // namespace ctr
 
 using namespace ctr;
+
+extern "C" void ctr_opt_hyper(const ctr_opt_t *opt, ctr_hyper_t *out) {
+    out->lr = (float)opt->lr;
+    out->eps = (float)opt->eps;
+    out->one_minus_beta1 = (float)(1.0 - opt->beta1);   // torch forms 1 - beta in double, then rounds
+    out->one_minus_beta2 = (float)(1.0 - opt->beta2);
+    out->adam_step_size = 0.f;
+    if (opt->kind == CTR_OPT_ADAM && opt->step >= 1) {
+        const double bc1 = 1.0 - pow(opt->beta1, (double)opt->step);
+        const double bc2 = 1.0 - pow(opt->beta2, (double)opt->step);
+        out->adam_step_size = (float)(opt->lr * sqrt(bc2) / bc1);
+    }
+}
 
 extern "C" int64_t ctr_emb_bwd_workspace_bytes(const ctr_group_t *group) {
     static thread_local DevGroup dg;
@@ -474,6 +558,7 @@ extern "C" int ctr_emb_bwd_apply(const ctr_group_t *group, void *workspace, cons
     a.vals = reinterpret_cast<const uint32_t *>(ws + (p.sorted_in_b ? p.vals_b : p.vals_a));
     a.run_start = reinterpret_cast<const uint32_t *>(ws + p.run_start);
     a.counters = reinterpret_cast<uint32_t *>(ws + p.counters);
+    a.med_list = reinterpret_cast<uint32_t *>(ws + p.med_list);
     a.long_list = reinterpret_cast<uint32_t *>(ws + p.long_list);
     a.long_cbase = reinterpret_cast<uint32_t *>(ws + p.long_cbase);
     a.chunk_q = reinterpret_cast<uint32_t *>(ws + p.chunk_q);
@@ -485,29 +570,23 @@ extern "C" int ctr_emb_bwd_apply(const ctr_group_t *group, void *workspace, cons
     a.row_grad_stride = row_grad_stride;
     a.num_unique = num_unique;
     a.kind = opt->kind;
-    a.lr = (float)opt->lr;
-    a.eps = (float)opt->eps;
-    a.one_minus_beta1 = (float)(1.0 - opt->beta1);   // torch forms 1 - beta in double, then rounds
-    a.one_minus_beta2 = (float)(1.0 - opt->beta2);
+    ctr_opt_hyper(opt, &a.h);
+    a.hyper_dev = opt->device_hyper;
     a.team = team;
-    if (opt->kind == CTR_OPT_ADAM) {
-        CTR_REQUIRE(opt->step >= 1, "Adam step must be >= 1");
-        const double bc1 = 1.0 - pow(opt->beta1, (double)opt->step);
-        const double bc2 = 1.0 - pow(opt->beta2, (double)opt->step);
-        a.adam_step_size = (float)(opt->lr * sqrt(bc2) / bc1);
-    }
+    if (opt->kind == CTR_OPT_ADAM) CTR_REQUIRE(opt->step >= 1, "Adam step must be >= 1");
     if (p.S == 0) {
         if (num_unique != nullptr) CTR_CUDA_OK(cudaMemsetAsync(num_unique, 0, sizeof(int64_t), stream));
         return CTR_OK;
     }
     // the long-run queue is rebuilt by every apply
-    CTR_CUDA_OK(cudaMemsetAsync(a.counters + 2, 0, 2 * sizeof(uint32_t), stream));
+    CTR_CUDA_OK(cudaMemsetAsync(a.counters + 2, 0, 3 * sizeof(uint32_t), stream));
     const int teams_per_block = kApplyThreads / team;
     int64_t blocks = (p.S + teams_per_block - 1) / teams_per_block;  // upper bound: one run per slot
     const int64_t cap = (int64_t)kNumSMs * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     note_launch(), emb_bwd_apply_kernel<<<(unsigned)blocks, kApplyThreads, 0, stream>>>(dg, a);
+    note_launch(), emb_bwd_medium_kernel<<<kNumSMs * 8, kApplyThreads, 0, stream>>>(dg, a);
     note_launch(), emb_bwd_chunk_kernel<<<kNumSMs * 8, kApplyThreads, 0, stream>>>(dg, a);
     note_launch(), emb_bwd_long_finish_kernel<<<kNumSMs, kApplyThreads, 0, stream>>>(dg, a);
     CTR_CUDA_OK(cudaGetLastError());

@@ -1,0 +1,77 @@
+"""Whole-step CUDA graphs: forward + backward + fused table update + dense optimizer captured once,
+replayed per batch.  The reference loop (``torchctr/trainer.py:291-303``) issues ~150 kernel
+launches per step from Python; at B200 speeds the step is launch-bound, a graph replay is not.
+
+    step = GraphedTrainStep(model, optimizer, example_batch)
+    loss = step(batch)            # batch: host (pinned or not) or device tensors, same shapes
+
+Inputs are staged into static device buffers (asynchronous copies when the batch sits in pinned
+host memory), the loss is a static device scalar.  Table hyper-parameters (lr
+schedule, Adam step) reach the kernels through a device tensor refreshed before each replay.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class GraphedTrainStep:
+    def __init__(self, model, optimizer, example_batch, warmup: int = 3):
+        feats, labels = example_batch
+        self.model, self.optimizer = model, optimizer
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedTrainStep needs the model on a CUDA device")
+        for m in model.modules():
+            if getattr(m, "index_kind", None) == "vocab":
+                raise RuntimeError("growing vocabularies read the table size on the host every step; "
+                                   "such models cannot be captured into a CUDA graph")
+        self.device = dev
+        # one packed static buffer: every tensor of the batch is a view into it
+        self._keys = [k for k in feats if torch.is_tensor(feats[k])]
+        tensors = [feats[k] for k in self._keys] + [labels]
+        self._layout, off = [], 0
+        for t in tensors:
+            nbytes = t.numel() * t.element_size()
+            self._layout.append((off, nbytes, t.dtype, tuple(t.shape)))
+            off = (off + nbytes + 255) // 256 * 256
+        self._nbytes = off
+        self._static = torch.empty(off, dtype=torch.uint8, device=dev)
+        views = [self._static[o:o + n].view(dt).view(shape) for o, n, dt, shape in self._layout]
+        self._views = views
+        self.static_feats = dict(zip(self._keys, views[:-1]))
+        self.static_labels = views[-1]
+        self._bindings = [g.binding for g in getattr(model, "_groups", []) if g.binding is not None]
+        for b in self._bindings:
+            b.enable_device_hyper(dev)
+        self._stage(example_batch)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._eager_step()
+        torch.cuda.synchronize(dev)
+
+    def _eager_step(self):
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = self.model.training_step((self.static_feats, self.static_labels), 0)
+        loss.backward()
+        self.optimizer.step()
+        return loss
+
+    def _stage(self, batch):
+        feats, labels = batch
+        tensors = [feats[k] for k in self._keys] + [labels]
+        for v, t in zip(self._views, tensors):               # async from pinned host memory, D2D otherwise
+            v.copy_(t, non_blocking=True)
+
+    def __call__(self, batch) -> torch.Tensor:
+        self._stage(batch)
+        for b in self._bindings:
+            b.advance()
+        self.graph.replay()
+        return self.static_loss

@@ -5,8 +5,8 @@ from __future__ import annotations
 
 import torch.nn as nn
 
-from ..nn.embedding import EmbeddingTable, PooledLookupGroup
-from ..nn.interaction import fm_interaction
+from ..nn.embedding import EmbeddingTable, PlanLink, PooledLookupGroup
+from ..nn.interaction import fm_interaction_passthrough
 from .base import CTRModelBase, make_tower
 
 
@@ -31,10 +31,12 @@ class DeepFM(CTRModelBase):
     def forward(self, input_feats):
         self._grow_vocabularies(input_feats)
         dense = self.dense_block(input_feats)
-        x = self._lookup(input_feats, dense, self.training)                  # [B, pad4(F*D + Nd)]
-        first = self._linear_lookup(input_feats, None, self.training)        # [B, pad4(F)]
+        link = PlanLink() if self.training else None                         # same ids: one backward sort for both
+        x = self._lookup(input_feats, dense, self.training, link)            # [B, pad4(F*D + Nd)]
+        first = self._linear_lookup(input_feats, None, self.training, link)  # [B, pad4(F)]
         nf = len(self._names)
-        logit = fm_interaction(x, nf, self._dim, first, nf) + self._run_tower(x)
+        x, fm = fm_interaction_passthrough(x, nf, self._dim, first, nf)
+        logit = fm + self._run_tower(x)
         if self.linear_dense is not None:
             c0 = self._sparse_width
             logit = logit + self.linear_dense(x[:, c0:c0 + self._dense_width])

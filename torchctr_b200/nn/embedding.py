@@ -143,15 +143,42 @@ class SparseOptimizerBinding:
             raise ValueError("fused table update supports neither weight_decay nor momentum "
                              "(a touched-rows-only update cannot reproduce them)")
 
-    def next_opt(self) -> _lib.Opt:
-        self.step += 1
+    def _opt_for_step(self, step: int, device_hyper=None) -> _lib.Opt:
         g = self.group
         lr = float(g["lr"])
         if self.kind in ("adagrad", "rowwise_adagrad"):
-            lr = lr / (1.0 + (self.step - 1) * float(g.get("lr_decay", 0.0)))
+            lr = lr / (1.0 + (step - 1) * float(g.get("lr_decay", 0.0)))
         eps = float(g.get("eps", 1e-10 if self.kind != "adam" else 1e-8))
         betas = g.get("betas", (0.9, 0.999))
-        return ops.make_opt(self.kind, lr, eps, (float(betas[0]), float(betas[1])), self.step)
+        return ops.make_opt(self.kind, lr, eps, (float(betas[0]), float(betas[1])), step, device_hyper)
+
+    def next_opt(self) -> _lib.Opt:
+        """Hyper-parameters of the next fused update.  Eager mode: passed by value.  Graph mode
+        (``enable_device_hyper``): the kernels read them from a device tensor that ``advance``
+        refreshes before every replay, so lr schedules and Adam's step keep working."""
+        if self._hyper_dev is not None:
+            if torch.cuda.is_current_stream_capturing():
+                return self._opt_for_step(max(self.step, 1), self._hyper_dev)
+            self.advance()
+            return self._opt_for_step(self.step, self._hyper_dev)
+        self.step += 1
+        return self._opt_for_step(self.step)
+
+    _hyper_dev = None
+    _hyper_last = None
+
+    def enable_device_hyper(self, device):
+        if self._hyper_dev is None:
+            self._hyper_dev = torch.zeros(5, dtype=torch.float32, device=device)
+        return self
+
+    def advance(self):
+        """One optimizer step further: refresh the device copy of the scalars if they changed."""
+        self.step += 1
+        vals = ops.opt_hyper(self._opt_for_step(self.step))
+        if vals != self._hyper_last:
+            self._hyper_dev.copy_(torch.tensor(vals, dtype=torch.float32).pin_memory(), non_blocking=True)
+            self._hyper_last = vals
 
     def initial_accumulator_value(self) -> float:
         return float(self.group.get("initial_accumulator_value", 0.0))
@@ -165,9 +192,13 @@ class _Workspace:
     def get(cls, device, nbytes: int) -> torch.Tensor:
         buf = cls._bufs.get(device)
         if buf is None or buf.numel() < nbytes:
+            if buf is not None:
+                cls._retired.append(buf)      # a captured CUDA graph may still point into it
             buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
             cls._bufs[device] = buf
         return buf
+
+    _retired: list = []
 
 
 class _PooledLookupFn(torch.autograd.Function):
@@ -190,9 +221,10 @@ class _PooledLookupFn(torch.autograd.Function):
 class _LookupCall:
     """One forward/backward of a group of tables over one batch."""
 
-    def __init__(self, entries, dense_width, layout, binding, training):
+    def __init__(self, entries, dense_width, layout, binding, training, plan_link=None):
         # entries: [(table module, ids [B, L] i64, id_weight or None)]
         self.entries = entries
+        self.plan_link = plan_link
         self.layout = layout            # (out_cols, width, stride, dense_col)
         self.out_cols, self.width, self.stride, self.dense_col = layout
         self.dense_width = dense_width
@@ -226,6 +258,8 @@ class _LookupCall:
         call = ops.make_group(self._specs([w.detach() for w in weights], False), B, out, self.stride,
                               dense=dense, dense_col=self.dense_col, zero_from=zero_from, status=self.status)
         ops.emb_pool_fwd(call)
+        if self.plan_link is not None and self.training:     # both linked forwards run before any backward
+            self.plan_link.nbytes = max(self.plan_link.nbytes, ops.emb_bwd_workspace_bytes(call))
         return out
 
     def run_backward(self, grad_out):
@@ -242,8 +276,21 @@ class _LookupCall:
                 m._ensure_state(self.binding.kind, self.binding.initial_accumulator_value())
         tables = [m.weight.data for m in mods]
         call = ops.make_group(self._specs(tables, fused), self.B, grad_out, grad_out.shape[1])
-        ws = _Workspace.get(dev, ops.emb_bwd_workspace_bytes(call))
-        ops.emb_bwd_plan(call, ws)
+        link = self.plan_link
+        if link is None:
+            ws = _Workspace.get(dev, ops.emb_bwd_workspace_bytes(call))
+            ops.emb_bwd_plan(call, ws)
+        else:
+            # the sort / run list depends on the ids only: tables that share them (DeepFM's first-order
+            # weights next to its embeddings) share one plan per step
+            need = ops.emb_bwd_workspace_bytes(call)
+            link.nbytes = max(link.nbytes, need)
+            if link.ws is None:
+                link.ws = torch.empty(max(link.nbytes, need) + 256, dtype=torch.uint8, device=dev)
+                ops.emb_bwd_plan(call, link.ws)
+            elif link.ws.numel() < need:
+                raise RuntimeError("shared backward plan: workspace too small; call PlanLink.reserve first")
+            ws = link.ws
         if fused:
             ops.emb_bwd_apply(call, ws, self.binding.next_opt())
             return [None] * len(mods)
@@ -280,8 +327,17 @@ def _layout(entries, dense_width, align=4):
     return cols, width, stride, dense_col
 
 
+class PlanLink:
+    """Shared by the lookups of ONE step whose ids, index mapping and table sizes are identical: the
+    first backward builds the sort / run plan, the others reuse it.  Create one per forward."""
+
+    def __init__(self, nbytes: int = 0):
+        self.ws = None
+        self.nbytes = nbytes
+
+
 def pooled_lookup(entries, dense: torch.Tensor | None = None, binding: SparseOptimizerBinding | None = None,
-                  training: bool = False) -> torch.Tensor:
+                  training: bool = False, plan_link: PlanLink | None = None) -> torch.Tensor:
     """Pools every (table, ids [B, L], id_weight) entry and concatenates them with ``dense``.
 
     Returns f32 ``[B, stride]`` with ``stride`` = total width rounded up to 4 floats; columns past
@@ -310,7 +366,7 @@ def pooled_lookup(entries, dense: torch.Tensor | None = None, binding: SparseOpt
         dense_width = dense.shape[1]
     # a launch group carries at most MAX_FEATURES tables and a 32-bit key space
     if len(prepared) <= _lib.MAX_FEATURES and sum(m.num_embeddings for m, _, _ in prepared) < 2 ** 32 - 1:
-        call = _LookupCall(prepared, dense_width, _layout(prepared, dense_width), binding, training)
+        call = _LookupCall(prepared, dense_width, _layout(prepared, dense_width), binding, training, plan_link)
         return _PooledLookupFn.apply(call, dense, *[m.weight for m, _, _ in prepared])
     raise NotImplementedError("split the features into several pooled_lookup calls "
                               f"(more than {_lib.MAX_FEATURES} tables or >= 2^32 rows in one group)")
@@ -328,7 +384,7 @@ class PooledLookupGroup:
         self.binding = SparseOptimizerBinding(optimizer, [self.tables[n] for n in self.names], kind)
         return self.binding
 
-    def __call__(self, feats: dict, dense: torch.Tensor | None, training: bool) -> torch.Tensor:
+    def __call__(self, feats: dict, dense: torch.Tensor | None, training: bool, plan_link: PlanLink | None = None) -> torch.Tensor:
         entries = [(self.tables[n], feats[n], feats.get(n + "_weight") if self.tables[n].use_id_weight else None)
                    for n in self.names]
-        return pooled_lookup(entries, dense, self.binding, training)
+        return pooled_lookup(entries, dense, self.binding, training, plan_link)

@@ -41,6 +41,42 @@ def fm_interaction(x: torch.Tensor, num_fields: int, dim: int, first: torch.Tens
     return _FMFn.apply(x, first, num_fields, dim, num_first)
 
 
+class _FMPassFn(torch.autograd.Function):
+    """FM term + pass-through of x: the tower reads the alias ``x_t``, so in backward the gradient of
+    the tower arrives here and the FM gradient is ACCUMULATED into it in place -- no zero-filled
+    gradient buffer and no extra ``add`` pass over [B, F*D]."""
+
+    @staticmethod
+    def forward(ctx, x, first, num_fields, dim, num_first):
+        ctx.save_for_backward(x)
+        ctx.meta = (num_fields, dim, num_first, None if first is None else first.shape)
+        f = None if first is None else first[:, :num_first]
+        return x, ops.fm_fwd(x, num_fields, dim, first=f)
+
+    @staticmethod
+    def backward(ctx, g_x, g_fm):
+        (x,) = ctx.saved_tensors
+        num_fields, dim, num_first, first_shape = ctx.meta
+        gfirst = None
+        if first_shape is not None:
+            gfirst = torch.zeros(first_shape, dtype=torch.float32, device=x.device) \
+                if first_shape[1] > num_first else torch.empty(first_shape, dtype=torch.float32, device=x.device)
+        if g_fm is None:
+            return g_x, (None if gfirst is None else gfirst.zero_()), None, None, None
+        g_fm = g_fm.contiguous()
+        if g_x is None:
+            g_x = torch.zeros_like(x)
+        elif g_x.stride(1) != 1 or g_x.stride(0) != x.shape[1]:
+            g_x = g_x.contiguous()
+        ops.fm_bwd(x, num_fields, dim, g_fm, g_x, True, None if gfirst is None else gfirst[:, :num_first])
+        return g_x, gfirst, None, None, None
+
+
+def fm_interaction_passthrough(x, num_fields: int, dim: int, first=None, num_first: int = 0):
+    """Returns ``(x_alias, fm)``: feed ``x_alias`` to every other consumer of ``x`` (the tower)."""
+    return _FMPassFn.apply(x, first, num_fields, dim, num_first)
+
+
 class _CrossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x0, x, u, bias):

@@ -186,8 +186,18 @@ def emb_bwd_plan(call: GroupCall, workspace: torch.Tensor) -> None:
                    "ctr_emb_bwd_plan")
 
 
-def make_opt(kind: str = "none", lr: float = 0.0, eps: float = 1e-10, betas=(0.9, 0.999), step: int = 1) -> _lib.Opt:
-    return _lib.Opt(_OPT_KINDS[kind], step, lr, eps, betas[0], betas[1])
+def make_opt(kind: str = "none", lr: float = 0.0, eps: float = 1e-10, betas=(0.9, 0.999), step: int = 1,
+             device_hyper: torch.Tensor | None = None) -> _lib.Opt:
+    """``device_hyper``: optional f32 [5] CUDA tensor the kernels read the scalars from (see ``opt_hyper``)."""
+    _chk(device_hyper, "device_hyper", torch.float32)
+    return _lib.Opt(_OPT_KINDS[kind], step, lr, eps, betas[0], betas[1], _lib.ptr(device_hyper))
+
+
+def opt_hyper(opt: _lib.Opt):
+    """The five fp32 scalars (lr, eps, 1-beta1, 1-beta2, adam step size) the kernels use for ``opt``."""
+    h = _lib.Hyper()
+    _lib.lib().ctr_opt_hyper(C.byref(opt), C.byref(h))
+    return [h.lr, h.eps, h.one_minus_beta1, h.one_minus_beta2, h.adam_step_size]
 
 
 def emb_bwd_apply(call: GroupCall, workspace: torch.Tensor, opt: _lib.Opt, uniq_feature=None, uniq_row=None,
