@@ -1,0 +1,109 @@
+"""CPU-side checks (no GPU, no compute calls): the C-ABI library builds, loads and exports every
+symbol include/ctr_b200.h declares; struct layouts agree between the header and the ctypes
+mirror; host-side argument validation and model plumbing behave like the reference."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ctr_b200.h")
+
+
+def declared_in_header():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ctr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from torchctr_b200 import _lib, build
+    path = build.build()
+    assert os.path.exists(path)
+    handle = ctypes.CDLL(path)
+    names = declared_in_header()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(handle, name), f"{name} declared in ctr_b200.h but not exported"
+    assert set(_lib.declared_symbols()) == set(names), "ctypes signature table out of sync with the header"
+    assert _lib.lib().ctr_abi_version() == 1
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """Compile a tiny C program against the header and compare sizeof / offsetof with ctypes."""
+    from torchctr_b200 import _lib
+    prog = tmp_path / "layout.c"
+    prog.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "ctr_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu\n", sizeof(ctr_feature_t), sizeof(ctr_group_t), sizeof(ctr_opt_t), sizeof(ctr_vocab_map_t), sizeof(ctr_hyper_t));
+  printf("%zu %zu %zu %zu\n", offsetof(ctr_feature_t, num_rows), offsetof(ctr_feature_t, hash_seed), offsetof(ctr_group_t, status), offsetof(ctr_opt_t, device_hyper));
+  return 0; }''')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    sizes = [ctypes.sizeof(x) for x in (_lib.Feature, _lib.Group, _lib.Opt, _lib.VocabMap, _lib.Hyper)]
+    offs = [_lib.Feature.num_rows.offset, _lib.Feature.hash_seed.offset, _lib.Group.status.offset, _lib.Opt.device_hyper.offset]
+    assert [int(v) for v in out] == sizes + offs
+
+
+def test_no_cpu_fallback_and_reference_error_messages():
+    from torchctr_b200.models import DNN, DeepFM
+    from torchctr_b200.models.base import split_feature_configs
+    fc = [{"name": "a", "type": "sparse", "num_embeddings": 10, "emb_dim": 16}, {"name": "d", "type": "dense"},
+          {"name": "s", "type": "dense", "islist": True}]
+    sparse, dense_width = split_feature_configs(fc)
+    assert len(sparse) == 1 and dense_width == 4              # dnn.py:24-27: 3 per dense list feature
+    with pytest.raises(ValueError, match="emb_dim must be specified for sparse features."):
+        DNN([{"name": "a", "type": "sparse", "num_embeddings": 3}])
+    with pytest.raises(ValueError, match="Unsupported feature type: weird"):
+        DNN([{"name": "a", "type": "weird"}])
+    m = DNN(fc[:2], [8])
+    assert list(m.state_dict().keys())[:1] == ["embeddings.a.weight"]
+    assert m.feat_configs is fc[:2] or m.feat_configs == fc[:2]
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m({"a": torch.zeros(4, 1, dtype=torch.long), "dense_features": torch.zeros(4, 1)})
+    with pytest.raises(ValueError, match="common emb_dim"):
+        DeepFM([{"name": "a", "type": "sparse", "num_embeddings": 3, "emb_dim": 4},
+                {"name": "b", "type": "sparse", "num_embeddings": 3, "emb_dim": 8}])
+
+
+def test_state_dict_keys_match_oracle_models():
+    from oracle import models as om
+    from torchctr_b200.models import DCNv2, DeepFM, DNN
+    fc = [{"name": "a", "type": "sparse", "num_embeddings": 10, "emb_dim": 8},
+          {"name": "b", "type": "sparse", "num_embeddings": 7, "emb_dim": 8}, {"name": "d", "type": "dense"}]
+    for ours, ref in ((DNN(fc, [8, 4]), om.OracleDNN(fc, [8, 4])), (DeepFM(fc, [8]), om.OracleDeepFM(fc, [8])),
+                      (DCNv2(fc, [8], 2), om.OracleDCNv2(fc, [8], 2))):
+        assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+        ours.load_state_dict(ref.state_dict())
+
+
+def test_optimizer_binding_reads_torch_hyperparameters():
+    from torchctr_b200 import ops
+    from torchctr_b200.models import DNN
+    fc = [{"name": "a", "type": "sparse", "num_embeddings": 10, "emb_dim": 8}, {"name": "d", "type": "dense"}]
+    m = DNN(fc, [4])
+    opt = torch.optim.Adagrad(m.parameters(), lr=0.5, lr_decay=0.1, eps=1e-9)
+    b = m.bind_optimizer(opt)._lookup.binding
+    assert b.kind == "adagrad"
+    o1, o2 = b.next_opt(), b.next_opt()
+    assert o1.step == 1 and abs(o1.lr - 0.5) < 1e-12 and abs(o2.lr - 0.5 / 1.1) < 1e-12 and o1.eps == 1e-9
+    opt.param_groups[0]["lr"] = 0.25                             # an lr scheduler's effect is picked up
+    assert abs(b.next_opt().lr - 0.25 / 1.2) < 1e-12
+    with pytest.raises(ValueError, match="weight_decay"):
+        m.bind_optimizer(torch.optim.SGD(m.parameters(), lr=0.1, weight_decay=1e-3))
+    adam = ops.opt_hyper(ops.make_opt("adam", lr=0.01, eps=1e-8, betas=(0.9, 0.999), step=3))
+    import math
+    assert abs(adam[4] - 0.01 * math.sqrt(1 - 0.999 ** 3) / (1 - 0.9 ** 3)) < 1e-9
+    assert adam[2] == pytest.approx(0.1, rel=1e-6) and adam[3] == pytest.approx(0.001, rel=1e-6)
+
+
+def test_graft_entry_build():
+    import __graft_entry__ as g
+    g.build()
