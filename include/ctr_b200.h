@@ -202,6 +202,22 @@ int ctr_cross_combine_fwd(const float *x0, const float *x, const float *u, const
 int ctr_cross_combine_bwd(const float *x0, const float *u, const float *bias, const float *gy, int32_t B,
                           int32_t d, int64_t stride, float *gu, float *gx0, int32_t accumulate_gx0, void *stream);
 
+/* ---- row-sharded tables: pack / unpack around the NCCL all-to-all ------------------------------
+ * (the reference is replicas-only, torchctr/trainer.py:128-130).  owner(row) = row mod world; on the owner
+ * all tables of the group live in one fused shard, row base[owner * num_features + table] + row / world. */
+int64_t ctr_route_workspace_bytes(const ctr_group_t *group, int32_t world);
+/* For every id slot of the group (features in order, slot = bag * L + l): bucket by owner (stable),
+ *   counts    i64 [world + 1]  slots per owner (last = padding / invalid),
+ *   send_rows i64 [S]          virtual rows in exchange order (first sum(counts[:world]) entries valid),
+ *   inv       i64 [S]          slot -> position in exchange order, -1 for padding (feature-major, ready to be
+ *                              used as the ids of a pooled lookup over the received vectors). */
+int ctr_route_build(const ctr_group_t *group, int32_t world, const int64_t *base, int64_t *counts,
+                    int64_t *send_rows, int64_t *inv, void *workspace, int64_t workspace_bytes, void *stream);
+/* g_send[k, :] = grad_out[bag(slot_k), columns of feature(slot_k)] for the first n exchange positions
+ * (group->out is grad_out; every feature of the group has dim D). */
+int ctr_route_grad_gather(const ctr_group_t *group, int32_t world, const void *workspace, int64_t n, int32_t D,
+                          float *g_send, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

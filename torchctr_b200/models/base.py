@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ..nn.embedding import EmbeddingTable, PooledLookupGroup
+from ..nn.embedding import EmbeddingTable, PlanLink, PooledLookupGroup
 from ..nn.vocab import VocabIndex
 
 
@@ -70,11 +70,26 @@ class CTRModelBase(nn.Module):
         self._sparse_width = sum(c["emb_dim"] for c in self._sparse)
         self._lookup = PooledLookupGroup(self._names, self.embeddings)
         self._groups = [self._lookup]
+        self._sharded = None              # set by torchctr_b200.parallel.shard_model
+
+    def _lookup_all(self, feats, dense):
+        """Pooled output of every lookup group (the dense block rides with the first).  Groups share
+        the ids, hence one backward sort (``PlanLink``) -- or one all-to-all routing when sharded."""
+        if self._sharded is not None:
+            return self._sharded(feats, dense)
+        link = PlanLink() if self.training and len(self._groups) > 1 else None
+        outs = [self._groups[0](feats, dense, self.training, link)]
+        for g in self._groups[1:]:
+            outs.append(g(feats, None, self.training, link))
+        return tuple(outs)
 
     # ---- optimizer / ids checks -------------------------------------------------------------
     def bind_optimizer(self, optimizer, kind: str | None = None):
         """Fuse the table update into backward, following ``optimizer``'s hyper-parameters (the
         optimizer itself keeps stepping the dense parameters; tables get no ``.grad``)."""
+        if self._sharded is not None:
+            self._sharded.bind_optimizer(optimizer, kind)
+            return self
         for g in self._groups:
             g.bind_optimizer(optimizer, kind)
         return self

@@ -17,7 +17,7 @@ class DCNv2(CTRModelBase):
 
     def forward(self, input_feats):
         self._grow_vocabularies(input_feats)
-        x0 = self._lookup(input_feats, self.dense_block(input_feats), self.training)
+        (x0,) = self._lookup_all(input_feats, self.dense_block(input_feats))
         x = x0
         for layer in self.cross:
             x = layer(x0, x)

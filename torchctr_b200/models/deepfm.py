@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import torch.nn as nn
 
-from ..nn.embedding import EmbeddingTable, PlanLink, PooledLookupGroup
+from ..nn.embedding import EmbeddingTable, PooledLookupGroup
 from ..nn.interaction import fm_interaction_passthrough
 from .base import CTRModelBase, make_tower
 
@@ -31,9 +31,7 @@ class DeepFM(CTRModelBase):
     def forward(self, input_feats):
         self._grow_vocabularies(input_feats)
         dense = self.dense_block(input_feats)
-        link = PlanLink() if self.training else None                         # same ids: one backward sort for both
-        x = self._lookup(input_feats, dense, self.training, link)            # [B, pad4(F*D + Nd)]
-        first = self._linear_lookup(input_feats, None, self.training, link)  # [B, pad4(F)]
+        x, first = self._lookup_all(input_feats, dense)       # [B, pad4(F*D + Nd)], [B, pad4(F)]; one backward sort
         nf = len(self._names)
         x, fm = fm_interaction_passthrough(x, nf, self._dim, first, nf)
         logit = fm + self._run_tower(x)

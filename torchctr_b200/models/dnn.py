@@ -11,5 +11,5 @@ class DNN(CTRModelBase):
 
     def forward(self, input_feats):
         self._grow_vocabularies(input_feats)
-        x = self._lookup(input_feats, self.dense_block(input_feats), self.training)   # dnn.py:53-67 in one launch
+        (x,) = self._lookup_all(input_feats, self.dense_block(input_feats))          # dnn.py:53-67 in one launch
         return self._run_tower(x)                                                     # dnn.py:68

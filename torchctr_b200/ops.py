@@ -330,3 +330,28 @@ def cross_combine_bwd(x0, u, bias, gy, gx0: torch.Tensor, accumulate: bool) -> t
                                                 gu.data_ptr(), gx0.data_ptr(), int(accumulate), _stream(x0)),
                "ctr_cross_combine_bwd")
     return gu
+
+
+def route_build(call: GroupCall, world: int, base: torch.Tensor, S: int):
+    """Buckets the id slots of ``call`` by owner rank.  Returns (counts i64 [world+1], send_rows i64 [S],
+    inv i64 [S], workspace) -- see ``ctr_route_build``."""
+    _chk(base, "base", torch.int64)
+    dev = base.device
+    counts = torch.empty(world + 1, dtype=torch.int64, device=dev)
+    send_rows = torch.empty(S, dtype=torch.int64, device=dev)
+    inv = torch.empty(S, dtype=torch.int64, device=dev)
+    nbytes = _lib.check(_lib.lib().ctr_route_workspace_bytes(C.byref(call.struct), world))
+    ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+    with _timed("route_build"):
+        _lib.check(_lib.lib().ctr_route_build(C.byref(call.struct), world, base.data_ptr(), counts.data_ptr(),
+                                              send_rows.data_ptr(), inv.data_ptr(), ws.data_ptr(), ws.numel(),
+                                              _stream(base)), "ctr_route_build")
+    return counts, send_rows, inv, ws
+
+
+def route_grad_gather(call: GroupCall, world: int, workspace: torch.Tensor, n: int, D: int) -> torch.Tensor:
+    g_send = torch.empty(n, D, dtype=torch.float32, device=workspace.device)
+    with _timed("route_grad_gather"):
+        _lib.check(_lib.lib().ctr_route_grad_gather(C.byref(call.struct), world, workspace.data_ptr(), n, D,
+                                                    g_send.data_ptr(), _stream(workspace)), "ctr_route_grad_gather")
+    return g_send

@@ -1,0 +1,4 @@
+from .sharded import ShardedTables, reduce_dense_grads, shard_bases, local_rows
+from .model import shard_model
+
+__all__ = ["ShardedTables", "reduce_dense_grads", "shard_bases", "local_rows", "shard_model"]

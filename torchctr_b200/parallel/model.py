@@ -1,0 +1,35 @@
+"""``shard_model``: turn a replicated-initialised model into its row-sharded form, in place."""
+from __future__ import annotations
+
+import torch.nn as nn
+
+from .sharded import ShardedTables, reduce_dense_grads
+
+
+def shard_model(model, pg=None, device=None, backend=None):
+    """Every rank calls this with an identically initialised ``model`` (same seed).  The model's tables
+    (and, for DeepFM, its first-order tables, which share the ids) are cut into this rank's rows, fused
+    into one shard per width on ``device`` and the full tables are dropped; the dense part stays
+    replicated.  Afterwards use::
+
+        loss = model.training_step(batch, i)
+        (loss / world).backward()            # tables are updated inside backward
+        model.reduce_dense_grads()           # one all-reduce for the tower
+        optimizer.step()
+    """
+    groups = model._groups
+    full = [[g.tables[n] for n in g.names] for g in groups]
+    if device is not None:
+        # shards are built on the target device straight from the (host) full tables
+        import torch
+        with torch.device(device):
+            sharded = ShardedTables(groups[0].names, full, pg, backend)
+    else:
+        sharded = ShardedTables(groups[0].names, full, pg, backend)
+    model._sharded = sharded
+    for g in groups:                       # drop the replicated tables
+        for n in list(g.tables.keys()):
+            del g.tables[n]
+    model._pg = pg
+    model.reduce_dense_grads = lambda: reduce_dense_grads(model.dense_parameters(), pg)
+    return model
