@@ -7,7 +7,7 @@
 namespace ctr {
 
 constexpr int kSortThreads = 256;
-constexpr int kSortItems = 16;
+constexpr int kSortItems = 8;
 constexpr int kSortTile = kSortThreads * kSortItems;  // keys per block per pass
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;

@@ -85,7 +85,9 @@ class CudaBackend:
         call = ops.make_group(specs, B, grad_out, grad_out.shape[1])
         return ops.route_grad_gather(call, st.world, ws, n_send, st.dims[w])
 
-    def update(self, shard_mod, rows, grads, binding):
+    def update(self, shard_mod, rows, grads, binding, cache=None):
+        """Owner side of the backward: K2 over the received (row, gradient) pairs.  ``cache`` lets the
+        widths of one step, which received the same rows, share one sort."""
         n = rows.shape[0]
         if n == 0:
             return
@@ -94,8 +96,17 @@ class CudaBackend:
                                D=shard_mod.embedding_dim, out_col=0, state0=getattr(shard_mod, "opt_state0", None),
                                state1=getattr(shard_mod, "opt_state1", None))
         call = ops.make_group([spec], n, grads, grads.shape[1])
-        ws = _Workspace.get(grads.device, ops.emb_bwd_workspace_bytes(call))
-        ops.emb_bwd_plan(call, ws)
+        if cache is not None and "ws" in cache:
+            ws = cache["ws"]
+        else:
+            widest = ops.FeatureSpec(ids=rows.view(n, 1), table=None, num_rows=shard_mod.num_embeddings,
+                                     D=(cache or {}).get("max_dim", shard_mod.embedding_dim), out_col=0)
+            need = ops.emb_bwd_workspace_bytes(ops.make_group([widest], n, None, widest.D))
+            ws = torch.empty(need + 256, dtype=torch.uint8, device=grads.device) if cache is not None \
+                else _Workspace.get(grads.device, need)
+            ops.emb_bwd_plan(call, ws)
+            if cache is not None:
+                cache["ws"] = ws
         ops.emb_bwd_apply(call, ws, binding.next_opt())
 
 
@@ -129,6 +140,7 @@ class _ShardedLookupFn(torch.autograd.Function):
         st = ctx.st
         be, pg = st.backend, st.pg
         send_splits, recv_splits, n_send, n_recv = ctx.splits
+        cache = {"max_dim": max(st.dims)}
         for w, g in enumerate(grad_outs):
             if g is None:
                 continue
@@ -138,7 +150,7 @@ class _ShardedLookupFn(torch.autograd.Function):
             dist.all_to_all_single(g_recv, g_send, recv_splits, send_splits, group=pg)
             if st.bindings[w] is None:
                 raise RuntimeError("sharded tables need bind_optimizer(): there is no dense or sparse .grad to hand back")
-            be.update(st.shards[w], ctx.recv_rows, g_recv, st.bindings[w])
+            be.update(st.shards[w], ctx.recv_rows, g_recv, st.bindings[w], cache)
         gdense = None
         if ctx.has_dense and ctx.needs_input_grad[2] and grad_outs[0] is not None:
             c0 = st.cols(0)[-1] + st.dims[0]
