@@ -202,6 +202,13 @@ int ctr_cross_combine_fwd(const float *x0, const float *x, const float *u, const
 int ctr_cross_combine_bwd(const float *x0, const float *u, const float *bias, const float *gy, int32_t B,
                           int32_t d, int64_t stride, float *gu, float *gx0, int32_t accumulate_gx0, void *stream);
 
+/* ---- dense layers on tensor cores (tcgen05.mma kind::tf32, fp32 accumulate in TMEM) ----------------
+ * C[M, N] = act(A[M, K] . W[N, K]^T + bias[N]); act 0 = none, 1 = relu.  Row-major, leading dimensions in
+ * floats; lda and ldw multiples of 4, A and W 16-byte aligned; bias may be NULL.  Replaces the Linear
+ * layers of torchctr/models/dnn.py:35-46 and the x.W^T of the DCN-v2 cross layer. */
+int ctr_linear_fwd(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias, float *C,
+                   int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t act, void *stream);
+
 /* ---- row-sharded tables: pack / unpack around the NCCL all-to-all ------------------------------
  * (the reference is replicas-only, torchctr/trainer.py:128-130).  owner(row) = row mod world; on the owner
  * all tables of the group live in one fused shard, row base[owner * num_features + table] + row / world. */

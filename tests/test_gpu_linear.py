@@ -1,0 +1,56 @@
+"""tcgen05 GEMM (K6) against torch: TF32 inputs / fp32 accumulate, so the tolerance is TF32's
+(10-bit mantissa): 2e-3 of max|ref| against an fp32 reference, and it must agree with torch's own TF32
+path to the same bound."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(got, ref):
+    return float((got - ref).abs().max()) / max(float(ref.abs().max()), 1e-30)
+
+
+@pytest.mark.parametrize("M,N,K,lda_pad", [(128, 128, 32, 0), (1000, 256, 432, 0), (4096, 128, 256, 0), (777, 64, 128, 0),
+                                           (300, 848, 848, 0), (65536, 256, 429, 3), (513, 16, 64, 0)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_linear_fwd_matches_torch(M, N, K, lda_pad, act):
+    from torchctr_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(M + N + K)
+    buf = torch.zeros(M, K + lda_pad, device="cuda")
+    buf[:, :K] = torch.randn(M, K, device="cuda", generator=gen)
+    A = buf[:, :K] if lda_pad else buf
+    Wfull = torch.zeros(N, K + lda_pad, device="cuda")
+    Wfull[:, :K] = torch.randn(N, K, device="cuda", generator=gen) / K ** 0.5
+    W = Wfull[:, :K] if lda_pad else Wfull
+    bias = torch.randn(N, device="cuda", generator=gen)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = A.double() @ W.double().t() + bias.double()
+    if act:
+        ref = ref.clamp(min=0)
+    got = ops.linear_fwd(A, W, bias, act)
+    torch.cuda.synchronize()
+    assert rel_err(got.double(), ref) < 2e-3
+    torch.backends.cuda.matmul.allow_tf32 = True
+    tf32 = torch.nn.functional.linear(A.contiguous(), W.contiguous(), bias)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    if act:
+        tf32 = tf32.clamp(min=0)
+    assert rel_err(got, tf32) < 2e-3
+
+
+def test_linear_tc_autograd_matches_torch():
+    from torchctr_b200.nn.linear import linear_tc
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(2048, 432, device="cuda", generator=gen, requires_grad=True)
+    w = (torch.randn(256, 432, device="cuda", generator=gen) / 20).requires_grad_(True)
+    b = torch.randn(256, device="cuda", generator=gen, requires_grad=True)
+    gy = torch.randn(2048, 256, device="cuda", generator=gen)
+    y = linear_tc(x, w, b)
+    y.backward(gy)
+    got = (y.detach(), x.grad.clone(), w.grad.clone(), b.grad.clone())
+    x.grad = w.grad = b.grad = None
+    yr = torch.nn.functional.linear(x, w, b)
+    yr.backward(gy)
+    for g, r in zip(got, (yr.detach(), x.grad, w.grad, b.grad)):
+        assert rel_err(g, r) < 2e-3

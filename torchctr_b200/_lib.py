@@ -85,6 +85,8 @@ _SIGNATURES = {
                              C.c_int32, _P, C.c_int32, C.c_int64, _P]),
     "ctr_cross_combine_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P]),
     "ctr_cross_combine_bwd": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, C.c_int32, _P]),
+    "ctr_linear_fwd": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_int32, _P]),
     "ctr_route_workspace_bytes": (C.c_int64, [C.POINTER(Group), C.c_int32]),
     "ctr_route_build": (C.c_int, [C.POINTER(Group), C.c_int32, _P, _P, _P, _P, _P, C.c_int64, _P]),
     "ctr_route_grad_gather": (C.c_int, [C.POINTER(Group), C.c_int32, _P, C.c_int64, C.c_int32, _P, _P]),

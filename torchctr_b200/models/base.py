@@ -130,7 +130,7 @@ class CTRModelBase(nn.Module):
         return h
 
     def _grow_vocabularies(self, feats):
-        if not self.training:
+        if not self.training or self._sharded is not None:
             return
         for name in self._names:
             table = self.embeddings[name]

@@ -355,3 +355,24 @@ def route_grad_gather(call: GroupCall, world: int, workspace: torch.Tensor, n: i
         _lib.check(_lib.lib().ctr_route_grad_gather(C.byref(call.struct), world, workspace.data_ptr(), n, D,
                                                     g_send.data_ptr(), _stream(workspace)), "ctr_route_grad_gather")
     return g_send
+
+
+def linear_fwd(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor | None = None, act: int = 0,
+               out: torch.Tensor | None = None) -> torch.Tensor:
+    """``act(A @ W.T + bias)`` on tcgen05 tensor cores (TF32 inputs, fp32 accumulate).  A f32 [M, K] with unit
+    inner stride and a row pitch that is a multiple of 4 floats, W f32 [N, K] likewise."""
+    _lib.require_cuda(A, "A")
+    for name, t in (("A", A), ("W", W)):
+        if t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
+            raise ValueError(f"{name} must be f32 [rows, K] with unit inner stride")
+    M, K = A.shape
+    N = W.shape[0]
+    if W.shape[1] != K:
+        raise ValueError(f"shape mismatch: A {tuple(A.shape)} vs W {tuple(W.shape)}")
+    _chk(bias, "bias", torch.float32)
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    with _timed("linear_fwd"):
+        _lib.check(_lib.lib().ctr_linear_fwd(A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), _lib.ptr(bias),
+                                             out.data_ptr(), out.stride(0), M, N, K, act, _stream(A)), "ctr_linear_fwd")
+    return out
