@@ -10,6 +10,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..nn.embedding import EmbeddingTable, PlanLink, PooledLookupGroup
+from ..nn.linear import linear_tc
 from ..nn.vocab import VocabIndex
 
 
@@ -121,12 +122,20 @@ class CTRModelBase(nn.Module):
         slicing (and copying) the activations."""
         pad = x.shape[1] - layer.in_features
         w = F.pad(layer.weight, (0, pad)) if pad else layer.weight
-        return F.linear(x, w, layer.bias)
+        return self._linear(x, w, layer.bias)
+
+    @staticmethod
+    def _linear(x, weight, bias):
+        """Linear layer: the hand-written tcgen05 TF32 kernel when torch is allowed to use TF32 for matmuls
+        (``torch.backends.cuda.matmul.allow_tf32``), exact fp32 cuBLAS otherwise (the parity mode)."""
+        if torch.backends.cuda.matmul.allow_tf32:
+            return linear_tc(x, weight, bias)
+        return F.linear(x, weight, bias)
 
     def _run_tower(self, x: torch.Tensor) -> torch.Tensor:
         h = self._first_linear(x, self.tower[0])
         for layer in list(self.tower)[1:]:
-            h = layer(h)
+            h = self._linear(h, layer.weight, layer.bias) if isinstance(layer, nn.Linear) else layer(h)
         return h
 
     def _grow_vocabularies(self, feats):

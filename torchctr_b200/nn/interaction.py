@@ -10,6 +10,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
+from .linear import linear_tc
 
 
 class _FMFn(torch.autograd.Function):
@@ -100,5 +101,6 @@ class CrossLayer(nn.Linear):
         pad = x.shape[1] - self.in_features
         w = F.pad(self.weight, (0, pad, 0, pad)) if pad else self.weight
         b = F.pad(self.bias, (0, pad)) if pad else self.bias
-        u = x @ w.t()                       # dense contraction: tensor cores
+        # dense contraction: tcgen05 TF32 kernel when TF32 matmuls are allowed, fp32 cuBLAS otherwise
+        u = linear_tc(x, w, None) if torch.backends.cuda.matmul.allow_tf32 else x @ w.t()
         return _CrossFn.apply(x0, x, u, b)
