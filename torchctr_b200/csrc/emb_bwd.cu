@@ -93,6 +93,29 @@ __global__ void reset_counters_kernel(uint32_t *counters) {
     if (threadIdx.x < kNumCounters) counters[threadIdx.x] = 0;
 }
 
+// Plan-time classification of the runs by length: <= kTeamRun stay with the short-run kernel, up to
+// kLongRun go to the warp-per-run queue, longer ones are cut into kChunk-position chunks.  Queue order is
+// scheduling-dependent, results are not (every run is reduced in slot order by whoever takes it).
+__global__ void __launch_bounds__(256)
+    classify_runs_kernel(const uint32_t *__restrict__ run_start, uint32_t *counters, uint32_t *__restrict__ med_list,
+                         uint32_t *__restrict__ long_list, uint32_t *__restrict__ long_cbase, uint32_t *__restrict__ chunk_q) {
+    const uint32_t num_runs = counters[1];
+    for (uint32_t run = blockIdx.x * blockDim.x + threadIdx.x; run < num_runs; run += gridDim.x * blockDim.x) {
+        const uint32_t len = run_start[run + 1] - run_start[run];
+        if (len <= (uint32_t)kTeamRun) continue;
+        if (len <= (uint32_t)kLongRun) {
+            med_list[atomicAdd(&counters[4], 1u)] = run;
+        } else {
+            const uint32_t nch = (len + kChunk - 1) / kChunk;
+            const uint32_t q = atomicAdd(&counters[2], 1u);
+            const uint32_t cbase = atomicAdd(&counters[3], nch);
+            long_list[q] = run;
+            long_cbase[q] = cbase;
+            for (uint32_t c = 0; c < nch; ++c) chunk_q[cbase + c] = q;
+        }
+    }
+}
+
 // ---- apply ----------------------------------------------------------------------------------
 struct ApplyArgs {
     const uint32_t *keys;       // sorted
@@ -253,24 +276,7 @@ __global__ void __launch_bounds__(kApplyThreads)
     const int64_t team_global = ((int64_t)blockIdx.x * kApplyThreads + threadIdx.x) / TG;
     for (int64_t run = team_global; run < num_runs; run += teams_total) {
         const uint32_t s = a.run_start[run], e = a.run_start[run + 1];
-        if (e - s > (uint32_t)kTeamRun && e - s <= (uint32_t)kLongRun) {  // medium run: one warp
-            if (t == 0) a.med_list[atomicAdd(&a.counters[4], 1u)] = (uint32_t)run;
-            continue;
-        }
-        if (e - s > (uint32_t)kLongRun) {  // hot row: hand it to the chunked block reduction
-            const uint32_t nch = (e - s + kChunk - 1) / kChunk;
-            uint32_t q = 0, cbase = 0;
-            if (t == 0) {
-                q = atomicAdd(&a.counters[2], 1u);
-                cbase = atomicAdd(&a.counters[3], nch);
-                a.long_list[q] = (uint32_t)run;
-                a.long_cbase[q] = cbase;
-            }
-            q = __shfl_sync(mask, q, team_in_warp * TG);
-            cbase = __shfl_sync(mask, cbase, team_in_warp * TG);
-            for (uint32_t c = t; c < nch; c += TG) a.chunk_q[cbase + c] = q;
-            continue;
-        }
+        if (e - s > (uint32_t)kTeamRun) continue;  // medium / long runs were queued by the plan for the other tiers
         const uint32_t key = a.keys[s];
         const int fi = find_feature(g, key);
         const DevFeature &f = g.f[fi];
@@ -457,6 +463,35 @@ __global__ void __launch_bounds__(kApplyThreads)
     }
 }
 
+// helper streams / events of the calling thread's current device (created once, never destroyed)
+struct TierStreams {
+    cudaStream_t s[2];
+    cudaEvent_t fork, join[2];
+};
+static TierStreams *tier_streams() {
+    static thread_local TierStreams per_device[16];
+    static thread_local bool ready[16] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) {
+        set_error("cannot resolve the current CUDA device");
+        return nullptr;
+    }
+    if (!ready[dev]) {
+        TierStreams &t = per_device[dev];
+        bool ok = cudaStreamCreateWithFlags(&t.s[0], cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&t.s[1], cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&t.join[0], cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&t.join[1], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
+            set_error("cannot create helper streams: %s", cudaGetErrorString(cudaGetLastError()));
+            return nullptr;
+        }
+        ready[dev] = true;
+    }
+    return &per_device[dev];
+}
+
 }  // namespace ctr
 
 using namespace ctr;
@@ -521,7 +556,15 @@ extern "C" int ctr_emb_bwd_plan(const ctr_group_t *group, void *workspace, int64
     const uint32_t *sorted_keys = p.sorted_in_b ? keys_b : keys_a;
     rc = find_runs(sorted_keys, p.S, reinterpret_cast<uint32_t *>(ws + p.run_start), counters,
                    reinterpret_cast<uint32_t *>(ws + p.spine), stream);
-    return rc;
+    if (rc != CTR_OK || p.S == 0) return rc;
+    int64_t cb = (p.S + 255) / 256;
+    if (cb > kNumSMs * 8) cb = kNumSMs * 8;
+    note_launch(), classify_runs_kernel<<<(unsigned)cb, 256, 0, stream>>>(
+        reinterpret_cast<const uint32_t *>(ws + p.run_start), counters, reinterpret_cast<uint32_t *>(ws + p.med_list),
+        reinterpret_cast<uint32_t *>(ws + p.long_list), reinterpret_cast<uint32_t *>(ws + p.long_cbase),
+        reinterpret_cast<uint32_t *>(ws + p.chunk_q));
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
 }
 
 extern "C" int ctr_emb_bwd_apply(const ctr_group_t *group, void *workspace, const ctr_opt_t *opt,
@@ -578,17 +621,26 @@ extern "C" int ctr_emb_bwd_apply(const ctr_group_t *group, void *workspace, cons
         if (num_unique != nullptr) CTR_CUDA_OK(cudaMemsetAsync(num_unique, 0, sizeof(int64_t), stream));
         return CTR_OK;
     }
-    // the long-run queue is rebuilt by every apply
-    CTR_CUDA_OK(cudaMemsetAsync(a.counters + 2, 0, 3 * sizeof(uint32_t), stream));
     const int teams_per_block = kApplyThreads / team;
     int64_t blocks = (p.S + teams_per_block - 1) / teams_per_block;  // upper bound: one run per slot
     const int64_t cap = (int64_t)kNumSMs * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    // The three tiers touch disjoint rows: fork them onto two helper streams so that their latency-bound
+    // tails overlap, then join back into the caller's stream (capturable: the fork / join is all events).
+    TierStreams *ts = tier_streams();
+    if (ts == nullptr) return CTR_E_CUDA;
+    CTR_CUDA_OK(cudaEventRecord(ts->fork, stream));
+    CTR_CUDA_OK(cudaStreamWaitEvent(ts->s[0], ts->fork, 0));
+    CTR_CUDA_OK(cudaStreamWaitEvent(ts->s[1], ts->fork, 0));
     note_launch(), emb_bwd_apply_kernel<<<(unsigned)blocks, kApplyThreads, 0, stream>>>(dg, a);
-    note_launch(), emb_bwd_medium_kernel<<<kNumSMs * 8, kApplyThreads, 0, stream>>>(dg, a);
-    note_launch(), emb_bwd_chunk_kernel<<<kNumSMs * 8, kApplyThreads, 0, stream>>>(dg, a);
-    note_launch(), emb_bwd_long_finish_kernel<<<kNumSMs, kApplyThreads, 0, stream>>>(dg, a);
+    note_launch(), emb_bwd_medium_kernel<<<kNumSMs * 4, kApplyThreads, 0, ts->s[0]>>>(dg, a);
+    note_launch(), emb_bwd_chunk_kernel<<<kNumSMs * 4, kApplyThreads, 0, ts->s[1]>>>(dg, a);
+    note_launch(), emb_bwd_long_finish_kernel<<<kNumSMs, kApplyThreads, 0, ts->s[1]>>>(dg, a);
+    CTR_CUDA_OK(cudaEventRecord(ts->join[0], ts->s[0]));
+    CTR_CUDA_OK(cudaEventRecord(ts->join[1], ts->s[1]));
+    CTR_CUDA_OK(cudaStreamWaitEvent(stream, ts->join[0], 0));
+    CTR_CUDA_OK(cudaStreamWaitEvent(stream, ts->join[1], 0));
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }
