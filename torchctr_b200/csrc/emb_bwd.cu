@@ -26,7 +26,7 @@ struct PlanLayout {
     // offsets in bytes from the workspace base
     int64_t counters, keys_a, keys_b, vals_a, vals_b, counts, spine, run_start;
     // apply-time scratch (rebuilt by every apply; sized by the group being applied)
-    int64_t med_list, long_list, long_cbase, chunk_q, partials, max_med, max_long, max_chunks, row_floats, total;
+    int64_t med_list, long_list, long_cbase, chunk_q, long_done, partials, max_med, max_long, max_chunks, row_floats, total;
 };
 // counters (u32): [0] runs, [1] unique valid rows, [2] long-run queue, [3] chunk queue, [4] medium-run queue
 constexpr int kNumCounters = 8;
@@ -69,6 +69,7 @@ static PlanLayout plan_layout(const DevGroup &g) {
     p.long_list = off; off = align256(off + p.max_long * 4);
     p.long_cbase = off; off = align256(off + p.max_long * 4);
     p.chunk_q = off; off = align256(off + p.max_chunks * 4);
+    p.long_done = off; off = align256(off + p.max_long * 4);
     p.partials = off; off = align256(off + p.max_chunks * row_floats * 4);
     p.total = off;
     return p;
@@ -125,6 +126,7 @@ struct ApplyArgs {
     uint32_t *med_list;         // [q] -> run (medium runs, one warp each)
     uint32_t *long_list;        // [q] -> run
     uint32_t *long_cbase;       // [q] -> first chunk of the run
+    uint32_t *long_done;        // [q] -> chunks finished so far (zeroed by every apply)
     uint32_t *chunk_q;          // [chunk] -> q
     float *partials;            // [chunk, row_floats]
     int row_floats;
@@ -260,236 +262,205 @@ __device__ __forceinline__ void update_row(const DevGroup &g, const DevFeature &
     }
 }
 
-// Short runs: one team of a.team lanes per run.
+// ---- the three run-length tiers as device functions ------------------------------------------------
+// accumulate coef * grad_out[bag] over positions p0, p0 + stride, ... < e, four loads in flight
+__device__ __forceinline__ float4 strided_run_sum(const DevGroup &g, const DevFeature &f, const ApplyArgs &a, uint32_t p_first,
+                                                  uint32_t e, uint32_t stride, int g_lane, bool col_ok) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t p0 = p_first; p0 < e; p0 += 4 * stride) {
+        uint32_t bag[4];
+        float coef[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t p = p0 + j * stride;
+            bag[j] = 0; coef[j] = 0.f;
+            if (p < e) {
+                const uint32_t slot = a.vals[p];
+                bag[j] = slot / (uint32_t)f.L;
+                coef[j] = slot_coef(f, slot, bag[j]);
+            }
+        }
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col_ok && p0 + j * stride < e) v[j] = load_grad_part(g, f, bag[j], g_lane);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc.x = fmaf(coef[j], v[j].x, acc.x);
+            acc.y = fmaf(coef[j], v[j].y, acc.y);
+            acc.z = fmaf(coef[j], v[j].z, acc.z);
+            acc.w = fmaf(coef[j], v[j].w, acc.w);
+        }
+    }
+    return acc;
+}
+
+// Short run (<= kTeamRun): one team of TG lanes, slot order.
+__device__ __forceinline__ void short_run(const DevGroup &g, const ApplyArgs &a, uint32_t run, uint32_t s, uint32_t e, int TG,
+                                          int t, int team_in_warp, unsigned mask) {
+    const uint32_t key = a.keys[s];
+    const int fi = find_feature(g, key);
+    const DevFeature &f = g.f[fi];
+    const bool col_ok = t < f.G && t * f.vec < f.D;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t base = s; base < e; base += TG) {
+        uint32_t bag = 0;
+        float coef = 0.f;
+        if (base + t < e) {
+            const uint32_t slot = a.vals[base + t];
+            bag = slot / (uint32_t)f.L;
+            coef = slot_coef(f, slot, bag);
+        }
+        const int m = (int)min((uint32_t)TG, e - base);
+        for (int k = 0; k < m; ++k) {
+            const uint32_t bk = __shfl_sync(mask, bag, team_in_warp * TG + k);
+            const float ck = __shfl_sync(mask, coef, team_in_warp * TG + k);
+            if (col_ok) {
+                const float4 v = load_grad_part(g, f, bk, t);
+                acc.x = fmaf(ck, v.x, acc.x);
+                acc.y = fmaf(ck, v.y, acc.y);
+                acc.z = fmaf(ck, v.z, acc.z);
+                acc.w = fmaf(ck, v.w, acc.w);
+            }
+        }
+    }
+    update_row(g, f, a, run, fi, key - f.row_base, t, col_ok, acc, mask, TG);
+}
+
+// Medium run (<= kLongRun): one warp; 32 / G row slots stride the run, xor-shuffles fold the slots.
+__device__ __forceinline__ void medium_run(const DevGroup &g, const ApplyArgs &a, uint32_t run, int lane) {
+    const uint32_t s = a.run_start[run], e = a.run_start[run + 1];
+    const uint32_t key = a.keys[s];
+    const int fi = find_feature(g, key);
+    const DevFeature &f = g.f[fi];
+    const int G = f.G;
+    const int g_lane = lane & (G - 1);
+    const bool col_ok = g_lane * f.vec < f.D;
+    float4 acc = strided_run_sum(g, f, a, s + lane / G, e, kWarp / G, g_lane, col_ok);
+    for (int off = G; off < kWarp; off <<= 1) {
+        acc.x += __shfl_xor_sync(kFull, acc.x, off);
+        acc.y += __shfl_xor_sync(kFull, acc.y, off);
+        acc.z += __shfl_xor_sync(kFull, acc.z, off);
+        acc.w += __shfl_xor_sync(kFull, acc.w, off);
+    }
+    update_row(g, f, a, run, fi, key - f.row_base, lane, lane < G && col_ok, acc, kFull, G);
+}
+
+// One chunk of a long run: the whole block; 256 / G row slots, fixed-order shared-memory tree -> partials[ci].
+__device__ __forceinline__ void chunk_task(const DevGroup &g, const ApplyArgs &a, uint32_t ci, float4 *red) {
+    const uint32_t q = a.chunk_q[ci];
+    const uint32_t run = a.long_list[q];
+    const uint32_t c = ci - a.long_cbase[q];
+    const uint32_t s = a.run_start[run] + c * kChunk;
+    const uint32_t e = min(a.run_start[run + 1], s + (uint32_t)kChunk);
+    const DevFeature &f = g.f[find_feature(g, a.keys[s])];
+    const int G = f.G;
+    const int g_lane = threadIdx.x & (G - 1);
+    const bool col_ok = g_lane * f.vec < f.D;
+    red[threadIdx.x] = strided_run_sum(g, f, a, s + threadIdx.x / G, e, kApplyThreads / G, g_lane, col_ok);
+    __syncthreads();
+    for (int stride = kApplyThreads / 2; stride >= G; stride >>= 1) {
+        if ((int)threadIdx.x < stride) {
+            const float4 o = red[threadIdx.x + stride];
+            float4 m = red[threadIdx.x];
+            m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
+            red[threadIdx.x] = m;
+        }
+        __syncthreads();
+    }
+    if ((int)threadIdx.x < G) reinterpret_cast<float4 *>(a.partials + (size_t)ci * a.row_floats)[threadIdx.x] = red[threadIdx.x];
+}
+
+// Finish a long run whose chunks are all done: the first warp adds the partials in chunk order and updates.
+__device__ __forceinline__ void long_finish(const DevGroup &g, const ApplyArgs &a, uint32_t q, int lane) {
+    const uint32_t run = a.long_list[q];
+    const uint32_t s = a.run_start[run], e = a.run_start[run + 1];
+    const uint32_t nch = (e - s + kChunk - 1) / kChunk;
+    const uint32_t cbase = a.long_cbase[q];
+    const uint32_t key = a.keys[s];
+    const int fi = find_feature(g, key);
+    const DevFeature &f = g.f[fi];
+    const bool col_ok = lane < f.G && lane * f.vec < f.D;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < f.G) {
+        for (uint32_t c = 0; c < nch; ++c) {   // .cg: partials were written by other blocks
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(a.partials + (size_t)(cbase + c) * a.row_floats) + lane);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    update_row(g, f, a, run, fi, key - f.row_base, lane, col_ok, acc, kFull, f.G);
+}
+
+// One launch for all tiers.  Work is handed out dynamically (atomic tickets in the plan's counter block),
+// longest tasks first: chunks of hot rows, then warp-sized runs, then the bulk of short runs -- so the
+// latency-bound tails of the tiers overlap instead of running back to back.  counters: [5] chunk ticket,
+// [6] medium ticket, [7] short ticket; long_done[q] counts finished chunks of long run q.
 __global__ void __launch_bounds__(kApplyThreads)
     emb_bwd_apply_kernel(const __grid_constant__ DevGroup g, const __grid_constant__ ApplyArgs a_in) {
-    ApplyArgs a = a_in;
-    if (a.hyper_dev != nullptr) a.h = *a.hyper_dev;
-    const int TG = a.team;
-    const int lane = threadIdx.x & 31;
-    const int t = lane & (TG - 1);
-    const int team_in_warp = lane / TG;
-    const unsigned mask = TG == 32 ? kFull : (((1u << TG) - 1u) << (team_in_warp * TG));
-    const uint32_t num_runs = a.counters[1];
-    if (blockIdx.x == 0 && threadIdx.x == 0 && a.num_unique != nullptr) *a.num_unique = (int64_t)num_runs;
-    const int64_t teams_total = (int64_t)gridDim.x * (kApplyThreads / TG);
-    const int64_t team_global = ((int64_t)blockIdx.x * kApplyThreads + threadIdx.x) / TG;
-    for (int64_t run = team_global; run < num_runs; run += teams_total) {
-        const uint32_t s = a.run_start[run], e = a.run_start[run + 1];
-        if (e - s > (uint32_t)kTeamRun) continue;  // medium / long runs were queued by the plan for the other tiers
-        const uint32_t key = a.keys[s];
-        const int fi = find_feature(g, key);
-        const DevFeature &f = g.f[fi];
-        const uint32_t row = key - f.row_base;
-        const int g_lane = t;  // lanes [0, f.G) carry the row
-        const bool col_ok = g_lane < f.G && g_lane * f.vec < f.D;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (uint32_t base = s; base < e; base += TG) {
-            uint32_t bag = 0;
-            float coef = 0.f;
-            if (base + t < e) {
-                const uint32_t slot = a.vals[base + t];
-                bag = slot / (uint32_t)f.L;
-                coef = slot_coef(f, slot, bag);
-            }
-            const int m = (int)min((uint32_t)TG, e - base);
-            for (int k = 0; k < m; ++k) {
-                const uint32_t bk = __shfl_sync(mask, bag, team_in_warp * TG + k);
-                const float ck = __shfl_sync(mask, coef, team_in_warp * TG + k);
-                if (col_ok) {
-                    const float4 v = load_grad_part(g, f, bk, g_lane);
-                    acc.x = fmaf(ck, v.x, acc.x);
-                    acc.y = fmaf(ck, v.y, acc.y);
-                    acc.z = fmaf(ck, v.z, acc.z);
-                    acc.w = fmaf(ck, v.w, acc.w);
-                }
-            }
-        }
-        update_row(g, f, a, (uint32_t)run, fi, row, g_lane, col_ok, acc, mask, TG);
-    }
-}
-
-// Medium runs: one warp per queued run; 32 / G row slots stride the run four positions at a time,
-// xor-shuffles fold the slots, lanes [0, G) update the row.
-__global__ void __launch_bounds__(kApplyThreads)
-    emb_bwd_medium_kernel(const __grid_constant__ DevGroup g, const __grid_constant__ ApplyArgs a_in) {
-    ApplyArgs a = a_in;
-    if (a.hyper_dev != nullptr) a.h = *a.hyper_dev;
-    const int lane = threadIdx.x & 31;
-    const uint32_t nmed = a.counters[4];
-    const int64_t warps_total = (int64_t)gridDim.x * (kApplyThreads / kWarp);
-    for (int64_t q = (int64_t)blockIdx.x * (kApplyThreads / kWarp) + (threadIdx.x >> 5); q < nmed; q += warps_total) {
-        const uint32_t run = a.med_list[q];
-        const uint32_t s = a.run_start[run], e = a.run_start[run + 1];
-        const uint32_t key = a.keys[s];
-        const int fi = find_feature(g, key);
-        const DevFeature &f = g.f[fi];
-        const int G = f.G;
-        const int g_lane = lane & (G - 1);
-        const uint32_t slot_id = lane / G;
-        const uint32_t nslots = kWarp / G;
-        const bool col_ok = g_lane * f.vec < f.D;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (uint32_t p0 = s + slot_id; p0 < e; p0 += 4 * nslots) {
-            uint32_t bag[4];
-            float coef[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t p = p0 + j * nslots;
-                bag[j] = 0; coef[j] = 0.f;
-                if (p < e) {
-                    const uint32_t slot = a.vals[p];
-                    bag[j] = slot / (uint32_t)f.L;
-                    coef[j] = slot_coef(f, slot, bag[j]);
-                }
-            }
-            float4 v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (col_ok && p0 + j * nslots < e) v[j] = load_grad_part(g, f, bag[j], g_lane);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                acc.x = fmaf(coef[j], v[j].x, acc.x);
-                acc.y = fmaf(coef[j], v[j].y, acc.y);
-                acc.z = fmaf(coef[j], v[j].z, acc.z);
-                acc.w = fmaf(coef[j], v[j].w, acc.w);
-            }
-        }
-        for (int off = G; off < kWarp; off <<= 1) {
-            acc.x += __shfl_xor_sync(kFull, acc.x, off);
-            acc.y += __shfl_xor_sync(kFull, acc.y, off);
-            acc.z += __shfl_xor_sync(kFull, acc.z, off);
-            acc.w += __shfl_xor_sync(kFull, acc.w, off);
-        }
-        update_row(g, f, a, run, fi, key - f.row_base, lane, lane < G && col_ok, acc, kFull, G);
-    }
-}
-
-// Long runs, stage 1: one block per chunk of kChunk sorted positions.  256 / G row slots stride the
-// chunk four positions at a time (independent loads in flight), then a fixed-order shared-memory
-// tree leaves the chunk's partial sum in partials[chunk].
-__global__ void __launch_bounds__(kApplyThreads)
-    emb_bwd_chunk_kernel(const __grid_constant__ DevGroup g, const __grid_constant__ ApplyArgs a) {
     __shared__ float4 red[kApplyThreads];
-    const uint32_t nchunks = a.counters[3];
-    for (uint32_t ci = blockIdx.x; ci < nchunks; ci += gridDim.x) {
-        const uint32_t q = a.chunk_q[ci];
-        const uint32_t run = a.long_list[q];
-        const uint32_t c = ci - a.long_cbase[q];
-        const uint32_t s = a.run_start[run] + c * kChunk;
-        const uint32_t run_end = a.run_start[run + 1];
-        const uint32_t e = min(run_end, s + (uint32_t)kChunk);
-        const DevFeature &f = g.f[find_feature(g, a.keys[s])];
-        const int G = f.G;
-        const int g_lane = threadIdx.x & (G - 1);
-        const uint32_t slot_id = threadIdx.x / G;
-        const uint32_t nslots = kApplyThreads / G;
-        const bool col_ok = g_lane * f.vec < f.D;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (uint32_t p0 = s + slot_id; p0 < e; p0 += 4 * nslots) {
-            uint32_t bag[4];
-            float coef[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t p = p0 + j * nslots;
-                bag[j] = 0; coef[j] = 0.f;
-                if (p < e) {
-                    const uint32_t slot = a.vals[p];
-                    bag[j] = slot / (uint32_t)f.L;
-                    coef[j] = slot_coef(f, slot, bag[j]);
-                }
-            }
-            float4 v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (col_ok && p0 + j * nslots < e) v[j] = load_grad_part(g, f, bag[j], g_lane);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                acc.x = fmaf(coef[j], v[j].x, acc.x);
-                acc.y = fmaf(coef[j], v[j].y, acc.y);
-                acc.z = fmaf(coef[j], v[j].z, acc.z);
-                acc.w = fmaf(coef[j], v[j].w, acc.w);
-            }
-        }
-        red[threadIdx.x] = acc;
-        __syncthreads();
-        for (int stride = kApplyThreads / 2; stride >= G; stride >>= 1) {
-            if ((int)threadIdx.x < stride) {
-                const float4 o = red[threadIdx.x + stride];
-                float4 m = red[threadIdx.x];
-                m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
-                red[threadIdx.x] = m;
-            }
-            __syncthreads();
-        }
-        if ((int)threadIdx.x < G) reinterpret_cast<float4 *>(a.partials + (size_t)ci * a.row_floats)[threadIdx.x] = red[threadIdx.x];
-        __syncthreads();
-    }
-}
-
-// Long runs, stage 2: one team per queued run adds its chunk partials in chunk order and updates the row.
-__global__ void __launch_bounds__(kApplyThreads)
-    emb_bwd_long_finish_kernel(const __grid_constant__ DevGroup g, const __grid_constant__ ApplyArgs a_in) {
+    __shared__ uint32_t ticket;
+    __shared__ uint32_t finish_q;
     ApplyArgs a = a_in;
     if (a.hyper_dev != nullptr) a.h = *a.hyper_dev;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t num_runs = a.counters[1], nlong_chunks = a.counters[3], nmed = a.counters[4];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.num_unique != nullptr) *a.num_unique = (int64_t)num_runs;
+
+    // tier 1: chunks of long runs (whole block per chunk)
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) ticket = atomicAdd(&a.counters[5], 1u);
+        __syncthreads();
+        const uint32_t ci = ticket;
+        if (ci >= nlong_chunks) break;
+        chunk_task(g, a, ci, red);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t q = a.chunk_q[ci];
+            const uint32_t run = a.long_list[q];
+            const uint32_t nch = (a.run_start[run + 1] - a.run_start[run] + kChunk - 1) / kChunk;
+            finish_q = (atomicAdd(&a.long_done[q], 1u) == nch - 1) ? q : 0xffffffffu;
+        }
+        __syncthreads();
+        if (finish_q != 0xffffffffu && warp == 0) {
+            __threadfence();
+            long_finish(g, a, finish_q, lane);
+        }
+    }
+    // tier 2: medium runs, one per warp, eight per ticket
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) ticket = atomicAdd(&a.counters[6], (uint32_t)(kApplyThreads / kWarp));
+        __syncthreads();
+        const uint32_t base = ticket;
+        if (base >= nmed) break;
+        if (base + warp < nmed) medium_run(g, a, a.med_list[base + warp], lane);
+    }
+    // tier 3: short runs, one per team; a ticket covers kShortBatch rounds of the block's teams
     const int TG = a.team;
-    const int lane = threadIdx.x & 31;
     const int t = lane & (TG - 1);
     const int team_in_warp = lane / TG;
     const unsigned mask = TG == 32 ? kFull : (((1u << TG) - 1u) << (team_in_warp * TG));
-    const uint32_t nlong = a.counters[2];
-    const int64_t teams_total = (int64_t)gridDim.x * (kApplyThreads / TG);
-    for (int64_t q = ((int64_t)blockIdx.x * kApplyThreads + threadIdx.x) / TG; q < nlong; q += teams_total) {
-        const uint32_t run = a.long_list[q];
-        const uint32_t s = a.run_start[run], e = a.run_start[run + 1];
-        const uint32_t nch = (e - s + kChunk - 1) / kChunk;
-        const uint32_t cbase = a.long_cbase[q];
-        const uint32_t key = a.keys[s];
-        const int fi = find_feature(g, key);
-        const DevFeature &f = g.f[fi];
-        const bool col_ok = t < f.G && t * f.vec < f.D;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t < f.G) {
-            for (uint32_t c = 0; c < nch; ++c) {
-                const float4 v = reinterpret_cast<const float4 *>(a.partials + (size_t)(cbase + c) * a.row_floats)[t];
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    const uint32_t teams = kApplyThreads / TG;
+    constexpr uint32_t kShortBatch = 4;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) ticket = atomicAdd(&a.counters[7], teams * kShortBatch);
+        __syncthreads();
+        const uint32_t base = ticket;
+        if (base >= num_runs) break;
+#pragma unroll 1
+        for (uint32_t r = 0; r < kShortBatch; ++r) {
+            const uint32_t run = base + r * teams + threadIdx.x / TG;
+            if (run < num_runs) {
+                const uint32_t s = a.run_start[run], e = a.run_start[run + 1];
+                if (e - s <= (uint32_t)kTeamRun) short_run(g, a, run, s, e, TG, t, team_in_warp, mask);
             }
         }
-        update_row(g, f, a, run, fi, key - f.row_base, t, col_ok, acc, mask, TG);
     }
-}
-
-// helper streams / events of the calling thread's current device (created once, never destroyed)
-struct TierStreams {
-    cudaStream_t s[2];
-    cudaEvent_t fork, join[2];
-};
-static TierStreams *tier_streams() {
-    static thread_local TierStreams per_device[16];
-    static thread_local bool ready[16] = {};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) {
-        set_error("cannot resolve the current CUDA device");
-        return nullptr;
-    }
-    if (!ready[dev]) {
-        TierStreams &t = per_device[dev];
-        bool ok = cudaStreamCreateWithFlags(&t.s[0], cudaStreamNonBlocking) == cudaSuccess &&
-                  cudaStreamCreateWithFlags(&t.s[1], cudaStreamNonBlocking) == cudaSuccess &&
-                  cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) == cudaSuccess &&
-                  cudaEventCreateWithFlags(&t.join[0], cudaEventDisableTiming) == cudaSuccess &&
-                  cudaEventCreateWithFlags(&t.join[1], cudaEventDisableTiming) == cudaSuccess;
-        if (!ok) {
-            set_error("cannot create helper streams: %s", cudaGetErrorString(cudaGetLastError()));
-            return nullptr;
-        }
-        ready[dev] = true;
-    }
-    return &per_device[dev];
 }
 
 }  // namespace ctr
@@ -604,6 +575,7 @@ extern "C" int ctr_emb_bwd_apply(const ctr_group_t *group, void *workspace, cons
     a.med_list = reinterpret_cast<uint32_t *>(ws + p.med_list);
     a.long_list = reinterpret_cast<uint32_t *>(ws + p.long_list);
     a.long_cbase = reinterpret_cast<uint32_t *>(ws + p.long_cbase);
+    a.long_done = reinterpret_cast<uint32_t *>(ws + p.long_done);
     a.chunk_q = reinterpret_cast<uint32_t *>(ws + p.chunk_q);
     a.partials = reinterpret_cast<float *>(ws + p.partials);
     a.row_floats = (int)p.row_floats;
@@ -626,21 +598,10 @@ extern "C" int ctr_emb_bwd_apply(const ctr_group_t *group, void *workspace, cons
     const int64_t cap = (int64_t)kNumSMs * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    // The three tiers touch disjoint rows: fork them onto two helper streams so that their latency-bound
-    // tails overlap, then join back into the caller's stream (capturable: the fork / join is all events).
-    TierStreams *ts = tier_streams();
-    if (ts == nullptr) return CTR_E_CUDA;
-    CTR_CUDA_OK(cudaEventRecord(ts->fork, stream));
-    CTR_CUDA_OK(cudaStreamWaitEvent(ts->s[0], ts->fork, 0));
-    CTR_CUDA_OK(cudaStreamWaitEvent(ts->s[1], ts->fork, 0));
-    note_launch(), emb_bwd_apply_kernel<<<(unsigned)blocks, kApplyThreads, 0, stream>>>(dg, a);
-    note_launch(), emb_bwd_medium_kernel<<<kNumSMs * 4, kApplyThreads, 0, ts->s[0]>>>(dg, a);
-    note_launch(), emb_bwd_chunk_kernel<<<kNumSMs * 4, kApplyThreads, 0, ts->s[1]>>>(dg, a);
-    note_launch(), emb_bwd_long_finish_kernel<<<kNumSMs, kApplyThreads, 0, ts->s[1]>>>(dg, a);
-    CTR_CUDA_OK(cudaEventRecord(ts->join[0], ts->s[0]));
-    CTR_CUDA_OK(cudaEventRecord(ts->join[1], ts->s[1]));
-    CTR_CUDA_OK(cudaStreamWaitEvent(stream, ts->join[0], 0));
-    CTR_CUDA_OK(cudaStreamWaitEvent(stream, ts->join[1], 0));
+    // tickets and per-long-run completion counters are rebuilt by every apply
+    CTR_CUDA_OK(cudaMemsetAsync(a.counters + 5, 0, 3 * sizeof(uint32_t), stream));
+    CTR_CUDA_OK(cudaMemsetAsync(a.long_done, 0, (size_t)p.max_long * sizeof(uint32_t), stream));
+    note_launch(), emb_bwd_apply_kernel<<<kNumSMs * 5, kApplyThreads, 0, stream>>>(dg, a);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }
