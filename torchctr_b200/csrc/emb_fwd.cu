@@ -177,6 +177,74 @@ __global__ void __launch_bounds__(kFwdThreads) emb_pool_fwd_kernel(const __grid_
     }
 }
 
+// ---- fast path: single-id bags, uniform width ------------------------------------------------------------
+// Every table of the group has L == 1, the same D = G * VEC, 16-byte aligned output slices (VEC == 4) and no
+// per-id weights (Criteo-shaped groups: BASELINE configs 2-4).  Bag-major: a team of G lanes owns one bag and
+// walks the tables four at a time -- four id loads, then four independent row loads, then four stores -- so
+// there is no per-feature block row, no shuffle and ~2 instructions per id instead of ~20; the dense block and
+// the zero padding of the same bag are written by the same team.
+template <int G, int VEC>
+__global__ void __launch_bounds__(kFwdThreads) emb_pool_fwd_l1_kernel(const __grid_constant__ DevGroup g) {
+    constexpr int kTeams = kFwdThreads / G;
+    constexpr int D = G * VEC;
+    const int t = threadIdx.x % G;
+    const int F = g.num_features;
+    const int extra_from = g.dense_col + g.dense_width;
+    for (int bag = blockIdx.x * kTeams + threadIdx.x / G; bag < g.B; bag += gridDim.x * kTeams) {
+        float *out_row = g.out + (size_t)bag * g.out_stride;
+        for (int f0 = 0; f0 < F; f0 += 4) {
+            int32_t row[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                row[j] = -1;
+                if (f0 + j < F) {
+                    const DevFeature &f = g.f[f0 + j];
+                    row[j] = map_index(f, __ldg(f.ids + bag));
+                    if (row[j] == -2) flag_status(g.status, CTR_STATUS_INDEX_OOB);
+                }
+            }
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row[j] >= 0) {
+                    const float *src = g.f[f0 + j].table + (size_t)(uint32_t)row[j] * D + t * VEC;
+                    if (VEC == 4) v[j] = __ldg(reinterpret_cast<const float4 *>(src));
+                    else v[j].x = __ldg(src);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (f0 + j < F) {
+                    float *dst = out_row + g.f[f0 + j].out_col + t * VEC;
+                    if (VEC == 4) *reinterpret_cast<float4 *>(dst) = v[j];
+                    else *dst = v[j].x;
+                    if (t == 0 && g.f[f0 + j].pooling == CTR_POOL_MEAN) g.f[f0 + j].bag_scale[bag] = 1.f;
+                }
+            }
+        }
+        for (int c = t; c < g.dense_width; c += G) out_row[g.dense_col + c] = __ldg(g.dense + (size_t)bag * g.dense_width + c);
+        if (g.zero_from >= 0)
+            for (int c = g.zero_from + t; c < (int)g.out_stride; c += G) out_row[c] = 0.f;
+    }
+    (void)extra_from;
+}
+
+// 0 when the group does not qualify, else the lane count G (VEC reported through *vec)
+static int l1_fast_path(const DevGroup &dg, int *vec) {
+    if (dg.num_features == 0) return 0;
+    const DevFeature &f0 = dg.f[0];
+    for (int i = 0; i < dg.num_features; ++i) {
+        const DevFeature &f = dg.f[i];
+        if (f.L != 1 || f.D != f0.D || f.id_weight != nullptr) return 0;
+        if (f.vec == 4 && !f.aligned) return 0;
+    }
+    *vec = f0.vec;
+    if (f0.vec == 4 && (f0.G == 4 || f0.G == 8 || f0.G == 16)) return f0.G;
+    if (f0.vec == 1 && f0.D == 1) return 1;
+    return 0;
+}
+
 // ---- standalone index kernels ----------------------------------------------------------
 
 __global__ void hash_bucket_kernel(const int64_t *__restrict__ ids, int64_t n, uint32_t buckets, uint32_t seed,
@@ -263,6 +331,20 @@ extern "C" int ctr_emb_pool_fwd(const ctr_group_t *group, void *stream) {
     if (rc != CTR_OK) return rc;
     const int extra_w = dg.dense_width + (dg.zero_from >= 0 ? (int)(dg.out_stride - dg.zero_from) : 0);
     if (dg.B == 0 || (dg.num_features == 0 && extra_w == 0)) return CTR_OK;
+    int vec = 0;
+    const int fastG = l1_fast_path(dg, &vec);
+    if (fastG > 0) {
+        const int teams = kFwdThreads / fastG;
+        const int blocks = grid_for(dg.B, teams, kNumSMs * 16);
+        cudaStream_t st = (cudaStream_t)stream;
+        note_launch();
+        if (vec == 1) emb_pool_fwd_l1_kernel<1, 1><<<blocks, kFwdThreads, 0, st>>>(dg);
+        else if (fastG == 4) emb_pool_fwd_l1_kernel<4, 4><<<blocks, kFwdThreads, 0, st>>>(dg);
+        else if (fastG == 8) emb_pool_fwd_l1_kernel<8, 4><<<blocks, kFwdThreads, 0, st>>>(dg);
+        else emb_pool_fwd_l1_kernel<16, 4><<<blocks, kFwdThreads, 0, st>>>(dg);
+        CTR_CUDA_OK(cudaGetLastError());
+        return CTR_OK;
+    }
     int64_t max_warps = 1;
     for (int i = 0; i < dg.num_features; ++i) {
         const DevFeature &f = dg.f[i];
