@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CTR_B200_ABI_VERSION 1
+#define CTR_B200_ABI_VERSION 2
 #define CTR_MAX_FEATURES 40 /* features per launch group (kernel-parameter budget) */
 
 /* status codes */
@@ -48,6 +48,7 @@ extern "C" {
 /* bits of the device-side status word (ctr_group_t.status, optional) */
 #define CTR_STATUS_INDEX_OOB 1u   /* a table index was >= num_rows (IndexError upstream) */
 #define CTR_STATUS_MAP_FULL 2u    /* vocabulary map ran out of slots                      */
+#define CTR_STATUS_NO_RUNS 4u     /* unique-row outputs asked of a plan built with CTR_PLAN_NO_RUNS */
 
 /* ctr_feature_t.index_kind */
 #define CTR_INDEX_DIRECT 0 /* ids are table rows                                          */
@@ -157,6 +158,11 @@ int64_t ctr_emb_bwd_workspace_bytes(const ctr_group_t *group);
  * lives inside `workspace` and stays valid until the workspace is reused.  It depends on
  * the ids only, so it can be applied to several tables that share those ids. */
 int ctr_emb_bwd_plan(const ctr_group_t *group, void *workspace, int64_t workspace_bytes, void *stream);
+/* Same with flags.  CTR_PLAN_NO_RUNS: sort only, skip the list of runs -- enough for a fused update that asks for
+ * no unique-row outputs (uniq_row == NULL), which is what a training step does. */
+#define CTR_PLAN_NO_RUNS 1u
+int ctr_emb_bwd_plan_ex(const ctr_group_t *group, void *workspace, int64_t workspace_bytes, uint32_t flags,
+                        void *stream);
 
 /* For every unique row touched: g = sum over its slots of coef * grad_out[bag, cols];
  * then the optimizer update of that row, in place.  `group->out` is grad_out here and the
@@ -224,6 +230,53 @@ int ctr_route_build(const ctr_group_t *group, int32_t world, const int64_t *base
  * (group->out is grad_out; every feature of the group has dim D). */
 int ctr_route_grad_gather(const ctr_group_t *group, int32_t world, const void *workspace, int64_t n, int32_t D,
                           float *g_send, void *stream);
+
+/* ---- row-sharded tables over peer memory (NVLink P2P inside the kernels, no all-to-all) -----------
+ * One process per GPU.  Every rank allocates its table shard, gradient buffer and routing lists with
+ * ctr_peer_alloc, exports them (ctr_peer_export -> 64-byte handle, exchanged by the host, e.g. with
+ * torch.distributed.all_gather_object) and maps the other ranks' buffers with ctr_peer_open.  The kernels
+ * below then read peer pointers directly; a host-side barrier (any collective on the stream) separates the
+ * phases.  Table f's row r lives on rank (r + f) mod world, at row  adj[owner * F + f] + (r + f) / world  of
+ * that rank's fused shard (all tables of the group back to back, same D). */
+#define CTR_MAX_WORLD 16
+#define CTR_PEER_HANDLE_BYTES 64
+int ctr_peer_alloc(int64_t bytes, void **ptr);          /* zero-filled device memory other processes can map */
+int ctr_peer_free(void *ptr);
+int ctr_peer_export(void *ptr, void *handle_out);       /* handle_out: CTR_PEER_HANDLE_BYTES bytes             */
+int ctr_peer_open(const void *handle, void **ptr);      /* in ANOTHER process than the one that exported       */
+int ctr_peer_close(void *ptr);
+
+typedef struct ctr_shard {
+    int32_t world, rank;
+    const int64_t *adj;        /* DEVICE i64 [world * num_features], see above                                  */
+} ctr_shard_t;
+
+/* ctr_emb_pool_fwd with every row read from its owner: tables[o] = fused shard of rank o (device pointers, the
+ * local one included).  The features' `table` fields are ignored; `num_rows` is the size of the FULL table. */
+int ctr_emb_pool_fwd_sharded(const ctr_group_t *group, const ctr_shard_t *shard, const float *const *tables,
+                             void *stream);
+
+/* Buckets this rank's id slots by owner (stable).  Outputs, to be placed in peer-visible memory:
+ *   counts u32 [CTR_MAX_WORLD + 1]  slots per owner (entry `world` = padding / invalid),
+ *   keys   u32 [S]  virtual row inside the owner's fused shard, owner-major, slot order inside an owner,
+ *   slots  u32 [S]  feature-relative slot (bag * L + l) of the same position. */
+int64_t ctr_route_p2p_workspace_bytes(const ctr_group_t *group);
+int ctr_route_p2p_build(const ctr_group_t *group, const ctr_shard_t *shard, uint32_t *counts, uint32_t *keys,
+                        uint32_t *slots, void *workspace, int64_t workspace_bytes, void *stream);
+
+/* Owner side of the backward.  `group` describes THIS rank's shard: feature f = the local rows of table f
+ * (table / state pointers into the fused shard, num_rows = local row count, L / out_col / D as on the
+ * requesters), B = per-rank batch.  The plan pulls the (key, slot) lists addressed to this rank from every
+ * peer's routing buffers (peer_counts / peer_keys / peer_slots: host arrays [world] of device pointers) and sorts
+ * them; the number of pairs stays on the device.  capacity_slots = world * S bounds it. */
+int64_t ctr_emb_bwd_p2p_workspace_bytes(const ctr_group_t *group, int32_t world);
+int ctr_emb_bwd_plan_p2p(const ctr_group_t *group, const ctr_shard_t *shard, const uint32_t *const *peer_counts,
+                         const uint32_t *const *peer_keys, const uint32_t *const *peer_slots, void *workspace,
+                         int64_t workspace_bytes, void *stream);
+/* Fused reduce + row update of the local shard; the gradient of a slot is read from the grad_out matrix of the
+ * rank that sent it: peer_grads[r] f32 [B, group->out_stride] (group->out is ignored). */
+int ctr_emb_bwd_apply_p2p(const ctr_group_t *group, const ctr_shard_t *shard, void *workspace, const ctr_opt_t *opt,
+                          const float *const *peer_grads, int64_t *num_unique, void *stream);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in names:
         assert hasattr(handle, name), f"{name} declared in ctr_b200.h but not exported"
     assert set(_lib.declared_symbols()) == set(names), "ctypes signature table out of sync with the header"
-    assert _lib.lib().ctr_abi_version() == 1
+    assert _lib.lib().ctr_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header(tmp_path):
@@ -107,3 +107,26 @@ def test_optimizer_binding_reads_torch_hyperparameters():
 def test_graft_entry_build():
     import __graft_entry__ as g
     g.build()
+
+
+def test_peer_shard_geometry_is_a_bijection():
+    """Row r of table f -> (owner (r + f) % P, adj[o, f] + (r + f) // P): every row lands on exactly one slot of
+    its owner's fused shard, inside that table's range, in row order (what the kernels' shard_vrow computes)."""
+    from torchctr_b200.parallel.peer import owned_rows, shard_geometry
+    for world in (1, 2, 3, 4, 8, 16):
+        Vs = [37, 101, 2, 1000, 5, 1]
+        base, total, adj = shard_geometry(Vs, world)
+        F = len(Vs)
+        for o in range(world):
+            assert total[o] == base[o][-1] + max(owned_rows(Vs[-1], F - 1, o, world)[1], 1)
+        for f, v in enumerate(Vs):
+            seen = set()
+            for r in range(v):
+                o = (r + f) % world
+                vr = int(adj[o * F + f]) + (r + f) // world
+                fr, n = owned_rows(v, f, o, world)
+                assert base[o][f] <= vr < base[o][f] + n
+                assert (r - fr) % world == 0 and vr - base[o][f] == (r - fr) // world
+                assert (o, vr) not in seen
+                seen.add((o, vr))
+            assert len(seen) == v

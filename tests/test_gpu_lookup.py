@@ -294,3 +294,57 @@ def test_full_size_sgd_equals_index_add():
         close(ft.table, ref, rtol=2e-5)                       # atomics in index_add: order differs
         nuniq += int(torch.unique(s["ids"]).numel())
     assert U == nuniq
+
+
+@pytest.mark.parametrize("D", [1, 3, 16, 32, 64, 128])
+@pytest.mark.parametrize("pattern", ["one_row", "distinct", "blocks", "zipf"])
+def test_sweep_handles_every_run_length(D, pattern):
+    """The segmented sweep must not care how the sorted positions split into runs: one giant run that crosses
+    every warp range, no repeats at all, runs of ragged lengths straddling range boundaries, Zipf."""
+    from oracle import embedding as oe
+    gen = torch.Generator().manual_seed(1000 + D)
+    B, L = 6000, 3
+    V = 2 * B * L
+    if pattern == "one_row":
+        ids = torch.full((B, L), 7, dtype=torch.int64)
+    elif pattern == "distinct":
+        ids = torch.randperm(V, generator=gen)[: B * L].reshape(B, L)
+    elif pattern == "blocks":
+        lens = torch.randint(1, 700, (200,), generator=gen)
+        vals = torch.repeat_interleave(torch.randperm(V, generator=gen)[:200], lens)[: B * L]
+        ids = torch.cat([vals, torch.randint(0, V, (B * L - vals.numel(),), generator=gen)])
+        ids = ids[torch.randperm(B * L, generator=gen)].reshape(B, L)
+    else:
+        u = torch.rand(B, L, generator=gen)
+        ids = (V ** u - 1).long().clamp(0, V - 1)
+    ids[torch.rand(B, L, generator=gen) < 0.1] = -100
+    table = torch.randn(V, D, generator=gen)
+    gout = torch.randn(B, (D + 3) // 4 * 4, generator=gen)
+    feats, uf, ur, rg, U = run_bwd([dict(ids=ids, table=table)], B, gout, "sgd", dict(lr=0.25))
+    rows, grads = oe.unique_row_grads(ids, gout[:, :D], V)
+    assert U == rows.numel() and torch.equal(ur.long(), rows)
+    close(rg[:, :D], grads, rtol=2e-5)
+    ref = table.clone()
+    ref[rows] -= 0.25 * grads
+    close(feats[0].table, ref, rtol=2e-5)
+
+
+def test_sort_only_plan_counts_unique_rows_and_updates():
+    """CTR_PLAN_NO_RUNS (what a fused training step uses): same update, num_unique still reported."""
+    from torchctr_b200 import ops
+    gen = torch.Generator().manual_seed(77)
+    B, V, D = 30000, 5000, 16
+    u = torch.rand(B, 1, generator=gen)
+    ids = (V ** u - 1).long().clamp(0, V - 1)
+    table = torch.randn(V, D, generator=gen)
+    gout = torch.randn(B, D, generator=gen)
+    t = table.cuda()
+    spec = ops.FeatureSpec(ids=ids.cuda(), table=t, num_rows=V, D=D, out_col=0)
+    call = ops.make_group([spec], B, gout.cuda(), D)
+    ws = torch.empty(ops.emb_bwd_workspace_bytes(call) + 256, dtype=torch.uint8, device="cuda")
+    ops.emb_bwd_plan(call, ws, runs=False)
+    nu = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ops.emb_bwd_apply(call, ws, ops.make_opt("sgd", lr=0.5), num_unique=nu)
+    ref = table.cuda().index_add(0, ids.cuda()[:, 0], gout.cuda(), alpha=-0.5)
+    close(t, ref, rtol=2e-5)
+    assert int(nu.item()) == int(torch.unique(ids).numel())

@@ -1,0 +1,127 @@
+"""Row-sharded tables over peer memory (torchctr_b200.parallel.peer): every kernel of the multi-rank path --
+sharded lookup, owner bucketing, owner-side pull + sort + fused update with device-side counts -- run here with
+the ranks as THREADS of one process on one GPU (ThreadTransport), checked against the single-table oracle on the
+global batch.  The 2-GPU run of the same module over CUDA IPC is tests/test_sharded.py::test_peer_two_gpus."""
+import threading
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5     # relative to the largest reference magnitude (fp32 sums of up to ~100 gradients per hot row)
+
+
+def _close(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    return got.shape == ref.shape and float((got - ref).abs().max()) <= RTOL * max(float(ref.abs().max()), 1e-30)
+
+
+def _problem(world, seed=5):
+    gen = torch.Generator().manual_seed(seed)
+    Vs, Ls, D, B = [37, 101, 2, 1000, 5000], [1, 6, 1, 3, 1], 16, 300
+    full16 = [torch.randn(v, D, generator=gen) for v in Vs]
+    full1 = [torch.randn(v, 1, generator=gen) for v in Vs]
+    ids_all, g16_all, g1_all = [], [], []
+    for r in range(world):
+        ids = []
+        for v, L in zip(Vs, Ls):
+            t = torch.randint(0, v, (B, L), generator=gen)
+            if L > 1:
+                t[torch.rand(B, L, generator=gen) < 0.3] = -100
+            t[:, 0] = torch.randint(0, min(v, 3), (B,), generator=gen)       # hot rows
+            ids.append(t)
+        ids_all.append(ids)
+        g16_all.append(torch.randn(B, len(Vs) * D + 4, generator=gen))
+        g1_all.append(torch.randn(B, 8, generator=gen))
+    dense = torch.randn(B, 3, generator=gen)
+    return Vs, Ls, D, B, full16, full1, ids_all, g16_all, g1_all, dense
+
+
+def _rank_main(rank, world, shared, prob, kind, errors, steps):
+    try:
+        from oracle import embedding as oe
+        from torchctr_b200.nn.embedding import EmbeddingTable
+        from torchctr_b200.parallel.peer import PeerShardedTables, ThreadTransport, owned_rows
+        Vs, Ls, D, B, full16, full1, ids_all, g16_all, g1_all, dense = prob
+        dev = torch.device("cuda", 0)
+        tr = ThreadTransport(shared, rank, dev)
+        names = [f"f{i}" for i in range(len(Vs))]
+        tabs16 = [EmbeddingTable(v, D, _weight=w.clone()) for v, w in zip(Vs, full16)]
+        tabs1 = [EmbeddingTable(v, 1, _weight=w.clone()) for v, w in zip(Vs, full1)]
+        st = PeerShardedTables(names, [tabs16, tabs1], tr, dev).train()
+        opt = torch.optim.SGD(list(st.shards), lr=0.5) if kind == "sgd" else torch.optim.Adagrad(list(st.shards), lr=0.5)
+        st.bind_optimizer(opt, kind=kind)
+        feats = {n: t for n, t in zip(names, ids_all[rank])}
+        w16 = [w.clone() for w in full16]
+        w1 = [w.clone() for w in full1]
+        acc16 = [torch.zeros_like(w) for w in full16]
+        acc1 = [torch.zeros_like(w) for w in full1]
+        for step in range(steps):
+            # the autograd engine runs every CUDA backward of a process on ONE thread per device, so ranks that are
+            # threads cannot meet at a barrier inside backward(): drive the two halves of the Function directly
+            ids_dev = [feats[n].to(dev) for n in names]
+            x, first = st._forward(ids_dev, dense.to(dev))
+            ref_x = torch.cat([oe.pooled_lookup(i, w) for i, w in zip(ids_all[rank], w16)] + [dense], 1)
+            ref_1 = torch.cat([oe.pooled_lookup(i, w) for i, w in zip(ids_all[rank], w1)], 1)
+            width = ref_x.shape[1]
+            assert x.shape[1] % 4 == 0 and float(x[:, width:].abs().sum()) == 0.0
+            err16 = (x[:, :width].cpu() - ref_x).abs()
+            per_feature = [round(float(err16[:, f * D:(f + 1) * D].max()), 6) for f in range(len(Vs))]
+            assert _close(x[:, :width], ref_x), \
+                f"forward D=16 step {step}: max abs err per table {per_feature}, scale {float(ref_x.abs().max()):.2f}"
+            assert _close(first[:, :len(Vs)], ref_1), f"forward D=1 step {step}"
+            g16 = torch.zeros(B, x.shape[1])
+            g16[:, :len(Vs) * D] = g16_all[rank][:, :len(Vs) * D]
+            g1 = g1_all[rank][:, :first.shape[1]].contiguous()
+            st._backward((g16.to(dev), g1.to(dev)))
+            torch.cuda.synchronize()
+            # oracle: the optimizer on the touched rows with the gradients of ALL ranks
+            for ws, accs, gouts, Dw in ((w16, acc16, g16_all, D), (w1, acc1, g1_all, 1)):
+                for f, v in enumerate(Vs):
+                    dg = torch.zeros(v, Dw)
+                    for r in range(world):
+                        dg += oe.dense_table_grad(ids_all[r][f], gouts[r][:, f * Dw:(f + 1) * Dw], v)
+                    if kind == "sgd":
+                        ws[f] -= 0.5 * dg
+                    else:
+                        touched = torch.zeros(v, dtype=torch.bool)
+                        for r in range(world):
+                            flat = ids_all[r][f].reshape(-1)
+                            touched[flat[flat >= 0]] = True
+                        accs[f] += dg * dg
+                        upd = 0.5 * dg / (accs[f].sqrt() + 1e-10)
+                        ws[f][touched] -= upd[touched]
+            for w, ws in enumerate((w16, w1)):
+                for f, v in enumerate(Vs):
+                    fr, rows = st.local_rows_of(w, f)
+                    expect = ws[f][fr::world]
+                    assert rows.shape == expect.shape, (rows.shape, expect.shape)
+                    assert _close(rows, expect), \
+                        f"update width {w} table {f} step {step}: max abs err {float((rows.cpu() - expect).abs().max()):.3e}"
+            assert int(st.status.item()) == 0
+    except BaseException as e:          # noqa: BLE001 -- reported by the main thread
+        errors.append((rank, repr(e)[:600]))
+        try:
+            shared.barrier.abort()
+        except Exception:
+            pass
+
+
+@pytest.mark.parametrize("world,kind", [(2, "sgd"), (3, "sgd"), (4, "adagrad")])
+def test_peer_sharded_threads(world, kind):
+    import faulthandler
+    import sys
+    from torchctr_b200.parallel.peer import ThreadTransport
+    faulthandler.dump_traceback_later(100, exit=True, file=sys.stderr)      # a stuck rank must not hang the suite
+    shared = ThreadTransport.Shared(world)
+    prob = _problem(world)
+    errors = []
+    threads = [threading.Thread(target=_rank_main, args=(r, world, shared, prob, kind, errors, 2)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=90)
+    faulthandler.cancel_dump_traceback_later()
+    assert not errors, errors
+    assert all(not t.is_alive() for t in threads)

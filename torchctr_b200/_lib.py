@@ -17,6 +17,8 @@ MAX_FEATURES = 40
 OK = 0
 STATUS_INDEX_OOB = 1
 STATUS_MAP_FULL = 2
+STATUS_NO_RUNS = 4
+PLAN_NO_RUNS = 1
 
 INDEX_DIRECT, INDEX_HASH, INDEX_REMAP = 0, 1, 2
 POOL_SUM, POOL_MEAN = 0, 1
@@ -49,6 +51,14 @@ class Group(C.Structure):
     ]
 
 
+class Shard(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("adj", C.c_void_p)]
+
+
+MAX_WORLD = 16
+PEER_HANDLE_BYTES = 64
+
+
 class Opt(C.Structure):
     _fields_ = [("kind", C.c_int32), ("step", C.c_int32), ("lr", C.c_double), ("eps", C.c_double),
                 ("beta1", C.c_double), ("beta2", C.c_double), ("device_hyper", C.c_void_p)]
@@ -73,6 +83,7 @@ _SIGNATURES = {
     "ctr_ids_minmax": (C.c_int, [_P, C.c_int64, _P, _P]),
     "ctr_emb_bwd_workspace_bytes": (C.c_int64, [C.POINTER(Group)]),
     "ctr_emb_bwd_plan": (C.c_int, [C.POINTER(Group), _P, C.c_int64, _P]),
+    "ctr_emb_bwd_plan_ex": (C.c_int, [C.POINTER(Group), _P, C.c_int64, C.c_uint32, _P]),
     "ctr_emb_bwd_apply": (C.c_int, [C.POINTER(Group), _P, C.POINTER(Opt), _P, _P, _P, C.c_int64, _P, _P]),
     "ctr_vocab_fit_workspace_bytes": (C.c_int64, [C.c_int64]),
     "ctr_vocab_fit": (C.c_int, [C.POINTER(VocabMap), _P, C.c_int64, C.c_int32, _P, _P, _P, _P, C.c_int64, _P]),
@@ -90,6 +101,18 @@ _SIGNATURES = {
     "ctr_route_workspace_bytes": (C.c_int64, [C.POINTER(Group), C.c_int32]),
     "ctr_route_build": (C.c_int, [C.POINTER(Group), C.c_int32, _P, _P, _P, _P, _P, C.c_int64, _P]),
     "ctr_route_grad_gather": (C.c_int, [C.POINTER(Group), C.c_int32, _P, C.c_int64, C.c_int32, _P, _P]),
+    "ctr_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    "ctr_peer_free": (C.c_int, [_P]),
+    "ctr_peer_export": (C.c_int, [_P, _P]),
+    "ctr_peer_open": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
+    "ctr_peer_close": (C.c_int, [_P]),
+    "ctr_emb_pool_fwd_sharded": (C.c_int, [C.POINTER(Group), C.POINTER(Shard), C.POINTER(C.c_void_p), _P]),
+    "ctr_route_p2p_workspace_bytes": (C.c_int64, [C.POINTER(Group)]),
+    "ctr_route_p2p_build": (C.c_int, [C.POINTER(Group), C.POINTER(Shard), _P, _P, _P, _P, C.c_int64, _P]),
+    "ctr_emb_bwd_p2p_workspace_bytes": (C.c_int64, [C.POINTER(Group), C.c_int32]),
+    "ctr_emb_bwd_plan_p2p": (C.c_int, [C.POINTER(Group), C.POINTER(Shard), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_void_p), _P, C.c_int64, _P]),
+    "ctr_emb_bwd_apply_p2p": (C.c_int, [C.POINTER(Group), C.POINTER(Shard), _P, C.POINTER(Opt), C.POINTER(C.c_void_p), _P, _P]),
 }
 
 _lib = None

@@ -66,7 +66,32 @@ struct DevGroup {
     int32_t dense_col;
     int32_t zero_from;
     uint32_t *status;
+    // row-sharded tables (world > 1): row r of table f lives on rank (r + f) % world, at row
+    // shard_adj[owner * num_features + f] + (r + f) / world of that rank's fused shard peer_tables[owner]
+    int32_t world;
+    int32_t rank;
+    const int64_t *shard_adj;
+    const float *peer_tables[CTR_MAX_WORLD];
 };
+
+// Validates a ctr_shard_t and attaches it to a lowered group.
+int attach_shard(DevGroup *g, const ctr_shard_t *shard, const float *const *tables);
+
+// (table f, row) -> owner rank and row inside the owner's fused shard
+__device__ __forceinline__ int64_t shard_vrow(const DevGroup &g, int fi, uint32_t row, uint32_t *owner) {
+    const uint32_t r = row + (uint32_t)fi;
+    const uint32_t o = r % (uint32_t)g.world;
+    *owner = o;
+    return __ldg(g.shard_adj + (size_t)o * g.num_features + fi) + (int64_t)(r / (uint32_t)g.world);
+}
+
+// address of (table f, row): the local table, or the owner's shard through its peer mapping
+__device__ __forceinline__ const float *table_row(const DevGroup &g, const DevFeature &f, int fi, int32_t row) {
+    if (g.world <= 1) return f.table + (size_t)(uint32_t)row * f.D;
+    uint32_t o;
+    const int64_t v = shard_vrow(g, fi, (uint32_t)row, &o);
+    return g.peer_tables[o] + v * f.D;
+}
 
 // Validates a ctr_group_t and lowers it to the device view.  need_tables: table pointers must
 // be non-null.  Returns CTR_OK or a negative code.

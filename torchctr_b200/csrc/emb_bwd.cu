@@ -4,19 +4,27 @@
 // the whole-table optimizer.step() of torchctr/trainer.py:303.  No dense [V, D] gradient is
 // ever built:
 //   plan   keygen (row key = table base + mapped row, value = slot) -> stable radix sort ->
-//          runs of equal keys (= unique rows) listed by a head-flag scan;
-//   apply  one team of lanes per unique row sums coef * grad_out[bag] over the run in slot
-//          order (deterministic), then applies SGD / Adagrad / row-wise Adagrad / lazy Adam
-//          to that row in place.  Runs longer than kLongRun (hot Zipf rows) are queued, cut
-//          into chunks of kChunk positions that one block each reduces with a fixed-order
-//          shared-memory tree, and finished by a team that adds the chunk partials in order.
+//          (optionally) runs of equal keys listed by a head-flag scan;
+//   apply  a position-parallel segmented sweep over the sorted pairs.  Every warp owns a range
+//          of consecutive sorted positions; a team of G lanes gathers grad_out[bag] of one
+//          position (all gathers independent, four in flight per lane), teams combine equal
+//          keys with a segmented shuffle scan, a register carry joins the sub-steps, and the
+//          team that holds the last position of a run applies SGD / Adagrad / row-wise
+//          Adagrad / lazy Adam to that row in place.  Work per warp does not depend on the run
+//          lengths, so Zipf-hot rows cost the same per position as cold ones.  Runs that cross
+//          a range boundary leave per-range partial sums; a small fix-up kernel adds them in
+//          range order and updates those rows.  Summation order is fixed by the layout, so the
+//          result is deterministic.
+#include <stdlib.h>
+
 #include "sort.cuh"
 
 namespace ctr {
 
-constexpr int kTeamRun = 8;    // runs up to this length: one team of lanes (short-run kernel)
-constexpr int kLongRun = 256;  // up to this length: one warp per run; longer: chunked block reduction
 constexpr int kApplyThreads = 256;
+constexpr int kApplyWarps = kApplyThreads / kWarp;
+constexpr uint32_t kInvalidKey = 0xffffffffu;
+constexpr int kMinRange = 32;   // sorted positions per warp range: at least this many
 
 // ---- workspace layout ---------------------------------------------------------------------
 struct PlanLayout {
@@ -26,15 +34,18 @@ struct PlanLayout {
     // offsets in bytes from the workspace base
     int64_t counters, keys_a, keys_b, vals_a, vals_b, counts, spine, run_start;
     // apply-time scratch (rebuilt by every apply; sized by the group being applied)
-    int64_t med_list, long_list, long_cbase, chunk_q, long_done, partials, max_med, max_long, max_chunks, row_floats, total;
+    int64_t range_flags, tail_part, max_ranges, row_floats, total;
 };
-// counters (u32): [0] runs, [1] unique valid rows, [2] long-run queue, [3] chunk queue, [4] medium-run queue
+// counters (u32): [0] runs, [1] unique valid rows, [2] 1 when run_start was built by the plan, [3] number of
+// pairs when it is only known on the device (sharded owner side); [8..] per-peer offsets of that gather
 constexpr int kNumCounters = 8;
-constexpr int kChunk = 1024;   // sorted positions reduced by one block
+constexpr int kCounterWords = 64;
+constexpr int kMetaSrc = 8, kMetaDst = 24, kMetaCnt = 40;   // u32 [CTR_MAX_WORLD] each, inside the counter block
 
 static int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
 
-static PlanLayout plan_layout(const DevGroup &g) {
+// scale > 1: owner side of the sharded backward, where up to `scale` ranks' slots can land on this rank
+static PlanLayout plan_layout(const DevGroup &g, int scale = 1) {
     PlanLayout p{};
     int64_t S = 0;
     uint64_t rows = 0;
@@ -42,16 +53,17 @@ static PlanLayout plan_layout(const DevGroup &g) {
         S += (int64_t)g.B * g.f[i].L;
         rows += g.f[i].num_rows;
     }
+    S *= scale;
     p.S = S;
     int bits = 0;
     while ((rows >> bits) != 0) ++bits;  // bit_length(rows): 2^bits - 1 > every valid key
     p.key_bits = bits < 1 ? 1 : bits;
-    const int passes = (p.key_bits + kRadixBits - 1) / kRadixBits;
+    const int passes = sort_num_passes(p.key_bits);
     p.sorted_in_b = passes & 1;
     int64_t off = 0;
-    p.counters = off; off = align256(off + kNumCounters * 4);
-    p.keys_a = off; off = align256(off + S * 4);
-    p.keys_b = off; off = align256(off + S * 4);
+    p.counters = off; off = align256(off + kCounterWords * 4);
+    p.keys_a = off; off = align256(off + (S + 1) * 4);
+    p.keys_b = off; off = align256(off + (S + 1) * 4);
     p.vals_a = off; off = align256(off + S * 4);
     p.vals_b = off; off = align256(off + S * 4);
     const int64_t counts = sort_counts_elems(S);
@@ -59,93 +71,96 @@ static PlanLayout plan_layout(const DevGroup &g) {
     const int64_t spine = scan_spine_elems(counts > S ? counts : S) + 8;
     p.spine = off; off = align256(off + spine * 4);
     p.run_start = off; off = align256(off + (S + 2) * 4);
-    int row_floats = 4;  // one float4 slot per lane of the widest row, whatever the lane width
+    p.row_floats = 128;   // one float4 per lane of a full warp: any team width fits
+    p.max_ranges = S / kMinRange + 2;
+    p.range_flags = off; off = align256(off + (p.max_ranges + 64) * 4);   // 64 words of header: [0] = range ticket
+    // partial sums of runs that cross a range boundary: [range][team lane] float4
+    int row_floats = 4;
     for (int i = 0; i < g.num_features; ++i) row_floats = max(row_floats, g.f[i].G * 4);
     p.row_floats = row_floats;
-    p.max_med = S / (kTeamRun + 1) + 2;
-    p.max_long = S / (kLongRun + 1) + 2;
-    p.max_chunks = p.max_long + S / kChunk + 2;
-    p.med_list = off; off = align256(off + p.max_med * 4);
-    p.long_list = off; off = align256(off + p.max_long * 4);
-    p.long_cbase = off; off = align256(off + p.max_long * 4);
-    p.chunk_q = off; off = align256(off + p.max_chunks * 4);
-    p.long_done = off; off = align256(off + p.max_long * 4);
-    p.partials = off; off = align256(off + p.max_chunks * row_floats * 4);
+    p.tail_part = off; off = align256(off + p.max_ranges * row_floats * 4);
     p.total = off;
     return p;
 }
 
 // ---- keygen -------------------------------------------------------------------------------
+// Also builds the digit histograms of every radix pass (the sort then needs no pass of its own over the keys).
 __global__ void __launch_bounds__(256)
-    emb_keygen_kernel(const __grid_constant__ DevGroup g, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    emb_keygen_kernel(const __grid_constant__ DevGroup g, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                      uint32_t *__restrict__ hist, int passes, int bits) {
+    __shared__ uint32_t sh[kMaxPasses][kMaxRadix];
+    for (int i = threadIdx.x; i < kMaxPasses * kMaxRadix; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __syncthreads();
     const int fi = blockIdx.y;
     const DevFeature &f = g.f[fi];
     int64_t slot_base = 0;
     for (int i = 0; i < fi; ++i) slot_base += (int64_t)g.B * g.f[i].L;
     const int64_t n = (int64_t)g.B * f.L;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t row = map_index(f, __ldg(f.ids + j));
-        keys[slot_base + j] = row >= 0 ? f.row_base + (uint32_t)row : 0xffffffffu;
-        vals[slot_base + j] = (uint32_t)j;
-    }
-}
-
-__global__ void reset_counters_kernel(uint32_t *counters) {
-    if (threadIdx.x < kNumCounters) counters[threadIdx.x] = 0;
-}
-
-// Plan-time classification of the runs by length: <= kTeamRun stay with the short-run kernel, up to
-// kLongRun go to the warp-per-run queue, longer ones are cut into kChunk-position chunks.  Queue order is
-// scheduling-dependent, results are not (every run is reduced in slot order by whoever takes it).
-__global__ void __launch_bounds__(256)
-    classify_runs_kernel(const uint32_t *__restrict__ run_start, uint32_t *counters, uint32_t *__restrict__ med_list,
-                         uint32_t *__restrict__ long_list, uint32_t *__restrict__ long_cbase, uint32_t *__restrict__ chunk_q) {
-    const uint32_t num_runs = counters[1];
-    for (uint32_t run = blockIdx.x * blockDim.x + threadIdx.x; run < num_runs; run += gridDim.x * blockDim.x) {
-        const uint32_t len = run_start[run + 1] - run_start[run];
-        if (len <= (uint32_t)kTeamRun) continue;
-        if (len <= (uint32_t)kLongRun) {
-            med_list[atomicAdd(&counters[4], 1u)] = run;
-        } else {
-            const uint32_t nch = (len + kChunk - 1) / kChunk;
-            const uint32_t q = atomicAdd(&counters[2], 1u);
-            const uint32_t cbase = atomicAdd(&counters[3], nch);
-            long_list[q] = run;
-            long_cbase[q] = cbase;
-            for (uint32_t c = 0; c < nch; ++c) chunk_q[cbase + c] = q;
+    const int lane = threadIdx.x & 31;
+    const uint32_t dmask = (1u << bits) - 1u;
+    const int64_t nround = (n + 31) / 32 * 32;   // whole warps iterate together (match.any below)
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += (int64_t)gridDim.x * blockDim.x) {
+        const bool valid = j < n;
+        uint32_t key = kInvalidKey;
+        if (valid) {
+            const int32_t row = map_index(f, __ldg(f.ids + j));
+            if (row >= 0) key = f.row_base + (uint32_t)row;
+            keys[slot_base + j] = key;
+            vals[slot_base + j] = (uint32_t)j;
+        }
+        for (int p = 0; p < passes; ++p) {
+            const uint32_t d = (key >> (p * bits)) & dmask;
+            const uint32_t peers = __match_any_sync(kFull, valid ? d : (uint32_t)(kMaxRadix + lane));
+            if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[p][d], (uint32_t)__popc(peers));
         }
     }
+    __syncthreads();
+    const int radix = 1 << bits;
+    for (int i = threadIdx.x; i < passes * radix; i += blockDim.x) {
+        const uint32_t c = sh[i / radix][i % radix];
+        if (c) atomicAdd(&hist[(i / radix) * kMaxRadix + (i % radix)], c);
+    }
+}
+
+__global__ void reset_counters_kernel(uint32_t *counters, uint32_t runs_built) {
+    if (threadIdx.x < kNumCounters) counters[threadIdx.x] = threadIdx.x == 2 ? runs_built : 0u;
 }
 
 // ---- apply ----------------------------------------------------------------------------------
 struct ApplyArgs {
     const uint32_t *keys;       // sorted
     const uint32_t *vals;       // sorted with the keys: slot inside the feature (bag * L + l)
-    const uint32_t *run_start;
+    const uint32_t *run_start;  // only read when uniq outputs are requested
     uint32_t *counters;
-    uint32_t *med_list;         // [q] -> run (medium runs, one warp each)
-    uint32_t *long_list;        // [q] -> run
-    uint32_t *long_cbase;       // [q] -> first chunk of the run
-    uint32_t *long_done;        // [q] -> chunks finished so far (zeroed by every apply)
-    uint32_t *chunk_q;          // [chunk] -> q
-    float *partials;            // [chunk, row_floats]
+    uint32_t *ticket;           // next range to hand out (zeroed by every apply)
+    uint32_t *range_flags;      // [range] 0: not finished yet, 1: finished, 3: finished and tail_part holds the open run
+    float *tail_part;           // [range, row_floats]
     int row_floats;
+    uint32_t S;                 // sorted positions (upper bound when S_dev is set)
+    const uint32_t *S_dev;      // device-side count of sorted positions (sharded owner side), or null
+    const float *peer_grads[CTR_MAX_WORLD];   // sharded owner side: grad_out of every rank (slot's top 4 bits = rank)
+    int p2p;
+    uint32_t range;             // positions per warp range (multiple of the positions per outer iteration)
+    uint32_t num_ranges;
     int32_t *uniq_feature;
     int32_t *uniq_row;
     float *row_grad;
     int64_t row_grad_stride;
-    int64_t *num_unique;
+    unsigned long long *num_unique;
     int kind;
     ctr_hyper_t h;              // used when hyper_dev == nullptr
     const ctr_hyper_t *hyper_dev;  // device copy read at run time (CUDA-graph replays see new values)
-    int team;                   // lanes per run in the short-run kernel (max G of the group)
+    int team;                   // lanes per sorted position (max G of the group), power of two
+    uint32_t *status;           // group status word (may be null)
 };
 
-__device__ __forceinline__ int find_feature(const DevGroup &g, uint32_t key) {
-    int lo = 0, hi = g.num_features - 1;
-    while (lo < hi) {  // last feature whose row_base <= key
+// last feature whose row_base <= key.  sf is the kernel's parameter copy of the features: sorted positions
+// next to each other almost always belong to one table, so these constant-bank reads are warp-uniform.
+__device__ __forceinline__ int find_feature(const DevFeature *sf, int nf, uint32_t key) {
+    int lo = 0, hi = nf - 1;
+    while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (g.f[mid].row_base <= key) lo = mid; else hi = mid - 1;
+        if (sf[mid].row_base <= key) lo = mid; else hi = mid - 1;
     }
     return lo;
 }
@@ -158,8 +173,9 @@ __device__ __forceinline__ float slot_coef(const DevFeature &f, uint32_t slot, u
     return c;
 }
 
-__device__ __forceinline__ float4 load_grad_part(const DevGroup &g, const DevFeature &f, uint32_t bag, int g_lane) {
-    const float *src = g.out + (int64_t)bag * g.out_stride + f.out_col;
+__device__ __forceinline__ float4 load_grad_part(const float *gout, int64_t gstride, const DevFeature &f, uint32_t bag,
+                                                 int g_lane) {
+    const float *src = gout + (int64_t)bag * gstride + f.out_col;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (f.vec == 4) {
         if (f.aligned) {
@@ -186,21 +202,36 @@ __device__ __forceinline__ float adam_elem(float w, float &m, float &v, float gr
     return w - a.h.adam_step_size * __fdiv_rn(m, __fsqrt_rn(v) + a.h.eps);
 }
 
-// Lanes [0, G) of a team hold the summed gradient of (feature f, row); mask names the team.
-__device__ __forceinline__ void update_row(const DevGroup &g, const DevFeature &f, const ApplyArgs &a, uint32_t run,
-                                           int fi, uint32_t row, int g_lane, bool col_ok, float4 gr, unsigned mask,
-                                           int team_lanes) {
-    if (a.uniq_row != nullptr && g_lane == 0) {
-        a.uniq_row[run] = (int32_t)row;
-        if (a.uniq_feature != nullptr) a.uniq_feature[run] = fi;
+// index of the run that contains sorted position p (uniq outputs only): last r with run_start[r] <= p
+__device__ __forceinline__ uint32_t run_of_position(const ApplyArgs &a, uint32_t p) {
+    uint32_t lo = 0, hi = a.counters[0];
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a.run_start[mid] <= p) lo = mid; else hi = mid;
     }
-    if (a.row_grad != nullptr && col_ok) {
-        float *dst = a.row_grad + (int64_t)run * a.row_grad_stride;
-        if (f.vec == 4) {
-            dst[4 * g_lane + 0] = gr.x; dst[4 * g_lane + 1] = gr.y;
-            dst[4 * g_lane + 2] = gr.z; dst[4 * g_lane + 3] = gr.w;
-        } else {
-            dst[g_lane] = gr.x;
+    return lo;
+}
+
+// Lanes [0, G) of a team hold the summed gradient of (feature f, row); mask names the team; pos is any sorted
+// position of the run (names the run when the unique-row outputs are requested).
+__device__ __forceinline__ void update_row(const DevFeature &f, const ApplyArgs &a, uint32_t pos, int fi, uint32_t row,
+                                           int g_lane, bool col_ok, float4 gr, unsigned mask, int team_lanes) {
+    if (a.uniq_row != nullptr && a.counters[2] == 0u) {   // plan was built without the run list
+        if (a.status != nullptr && g_lane == 0) atomicOr(a.status, CTR_STATUS_NO_RUNS);
+    } else if (a.uniq_row != nullptr) {
+        const uint32_t run = run_of_position(a, pos);
+        if (g_lane == 0) {
+            a.uniq_row[run] = (int32_t)row;
+            if (a.uniq_feature != nullptr) a.uniq_feature[run] = fi;
+        }
+        if (a.row_grad != nullptr && col_ok) {
+            float *dst = a.row_grad + (int64_t)run * a.row_grad_stride;
+            if (f.vec == 4) {
+                dst[4 * g_lane + 0] = gr.x; dst[4 * g_lane + 1] = gr.y;
+                dst[4 * g_lane + 2] = gr.z; dst[4 * g_lane + 3] = gr.w;
+            } else {
+                dst[g_lane] = gr.x;
+            }
         }
     }
     if (a.kind == CTR_OPT_NONE) return;
@@ -262,203 +293,279 @@ __device__ __forceinline__ void update_row(const DevGroup &g, const DevFeature &
     }
 }
 
-// ---- the three run-length tiers as device functions ------------------------------------------------
-// accumulate coef * grad_out[bag] over positions p0, p0 + stride, ... < e, four loads in flight
-__device__ __forceinline__ float4 strided_run_sum(const DevGroup &g, const DevFeature &f, const ApplyArgs &a, uint32_t p_first,
-                                                  uint32_t e, uint32_t stride, int g_lane, bool col_ok) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (uint32_t p0 = p_first; p0 < e; p0 += 4 * stride) {
-        uint32_t bag[4];
-        float coef[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t p = p0 + j * stride;
-            bag[j] = 0; coef[j] = 0.f;
-            if (p < e) {
-                const uint32_t slot = a.vals[p];
-                bag[j] = slot / (uint32_t)f.L;
-                coef[j] = slot_coef(f, slot, bag[j]);
+// one shared copy of the update code for the general (many-option) kernels
+__device__ __noinline__ void update_row_call(const DevFeature &f, const ApplyArgs &a, uint32_t pos, int fi, uint32_t row,
+                                             int g_lane, bool col_ok, float4 gr, unsigned mask, int team_lanes) {
+    update_row(f, a, pos, fi, row, g_lane, col_ok, gr, mask, team_lanes);
+}
+
+template <int VEC>
+__device__ __forceinline__ float4 shfl_up4(float4 v, int delta) {
+    float4 o;
+    o.x = __shfl_up_sync(kFull, v.x, delta);
+    if (VEC == 4) {
+        o.y = __shfl_up_sync(kFull, v.y, delta);
+        o.z = __shfl_up_sync(kFull, v.z, delta);
+        o.w = __shfl_up_sync(kFull, v.w, delta);
+    } else {
+        o.y = o.z = o.w = 0.f;
+    }
+    return o;
+}
+template <int VEC>
+__device__ __forceinline__ float4 shfl_idx4(float4 v, int src) {
+    float4 o;
+    o.x = __shfl_sync(kFull, v.x, src);
+    if (VEC == 4) {
+        o.y = __shfl_sync(kFull, v.y, src);
+        o.z = __shfl_sync(kFull, v.z, src);
+        o.w = __shfl_sync(kFull, v.w, src);
+    } else {
+        o.y = o.z = o.w = 0.f;
+    }
+    return o;
+}
+__device__ __forceinline__ void add4(float4 &x, const float4 &o) { x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w; }
+
+// range flags: plain relaxed accesses at gpu scope; the (rare) publisher of a partial sum fences before the store
+// and its reader fences after the spin, so the common case pays for no fence at all
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// The sweep.  A warp is P = 32 / TG teams of TG lanes.  An outer iteration covers Q = P * U consecutive sorted
+// positions, U = min(4, 32 / P) per team: lane i < Q loads the key / slot of position p0 + i, team t owns positions
+// p0 + t * U .. + U - 1.  Where runs end is known from one ballot (key != next key), so the reduction needs no key
+// traffic: a team adds up its own positions, the teams' trailing sums are combined with a segmented shuffle scan
+// whose segment flags come from the ballot, and every team then walks its positions once more, starting from what
+// flowed in from the left, and updates the row wherever a run ends.  `carry` joins the outer iterations.
+// Ranges are handed out by ticket so that a warp may wait for ranges before its own: the run that was open when
+// the range started is finished by the warp that sees its end, which adds the partial sums the earlier ranges
+// published (in range order) -- no second kernel.
+// VEC = 4: lanes hold float4 pieces of the rows (some feature has D % 4 == 0); VEC = 1: every feature is scalar-laned.
+// SIMPLE: every table has D % 4 == 0, 16-byte aligned gradient slices, L == 1, no per-id weight, sum pooling.
+template <int VEC, bool SIMPLE, bool INL>
+__global__ void __launch_bounds__(kApplyThreads, 3)
+    emb_bwd_sweep_kernel(const __grid_constant__ DevGroup g, const __grid_constant__ ApplyArgs a_in) {
+    __shared__ ApplyArgs sa;
+    __shared__ uint32_t s_first_range;
+    if (threadIdx.x == 0) {
+        sa = a_in;
+        if (a_in.hyper_dev != nullptr) sa.h = *a_in.hyper_dev;
+        s_first_range = atomicAdd(a_in.ticket, (uint32_t)kApplyWarps);
+    }
+    __syncthreads();
+    const ApplyArgs &a = sa;
+    const DevFeature *sf = g.f;
+    const int lane = threadIdx.x & 31;
+    const uint32_t w = s_first_range + (threadIdx.x >> 5);
+    if (w >= a.num_ranges) return;
+    const int nf = g.num_features;
+    const float *gout_local = g.out;
+    const int64_t gstride = g.out_stride;
+    const int TG = a.team;
+    const int P = kWarp / TG;
+    const int U = P >= 8 ? (kWarp / P < 4 ? kWarp / P : 4) : 4;
+    const int Q = P * U;
+    const int team = lane / TG;
+    const int t = lane & (TG - 1);
+    const unsigned tmask = TG == kWarp ? kFull : (((1u << TG) - 1u) << (team * TG));
+    const unsigned umask = (1u << U) - 1u;
+    const uint32_t S = a.S_dev != nullptr ? min(*a.S_dev, a.S) : a.S;
+    const uint32_t first = w * a.range;
+    if (first >= S) {                      // beyond the device-side count: nothing to do, nobody waits for this range
+        if (lane == 0) st_relaxed_u32(a.range_flags + w, 1u);
+        return;
+    }
+    const uint32_t end = min(first + a.range, S);
+    const uint32_t first_key = a.keys[first];
+    // the run at the start of the range began in an earlier range: its end (if inside) is finished by look-back
+    bool head_pending = first > 0 && first_key != kInvalidKey && a.keys[first - 1] == first_key;
+    bool have_head = false;                 // this team holds the sum of that run's part inside this range
+    float4 head_acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool carry_open = false;                // the position before p0 (inside this range) did not end a run
+    float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
+    int fi = 0;                             // per-team cache of the table the current key belongs to
+    uint32_t f_lo = 1, f_hi = 0;
+    uint32_t closed = 0;
+
+    uint32_t k = kInvalidKey, nk = kInvalidKey, slot = 0;
+    if (lane < Q && first + lane < end) {
+        k = a.keys[first + lane];
+        slot = a.vals[first + lane];
+        if (first + lane + 1 < S) nk = a.keys[first + lane + 1];
+    }
+    for (uint32_t p0 = first; p0 < end; p0 += Q) {
+        // the next outer iteration's keys are requested before this one's gradients (one latency off the chain)
+        uint32_t k_next = kInvalidKey, nk_next = kInvalidKey, slot_next = 0;
+        const uint32_t pn = p0 + Q + lane;
+        if (lane < Q && pn < end) {
+            k_next = a.keys[pn];
+            slot_next = a.vals[pn];
+            if (pn + 1 < S) nk_next = a.keys[pn + 1];
+        }
+        const bool is_tail = k != kInvalidKey && nk != k;
+        const unsigned tails = __ballot_sync(kFull, is_tail);
+        if (is_tail && a.kind != CTR_OPT_NONE) {
+            // this lane's position ends a run: pull the row (and its optimizer state) towards L2 now, so that the
+            // update at the end of the iteration does not wait for DRAM after the gradients already did
+            if (k < f_lo || k >= f_hi) {
+                fi = find_feature(sf, nf, k);
+                f_lo = sf[fi].row_base;
+                f_hi = f_lo + sf[fi].num_rows;
+            }
+            const DevFeature &f = sf[fi];
+            const size_t off = (size_t)(k - f_lo) * f.D;
+            for (int b = 0; b < f.D; b += 32) {
+                prefetch_l2(f.table + off + b);
+                if (a.kind == CTR_OPT_ADAGRAD || a.kind == CTR_OPT_ADAM) prefetch_l2(f.state0 + off + b);
+                if (a.kind == CTR_OPT_ADAM) prefetch_l2(f.state1 + off + b);
             }
         }
         float4 v[4];
+        uint32_t kk[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col_ok && p0 + j * stride < e) v[j] = load_grad_part(g, f, bag[j], g_lane);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            acc.x = fmaf(coef[j], v[j].x, acc.x);
-            acc.y = fmaf(coef[j], v[j].y, acc.y);
-            acc.z = fmaf(coef[j], v[j].z, acc.z);
-            acc.w = fmaf(coef[j], v[j].w, acc.w);
-        }
-    }
-    return acc;
-}
-
-// Short run (<= kTeamRun): one team of TG lanes, slot order.
-__device__ __forceinline__ void short_run(const DevGroup &g, const ApplyArgs &a, uint32_t run, uint32_t s, uint32_t e, int TG,
-                                          int t, int team_in_warp, unsigned mask) {
-    const uint32_t key = a.keys[s];
-    const int fi = find_feature(g, key);
-    const DevFeature &f = g.f[fi];
-    const bool col_ok = t < f.G && t * f.vec < f.D;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (uint32_t base = s; base < e; base += TG) {
-        uint32_t bag = 0;
-        float coef = 0.f;
-        if (base + t < e) {
-            const uint32_t slot = a.vals[base + t];
-            bag = slot / (uint32_t)f.L;
-            coef = slot_coef(f, slot, bag);
-        }
-        const int m = (int)min((uint32_t)TG, e - base);
-        for (int k = 0; k < m; ++k) {
-            const uint32_t bk = __shfl_sync(mask, bag, team_in_warp * TG + k);
-            const float ck = __shfl_sync(mask, coef, team_in_warp * TG + k);
-            if (col_ok) {
-                const float4 v = load_grad_part(g, f, bk, t);
-                acc.x = fmaf(ck, v.x, acc.x);
-                acc.y = fmaf(ck, v.y, acc.y);
-                acc.z = fmaf(ck, v.z, acc.z);
-                acc.w = fmaf(ck, v.w, acc.w);
+        for (int u = 0; u < 4; ++u) {
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            kk[u] = kInvalidKey;
+            if (u < U) {
+                const int src = team * U + u;
+                kk[u] = __shfl_sync(kFull, k, src);
+                uint32_t sl = __shfl_sync(kFull, slot, src);
+                const float *gout = gout_local;
+                if (a.p2p) {               // the gradient lives on the rank that sent this slot
+                    gout = a.peer_grads[sl >> 28];
+                    sl &= 0x0fffffffu;
+                }
+                if (kk[u] != kInvalidKey) {
+                    if (kk[u] < f_lo || kk[u] >= f_hi) {
+                        fi = find_feature(sf, nf, kk[u]);
+                        f_lo = sf[fi].row_base;
+                        f_hi = f_lo + sf[fi].num_rows;
+                    }
+                    const DevFeature &f = sf[fi];
+                    if (SIMPLE) {   // every table: D % 4 == 0, aligned slices, single-id bags, plain sum
+                        if (t < f.G)
+                            v[u] = __ldg(reinterpret_cast<const float4 *>(gout + (int64_t)sl * gstride + f.out_col) + t);
+                    } else if (t < f.G && t * f.vec < f.D) {
+                        const uint32_t bag = f.L == 1 ? sl : sl / (uint32_t)f.L;
+                        const float4 x = load_grad_part(gout, gstride, f, bag, t);
+                        if (f.id_weight != nullptr || f.pooling == CTR_POOL_MEAN) {
+                            const float c = slot_coef(f, sl, bag);
+                            v[u] = make_float4(c * x.x, c * x.y, c * x.z, c * x.w);
+                        } else {
+                            v[u] = x;
+                        }
+                    }
+                }
             }
         }
-    }
-    update_row(g, f, a, run, fi, key - f.row_base, t, col_ok, acc, mask, TG);
-}
-
-// Medium run (<= kLongRun): one warp; 32 / G row slots stride the run, xor-shuffles fold the slots.
-__device__ __forceinline__ void medium_run(const DevGroup &g, const ApplyArgs &a, uint32_t run, int lane) {
-    const uint32_t s = a.run_start[run], e = a.run_start[run + 1];
-    const uint32_t key = a.keys[s];
-    const int fi = find_feature(g, key);
-    const DevFeature &f = g.f[fi];
-    const int G = f.G;
-    const int g_lane = lane & (G - 1);
-    const bool col_ok = g_lane * f.vec < f.D;
-    float4 acc = strided_run_sum(g, f, a, s + lane / G, e, kWarp / G, g_lane, col_ok);
-    for (int off = G; off < kWarp; off <<= 1) {
-        acc.x += __shfl_xor_sync(kFull, acc.x, off);
-        acc.y += __shfl_xor_sync(kFull, acc.y, off);
-        acc.z += __shfl_xor_sync(kFull, acc.z, off);
-        acc.w += __shfl_xor_sync(kFull, acc.w, off);
-    }
-    update_row(g, f, a, run, fi, key - f.row_base, lane, lane < G && col_ok, acc, kFull, G);
-}
-
-// One chunk of a long run: the whole block; 256 / G row slots, fixed-order shared-memory tree -> partials[ci].
-__device__ __forceinline__ void chunk_task(const DevGroup &g, const ApplyArgs &a, uint32_t ci, float4 *red) {
-    const uint32_t q = a.chunk_q[ci];
-    const uint32_t run = a.long_list[q];
-    const uint32_t c = ci - a.long_cbase[q];
-    const uint32_t s = a.run_start[run] + c * kChunk;
-    const uint32_t e = min(a.run_start[run + 1], s + (uint32_t)kChunk);
-    const DevFeature &f = g.f[find_feature(g, a.keys[s])];
-    const int G = f.G;
-    const int g_lane = threadIdx.x & (G - 1);
-    const bool col_ok = g_lane * f.vec < f.D;
-    red[threadIdx.x] = strided_run_sum(g, f, a, s + threadIdx.x / G, e, kApplyThreads / G, g_lane, col_ok);
-    __syncthreads();
-    for (int stride = kApplyThreads / 2; stride >= G; stride >>= 1) {
-        if ((int)threadIdx.x < stride) {
-            const float4 o = red[threadIdx.x + stride];
-            float4 m = red[threadIdx.x];
-            m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
-            red[threadIdx.x] = m;
+        // ends of runs among this team's positions; bit U - 1 = the team's last position
+        const unsigned m = (tails >> (team * U)) & umask;
+        const bool single = (m & (umask >> 1)) == 0u;          // no run ends strictly inside the team
+        const bool prev_open = team > 0 ? ((tails >> (team * U - 1)) & 1u) == 0u : carry_open;
+        // sum of the team's trailing run
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (u < U) {
+                add4(out, v[u]);
+                if (u < U - 1 && ((m >> u) & 1u)) out = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
-        __syncthreads();
-    }
-    if ((int)threadIdx.x < G) reinterpret_cast<float4 *>(a.partials + (size_t)ci * a.row_floats)[threadIdx.x] = red[threadIdx.x];
-}
-
-// Finish a long run whose chunks are all done: the first warp adds the partials in chunk order and updates.
-__device__ __forceinline__ void long_finish(const DevGroup &g, const ApplyArgs &a, uint32_t q, int lane) {
-    const uint32_t run = a.long_list[q];
-    const uint32_t s = a.run_start[run], e = a.run_start[run + 1];
-    const uint32_t nch = (e - s + kChunk - 1) / kChunk;
-    const uint32_t cbase = a.long_cbase[q];
-    const uint32_t key = a.keys[s];
-    const int fi = find_feature(g, key);
-    const DevFeature &f = g.f[fi];
-    const bool col_ok = lane < f.G && lane * f.vec < f.D;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < f.G) {
-        for (uint32_t c = 0; c < nch; ++c) {   // .cg: partials were written by other blocks
-            const float4 v = __ldcg(reinterpret_cast<const float4 *>(a.partials + (size_t)(cbase + c) * a.row_floats) + lane);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        if (team == 0 && single && carry_open) add4(out, carry);
+        // segmented inclusive scan over the teams; a segment starts at a team unless it is one run joined to its left
+        const unsigned starts = __ballot_sync(kFull, t == 0 && !(single && prev_open));
+        for (int d = 1; d < P; d <<= 1) {
+            const float4 o = shfl_up4<VEC>(out, d * TG);
+            // lanes of teams team - d + 1 .. team
+            const unsigned span = team >= d ? ((d * TG == kWarp ? kFull : ((1u << (d * TG)) - 1u)) << ((team - d + 1) * TG)) : kFull;
+            if (team >= d && (starts & span) == 0u) add4(out, o);
         }
-    }
-    update_row(g, f, a, run, fi, key - f.row_base, lane, col_ok, acc, kFull, f.G);
-}
-
-// One launch for all tiers.  Work is handed out dynamically (atomic tickets in the plan's counter block),
-// longest tasks first: chunks of hot rows, then warp-sized runs, then the bulk of short runs -- so the
-// latency-bound tails of the tiers overlap instead of running back to back.  counters: [5] chunk ticket,
-// [6] medium ticket, [7] short ticket; long_done[q] counts finished chunks of long run q.
-__global__ void __launch_bounds__(kApplyThreads)
-    emb_bwd_apply_kernel(const __grid_constant__ DevGroup g, const __grid_constant__ ApplyArgs a_in) {
-    __shared__ float4 red[kApplyThreads];
-    __shared__ uint32_t ticket;
-    __shared__ uint32_t finish_q;
-    ApplyArgs a = a_in;
-    if (a.hyper_dev != nullptr) a.h = *a.hyper_dev;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t num_runs = a.counters[1], nlong_chunks = a.counters[3], nmed = a.counters[4];
-    if (blockIdx.x == 0 && threadIdx.x == 0 && a.num_unique != nullptr) *a.num_unique = (int64_t)num_runs;
-
-    // tier 1: chunks of long runs (whole block per chunk)
-    while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) ticket = atomicAdd(&a.counters[5], 1u);
-        __syncthreads();
-        const uint32_t ci = ticket;
-        if (ci >= nlong_chunks) break;
-        chunk_task(g, a, ci, red);
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const uint32_t q = a.chunk_q[ci];
-            const uint32_t run = a.long_list[q];
-            const uint32_t nch = (a.run_start[run + 1] - a.run_start[run] + kChunk - 1) / kChunk;
-            finish_q = (atomicAdd(&a.long_done[q], 1u) == nch - 1) ? q : 0xffffffffu;
+        float4 acc = shfl_up4<VEC>(out, TG);                   // what flows in from the left
+        if (team == 0) acc = carry;
+        if (!prev_open) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        carry = shfl_idx4<VEC>(out, (P - 1) * TG + t);
+        carry_open = ((tails >> (Q - 1)) & 1u) == 0u;
+        // second walk: close the runs that end at this team's positions
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (u < U) {
+                add4(acc, v[u]);
+                if ((m >> u) & 1u) {
+                    const int idx = team * U + u;
+                    if (head_pending && (tails & ((1u << idx) - 1u)) == 0u) {   // first end of a run in this range
+                        have_head = true;
+                        head_acc = acc;
+                    } else {
+                        const uint32_t key = kk[u];
+                        if (key < f_lo || key >= f_hi) {
+                            fi = find_feature(sf, nf, key);
+                            f_lo = sf[fi].row_base;
+                            f_hi = f_lo + sf[fi].num_rows;
+                        }
+                        const DevFeature &f = sf[fi];
+                        if (INL) update_row(f, a, p0 + idx, fi, key - f.row_base, t, t < f.G && t * f.vec < f.D, acc, tmask, TG);
+                        else update_row_call(f, a, p0 + idx, fi, key - f.row_base, t, t < f.G && t * f.vec < f.D, acc, tmask, TG);
+                    }
+                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
         }
-        __syncthreads();
-        if (finish_q != 0xffffffffu && warp == 0) {
+        if (tails != 0u) head_pending = false;
+        closed += (uint32_t)__popc(tails);
+        k = k_next; nk = nk_next; slot = slot_next;
+    }
+    // publish: the last run of the range continues in the next one -> leave its partial sum for whoever ends it
+    uint32_t flag = 1u;
+    if (end < S) {
+        const uint32_t kl = a.keys[end - 1];
+        if (kl != kInvalidKey && a.keys[end] == kl) {
+            if (team == 0) reinterpret_cast<float4 *>(a.tail_part + (size_t)w * a.row_floats)[t] = carry;
+            flag = 3u;
             __threadfence();
-            long_finish(g, a, finish_q, lane);
+            __syncwarp();
         }
     }
-    // tier 2: medium runs, one per warp, eight per ticket
-    while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) ticket = atomicAdd(&a.counters[6], (uint32_t)(kApplyThreads / kWarp));
-        __syncthreads();
-        const uint32_t base = ticket;
-        if (base >= nmed) break;
-        if (base + warp < nmed) medium_run(g, a, a.med_list[base + warp], lane);
+    if (lane == 0) {
+        st_relaxed_u32(a.range_flags + w, flag);
+        if (a.num_unique != nullptr && closed != 0) atomicAdd(a.num_unique, (unsigned long long)closed);
     }
-    // tier 3: short runs, one per team; a ticket covers kShortBatch rounds of the block's teams
-    const int TG = a.team;
-    const int t = lane & (TG - 1);
-    const int team_in_warp = lane / TG;
-    const unsigned mask = TG == 32 ? kFull : (((1u << TG) - 1u) << (team_in_warp * TG));
-    const uint32_t teams = kApplyThreads / TG;
-    constexpr uint32_t kShortBatch = 4;
-    while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) ticket = atomicAdd(&a.counters[7], teams * kShortBatch);
-        __syncthreads();
-        const uint32_t base = ticket;
-        if (base >= num_runs) break;
-#pragma unroll 1
-        for (uint32_t r = 0; r < kShortBatch; ++r) {
-            const uint32_t run = base + r * teams + threadIdx.x / TG;
-            if (run < num_runs) {
-                const uint32_t s = a.run_start[run], e = a.run_start[run + 1];
-                if (e - s <= (uint32_t)kTeamRun) short_run(g, a, run, s, e, TG, t, team_in_warp, mask);
-            }
+    // finish the run that was open when this range started (at most one per range)
+    const unsigned head_lanes = __ballot_sync(kFull, have_head);
+    if (head_lanes != 0u) {
+        const int src_team = (__ffs(head_lanes) - 1) / TG;
+        const float4 hv = shfl_idx4<4>(head_acc, src_team * TG + t);
+        // first range of the run: smallest j whose last key reaches first_key (keys are sorted; j = w - 1 qualifies)
+        uint32_t lo = 0, hi = w - 1;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (a.keys[(mid + 1) * a.range - 1] >= first_key) hi = mid; else lo = mid + 1;
+        }
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t j = lo + team; j < w; j += P) {
+            while (ld_relaxed_u32(a.range_flags + j) == 0u) { }
+            __threadfence();
+            add4(sum, __ldcg(reinterpret_cast<const float4 *>(a.tail_part + (size_t)j * a.row_floats) + t));
+        }
+        for (int off = TG; off < kWarp; off <<= 1) {
+            float4 o;
+            o.x = __shfl_xor_sync(kFull, sum.x, off); o.y = __shfl_xor_sync(kFull, sum.y, off);
+            o.z = __shfl_xor_sync(kFull, sum.z, off); o.w = __shfl_xor_sync(kFull, sum.w, off);
+            add4(sum, o);
+        }
+        add4(sum, hv);
+        if (team == 0) {
+            const int hf = find_feature(sf, nf, first_key);
+            const DevFeature &f = sf[hf];
+            update_row_call(f, a, first, hf, first_key - f.row_base, t, t < f.G && t * f.vec < f.D, sum,
+                            TG == kWarp ? kFull : ((1u << TG) - 1u), TG);
         }
     }
 }
@@ -487,7 +594,8 @@ extern "C" int64_t ctr_emb_bwd_workspace_bytes(const ctr_group_t *group) {
     return plan_layout(dg).total;
 }
 
-extern "C" int ctr_emb_bwd_plan(const ctr_group_t *group, void *workspace, int64_t workspace_bytes, void *stream_) {
+extern "C" int ctr_emb_bwd_plan_ex(const ctr_group_t *group, void *workspace, int64_t workspace_bytes, uint32_t flags,
+                                   void *stream_) {
     static thread_local DevGroup dg;
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = lower_group(group, &dg, /*need_tables=*/false, /*need_out=*/false);
@@ -504,49 +612,48 @@ extern "C" int ctr_emb_bwd_plan(const ctr_group_t *group, void *workspace, int64
     uint32_t *counters = reinterpret_cast<uint32_t *>(ws + p.counters);
     uint32_t *keys_a = reinterpret_cast<uint32_t *>(ws + p.keys_a), *keys_b = reinterpret_cast<uint32_t *>(ws + p.keys_b);
     uint32_t *vals_a = reinterpret_cast<uint32_t *>(ws + p.vals_a), *vals_b = reinterpret_cast<uint32_t *>(ws + p.vals_b);
-    note_launch(), reset_counters_kernel<<<1, 32, 0, stream>>>(counters);
+    const bool want_runs = (flags & CTR_PLAN_NO_RUNS) == 0;
+    note_launch(), reset_counters_kernel<<<1, 32, 0, stream>>>(counters, want_runs ? 1u : 0u);
     if (p.S > 0) {
         int64_t max_slots = 0;
         for (int i = 0; i < dg.num_features; ++i) {
             const int64_t n = (int64_t)dg.B * dg.f[i].L;
             if (n > max_slots) max_slots = n;
         }
-        int64_t bx = (max_slots + 1023) / 1024;  // 4 slots per thread
-        if (bx > kNumSMs * 8) bx = kNumSMs * 8;
+        // ~4 blocks per SM over all features; every block folds its keys into the radix histograms
+        int64_t bx = (max_slots + 1023) / 1024;  // at least 4 slots per thread
+        const int64_t per_feature = ((int64_t)kNumSMs * 4 + dg.num_features - 1) / dg.num_features;
+        if (bx > per_feature) bx = per_feature;
         if (bx < 1) bx = 1;
-        note_launch(), emb_keygen_kernel<<<dim3((unsigned)bx, dg.num_features), 256, 0, stream>>>(dg, keys_a, vals_a);
+        uint32_t *scratch = reinterpret_cast<uint32_t *>(ws + p.counts);
+        rc = radix_sort_prepare(scratch, p.S, p.key_bits, stream);
+        if (rc != CTR_OK) return rc;
+        note_launch(), emb_keygen_kernel<<<dim3((unsigned)bx, dg.num_features), 256, 0, stream>>>(
+            dg, keys_a, vals_a, sort_hist(scratch), sort_num_passes(p.key_bits), sort_digit_bits(p.key_bits));
         CTR_CUDA_OK(cudaGetLastError());
     }
     rc = radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, p.S, p.key_bits, reinterpret_cast<uint32_t *>(ws + p.counts),
-                          reinterpret_cast<uint32_t *>(ws + p.spine), stream);
+                          reinterpret_cast<uint32_t *>(ws + p.spine), stream, /*hist_ready=*/true);
     if (rc < 0) return rc;
     if (p.S > 0 && rc != p.sorted_in_b) {
         set_error("internal: sort parity mismatch");
         return CTR_E_CUDA;
     }
+    if (!want_runs) return CTR_OK;
     const uint32_t *sorted_keys = p.sorted_in_b ? keys_b : keys_a;
-    rc = find_runs(sorted_keys, p.S, reinterpret_cast<uint32_t *>(ws + p.run_start), counters,
-                   reinterpret_cast<uint32_t *>(ws + p.spine), stream);
-    if (rc != CTR_OK || p.S == 0) return rc;
-    int64_t cb = (p.S + 255) / 256;
-    if (cb > kNumSMs * 8) cb = kNumSMs * 8;
-    note_launch(), classify_runs_kernel<<<(unsigned)cb, 256, 0, stream>>>(
-        reinterpret_cast<const uint32_t *>(ws + p.run_start), counters, reinterpret_cast<uint32_t *>(ws + p.med_list),
-        reinterpret_cast<uint32_t *>(ws + p.long_list), reinterpret_cast<uint32_t *>(ws + p.long_cbase),
-        reinterpret_cast<uint32_t *>(ws + p.chunk_q));
-    CTR_CUDA_OK(cudaGetLastError());
-    return CTR_OK;
+    return find_runs(sorted_keys, p.S, reinterpret_cast<uint32_t *>(ws + p.run_start), counters,
+                     reinterpret_cast<uint32_t *>(ws + p.spine), stream);
 }
 
-extern "C" int ctr_emb_bwd_apply(const ctr_group_t *group, void *workspace, const ctr_opt_t *opt,
-                                 int32_t *uniq_feature, int32_t *uniq_row, float *row_grad, int64_t row_grad_stride,
-                                 int64_t *num_unique, void *stream_) {
-    static thread_local DevGroup dg;
-    cudaStream_t stream = (cudaStream_t)stream_;
-    CTR_REQUIRE(opt != nullptr, "opt is null");
+extern "C" int ctr_emb_bwd_plan(const ctr_group_t *group, void *workspace, int64_t workspace_bytes, void *stream) {
+    return ctr_emb_bwd_plan_ex(group, workspace, workspace_bytes, 0u, stream);
+}
+
+// shared by the single-GPU apply and the sharded owner-side apply
+static int apply_impl(DevGroup &dg, const PlanLayout &p, void *workspace, const ctr_opt_t *opt, int32_t *uniq_feature,
+                      int32_t *uniq_row, float *row_grad, int64_t row_grad_stride, int64_t *num_unique,
+                      const float *const *peer_grads, int world, cudaStream_t stream) {
     const bool updates = opt->kind != CTR_OPT_NONE;
-    int rc = lower_group(group, &dg, /*need_tables=*/updates, /*need_out=*/true);
-    if (rc != CTR_OK) return rc;
     CTR_REQUIRE(workspace != nullptr, "workspace is null");
     CTR_REQUIRE(opt->kind >= CTR_OPT_NONE && opt->kind <= CTR_OPT_ADAM, "bad optimizer kind %d", opt->kind);
     int team = 1;
@@ -565,25 +672,22 @@ extern "C" int ctr_emb_bwd_apply(const ctr_group_t *group, void *workspace, cons
         }
     }
     CTR_REQUIRE(row_grad == nullptr || uniq_row != nullptr, "row_grad needs uniq_row");
-    const PlanLayout p = plan_layout(dg);
     char *ws = static_cast<char *>(workspace);
     ApplyArgs a{};
     a.keys = reinterpret_cast<const uint32_t *>(ws + (p.sorted_in_b ? p.keys_b : p.keys_a));
     a.vals = reinterpret_cast<const uint32_t *>(ws + (p.sorted_in_b ? p.vals_b : p.vals_a));
     a.run_start = reinterpret_cast<const uint32_t *>(ws + p.run_start);
     a.counters = reinterpret_cast<uint32_t *>(ws + p.counters);
-    a.med_list = reinterpret_cast<uint32_t *>(ws + p.med_list);
-    a.long_list = reinterpret_cast<uint32_t *>(ws + p.long_list);
-    a.long_cbase = reinterpret_cast<uint32_t *>(ws + p.long_cbase);
-    a.long_done = reinterpret_cast<uint32_t *>(ws + p.long_done);
-    a.chunk_q = reinterpret_cast<uint32_t *>(ws + p.chunk_q);
-    a.partials = reinterpret_cast<float *>(ws + p.partials);
+    a.ticket = reinterpret_cast<uint32_t *>(ws + p.range_flags);
+    a.range_flags = a.ticket + 64;
+    a.tail_part = reinterpret_cast<float *>(ws + p.tail_part);
     a.row_floats = (int)p.row_floats;
     a.uniq_feature = uniq_feature;
     a.uniq_row = uniq_row;
     a.row_grad = row_grad;
     a.row_grad_stride = row_grad_stride;
-    a.num_unique = num_unique;
+    a.num_unique = reinterpret_cast<unsigned long long *>(num_unique);
+    a.status = dg.status;
     a.kind = opt->kind;
     ctr_opt_hyper(opt, &a.h);
     a.hyper_dev = opt->device_hyper;
@@ -593,15 +697,218 @@ extern "C" int ctr_emb_bwd_apply(const ctr_group_t *group, void *workspace, cons
         if (num_unique != nullptr) CTR_CUDA_OK(cudaMemsetAsync(num_unique, 0, sizeof(int64_t), stream));
         return CTR_OK;
     }
-    const int teams_per_block = kApplyThreads / team;
-    int64_t blocks = (p.S + teams_per_block - 1) / teams_per_block;  // upper bound: one run per slot
-    const int64_t cap = (int64_t)kNumSMs * 16;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    // tickets and per-long-run completion counters are rebuilt by every apply
-    CTR_CUDA_OK(cudaMemsetAsync(a.counters + 5, 0, 3 * sizeof(uint32_t), stream));
-    CTR_CUDA_OK(cudaMemsetAsync(a.long_done, 0, (size_t)p.max_long * sizeof(uint32_t), stream));
-    note_launch(), emb_bwd_apply_kernel<<<kNumSMs * 5, kApplyThreads, 0, stream>>>(dg, a);
+    int64_t expected = p.S;
+    if (peer_grads != nullptr) {
+        a.p2p = 1;
+        a.S_dev = a.counters + 3;
+        for (int r = 0; r < world; ++r) {
+            CTR_REQUIRE(peer_grads[r] != nullptr, "peer_grads[%d] is null", r);
+            a.peer_grads[r] = peer_grads[r];
+        }
+        expected = p.S / world;            // the capacity is world x that; ranges are sized for the balanced case
+    }
+    // range length: a multiple of the positions one outer iteration covers, sized for ~3 waves of resident warps
+    const int P = kWarp / team;
+    const int U = P >= 8 ? (kWarp / P < 4 ? kWarp / P : 4) : 4;
+    const int Q = P * U;
+    const int64_t target_ranges = (int64_t)kNumSMs * 24 * 3;
+    int64_t range = (expected + target_ranges - 1) / target_ranges;
+    range = (range + Q - 1) / Q * Q;
+    const int64_t lo = kMinRange > Q ? kMinRange : Q;
+    if (range < lo) range = lo;
+    if (range > 512) range = 512;
+    static const int range_env = getenv("CTR_SWEEP_RANGE") ? atoi(getenv("CTR_SWEEP_RANGE")) : 0;   // tuning knob
+    if (range_env > 0) range = (range_env + Q - 1) / Q * Q;
+    a.S = (uint32_t)p.S;
+    a.range = (uint32_t)range;
+    a.num_ranges = (uint32_t)((p.S + range - 1) / range);
+    bool any_vec4 = false, simple = true;
+    for (int i = 0; i < dg.num_features; ++i) {
+        const DevFeature &f = dg.f[i];
+        any_vec4 |= f.vec == 4;
+        simple &= f.vec == 4 && f.aligned && f.L == 1 && f.id_weight == nullptr && f.pooling == CTR_POOL_SUM;
+    }
+    if (num_unique != nullptr) CTR_CUDA_OK(cudaMemsetAsync(num_unique, 0, sizeof(int64_t), stream));
+    CTR_CUDA_OK(cudaMemsetAsync(a.ticket, 0, (64 + (size_t)a.num_ranges) * sizeof(uint32_t), stream));
+    const unsigned blocks = (a.num_ranges + kApplyWarps - 1) / kApplyWarps;
+    note_launch();
+    static const int inl = getenv("CTR_SWEEP_INLINE") ? atoi(getenv("CTR_SWEEP_INLINE")) : 0;   // tuning knob
+    if (simple && inl) emb_bwd_sweep_kernel<4, true, true><<<blocks, kApplyThreads, 0, stream>>>(dg, a);
+    else if (simple) emb_bwd_sweep_kernel<4, true, false><<<blocks, kApplyThreads, 0, stream>>>(dg, a);
+    else if (any_vec4) emb_bwd_sweep_kernel<4, false, false><<<blocks, kApplyThreads, 0, stream>>>(dg, a);
+    else emb_bwd_sweep_kernel<1, false, false><<<blocks, kApplyThreads, 0, stream>>>(dg, a);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
+}
+
+extern "C" int ctr_emb_bwd_apply(const ctr_group_t *group, void *workspace, const ctr_opt_t *opt,
+                                 int32_t *uniq_feature, int32_t *uniq_row, float *row_grad, int64_t row_grad_stride,
+                                 int64_t *num_unique, void *stream_) {
+    static thread_local DevGroup dg;
+    CTR_REQUIRE(opt != nullptr, "opt is null");
+    int rc = lower_group(group, &dg, /*need_tables=*/opt->kind != CTR_OPT_NONE, /*need_out=*/true);
+    if (rc != CTR_OK) return rc;
+    return apply_impl(dg, plan_layout(dg), workspace, opt, uniq_feature, uniq_row, row_grad, row_grad_stride, num_unique,
+                      nullptr, 1, (cudaStream_t)stream_);
+}
+
+// ---- sharded owner side: pull the routed (key, slot) lists from the peers, sort, apply -----------------------
+namespace ctr {
+
+struct PeerLists {
+    int world, rank;
+    const uint32_t *counts[CTR_MAX_WORLD];
+    const uint32_t *keys[CTR_MAX_WORLD];
+    const uint32_t *slots[CTR_MAX_WORLD];
+};
+
+// one warp: where each peer's list for this rank starts (in the peer's buffer and in the gathered array)
+__global__ void p2p_offsets_kernel(const __grid_constant__ PeerLists pl, uint32_t *counters) {
+    const int r = threadIdx.x;
+    uint32_t src = 0, cnt = 0;
+    if (r < pl.world) {
+        for (int o = 0; o < pl.rank; ++o) src += pl.counts[r][o];
+        cnt = pl.counts[r][pl.rank];
+    }
+    uint32_t incl = cnt;
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t v = __shfl_up_sync(kFull, incl, off);
+        if (r >= off) incl += v;
+    }
+    if (r < pl.world) {
+        counters[kMetaSrc + r] = src;
+        counters[kMetaDst + r] = incl - cnt;
+        counters[kMetaCnt + r] = cnt;
+    }
+    if (r == 31) counters[3] = incl;
+}
+
+// grid (bx, world): copies peer r's list for this rank into the sort input, tags the slots with r and builds the
+// radix histograms of the keys
+__global__ void __launch_bounds__(256)
+    p2p_gather_kernel(const __grid_constant__ PeerLists pl, const uint32_t *__restrict__ counters, uint32_t *__restrict__ keys,
+                      uint32_t *__restrict__ vals, uint32_t *__restrict__ hist, int passes, int bits) {
+    __shared__ uint32_t sh[kMaxPasses][kMaxRadix];
+    for (int i = threadIdx.x; i < kMaxPasses * kMaxRadix; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const int r = blockIdx.y;
+    const uint32_t n = counters[kMetaCnt + r];
+    const uint32_t *src_k = pl.keys[r] + counters[kMetaSrc + r];
+    const uint32_t *src_s = pl.slots[r] + counters[kMetaSrc + r];
+    const uint32_t dst = counters[kMetaDst + r];
+    const int lane = threadIdx.x & 31;
+    const uint32_t dmask = (1u << bits) - 1u;
+    const uint32_t nround = (n + 31u) / 32u * 32u;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += gridDim.x * blockDim.x) {
+        const bool valid = j < n;
+        uint32_t key = 0;
+        if (valid) {
+            key = src_k[j];
+            keys[dst + j] = key;
+            vals[dst + j] = src_s[j] | ((uint32_t)r << 28);
+        }
+        for (int p = 0; p < passes; ++p) {
+            const uint32_t d = (key >> (p * bits)) & dmask;
+            const uint32_t peers = __match_any_sync(kFull, valid ? d : (uint32_t)(kMaxRadix + lane));
+            if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[p][d], (uint32_t)__popc(peers));
+        }
+    }
+    __syncthreads();
+    const int radix = 1 << bits;
+    for (int i = threadIdx.x; i < passes * radix; i += blockDim.x) {
+        const uint32_t c = sh[i / radix][i % radix];
+        if (c) atomicAdd(&hist[(i / radix) * kMaxRadix + (i % radix)], c);
+    }
+}
+
+static int check_owner_group(const DevGroup &dg, const ctr_shard_t *shard) {
+    CTR_REQUIRE(shard != nullptr, "shard is null");
+    CTR_REQUIRE(shard->world >= 1 && shard->world <= CTR_MAX_WORLD, "world=%d outside [1, %d]", shard->world, CTR_MAX_WORLD);
+    CTR_REQUIRE(shard->rank >= 0 && shard->rank < shard->world, "rank=%d outside [0, %d)", shard->rank, shard->world);
+    for (int i = 0; i < dg.num_features; ++i)
+        CTR_REQUIRE((int64_t)dg.B * dg.f[i].L < (1ll << 28), "feature %d: B*L must stay below 2^28 on the sharded path", i);
+    return CTR_OK;
+}
+
+}  // namespace ctr
+
+extern "C" int64_t ctr_emb_bwd_p2p_workspace_bytes(const ctr_group_t *group, int32_t world) {
+    static thread_local DevGroup dg;
+    int rc = lower_group(group, &dg, false, false);
+    if (rc != CTR_OK) return rc;
+    CTR_REQUIRE(world >= 1 && world <= CTR_MAX_WORLD, "world=%d outside [1, %d]", world, CTR_MAX_WORLD);
+    return plan_layout(dg, world).total;
+}
+
+extern "C" int ctr_emb_bwd_plan_p2p(const ctr_group_t *group, const ctr_shard_t *shard, const uint32_t *const *peer_counts,
+                                    const uint32_t *const *peer_keys, const uint32_t *const *peer_slots, void *workspace,
+                                    int64_t workspace_bytes, void *stream_) {
+    static thread_local DevGroup dg;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = lower_group(group, &dg, false, false);
+    if (rc != CTR_OK) return rc;
+    rc = check_owner_group(dg, shard);
+    if (rc != CTR_OK) return rc;
+    CTR_REQUIRE(peer_counts != nullptr && peer_keys != nullptr && peer_slots != nullptr, "null peer list arrays");
+    const PlanLayout p = plan_layout(dg, shard->world);
+    CTR_REQUIRE(p.S < (1ll << 30), "capacity of %lld pairs; must stay below 2^30", (long long)p.S);
+    CTR_REQUIRE(workspace != nullptr, "workspace is null");
+    if (workspace_bytes < p.total) {
+        set_error("workspace too small: %lld < %lld bytes", (long long)workspace_bytes, (long long)p.total);
+        return CTR_E_WORKSPACE;
+    }
+    CTR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
+    PeerLists pl{};
+    pl.world = shard->world;
+    pl.rank = shard->rank;
+    for (int r = 0; r < shard->world; ++r) {
+        CTR_REQUIRE(peer_counts[r] != nullptr && peer_keys[r] != nullptr && peer_slots[r] != nullptr, "peer %d: null list", r);
+        pl.counts[r] = peer_counts[r];
+        pl.keys[r] = peer_keys[r];
+        pl.slots[r] = peer_slots[r];
+    }
+    char *ws = static_cast<char *>(workspace);
+    uint32_t *counters = reinterpret_cast<uint32_t *>(ws + p.counters);
+    uint32_t *keys_a = reinterpret_cast<uint32_t *>(ws + p.keys_a), *keys_b = reinterpret_cast<uint32_t *>(ws + p.keys_b);
+    uint32_t *vals_a = reinterpret_cast<uint32_t *>(ws + p.vals_a), *vals_b = reinterpret_cast<uint32_t *>(ws + p.vals_b);
+    note_launch(), reset_counters_kernel<<<1, 32, 0, stream>>>(counters, 0u);
+    if (p.S == 0) return CTR_OK;
+    note_launch(), p2p_offsets_kernel<<<1, 32, 0, stream>>>(pl, counters);
+    uint32_t *scratch = reinterpret_cast<uint32_t *>(ws + p.counts);
+    rc = radix_sort_prepare(scratch, p.S, p.key_bits, stream);
+    if (rc != CTR_OK) return rc;
+    int64_t bx = (p.S / shard->world / shard->world + 2047) / 2048;   // a peer's list for this rank, balanced case
+    const int64_t per_peer = ((int64_t)kNumSMs * 4 + shard->world - 1) / shard->world;
+    if (bx > per_peer) bx = per_peer;
+    if (bx < 1) bx = 1;
+    note_launch(), p2p_gather_kernel<<<dim3((unsigned)bx, shard->world), 256, 0, stream>>>(
+        pl, counters, keys_a, vals_a, sort_hist(scratch), sort_num_passes(p.key_bits), sort_digit_bits(p.key_bits));
+    CTR_CUDA_OK(cudaGetLastError());
+    rc = radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, p.S, p.key_bits, scratch, reinterpret_cast<uint32_t *>(ws + p.spine),
+                          stream, /*hist_ready=*/true, /*n_dev=*/counters + 3);
+    if (rc < 0) return rc;
+    if (rc != p.sorted_in_b) {
+        set_error("internal: sort parity mismatch");
+        return CTR_E_CUDA;
+    }
+    return CTR_OK;
+}
+
+extern "C" int ctr_emb_bwd_apply_p2p(const ctr_group_t *group, const ctr_shard_t *shard, void *workspace, const ctr_opt_t *opt,
+                                     const float *const *peer_grads, int64_t *num_unique, void *stream_) {
+    static thread_local DevGroup dg;
+    CTR_REQUIRE(opt != nullptr && peer_grads != nullptr, "null pointer");
+    int rc = lower_group(group, &dg, /*need_tables=*/opt->kind != CTR_OPT_NONE, /*need_out=*/false);
+    if (rc != CTR_OK) return rc;
+    rc = check_owner_group(dg, shard);
+    if (rc != CTR_OK) return rc;
+    // `aligned` was derived from group->out, which is not used here: look at the peers' matrices instead
+    for (int i = 0; i < dg.num_features; ++i) {
+        DevFeature &f = dg.f[i];
+        bool al = f.vec == 4 && f.out_col % 4 == 0 && dg.out_stride % 4 == 0;
+        for (int r = 0; r < shard->world && al; ++r) al = (reinterpret_cast<uintptr_t>(peer_grads[r]) & 15u) == 0;
+        f.aligned = al ? 1 : 0;
+    }
+    return apply_impl(dg, plan_layout(dg, shard->world), workspace, opt, nullptr, nullptr, nullptr, 0, num_unique, peer_grads,
+                      shard->world, (cudaStream_t)stream_);
 }

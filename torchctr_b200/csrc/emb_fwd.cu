@@ -24,12 +24,13 @@ __device__ __forceinline__ void flag_status(uint32_t *status, uint32_t bit) {
     if (status != nullptr) atomicOr(status, bit);
 }
 
-__device__ __forceinline__ float4 load_row_part(const DevFeature &f, int32_t row, int g_lane) {
+__device__ __forceinline__ float4 load_row_part(const DevGroup &g, const DevFeature &f, int fi, int32_t row, int g_lane) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *src = table_row(g, f, fi, row);
     if (f.vec == 4) {
-        v = __ldg(reinterpret_cast<const float4 *>(f.table + (size_t)row * f.D) + g_lane);
+        v = __ldg(reinterpret_cast<const float4 *>(src) + g_lane);
     } else {
-        v.x = __ldg(f.table + (size_t)row * f.D + g_lane);
+        v.x = __ldg(src + g_lane);
     }
     return v;
 }
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kFwdThreads) emb_pool_fwd_kernel(const __grid_
                 const float wk = __shfl_sync(kFull, w, src);
                 acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (k < K && rk[k] >= 0 && col_ok) {
-                    const float4 v = load_row_part(f, rk[k], g_lane);
+                    const float4 v = load_row_part(g, f, fi, rk[k], g_lane);
                     acc[k] = make_float4(v.x * wk, v.y * wk, v.z * wk, v.w * wk);
                 }
             }
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(kFwdThreads) emb_pool_fwd_kernel(const __grid_
                 const int32_t r = __shfl_sync(kFull, row, src0 + k);
                 const float wk = __shfl_sync(kFull, w, src0 + k);
                 if (r >= 0 && col_ok) {
-                    const float4 v = load_row_part(f, r, g_lane);
+                    const float4 v = load_row_part(g, f, fi, r, g_lane);
                     acc.x = fmaf(wk, v.x, acc.x);
                     acc.y = fmaf(wk, v.y, acc.y);
                     acc.z = fmaf(wk, v.z, acc.z);
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(kFwdThreads) emb_pool_fwd_kernel(const __grid_
 // walks the tables four at a time -- four id loads, then four independent row loads, then four stores -- so
 // there is no per-feature block row, no shuffle and ~2 instructions per id instead of ~20; the dense block and
 // the zero padding of the same bag are written by the same team.
-template <int G, int VEC>
+template <int G, int VEC, bool SHARDED>
 __global__ void __launch_bounds__(kFwdThreads) emb_pool_fwd_l1_kernel(const __grid_constant__ DevGroup g) {
     constexpr int kTeams = kFwdThreads / G;
     constexpr int D = G * VEC;
@@ -208,7 +209,8 @@ __global__ void __launch_bounds__(kFwdThreads) emb_pool_fwd_l1_kernel(const __gr
             for (int j = 0; j < 4; ++j) {
                 v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (row[j] >= 0) {
-                    const float *src = g.f[f0 + j].table + (size_t)(uint32_t)row[j] * D + t * VEC;
+                    const float *src = SHARDED ? table_row(g, g.f[f0 + j], f0 + j, row[j]) + t * VEC
+                                               : g.f[f0 + j].table + (size_t)(uint32_t)row[j] * D + t * VEC;
                     if (VEC == 4) v[j] = __ldg(reinterpret_cast<const float4 *>(src));
                     else v[j].x = __ldg(src);
                 }
@@ -325,10 +327,27 @@ static int grid_for(int64_t work_items, int threads, int cap) {
 
 using namespace ctr;
 
+static int launch_pool_fwd(const DevGroup &dg, void *stream);
+
 extern "C" int ctr_emb_pool_fwd(const ctr_group_t *group, void *stream) {
     static thread_local DevGroup dg;
     int rc = lower_group(group, &dg, /*need_tables=*/true, /*need_out=*/true);
     if (rc != CTR_OK) return rc;
+    return launch_pool_fwd(dg, stream);
+}
+
+extern "C" int ctr_emb_pool_fwd_sharded(const ctr_group_t *group, const ctr_shard_t *shard, const float *const *tables,
+                                        void *stream) {
+    static thread_local DevGroup dg;
+    int rc = lower_group(group, &dg, /*need_tables=*/false, /*need_out=*/true);
+    if (rc != CTR_OK) return rc;
+    CTR_REQUIRE(tables != nullptr, "tables is null");
+    rc = attach_shard(&dg, shard, tables);
+    if (rc != CTR_OK) return rc;
+    return launch_pool_fwd(dg, stream);
+}
+
+static int launch_pool_fwd(const DevGroup &dg, void *stream) {
     const int extra_w = dg.dense_width + (dg.zero_from >= 0 ? (int)(dg.out_stride - dg.zero_from) : 0);
     if (dg.B == 0 || (dg.num_features == 0 && extra_w == 0)) return CTR_OK;
     int vec = 0;
@@ -338,10 +357,15 @@ extern "C" int ctr_emb_pool_fwd(const ctr_group_t *group, void *stream) {
         const int blocks = grid_for(dg.B, teams, kNumSMs * 16);
         cudaStream_t st = (cudaStream_t)stream;
         note_launch();
-        if (vec == 1) emb_pool_fwd_l1_kernel<1, 1><<<blocks, kFwdThreads, 0, st>>>(dg);
-        else if (fastG == 4) emb_pool_fwd_l1_kernel<4, 4><<<blocks, kFwdThreads, 0, st>>>(dg);
-        else if (fastG == 8) emb_pool_fwd_l1_kernel<8, 4><<<blocks, kFwdThreads, 0, st>>>(dg);
-        else emb_pool_fwd_l1_kernel<16, 4><<<blocks, kFwdThreads, 0, st>>>(dg);
+        const bool sh = dg.world > 1;
+        if (vec == 1 && sh) emb_pool_fwd_l1_kernel<1, 1, true><<<blocks, kFwdThreads, 0, st>>>(dg);
+        else if (vec == 1) emb_pool_fwd_l1_kernel<1, 1, false><<<blocks, kFwdThreads, 0, st>>>(dg);
+        else if (fastG == 4 && sh) emb_pool_fwd_l1_kernel<4, 4, true><<<blocks, kFwdThreads, 0, st>>>(dg);
+        else if (fastG == 4) emb_pool_fwd_l1_kernel<4, 4, false><<<blocks, kFwdThreads, 0, st>>>(dg);
+        else if (fastG == 8 && sh) emb_pool_fwd_l1_kernel<8, 4, true><<<blocks, kFwdThreads, 0, st>>>(dg);
+        else if (fastG == 8) emb_pool_fwd_l1_kernel<8, 4, false><<<blocks, kFwdThreads, 0, st>>>(dg);
+        else if (sh) emb_pool_fwd_l1_kernel<16, 4, true><<<blocks, kFwdThreads, 0, st>>>(dg);
+        else emb_pool_fwd_l1_kernel<16, 4, false><<<blocks, kFwdThreads, 0, st>>>(dg);
         CTR_CUDA_OK(cudaGetLastError());
         return CTR_OK;
     }

@@ -101,6 +101,27 @@ int lower_group(const ctr_group_t *g, DevGroup *out, bool need_tables, bool need
     return CTR_OK;
 }
 
+int attach_shard(DevGroup *g, const ctr_shard_t *shard, const float *const *tables) {
+    CTR_REQUIRE(shard != nullptr, "shard is null");
+    CTR_REQUIRE(shard->world >= 1 && shard->world <= CTR_MAX_WORLD, "world=%d outside [1, %d]", shard->world, CTR_MAX_WORLD);
+    CTR_REQUIRE(shard->rank >= 0 && shard->rank < shard->world, "rank=%d outside [0, %d)", shard->rank, shard->world);
+    CTR_REQUIRE(shard->adj != nullptr, "shard->adj is null");
+    for (int i = 1; i < g->num_features; ++i)
+        CTR_REQUIRE(g->f[i].D == g->f[0].D, "sharded groups need one embedding dim (feature %d: %d vs %d)", i, g->f[i].D,
+                    g->f[0].D);
+    g->world = shard->world;
+    g->rank = shard->rank;
+    g->shard_adj = shard->adj;
+    if (tables != nullptr) {
+        for (int o = 0; o < shard->world; ++o) {
+            CTR_REQUIRE(tables[o] != nullptr, "tables[%d] is null", o);
+            CTR_REQUIRE((reinterpret_cast<uintptr_t>(tables[o]) & 15u) == 0, "tables[%d] not 16-byte aligned", o);
+            g->peer_tables[o] = tables[o];
+        }
+    }
+    return CTR_OK;
+}
+
 }  // namespace ctr
 
 extern "C" const char *ctr_last_error_string(void) { return ctr::g_err; }

@@ -29,7 +29,7 @@ static RouteLayout route_layout(int64_t S, int world) {
     int bits = 0;
     while ((world >> bits) != 0) ++bits;  // keys are 0 .. world (world = padding bucket)
     r.key_bits = bits < 1 ? 1 : bits;
-    r.sorted_in_b = ((r.key_bits + kRadixBits - 1) / kRadixBits) & 1;
+    r.sorted_in_b = sort_num_passes(r.key_bits) & 1;
     int64_t off = 0;
     r.keys_a = off; off = al256(off + S * 4);
     r.keys_b = off; off = al256(off + S * 4);
@@ -205,6 +205,114 @@ extern "C" int ctr_route_grad_gather(const ctr_group_t *group, int32_t world, co
     int64_t gb = (n * pieces + 255) / 256;
     if (gb > kNumSMs * 16) gb = kNumSMs * 16;
     note_launch(), slot_grad_gather_kernel<<<(unsigned)gb, 256, 0, stream>>>(dg, sorted_slots, n, D, g_send);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+// ---- peer-memory variant: routing lists the OWNERS read over NVLink (no all-to-all) -----------------------------
+namespace ctr {
+
+// one thread per slot: owner, virtual row on the owner, per-owner counts (warp-aggregated)
+__global__ void __launch_bounds__(256)
+    route_p2p_build_kernel(const __grid_constant__ DevGroup g, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                           uint32_t *__restrict__ vrow, uint32_t *__restrict__ counts) {
+    const int fi = blockIdx.y;
+    const DevFeature &f = g.f[fi];
+    int64_t slot_base = 0;
+    for (int i = 0; i < fi; ++i) slot_base += (int64_t)g.B * g.f[i].L;
+    const int64_t n = (int64_t)g.B * f.L;
+    const int lane = threadIdx.x & 31;
+    const int64_t nround = (n + 31) / 32 * 32;  // whole warps iterate together (match.any below)
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t owner = (uint32_t)g.world;       // padding / invalid ids sort behind every rank
+        if (j < n) {
+            const int32_t row = map_index(f, __ldg(f.ids + j));
+            uint32_t vr = 0xffffffffu;
+            if (row >= 0) {
+                vr = (uint32_t)shard_vrow(g, fi, (uint32_t)row, &owner);
+            } else if (row == -2 && g.status != nullptr) {
+                atomicOr(g.status, CTR_STATUS_INDEX_OOB);
+            }
+            keys[slot_base + j] = owner;
+            vals[slot_base + j] = (uint32_t)(slot_base + j);
+            vrow[slot_base + j] = vr;
+        }
+        const uint32_t peers = __match_any_sync(kFull, j < n ? owner : 0xffffffffu);
+        if (j < n && lane == __ffs(peers) - 1) atomicAdd(counts + owner, (uint32_t)__popc(peers));
+    }
+}
+
+// owner-major position k -> keys_out[k] = virtual row, slots_out[k] = slot inside its feature (bag * L + l)
+__global__ void __launch_bounds__(256)
+    route_p2p_finish_kernel(const __grid_constant__ DevGroup g, const uint32_t *__restrict__ sorted_slots,
+                            const uint32_t *__restrict__ vrow, int64_t S, uint32_t *__restrict__ keys_out,
+                            uint32_t *__restrict__ slots_out) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < S; k += (int64_t)gridDim.x * blockDim.x) {
+        int64_t slot = sorted_slots[k];
+        const uint32_t vr = vrow[slot];
+        int fi = 0;
+        while (fi + 1 < g.num_features && slot >= (int64_t)g.B * g.f[fi].L) {
+            slot -= (int64_t)g.B * g.f[fi].L;
+            ++fi;
+        }
+        keys_out[k] = vr;                 // 0xffffffff for the padding bucket, which no owner reads
+        slots_out[k] = (uint32_t)slot;
+    }
+}
+
+}  // namespace ctr
+
+extern "C" int64_t ctr_route_p2p_workspace_bytes(const ctr_group_t *group) {
+    static thread_local DevGroup dg;
+    int rc = lower_group(group, &dg, false, false);
+    if (rc != CTR_OK) return rc;
+    int64_t S = 0;
+    for (int i = 0; i < dg.num_features; ++i) S += (int64_t)dg.B * dg.f[i].L;
+    return route_layout(S, CTR_MAX_WORLD).total;
+}
+
+extern "C" int ctr_route_p2p_build(const ctr_group_t *group, const ctr_shard_t *shard, uint32_t *counts, uint32_t *keys,
+                                   uint32_t *slots, void *workspace, int64_t workspace_bytes, void *stream_) {
+    static thread_local DevGroup dg;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = lower_group(group, &dg, false, false);
+    if (rc != CTR_OK) return rc;
+    rc = attach_shard(&dg, shard, nullptr);
+    if (rc != CTR_OK) return rc;
+    CTR_REQUIRE(counts != nullptr && workspace != nullptr, "null pointer");
+    int64_t S = 0, max_slots = 0;
+    for (int i = 0; i < dg.num_features; ++i) {
+        const int64_t n = (int64_t)dg.B * dg.f[i].L;
+        CTR_REQUIRE(n < (1ll << 28), "feature %d: B*L must stay below 2^28 on the sharded path", i);
+        S += n;
+        if (n > max_slots) max_slots = n;
+    }
+    CTR_REQUIRE(S < (1ll << 30), "group has %lld id slots; must stay below 2^30", (long long)S);
+    const RouteLayout r = route_layout(S, CTR_MAX_WORLD);   // key bits for any world <= CTR_MAX_WORLD
+    if (workspace_bytes < r.total) {
+        set_error("workspace too small: %lld < %lld bytes", (long long)workspace_bytes, (long long)r.total);
+        return CTR_E_WORKSPACE;
+    }
+    CTR_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (CTR_MAX_WORLD + 1), stream));
+    if (S == 0) return CTR_OK;
+    CTR_REQUIRE(keys != nullptr && slots != nullptr, "null pointer");
+    char *ws = static_cast<char *>(workspace);
+    uint32_t *keys_a = reinterpret_cast<uint32_t *>(ws + r.keys_a), *keys_b = reinterpret_cast<uint32_t *>(ws + r.keys_b);
+    uint32_t *vals_a = reinterpret_cast<uint32_t *>(ws + r.vals_a), *vals_b = reinterpret_cast<uint32_t *>(ws + r.vals_b);
+    uint32_t *vrow = reinterpret_cast<uint32_t *>(ws + r.vrow);
+    int64_t bx = (max_slots + 1023) / 1024;
+    const int64_t per_feature = ((int64_t)kNumSMs * 4 + dg.num_features - 1) / dg.num_features;
+    if (bx > per_feature) bx = per_feature;
+    if (bx < 1) bx = 1;
+    note_launch(), route_p2p_build_kernel<<<dim3((unsigned)bx, dg.num_features), 256, 0, stream>>>(dg, keys_a, vals_a, vrow, counts);
+    CTR_CUDA_OK(cudaGetLastError());
+    rc = radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, S, r.key_bits, reinterpret_cast<uint32_t *>(ws + r.counts),
+                          reinterpret_cast<uint32_t *>(ws + r.spine), stream);
+    if (rc < 0) return rc;
+    const uint32_t *sorted_slots = rc ? vals_b : vals_a;
+    int64_t gb = (S + 255) / 256;
+    if (gb > kNumSMs * 16) gb = kNumSMs * 16;
+    note_launch(), route_p2p_finish_kernel<<<(unsigned)gb, 256, 0, stream>>>(dg, sorted_slots, vrow, S, keys, slots);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }

@@ -1,8 +1,7 @@
 // Stable LSD radix sort of (u32 key, u32 value) pairs + run detection, hand-written for the
-// backward plan (K2).  8-bit digits; per pass: per-tile digit histogram -> device scan of the
-// digit-major count matrix -> stable scatter.  Ranking inside a tile is warp-synchronous:
-// lanes that hold the same digit find each other with match.any, the lowest one bumps the
-// warp's shared-memory counter for all of them, so no per-key atomics and no sorting network.
+// backward plan (K2).  8- or 9-bit digits; the digit histograms of all passes come from one read
+// of the keys, then each pass is ONE kernel: tile ranking is warp-synchronous (match.any, no
+// per-key atomics) and the per-digit tile offsets are chained with a decoupled look-back.
 #include "sort.cuh"
 
 namespace ctr {
@@ -159,38 +158,75 @@ int find_runs(const uint32_t *sorted_keys, int64_t n, uint32_t *run_start, uint3
 
 // ---- radix passes -----------------------------------------------------------------------
 
-__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift,
-                                                                uint32_t *__restrict__ counts, int64_t ntiles) {
-    __shared__ uint32_t hist[kRadix];
-    hist[threadIdx.x] = 0;
+// Digit histograms of every pass in one read of the keys: hist[pass][digit] += ...
+template <int BITS>
+__global__ void __launch_bounds__(kSortThreads)
+    radix_hist_all_kernel(const uint32_t *__restrict__ keys, int64_t n, int passes, uint32_t *__restrict__ hist) {
+    constexpr int RADIX = 1 << BITS;
+    __shared__ uint32_t sh[kMaxPasses][RADIX];
+    for (int i = threadIdx.x; i < kMaxPasses * RADIX; i += kSortThreads) (&sh[0][0])[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int64_t base = (int64_t)blockIdx.x * kSortTile;
-#pragma unroll 4
-    for (int j = 0; j < kSortItems; ++j) {
-        const int64_t i = base + (int64_t)j * kSortThreads + threadIdx.x;
+    for (int64_t base = (int64_t)blockIdx.x * kSortThreads; base < n; base += (int64_t)gridDim.x * kSortThreads) {
+        const int64_t i = base + threadIdx.x;
         const bool valid = i < n;
-        const uint32_t d = valid ? ((keys[i] >> shift) & (kRadix - 1)) : (uint32_t)(kRadix + lane);
-        const uint32_t peers = __match_any_sync(kFull, d);
-        if (valid && lane == __ffs(peers) - 1) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+        const uint32_t k = valid ? keys[i] : 0u;
+        for (int p = 0; p < passes; ++p) {
+            const uint32_t d = (k >> (p * BITS)) & (RADIX - 1);
+            const uint32_t peers = __match_any_sync(kFull, valid ? d : (uint32_t)(RADIX + lane));
+            if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[p][d], (uint32_t)__popc(peers));
+        }
     }
     __syncthreads();
-    counts[(int64_t)threadIdx.x * ntiles + blockIdx.x] = hist[threadIdx.x];
+    for (int i = threadIdx.x; i < passes * RADIX; i += kSortThreads) {
+        const uint32_t c = sh[i / RADIX][i % RADIX];
+        if (c) atomicAdd(&hist[(i / RADIX) * kMaxRadix + (i % RADIX)], c);
+    }
 }
 
-__global__ void __launch_bounds__(kSortThreads)
-    radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                         uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
-                         const uint32_t *__restrict__ offsets, int64_t ntiles) {
+constexpr uint32_t kFlagAgg = 1u << 30;   // tile status: count of this tile only
+constexpr uint32_t kFlagInc = 1u << 31;   // tile status: count of this tile and every tile before it
+constexpr uint32_t kValMask = kFlagAgg - 1u;
+
+__device__ __forceinline__ uint32_t ld_status(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// One LSD pass in one kernel.  Tiles are taken in ticket order, so a tile only ever waits for tiles that
+// started before it.  Ranking inside a tile is warp-synchronous: lanes that hold the same digit find each
+// other with match.any and the lowest one bumps the warp's shared-memory counter for all of them (no per-key
+// atomics); warp w owns a contiguous slice of the tile, so (warp, round, lane) order is memory order and the
+// sort is stable.  Per digit, the tile publishes its count, looks back over earlier tiles until it meets an
+// inclusive prefix, and publishes its own inclusive prefix.
+template <int BITS>
+__global__ void __launch_bounds__(kSortThreads, 3)
+    radix_onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                          uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n_cap,
+                          const uint32_t *__restrict__ n_dev, int shift, const uint32_t *__restrict__ ghist,
+                          uint32_t *status, uint32_t *ticket) {
+    constexpr int RADIX = 1 << BITS;
+    constexpr int DPT = RADIX / kSortThreads;   // digits per thread
     constexpr int kWarps = kSortThreads / kWarp;
-    __shared__ uint32_t wh[kWarps][kRadix];
-    for (int i = threadIdx.x; i < kWarps * kRadix; i += kSortThreads) (&wh[0][0])[i] = 0;
+    __shared__ uint32_t wh[kWarps][RADIX];
+    __shared__ uint32_t base[RADIX];
+    __shared__ uint32_t scratch[33];
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < kWarps * RADIX; i += kSortThreads) (&wh[0][0])[i] = 0;
     __syncthreads();
+    const uint32_t tile = s_tile;
+    // the pair count may live on the device (owner side of the sharded backward): tiles past it have nothing to do
+    const int64_t n = n_dev != nullptr ? ((int64_t)*n_dev < n_cap ? (int64_t)*n_dev : n_cap) : n_cap;
+    if ((int64_t)tile * kSortTile >= n) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // warp w owns the contiguous slice [w * 32 * items, (w + 1) * 32 * items) of the tile so that
-    // (warp, round, lane) order is memory order: the sort stays stable.
-    const int64_t warp_base = (int64_t)blockIdx.x * kSortTile + (int64_t)warp * (kWarp * kSortItems);
-    uint32_t k[kSortItems], v[kSortItems], rank[kSortItems];
+    const int64_t warp_base = (int64_t)tile * kSortTile + (int64_t)warp * (kWarp * kSortItems);
+    uint32_t k[kSortItems], v[kSortItems];
+    uint16_t rank[kSortItems];
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         const int64_t i = warp_base + r * kWarp + lane;
@@ -200,8 +236,8 @@ __global__ void __launch_bounds__(kSortThreads)
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         const bool valid = warp_base + r * kWarp + lane < n;
-        const uint32_t d = (k[r] >> shift) & (kRadix - 1);
-        const uint32_t peers = __match_any_sync(kFull, valid ? d : (uint32_t)(kRadix + lane));
+        const uint32_t d = (k[r] >> shift) & (RADIX - 1);
+        const uint32_t peers = __match_any_sync(kFull, valid ? d : (uint32_t)(RADIX + lane));
         const int leader = __ffs(peers) - 1;
         uint32_t pre = 0;
         if (valid && lane == leader) {
@@ -209,54 +245,125 @@ __global__ void __launch_bounds__(kSortThreads)
             wh[warp][d] = pre + (uint32_t)__popc(peers);
         }
         pre = __shfl_sync(kFull, pre, leader);
-        rank[r] = pre + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        rank[r] = (uint16_t)(pre + (uint32_t)__popc(peers & ((1u << lane) - 1u)));
         __syncwarp();
     }
     __syncthreads();
-    {
-        const int d = threadIdx.x;  // one digit per thread (kSortThreads == kRadix)
-        uint32_t run = offsets[(int64_t)d * ntiles + blockIdx.x];
+    // thread t owns digits t * DPT .. t * DPT + DPT - 1
+    uint32_t gsum = 0, gh[DPT];
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) {
+        gh[j] = ghist[threadIdx.x * DPT + j];
+        gsum += gh[j];
+    }
+    uint32_t total;
+    uint32_t gbase = block_exclusive_256(gsum, scratch, &total);   // first output position of the thread's digits
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) {
+        const int d = threadIdx.x * DPT + j;
+        uint32_t count = 0;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
             const uint32_t c = wh[w][d];
-            wh[w][d] = run;
-            run += c;
+            wh[w][d] = count;          // exclusive over the warps of this tile
+            count += c;
         }
+        uint32_t *mine = status + (size_t)tile * RADIX + d;
+        uint32_t prefix = 0;
+        if (tile == 0) {
+            st_status(mine, count | kFlagInc);
+        } else {
+            st_status(mine, count | kFlagAgg);
+            // look back over earlier tiles, kLook of them per round trip, until an inclusive prefix turns up
+            constexpr int kLook = 8;
+            int64_t prev = (int64_t)tile - 1;
+            bool done = false;
+            while (!done) {
+                uint32_t s[kLook];
+#pragma unroll
+                for (int i = 0; i < kLook; ++i)
+                    s[i] = prev - i >= 0 ? ld_status(status + (size_t)(prev - i) * RADIX + d) : kFlagInc;
+#pragma unroll
+                for (int i = 0; i < kLook; ++i) {
+                    if (!done) {
+                        while ((s[i] & (kFlagAgg | kFlagInc)) == 0u) s[i] = ld_status(status + (size_t)(prev - i) * RADIX + d);
+                        prefix += s[i] & kValMask;
+                        done = (s[i] & kFlagInc) != 0u;
+                    }
+                }
+                prev -= kLook;
+            }
+            st_status(mine, (prefix + count) | kFlagInc);
+        }
+        base[d] = gbase + prefix;
+        gbase += gh[j];
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         if (warp_base + r * kWarp + lane < n) {
-            const uint32_t d = (k[r] >> shift) & (kRadix - 1);
-            const uint32_t dst = wh[warp][d] + rank[r];
+            const uint32_t d = (k[r] >> shift) & (RADIX - 1);
+            const uint32_t dst = base[d] + wh[warp][d] + rank[r];
             keys_out[dst] = k[r];
             vals_out[dst] = v[r];
         }
     }
 }
 
-static_assert(kSortThreads == kRadix, "scatter kernel maps one digit per thread");
-
-int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, int64_t n, int key_bits,
-                     uint32_t *counts, uint32_t *spine, cudaStream_t stream) {
-    if (n <= 0) return 0;
-    if (key_bits < 1) key_bits = 1;
-    if (key_bits > 32) key_bits = 32;
-    const int passes = (key_bits + kRadixBits - 1) / kRadixBits;
+template <int BITS>
+static int radix_sort_impl(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, int64_t n, int passes,
+                           uint32_t *scratch, cudaStream_t stream, bool hist_ready, const uint32_t *n_dev) {
+    constexpr int RADIX = 1 << BITS;
     const int64_t ntiles = sort_num_tiles(n);
+    uint32_t *tickets = scratch;
+    uint32_t *hist = scratch + 8;
+    uint32_t *status = hist + kMaxPasses * kMaxRadix;
+    cudaError_t e = cudaSuccess;
+    if (!hist_ready) {
+        if (n_dev != nullptr) {
+            set_error("radix_sort_pairs: a device-side count needs the histograms from the caller");
+            return CTR_E_BADARG;
+        }
+        int rc = radix_sort_prepare(scratch, n, passes * BITS, stream);
+        if (rc != CTR_OK) return rc;
+        int64_t hb = (n + kSortThreads * 8 - 1) / (kSortThreads * 8);
+        if (hb > kNumSMs * 4) hb = kNumSMs * 4;
+        note_launch(), radix_hist_all_kernel<BITS><<<(unsigned)hb, kSortThreads, 0, stream>>>(keys_a, n, passes, hist);
+    }
     uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
     for (int p = 0; p < passes; ++p) {
-        const int shift = p * kRadixBits;
-        note_launch(), radix_hist_kernel<<<(unsigned)ntiles, kSortThreads, 0, stream>>>(kin, n, shift, counts, ntiles);
-        int rc = exclusive_scan_u32(counts, (int64_t)kRadix * ntiles, spine, stream);
-        if (rc != CTR_OK) return rc;
-        note_launch(), radix_scatter_kernel<<<(unsigned)ntiles, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, counts, ntiles);
+        note_launch(), radix_onesweep_kernel<BITS><<<(unsigned)ntiles, kSortThreads, 0, stream>>>(
+            kin, vin, kout, vout, n, n_dev, p * BITS, hist + p * kMaxRadix, status + (size_t)p * ntiles * RADIX, tickets + p);
         uint32_t *t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }
-    cudaError_t e = cudaGetLastError();
+    e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "radix_sort_pairs");
     return passes & 1;
+}
+
+int radix_sort_prepare(uint32_t *scratch, int64_t n, int key_bits, cudaStream_t stream) {
+    if (n <= 0) return CTR_OK;
+    const int passes = sort_num_passes(key_bits);
+    const size_t zero_elems = 8 + (size_t)kMaxPasses * kMaxRadix + (size_t)passes * sort_num_tiles(n) * (1u << sort_digit_bits(key_bits));
+    cudaError_t e = cudaMemsetAsync(scratch, 0, zero_elems * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return cuda_fail(e, "radix sort scratch memset");
+    return CTR_OK;
+}
+
+int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, int64_t n, int key_bits,
+                     uint32_t *counts, uint32_t *spine, cudaStream_t stream, bool hist_ready, const uint32_t *n_dev) {
+    (void)spine;
+    if (n <= 0) return 0;
+    if (n >= (1ll << 30)) {
+        set_error("radix_sort_pairs: n=%lld must stay below 2^30", (long long)n);
+        return CTR_E_BADARG;
+    }
+    if (key_bits < 1) key_bits = 1;
+    if (key_bits > 32) key_bits = 32;
+    const int passes = sort_num_passes(key_bits);
+    if (sort_digit_bits(key_bits) == 9) return radix_sort_impl<9>(keys_a, vals_a, keys_b, vals_b, n, passes, counts, stream, hist_ready, n_dev);
+    return radix_sort_impl<8>(keys_a, vals_a, keys_b, vals_b, n, passes, counts, stream, hist_ready, n_dev);
 }
 
 }  // namespace ctr

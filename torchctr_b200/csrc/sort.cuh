@@ -7,24 +7,46 @@
 namespace ctr {
 
 constexpr int kSortThreads = 256;
-constexpr int kSortItems = 8;
+constexpr int kSortItems = 16;
 constexpr int kSortTile = kSortThreads * kSortItems;  // keys per block per pass
-constexpr int kRadixBits = 8;
-constexpr int kRadix = 1 << kRadixBits;
+constexpr int kMaxRadixBits = 9;
+constexpr int kMaxRadix = 1 << kMaxRadixBits;
+constexpr int kMaxPasses = 4;
 constexpr int kScanTile = 4096;                        // elements per block of the device scan
 
 inline int64_t sort_num_tiles(int64_t n) { return (n + kSortTile - 1) / kSortTile; }
 inline int64_t scan_num_blocks(int64_t m) { return (m + kScanTile - 1) / kScanTile; }
 
-// scratch sizes, in u32 elements
-inline int64_t sort_counts_elems(int64_t n) { return (int64_t)kRadix * sort_num_tiles(n); }
+// digit width of the LSD passes: 9 bits when that saves a pass (e.g. 26-bit keys: 3 passes instead of 4), else 8
+inline int sort_digit_bits(int key_bits) {
+    const int p8 = (key_bits + 7) / 8, p9 = (key_bits + 8) / 9;
+    return p9 < p8 ? 9 : 8;
+}
+inline int sort_num_passes(int key_bits) {
+    if (key_bits < 1) key_bits = 1;
+    if (key_bits > 32) key_bits = 32;
+    const int b = sort_digit_bits(key_bits);
+    return (key_bits + b - 1) / b;
+}
+
+// scratch sizes, in u32 elements: [tickets 8][global histograms passes x radix][tile status passes x tiles x radix]
+inline int64_t sort_counts_elems(int64_t n) {
+    return 8 + (int64_t)kMaxPasses * kMaxRadix + (int64_t)kMaxPasses * sort_num_tiles(n) * kMaxRadix;
+}
 inline int64_t scan_spine_elems(int64_t m) { return scan_num_blocks(m) + 1; }
 
-// Sorts n pairs by the low `key_bits` bits of the key.  Ping-pongs between (keys_a, vals_a) and
-// (keys_b, vals_b); returns 0 when the result ends in the a buffers, 1 when in the b buffers,
-// negative on a launch error.  counts: sort_counts_elems(n) u32; spine: scan_spine_elems(counts) u32.
+// Sorts n pairs by the low `key_bits` bits of the key: stable LSD radix sort, one kernel per pass (tile histograms
+// are chained with a decoupled look-back instead of a separate device scan), plus one kernel that builds the
+// digit histograms of every pass up front.  Ping-pongs between (keys_a, vals_a) and (keys_b, vals_b); returns 0
+// when the result ends in the a buffers (sort_num_passes(key_bits) even), 1 when in the b buffers, negative on a
+// launch error.  counts: sort_counts_elems(n) u32 of scratch; n < 2^30.
+// hist_ready: the caller zeroed the scratch with radix_sort_prepare() and then filled the digit histograms
+// (sort_hist(counts), [pass * kMaxRadix + digit]) itself, e.g. inside the kernel that produced the keys.
 int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, int64_t n,
-                     int key_bits, uint32_t *counts, uint32_t *spine, cudaStream_t stream);
+                     int key_bits, uint32_t *counts, uint32_t *spine, cudaStream_t stream, bool hist_ready = false,
+                     const uint32_t *n_dev = nullptr);   // n_dev: device-side pair count (<= n), needs hist_ready
+int radix_sort_prepare(uint32_t *counts, int64_t n, int key_bits, cudaStream_t stream);
+inline uint32_t *sort_hist(uint32_t *counts) { return counts + 8; }
 
 // Given sorted keys: run_start[r] = first position of the r-th run of equal keys, run_start[R] = n,
 // counters[0] = R (all runs), counters[1] = number of runs whose key != 0xffffffff.

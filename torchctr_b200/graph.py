@@ -15,7 +15,10 @@ import torch
 
 
 class GraphedTrainStep:
-    def __init__(self, model, optimizer, example_batch, warmup: int = 3):
+    def __init__(self, model, optimizer, example_batch, warmup: int = 3, backward_fn=None):
+        """``backward_fn(loss)`` replaces ``loss.backward()`` (multi-GPU: scale by 1 / world, all-reduce the
+        replicated gradients -- NCCL collectives are captured with the rest of the step)."""
+        self._backward_fn = backward_fn
         feats, labels = example_batch
         self.model, self.optimizer = model, optimizer
         dev = next(model.parameters()).device
@@ -41,6 +44,7 @@ class GraphedTrainStep:
         self.static_feats = dict(zip(self._keys, views[:-1]))
         self.static_labels = views[-1]
         self._bindings = [g.binding for g in getattr(model, "_groups", []) if g.binding is not None]
+        self._bindings += [b for b in getattr(getattr(model, "_sharded", None), "bindings", []) if b is not None]
         for b in self._bindings:
             b.enable_device_hyper(dev)
         self._stage(example_batch)
@@ -59,7 +63,10 @@ class GraphedTrainStep:
     def _eager_step(self):
         self.optimizer.zero_grad(set_to_none=True)
         loss = self.model.training_step((self.static_feats, self.static_labels), 0)
-        loss.backward()
+        if self._backward_fn is not None:
+            self._backward_fn(loss)
+        else:
+            loss.backward()
         self.optimizer.step()
         return loss
 

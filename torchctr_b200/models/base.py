@@ -98,7 +98,11 @@ class CTRModelBase(nn.Module):
     def table_parameters(self):
         """Parameters updated by the fused sparse optimizer (every EmbeddingTable weight)."""
         from ..nn.embedding import EmbeddingTable
-        return [m.weight for m in self.modules() if isinstance(m, EmbeddingTable)]
+        params = [m.weight for m in self.modules() if isinstance(m, EmbeddingTable)]
+        shards = getattr(self._sharded, "shards", None)
+        if isinstance(shards, nn.ParameterList):          # peer-memory shards are bare parameters
+            params += list(shards)
+        return params
 
     def dense_parameters(self):
         """Everything else: hand these to the torch optimizer when the tables are fused, so that it

@@ -279,7 +279,7 @@ class _LookupCall:
         link = self.plan_link
         if link is None:
             ws = _Workspace.get(dev, ops.emb_bwd_workspace_bytes(call))
-            ops.emb_bwd_plan(call, ws)
+            ops.emb_bwd_plan(call, ws, runs=not fused)
         else:
             # the sort / run list depends on the ids only: tables that share them (DeepFM's first-order
             # weights next to its embeddings) share one plan per step
@@ -287,7 +287,7 @@ class _LookupCall:
             link.nbytes = max(link.nbytes, need)
             if link.ws is None:
                 link.ws = torch.empty(max(link.nbytes, need) + 256, dtype=torch.uint8, device=dev)
-                ops.emb_bwd_plan(call, link.ws)
+                ops.emb_bwd_plan(call, link.ws, runs=not fused)
             elif link.ws.numel() < need:
                 raise RuntimeError("shared backward plan: workspace too small; call PlanLink.reserve first")
             ws = link.ws

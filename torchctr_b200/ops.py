@@ -179,11 +179,13 @@ def emb_bwd_workspace_bytes(call: GroupCall) -> int:
     return _lib.check(_lib.lib().ctr_emb_bwd_workspace_bytes(C.byref(call.struct)), "ctr_emb_bwd_workspace_bytes")
 
 
-def emb_bwd_plan(call: GroupCall, workspace: torch.Tensor) -> None:
+def emb_bwd_plan(call: GroupCall, workspace: torch.Tensor, runs: bool = True) -> None:
+    """Sort the (row, slot) pairs of the group; ``runs=False`` skips the run list, which only the unique-row
+    outputs of ``emb_bwd_apply`` need (a fused training step does not ask for them)."""
     _chk(workspace, "workspace", torch.uint8)
     with _timed("emb_bwd_plan"):
-        _lib.check(_lib.lib().ctr_emb_bwd_plan(C.byref(call.struct), workspace.data_ptr(), workspace.numel(), _stream()),
-                   "ctr_emb_bwd_plan")
+        _lib.check(_lib.lib().ctr_emb_bwd_plan_ex(C.byref(call.struct), workspace.data_ptr(), workspace.numel(),
+                                                  0 if runs else _lib.PLAN_NO_RUNS, _stream()), "ctr_emb_bwd_plan")
 
 
 def make_opt(kind: str = "none", lr: float = 0.0, eps: float = 1e-10, betas=(0.9, 0.999), step: int = 1,
@@ -295,9 +297,10 @@ def fm_fwd(x: torch.Tensor, F: int, D: int, first: torch.Tensor | None = None, o
     nfirst = 0 if first is None else first.shape[1]
     if first is not None and (first.dtype != torch.float32 or first.stride(1) != 1):
         raise ValueError("first must be f32 with unit inner stride")
-    _lib.check(_lib.lib().ctr_fm_fwd(x.data_ptr(), x.stride(0), B, F, D, _lib.ptr(first), nfirst,
-                                     0 if first is None else first.stride(0), out.data_ptr(), out.stride(0),
-                                     int(accumulate), _stream(x)), "ctr_fm_fwd")
+    with _timed("fm_fwd"):
+        _lib.check(_lib.lib().ctr_fm_fwd(x.data_ptr(), x.stride(0), B, F, D, _lib.ptr(first), nfirst,
+                                         0 if first is None else first.stride(0), out.data_ptr(), out.stride(0),
+                                         int(accumulate), _stream(x)), "ctr_fm_fwd")
     return out
 
 
@@ -305,9 +308,10 @@ def fm_bwd(x: torch.Tensor, F: int, D: int, gout: torch.Tensor, gx: torch.Tensor
            gfirst: torch.Tensor | None = None) -> None:
     B = x.shape[0]
     nfirst = 0 if gfirst is None else gfirst.shape[1]
-    _lib.check(_lib.lib().ctr_fm_bwd(x.data_ptr(), x.stride(0), B, F, D, gout.data_ptr(), gout.stride(0), gx.data_ptr(),
-                                     gx.stride(0), int(accumulate), _lib.ptr(gfirst), nfirst,
-                                     0 if gfirst is None else gfirst.stride(0), _stream(x)), "ctr_fm_bwd")
+    with _timed("fm_bwd"):
+        _lib.check(_lib.lib().ctr_fm_bwd(x.data_ptr(), x.stride(0), B, F, D, gout.data_ptr(), gout.stride(0), gx.data_ptr(),
+                                         gx.stride(0), int(accumulate), _lib.ptr(gfirst), nfirst,
+                                         0 if gfirst is None else gfirst.stride(0), _stream(x)), "ctr_fm_bwd")
 
 
 def cross_combine_fwd(x0, x, u, bias) -> torch.Tensor:
@@ -376,3 +380,49 @@ def linear_fwd(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor | None = Non
         _lib.check(_lib.lib().ctr_linear_fwd(A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), _lib.ptr(bias),
                                              out.data_ptr(), out.stride(0), M, N, K, act, _stream(A)), "ctr_linear_fwd")
     return out
+
+
+# ---- row-sharded tables over peer memory -----------------------------------------------------------------------
+def ptr_array(ptrs):
+    """ctypes array of device pointers (one per rank)."""
+    return (C.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+def make_shard(world: int, rank: int, adj: torch.Tensor) -> _lib.Shard:
+    _chk(adj, "adj", torch.int64)
+    return _lib.Shard(world, rank, adj.data_ptr())
+
+
+def emb_pool_fwd_sharded(call: GroupCall, shard: _lib.Shard, tables) -> None:
+    with _timed("emb_pool_fwd"):
+        _lib.check(_lib.lib().ctr_emb_pool_fwd_sharded(C.byref(call.struct), C.byref(shard), tables, _stream()),
+                   "ctr_emb_pool_fwd_sharded")
+
+
+def route_p2p_workspace_bytes(call: GroupCall) -> int:
+    return _lib.check(_lib.lib().ctr_route_p2p_workspace_bytes(C.byref(call.struct)), "ctr_route_p2p_workspace_bytes")
+
+
+def route_p2p_build(call: GroupCall, shard: _lib.Shard, counts_ptr: int, keys_ptr: int, slots_ptr: int,
+                    workspace: torch.Tensor) -> None:
+    with _timed("route_p2p_build"):
+        _lib.check(_lib.lib().ctr_route_p2p_build(C.byref(call.struct), C.byref(shard), counts_ptr, keys_ptr, slots_ptr,
+                                                  workspace.data_ptr(), workspace.numel(), _stream()), "ctr_route_p2p_build")
+
+
+def emb_bwd_p2p_workspace_bytes(call: GroupCall, world: int) -> int:
+    return _lib.check(_lib.lib().ctr_emb_bwd_p2p_workspace_bytes(C.byref(call.struct), world), "ctr_emb_bwd_p2p_workspace_bytes")
+
+
+def emb_bwd_plan_p2p(call: GroupCall, shard: _lib.Shard, counts, keys, slots, workspace: torch.Tensor) -> None:
+    with _timed("emb_bwd_plan"):
+        _lib.check(_lib.lib().ctr_emb_bwd_plan_p2p(C.byref(call.struct), C.byref(shard), counts, keys, slots,
+                                                   workspace.data_ptr(), workspace.numel(), _stream()), "ctr_emb_bwd_plan_p2p")
+
+
+def emb_bwd_apply_p2p(call: GroupCall, shard: _lib.Shard, workspace: torch.Tensor, opt: _lib.Opt, grads,
+                      num_unique: torch.Tensor | None = None) -> None:
+    _chk(num_unique, "num_unique", torch.int64)
+    with _timed("emb_bwd_apply"):
+        _lib.check(_lib.lib().ctr_emb_bwd_apply_p2p(C.byref(call.struct), C.byref(shard), workspace.data_ptr(), C.byref(opt),
+                                                    grads, _lib.ptr(num_unique), _stream()), "ctr_emb_bwd_apply_p2p")

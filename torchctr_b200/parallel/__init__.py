@@ -1,4 +1,6 @@
 from .sharded import ShardedTables, reduce_dense_grads, shard_bases, local_rows
 from .model import shard_model
+from .peer import IpcTransport, PeerShardedTables, ThreadTransport
 
-__all__ = ["ShardedTables", "reduce_dense_grads", "shard_bases", "local_rows", "shard_model"]
+__all__ = ["ShardedTables", "reduce_dense_grads", "shard_bases", "local_rows", "shard_model", "PeerShardedTables", "IpcTransport",
+           "ThreadTransport"]

@@ -6,7 +6,7 @@ import torch.nn as nn
 from .sharded import ShardedTables, reduce_dense_grads
 
 
-def shard_model(model, pg=None, device=None, backend=None):
+def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=None):
     """Every rank calls this with an identically initialised ``model`` (same seed).  The model's tables
     (and, for DeepFM, its first-order tables, which share the ids) are cut into this rank's rows, fused
     into one shard per width on ``device`` and the full tables are dropped; the dense part stays
@@ -19,7 +19,15 @@ def shard_model(model, pg=None, device=None, backend=None):
     """
     groups = model._groups
     full = [[g.tables[n] for n in g.names] for g in groups]
-    if device is not None:
+    if mode is None:
+        mode = "peer" if (backend is None and device is not None and str(device).startswith("cuda")) or transport is not None else "a2a"
+    if mode == "peer":
+        # B200 path: rows are read from / gradients pulled through NVLink peer mappings inside the kernels
+        from .peer import IpcTransport, PeerShardedTables
+        if transport is None:
+            transport = IpcTransport(pg, device)
+        sharded = PeerShardedTables(groups[0].names, full, transport, device)
+    elif device is not None:
         # shards are built on the target device straight from the (host) full tables
         import torch
         with torch.device(device):

@@ -1,0 +1,370 @@
+"""Row-sharded embedding tables over peer memory: NVLink P2P loads inside the kernels, no all-to-all.
+
+The reference is replicas-only (``Accelerator().prepare`` -> DDP, ``torchctr/trainer.py:128-130``): every rank
+holds every table and dense ``[V, D]`` gradients are all-reduced.  Here one process per GPU holds ``1/P`` of every
+table -- row ``r`` of table ``f`` lives on rank ``(r + f) mod P`` (the ``+ f`` spreads the hottest row of every
+table, id 0 under a Zipf law, over the ranks) -- the batch stays data-parallel and a step is
+
+  forward   ONE lookup kernel per width that reads every row straight from its owner's shard through the peer
+            mapping (``ctr_emb_pool_fwd_sharded``); the slots are also bucketed by owner into this rank's routing
+            lists (``ctr_route_p2p_build``), which live in peer-visible memory;
+  backward  the gradient w.r.t. the pooled output is copied into a peer-visible buffer; barrier; every OWNER pulls
+            the (row, slot) lists addressed to it from all ranks, sorts them (``ctr_emb_bwd_plan_p2p``) and runs the
+            fused reduce + optimizer sweep, reading each slot's gradient from the rank that produced it
+            (``ctr_emb_bwd_apply_p2p``); barrier.
+
+No host read happens anywhere (pair counts stay on the device), so the whole step can be captured into a CUDA
+graph together with the NCCL all-reduce of the replicated tower.  The two barriers are tiny NCCL all-reduces on the
+compute stream (``IpcTransport``); the tests run the ranks as threads of one process on one GPU
+(``ThreadTransport``), which exercises every kernel of the path without a second device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .. import _lib, ops
+from ..nn.embedding import SparseOptimizerBinding
+
+_TYPESTR = {torch.float32: "<f4", torch.int32: "<i4", torch.int64: "<i8", torch.uint8: "|u1"}
+
+
+class PeerBuffer:
+    """Device memory other processes can map (``ctr_peer_alloc``), viewed as torch tensors."""
+
+    def __init__(self, nbytes: int, device):
+        self.device = torch.device(device)
+        self.nbytes = max(int(nbytes), 256)
+        ptr = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ctr_peer_alloc(self.nbytes, C.byref(ptr)), "ctr_peer_alloc")
+        self.ptr = int(ptr.value)
+
+    def handle(self) -> bytes:
+        buf = C.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ctr_peer_export(self.ptr, buf), "ctr_peer_export")
+        return buf.raw
+
+    def tensor(self, dtype, shape, offset_bytes: int = 0) -> torch.Tensor:
+        """A torch view of the buffer (it keeps this object alive)."""
+        view = _ArrayView(self, self.ptr + offset_bytes, tuple(int(s) for s in shape), _TYPESTR[dtype])
+        return torch.as_tensor(view, device=self.device)
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", 0):
+                with torch.cuda.device(self.device):
+                    _lib.lib().ctr_peer_free(self.ptr)
+                self.ptr = 0
+        except Exception:       # interpreter shutdown
+            pass
+
+
+class _ArrayView:
+    def __init__(self, owner, ptr, shape, typestr):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2,
+                                         "strides": None}
+
+
+class IpcTransport:
+    """One process per GPU: buffers are exchanged as CUDA IPC handles through ``torch.distributed``."""
+
+    def __init__(self, pg=None, device=None):
+        self.pg = pg
+        self.world = dist.get_world_size(pg)
+        self.rank = dist.get_rank(pg)
+        self.device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self._token = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._opened = []
+
+    def share(self, buf: PeerBuffer):
+        """Collective: every rank passes its buffer, gets the device pointer of every rank's buffer."""
+        handles = [None] * self.world
+        dist.all_gather_object(handles, buf.handle(), group=self.pg)
+        ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(buf.ptr)
+                continue
+            p = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().ctr_peer_open(C.create_string_buffer(h, len(h)), C.byref(p)), "ctr_peer_open")
+            self._opened.append(int(p.value))
+            ptrs.append(int(p.value))
+        return ptrs
+
+    def barrier(self):
+        """After this point of the stream every rank's earlier work on its stream is complete (and visible
+        through the peer mappings).  A 4-byte NCCL all-reduce: capturable into a CUDA graph."""
+        dist.all_reduce(self._token, group=self.pg)
+
+
+class ThreadTransport:
+    """Test transport: the ranks are threads of one process on ONE device; 'peer' pointers are plain device pointers."""
+
+    class Shared:
+        def __init__(self, world):
+            self.world = world
+            self.barrier = threading.Barrier(world)
+            self.slots = {}
+            self.lock = threading.Lock()
+
+    def __init__(self, shared: "ThreadTransport.Shared", rank: int, device):
+        self.shared, self.world, self.rank, self.device = shared, shared.world, rank, torch.device(device)
+        self._seq = 0
+
+    def share(self, buf: PeerBuffer):
+        key = self._seq
+        self._seq += 1
+        with self.shared.lock:
+            self.shared.slots.setdefault(key, {})[self.rank] = buf.ptr
+        self.shared.barrier.wait()
+        ptrs = [self.shared.slots[key][r] for r in range(self.world)]
+        self.shared.barrier.wait()
+        return ptrs
+
+    def barrier(self):
+        torch.cuda.synchronize(self.device)
+        self.shared.barrier.wait()
+
+
+def owned_rows(num_rows: int, table: int, rank: int, world: int):
+    """(first row, count) of the rows of table ``table`` that rank ``rank`` owns: rows r with (r + table) % world == rank."""
+    first = (rank - table) % world
+    count = 0 if first >= num_rows else (num_rows - first + world - 1) // world
+    return first, count
+
+
+def shard_geometry(num_rows_list, world: int):
+    """base[o][f] = first row of table f inside owner o's fused shard (every table gets at least one row so that no
+    table is empty anywhere), total[o] = rows of that shard, adj i64 [world * F] as the kernels use it:
+    virtual row = adj[o * F + f] + (r + f) // world."""
+    F = len(num_rows_list)
+    base = [[0] * F for _ in range(world)]
+    total = [0] * world
+    adj = torch.zeros(world * F, dtype=torch.int64)
+    for o in range(world):
+        acc = 0
+        for f, v in enumerate(num_rows_list):
+            first, count = owned_rows(v, f, o, world)
+            base[o][f] = acc
+            adj[o * F + f] = acc - (first + f) // world
+            acc += max(count, 1)
+        total[o] = acc
+    return base, total, adj
+
+
+class _PeerLookupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, st, ids_list, dense, *weights):
+        ctx.st = st
+        ctx.has_dense = dense is not None
+        ctx.dense_width = 0 if dense is None else dense.shape[1]
+        outs = st._forward(ids_list, dense)
+        ctx.training = st.training
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grad_outs):
+        st = ctx.st
+        st._backward(grad_outs)
+        gdense = None
+        if ctx.has_dense and ctx.needs_input_grad[2] and grad_outs[0] is not None:
+            c0 = st.num_features * st.dims[0]
+            gdense = grad_outs[0][:, c0:c0 + ctx.dense_width]
+        return (None, None, gdense) + (None,) * len(st.dims)
+
+
+class PeerShardedTables(nn.Module):
+    """The tables of one lookup group, row-sharded over the ranks of ``transport``.  ``dims`` lists the widths that
+    share the ids (DeepFM: ``[emb_dim, 1]``); width ``w`` of table ``f`` is ``full_tables[w][f]`` (``[V_f, dims[w]]``)."""
+
+    def __init__(self, names, full_tables, transport, device=None):
+        super().__init__()
+        self.transport = transport
+        self.world, self.rank = transport.world, transport.rank
+        if self.world > _lib.MAX_WORLD:
+            raise ValueError(f"at most {_lib.MAX_WORLD} ranks")
+        dev = torch.device(device if device is not None else transport.device)
+        self.device = dev
+        self.names = list(names)
+        self.num_features = len(self.names)
+        first = full_tables[0]
+        self.num_rows = [int(t.num_embeddings) for t in first]
+        self.index_kinds = [t.index_kind for t in first]
+        self.hash_seeds = [t.hash_seed for t in first]
+        for t in first:
+            if t.pooling != "sum" or t.use_id_weight or t.index_kind == "vocab":
+                raise NotImplementedError("sharded lookup: sum pooling, direct / hashed ids")
+        self.dims = [int(tabs[0].embedding_dim) for tabs in full_tables]
+        self.base, self.total, adj = shard_geometry(self.num_rows, self.world)
+        self.register_buffer("adj", adj.to(dev), persistent=False)
+        self._shard_struct = ops.make_shard(self.world, self.rank, self.adj)
+        # this rank's fused shard of every width, in peer-visible memory
+        self._shard_bufs, self._table_ptrs = [], []
+        self.shards = nn.ParameterList()
+        rows = self.total[self.rank]
+        for tabs, D in zip(full_tables, self.dims):
+            buf = PeerBuffer(rows * D * 4, dev)
+            w = buf.tensor(torch.float32, (rows, D))
+            for f, t in enumerate(tabs):
+                fr, n = owned_rows(self.num_rows[f], f, self.rank, self.world)
+                if n:
+                    b = self.base[self.rank][f]
+                    w[b:b + n] = t.weight.detach()[fr::self.world].to(dev)
+            self._shard_bufs.append(buf)
+            self.shards.append(nn.Parameter(w, requires_grad=True))
+            self._table_ptrs.append(ops.ptr_array(transport.share(buf)))
+        self.opt_state0 = [None] * len(self.dims)
+        self.opt_state1 = [None] * len(self.dims)
+        self.bindings = [None] * len(self.dims)
+        self._B = None              # batch geometry the peer buffers were sized for
+        self._route_ws = None
+        self._plan_ws = None
+
+    # ---- optimizer ---------------------------------------------------------------------------------------------
+    def bind_optimizer(self, optimizer, kind=None):
+        self.bindings = []
+        for w in range(len(self.dims)):
+            holder = _ShardHolder(self.shards[w])
+            self.bindings.append(SparseOptimizerBinding(optimizer, [holder], kind))
+
+    def _ensure_state(self, w, kind, init):
+        p = self.shards[w]
+        if kind in ("adagrad", "adam") and self.opt_state0[w] is None:
+            self.opt_state0[w] = torch.full_like(p.data, init if kind == "adagrad" else 0.0)
+        if kind == "rowwise_adagrad" and self.opt_state0[w] is None:
+            self.opt_state0[w] = torch.full((p.shape[0],), init, device=p.device)
+        if kind == "adam" and self.opt_state1[w] is None:
+            self.opt_state1[w] = torch.zeros_like(p.data)
+
+    # ---- per-batch peer buffers ----------------------------------------------------------------------------------
+    def _ensure_buffers(self, ids_list):
+        B = ids_list[0].shape[0]
+        Ls = tuple(i.shape[1] for i in ids_list) + (self._dense_width,)
+        if self._B == (B, Ls):
+            return
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("peer buffers must be sized (one eager step) before the step is captured into a CUDA graph")
+        S = B * sum(Ls[:-1])
+        dev = self.device
+        tr = self.transport
+        self._route_buf = PeerBuffer(256 + 8 * max(S, 1), dev)          # [counts 64 words][keys S][slots S]
+        ptrs = tr.share(self._route_buf)
+        self._peer_counts = ops.ptr_array(ptrs)
+        self._peer_keys = ops.ptr_array([p + 256 for p in ptrs])
+        self._peer_slots = ops.ptr_array([p + 256 + 4 * max(S, 1) for p in ptrs])
+        self._grad_bufs, self._peer_grads, self._strides = [], [], []
+        for w, D in enumerate(self.dims):
+            stride = (self.num_features * D + (self._dense_width if w == 0 else 0) + 3) // 4 * 4
+            buf = PeerBuffer(B * stride * 4, dev)
+            self._grad_bufs.append(buf)
+            self._peer_grads.append(ops.ptr_array(tr.share(buf)))
+            self._strides.append(stride)
+        self._S = S
+        self._B = (B, Ls)
+
+    _dense_width = 0
+
+    def _request_specs(self, ids_list, w):
+        D = self.dims[w]
+        return [ops.FeatureSpec(ids=ids, table=None, num_rows=v, D=D, out_col=f * D, index_kind=k, hash_seed=s)
+                for f, (ids, v, k, s) in enumerate(zip(ids_list, self.num_rows, self.index_kinds, self.hash_seeds))]
+
+    def _owner_specs(self, ids_list, w, with_state):
+        D = self.dims[w]
+        shard = self.shards[w].data
+        specs = []
+        for f, ids in enumerate(ids_list):
+            _, n = owned_rows(self.num_rows[f], f, self.rank, self.world)
+            n = max(n, 1)
+            b = self.base[self.rank][f]
+            s0 = self.opt_state0[w] if with_state else None
+            s1 = self.opt_state1[w] if with_state else None
+            specs.append(ops.FeatureSpec(ids=ids, table=shard[b:b + n], num_rows=n, D=D, out_col=f * D,
+                                         state0=None if s0 is None else s0[b:b + n],
+                                         state1=None if s1 is None else s1[b:b + n]))
+        return specs
+
+    # ---- forward / backward ----------------------------------------------------------------------------------------
+    def forward(self, feats, dense=None):
+        dev = self.device
+        ids = []
+        for n in self.names:
+            t = feats[n]
+            if t.dim() == 1:
+                t = t.unsqueeze(1)
+            ids.append(t.to(dev, dtype=torch.int64, non_blocking=True).contiguous())
+        if dense is not None:
+            dense = dense.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        return _PeerLookupFn.apply(self, ids, dense, *list(self.shards))
+
+    def _forward(self, ids_list, dense):
+        B = ids_list[0].shape[0]
+        self._dense_width = 0 if dense is None else dense.shape[1]
+        if self.training:
+            self._ensure_buffers(ids_list)
+        self._ids = ids_list
+        dev = self.device
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        outs = []
+        for w, D in enumerate(self.dims):
+            width = self.num_features * D + (self._dense_width if w == 0 else 0)
+            stride = (width + 3) // 4 * 4
+            out = torch.empty(B, stride, dtype=torch.float32, device=dev)
+            call = ops.make_group(self._request_specs(ids_list, w), B, out, stride, dense=dense if w == 0 else None,
+                                  dense_col=self.num_features * D, zero_from=width if stride > width else -1, status=status)
+            ops.emb_pool_fwd_sharded(call, self._shard_struct, self._table_ptrs[w])
+            outs.append(out)
+        if self.training:
+            call = ops.make_group(self._request_specs(ids_list, 0), B, None, self.num_features * self.dims[0], status=status)
+            need = ops.route_p2p_workspace_bytes(call)
+            if self._route_ws is None or self._route_ws.numel() < need:
+                self._route_ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+            rp = self._route_buf.ptr
+            ops.route_p2p_build(call, self._shard_struct, rp, rp + 256, rp + 256 + 4 * max(self._S, 1), self._route_ws)
+        self.status = status
+        return outs
+
+    def _backward(self, grad_outs):
+        if any(b is None for b in self.bindings):
+            raise RuntimeError("sharded tables need bind_optimizer(): there is no dense or sparse .grad to hand back")
+        ids_list = self._ids
+        B = ids_list[0].shape[0]
+        live = [w for w, g in enumerate(grad_outs) if g is not None]
+        for w in live:                                   # gradients into the peer-visible buffers
+            g = grad_outs[w]
+            self._grad_bufs[w].tensor(torch.float32, (B, self._strides[w])).copy_(g)
+        self.transport.barrier()                         # every rank's routing lists and gradients are in place
+        plan_call = ops.make_group(self._owner_specs(ids_list, 0, False), B, None, self._strides[0])
+        need = ops.emb_bwd_p2p_workspace_bytes(plan_call, self.world)
+        if self._plan_ws is None or self._plan_ws.numel() < need:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("run one eager step before capturing: the owner-side workspace is not sized yet")
+            self._plan_ws = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+        ops.emb_bwd_plan_p2p(plan_call, self._shard_struct, self._peer_counts, self._peer_keys, self._peer_slots, self._plan_ws)
+        for w in live:
+            bind = self.bindings[w]
+            self._ensure_state(w, bind.kind, bind.initial_accumulator_value())
+            call = ops.make_group(self._owner_specs(ids_list, w, True), B, None, self._strides[w])
+            ops.emb_bwd_apply_p2p(call, self._shard_struct, self._plan_ws, bind.next_opt(), self._peer_grads[w])
+        self.transport.barrier()                         # nobody overwrites lists / gradients / reads rows too early
+
+    # ---- inspection (tests, checkpoints): this rank's rows of table f, width w ------------------------------------------
+    def local_rows_of(self, w, f):
+        fr, n = owned_rows(self.num_rows[f], f, self.rank, self.world)
+        b = self.base[self.rank][f]
+        return fr, self.shards[w].data[b:b + n]
+
+
+class _ShardHolder:
+    """What SparseOptimizerBinding needs from a table module: its ``weight``."""
+
+    def __init__(self, weight):
+        self.weight = weight

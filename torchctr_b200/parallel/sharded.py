@@ -104,7 +104,7 @@ class CudaBackend:
             need = ops.emb_bwd_workspace_bytes(ops.make_group([widest], n, None, widest.D))
             ws = torch.empty(need + 256, dtype=torch.uint8, device=grads.device) if cache is not None \
                 else _Workspace.get(grads.device, need)
-            ops.emb_bwd_plan(call, ws)
+            ops.emb_bwd_plan(call, ws, runs=False)
             if cache is not None:
                 cache["ws"] = ws
         ops.emb_bwd_apply(call, ws, binding.next_opt())
