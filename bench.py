@@ -307,12 +307,16 @@ def run_ours(args):
         kern, roofline = kernel_roofline(model, resident, B, dev, iters=args.steps)
         print(json.dumps({"kernels": kern, "roofline": roofline, "kernels_in_step": in_step}), flush=True)
         return
-    if args.no_graph or world > 1:                      # the all-to-all split sizes are read on the host: no graph
+    if args.no_graph:
         step = eager_step
     else:
         from torchctr_b200.graph import GraphedTrainStep
         l0 = ops.kernel_launches()
-        graphed = GraphedTrainStep(model, opt, resident[0], warmup=1)
+
+        def sharded_backward(loss):                      # tables: owners pull gradients over NVLink; tower: all-reduce
+            (loss / world).backward()
+            model.reduce_dense_grads()
+        graphed = GraphedTrainStep(model, opt, resident[0], warmup=1, backward_fn=sharded_backward if world > 1 else None)
         launches_per_step = (ops.kernel_launches() - l0) // 2      # one eager warm-up + one captured step
         step = lambda batch, i: graphed(batch)           # noqa: E731
 
@@ -364,10 +368,11 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, world),
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "cuda_graph": not (args.no_graph or world > 1), "kernels": kern, "kernels_in_step": in_step,
+        "gpu_launches": launches, "cuda_graph": not args.no_graph, "kernels": kern, "kernels_in_step": in_step,
         "roofline": roofline,
-        "parallelism": "single GPU" if world == 1 else f"tables row-sharded over {world} GPUs (owner = row mod P, NCCL all-to-all of "
-                       "rows / vectors / gradients), batch data-parallel, tower replicated + all-reduce",
+        "parallelism": "single GPU" if world == 1 else f"tables row-sharded over {world} GPUs (owner = (row + table) mod P); rows read "
+                       "and gradients pulled through NVLink peer mappings inside the lookup / update kernels (no all-to-all), "
+                       "batch data-parallel, tower replicated + one NCCL all-reduce",
         "clocks": clock_info,
         "tower_matmul": "torch F.linear, TF32 tensor cores, fp32 accumulate",
     }
@@ -380,7 +385,14 @@ def run_ours(args):
                           f"(oracle.models.OracleDeepFM, eager fp32 CPU)"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # the measurement is done and printed: tear down without letting a slow NCCL / IPC teardown hold the job
+        sys.stdout.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(timeout=20)
+        os._exit(0)
 
 
 def main():

@@ -78,7 +78,7 @@ class TorchCpuBackend:
 def main():
     backend = sys.argv[1]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    if backend == "cuda":
+    if backend in ("cuda", "peer"):
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
         dev = torch.device("cuda", torch.cuda.current_device())
         dist.init_process_group("nccl", device_id=dev)
@@ -106,15 +106,21 @@ def main():
     names = [f"f{i}" for i in range(len(Vs))]
     tabs16 = [EmbeddingTable(v, D, _weight=w.clone()) for v, w in zip(Vs, full16)]
     tabs1 = [EmbeddingTable(v, 1, _weight=w.clone()) for v, w in zip(Vs, full1)]
-    with torch.device(dev):
-        st = ShardedTables(names, [tabs16, tabs1], None, TorchCpuBackend() if backend == "cpu" else None)
-    st = st.to(dev)
-    opt = torch.optim.SGD([s.weight for s in st.shards], lr=0.5)
+    if backend == "peer":          # rows read / gradients pulled through CUDA IPC peer mappings, no all-to-all
+        from torchctr_b200.parallel.peer import IpcTransport, PeerShardedTables
+        st = PeerShardedTables(names, [tabs16, tabs1], IpcTransport(None, dev), dev).train()
+        shard_params = list(st.shards)
+    else:
+        with torch.device(dev):
+            st = ShardedTables(names, [tabs16, tabs1], None, TorchCpuBackend() if backend == "cpu" else None)
+        st = st.to(dev)
+        shard_params = [s.weight for s in st.shards]
+    opt = torch.optim.SGD(shard_params, lr=0.5)
     st.bind_optimizer(opt, kind="sgd")
 
     feats = {n: t for n, t in zip(names, ids_all[rank])}
-    for s in st.shards:
-        s.weight.requires_grad_(True)
+    for p in shard_params:
+        p.requires_grad_(True)
     x, first = st(feats, dense.to(dev))
     ref_x = torch.cat([oe.pooled_lookup(i, w) for i, w in zip(ids_all[rank], full16)] + [dense], 1)
     ref_1 = torch.cat([oe.pooled_lookup(i, w) for i, w in zip(ids_all[rank], full1)], 1)
@@ -136,10 +142,14 @@ def main():
             for r in range(world):
                 dense_grad += oe.dense_table_grad(ids_all[r][f], gouts[r][:, f * Dw:(f + 1) * Dw], v)
             expect = wt - 0.5 * dense_grad
-            n = local_rows(v, rank, world)
-            b = int(base[rank, f])
-            got = st.shards[w].weight.detach().cpu()[b:b + n]
-            assert torch.allclose(got, expect[rank::world], rtol=1e-5, atol=1e-5), f"update width {Dw} table {f}"
+            if backend == "peer":
+                fr, rows = st.local_rows_of(w, f)
+                got, want = rows.cpu(), expect[fr::world]
+            else:
+                n = local_rows(v, rank, world)
+                b = int(base[rank, f])
+                got, want = st.shards[w].weight.detach().cpu()[b:b + n], expect[rank::world]
+            assert got.shape == want.shape and torch.allclose(got, want, rtol=1e-5, atol=2e-5), f"update width {Dw} table {f}"
     dist.barrier()
     if rank == 0:
         print("SHARDED_OK", backend, world)

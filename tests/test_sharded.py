@@ -37,3 +37,11 @@ def test_sharded_two_gpus_nccl():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     _run("cuda", 2)
+
+
+@pytest.mark.gpu
+def test_peer_two_gpus_ipc():
+    """The peer-memory path with real CUDA IPC mappings between two processes / two GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    _run("peer", 2)

@@ -55,14 +55,14 @@ class PeerBuffer:
         view = _ArrayView(self, self.ptr + offset_bytes, tuple(int(s) for s in shape), _TYPESTR[dtype])
         return torch.as_tensor(view, device=self.device)
 
-    def __del__(self):
-        try:
-            if getattr(self, "ptr", 0):
-                with torch.cuda.device(self.device):
-                    _lib.lib().ctr_peer_free(self.ptr)
-                self.ptr = 0
-        except Exception:       # interpreter shutdown
-            pass
+    def release(self):
+        """Free the memory.  Only call once no other rank maps it any more (the ranks agree on that themselves, e.g.
+        with a barrier); dropping the object does NOT free it, because cudaFree of memory a peer still has open is
+        undefined and process exit releases it anyway."""
+        if getattr(self, "ptr", 0):
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().ctr_peer_free(self.ptr), "ctr_peer_free")
+            self.ptr = 0
 
 
 class _ArrayView:
