@@ -215,6 +215,27 @@ int ctr_cross_combine_bwd(const float *x0, const float *u, const float *bias, co
 int ctr_linear_fwd(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias, float *C,
                    int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t act, void *stream);
 
+/* ---- tower block: BatchNorm1d (training) + ReLU + Dropout around a Linear, fused --------------------------
+ * Replaces the BatchNorm1d / ReLU / Dropout modules of torchctr/models/dnn.py:39-45 in training mode and the
+ * bias-gradient reduction of the Linear in front of them.  z = x W^T + b is f32 [B, N] (N multiple of 4, <= 1024),
+ * row pitches in floats, multiples of 4; every pointer 16-byte aligned.  workspace: ctr_tower_workspace_bytes(N). */
+int64_t ctr_tower_workspace_bytes(int32_t N);
+/* batch statistics of z: mean[N], rstd[N] = 1 / sqrt(biased var + eps); running_mean / running_var (may be NULL)
+ * and num_batches_tracked (may be NULL) are updated as torch.nn.BatchNorm1d does with `momentum`. */
+int ctr_bn_stats(const float *z, int64_t ldz, int32_t B, int32_t N, float eps, float momentum, float *mean, float *rstd,
+                 float *running_mean, float *running_var, int64_t *num_batches_tracked, void *workspace, void *stream);
+/* y = dropout_p(relu((z - mean) * rstd * gamma + beta)).  The keep mask is a function of (*seed_dev, seed_offset,
+ * element index) and is not stored; the backward call must get the same three values. */
+int ctr_bn_relu_dropout_fwd(const float *z, int64_t ldz, int32_t B, int32_t N, const float *mean, const float *rstd,
+                            const float *gamma, const float *beta, float p_drop, const uint64_t *seed_dev,
+                            uint64_t seed_offset, float *y, int64_t ldy, void *stream);
+/* given gy = dL/dy: gz = dL/dz (through dropout, ReLU and the batch statistics), dgamma[N], dbeta[N], and
+ * dbias[N] = column sums of gz (may be NULL). */
+int ctr_bn_relu_dropout_bwd(const float *gy, int64_t ldgy, const float *z, int64_t ldz, int32_t B, int32_t N,
+                            const float *mean, const float *rstd, const float *gamma, const float *beta, float p_drop,
+                            const uint64_t *seed_dev, uint64_t seed_offset, float *gz, int64_t ldgz, float *dgamma,
+                            float *dbeta, float *dbias, void *workspace, void *stream);
+
 /* ---- row-sharded tables: pack / unpack around the NCCL all-to-all ------------------------------
  * (the reference is replicas-only, torchctr/trainer.py:128-130).  owner(row) = row mod world; on the owner
  * all tables of the group live in one fused shard, row base[owner * num_features + table] + row / world. */

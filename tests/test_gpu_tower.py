@@ -1,0 +1,104 @@
+"""Fused tower block (BatchNorm1d training statistics + ReLU + Dropout, and their backward) against torch modules:
+the reference tower is [Linear, BatchNorm1d, ReLU, Dropout(0.5)] x k (torchctr/models/dnn.py:39-45)."""
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(got, ref, rtol=1e-5):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    err = float((got - ref).abs().max())
+    assert err <= rtol * max(float(ref.abs().max()), 1e-30), f"max abs err {err:.3e} vs scale {float(ref.abs().max()):.3e}"
+
+
+@pytest.mark.parametrize("B,N", [(257, 64), (4096, 128), (65536, 256), (1000, 48), (3, 8), (5000, 1024)])
+def test_bn_relu_forward_backward_match_torch(B, N):
+    from torchctr_b200 import ops
+    gen = torch.Generator().manual_seed(B + N)
+    z = (torch.randn(B, N, generator=gen) * 2 + torch.randn(N, generator=gen)).cuda()
+    gy = torch.randn(B, N, generator=gen).cuda()
+    bn = nn.BatchNorm1d(N).cuda().train()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(N, generator=gen) + 0.5)
+        bn.bias.copy_(torch.randn(N, generator=gen) * 0.3)
+    rm, rv, nbt = bn.running_mean.clone(), bn.running_var.clone(), bn.num_batches_tracked.clone()
+    zr = z.clone().requires_grad_(True)
+    y_ref = torch.relu(bn(zr))
+    y_ref.backward(gy)
+    mean, rstd = ops.bn_stats(z, bn.eps, bn.momentum, rm, rv, nbt)
+    y = ops.bn_relu_dropout_fwd(z, mean, rstd, bn.weight.data, bn.bias.data, 0.0, None, 0)
+    _close(y, y_ref)
+    _close(rm, bn.running_mean)
+    _close(rv, bn.running_var)
+    assert int(nbt) == int(bn.num_batches_tracked) == 1
+    gz, dgamma, dbeta, dbias = ops.bn_relu_dropout_bwd(gy, z, mean, rstd, bn.weight.data, bn.bias.data, 0.0, None, 0)
+    _close(gz, zr.grad, rtol=2e-5)
+    _close(dgamma, bn.weight.grad, rtol=2e-5)
+    _close(dbeta, bn.bias.grad, rtol=2e-5)
+    # column sums of gz vanish analytically (BatchNorm removes the mean): only rounding noise is left, as in torch
+    assert float(dbias.abs().max()) <= 1e-3 * max(float(gz.abs().sum(0).max()), 1e-30)
+
+
+def test_dropout_mask_is_bernoulli_consistent_and_reseeded():
+    from torchctr_b200 import ops
+    gen = torch.Generator().manual_seed(9)
+    B, N, p = 8192, 256, 0.5
+    z = torch.randn(B, N, generator=gen).cuda()
+    gy = torch.randn(B, N, generator=gen).cuda()
+    gamma, beta = torch.ones(N, device="cuda"), torch.full((N,), 3.0, device="cuda")     # + 3: almost every unit active
+    seed = torch.tensor([1234], dtype=torch.int64, device="cuda")
+    mean, rstd = ops.bn_stats(z, 1e-5, 0.1)
+    y0 = ops.bn_relu_dropout_fwd(z, mean, rstd, gamma, beta, 0.0, None, 0)
+    y = ops.bn_relu_dropout_fwd(z, mean, rstd, gamma, beta, p, seed, 7)
+    active = y0 > 0
+    kept = (y != 0) & active
+    frac = float(kept.sum()) / float(active.sum())
+    assert abs(frac - (1 - p)) < 0.005, frac
+    _close(y, torch.where(kept, y0 / (1 - p), torch.zeros_like(y0)))
+    # per-column keep rates are balanced too (the generator must not correlate with the layout)
+    col = kept.float().mean(0)
+    assert float(col.min()) > 0.45 and float(col.max()) < 0.55
+    # same seed / layer -> same mask; other layer or next step -> a different one
+    assert torch.equal(y, ops.bn_relu_dropout_fwd(z, mean, rstd, gamma, beta, p, seed, 7))
+    assert not torch.equal(y, ops.bn_relu_dropout_fwd(z, mean, rstd, gamma, beta, p, seed, 8))
+    seed2 = seed + 1
+    assert not torch.equal(y, ops.bn_relu_dropout_fwd(z, mean, rstd, gamma, beta, p, seed2, 7))
+    # backward sees the same mask: compare with torch autograd through an explicit mask
+    zr = z.clone().requires_grad_(True)
+    g_t, b_t = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    zh = (zr - zr.mean(0)) / torch.sqrt(zr.var(0, unbiased=False) + 1e-5)
+    y_ref = torch.relu(zh * g_t + b_t) * kept.float() / (1 - p)
+    y_ref.backward(gy)
+    gz, dgamma, dbeta, _ = ops.bn_relu_dropout_bwd(gy, z, mean, rstd, gamma, beta, p, seed, 7)
+    _close(gz, zr.grad, rtol=3e-5)
+    _close(dgamma, g_t.grad, rtol=3e-5)
+    _close(dbeta, b_t.grad, rtol=3e-5)
+
+
+def test_tower_block_autograd_matches_torch_modules():
+    """The fused node against nn.Linear + nn.BatchNorm1d + ReLU (Dropout p = 0), exact fp32 matmul mode."""
+    from torchctr_b200.nn.tower import tower_block
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gen = torch.Generator().manual_seed(3)
+    B, K, N = 3000, 148, 64
+    x = torch.randn(B, K, generator=gen).cuda()
+    lin, bn, drop = nn.Linear(K, N).cuda(), nn.BatchNorm1d(N).cuda().train(), nn.Dropout(0.0)
+    lin2, bn2 = nn.Linear(K, N).cuda(), nn.BatchNorm1d(N).cuda().train()
+    lin2.load_state_dict(lin.state_dict())
+    gy = torch.randn(B, N, generator=gen).cuda()
+    xr = x.clone().requires_grad_(True)
+    y_ref = torch.relu(bn2(lin2(xr)))
+    y_ref.backward(gy)
+    xf = x.clone().requires_grad_(True)
+    seed = torch.zeros(1, dtype=torch.int64, device="cuda")
+    y = tower_block(xf, lin, bn, drop, seed, 0)
+    y.backward(gy)
+    _close(y, y_ref, rtol=2e-5)
+    _close(xf.grad, xr.grad, rtol=5e-5)
+    _close(lin.weight.grad, lin2.weight.grad, rtol=5e-5)
+    _close(bn.weight.grad, bn2.weight.grad, rtol=5e-5)
+    _close(bn.bias.grad, bn2.bias.grad, rtol=5e-5)
+    _close(bn.running_var, bn2.running_var)

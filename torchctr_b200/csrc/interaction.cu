@@ -107,6 +107,89 @@ __global__ void __launch_bounds__(256) fm_bwd_kernel(const FmArgs a) {
     }
 }
 
+// ---- warp-per-sample variants (the main path) ----------------------------------------------------------------
+// A team of G lanes per sample reads 64-byte pieces of 8 different rows per warp instruction; HBM likes wider
+// requests.  Here a whole warp walks ONE sample: lane l loads the float4 columns l, l + 32, ... of the row (512
+// contiguous bytes per instruction), so column c belongs to field c / G and to the d-part c % G = l % G.  The
+// per-d sums over the fields are therefore a register accumulation over k followed by an xor-butterfly over the
+// lane bits above G.  Needs D % 4 == 0, G = D / 4 a power of two and F * G <= 32 * kFmK float4 columns.
+constexpr int kFmK = 8;
+
+__device__ __forceinline__ float4 fm_field_sums(float4 s, int G) {
+    for (int off = G; off < kWarp; off <<= 1) {
+        s.x += __shfl_xor_sync(kFull, s.x, off);
+        s.y += __shfl_xor_sync(kFull, s.y, off);
+        s.z += __shfl_xor_sync(kFull, s.z, off);
+        s.w += __shfl_xor_sync(kFull, s.w, off);
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(256) fm_fwd_row_kernel(const FmArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int cols = a.F * a.G;                       // float4 columns of the FM part of a row
+    const int64_t warps_total = (int64_t)gridDim.x * (256 / kWarp);
+    for (int64_t b = (int64_t)blockIdx.x * (256 / kWarp) + (threadIdx.x >> 5); b < a.B; b += warps_total) {
+        const float4 *row = reinterpret_cast<const float4 *>(a.x + b * a.x_stride);
+        float4 v[kFmK];
+#pragma unroll
+        for (int k = 0; k < kFmK; ++k) {
+            const int c = lane + 32 * k;
+            v[k] = c < cols ? __ldg(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < kFmK; ++k) {
+            s.x += v[k].x; s.y += v[k].y; s.z += v[k].z; s.w += v[k].w;
+            q = fmaf(v[k].x, v[k].x, q); q = fmaf(v[k].y, v[k].y, q); q = fmaf(v[k].z, v[k].z, q); q = fmaf(v[k].w, v[k].w, q);
+        }
+        s = fm_field_sums(s, a.G);
+        // every d-part once (lanes < G), minus all the squares; the first-order terms ride on the same reduction
+        float t = 0.5f * ((lane < a.G ? s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w : 0.f) - q);
+        if (a.first != nullptr)
+            for (int j = lane; j < a.nfirst; j += kWarp) t += __ldg(a.first + b * a.first_stride + j);
+        for (int off = 16; off; off >>= 1) t += __shfl_xor_sync(kFull, t, off);
+        if (lane == 0) {
+            float *o = a.out + b * a.out_stride;
+            *o = a.accumulate ? *o + t : t;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) fm_bwd_row_kernel(const FmArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int cols = a.F * a.G;
+    const int64_t warps_total = (int64_t)gridDim.x * (256 / kWarp);
+    for (int64_t b = (int64_t)blockIdx.x * (256 / kWarp) + (threadIdx.x >> 5); b < a.B; b += warps_total) {
+        const float go = __ldg(a.gout + b * a.gout_stride);
+        if (a.gfirst != nullptr)
+            for (int j = lane; j < a.nfirst; j += kWarp) a.gfirst[b * a.gfirst_stride + j] = go;
+        const float4 *row = reinterpret_cast<const float4 *>(a.x + b * a.x_stride);
+        float4 *grow = reinterpret_cast<float4 *>(a.gx + b * a.gx_stride);
+        float4 v[kFmK], o[kFmK];
+#pragma unroll
+        for (int k = 0; k < kFmK; ++k) {
+            const int c = lane + 32 * k;
+            v[k] = c < cols ? __ldg(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            o[k] = (a.accumulate && c < cols) ? grow[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < kFmK; ++k) { s.x += v[k].x; s.y += v[k].y; s.z += v[k].z; s.w += v[k].w; }
+        s = fm_field_sums(s, a.G);
+#pragma unroll
+        for (int k = 0; k < kFmK; ++k) {
+            const int c = lane + 32 * k;
+            if (c < cols)
+                grow[c] = make_float4(fmaf(go, s.x - v[k].x, o[k].x), fmaf(go, s.y - v[k].y, o[k].y),
+                                      fmaf(go, s.z - v[k].z, o[k].z), fmaf(go, s.w - v[k].w, o[k].w));
+        }
+    }
+}
+
+static bool fm_row_path(const FmArgs &a) { return a.vec == 4 && a.G * 4 == a.D && a.F * a.G <= kWarp * kFmK; }
+
 static int fm_lower(FmArgs &a) {
     CTR_REQUIRE(a.B >= 0 && a.F >= 1 && a.D >= 1, "bad FM shape B=%d F=%d D=%d", a.B, a.F, a.D);
     CTR_REQUIRE(a.x != nullptr || a.B == 0, "x is null");
@@ -170,6 +253,13 @@ extern "C" int ctr_fm_fwd(const float *x, int64_t x_stride, int32_t B, int32_t F
     if (B == 0) return CTR_OK;
     CTR_REQUIRE(out != nullptr, "out is null");
     CTR_REQUIRE(nfirst == 0 || first != nullptr, "first is null");
+    if (fm_row_path(a)) {
+        int64_t blocks = ((int64_t)B + 7) / 8;
+        if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+        note_launch(), fm_fwd_row_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+        CTR_CUDA_OK(cudaGetLastError());
+        return CTR_OK;
+    }
     const int teams_per_block = 256 / a.G;
     int64_t blocks = ((int64_t)B + teams_per_block - 1) / teams_per_block;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
@@ -190,6 +280,13 @@ extern "C" int ctr_fm_bwd(const float *x, int64_t x_stride, int32_t B, int32_t F
     if (B == 0) return CTR_OK;
     CTR_REQUIRE(gout != nullptr && gx != nullptr, "null gradient pointer");
     CTR_REQUIRE((int64_t)F * D <= gx_stride, "F*D exceeds the gradient row stride");
+    if (fm_row_path(a)) {
+        int64_t blocks = ((int64_t)B + 7) / 8;
+        if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+        note_launch(), fm_bwd_row_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+        CTR_CUDA_OK(cudaGetLastError());
+        return CTR_OK;
+    }
     const int teams_per_block = 256 / a.G;
     int64_t blocks = ((int64_t)B + teams_per_block - 1) / teams_per_block;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;

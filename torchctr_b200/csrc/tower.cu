@@ -1,0 +1,364 @@
+// K6b: the element-wise / column-reduction half of a tower block, fused.
+//
+// The reference tower (torchctr/models/dnn.py:35-46) is [Linear, BatchNorm1d, ReLU, Dropout(0.5)] x k + Linear.  In
+// training mode torch runs, per block, ~5 kernels forward (batch statistics, normalise, clamp, dropout mask,
+// scale) and ~6 backward (mask, threshold, two BatchNorm passes, bias-gradient reduction ...), each a full pass over
+// the [B, N] activation.  Here:
+//   forward   col_stats (one read of z = x W^T + b)  ->  finalize (mean, rstd, running statistics)
+//             -> bn_act_fwd: y = dropout(relu((z - mean) * rstd * gamma + beta))        (one read, one write)
+//   backward  bn_act_bwd_reduce: sum g, sum g * zhat per column, g = gy * dropout * relu'   (reads gy, z)
+//             -> finalize (dgamma, dbeta, the two means)
+//             -> bn_act_bwd_apply: gz = gamma * rstd * (g - mean(g) - zhat * mean(g zhat)), and the column sums of
+//                gz (the Linear's bias gradient) in the same pass
+// The dropout mask is never stored: both directions recompute it from a counter-based generator keyed by
+// (device-resident step seed, layer, element), so a captured CUDA graph draws a fresh mask every replay.
+// All of it is HBM-bound fp32 streaming work; the GEMMs on either side are in gemm_tc.cu.
+#include "common.cuh"
+
+namespace ctr {
+
+constexpr int kTowerThreads = 256;
+constexpr int kTowerMaxBlocks = kNumSMs * 4;
+
+// geometry shared by every kernel: a thread owns 4 consecutive columns (CG = N / 4 column groups) and every
+// RL-th row of the block's row range
+struct TowerGeom {
+    int B, N, CG, RL, blocks, rows_per_block;
+};
+
+static TowerGeom tower_geom(int B, int N) {
+    TowerGeom g{};
+    g.B = B;
+    g.N = N;
+    g.CG = N / 4;
+    g.RL = kTowerThreads / g.CG;
+    if (g.RL < 1) g.RL = 1;
+    int blocks = (B + g.RL * 8 - 1) / (g.RL * 8);   // at least 8 rows per row lane
+    if (blocks > kTowerMaxBlocks) blocks = kTowerMaxBlocks;
+    if (blocks < 1) blocks = 1;
+    g.rows_per_block = (B + blocks - 1) / blocks;
+    g.blocks = (B + g.rows_per_block - 1) / g.rows_per_block;
+    return g;
+}
+
+__device__ __forceinline__ float4 ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// keep-mask of 4 consecutive elements: one 64-bit hash, 16 bits per element
+__device__ __forceinline__ void drop_keep4(uint64_t seed, uint64_t elem4, uint32_t thresh16, bool keep[4]) {
+    const uint64_t h = mix64(seed ^ (elem4 * 0x9e3779b97f4a7c15ull + 0x632be59bd9b4e019ull));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) keep[j] = (uint32_t)((h >> (16 * j)) & 0xffffu) >= thresh16;
+}
+
+// block-level fixed-order reduction of NQ float4 accumulators over the RL row lanes; the block's partial goes to
+// partial[(block * NQ + q) * N + col]
+template <int NQ>
+__device__ __forceinline__ void reduce_rows_and_store(float4 (&acc)[NQ], const TowerGeom &g, int cg, int rl, float4 *red,
+                                                      float *__restrict__ partial) {
+    const bool active = rl < g.RL;      // threads past RL * CG only keep the barriers company
+    for (int q = 0; q < NQ; ++q) {
+        __syncthreads();
+        if (active) red[rl * g.CG + cg] = acc[q];
+        __syncthreads();
+        if (rl == 0) {
+            float4 s = red[cg];
+            for (int r = 1; r < g.RL; ++r) {
+                const float4 o = red[r * g.CG + cg];
+                s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+            }
+            reinterpret_cast<float4 *>(partial + ((size_t)blockIdx.x * NQ + q) * g.N)[cg] = s;
+        }
+    }
+}
+
+// ---- forward -----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTowerThreads)
+    col_stats_kernel(const float *__restrict__ z, int64_t ldz, const TowerGeom g, float *__restrict__ partial) {
+    __shared__ float4 red[kTowerThreads];
+    const int cg = threadIdx.x % g.CG, rl = threadIdx.x / g.CG;
+    float4 acc[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
+    if (rl < g.RL) {
+        const int r0 = blockIdx.x * g.rows_per_block;
+        const int r1 = min(r0 + g.rows_per_block, g.B);
+        for (int r = r0 + rl; r < r1; r += 4 * g.RL) {       // four rows in flight
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                v[j] = r + j * g.RL < r1 ? ld4(z + (size_t)(r + j * g.RL) * ldz + 4 * cg) : make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc[0].x += v[j].x; acc[0].y += v[j].y; acc[0].z += v[j].z; acc[0].w += v[j].w;
+                acc[1].x = fmaf(v[j].x, v[j].x, acc[1].x); acc[1].y = fmaf(v[j].y, v[j].y, acc[1].y);
+                acc[1].z = fmaf(v[j].z, v[j].z, acc[1].z); acc[1].w = fmaf(v[j].w, v[j].w, acc[1].w);
+            }
+        }
+    }
+    reduce_rows_and_store<2>(acc, g, cg, rl, red, partial);
+}
+
+// Finalize kernels: a block of kFinCols x kFinLanes threads owns kFinCols columns; lane j adds the partials of
+// blocks j, j + kFinLanes, ... in double, the lanes are then added in lane order (fixed order: deterministic).
+constexpr int kFinCols = 16, kFinLanes = 16;
+
+template <int NQ>
+__device__ __forceinline__ bool column_totals(const float *__restrict__ partial, int blocks, int N, double (&tot)[NQ], int *col) {
+    __shared__ double sh[NQ][kFinLanes][kFinCols];
+    const int c = threadIdx.x % kFinCols, j = threadIdx.x / kFinCols;
+    const int n = blockIdx.x * kFinCols + c;
+    double acc[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
+    if (n < N) {
+#pragma unroll 4
+        for (int b = j; b < blocks; b += kFinLanes) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) acc[q] += (double)partial[((size_t)b * NQ + q) * N + n];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) sh[q][j][c] = acc[q];
+    __syncthreads();
+    *col = n;
+    if (j != 0 || n >= N) return false;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        double t = 0.0;
+        for (int l = 0; l < kFinLanes; ++l) t += sh[q][l][c];
+        tot[q] = t;
+    }
+    return true;
+}
+
+// partials -> mean, rstd (+ running statistics, torch.nn.BatchNorm1d semantics)
+__global__ void __launch_bounds__(kFinCols * kFinLanes)
+    bn_finalize_fwd_kernel(const float *__restrict__ partial, int blocks, int B, int N, float eps, float momentum,
+                           float *__restrict__ mean, float *__restrict__ rstd, float *running_mean, float *running_var,
+                           long long *num_batches_tracked) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+    double tot[2];
+    int n;
+    if (!column_totals<2>(partial, blocks, N, tot, &n)) return;
+    const double s = tot[0], ss = tot[1];
+    const double m = s / B;
+    double var = ss / B - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[n] = (float)m;
+    rstd[n] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean != nullptr) {
+        const double unbiased = B > 1 ? var * ((double)B / (double)(B - 1)) : var;
+        running_mean[n] = (float)((1.0 - momentum) * running_mean[n] + momentum * m);
+        running_var[n] = (float)((1.0 - momentum) * running_var[n] + momentum * unbiased);
+    }
+}
+
+struct ActArgs {
+    const float *mean, *rstd, *gamma, *beta;
+    const unsigned long long *seed_dev;   // step seed on the device (may be null: seed 0)
+    unsigned long long seed_offset;       // layer id
+    float p_drop;
+};
+
+__global__ void __launch_bounds__(kTowerThreads)
+    bn_act_fwd_kernel(const float *__restrict__ z, int64_t ldz, const TowerGeom g, const ActArgs a, float *__restrict__ y,
+                      int64_t ldy) {
+    const int cg = threadIdx.x % g.CG, rl = threadIdx.x / g.CG;
+    if (rl >= g.RL) return;
+    const float4 mu = ld4(a.mean + 4 * cg), rs = ld4(a.rstd + 4 * cg), ga = ld4(a.gamma + 4 * cg), be = ld4(a.beta + 4 * cg);
+    const float4 sc = make_float4(rs.x * ga.x, rs.y * ga.y, rs.z * ga.z, rs.w * ga.w);
+    const bool drop = a.p_drop > 0.f;
+    const float keep_scale = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+    const uint32_t thresh = (uint32_t)(a.p_drop * 65536.f);
+    const uint64_t seed = (a.seed_dev != nullptr ? *a.seed_dev : 0ull) * 0x100000001b3ull + a.seed_offset;
+    const int r0 = blockIdx.x * g.rows_per_block;
+    const int r1 = min(r0 + g.rows_per_block, g.B);
+#pragma unroll 4
+    for (int r = r0 + rl; r < r1; r += g.RL) {
+        const float4 v = ld4(z + (size_t)r * ldz + 4 * cg);
+        float o[4] = {fmaf(v.x - mu.x, sc.x, be.x), fmaf(v.y - mu.y, sc.y, be.y), fmaf(v.z - mu.z, sc.z, be.z),
+                      fmaf(v.w - mu.w, sc.w, be.w)};
+        bool keep[4] = {true, true, true, true};
+        if (drop) drop_keep4(seed, (uint64_t)r * g.CG + cg, thresh, keep);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = (o[j] > 0.f && keep[j]) ? o[j] * keep_scale : 0.f;
+        *reinterpret_cast<float4 *>(y + (size_t)r * ldy + 4 * cg) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ---- backward ----------------------------------------------------------------------------------------------
+// g = gy * keep_scale where the unit was kept and active, else 0; zhat = (z - mean) * rstd
+__device__ __forceinline__ void act_grad4(const float4 gy, const float4 v, const float4 mu, const float4 rs, const float4 ga,
+                                          const float4 be, bool drop, float keep_scale, uint64_t seed, uint64_t elem4,
+                                          uint32_t thresh, float (&gq)[4], float (&zh)[4]) {
+    zh[0] = (v.x - mu.x) * rs.x; zh[1] = (v.y - mu.y) * rs.y; zh[2] = (v.z - mu.z) * rs.z; zh[3] = (v.w - mu.w) * rs.w;
+    const float pre[4] = {fmaf(v.x - mu.x, rs.x * ga.x, be.x), fmaf(v.y - mu.y, rs.y * ga.y, be.y),
+                          fmaf(v.z - mu.z, rs.z * ga.z, be.z), fmaf(v.w - mu.w, rs.w * ga.w, be.w)};
+    bool keep[4] = {true, true, true, true};
+    if (drop) drop_keep4(seed, elem4, thresh, keep);
+    const float gin[4] = {gy.x, gy.y, gy.z, gy.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gq[j] = (pre[j] > 0.f && keep[j]) ? gin[j] * keep_scale : 0.f;
+}
+
+__global__ void __launch_bounds__(kTowerThreads)
+    bn_act_bwd_reduce_kernel(const float *__restrict__ gy, int64_t ldgy, const float *__restrict__ z, int64_t ldz,
+                             const TowerGeom g, const ActArgs a, float *__restrict__ partial) {
+    __shared__ float4 red[kTowerThreads];
+    const int cg = threadIdx.x % g.CG, rl = threadIdx.x / g.CG;
+    float4 acc[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
+    if (rl < g.RL) {
+        const float4 mu = ld4(a.mean + 4 * cg), rs = ld4(a.rstd + 4 * cg), ga = ld4(a.gamma + 4 * cg), be = ld4(a.beta + 4 * cg);
+        const bool drop = a.p_drop > 0.f;
+        const float keep_scale = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+        const uint32_t thresh = (uint32_t)(a.p_drop * 65536.f);
+        const uint64_t seed = (a.seed_dev != nullptr ? *a.seed_dev : 0ull) * 0x100000001b3ull + a.seed_offset;
+        const int r0 = blockIdx.x * g.rows_per_block;
+        const int r1 = min(r0 + g.rows_per_block, g.B);
+#pragma unroll 2
+        for (int r = r0 + rl; r < r1; r += g.RL) {
+            float gq[4], zh[4];
+            act_grad4(ld4(gy + (size_t)r * ldgy + 4 * cg), ld4(z + (size_t)r * ldz + 4 * cg), mu, rs, ga, be, drop, keep_scale,
+                      seed, (uint64_t)r * g.CG + cg, thresh, gq, zh);
+            acc[0].x += gq[0]; acc[0].y += gq[1]; acc[0].z += gq[2]; acc[0].w += gq[3];
+            acc[1].x = fmaf(gq[0], zh[0], acc[1].x); acc[1].y = fmaf(gq[1], zh[1], acc[1].y);
+            acc[1].z = fmaf(gq[2], zh[2], acc[1].z); acc[1].w = fmaf(gq[3], zh[3], acc[1].w);
+        }
+    }
+    reduce_rows_and_store<2>(acc, g, cg, rl, red, partial);
+}
+
+// dbeta = sum g, dgamma = sum g zhat; c1 = mean(g), c2 = mean(g zhat) for the apply pass
+__global__ void __launch_bounds__(kFinCols * kFinLanes)
+    bn_finalize_bwd_kernel(const float *__restrict__ partial, int blocks, int B, int N, float *__restrict__ dgamma,
+                           float *__restrict__ dbeta, float *__restrict__ c1, float *__restrict__ c2) {
+    double tot[2];
+    int n;
+    if (!column_totals<2>(partial, blocks, N, tot, &n)) return;
+    const double s = tot[0], sz = tot[1];
+    dbeta[n] = (float)s;
+    dgamma[n] = (float)sz;
+    c1[n] = (float)(s / B);
+    c2[n] = (float)(sz / B);
+}
+
+__global__ void __launch_bounds__(kTowerThreads)
+    bn_act_bwd_apply_kernel(const float *__restrict__ gy, int64_t ldgy, const float *__restrict__ z, int64_t ldz,
+                            const TowerGeom g, const ActArgs a, const float *__restrict__ c1, const float *__restrict__ c2,
+                            float *__restrict__ gz, int64_t ldgz, float *__restrict__ partial) {
+    __shared__ float4 red[kTowerThreads];
+    const int cg = threadIdx.x % g.CG, rl = threadIdx.x / g.CG;
+    float4 acc[1] = {make_float4(0, 0, 0, 0)};
+    if (rl < g.RL) {
+        const float4 mu = ld4(a.mean + 4 * cg), rs = ld4(a.rstd + 4 * cg), ga = ld4(a.gamma + 4 * cg), be = ld4(a.beta + 4 * cg);
+        const float4 m1 = ld4(c1 + 4 * cg), m2 = ld4(c2 + 4 * cg);
+        const float k[4] = {ga.x * rs.x, ga.y * rs.y, ga.z * rs.z, ga.w * rs.w};
+        const float mm1[4] = {m1.x, m1.y, m1.z, m1.w}, mm2[4] = {m2.x, m2.y, m2.z, m2.w};
+        const bool drop = a.p_drop > 0.f;
+        const float keep_scale = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+        const uint32_t thresh = (uint32_t)(a.p_drop * 65536.f);
+        const uint64_t seed = (a.seed_dev != nullptr ? *a.seed_dev : 0ull) * 0x100000001b3ull + a.seed_offset;
+        const int r0 = blockIdx.x * g.rows_per_block;
+        const int r1 = min(r0 + g.rows_per_block, g.B);
+#pragma unroll 2
+        for (int r = r0 + rl; r < r1; r += g.RL) {
+            float gq[4], zh[4], o[4];
+            act_grad4(ld4(gy + (size_t)r * ldgy + 4 * cg), ld4(z + (size_t)r * ldz + 4 * cg), mu, rs, ga, be, drop, keep_scale,
+                      seed, (uint64_t)r * g.CG + cg, thresh, gq, zh);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = k[j] * (gq[j] - mm1[j] - zh[j] * mm2[j]);
+            *reinterpret_cast<float4 *>(gz + (size_t)r * ldgz + 4 * cg) = make_float4(o[0], o[1], o[2], o[3]);
+            acc[0].x += o[0]; acc[0].y += o[1]; acc[0].z += o[2]; acc[0].w += o[3];
+        }
+    }
+    reduce_rows_and_store<1>(acc, g, cg, rl, red, partial);
+}
+
+// column sums from one-quantity partials (bias gradient of the Linear in front of the BatchNorm)
+__global__ void __launch_bounds__(kFinCols * kFinLanes)
+    col_sum_finalize_kernel(const float *__restrict__ partial, int blocks, int N, float *__restrict__ out) {
+    double tot[1];
+    int n;
+    if (!column_totals<1>(partial, blocks, N, tot, &n)) return;
+    out[n] = (float)tot[0];
+}
+
+static int check_tower_shape(int B, int N, int64_t ld) {
+    CTR_REQUIRE(B >= 1 && N >= 4 && N % 4 == 0 && N <= 1024, "tower block: B=%d, N=%d unsupported (N: multiple of 4 up to 1024)", B, N);
+    CTR_REQUIRE(ld >= N && ld % 4 == 0, "row pitch %lld must be a multiple of 4 and >= N", (long long)ld);
+    return CTR_OK;
+}
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace ctr
+
+using namespace ctr;
+
+extern "C" int64_t ctr_tower_workspace_bytes(int32_t N) {
+    // partials: up to kTowerMaxBlocks x 2 quantities x N floats, + 2 N floats (c1, c2)
+    return ((int64_t)kTowerMaxBlocks * 2 * N + 2 * N) * (int64_t)sizeof(float) + 256;
+}
+
+extern "C" int ctr_bn_stats(const float *z, int64_t ldz, int32_t B, int32_t N, float eps, float momentum, float *mean,
+                            float *rstd, float *running_mean, float *running_var, int64_t *num_batches_tracked, void *workspace,
+                            void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_tower_shape(B, N, ldz);
+    if (rc != CTR_OK) return rc;
+    CTR_REQUIRE(z != nullptr && mean != nullptr && rstd != nullptr && workspace != nullptr, "null pointer");
+    CTR_REQUIRE(aligned16(z) && aligned16(workspace), "z / workspace must be 16-byte aligned");
+    CTR_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "running_mean and running_var go together");
+    const TowerGeom g = tower_geom(B, N);
+    float *partial = static_cast<float *>(workspace);
+    note_launch(), col_stats_kernel<<<g.blocks, kTowerThreads, 0, stream>>>(z, ldz, g, partial);
+    note_launch(), bn_finalize_fwd_kernel<<<(N + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, stream>>>(partial, g.blocks, B, N, eps, momentum, mean, rstd,
+                                                                              running_mean, running_var,
+                                                                              reinterpret_cast<long long *>(num_batches_tracked));
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int ctr_bn_relu_dropout_fwd(const float *z, int64_t ldz, int32_t B, int32_t N, const float *mean, const float *rstd,
+                                       const float *gamma, const float *beta, float p_drop, const uint64_t *seed_dev,
+                                       uint64_t seed_offset, float *y, int64_t ldy, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_tower_shape(B, N, ldz);
+    if (rc != CTR_OK) return rc;
+    rc = check_tower_shape(B, N, ldy);
+    if (rc != CTR_OK) return rc;
+    CTR_REQUIRE(z && mean && rstd && gamma && beta && y, "null pointer");
+    CTR_REQUIRE(aligned16(z) && aligned16(y) && aligned16(mean) && aligned16(rstd) && aligned16(gamma) && aligned16(beta),
+                "operands must be 16-byte aligned");
+    CTR_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "p_drop=%f outside [0, 1)", p_drop);
+    const TowerGeom g = tower_geom(B, N);
+    ActArgs a{mean, rstd, gamma, beta, reinterpret_cast<const unsigned long long *>(seed_dev), seed_offset, p_drop};
+    note_launch(), bn_act_fwd_kernel<<<g.blocks, kTowerThreads, 0, stream>>>(z, ldz, g, a, y, ldy);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int ctr_bn_relu_dropout_bwd(const float *gy, int64_t ldgy, const float *z, int64_t ldz, int32_t B, int32_t N,
+                                       const float *mean, const float *rstd, const float *gamma, const float *beta, float p_drop,
+                                       const uint64_t *seed_dev, uint64_t seed_offset, float *gz, int64_t ldgz, float *dgamma,
+                                       float *dbeta, float *dbias, void *workspace, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_tower_shape(B, N, ldz);
+    if (rc == CTR_OK) rc = check_tower_shape(B, N, ldgy);
+    if (rc == CTR_OK) rc = check_tower_shape(B, N, ldgz);
+    if (rc != CTR_OK) return rc;
+    CTR_REQUIRE(gy && z && mean && rstd && gamma && beta && gz && dgamma && dbeta && workspace, "null pointer");
+    CTR_REQUIRE(aligned16(gy) && aligned16(z) && aligned16(gz) && aligned16(mean) && aligned16(rstd) && aligned16(gamma) &&
+                    aligned16(beta) && aligned16(workspace),
+                "operands must be 16-byte aligned");
+    CTR_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "p_drop=%f outside [0, 1)", p_drop);
+    const TowerGeom g = tower_geom(B, N);
+    ActArgs a{mean, rstd, gamma, beta, reinterpret_cast<const unsigned long long *>(seed_dev), seed_offset, p_drop};
+    float *partial = static_cast<float *>(workspace);
+    float *c1 = partial + (size_t)kTowerMaxBlocks * 2 * N;
+    float *c2 = c1 + N;
+    note_launch(), bn_act_bwd_reduce_kernel<<<g.blocks, kTowerThreads, 0, stream>>>(gy, ldgy, z, ldz, g, a, partial);
+    note_launch(), bn_finalize_bwd_kernel<<<(N + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, stream>>>(partial, g.blocks, B, N, dgamma, dbeta, c1, c2);
+    note_launch(), bn_act_bwd_apply_kernel<<<g.blocks, kTowerThreads, 0, stream>>>(gy, ldgy, z, ldz, g, a, c1, c2, gz, ldgz, partial);
+    if (dbias != nullptr)
+        note_launch(), col_sum_finalize_kernel<<<(N + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, stream>>>(partial, g.blocks, N, dbias);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}

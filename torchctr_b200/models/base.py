@@ -11,6 +11,7 @@ import torch.nn.functional as F
 
 from ..nn.embedding import EmbeddingTable, PlanLink, PooledLookupGroup
 from ..nn.linear import linear_tc
+from ..nn.tower import block_is_fusable, tower_block
 from ..nn.vocab import VocabIndex
 
 
@@ -137,10 +138,35 @@ class CTRModelBase(nn.Module):
         return F.linear(x, weight, bias)
 
     def _run_tower(self, x: torch.Tensor) -> torch.Tensor:
-        h = self._first_linear(x, self.tower[0])
-        for layer in list(self.tower)[1:]:
+        layers = list(self.tower)
+        if self.training and x.is_cuda and x.dtype == torch.float32:
+            # training mode: every [Linear, BatchNorm1d, ReLU, Dropout] block is one fused autograd node
+            seed = self._step_seed(x.device)
+            h, i, block = x, 0, 0
+            while i + 3 < len(layers) and block_is_fusable(*layers[i:i + 4]):
+                lin = layers[i]
+                pad = h.shape[1] - lin.in_features
+                w = F.pad(lin.weight, (0, pad)) if pad else None      # first layer: 4-float-padded lookup output
+                h = tower_block(h, lin, layers[i + 1], layers[i + 3], seed, block, weight=w)
+                i += 4
+                block += 1
+            if i > 0:
+                for layer in layers[i:]:
+                    h = self._linear(h, layer.weight, layer.bias) if isinstance(layer, nn.Linear) else layer(h)
+                return h
+        h = self._first_linear(x, layers[0])
+        for layer in layers[1:]:
             h = self._linear(h, layer.weight, layer.bias) if isinstance(layer, nn.Linear) else layer(h)
         return h
+
+    def _step_seed(self, device):
+        """Device-resident dropout seed, advanced once per training forward (inside a captured CUDA graph too)."""
+        seed = getattr(self, "_drop_seed", None)
+        if seed is None or seed.device != device:
+            seed = torch.full((1,), torch.initial_seed() & 0x7fffffffffff, dtype=torch.int64, device=device)
+            self._drop_seed = seed
+        seed += 1
+        return seed
 
     def _grow_vocabularies(self, feats):
         if not self.training or self._sharded is not None:

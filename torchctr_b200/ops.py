@@ -426,3 +426,65 @@ def emb_bwd_apply_p2p(call: GroupCall, shard: _lib.Shard, workspace: torch.Tenso
     with _timed("emb_bwd_apply"):
         _lib.check(_lib.lib().ctr_emb_bwd_apply_p2p(C.byref(call.struct), C.byref(shard), workspace.data_ptr(), C.byref(opt),
                                                     grads, _lib.ptr(num_unique), _stream()), "ctr_emb_bwd_apply_p2p")
+
+
+# ---- tower block (BatchNorm1d + ReLU + Dropout around a Linear) ------------------------------------------------------
+_tower_ws: dict = {}
+
+
+def tower_workspace(device, N: int) -> torch.Tensor:
+    key = (device, N)
+    ws = _tower_ws.get(key)
+    if ws is None:
+        ws = torch.empty(_lib.check(_lib.lib().ctr_tower_workspace_bytes(N)), dtype=torch.uint8, device=device)
+        _tower_ws[key] = ws
+    return ws
+
+
+def _rows2d(t, name):
+    _lib.require_cuda(t, name)
+    if t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name} must be f32 [B, N] with unit inner stride")
+
+
+def bn_stats(z, eps: float, momentum: float, running_mean=None, running_var=None, num_batches_tracked=None):
+    """Batch statistics of z [B, N] -> (mean [N], rstd [N]); updates the running statistics in place."""
+    _rows2d(z, "z")
+    B, N = z.shape
+    mean = torch.empty(N, dtype=torch.float32, device=z.device)
+    rstd = torch.empty(N, dtype=torch.float32, device=z.device)
+    with _timed("bn_stats"):
+        _lib.check(_lib.lib().ctr_bn_stats(z.data_ptr(), z.stride(0), B, N, eps, momentum, mean.data_ptr(), rstd.data_ptr(),
+                                           _lib.ptr(running_mean), _lib.ptr(running_var), _lib.ptr(num_batches_tracked),
+                                           tower_workspace(z.device, N).data_ptr(), _stream(z)), "ctr_bn_stats")
+    return mean, rstd
+
+
+def bn_relu_dropout_fwd(z, mean, rstd, gamma, beta, p_drop: float, seed_dev, seed_offset: int):
+    _rows2d(z, "z")
+    B, N = z.shape
+    y = torch.empty(B, N, dtype=torch.float32, device=z.device)
+    with _timed("bn_act_fwd"):
+        _lib.check(_lib.lib().ctr_bn_relu_dropout_fwd(z.data_ptr(), z.stride(0), B, N, mean.data_ptr(), rstd.data_ptr(),
+                                                      gamma.data_ptr(), beta.data_ptr(), p_drop, _lib.ptr(seed_dev), seed_offset,
+                                                      y.data_ptr(), y.stride(0), _stream(z)), "ctr_bn_relu_dropout_fwd")
+    return y
+
+
+def bn_relu_dropout_bwd(gy, z, mean, rstd, gamma, beta, p_drop: float, seed_dev, seed_offset: int, want_dbias: bool = True):
+    """-> (gz [B, N], dgamma [N], dbeta [N], dbias [N] or None)"""
+    _rows2d(gy, "gy")
+    _rows2d(z, "z")
+    B, N = z.shape
+    dev = z.device
+    gz = torch.empty(B, N, dtype=torch.float32, device=dev)
+    dgamma = torch.empty(N, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(N, dtype=torch.float32, device=dev)
+    dbias = torch.empty(N, dtype=torch.float32, device=dev) if want_dbias else None
+    with _timed("bn_act_bwd"):
+        _lib.check(_lib.lib().ctr_bn_relu_dropout_bwd(gy.data_ptr(), gy.stride(0), z.data_ptr(), z.stride(0), B, N, mean.data_ptr(),
+                                                      rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), p_drop,
+                                                      _lib.ptr(seed_dev), seed_offset, gz.data_ptr(), gz.stride(0),
+                                                      dgamma.data_ptr(), dbeta.data_ptr(), _lib.ptr(dbias),
+                                                      tower_workspace(dev, N).data_ptr(), _stream(z)), "ctr_bn_relu_dropout_bwd")
+    return gz, dgamma, dbeta, dbias
