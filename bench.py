@@ -302,7 +302,7 @@ def run_ours(args):
     for i in range(max(args.warmup, 3)):                 # eager warm-up (also sizes workspaces / optimizer state)
         eager_step(resident[i % nb], i)
     launches_per_step = None
-    in_step = kernels_in_step(eager_step, resident) if world == 1 else {}
+    in_step = kernels_in_step(eager_step, resident)      # at N > 1: this rank's kernels, peers' rows over NVLink included
     if args.roofline_only:                               # profiling hook: just the embedding entry points
         kern, roofline = kernel_roofline(model, resident, B, dev, iters=args.steps)
         print(json.dumps({"kernels": kern, "roofline": roofline, "kernels_in_step": in_step}), flush=True)

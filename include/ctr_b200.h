@@ -215,6 +215,13 @@ int ctr_cross_combine_bwd(const float *x0, const float *u, const float *bias, co
 int ctr_linear_fwd(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias, float *C,
                    int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t act, void *stream);
 
+/* Weight gradient of the same layers: dW[N, K] = sum_b G[b, N] . X[b, K] (G = dL/dz, X = the layer input), TF32 in,
+ * fp32 accumulate, the batch split over the SMs and the slices added in order.  ldg, ldx multiples of 4 floats,
+ * G, X, workspace 16-byte aligned; workspace: ctr_linear_wgrad_workspace_bytes(B, N, K). */
+int64_t ctr_linear_wgrad_workspace_bytes(int32_t B, int32_t N, int32_t K);
+int ctr_linear_wgrad(const float *G, int64_t ldg, const float *X, int64_t ldx, int32_t B, int32_t N, int32_t K, float *dW,
+                     int64_t lddw, void *workspace, int64_t workspace_bytes, void *stream);
+
 /* ---- tower block: BatchNorm1d (training) + ReLU + Dropout around a Linear, fused --------------------------
  * Replaces the BatchNorm1d / ReLU / Dropout modules of torchctr/models/dnn.py:39-45 in training mode and the
  * bias-gradient reduction of the Linear in front of them.  z = x W^T + b is f32 [B, N] (N multiple of 4, <= 1024),

@@ -54,3 +54,24 @@ def test_linear_tc_autograd_matches_torch():
     yr.backward(gy)
     for g, r in zip(got, (yr.detach(), x.grad, w.grad, b.grad)):
         assert rel_err(g, r) < 2e-3
+
+
+@pytest.mark.parametrize("B,N,K", [(65536, 256, 432), (65536, 128, 256), (65536, 64, 128), (1000, 64, 128), (70, 48, 20),
+                                   (4097, 300, 520), (31, 8, 4)])
+def test_wgrad_matches_fp32_matmul(B, N, K):
+    """dW = gz^T x on tcgen05 with MN-major operands and a batch split: TF32 inputs (10-bit mantissa) against fp32."""
+    from torchctr_b200 import ops
+    gen = torch.Generator().manual_seed(B + N + K)
+    gz = torch.randn(B, N, generator=gen).cuda()
+    x = torch.randn(B, K, generator=gen).cuda()
+    got = ops.linear_wgrad(gz, x)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = gz.double().t() @ x.double()
+    # TF32 operands (10-bit mantissa): same bound as the forward GEMM tests, 2e-3 of max|ref|
+    assert got.shape == (N, K)
+    assert rel_err(got.double(), ref) < 2e-3
+    # strided views: rows padded to a multiple of 4 floats, as the lookup output is
+    xp = torch.zeros(B, (K + 7) // 4 * 4 + 4, device="cuda")
+    xp[:, :K] = x
+    got2 = ops.linear_wgrad(gz, xp[:, :K])
+    assert torch.equal(got, got2)

@@ -101,6 +101,8 @@ _SIGNATURES = {
     "ctr_route_workspace_bytes": (C.c_int64, [C.POINTER(Group), C.c_int32]),
     "ctr_route_build": (C.c_int, [C.POINTER(Group), C.c_int32, _P, _P, _P, _P, _P, C.c_int64, _P]),
     "ctr_route_grad_gather": (C.c_int, [C.POINTER(Group), C.c_int32, _P, C.c_int64, C.c_int32, _P, _P]),
+    "ctr_linear_wgrad_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "ctr_linear_wgrad": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P, C.c_int64, _P]),
     "ctr_tower_workspace_bytes": (C.c_int64, [C.c_int32]),
     "ctr_bn_stats": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P]),
     "ctr_bn_relu_dropout_fwd": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_float, _P, C.c_uint64,

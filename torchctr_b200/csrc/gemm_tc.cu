@@ -209,7 +209,8 @@ static EncodeTiledFn encode_fn() {
 }
 
 // rows x cols fp32, row pitch ld floats; box = 32 floats x box_rows, 128-byte swizzle, OOB reads give zeros
-static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -220,7 +221,7 @@ static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int64_t co
     cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld ld=%lld)", (int)r, (long long)rows,
@@ -228,6 +229,171 @@ static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int64_t co
         return CTR_E_CUDA;
     }
     return CTR_OK;
+}
+
+
+// ---- weight gradient: dW[N, K] = sum_b G[b, N] X[b, K] -------------------------------------------------------
+// The reduction runs over the batch, so both operands are MN-major for the tensor core (the row index b is the MMA's
+// K): TMA drops [32 batch rows x 32 floats] boxes (128-byte swizzle with 32-byte atoms -- the only shared-memory
+// layout tcgen05 accepts for MN-major 32-bit operands) and the descriptors say "MN-major, SWIZZLE_128B_BASE32B":
+// 32-float groups along M / N are kWgBoxBytes apart (leading byte offset), 4-row groups along the batch 512 bytes.  The output is tiny (N x K) and the batch huge, so the batch is split over the
+// CTAs (one output tile x one batch slice each, ~one CTA per SM); every CTA leaves its partial tile in a workspace
+// and a second kernel adds the slices in order (deterministic).  cuBLAS needs 130 us for the 256 x 432 x 65536 case,
+// HBM time is 28 us.
+constexpr int kWgBM = 128;             // rows of dW per tile (columns of G)
+constexpr int kWgBNMax = 256;          // columns of dW per tile (columns of X): one TMEM accumulator of 256 columns
+constexpr int kWgRows = 32;            // batch rows per stage
+constexpr int kWgStages = 4;
+constexpr int kWgBoxBytes = kWgRows * 128;                      // one [32 rows x 32 floats] box
+constexpr int kWgABytes = (kWgBM / 32) * kWgBoxBytes;           // 16 KB
+constexpr int kWgBBytes = (kWgBNMax / 32) * kWgBoxBytes;        // 32 KB
+constexpr int kWgSmem = kWgStages * (kWgABytes + kWgBBytes) + 1024 + 256;
+
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);        // start address, 16-byte units
+    d |= (uint64_t)(kWgBoxBytes >> 4) << 16;            // leading byte offset: next 32-float group along M / N
+    d |= (uint64_t)(512 >> 4) << 32;                    // stride byte offset: next 4 rows of the batch
+    d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+    d |= (uint64_t)1 << 61;                             // SWIZZLE_128B_BASE32B: the one layout 32-bit MN-major operands may use
+    return d;
+}
+// D = F32, A = B = TF32, both MN-major (bits 15, 16)
+__device__ __forceinline__ uint32_t umma_idesc_tf32_mn(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct WgradArgs {
+    float *partial;      // [splits, N, K]
+    int B, N, K;
+    int tiles_n;         // tiles along K (columns of dW)
+    int rows_per_split;  // multiple of kWgRows
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x, const WgradArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_smem = base, b_smem = base + kWgStages * kWgABytes;
+    const uint32_t bars = b_smem + kWgStages * kWgBBytes;
+    const uint32_t full0 = bars, empty0 = bars + 8 * kWgStages, accum_full = bars + 16 * kWgStages;
+    const uint32_t tmem_slot = accum_full + 8;
+    uint8_t *gen_base = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(gen_base + (tmem_slot - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_m = blockIdx.x / g.tiles_n, tile_n = blockIdx.x % g.tiles_n;
+    const int n0 = tile_m * kWgBM;                         // first row of dW (column of G)
+    const int k0 = tile_n * kWgBNMax;                      // first column of dW (column of X)
+    int n_mma = g.K - k0;
+    n_mma = n_mma > kWgBNMax ? kWgBNMax : (n_mma + 15) / 16 * 16;
+    const int b_boxes = (n_mma + 31) / 32;
+    const int split = blockIdx.y;
+    const int row0 = split * g.rows_per_split;
+    int rows = g.B - row0;
+    rows = rows > g.rows_per_split ? g.rows_per_split : rows;
+    const int num_st = rows > 0 ? (rows + kWgRows - 1) / kWgRows : 0;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kWgStages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(accum_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kWgBNMax));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- TMA producer: 4 boxes of G and b_boxes boxes of X per stage
+            for (int st = 0; st < num_st; ++st) {
+                const int s = st % kWgStages;
+                if (st >= kWgStages) mbar_wait(empty0 + 8 * s, ((st / kWgStages) - 1) & 1);
+                mbar_expect_tx(full0 + 8 * s, (kWgBM / 32 + b_boxes) * kWgBoxBytes);
+                const int r = row0 + st * kWgRows;
+                for (int j = 0; j < kWgBM / 32; ++j)
+                    tma_load_2d(a_smem + s * kWgABytes + j * kWgBoxBytes, &map_g, full0 + 8 * s, n0 + 32 * j, r);
+                for (int j = 0; j < b_boxes; ++j)
+                    tma_load_2d(b_smem + s * kWgBBytes + j * kWgBoxBytes, &map_x, full0 + 8 * s, k0 + 32 * j, r);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---- MMA issuer: 4 instructions of 8 batch rows per stage
+            const uint32_t idesc = umma_idesc_tf32_mn(kWgBM, n_mma);
+            for (int st = 0; st < num_st; ++st) {
+                const int s = st % kWgStages;
+                mbar_wait(full0 + 8 * s, (st / kWgStages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t da = umma_desc_mn(a_smem + s * kWgABytes), db = umma_desc_mn(b_smem + s * kWgBBytes);
+#pragma unroll
+                for (int k = 0; k < kWgRows / kUmmaK; ++k)   // next 8 batch rows: 1024 bytes further inside every box
+                    umma_tf32(tmem_acc, da + (uint64_t)(k * 1024 >> 4), db + (uint64_t)(k * 1024 >> 4), idesc, (st | k) ? 1u : 0u);
+                umma_commit(empty0 + 8 * s);
+            }
+            umma_commit(accum_full);
+        }
+    } else {  // ---- epilogue warps 2..5: this split's partial tile -> workspace
+        const int q = warp & 3;
+        const int row = n0 + q * 32 + lane;
+        float *dst_row = g.partial + ((size_t)split * g.N + row) * g.K + k0;
+        if (num_st > 0) {
+            mbar_wait(accum_full, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+#pragma unroll 1
+        for (int c = 0; c < n_mma; c += 16) {
+            float v[16];
+            if (num_st > 0) {
+                tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+            if (row < g.N) {
+                if (k0 + c + 16 <= g.K && (g.K % 4 == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4 *>(dst_row + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+                    for (int j = 0; j < 16 && k0 + c + j < g.K; ++j) dst_row[c + j] = v[j];
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(kWgBNMax));
+    }
+}
+
+// dW[n, k] = sum over the batch slices, in slice order
+__global__ void __launch_bounds__(256)
+    wgrad_reduce_kernel(const float *__restrict__ partial, int splits, int64_t elems, int K, float *__restrict__ dW, int64_t lddw) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int p = 0; p < splits; ++p) s += partial[(size_t)p * elems + i];
+        dW[(i / K) * lddw + (i % K)] = s;
+    }
+}
+
+static void wgrad_plan(int B, int N, int K, int *tiles_m, int *tiles_n, int *splits, int *rows_per_split) {
+    *tiles_m = (N + kWgBM - 1) / kWgBM;
+    *tiles_n = (K + kWgBNMax - 1) / kWgBNMax;
+    const int tiles = *tiles_m * *tiles_n;
+    int sp = (kNumSMs + tiles - 1) / tiles;                       // ~ one CTA per SM
+    int rps = ((B + sp - 1) / sp + kWgRows - 1) / kWgRows * kWgRows;
+    if (rps < kWgRows) rps = kWgRows;
+    *rows_per_split = rps;
+    *splits = (B + rps - 1) / rps;
+    if (*splits < 1) *splits = 1;
 }
 
 }  // namespace ctr
@@ -257,6 +423,45 @@ extern "C" int ctr_linear_fwd(const float *A, int64_t lda, const float *W, int64
     GemmArgs g{C, bias, ldc, M, N, K, act};
     dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM);
     note_launch(), linear_tf32_kernel<<<grid, kGemmThreads, kGemmSmem, (cudaStream_t)stream>>>(ma, mb, g);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int64_t ctr_linear_wgrad_workspace_bytes(int32_t B, int32_t N, int32_t K) {
+    int tm, tn, sp, rps;
+    wgrad_plan(B < 1 ? 1 : B, N, K, &tm, &tn, &sp, &rps);
+    return (int64_t)sp * N * K * (int64_t)sizeof(float) + 256;
+}
+
+extern "C" int ctr_linear_wgrad(const float *G, int64_t ldg, const float *X, int64_t ldx, int32_t B, int32_t N, int32_t K,
+                                float *dW, int64_t lddw, void *workspace, int64_t workspace_bytes, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CTR_REQUIRE(B >= 1 && N >= 1 && K >= 1, "bad wgrad shape B=%d N=%d K=%d", B, N, K);
+    CTR_REQUIRE(G != nullptr && X != nullptr && dW != nullptr && workspace != nullptr, "null pointer");
+    CTR_REQUIRE(ldg >= N && ldx >= K && lddw >= K, "leading dimension smaller than the row length");
+    CTR_REQUIRE(ldg % 4 == 0 && ldx % 4 == 0, "ldg and ldx must be multiples of 4 floats (16-byte TMA row pitch)");
+    CTR_REQUIRE((reinterpret_cast<uintptr_t>(G) & 15u) == 0 && (reinterpret_cast<uintptr_t>(X) & 15u) == 0 &&
+                    (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0,
+                "G, X and the workspace must be 16-byte aligned");
+    int tm, tn, sp, rps;
+    wgrad_plan(B, N, K, &tm, &tn, &sp, &rps);
+    CTR_REQUIRE(workspace_bytes >= (int64_t)sp * N * K * (int64_t)sizeof(float), "workspace too small");
+    CUtensorMap mg, mx;
+    int rc = make_map(&mg, G, B, N, ldg, kWgRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc != CTR_OK) return rc;
+    rc = make_map(&mx, X, B, K, ldx, kWgRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc != CTR_OK) return rc;
+    static bool configured = false;
+    if (!configured) {
+        CTR_CUDA_OK(cudaFuncSetAttribute(wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
+        configured = true;
+    }
+    WgradArgs a{static_cast<float *>(workspace), B, N, K, tn, rps};
+    note_launch(), wgrad_tf32_kernel<<<dim3(tm * tn, sp), kGemmThreads, kWgSmem, stream>>>(mg, mx, a);
+    const int64_t elems = (int64_t)N * K;
+    int64_t rb = (elems + 255) / 256;
+    if (rb > kNumSMs * 8) rb = kNumSMs * 8;
+    note_launch(), wgrad_reduce_kernel<<<(unsigned)rb, 256, 0, stream>>>(a.partial, sp, elems, K, dW, lddw);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }

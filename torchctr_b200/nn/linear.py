@@ -18,6 +18,12 @@ def tc_eligible(x: torch.Tensor, weight: torch.Tensor) -> bool:
             and x.data_ptr() % 16 == 0 and weight.shape[1] % 4 == 0 and weight.shape[0] % 4 == 0 and weight.shape[0] >= 16)
 
 
+def wgrad_eligible(gy: torch.Tensor, x: torch.Tensor) -> bool:
+    ok = lambda t: (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0
+                    and t.data_ptr() % 16 == 0)      # noqa: E731
+    return ok(gy) and ok(x) and gy.shape[0] == x.shape[0] and gy.shape[0] >= 1
+
+
 class _LinearTCFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -34,7 +40,7 @@ class _LinearTCFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = ops.linear_fwd(gy, w.t().contiguous())          # [M, N] @ [N, K]: W^T is small, transpose it once
         if ctx.needs_input_grad[1]:
-            gw = gy.t() @ x
+            gw = ops.linear_wgrad(gy, x) if wgrad_eligible(gy, x) else gy.t() @ x
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gy.sum(dim=0)
         return gx, gw, gb

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .linear import tc_eligible
+from .linear import tc_eligible, wgrad_eligible
 
 
 class _TowerBlockFn(torch.autograd.Function):
@@ -43,7 +43,7 @@ class _TowerBlockFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = ops.linear_fwd(gz, w.t().contiguous()) if tc else gz @ w
         if ctx.needs_input_grad[1]:
-            gw = gz.t() @ x
+            gw = ops.linear_wgrad(gz, x) if tc and wgrad_eligible(gz, x) else gz.t() @ x
         return gx, gw, dbias, dgamma, dbeta, None, None, None, None, None
 
 

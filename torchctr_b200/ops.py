@@ -488,3 +488,27 @@ def bn_relu_dropout_bwd(gy, z, mean, rstd, gamma, beta, p_drop: float, seed_dev,
                                                       dgamma.data_ptr(), dbeta.data_ptr(), _lib.ptr(dbias),
                                                       tower_workspace(dev, N).data_ptr(), _stream(z)), "ctr_bn_relu_dropout_bwd")
     return gz, dgamma, dbeta, dbias
+
+
+_wgrad_ws: dict = {}
+
+
+def linear_wgrad(gz: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """``gz.T @ x`` -> [N, K]: the weight gradient of ``y = x W^T`` on tcgen05 (TF32 in, fp32 accumulate, split over
+    the batch).  gz f32 [B, N], x f32 [B, K], unit inner stride, row pitches multiples of 4 floats."""
+    _rows2d(gz, "gz")
+    _rows2d(x, "x")
+    B, N = gz.shape
+    K = x.shape[1]
+    if x.shape[0] != B:
+        raise ValueError(f"batch mismatch: gz {tuple(gz.shape)} vs x {tuple(x.shape)}")
+    need = _lib.check(_lib.lib().ctr_linear_wgrad_workspace_bytes(B, N, K))
+    key = (gz.device, need)
+    ws = _wgrad_ws.get(key)
+    if ws is None:
+        ws = _wgrad_ws[key] = torch.empty(need, dtype=torch.uint8, device=gz.device)
+    out = torch.empty(N, K, dtype=torch.float32, device=gz.device)
+    with _timed("linear_wgrad"):
+        _lib.check(_lib.lib().ctr_linear_wgrad(gz.data_ptr(), gz.stride(0), x.data_ptr(), x.stride(0), B, N, K, out.data_ptr(),
+                                               out.stride(0), ws.data_ptr(), ws.numel(), _stream(gz)), "ctr_linear_wgrad")
+    return out
