@@ -18,17 +18,16 @@
 // need no padding beyond 16-byte row pitches.  Two CTAs fit per SM (96 KB smem, 128 of 512 TMEM
 // columns each), so one tile's epilogue overlaps the other's main loop.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace ctr {
 
-constexpr int kBM = 128, kBN = 128, kBK = 32;   // tile; kBK floats = 128 bytes = one swizzle row
-constexpr int kStages = 3;
+constexpr int kBM = 128, kBK = 32;               // tile; kBK floats = 128 bytes = one swizzle row
 constexpr int kUmmaK = 8;                       // tf32: 32 bytes per MMA along K
 constexpr int kGemmThreads = 192;
-constexpr int kTileABytes = kBM * kBK * 4, kTileBBytes = kBN * kBK * 4;
-constexpr int kGemmSmem = kStages * (kTileABytes + kTileBBytes) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kTileABytes = kBM * kBK * 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -95,101 +94,224 @@ struct GemmArgs {
     const float *bias;
     int64_t ldc;
     int M, N, K, act;
+    int tiles_m, tiles_n;
+    const float *A;      // for the L2 prefetch of whole A tiles
+    int64_t lda;
 };
 
-__global__ void __launch_bounds__(kGemmThreads, 2)
+// pull a contiguous global range towards L2 (no data comes back to the SM): 16-byte aligned, multiple of 16 bytes
+__device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct GemmArgs;
+__device__ __forceinline__ void prefetch_a_rows(const GemmArgs &g, int tile_m);
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// rows [tile_m * 128, +128) of A are one contiguous range: stream them into L2
+__device__ __forceinline__ void prefetch_a_rows(const GemmArgs &g, int tile_m) {
+    const int r0 = tile_m * kBM;
+    const int nr = g.M - r0 < kBM ? g.M - r0 : kBM;
+    const char *p = reinterpret_cast<const char *>(g.A + (int64_t)r0 * g.lda);
+    const int64_t bytes = ((int64_t)(nr - 1) * g.lda + g.K) * 4 / 16 * 16;
+    for (int64_t off = 0; off < bytes; off += 32768)
+        l2_prefetch_bulk(p + off, (uint32_t)(bytes - off < 32768 ? bytes - off : 32768));
+}
+
+// Persistent, warp-specialised: one CTA per SM walks the output tiles (n fastest, so the CTAs that run side by side
+// share their A tile in L2).  The accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the TMA /
+// MMA main loop of tile i + 1; BN up to 256 columns keeps the re-reads of A (once per n tile) low.  Measured on
+// the 65536 x 256 x 432 layer (profiles/): 41 us with stores and MMAs switched off, i.e. the kernel is bound by the
+// L2 -> SM operand stream (344 MB: every 128-row tile re-reads its W tile), not by the tensor pipe (22 % busy) nor
+// by HBM; a 2-CTA (cta_group::2) variant that halves the W stream is the next step.
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
     linear_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const GemmArgs g) {
+    constexpr int kSt = 4;
+    constexpr int kTileB = BN * kBK * 4;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B wants 1024-byte alignment
-    const uint32_t a_smem = base, b_smem = base + kStages * kTileABytes;
-    const uint32_t bars = b_smem + kStages * kTileBBytes;
-    const uint32_t full0 = bars, empty0 = bars + 8 * kStages, accum_full = bars + 16 * kStages;
-    const uint32_t tmem_slot = accum_full + 8;
+    const uint32_t a_smem = base, b_smem = base + kSt * kTileABytes;
+    const uint32_t bars = b_smem + kSt * kTileB;
+    const uint32_t full0 = bars, empty0 = bars + 8 * kSt, acc_full0 = bars + 16 * kSt, acc_empty0 = acc_full0 + 16;
+    const uint32_t tmem_slot = acc_empty0 + 16;
+    const uint32_t epi_smem = bars + 256;                                  // 4 epilogue warps x 4 KB of staging
     uint8_t *gen_base = smem_raw + (base - smem_u32(smem_raw));
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(gen_base + (tmem_slot - base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
     const int num_kb = (g.K + kBK - 1) / kBK;
+    const int num_tiles = g.tiles_m * g.tiles_n;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kSt; ++s) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
         }
-        mbar_init(accum_full, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full0 + 8 * b, 1);
+            mbar_init(acc_empty0 + 8 * b, 4);      // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kBN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_acc = *tmem_slot_ptr;
+    const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
         if (lane == 0) {  // ---- TMA producer
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                if (kb >= kStages) mbar_wait(empty0 + 8 * s, ((kb / kStages) - 1) & 1);
-                mbar_expect_tx(full0 + 8 * s, kTileABytes + kTileBBytes);
-                tma_load_2d(a_smem + s * kTileABytes, &map_a, full0 + 8 * s, kb * kBK, m0);
-                tma_load_2d(b_smem + s * kTileBBytes, &map_b, full0 + 8 * s, kb * kBK, n0);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / g.tiles_n) * kBM, n0 = (tile % g.tiles_n) * BN;
+                // The TMA boxes below take 128 bytes from each of 128 rows -- 128 DRAM pages per box.  The rows of
+                // a tile are one contiguous range of A, so ask L2 for the NEXT tile's rows as one stream now; its
+                // boxes then hit L2.  (Only when the next tile is another row block: n tiles share their A rows.)
+                const int next = tile + gridDim.x;
+                if (tile == (int)blockIdx.x) prefetch_a_rows(g, tile / g.tiles_n);
+                if (next < num_tiles && next / g.tiles_n != tile / g.tiles_n) prefetch_a_rows(g, next / g.tiles_n);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % kSt;
+                    if (it >= kSt) mbar_wait(empty0 + 8 * s, ((it / kSt) - 1) & 1);
+                    mbar_expect_tx(full0 + 8 * s, kTileABytes + kTileB);
+                    tma_load_2d(a_smem + s * kTileABytes, &map_a, full0 + 8 * s, kb * kBK, m0);
+                    tma_load_2d(b_smem + s * kTileB, &map_b, full0 + 8 * s, kb * kBK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ---- MMA issuer
-            const uint32_t idesc = umma_idesc_tf32(kBM, kBN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                mbar_wait(full0 + 8 * s, (kb / kStages) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t da = umma_desc(a_smem + s * kTileABytes), db = umma_desc(b_smem + s * kTileBBytes);
+            const uint32_t idesc = umma_idesc_tf32(kBM, BN);
+            int it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+                const int buf = tl & 1;
+                if (tl >= 2) {                                  // the epilogue must have drained this accumulator
+                    mbar_wait(acc_empty0 + 8 * buf, ((tl >> 1) - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % kSt;
+                    mbar_wait(full0 + 8 * s, (it / kSt) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t da = umma_desc(a_smem + s * kTileABytes), db = umma_desc(b_smem + s * kTileB);
 #pragma unroll
-                for (int k = 0; k < kBK / kUmmaK; ++k)  // advance 32 bytes along K inside the swizzle atom
-                    umma_tf32(tmem_acc, da + (uint64_t)(k * kUmmaK * 4 >> 4), db + (uint64_t)(k * kUmmaK * 4 >> 4), idesc,
-                              (kb | k) ? 1u : 0u);
-                umma_commit(empty0 + 8 * s);       // stage free once these MMAs have read it
+                    for (int k = 0; k < kBK / kUmmaK; ++k)  // advance 32 bytes along K inside the swizzle atom
+                        umma_tf32(tmem_acc, da + (uint64_t)(k * kUmmaK * 4 >> 4), db + (uint64_t)(k * kUmmaK * 4 >> 4), idesc,
+                                  (kb | k) ? 1u : 0u);
+                    umma_commit(empty0 + 8 * s);       // stage free once these MMAs have read it
+                }
+                umma_commit(acc_full0 + 8 * buf);      // accumulator complete
             }
-            umma_commit(accum_full);               // accumulator complete
         }
     } else {  // ---- epilogue warps 2..5: TMEM lane quarter = warp % 4
-        mbar_wait(accum_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
         const bool vec_ok = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15u) == 0);
+        const bool bias_vec = g.bias != nullptr && (reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0;
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+            const int buf = tl & 1;
+            const int m0 = (tile / g.tiles_n) * kBM, n0 = (tile % g.tiles_n) * BN;
+            mbar_wait(acc_full0 + 8 * buf, (tl >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * BN);
+            // 32 columns at a time: lane = row out of TMEM, bias / activation in registers, then through this warp's
+            // 4 KB of shared memory (float4 slots xor-swizzled by row) so that the global stores are whole 128-byte
+            // row pieces, four rows per instruction, instead of 16 bytes to each of 32 rows
+            float4 *stage = reinterpret_cast<float4 *>(gen_base + (epi_smem - base)) + q * 256;
 #pragma unroll 1
-        for (int c = 0; c < kBN; c += 16) {
-            float v[16];
-            tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);   // all lanes take part (.sync.aligned)
-            const int col = n0 + c;
-            if (row < g.M && col < g.N) {
+            for (int c = 0; c < BN; c += 32) {
+                if (n0 + c >= g.N) break;              // warp-uniform: nothing left in this tile
+                float v[32];
+                tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);   // all lanes take part (.sync.aligned)
+                const int col = n0 + c;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float b = (g.bias != nullptr && col + j < g.N) ? __ldg(g.bias + col + j) : 0.f;
-                    float x = v[j] + b;
-                    v[j] = (g.act == 1 && x < 0.f) ? 0.f : x;
+                for (int j = 0; j < 32; j += 4) {
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bias_vec && col + j + 4 <= g.N) {
+                        b4 = __ldg(reinterpret_cast<const float4 *>(g.bias + col + j));
+                    } else if (g.bias != nullptr) {
+                        if (col + j + 0 < g.N) b4.x = __ldg(g.bias + col + j + 0);
+                        if (col + j + 1 < g.N) b4.y = __ldg(g.bias + col + j + 1);
+                        if (col + j + 2 < g.N) b4.z = __ldg(g.bias + col + j + 2);
+                        if (col + j + 3 < g.N) b4.w = __ldg(g.bias + col + j + 3);
+                    }
+                    float4 o = make_float4(v[j] + b4.x, v[j + 1] + b4.y, v[j + 2] + b4.z, v[j + 3] + b4.w);
+                    if (g.act == 1) {
+                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                    }
+                    stage[lane * 8 + ((j >> 2) ^ (lane & 7))] = o;
                 }
-                float *dst = g.C + (int64_t)row * g.ldc + col;
-                if (vec_ok && col + 16 <= g.N) {
+                __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-                    for (int j = 0; j < 16 && col + j < g.N; ++j) dst[j] = v[j];
+                for (int i = 0; i < 32; i += 4) {       // rows i .. i + 3 of this warp's 32, 8 lanes (128 bytes) per row
+                    const int r = i + (lane >> 3), slot = lane & 7;
+                    const float4 o = stage[r * 8 + (slot ^ (r & 7))];
+                    const int grow = m0 + q * 32 + r, gcol = col + 4 * slot;
+                    if (grow < g.M && gcol < g.N) {
+                        float *dst = g.C + (int64_t)grow * g.ldc + gcol;
+                        if (vec_ok && gcol + 4 <= g.N) {
+                            *reinterpret_cast<float4 *>(dst) = o;
+                        } else {
+                            dst[0] = o.x;
+                            if (gcol + 1 < g.N) dst[1] = o.y;
+                            if (gcol + 2 < g.N) dst[2] = o.z;
+                            if (gcol + 3 < g.N) dst[3] = o.w;
+                        }
+                    }
                 }
+                __syncwarp();
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(kBN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN));
     }
+}
+
+template <int BN>
+static int launch_linear(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs g, cudaStream_t stream) {
+    constexpr int smem = 4 * (kTileABytes + BN * kBK * 4) + 1024 + 256 + 4 * 4096;
+    static bool configured = false;
+    if (!configured) {
+        CTR_CUDA_OK(cudaFuncSetAttribute(linear_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    g.tiles_m = (g.M + kBM - 1) / kBM;
+    g.tiles_n = (g.N + BN - 1) / BN;
+    const int tiles = g.tiles_m * g.tiles_n;
+    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    note_launch(), linear_tf32_kernel<BN><<<grid, kGemmThreads, smem, stream>>>(ma, mb, g);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -410,21 +532,17 @@ extern "C" int ctr_linear_fwd(const float *A, int64_t lda, const float *W, int64
     CTR_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15u) == 0 && (reinterpret_cast<uintptr_t>(W) & 15u) == 0,
                 "A and W must be 16-byte aligned");
     CTR_REQUIRE(act == 0 || act == 1, "act must be 0 (none) or 1 (relu)");
+    // widest tile the output needs: fewer passes over A (one per n tile)
+    const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
     CUtensorMap ma, mb;
     int rc = make_map(&ma, A, M, K, lda, kBM);
     if (rc != CTR_OK) return rc;
-    rc = make_map(&mb, W, N, K, ldw, kBN);
+    rc = make_map(&mb, W, N, K, ldw, bn);
     if (rc != CTR_OK) return rc;
-    static bool configured = false;
-    if (!configured) {
-        CTR_CUDA_OK(cudaFuncSetAttribute(linear_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-        configured = true;
-    }
-    GemmArgs g{C, bias, ldc, M, N, K, act};
-    dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM);
-    note_launch(), linear_tf32_kernel<<<grid, kGemmThreads, kGemmSmem, (cudaStream_t)stream>>>(ma, mb, g);
-    CTR_CUDA_OK(cudaGetLastError());
-    return CTR_OK;
+    GemmArgs g{C, bias, ldc, M, N, K, act, 0, 0, A, lda};
+    if (bn == 256) return launch_linear<256>(ma, mb, g, (cudaStream_t)stream);
+    if (bn == 128) return launch_linear<128>(ma, mb, g, (cudaStream_t)stream);
+    return launch_linear<64>(ma, mb, g, (cudaStream_t)stream);
 }
 
 extern "C" int64_t ctr_linear_wgrad_workspace_bytes(int32_t B, int32_t N, int32_t K) {
