@@ -170,8 +170,13 @@ def kernel_launches() -> int:
     return int(_lib.lib().ctr_kernel_launches())
 
 
+def _width_tag(call: GroupCall) -> str:
+    """Timer label suffix: the embedding dim of the group's first table (DeepFM runs a D=16 and a D=1 group)."""
+    return f"_d{call.struct.features[0].D}" if call.struct.num_features > 0 else ""
+
+
 def emb_pool_fwd(call: GroupCall) -> None:
-    with _timed("emb_pool_fwd"):
+    with _timed("emb_pool_fwd" + _width_tag(call)):
         _lib.check(_lib.lib().ctr_emb_pool_fwd(C.byref(call.struct), _stream()), "ctr_emb_pool_fwd")
 
 
@@ -209,7 +214,7 @@ def emb_bwd_apply(call: GroupCall, workspace: torch.Tensor, opt: _lib.Opt, uniq_
     _chk(row_grad, "row_grad", torch.float32)
     _chk(num_unique, "num_unique", torch.int64)
     stride = 0 if row_grad is None else row_grad.shape[1]
-    with _timed("emb_bwd_apply"):
+    with _timed("emb_bwd_apply" + _width_tag(call)):
         _lib.check(_lib.lib().ctr_emb_bwd_apply(C.byref(call.struct), workspace.data_ptr(), C.byref(opt),
                                                 _lib.ptr(uniq_feature), _lib.ptr(uniq_row), _lib.ptr(row_grad), stride,
                                                 _lib.ptr(num_unique), _stream()), "ctr_emb_bwd_apply")
@@ -394,7 +399,7 @@ def make_shard(world: int, rank: int, adj: torch.Tensor) -> _lib.Shard:
 
 
 def emb_pool_fwd_sharded(call: GroupCall, shard: _lib.Shard, tables) -> None:
-    with _timed("emb_pool_fwd"):
+    with _timed("emb_pool_fwd" + _width_tag(call)):
         _lib.check(_lib.lib().ctr_emb_pool_fwd_sharded(C.byref(call.struct), C.byref(shard), tables, _stream()),
                    "ctr_emb_pool_fwd_sharded")
 
@@ -423,7 +428,7 @@ def emb_bwd_plan_p2p(call: GroupCall, shard: _lib.Shard, counts, keys, slots, wo
 def emb_bwd_apply_p2p(call: GroupCall, shard: _lib.Shard, workspace: torch.Tensor, opt: _lib.Opt, grads,
                       num_unique: torch.Tensor | None = None) -> None:
     _chk(num_unique, "num_unique", torch.int64)
-    with _timed("emb_bwd_apply"):
+    with _timed("emb_bwd_apply" + _width_tag(call)):
         _lib.check(_lib.lib().ctr_emb_bwd_apply_p2p(C.byref(call.struct), C.byref(shard), workspace.data_ptr(), C.byref(opt),
                                                     grads, _lib.ptr(num_unique), _stream()), "ctr_emb_bwd_apply_p2p")
 
