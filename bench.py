@@ -275,7 +275,8 @@ def run_ours(args):
     if world > 1:
         model = shard_model(model, None, device=dev)    # keep this rank's rows of every table, drop the rest
     model = model.to(dev).train()
-    opt = torch.optim.Adagrad(model.dense_parameters(), lr=LR)    # tower etc.; tables take the fused row update
+    from torchctr_b200.optim import FusedAdagrad
+    opt = FusedAdagrad(model.dense_parameters(), lr=LR)           # torch.optim.Adagrad arithmetic, one launch; tables take the fused row update
     model.bind_optimizer(opt, kind="adagrad")
 
     nb = 4

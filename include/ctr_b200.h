@@ -243,6 +243,24 @@ int ctr_bn_relu_dropout_bwd(const float *gy, int64_t ldgy, const float *z, int64
                             const uint64_t *seed_dev, uint64_t seed_offset, float *gz, int64_t ldgz, float *dgamma,
                             float *dbeta, float *dbias, void *workspace, void *stream);
 
+/* ---- logit head: the last Linear(H -> 1) of the tower (dnn.py:46) + extra logit terms + the mean
+ * binary_cross_entropy_with_logits of dnn.py:75, forward and backward.  h f32 [B, H] (H a power of two in [4, 128],
+ * row pitch multiple of 4), w [H], bias [1] or NULL, extra [B] (stride in floats) or NULL, labels [B] (stride).
+ * fwd: logits[B] (may be NULL), dz[B] = (sigmoid(z) - y) / B, loss[1] = mean loss.  bwd, given the DEVICE scalar
+ * gscale = dL/dloss: gh[B, H] = gscale dz w (may be NULL), gw[H], gb[1] (may be NULL), gextra[B] (may be NULL).
+ * workspace: ctr_tower_workspace_bytes(H). */
+int ctr_logit_bce_fwd(const float *h, int64_t ldh, int32_t B, int32_t H, const float *w, const float *bias,
+                      const float *extra, int64_t extra_stride, const float *labels, int64_t label_stride, float *logits,
+                      float *dz, float *loss, void *workspace, void *stream);
+int ctr_logit_bce_bwd(const float *h, int64_t ldh, int32_t B, int32_t H, const float *w, const float *dz,
+                      const float *gscale, float *gh, int64_t ldgh, float *gw, float *gb, float *gextra,
+                      int64_t gextra_stride, void *workspace, void *stream);
+
+/* torch.optim.Adagrad (lr_decay = 0, weight_decay = 0) over `count` <= 48 dense fp32 tensors in ONE launch:
+ * sum += g*g; p -= lr * g / (sqrt(sum) + eps).  params / grads / sums / sizes are HOST arrays of device pointers / sizes. */
+int ctr_dense_adagrad(int32_t count, float *const *params, const float *const *grads, float *const *sums,
+                      const int64_t *sizes, float lr, float eps, void *stream);
+
 /* ---- row-sharded tables: pack / unpack around the NCCL all-to-all ------------------------------
  * (the reference is replicas-only, torchctr/trainer.py:128-130).  owner(row) = row mod world; on the owner
  * all tables of the group live in one fused shard, row base[owner * num_features + table] + row / world. */

@@ -102,3 +102,55 @@ def test_tower_block_autograd_matches_torch_modules():
     _close(bn.weight.grad, bn2.weight.grad, rtol=5e-5)
     _close(bn.bias.grad, bn2.bias.grad, rtol=5e-5)
     _close(bn.running_var, bn2.running_var)
+
+
+@pytest.mark.parametrize("B,H,with_extra", [(65536, 64, True), (1000, 64, False), (257, 128, True), (33, 8, True)])
+def test_logit_bce_head_matches_torch(B, H, with_extra):
+    """Last Linear(H, 1) + extra logit terms + mean BCE-with-logits (dnn.py:46,68,75) as one node vs torch ops."""
+    import torch.nn.functional as F
+    from torchctr_b200.nn.head import head_eligible, logit_bce
+    gen = torch.Generator().manual_seed(B + H)
+    h = torch.randn(B, H, generator=gen).cuda().requires_grad_(True)
+    lin = nn.Linear(H, 1).cuda()
+    extra = (torch.randn(B, 1, generator=gen) * 2).cuda().requires_grad_(True) if with_extra else None
+    labels = (torch.rand(B, 1, generator=gen) < 0.25).float().cuda()
+    assert head_eligible(h, lin, labels)
+    loss = logit_bce(h, lin, extra, labels)
+    (loss * 0.5).backward()                     # a non-trivial upstream gradient (multi-GPU scales by 1 / world)
+    got = (loss.detach(), h.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone(), None if extra is None else extra.grad.clone())
+    h.grad = lin.weight.grad = lin.bias.grad = None
+    if extra is not None:
+        extra.grad = None
+    z = lin(h) + (extra if extra is not None else 0)
+    ref = F.binary_cross_entropy_with_logits(z, labels)
+    (ref * 0.5).backward()
+    want = (ref.detach(), h.grad, lin.weight.grad, lin.bias.grad, None if extra is None else extra.grad)
+    for g, r in zip(got, want):
+        if r is not None:
+            _close(g, r, rtol=2e-5)
+
+
+def test_fused_adagrad_equals_torch_adagrad():
+    from torchctr_b200.optim import FusedAdagrad
+    gen = torch.Generator().manual_seed(1)
+    shapes = [(256, 432), (256,), (128, 256), (1,), (64, 128), (7, 3)]
+    p1 = [torch.randn(*s, generator=gen).cuda().requires_grad_(True) for s in shapes]
+    p2 = [p.detach().clone().requires_grad_(True) for p in p1]
+    o1 = FusedAdagrad(p1, lr=0.05, eps=1e-10)
+    o2 = torch.optim.Adagrad(p2, lr=0.05, eps=1e-10)
+    for step in range(4):
+        for a, b in zip(p1, p2):
+            g = torch.randn(a.shape, generator=gen).cuda()
+            a.grad, b.grad = g.clone(), g.clone()
+        if step == 2:
+            p1[3].grad = p2[3].grad = None          # a parameter without gradient is skipped, like torch does
+        o1.step()
+        o2.step()
+    for a, b in zip(p1, p2):
+        _close(a, b, rtol=1e-6)
+    for a, b in zip(p1, p2):
+        _close(o1.state[a]["sum"], o2.state[b]["sum"], rtol=1e-6)
+        assert float(o1.state[a]["step"]) == float(o2.state[b]["step"])
+    sd = o1.state_dict()
+    o3 = torch.optim.Adagrad([p.detach().clone().requires_grad_(True) for p in p1], lr=0.05)
+    o3.load_state_dict(sd)                          # same state layout as torch.optim.Adagrad

@@ -109,6 +109,10 @@ _SIGNATURES = {
                                           _P, C.c_int64, _P]),
     "ctr_bn_relu_dropout_bwd": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_float, _P,
                                           C.c_uint64, _P, C.c_int64, _P, _P, _P, _P, _P]),
+    "ctr_logit_bce_fwd": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P, _P]),
+    "ctr_logit_bce_bwd": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_int64, _P, _P]),
+    "ctr_dense_adagrad": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_int64), C.c_float, C.c_float, _P]),
     "ctr_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "ctr_peer_free": (C.c_int, [_P]),
     "ctr_peer_export": (C.c_int, [_P, _P]),

@@ -281,6 +281,148 @@ __global__ void __launch_bounds__(kFinCols * kFinLanes)
     out[n] = (float)tot[0];
 }
 
+// ---- logit head: final Linear(H -> 1) + extra logit terms + BCE-with-logits (mean), forward and backward ---------
+// torchctr/models/dnn.py:46,68 (last Linear of the tower) and :75 (binary_cross_entropy_with_logits).  torch runs a
+// gemv, an add, the loss (5 element-wise kernels + a mean) and their backward (another ~8) over [B, 1] tensors; here
+// one pass computes z = h.w + b + extra, the per-sample loss and dz = (sigmoid(z) - y) / B, a second one (backward)
+// gh = g dz w and the reductions gw = g sum_b dz h, gb = g sum_b dz.  Same thread geometry as the tower kernels:
+// a row of h is covered by CG = H / 4 lanes (a power of two <= 32), reduced with xor shuffles.
+struct HeadArgs {
+    const float *h;
+    int64_t ldh;
+    const float *w;        // [H]
+    const float *bias;     // [1] or null
+    const float *extra;    // [B, extra_stride] column 0, or null
+    int64_t extra_stride;
+    const float *labels;   // [B, label_stride] column 0
+    int64_t label_stride;
+    float *logits;         // [B] or null
+    float *dz;             // [B]
+    float inv_B;
+};
+
+__global__ void __launch_bounds__(kTowerThreads)
+    head_fwd_kernel(const HeadArgs a, const TowerGeom g, float *__restrict__ partial) {
+    __shared__ float red[kTowerThreads / 32];
+    const int cg = threadIdx.x % g.CG, rl = threadIdx.x / g.CG;
+    float loss_acc = 0.f;
+    if (rl < g.RL) {
+        const float4 w4 = ld4(a.w + 4 * cg);
+        const float b0 = a.bias != nullptr ? __ldg(a.bias) : 0.f;
+        const int r0 = blockIdx.x * g.rows_per_block;
+        const int r1 = min(r0 + g.rows_per_block, g.B);
+        const int iters = (r1 - r0 + g.RL - 1) / g.RL;       // the same trip count for every lane of a row team
+        for (int it = 0; it < iters; ++it) {
+            const int r = r0 + rl + it * g.RL;
+            const bool ok = r < r1;
+            float d = 0.f;
+            if (ok) {
+                const float4 v = ld4(a.h + (size_t)r * a.ldh + 4 * cg);
+                d = v.x * w4.x + v.y * w4.y + v.z * w4.z + v.w * w4.w;
+            }
+            for (int off = 1; off < g.CG; off <<= 1) d += __shfl_xor_sync(kFull, d, off);
+            if (ok && cg == 0) {
+                float z = d + b0;
+                if (a.extra != nullptr) z += __ldg(a.extra + (size_t)r * a.extra_stride);
+                const float y = __ldg(a.labels + (size_t)r * a.label_stride);
+                // max(z, 0) - z y + log1p(exp(-|z|)): torch's stable form
+                loss_acc += fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));
+                const float sg = 1.f / (1.f + expf(-z));
+                a.dz[r] = (sg - y) * a.inv_B;
+                if (a.logits != nullptr) a.logits[r] = z;
+            }
+        }
+    }
+    for (int off = 16; off; off >>= 1) loss_acc += __shfl_xor_sync(kFull, loss_acc, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = loss_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < kTowerThreads / 32; ++i) t += red[i];
+        partial[blockIdx.x] = t;
+    }
+}
+
+__global__ void head_loss_finalize_kernel(const float *__restrict__ partial, int blocks, float inv_B, float *__restrict__ loss) {
+    __shared__ double sh[256];
+    double t = 0.0;
+    for (int i = threadIdx.x; i < blocks; i += 256) t += (double)partial[i];
+    sh[threadIdx.x] = t;
+    __syncthreads();
+    for (int s = 128; s; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *loss = (float)(sh[0] * (double)inv_B);
+}
+
+// gh[r, :] = g dz[r] w;  partial (2 quantities): sum_r dz[r] h[r, :], and sum_r dz[r] (column 0 of quantity 1)
+__global__ void __launch_bounds__(kTowerThreads)
+    head_bwd_kernel(const float *__restrict__ h, int64_t ldh, const float *__restrict__ w, const float *__restrict__ dz,
+                    const float *__restrict__ gscale, const TowerGeom g, float *__restrict__ gh, int64_t ldgh,
+                    float *__restrict__ gextra, int64_t gextra_stride, float *__restrict__ partial) {
+    __shared__ float4 red[kTowerThreads];
+    const int cg = threadIdx.x % g.CG, rl = threadIdx.x / g.CG;
+    float4 acc[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
+    if (rl < g.RL) {
+        const float gs = __ldg(gscale);
+        const float4 w4 = ld4(w + 4 * cg);
+        const int r0 = blockIdx.x * g.rows_per_block;
+        const int r1 = min(r0 + g.rows_per_block, g.B);
+#pragma unroll 4
+        for (int r = r0 + rl; r < r1; r += g.RL) {
+            const float d = __ldg(dz + r);
+            const float4 v = ld4(h + (size_t)r * ldh + 4 * cg);
+            acc[0].x = fmaf(d, v.x, acc[0].x); acc[0].y = fmaf(d, v.y, acc[0].y);
+            acc[0].z = fmaf(d, v.z, acc[0].z); acc[0].w = fmaf(d, v.w, acc[0].w);
+            const float gd = gs * d;
+            if (gh != nullptr)
+                *reinterpret_cast<float4 *>(gh + (size_t)r * ldgh + 4 * cg) = make_float4(gd * w4.x, gd * w4.y, gd * w4.z, gd * w4.w);
+            if (cg == 0) {
+                acc[1].x += d;
+                if (gextra != nullptr) gextra[(size_t)r * gextra_stride] = gd;
+            }
+        }
+    }
+    reduce_rows_and_store<2>(acc, g, cg, rl, red, partial);
+}
+
+__global__ void __launch_bounds__(kFinCols * kFinLanes)
+    head_bwd_finalize_kernel(const float *__restrict__ partial, int blocks, int H, const float *__restrict__ gscale,
+                             float *__restrict__ gw, float *__restrict__ gb) {
+    double tot[2];
+    int n;
+    if (!column_totals<2>(partial, blocks, H, tot, &n)) return;
+    const double gs = (double)__ldg(gscale);
+    gw[n] = (float)(gs * tot[0]);
+    if (n == 0 && gb != nullptr) *gb = (float)(gs * tot[1]);
+}
+
+// ---- dense Adagrad over a list of small tensors in one launch (the replicated tower parameters) -------------------
+constexpr int kMaxDenseTensors = 48;
+struct DenseAdagradArgs {
+    float *p[kMaxDenseTensors];
+    const float *g[kMaxDenseTensors];
+    float *s[kMaxDenseTensors];
+    long long n[kMaxDenseTensors];
+    int count;
+    float lr, eps;
+};
+
+__global__ void __launch_bounds__(256) dense_adagrad_kernel(const __grid_constant__ DenseAdagradArgs a) {
+    const int t = blockIdx.y;
+    const long long n = a.n[t];
+    float *p = a.p[t];
+    const float *gr = a.g[t];
+    float *st = a.s[t];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = gr[i];
+        const float si = st[i] + gi * gi;
+        st[i] = si;
+        p[i] = p[i] - a.lr * __fdiv_rn(gi, __fsqrt_rn(si) + a.eps);      // torch.optim.Adagrad: addcdiv_(grad, sqrt(sum) + eps, -clr)
+    }
+}
+
 static int check_tower_shape(int B, int N, int64_t ld) {
     CTR_REQUIRE(B >= 1 && N >= 4 && N % 4 == 0 && N <= 1024, "tower block: B=%d, N=%d unsupported (N: multiple of 4 up to 1024)", B, N);
     CTR_REQUIRE(ld >= N && ld % 4 == 0, "row pitch %lld must be a multiple of 4 and >= N", (long long)ld);
@@ -359,6 +501,60 @@ extern "C" int ctr_bn_relu_dropout_bwd(const float *gy, int64_t ldgy, const floa
     note_launch(), bn_act_bwd_apply_kernel<<<g.blocks, kTowerThreads, 0, stream>>>(gy, ldgy, z, ldz, g, a, c1, c2, gz, ldgz, partial);
     if (dbias != nullptr)
         note_launch(), col_sum_finalize_kernel<<<(N + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, stream>>>(partial, g.blocks, N, dbias);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int ctr_logit_bce_fwd(const float *h, int64_t ldh, int32_t B, int32_t H, const float *w, const float *bias,
+                                 const float *extra, int64_t extra_stride, const float *labels, int64_t label_stride,
+                                 float *logits, float *dz, float *loss, void *workspace, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CTR_REQUIRE(B >= 1 && H >= 4 && H <= 128 && (H & (H - 1)) == 0, "head: B=%d, H=%d unsupported (H: power of two in [4, 128])", B, H);
+    CTR_REQUIRE(ldh >= H && ldh % 4 == 0, "row pitch %lld must be a multiple of 4 and >= H", (long long)ldh);
+    CTR_REQUIRE(h && w && labels && dz && loss && workspace, "null pointer");
+    CTR_REQUIRE(aligned16(h) && aligned16(w), "h and w must be 16-byte aligned");
+    const TowerGeom g = tower_geom(B, H);
+    HeadArgs a{h, ldh, w, bias, extra, extra_stride, labels, label_stride, logits, dz, 1.0f / (float)B};
+    float *partial = static_cast<float *>(workspace);
+    note_launch(), head_fwd_kernel<<<g.blocks, kTowerThreads, 0, stream>>>(a, g, partial);
+    note_launch(), head_loss_finalize_kernel<<<1, 256, 0, stream>>>(partial, g.blocks, 1.0f / (float)B, loss);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int ctr_logit_bce_bwd(const float *h, int64_t ldh, int32_t B, int32_t H, const float *w, const float *dz,
+                                 const float *gscale, float *gh, int64_t ldgh, float *gw, float *gb, float *gextra,
+                                 int64_t gextra_stride, void *workspace, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CTR_REQUIRE(B >= 1 && H >= 4 && H <= 128 && (H & (H - 1)) == 0, "head: B=%d, H=%d unsupported (H: power of two in [4, 128])", B, H);
+    CTR_REQUIRE(ldh >= H && ldh % 4 == 0 && (gh == nullptr || (ldgh >= H && ldgh % 4 == 0)), "row pitches must be multiples of 4 and >= H");
+    CTR_REQUIRE(h && w && dz && gscale && gw && workspace, "null pointer");
+    CTR_REQUIRE(aligned16(h) && aligned16(w) && aligned16(gh) && aligned16(workspace), "operands must be 16-byte aligned");
+    const TowerGeom g = tower_geom(B, H);
+    float *partial = static_cast<float *>(workspace);
+    note_launch(), head_bwd_kernel<<<g.blocks, kTowerThreads, 0, stream>>>(h, ldh, w, dz, gscale, g, gh, ldgh, gextra, gextra_stride, partial);
+    note_launch(), head_bwd_finalize_kernel<<<(H + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, stream>>>(partial, g.blocks, H, gscale, gw, gb);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int ctr_dense_adagrad(int32_t count, float *const *params, const float *const *grads, float *const *sums,
+                                 const int64_t *sizes, float lr, float eps, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CTR_REQUIRE(count >= 0 && count <= kMaxDenseTensors, "count=%d outside [0, %d]", count, kMaxDenseTensors);
+    if (count == 0) return CTR_OK;
+    CTR_REQUIRE(params && grads && sums && sizes, "null pointer");
+    DenseAdagradArgs a{};
+    long long biggest = 1;
+    for (int i = 0; i < count; ++i) {
+        CTR_REQUIRE(params[i] && grads[i] && sums[i] && sizes[i] >= 0, "tensor %d: null pointer or negative size", i);
+        a.p[i] = params[i]; a.g[i] = grads[i]; a.s[i] = sums[i]; a.n[i] = sizes[i];
+        if (sizes[i] > biggest) biggest = sizes[i];
+    }
+    a.count = count; a.lr = lr; a.eps = eps;
+    long long bx = (biggest + 1023) / 1024;
+    if (bx > kNumSMs * 2) bx = kNumSMs * 2;
+    note_launch(), dense_adagrad_kernel<<<dim3((unsigned)bx, count), 256, 0, stream>>>(a);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }

@@ -11,6 +11,7 @@ import torch.nn.functional as F
 
 from ..nn.embedding import EmbeddingTable, PlanLink, PooledLookupGroup
 from ..nn.linear import linear_tc
+from ..nn.head import head_eligible, logit_bce
 from ..nn.tower import block_is_fusable, tower_block
 from ..nn.vocab import VocabIndex
 
@@ -79,7 +80,7 @@ class CTRModelBase(nn.Module):
         the ids, hence one backward sort (``PlanLink``) -- or one all-to-all routing when sharded."""
         if self._sharded is not None:
             return self._sharded(feats, dense)
-        link = PlanLink() if self.training and len(self._groups) > 1 else None
+        link = PlanLink() if self.training else None      # one sort per step, started early on a side stream
         outs = [self._groups[0](feats, dense, self.training, link)]
         for g in self._groups[1:]:
             outs.append(g(feats, None, self.training, link))
@@ -137,8 +138,12 @@ class CTRModelBase(nn.Module):
             return linear_tc(x, weight, bias)
         return F.linear(x, weight, bias)
 
-    def _run_tower(self, x: torch.Tensor) -> torch.Tensor:
+    def _run_tower(self, x: torch.Tensor, stop_before_last: bool = False) -> torch.Tensor:
+        """The tower of dnn.py:35-46 on the lookup output.  ``stop_before_last``: return the input of the final
+        ``Linear(., 1)`` instead of the logits (the fused logit + loss head of ``training_step`` takes it from there)."""
         layers = list(self.tower)
+        if stop_before_last:
+            layers = layers[:-1]
         if self.training and x.is_cuda and x.dtype == torch.float32:
             # training mode: every [Linear, BatchNorm1d, ReLU, Dropout] block is one fused autograd node
             seed = self._step_seed(x.device)
@@ -154,6 +159,8 @@ class CTRModelBase(nn.Module):
                 for layer in layers[i:]:
                     h = self._linear(h, layer.weight, layer.bias) if isinstance(layer, nn.Linear) else layer(h)
                 return h
+        if not layers:
+            return x
         h = self._first_linear(x, layers[0])
         for layer in layers[1:]:
             h = self._linear(h, layer.weight, layer.bias) if isinstance(layer, nn.Linear) else layer(h)
@@ -177,8 +184,27 @@ class CTRModelBase(nn.Module):
                 table.vocab.fit_and_grow(feats[name], table)
 
     # ---- step protocol: dnn.py:72-82 ----------------------------------------------------------
+    def hidden_and_extra(self, input_feats):
+        """(input of the tower's last Linear [B, H], other logit terms [B, 1] or None): logits = last(h) + extra.
+        Subclasses with extra logit terms (DeepFM) override."""
+        raise NotImplementedError
+
     def training_step(self, batch, batch_idx):
         features, labels = batch
+        last = self.tower[-1]
+        if self.training and isinstance(last, nn.Linear) and len(self.tower) > 1:
+            try:
+                h, extra = self.hidden_and_extra(features)
+            except NotImplementedError:
+                h = None
+            if h is not None:
+                labels = labels.to(h.device, non_blocking=True)
+                if head_eligible(h, last, labels):       # last Linear + logit terms + mean BCE as one autograd node
+                    return logit_bce(h, last, extra, labels)
+                logits = self._linear(h, last.weight, last.bias)
+                if extra is not None:
+                    logits = logits + extra
+                return F.binary_cross_entropy_with_logits(logits, labels)
         logits = self(features)
         return F.binary_cross_entropy_with_logits(logits, labels.to(logits.device, non_blocking=True))
 

@@ -15,10 +15,16 @@ class DCNv2(CTRModelBase):
         self.cross = nn.ModuleList([CrossLayer(width, width) for _ in range(num_cross_layers)])
         self.tower = make_tower(width, list(hidden_units))
 
-    def forward(self, input_feats):
+    def _crossed(self, input_feats):
         self._grow_vocabularies(input_feats)
         (x0,) = self._lookup_all(input_feats, self.dense_block(input_feats))
         x = x0
         for layer in self.cross:
             x = layer(x0, x)
-        return self._run_tower(x)
+        return x
+
+    def forward(self, input_feats):
+        return self._run_tower(self._crossed(input_feats))
+
+    def hidden_and_extra(self, input_feats):
+        return self._run_tower(self._crossed(input_feats), stop_before_last=True), None

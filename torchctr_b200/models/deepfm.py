@@ -28,14 +28,22 @@ class DeepFM(CTRModelBase):
         self.linear_dense = nn.Linear(self._dense_width, 1) if self._dense_width else None
         self.tower = make_tower(self._sparse_width + self._dense_width, list(hidden_units))
 
-    def forward(self, input_feats):
+    def _parts(self, input_feats):
+        """(tower input x, the logit terms outside the tower: FM second order + first order (+ Linear on dense))"""
         self._grow_vocabularies(input_feats)
         dense = self.dense_block(input_feats)
         x, first = self._lookup_all(input_feats, dense)       # [B, pad4(F*D + Nd)], [B, pad4(F)]; one backward sort
         nf = len(self._names)
-        x, fm = fm_interaction_passthrough(x, nf, self._dim, first, nf)
-        logit = fm + self._run_tower(x)
+        x, extra = fm_interaction_passthrough(x, nf, self._dim, first, nf)
         if self.linear_dense is not None:
             c0 = self._sparse_width
-            logit = logit + self.linear_dense(x[:, c0:c0 + self._dense_width])
-        return logit
+            extra = extra + self.linear_dense(x[:, c0:c0 + self._dense_width])
+        return x, extra
+
+    def forward(self, input_feats):
+        x, extra = self._parts(input_feats)
+        return extra + self._run_tower(x)
+
+    def hidden_and_extra(self, input_feats):
+        x, extra = self._parts(input_feats)
+        return self._run_tower(x, stop_before_last=True), extra

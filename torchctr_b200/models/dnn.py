@@ -13,3 +13,8 @@ class DNN(CTRModelBase):
         self._grow_vocabularies(input_feats)
         (x,) = self._lookup_all(input_feats, self.dense_block(input_feats))          # dnn.py:53-67 in one launch
         return self._run_tower(x)                                                     # dnn.py:68
+
+    def hidden_and_extra(self, input_feats):
+        self._grow_vocabularies(input_feats)
+        (x,) = self._lookup_all(input_feats, self.dense_block(input_feats))
+        return self._run_tower(x, stop_before_last=True), None

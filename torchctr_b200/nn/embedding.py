@@ -201,6 +201,17 @@ class _Workspace:
     _retired: list = []
 
 
+_side_streams: dict = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = torch.device(device)
+    st = _side_streams.get(key)
+    if st is None:
+        st = _side_streams[key] = torch.cuda.Stream(device=key)
+    return st
+
+
 class _PooledLookupFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, call, dense, *weights):
@@ -233,6 +244,7 @@ class _LookupCall:
         self.B = entries[0][1].shape[0] if entries else 0
         self.bag_scales = None
         self.status = None
+        self.grad_enabled = torch.is_grad_enabled()   # read outside the autograd Function (inside, grad mode is off)
 
     def _specs(self, tables_data, with_state):
         specs = []
@@ -258,8 +270,20 @@ class _LookupCall:
         call = ops.make_group(self._specs([w.detach() for w in weights], False), B, out, self.stride,
                               dense=dense, dense_col=self.dense_col, zero_from=zero_from, status=self.status)
         ops.emb_pool_fwd(call)
-        if self.plan_link is not None and self.training:     # both linked forwards run before any backward
-            self.plan_link.nbytes = max(self.plan_link.nbytes, ops.emb_bwd_workspace_bytes(call))
+        link = self.plan_link
+        if link is not None and self.training:               # every linked forward runs before any backward
+            need = ops.emb_bwd_workspace_bytes(call)
+            link.nbytes = max(link.nbytes, need)
+            if link.ws is None and self.binding is not None and self.grad_enabled:
+                # The sort depends on the ids only: start it NOW on a side stream, next to the tower's forward and
+                # backward (in a captured CUDA graph: a parallel branch).  It is a chain of small latency-bound
+                # kernels that leaves most of the machine idle, so the overlap is nearly free.
+                link.ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+                side = _side_stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    ops.emb_bwd_plan(call, link.ws, runs=False)
+                link.pending = side
         return out
 
     def run_backward(self, grad_out):
@@ -285,11 +309,13 @@ class _LookupCall:
             # weights next to its embeddings) share one plan per step
             need = ops.emb_bwd_workspace_bytes(call)
             link.nbytes = max(link.nbytes, need)
-            if link.ws is None:
+            if link.pending is not None:                      # the early sort of run_forward
+                torch.cuda.current_stream(dev).wait_stream(link.pending)
+                link.pending = None
+            if link.ws is None or link.ws.numel() < need or (not fused and not link.has_runs):
                 link.ws = torch.empty(max(link.nbytes, need) + 256, dtype=torch.uint8, device=dev)
                 ops.emb_bwd_plan(call, link.ws, runs=not fused)
-            elif link.ws.numel() < need:
-                raise RuntimeError("shared backward plan: workspace too small; call PlanLink.reserve first")
+                link.has_runs = not fused
             ws = link.ws
         if fused:
             ops.emb_bwd_apply(call, ws, self.binding.next_opt())
@@ -334,6 +360,8 @@ class PlanLink:
     def __init__(self, nbytes: int = 0):
         self.ws = None
         self.nbytes = nbytes
+        self.pending = None      # side stream an early sort is running on
+        self.has_runs = False    # the plan in ws lists the runs (needed for unique-row outputs only)
 
 
 def pooled_lookup(entries, dense: torch.Tensor | None = None, binding: SparseOptimizerBinding | None = None,

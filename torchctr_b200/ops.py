@@ -517,3 +517,50 @@ def linear_wgrad(gz: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
         _lib.check(_lib.lib().ctr_linear_wgrad(gz.data_ptr(), gz.stride(0), x.data_ptr(), x.stride(0), B, N, K, out.data_ptr(),
                                                out.stride(0), ws.data_ptr(), ws.numel(), _stream(gz)), "ctr_linear_wgrad")
     return out
+
+
+# ---- logit head + dense optimizer ----------------------------------------------------------------------------------
+def logit_bce_fwd(h, w, bias, extra, labels, want_logits: bool = False):
+    """h [B, H], w [H], bias [1] | None, extra [B, *] | None (column 0), labels [B, *] (column 0)
+    -> (loss [] mean BCE-with-logits, dz [B], logits [B] | None)"""
+    _rows2d(h, "h")
+    B, H = h.shape
+    dev = h.device
+    dz = torch.empty(B, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    logits = torch.empty(B, dtype=torch.float32, device=dev) if want_logits else None
+    with _timed("head_fwd"):
+        _lib.check(_lib.lib().ctr_logit_bce_fwd(h.data_ptr(), h.stride(0), B, H, w.data_ptr(), _lib.ptr(bias), _lib.ptr(extra),
+                                                0 if extra is None else extra.stride(0), labels.data_ptr(), labels.stride(0),
+                                                _lib.ptr(logits), dz.data_ptr(), loss.data_ptr(),
+                                                tower_workspace(dev, H).data_ptr(), _stream(h)), "ctr_logit_bce_fwd")
+    return loss, dz, logits
+
+
+def logit_bce_bwd(h, w, dz, gscale, want_gh: bool, want_gextra: bool):
+    """-> (gh [B, H] | None, gw [H], gb [1], gextra [B, 1] | None) for the upstream scalar gradient ``gscale`` (device)."""
+    B, H = h.shape
+    dev = h.device
+    gh = torch.empty(B, H, dtype=torch.float32, device=dev) if want_gh else None
+    gw = torch.empty(H, dtype=torch.float32, device=dev)
+    gb = torch.empty(1, dtype=torch.float32, device=dev)
+    gextra = torch.empty(B, 1, dtype=torch.float32, device=dev) if want_gextra else None
+    with _timed("head_bwd"):
+        _lib.check(_lib.lib().ctr_logit_bce_bwd(h.data_ptr(), h.stride(0), B, H, w.data_ptr(), dz.data_ptr(), gscale.data_ptr(),
+                                                _lib.ptr(gh), 0 if gh is None else gh.stride(0), gw.data_ptr(), gb.data_ptr(),
+                                                _lib.ptr(gextra), 1, tower_workspace(dev, H).data_ptr(), _stream(h)),
+                   "ctr_logit_bce_bwd")
+    return gh, gw, gb, gextra
+
+
+def dense_adagrad(params, grads, sums, lr: float, eps: float) -> None:
+    """One launch of torch.optim.Adagrad's update (lr_decay = weight_decay = 0) over up to 48 dense fp32 tensors."""
+    n = len(params)
+    if n == 0:
+        return
+    pa = (C.c_void_p * n)(*[p.data_ptr() for p in params])
+    ga = (C.c_void_p * n)(*[g.data_ptr() for g in grads])
+    sa = (C.c_void_p * n)(*[s.data_ptr() for s in sums])
+    na = (C.c_int64 * n)(*[p.numel() for p in params])
+    with _timed("dense_adagrad"):
+        _lib.check(_lib.lib().ctr_dense_adagrad(n, pa, ga, sa, na, lr, eps, _stream(params[0])), "ctr_dense_adagrad")

@@ -224,6 +224,8 @@ class PeerShardedTables(nn.Module):
         self.opt_state0 = [None] * len(self.dims)
         self.opt_state1 = [None] * len(self.dims)
         self.bindings = [None] * len(self.dims)
+        self._side = None           # side stream of the owner bucketing
+        self._route_pending = False
         self._B = None              # batch geometry the peer buffers were sized for
         self._route_ws = None
         self._plan_ws = None
@@ -323,12 +325,20 @@ class PeerShardedTables(nn.Module):
             ops.emb_pool_fwd_sharded(call, self._shard_struct, self._table_ptrs[w])
             outs.append(out)
         if self.training:
+            # bucketing the slots by owner is only needed by the backward: it runs on a side stream next to the
+            # tower (inside a captured CUDA graph this becomes a parallel branch)
             call = ops.make_group(self._request_specs(ids_list, 0), B, None, self.num_features * self.dims[0], status=status)
             need = ops.route_p2p_workspace_bytes(call)
             if self._route_ws is None or self._route_ws.numel() < need:
                 self._route_ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=dev)
+            main = torch.cuda.current_stream(dev)
+            self._side.wait_stream(main)
             rp = self._route_buf.ptr
-            ops.route_p2p_build(call, self._shard_struct, rp, rp + 256, rp + 256 + 4 * max(self._S, 1), self._route_ws)
+            with torch.cuda.stream(self._side):
+                ops.route_p2p_build(call, self._shard_struct, rp, rp + 256, rp + 256 + 4 * max(self._S, 1), self._route_ws)
+            self._route_pending = True
         self.status = status
         return outs
 
@@ -338,6 +348,9 @@ class PeerShardedTables(nn.Module):
         ids_list = self._ids
         B = ids_list[0].shape[0]
         live = [w for w, g in enumerate(grad_outs) if g is not None]
+        if self._route_pending:                          # the routing lists must be complete before the barrier
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+            self._route_pending = False
         for w in live:                                   # gradients into the peer-visible buffers
             g = grad_outs[w]
             self._grad_bufs[w].tensor(torch.float32, (B, self._strides[w])).copy_(g)
