@@ -275,6 +275,8 @@ def run_ours(args):
     if world > 1:
         model = shard_model(model, None, device=dev)    # keep this rank's rows of every table, drop the rest
     model = model.to(dev).train()
+    if world > 1:
+        model.enable_flat_dense_grads()                   # dense gradients live in one buffer: all-reduce without cat / copies
     from torchctr_b200.optim import FusedAdagrad
     opt = FusedAdagrad(model.dense_parameters(), lr=LR)           # torch.optim.Adagrad arithmetic, one launch; tables take the fused row update
     model.bind_optimizer(opt, kind="adagrad")
@@ -285,7 +287,10 @@ def run_ours(args):
     h2d = batch_bytes(host[0])
 
     def eager_step(batch, i):
-        opt.zero_grad(set_to_none=True)
+        if world > 1:
+            model.zero_dense_grads()
+        else:
+            opt.zero_grad(set_to_none=True)
         loss = model.training_step(batch, i)
         if world > 1:
             (loss / world).backward()                   # tables: all-to-all of gradients + owner-side fused update
@@ -317,7 +322,8 @@ def run_ours(args):
         def sharded_backward(loss):                      # tables: owners pull gradients over NVLink; tower: all-reduce
             (loss / world).backward()
             model.reduce_dense_grads()
-        graphed = GraphedTrainStep(model, opt, resident[0], warmup=1, backward_fn=sharded_backward if world > 1 else None)
+        graphed = GraphedTrainStep(model, opt, resident[0], warmup=1, backward_fn=sharded_backward if world > 1 else None,
+                                   zero_grad_fn=model.zero_dense_grads if world > 1 else None)
         launches_per_step = (ops.kernel_launches() - l0) // 2      # one eager warm-up + one captured step
         step = lambda batch, i: graphed(batch)           # noqa: E731
 

@@ -15,10 +15,11 @@ import torch
 
 
 class GraphedTrainStep:
-    def __init__(self, model, optimizer, example_batch, warmup: int = 3, backward_fn=None):
+    def __init__(self, model, optimizer, example_batch, warmup: int = 3, backward_fn=None, zero_grad_fn=None):
         """``backward_fn(loss)`` replaces ``loss.backward()`` (multi-GPU: scale by 1 / world, all-reduce the
         replicated gradients -- NCCL collectives are captured with the rest of the step)."""
         self._backward_fn = backward_fn
+        self._zero_grad_fn = zero_grad_fn        # replaces optimizer.zero_grad(set_to_none=True), e.g. flat gradient buffers
         feats, labels = example_batch
         self.model, self.optimizer = model, optimizer
         dev = next(model.parameters()).device
@@ -61,7 +62,10 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
 
     def _eager_step(self):
-        self.optimizer.zero_grad(set_to_none=True)
+        if self._zero_grad_fn is not None:
+            self._zero_grad_fn()
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
         loss = self.model.training_step((self.static_feats, self.static_labels), 0)
         if self._backward_fn is not None:
             self._backward_fn(loss)

@@ -112,6 +112,28 @@ class CTRModelBase(nn.Module):
         skip = {id(p) for p in self.table_parameters()}
         return [p for p in self.parameters() if id(p) not in skip]
 
+    def enable_flat_dense_grads(self):
+        """Make the ``.grad`` of every dense parameter a view of ONE flat buffer (as DDP's buckets do): the multi-GPU
+        all-reduce then needs no concatenation / copy-back.  Use ``zero_dense_grads()`` instead of
+        ``optimizer.zero_grad(set_to_none=True)`` afterwards, which would drop the views."""
+        params = [p for p in self.dense_parameters() if p.requires_grad]
+        total = sum(p.numel() for p in params)
+        flat = torch.zeros(total, dtype=torch.float32, device=params[0].device)
+        off = 0
+        for p in params:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self._flat_dense_grad = flat
+        return flat
+
+    def zero_dense_grads(self):
+        flat = getattr(self, "_flat_dense_grad", None)
+        if flat is None:
+            for p in self.dense_parameters():
+                p.grad = None
+        else:
+            flat.zero_()
+
     @staticmethod
     def dense_block(feats):
         parts = []
@@ -152,7 +174,10 @@ class CTRModelBase(nn.Module):
                 lin = layers[i]
                 pad = h.shape[1] - lin.in_features
                 w = F.pad(lin.weight, (0, pad)) if pad else None      # first layer: 4-float-padded lookup output
-                h = tower_block(h, lin, layers[i + 1], layers[i + 3], seed, block, weight=w)
+                # sharded tables: let the first block write dL/dx straight into the peer-visible gradient matrix
+                provider = getattr(self._sharded, "grad_buffer_provider", None) if block == 0 else None
+                h = tower_block(h, lin, layers[i + 1], layers[i + 3], seed, block, weight=w,
+                                gx_provider=provider(0) if provider is not None else None)
                 i += 4
                 block += 1
             if i > 0:

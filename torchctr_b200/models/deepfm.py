@@ -3,6 +3,7 @@
     logit = sum_f w1_f[id] + Linear(dense) + FM2(v) + tower(concat(v, dense))."""
 from __future__ import annotations
 
+import torch
 import torch.nn as nn
 
 from ..nn.embedding import EmbeddingTable, PooledLookupGroup
@@ -36,8 +37,9 @@ class DeepFM(CTRModelBase):
         nf = len(self._names)
         x, extra = fm_interaction_passthrough(x, nf, self._dim, first, nf)
         if self.linear_dense is not None:
-            c0 = self._sparse_width
-            extra = extra + self.linear_dense(x[:, c0:c0 + self._dense_width])
+            # the dense block itself, not the slice of x: same numbers, but no third gradient stream into x (autograd
+            # would sum it with the tower's out of place: a zero-fill and an add over [B, F*D + Nd] per step)
+            extra = extra + self.linear_dense(dense.to(x.device, dtype=torch.float32, non_blocking=True))
         return x, extra
 
     def forward(self, input_feats):

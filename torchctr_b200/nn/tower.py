@@ -20,7 +20,7 @@ from .linear import tc_eligible, wgrad_eligible
 
 class _TowerBlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, bn, p_drop, seed_dev, layer_id, use_tc):
+    def forward(ctx, x, weight, bias, gamma, beta, bn, p_drop, seed_dev, layer_id, use_tc, gx_provider=None):
         w = weight.contiguous()
         tc = bool(use_tc and tc_eligible(x, w))
         z = ops.linear_fwd(x, w, bias) if tc else torch.addmm(bias, x, w.t())
@@ -30,6 +30,7 @@ class _TowerBlockFn(torch.autograd.Function):
         y = ops.bn_relu_dropout_fwd(z, mean, rstd, gamma, beta, p_drop, seed_dev, layer_id)
         ctx.save_for_backward(x, w, z, mean, rstd, gamma, beta)
         ctx.meta = (p_drop, seed_dev, layer_id, tc)
+        ctx.gx_provider = gx_provider
         return y
 
     @staticmethod
@@ -41,10 +42,14 @@ class _TowerBlockFn(torch.autograd.Function):
         gz, dgamma, dbeta, dbias = ops.bn_relu_dropout_bwd(gy, z, mean, rstd, gamma, beta, p_drop, seed_dev, layer_id)
         gx = gw = None
         if ctx.needs_input_grad[0]:
-            gx = ops.linear_fwd(gz, w.t().contiguous()) if tc else gz @ w
+            # gx_provider: a buffer the caller wants dL/dx in (the peer-visible gradient matrix of the sharded tables)
+            out = ctx.gx_provider() if (tc and ctx.gx_provider is not None) else None
+            if out is not None and tuple(out.shape) != tuple(x.shape):
+                out = None
+            gx = ops.linear_fwd(gz, w.t().contiguous(), out=out) if tc else gz @ w
         if ctx.needs_input_grad[1]:
             gw = ops.linear_wgrad(gz, x) if tc and wgrad_eligible(gz, x) else gz.t() @ x
-        return gx, gw, dbias, dgamma, dbeta, None, None, None, None, None
+        return gx, gw, dbias, dgamma, dbeta, None, None, None, None, None, None
 
 
 def block_is_fusable(linear, bn, act, drop) -> bool:
@@ -53,9 +58,10 @@ def block_is_fusable(linear, bn, act, drop) -> bool:
             and linear.out_features % 4 == 0 and 4 <= linear.out_features <= 1024)
 
 
-def tower_block(x, linear: nn.Linear, bn: nn.BatchNorm1d, drop: nn.Dropout, seed_dev, layer_id: int, weight=None):
+def tower_block(x, linear: nn.Linear, bn: nn.BatchNorm1d, drop: nn.Dropout, seed_dev, layer_id: int, weight=None,
+                gx_provider=None):
     """Training-mode forward of [linear, bn, ReLU, drop] on a CUDA tensor.  ``weight`` overrides ``linear.weight``
     (the first layer reads a zero-padded copy, see ``CTRModelBase._first_linear``)."""
     w = linear.weight if weight is None else weight
     return _TowerBlockFn.apply(x, w, linear.bias, bn.weight, bn.bias, bn, float(drop.p), seed_dev, layer_id,
-                               torch.backends.cuda.matmul.allow_tf32)
+                               torch.backends.cuda.matmul.allow_tf32, gx_provider)

@@ -39,5 +39,12 @@ def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=
         for n in list(g.tables.keys()):
             del g.tables[n]
     model._pg = pg
-    model.reduce_dense_grads = lambda: reduce_dense_grads(model.dense_parameters(), pg)
+    def _reduce():
+        flat = getattr(model, "_flat_dense_grad", None)
+        if flat is not None:                    # one all-reduce over the flat gradient buffer, nothing to copy
+            import torch.distributed as dist
+            dist.all_reduce(flat, group=pg)
+        else:
+            reduce_dense_grads(model.dense_parameters(), pg)
+    model.reduce_dense_grads = _reduce
     return model

@@ -353,7 +353,8 @@ class PeerShardedTables(nn.Module):
             self._route_pending = False
         for w in live:                                   # gradients into the peer-visible buffers
             g = grad_outs[w]
-            self._grad_bufs[w].tensor(torch.float32, (B, self._strides[w])).copy_(g)
+            if g.data_ptr() != self._grad_bufs[w].ptr:   # (the tower's first block may have written it in place)
+                self._grad_bufs[w].tensor(torch.float32, (B, self._strides[w])).copy_(g)
         self.transport.barrier()                         # every rank's routing lists and gradients are in place
         plan_call = ops.make_group(self._owner_specs(ids_list, 0, False), B, None, self._strides[0])
         need = ops.emb_bwd_p2p_workspace_bytes(plan_call, self.world)
@@ -368,6 +369,15 @@ class PeerShardedTables(nn.Module):
             call = ops.make_group(self._owner_specs(ids_list, w, True), B, None, self._strides[w])
             ops.emb_bwd_apply_p2p(call, self._shard_struct, self._plan_ws, bind.next_opt(), self._peer_grads[w])
         self.transport.barrier()                         # nobody overwrites lists / gradients / reads rows too early
+
+    def grad_buffer_provider(self, w):
+        """A callable returning this rank's peer-visible gradient matrix of width ``w`` as a tensor [B, stride]: whoever
+        produces dL/d(pooled output) may write it there directly and hand it back through autograd."""
+        def provider():
+            if self._B is None:
+                return None
+            return self._grad_bufs[w].tensor(torch.float32, (self._B[0], self._strides[w]))
+        return provider
 
     # ---- inspection (tests, checkpoints): this rank's rows of table f, width w ------------------------------------------
     def local_rows_of(self, w, f):
