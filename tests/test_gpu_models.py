@@ -295,12 +295,17 @@ def test_graphed_train_step_equals_eager(opt_name):
     # the constructor runs `warmup` real steps on the example batch before capturing
     graphed = GraphedTrainStep(b, ob, batches[0], warmup=1)
     oa.zero_grad(); a.training_step(batches[0], 0).backward(); oa.step()
+    pinned = [({k: v.pin_memory() for k, v in f.items()}, l.pin_memory()) for f, l in batches]
     for i, batch in enumerate(batches):
         oa.zero_grad()
         la = a.training_step(batch, i)
         la.backward()
         oa.step()
-        lb = graphed(batch)
+        if i >= 2:                                   # the input-prefetch path: copy on a side stream, then one D2D move
+            graphed.prefetch(pinned[i])
+            lb = graphed(pinned[i])
+        else:
+            lb = graphed(batch)
         close(lb, la, 1e-5)
     sa, sb = a.state_dict(), b.state_dict()
     for k in sa:
