@@ -19,7 +19,9 @@ def _close(got, ref):
     return float((got - ref).abs().max()) <= RTOL * max(float(ref.abs().max()), 1e-30)
 
 
-def _problem(world, seed=5):
+def _problem(world, seed=5, hashed=False):
+    """``hashed``: tables 1 and 4 take RAW ids and bucket them with murmur3 inside the kernels (BASELINE config 4:
+    hash-embedding tables row-sharded over the GPUs); the oracle works on the bucketed rows."""
     gen = torch.Generator().manual_seed(seed)
     Vs, Ls, D, B = [37, 101, 2, 1000, 5000], [1, 6, 1, 3, 1], 16, 300
     full16 = [torch.randn(v, D, generator=gen) for v in Vs]
@@ -37,7 +39,22 @@ def _problem(world, seed=5):
         g16_all.append(torch.randn(B, len(Vs) * D + 4, generator=gen))
         g1_all.append(torch.randn(B, 8, generator=gen))
     dense = torch.randn(B, 3, generator=gen)
-    return Vs, Ls, D, B, full16, full1, ids_all, g16_all, g1_all, dense
+    raw_all = None
+    if hashed:
+        from oracle import hashing as oh
+        raw_all = []
+        for r in range(world):
+            raw = [t.clone() for t in ids_all[r]]
+            for f in (1, 4):
+                rid = torch.randint(0, 2 ** 40, ids_all[r][f].shape, generator=gen)
+                rid[:, 0] = torch.randint(0, 5, (B,), generator=gen)                   # hot raw ids
+                rid[ids_all[r][f] < 0] = -100
+                rows = torch.from_numpy(oh.hash_bucket_ids(rid.clamp(min=0).numpy(), Vs[f], 7 + f)).long()
+                rows[rid < 0] = -100
+                raw[f] = rid
+                ids_all[r][f] = rows                                                   # what the oracle indexes with
+            raw_all.append(raw)
+    return Vs, Ls, D, B, full16, full1, ids_all, g16_all, g1_all, dense, raw_all
 
 
 def _rank_main(rank, world, shared, prob, kind, errors, steps):
@@ -45,16 +62,18 @@ def _rank_main(rank, world, shared, prob, kind, errors, steps):
         from oracle import embedding as oe
         from torchctr_b200.nn.embedding import EmbeddingTable
         from torchctr_b200.parallel.peer import PeerShardedTables, ThreadTransport, owned_rows
-        Vs, Ls, D, B, full16, full1, ids_all, g16_all, g1_all, dense = prob
+        Vs, Ls, D, B, full16, full1, ids_all, g16_all, g1_all, dense, raw_all = prob
+        hashed = raw_all is not None
         dev = torch.device("cuda", 0)
         tr = ThreadTransport(shared, rank, dev)
         names = [f"f{i}" for i in range(len(Vs))]
-        tabs16 = [EmbeddingTable(v, D, _weight=w.clone()) for v, w in zip(Vs, full16)]
-        tabs1 = [EmbeddingTable(v, 1, _weight=w.clone()) for v, w in zip(Vs, full1)]
+        kw = [dict(index_kind="hash", hash_seed=7 + f) if hashed and f in (1, 4) else {} for f in range(len(Vs))]
+        tabs16 = [EmbeddingTable(v, D, _weight=w.clone(), **k) for v, w, k in zip(Vs, full16, kw)]
+        tabs1 = [EmbeddingTable(v, 1, _weight=w.clone(), **k) for v, w, k in zip(Vs, full1, kw)]
         st = PeerShardedTables(names, [tabs16, tabs1], tr, dev).train()
         opt = torch.optim.SGD(list(st.shards), lr=0.5) if kind == "sgd" else torch.optim.Adagrad(list(st.shards), lr=0.5)
         st.bind_optimizer(opt, kind=kind)
-        feats = {n: t for n, t in zip(names, ids_all[rank])}
+        feats = {n: t for n, t in zip(names, raw_all[rank] if hashed else ids_all[rank])}
         w16 = [w.clone() for w in full16]
         w1 = [w.clone() for w in full1]
         acc16 = [torch.zeros_like(w) for w in full16]
@@ -110,14 +129,14 @@ def _rank_main(rank, world, shared, prob, kind, errors, steps):
             pass
 
 
-@pytest.mark.parametrize("world,kind", [(2, "sgd"), (3, "sgd"), (4, "adagrad")])
-def test_peer_sharded_threads(world, kind):
+@pytest.mark.parametrize("world,kind,hashed", [(2, "sgd", False), (3, "sgd", False), (4, "adagrad", False), (3, "adagrad", True)])
+def test_peer_sharded_threads(world, kind, hashed):
     import faulthandler
     import sys
     from torchctr_b200.parallel.peer import ThreadTransport
     faulthandler.dump_traceback_later(100, exit=True, file=sys.stderr)      # a stuck rank must not hang the suite
     shared = ThreadTransport.Shared(world)
-    prob = _problem(world)
+    prob = _problem(world, hashed=hashed)
     errors = []
     threads = [threading.Thread(target=_rank_main, args=(r, world, shared, prob, kind, errors, 2)) for r in range(world)]
     for t in threads:
