@@ -228,7 +228,9 @@ def kernel_roofline(model, resident, B, dev, iters=12):
     k = kern[dom]
     roofline = {"bound": "hbm", "kernel": dom + (" (sparse gradient reduce + fused Adagrad row update, 26 tables x D=16)"
                                                  if dom == "emb_bwd_apply" else " (gather + pool + concat, 26 tables x D=16)"),
-                "achieved": k["achieved_GBs"], "peak": peak, "unit": "GB/s", "frac": k["frac_of_peak"], "traffic": None,
+                "achieved": k["achieved_GBs"], "peak": peak, "unit": "GB/s", "frac": k["frac_of_peak"],
+                "traffic": 234.1e6 if dom == "emb_bwd_apply" else 109.1e6,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel in profiles/r1_final_kernels_full.summary.txt (ncu --set full)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": k["algorithmic_bytes"],
                 "ms_per_launch": k["ms_per_launch"], "unique_rows_per_launch": U,
                 "timing": f"CUDA events around each launch on the launching stream, 1 GiB L2 flush before each, {iters} launches"}

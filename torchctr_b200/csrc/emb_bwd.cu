@@ -548,12 +548,14 @@ __global__ void __launch_bounds__(kApplyThreads, 3)
             const uint32_t mid = (lo + hi) >> 1;
             if (a.keys[(mid + 1) * a.range - 1] >= first_key) hi = mid; else lo = mid + 1;
         }
-        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (uint32_t j = lo + team; j < w; j += P) {
+        // wait until every range the run passed through has published, fence ONCE, then read the partial sums
+        for (uint32_t j = lo + lane; j < w; j += kWarp)
             while (ld_relaxed_u32(a.range_flags + j) == 0u) { }
-            __threadfence();
+        __syncwarp();
+        __threadfence();
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t j = lo + team; j < w; j += P)
             add4(sum, __ldcg(reinterpret_cast<const float4 *>(a.tail_part + (size_t)j * a.row_floats) + t));
-        }
         for (int off = TG; off < kWarp; off <<= 1) {
             float4 o;
             o.x = __shfl_xor_sync(kFull, sum.x, off); o.y = __shfl_xor_sync(kFull, sum.y, off);
@@ -711,7 +713,7 @@ static int apply_impl(DevGroup &dg, const PlanLayout &p, void *workspace, const 
     const int P = kWarp / team;
     const int U = P >= 8 ? (kWarp / P < 4 ? kWarp / P : 4) : 4;
     const int Q = P * U;
-    const int64_t target_ranges = (int64_t)kNumSMs * 24 * 3;
+    const int64_t target_ranges = (int64_t)kNumSMs * 24 * 2;   // ~2 waves of resident warps: longer ranges = fewer boundary fences
     int64_t range = (expected + target_ranges - 1) / target_ranges;
     range = (range + Q - 1) / Q * Q;
     const int64_t lo = kMinRange > Q ? kMinRange : Q;
