@@ -275,7 +275,8 @@ def run_ours(args):
         from torchctr_b200.parallel import shard_model
     model = DeepFM(fc, HIDDEN)                            # identical on every rank (same seed)
     if world > 1:
-        model = shard_model(model, None, device=dev)    # keep this rank's rows of every table, drop the rest
+        dedup = {"auto": None, "on": True, "off": False}[args.dedup]
+        model = shard_model(model, None, device=dev, dedup=dedup)    # keep this rank's rows of every table, drop the rest
     model = model.to(dev).train()
     if world > 1:
         model.enable_flat_dense_grads()                   # dense gradients live in one buffer: all-reduce without cat / copies
@@ -398,7 +399,9 @@ def run_ours(args):
         "roofline": roofline,
         "parallelism": "single GPU" if world == 1 else f"tables row-sharded over {world} GPUs (owner = (row + table) mod P); rows read "
                        "and gradients pulled through NVLink peer mappings inside the lookup / update kernels (no all-to-all), "
-                       "batch data-parallel, tower replicated + one NCCL all-reduce",
+                       "batch data-parallel, tower replicated + one NCCL all-reduce"
+                       + ("; requester-side de-duplication: every distinct row crosses NVLink once per direction"
+                          if getattr(getattr(model, "_sharded", None), "dedup", False) else ""),
         "clocks": clock_info,
         "tower_matmul": "torch F.linear, TF32 tensor cores, fp32 accumulate",
     }
@@ -451,6 +454,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--roofline-only", action="store_true", help="only time the embedding entry points (ncu target)")
+    ap.add_argument("--dedup", default="auto", choices=["auto", "on", "off"],
+                    help="N > 1: fetch / send every distinct row once (auto: from 4 GPUs on)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -324,6 +324,25 @@ int ctr_emb_bwd_plan_p2p(const ctr_group_t *group, const ctr_shard_t *shard, con
 int ctr_emb_bwd_apply_p2p(const ctr_group_t *group, const ctr_shard_t *shard, void *workspace, const ctr_opt_t *opt,
                           const float *const *peer_grads, int64_t *num_unique, void *stream);
 
+/* ---- de-duplicated exchange (every distinct row of a rank's batch crosses NVLink once per direction) -----------
+ * Requester, forward: plan the group with ctr_emb_bwd_plan (runs listed), then ctr_unique_fetch copies the row of every
+ * run from its owner into staging[run, :] (f32 [S, D]) and, when uidx != NULL, writes uidx[slot] = run (i64 [S],
+ * feature-major slots, -1 = padding): a pooled lookup over `staging` with `uidx` as ids gives the pooled output.
+ * Requester, backward: ctr_emb_bwd_apply with CTR_OPT_NONE on the same plan leaves uniq_feature / uniq_row /
+ * row_grad [U, D] / num_unique in peer-visible buffers.
+ * Owner: ctr_emb_bwd_plan_p2p_unique turns every rank's (feature, row) list into (row key | invalid, rank:index) pairs
+ * and sorts them (count on the device, capacity = world * S pairs); ctr_emb_bwd_apply_p2p_unique reduces and updates,
+ * reading gradient row `index` of peer_row_grads[rank] (f32 [S, group->out_stride]).  The owner group has L = 1,
+ * out_col = 0, tables = this rank's shard slices. */
+int ctr_unique_fetch(const ctr_group_t *group, const ctr_shard_t *shard, const float *const *tables, void *plan_workspace,
+                     float *staging, int64_t *uidx, void *stream);
+int64_t ctr_emb_bwd_p2p_unique_workspace_bytes(const ctr_group_t *group, int64_t capacity);
+int ctr_emb_bwd_plan_p2p_unique(const ctr_group_t *group, const ctr_shard_t *shard, const int64_t *const *peer_num_unique,
+                                const int32_t *const *peer_uniq_feature, const int32_t *const *peer_uniq_row, int64_t capacity,
+                                void *workspace, int64_t workspace_bytes, void *stream);
+int ctr_emb_bwd_apply_p2p_unique(const ctr_group_t *group, const ctr_shard_t *shard, void *workspace, const ctr_opt_t *opt,
+                                 const float *const *peer_row_grads, int64_t capacity, int64_t *num_unique, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

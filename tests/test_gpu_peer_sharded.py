@@ -57,7 +57,7 @@ def _problem(world, seed=5, hashed=False):
     return Vs, Ls, D, B, full16, full1, ids_all, g16_all, g1_all, dense, raw_all
 
 
-def _rank_main(rank, world, shared, prob, kind, errors, steps):
+def _rank_main(rank, world, shared, prob, kind, errors, steps, dedup=False):
     try:
         from oracle import embedding as oe
         from torchctr_b200.nn.embedding import EmbeddingTable
@@ -70,7 +70,7 @@ def _rank_main(rank, world, shared, prob, kind, errors, steps):
         kw = [dict(index_kind="hash", hash_seed=7 + f) if hashed and f in (1, 4) else {} for f in range(len(Vs))]
         tabs16 = [EmbeddingTable(v, D, _weight=w.clone(), **k) for v, w, k in zip(Vs, full16, kw)]
         tabs1 = [EmbeddingTable(v, 1, _weight=w.clone(), **k) for v, w, k in zip(Vs, full1, kw)]
-        st = PeerShardedTables(names, [tabs16, tabs1], tr, dev).train()
+        st = PeerShardedTables(names, [tabs16, tabs1], tr, dev, dedup=dedup).train()
         opt = torch.optim.SGD(list(st.shards), lr=0.5) if kind == "sgd" else torch.optim.Adagrad(list(st.shards), lr=0.5)
         st.bind_optimizer(opt, kind=kind)
         feats = {n: t for n, t in zip(names, raw_all[rank] if hashed else ids_all[rank])}
@@ -129,8 +129,9 @@ def _rank_main(rank, world, shared, prob, kind, errors, steps):
             pass
 
 
-@pytest.mark.parametrize("world,kind,hashed", [(2, "sgd", False), (3, "sgd", False), (4, "adagrad", False), (3, "adagrad", True)])
-def test_peer_sharded_threads(world, kind, hashed):
+@pytest.mark.parametrize("world,kind,hashed,dedup", [(2, "sgd", False, False), (3, "sgd", False, False), (4, "adagrad", False, False),
+                                                     (3, "adagrad", True, False), (2, "sgd", False, True), (4, "adagrad", True, True)])
+def test_peer_sharded_threads(world, kind, hashed, dedup):
     import faulthandler
     import sys
     from torchctr_b200.parallel.peer import ThreadTransport
@@ -138,7 +139,7 @@ def test_peer_sharded_threads(world, kind, hashed):
     shared = ThreadTransport.Shared(world)
     prob = _problem(world, hashed=hashed)
     errors = []
-    threads = [threading.Thread(target=_rank_main, args=(r, world, shared, prob, kind, errors, 2)) for r in range(world)]
+    threads = [threading.Thread(target=_rank_main, args=(r, world, shared, prob, kind, errors, 2, dedup)) for r in range(world)]
     for t in threads:
         t.start()
     for t in threads:

@@ -124,6 +124,12 @@ _SIGNATURES = {
     "ctr_emb_bwd_p2p_workspace_bytes": (C.c_int64, [C.POINTER(Group), C.c_int32]),
     "ctr_emb_bwd_plan_p2p": (C.c_int, [C.POINTER(Group), C.POINTER(Shard), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                        C.POINTER(C.c_void_p), _P, C.c_int64, _P]),
+    "ctr_unique_fetch": (C.c_int, [C.POINTER(Group), C.POINTER(Shard), C.POINTER(C.c_void_p), _P, _P, _P, _P]),
+    "ctr_emb_bwd_p2p_unique_workspace_bytes": (C.c_int64, [C.POINTER(Group), C.c_int64]),
+    "ctr_emb_bwd_plan_p2p_unique": (C.c_int, [C.POINTER(Group), C.POINTER(Shard), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                              C.POINTER(C.c_void_p), C.c_int64, _P, C.c_int64, _P]),
+    "ctr_emb_bwd_apply_p2p_unique": (C.c_int, [C.POINTER(Group), C.POINTER(Shard), _P, C.POINTER(Opt), C.POINTER(C.c_void_p),
+                                               C.c_int64, _P, _P]),
     "ctr_emb_bwd_apply_p2p": (C.c_int, [C.POINTER(Group), C.POINTER(Shard), _P, C.POINTER(Opt), C.POINTER(C.c_void_p), _P, _P]),
 }
 

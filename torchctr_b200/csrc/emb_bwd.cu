@@ -32,7 +32,7 @@ struct PlanLayout {
     int key_bits;
     int sorted_in_b;     // which ping-pong buffer holds the sorted pairs
     // offsets in bytes from the workspace base
-    int64_t counters, keys_a, keys_b, vals_a, vals_b, counts, spine, run_start;
+    int64_t counters, keys_a, keys_b, vals_a, vals_b, counts, spine, run_start, run_of_pos;
     // apply-time scratch (rebuilt by every apply; sized by the group being applied)
     int64_t range_flags, tail_part, max_ranges, row_floats, total;
 };
@@ -44,8 +44,9 @@ constexpr int kMetaSrc = 8, kMetaDst = 24, kMetaCnt = 40;   // u32 [CTR_MAX_WORL
 
 static int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
 
-// scale > 1: owner side of the sharded backward, where up to `scale` ranks' slots can land on this rank
-static PlanLayout plan_layout(const DevGroup &g, int scale = 1) {
+// scale > 1: owner side of the sharded backward, where up to `scale` ranks' slots can land on this rank;
+// capacity > 0: the pair capacity is given outright (owner side of the de-duplicated exchange)
+static PlanLayout plan_layout(const DevGroup &g, int scale = 1, int64_t capacity = 0) {
     PlanLayout p{};
     int64_t S = 0;
     uint64_t rows = 0;
@@ -54,6 +55,7 @@ static PlanLayout plan_layout(const DevGroup &g, int scale = 1) {
         rows += g.f[i].num_rows;
     }
     S *= scale;
+    if (capacity > 0) S = capacity;
     p.S = S;
     int bits = 0;
     while ((rows >> bits) != 0) ++bits;  // bit_length(rows): 2^bits - 1 > every valid key
@@ -71,6 +73,7 @@ static PlanLayout plan_layout(const DevGroup &g, int scale = 1) {
     const int64_t spine = scan_spine_elems(counts > S ? counts : S) + 8;
     p.spine = off; off = align256(off + spine * 4);
     p.run_start = off; off = align256(off + (S + 2) * 4);
+    p.run_of_pos = off; off = align256(off + (S + 1) * 4);
     p.row_floats = 128;   // one float4 per lane of a full warp: any team width fits
     p.max_ranges = S / kMinRange + 2;
     p.range_flags = off; off = align256(off + (p.max_ranges + 64) * 4);   // 64 words of header: [0] = range ticket
@@ -644,7 +647,7 @@ extern "C" int ctr_emb_bwd_plan_ex(const ctr_group_t *group, void *workspace, in
     if (!want_runs) return CTR_OK;
     const uint32_t *sorted_keys = p.sorted_in_b ? keys_b : keys_a;
     return find_runs(sorted_keys, p.S, reinterpret_cast<uint32_t *>(ws + p.run_start), counters,
-                     reinterpret_cast<uint32_t *>(ws + p.spine), stream);
+                     reinterpret_cast<uint32_t *>(ws + p.spine), stream, reinterpret_cast<uint32_t *>(ws + p.run_of_pos));
 }
 
 extern "C" int ctr_emb_bwd_plan(const ctr_group_t *group, void *workspace, int64_t workspace_bytes, void *stream) {
@@ -912,5 +915,294 @@ extern "C" int ctr_emb_bwd_apply_p2p(const ctr_group_t *group, const ctr_shard_t
         f.aligned = al ? 1 : 0;
     }
     return apply_impl(dg, plan_layout(dg, shard->world), workspace, opt, nullptr, nullptr, nullptr, 0, num_unique, peer_grads,
+                      shard->world, (cudaStream_t)stream_);
+}
+
+// ---- de-duplicated exchange: every rank fetches / sends each distinct row of its batch once ------------------------
+// Zipf ids repeat: 1.7 M slots of a Criteo batch touch 0.28 M distinct rows, and peer reads are not cached in L2, so
+// the plain sharded lookup pays NVLink for every repeat.  Here the requester sorts its slots first (the same plan the
+// single-GPU backward uses), fetches every distinct row ONCE into a local staging matrix and pools from there;
+// backward, it reduces its own duplicates locally (the sweep in NONE mode) and the owners pull one gradient row per
+// (rank, distinct row) instead of one per slot.
+namespace ctr {
+
+struct FetchArgs {
+    const uint32_t *keys, *vals, *run_start, *run_of_pos, *counters;
+    float *staging;       // [S, D]
+    long long *uidx;      // [S] or null: slot (feature-major, bag * L + l) -> run
+    uint32_t S;
+};
+
+// one team of G lanes per run: the row of that run, read from its owner's shard; four runs in flight per team (peer
+// loads take ~2 us, the only way to fill NVLink is to have many of them outstanding)
+__global__ void __launch_bounds__(256) uniq_fetch_kernel(const __grid_constant__ DevGroup g, const FetchArgs a) {
+    const DevFeature &f0 = g.f[0];
+    const int G = f0.G, vec = f0.vec, D = f0.D;
+    const int t = threadIdx.x % G;
+    const uint32_t teams = gridDim.x * (blockDim.x / G);
+    const uint32_t U = a.counters[1];                      // runs with a valid key
+    if (t * vec >= D) return;
+    for (uint32_t r0 = (blockIdx.x * (blockDim.x / G) + threadIdx.x / G) * 4u; r0 < U; r0 += teams * 4u) {
+        const float *src[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            src[j] = nullptr;
+            if (r0 + j < U) {
+                const uint32_t key = a.keys[a.run_start[r0 + j]];
+                int lo = 0, hi = g.num_features - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (g.f[mid].row_base <= key) lo = mid; else hi = mid - 1;
+                }
+                src[j] = table_row(g, g.f[lo], lo, (int32_t)(key - g.f[lo].row_base));
+            }
+        }
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (src[j] != nullptr) {
+                if (vec == 4) v[j] = __ldg(reinterpret_cast<const float4 *>(src[j]) + t);
+                else v[j].x = __ldg(src[j] + t);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (src[j] != nullptr) {
+                float *dst = a.staging + (size_t)(r0 + j) * D;
+                if (vec == 4) reinterpret_cast<float4 *>(dst)[t] = v[j];
+                else dst[t] = v[j].x;
+            }
+        }
+    }
+}
+
+// slot -> run, for every valid sorted position (uidx was pre-filled with -1 = padding)
+__global__ void __launch_bounds__(256) slot_uidx_kernel(const __grid_constant__ DevGroup g, const FetchArgs a) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < a.S; p += gridDim.x * blockDim.x) {
+        const uint32_t key = a.keys[p];
+        if (key == kInvalidKey) continue;
+        int lo = 0, hi = g.num_features - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (g.f[mid].row_base <= key) lo = mid; else hi = mid - 1;
+        }
+        long long slot_base = 0;
+        for (int i = 0; i < lo; ++i) slot_base += (long long)g.B * g.f[i].L;
+        a.uidx[slot_base + a.vals[p]] = (long long)a.run_of_pos[p];
+    }
+}
+
+struct PeerUniq {
+    int world, rank, num_features;
+    const long long *num_unique[CTR_MAX_WORLD];   // [1] on every rank
+    const int32_t *uniq_feature[CTR_MAX_WORLD];   // [U_r]
+    const int32_t *uniq_row[CTR_MAX_WORLD];       // [U_r]
+    const int64_t *adj;
+};
+
+__global__ void p2p_uniq_offsets_kernel(const __grid_constant__ PeerUniq pu, uint32_t *counters) {
+    const int r = threadIdx.x;
+    uint32_t cnt = r < pu.world ? (uint32_t)*pu.num_unique[r] : 0u;
+    uint32_t incl = cnt;
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t v = __shfl_up_sync(kFull, incl, off);
+        if (r >= off) incl += v;
+    }
+    if (r < pu.world) {
+        counters[kMetaSrc + r] = 0;
+        counters[kMetaDst + r] = incl - cnt;
+        counters[kMetaCnt + r] = cnt;
+    }
+    if (r == 31) counters[3] = incl;
+}
+
+// Owner side: only the (table, row) pairs this rank owns go into the sort.  Peer r's list is cut into chunks of
+// kUniqChunk entries, one block each: a count pass, a device scan of the chunk counts, and a compaction pass that
+// keeps the (rank, index) order -- so the order of every sum is fixed.
+constexpr int kUniqChunk = 2048;   // 256 threads x 8 consecutive entries
+
+__device__ __forceinline__ uint32_t owned_key(const PeerUniq &pu, int r, uint32_t j) {
+    const uint32_t fi = (uint32_t)pu.uniq_feature[r][j];
+    const uint32_t rr = (uint32_t)pu.uniq_row[r][j] + fi;
+    if ((int)(rr % (uint32_t)pu.world) != pu.rank) return kInvalidKey;
+    return (uint32_t)(__ldg(pu.adj + (size_t)pu.rank * pu.num_features + fi) + (long long)(rr / (uint32_t)pu.world));
+}
+
+__global__ void __launch_bounds__(256)
+    p2p_uniq_count_kernel(const __grid_constant__ PeerUniq pu, const uint32_t *__restrict__ counters, uint32_t *__restrict__ chunk_count) {
+    __shared__ uint32_t scratch[33];
+    const int r = blockIdx.y;
+    const uint32_t n = counters[kMetaCnt + r];
+    const uint32_t j0 = blockIdx.x * kUniqChunk + threadIdx.x * 8;
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (j0 + i < n && owned_key(pu, r, j0 + i) != kInvalidKey) ++c;
+    uint32_t total;
+    block_exclusive_256(c, scratch, &total);
+    if (threadIdx.x == 0) chunk_count[(size_t)r * gridDim.x + blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256)
+    p2p_uniq_compact_kernel(const __grid_constant__ PeerUniq pu, uint32_t *counters, const uint32_t *__restrict__ chunk_offset,
+                            const uint32_t *__restrict__ scan_total, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                            uint32_t *__restrict__ hist, int passes, int bits) {
+    __shared__ uint32_t sh[kMaxPasses][kMaxRadix];
+    __shared__ uint32_t scratch[33];
+    for (int i = threadIdx.x; i < kMaxPasses * kMaxRadix; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const int r = blockIdx.y;
+    if (blockIdx.x == 0 && r == 0 && threadIdx.x == 0) counters[3] = *scan_total;      // pairs to sort
+    const uint32_t n = counters[kMetaCnt + r];
+    const uint32_t j0 = blockIdx.x * kUniqChunk + threadIdx.x * 8;
+    uint32_t key[8];
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        key[i] = j0 + i < n ? owned_key(pu, r, j0 + i) : kInvalidKey;
+        c += key[i] != kInvalidKey;
+    }
+    uint32_t total;
+    uint32_t pos = chunk_offset[(size_t)r * gridDim.x + blockIdx.x] + block_exclusive_256(c, scratch, &total);
+    const uint32_t dmask = (1u << bits) - 1u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (key[i] != kInvalidKey) {
+            keys[pos] = key[i];
+            vals[pos] = (j0 + i) | ((uint32_t)r << 28);
+            ++pos;
+            for (int p = 0; p < passes; ++p) atomicAdd(&sh[p][(key[i] >> (p * bits)) & dmask], 1u);
+        }
+    }
+    __syncthreads();
+    const int radix = 1 << bits;
+    for (int i = threadIdx.x; i < passes * radix; i += blockDim.x) {
+        const uint32_t cc = sh[i / radix][i % radix];
+        if (cc) atomicAdd(&hist[(i / radix) * kMaxRadix + (i % radix)], cc);
+    }
+}
+
+}  // namespace ctr
+
+extern "C" int ctr_unique_fetch(const ctr_group_t *group, const ctr_shard_t *shard, const float *const *tables,
+                                void *plan_workspace, float *staging, int64_t *uidx, void *stream_) {
+    static thread_local DevGroup dg;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = lower_group(group, &dg, false, false);
+    if (rc != CTR_OK) return rc;
+    CTR_REQUIRE(tables != nullptr && plan_workspace != nullptr && staging != nullptr, "null pointer");
+    rc = attach_shard(&dg, shard, tables);
+    if (rc != CTR_OK) return rc;
+    CTR_REQUIRE((reinterpret_cast<uintptr_t>(staging) & 15u) == 0, "staging must be 16-byte aligned");
+    const PlanLayout p = plan_layout(dg);
+    if (p.S == 0) return CTR_OK;
+    char *ws = static_cast<char *>(plan_workspace);
+    FetchArgs a{};
+    a.keys = reinterpret_cast<const uint32_t *>(ws + (p.sorted_in_b ? p.keys_b : p.keys_a));
+    a.vals = reinterpret_cast<const uint32_t *>(ws + (p.sorted_in_b ? p.vals_b : p.vals_a));
+    a.run_start = reinterpret_cast<const uint32_t *>(ws + p.run_start);
+    a.run_of_pos = reinterpret_cast<const uint32_t *>(ws + p.run_of_pos);
+    a.counters = reinterpret_cast<const uint32_t *>(ws + p.counters);
+    a.staging = staging;
+    a.uidx = reinterpret_cast<long long *>(uidx);
+    a.S = (uint32_t)p.S;
+    const int teams = 256 / dg.f[0].G;
+    int64_t blocks = (p.S / 4 + teams - 1) / teams;        // ~ a quarter of the slots are distinct rows; the loop strides
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    if (blocks < 1) blocks = 1;
+    note_launch(), uniq_fetch_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dg, a);
+    if (uidx != nullptr) {
+        CTR_CUDA_OK(cudaMemsetAsync(uidx, 0xff, (size_t)p.S * sizeof(int64_t), stream));
+        int64_t b2 = (p.S + 1023) / 1024;
+        if (b2 > kNumSMs * 8) b2 = kNumSMs * 8;
+        note_launch(), slot_uidx_kernel<<<(unsigned)b2, 256, 0, stream>>>(dg, a);
+    }
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int64_t ctr_emb_bwd_p2p_unique_workspace_bytes(const ctr_group_t *group, int64_t capacity) {
+    static thread_local DevGroup dg;
+    int rc = lower_group(group, &dg, false, false);
+    if (rc != CTR_OK) return rc;
+    CTR_REQUIRE(capacity >= 1, "capacity must be positive");
+    return plan_layout(dg, 1, capacity).total;
+}
+
+extern "C" int ctr_emb_bwd_plan_p2p_unique(const ctr_group_t *group, const ctr_shard_t *shard, const int64_t *const *peer_num_unique,
+                                           const int32_t *const *peer_uniq_feature, const int32_t *const *peer_uniq_row,
+                                           int64_t capacity, void *workspace, int64_t workspace_bytes, void *stream_) {
+    static thread_local DevGroup dg;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = lower_group(group, &dg, false, false);
+    if (rc != CTR_OK) return rc;
+    CTR_REQUIRE(shard != nullptr && shard->adj != nullptr, "shard is null");
+    CTR_REQUIRE(shard->world >= 1 && shard->world <= CTR_MAX_WORLD && shard->rank >= 0 && shard->rank < shard->world, "bad world / rank");
+    CTR_REQUIRE(peer_num_unique && peer_uniq_feature && peer_uniq_row && workspace, "null pointer");
+    CTR_REQUIRE(capacity >= 1 && capacity < (1ll << 30) && capacity / shard->world < (1ll << 28), "capacity %lld out of range", (long long)capacity);
+    const PlanLayout p = plan_layout(dg, 1, capacity);
+    if (workspace_bytes < p.total) {
+        set_error("workspace too small: %lld < %lld bytes", (long long)workspace_bytes, (long long)p.total);
+        return CTR_E_WORKSPACE;
+    }
+    CTR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
+    PeerUniq pu{};
+    pu.world = shard->world; pu.rank = shard->rank; pu.num_features = dg.num_features; pu.adj = shard->adj;
+    for (int r = 0; r < shard->world; ++r) {
+        CTR_REQUIRE(peer_num_unique[r] && peer_uniq_feature[r] && peer_uniq_row[r], "peer %d: null list", r);
+        pu.num_unique[r] = reinterpret_cast<const long long *>(peer_num_unique[r]);
+        pu.uniq_feature[r] = peer_uniq_feature[r];
+        pu.uniq_row[r] = peer_uniq_row[r];
+    }
+    char *ws = static_cast<char *>(workspace);
+    uint32_t *counters = reinterpret_cast<uint32_t *>(ws + p.counters);
+    uint32_t *keys_a = reinterpret_cast<uint32_t *>(ws + p.keys_a), *keys_b = reinterpret_cast<uint32_t *>(ws + p.keys_b);
+    uint32_t *vals_a = reinterpret_cast<uint32_t *>(ws + p.vals_a), *vals_b = reinterpret_cast<uint32_t *>(ws + p.vals_b);
+    note_launch(), reset_counters_kernel<<<1, 32, 0, stream>>>(counters, 0u);
+    note_launch(), p2p_uniq_offsets_kernel<<<1, 32, 0, stream>>>(pu, counters);
+    uint32_t *scratch = reinterpret_cast<uint32_t *>(ws + p.counts);
+    rc = radix_sort_prepare(scratch, p.S, p.key_bits, stream);
+    if (rc != CTR_OK) return rc;
+    // chunks of a peer's list (capacity / world entries at most), counts and offsets in the (unused) run_start region
+    const int64_t chunks = (capacity / shard->world + kUniqChunk - 1) / kUniqChunk;
+    const int64_t m = chunks * shard->world;
+    CTR_REQUIRE(2 * m + 2 <= p.S + 2, "capacity too small for the chunk table");
+    uint32_t *chunk_count = reinterpret_cast<uint32_t *>(ws + p.run_start);
+    uint32_t *chunk_offset = chunk_count + m;
+    uint32_t *spine = reinterpret_cast<uint32_t *>(ws + p.spine);
+    note_launch(), p2p_uniq_count_kernel<<<dim3((unsigned)chunks, shard->world), 256, 0, stream>>>(pu, counters, chunk_count);
+    rc = exclusive_scan_u32_to(chunk_count, chunk_offset, m, spine, stream);          // total lands in spine[scan_num_blocks(m)]
+    if (rc != CTR_OK) return rc;
+    note_launch(), p2p_uniq_compact_kernel<<<dim3((unsigned)chunks, shard->world), 256, 0, stream>>>(
+        pu, counters, chunk_offset, spine + scan_num_blocks(m), keys_a, vals_a, sort_hist(scratch), sort_num_passes(p.key_bits),
+        sort_digit_bits(p.key_bits));
+    CTR_CUDA_OK(cudaGetLastError());
+    rc = radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, p.S, p.key_bits, scratch, reinterpret_cast<uint32_t *>(ws + p.spine),
+                          stream, /*hist_ready=*/true, /*n_dev=*/counters + 3);
+    if (rc < 0) return rc;
+    if (rc != p.sorted_in_b) {
+        set_error("internal: sort parity mismatch");
+        return CTR_E_CUDA;
+    }
+    return CTR_OK;
+}
+
+extern "C" int ctr_emb_bwd_apply_p2p_unique(const ctr_group_t *group, const ctr_shard_t *shard, void *workspace, const ctr_opt_t *opt,
+                                            const float *const *peer_row_grads, int64_t capacity, int64_t *num_unique, void *stream_) {
+    static thread_local DevGroup dg;
+    CTR_REQUIRE(opt != nullptr && peer_row_grads != nullptr && shard != nullptr, "null pointer");
+    int rc = lower_group(group, &dg, /*need_tables=*/opt->kind != CTR_OPT_NONE, /*need_out=*/false);
+    if (rc != CTR_OK) return rc;
+    CTR_REQUIRE(shard->world >= 1 && shard->world <= CTR_MAX_WORLD, "bad world");
+    // the "gradient matrix" of a peer is its [distinct rows, D] buffer: row index = the slot, no column offset
+    for (int i = 0; i < dg.num_features; ++i) {
+        DevFeature &f = dg.f[i];
+        CTR_REQUIRE(f.L == 1 && f.out_col == 0, "feature %d: the de-duplicated owner group wants L = 1 and out_col = 0", i);
+        bool al = f.vec == 4 && dg.out_stride % 4 == 0;
+        for (int r = 0; r < shard->world && al; ++r) al = (reinterpret_cast<uintptr_t>(peer_row_grads[r]) & 15u) == 0;
+        f.aligned = al ? 1 : 0;
+    }
+    return apply_impl(dg, plan_layout(dg, 1, capacity), workspace, opt, nullptr, nullptr, nullptr, 0, num_unique, peer_row_grads,
                       shard->world, (cudaStream_t)stream_);
 }

@@ -8,36 +8,6 @@ namespace ctr {
 
 // ---- block scan -----------------------------------------------------------------------
 
-// Exclusive prefix of `x` over the 256 threads of a block (warp shuffles + one smem hop).
-// scratch: 33 u32.  Returns the exclusive prefix; *total receives the block sum.
-__device__ __forceinline__ uint32_t block_exclusive_256(uint32_t x, uint32_t *scratch, uint32_t *total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t incl = x;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const uint32_t v = __shfl_up_sync(kFull, incl, off);
-        if (lane >= off) incl += v;
-    }
-    if (lane == 31) scratch[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        const uint32_t w = lane < (int)(blockDim.x >> 5) ? scratch[lane] : 0u;
-        uint32_t wi = w;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t v = __shfl_up_sync(kFull, wi, off);
-            if (lane >= off) wi += v;
-        }
-        scratch[lane] = wi - w;
-        if (lane == 31) scratch[32] = wi;
-    }
-    __syncthreads();
-    const uint32_t excl = incl - x + scratch[warp];
-    *total = scratch[32];
-    __syncthreads();
-    return excl;
-}
-
 struct ArrayIn {
     const uint32_t *p;
     __device__ __forceinline__ uint32_t operator()(int64_t i) const { return p[i]; }
@@ -58,8 +28,10 @@ struct RunsOut {
     uint32_t *counters;
     const uint32_t *keys;
     int64_t n;
+    uint32_t *run_of_pos;   // optional: index of the run every position belongs to
     __device__ __forceinline__ void operator()(int64_t i, uint32_t prefix, uint32_t head) const {
         if (head) run_start[prefix] = (uint32_t)i;
+        if (run_of_pos != nullptr) run_of_pos[i] = prefix + head - 1u;
     }
     __device__ __forceinline__ void finish(uint32_t total) const {
         run_start[total] = (uint32_t)n;
@@ -147,13 +119,13 @@ __global__ void empty_runs_kernel(uint32_t *run_start, uint32_t *counters) {
 }
 
 int find_runs(const uint32_t *sorted_keys, int64_t n, uint32_t *run_start, uint32_t *counters, uint32_t *spine,
-              cudaStream_t stream) {
+              cudaStream_t stream, uint32_t *run_of_pos) {
     if (n <= 0) {
         note_launch(), empty_runs_kernel<<<1, 1, 0, stream>>>(run_start, counters);
         cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? CTR_OK : cuda_fail(e, "empty_runs_kernel");
     }
-    return device_scan(HeadIn{sorted_keys}, RunsOut{run_start, counters, sorted_keys, n}, n, spine, stream);
+    return device_scan(HeadIn{sorted_keys}, RunsOut{run_start, counters, sorted_keys, n, run_of_pos}, n, spine, stream);
 }
 
 // ---- radix passes -----------------------------------------------------------------------

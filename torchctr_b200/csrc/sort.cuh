@@ -51,8 +51,39 @@ inline uint32_t *sort_hist(uint32_t *counts) { return counts + 8; }
 // Given sorted keys: run_start[r] = first position of the r-th run of equal keys, run_start[R] = n,
 // counters[0] = R (all runs), counters[1] = number of runs whose key != 0xffffffff.
 // spine: scan_spine_elems(n) u32.
+// run_of_pos (optional, u32 [n]): the run index of every sorted position.
 int find_runs(const uint32_t *sorted_keys, int64_t n, uint32_t *run_start, uint32_t *counters, uint32_t *spine,
-              cudaStream_t stream);
+              cudaStream_t stream, uint32_t *run_of_pos = nullptr);
+
+// Exclusive prefix of `x` over the 256 threads of a block (warp shuffles + one smem hop).
+// scratch: 33 u32.  Returns the exclusive prefix; *total receives the block sum.
+__device__ __forceinline__ uint32_t block_exclusive_256(uint32_t x, uint32_t *scratch, uint32_t *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = x;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t v = __shfl_up_sync(kFull, incl, off);
+        if (lane >= off) incl += v;
+    }
+    if (lane == 31) scratch[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = lane < (int)(blockDim.x >> 5) ? scratch[lane] : 0u;
+        uint32_t wi = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t v = __shfl_up_sync(kFull, wi, off);
+            if (lane >= off) wi += v;
+        }
+        scratch[lane] = wi - w;
+        if (lane == 31) scratch[32] = wi;
+    }
+    __syncthreads();
+    const uint32_t excl = incl - x + scratch[warp];
+    *total = scratch[32];
+    __syncthreads();
+    return excl;
+}
 
 // In-place exclusive scan of a u32 array (used on the radix counts; exposed for the tests).
 int exclusive_scan_u32(uint32_t *data, int64_t m, uint32_t *spine, cudaStream_t stream);

@@ -564,3 +564,33 @@ def dense_adagrad(params, grads, sums, lr: float, eps: float) -> None:
     na = (C.c_int64 * n)(*[p.numel() for p in params])
     with _timed("dense_adagrad"):
         _lib.check(_lib.lib().ctr_dense_adagrad(n, pa, ga, sa, na, lr, eps, _stream(params[0])), "ctr_dense_adagrad")
+
+
+# ---- de-duplicated exchange -------------------------------------------------------------------------------------------
+def unique_fetch(call: GroupCall, shard: _lib.Shard, tables, plan_ws: torch.Tensor, staging: torch.Tensor,
+                 uidx: torch.Tensor | None) -> None:
+    _chk(staging, "staging", torch.float32)
+    _chk(uidx, "uidx", torch.int64)
+    with _timed("unique_fetch" + _width_tag(call)):
+        _lib.check(_lib.lib().ctr_unique_fetch(C.byref(call.struct), C.byref(shard), tables, plan_ws.data_ptr(), staging.data_ptr(),
+                                               _lib.ptr(uidx), _stream()), "ctr_unique_fetch")
+
+
+def emb_bwd_p2p_unique_workspace_bytes(call: GroupCall, capacity: int) -> int:
+    return _lib.check(_lib.lib().ctr_emb_bwd_p2p_unique_workspace_bytes(C.byref(call.struct), capacity),
+                      "ctr_emb_bwd_p2p_unique_workspace_bytes")
+
+
+def emb_bwd_plan_p2p_unique(call: GroupCall, shard: _lib.Shard, peer_nu, peer_uf, peer_ur, capacity: int,
+                            workspace: torch.Tensor) -> None:
+    with _timed("emb_bwd_plan_owner"):
+        _lib.check(_lib.lib().ctr_emb_bwd_plan_p2p_unique(C.byref(call.struct), C.byref(shard), peer_nu, peer_uf, peer_ur, capacity,
+                                                          workspace.data_ptr(), workspace.numel(), _stream()),
+                   "ctr_emb_bwd_plan_p2p_unique")
+
+
+def emb_bwd_apply_p2p_unique(call: GroupCall, shard: _lib.Shard, workspace: torch.Tensor, opt: _lib.Opt, peer_row_grads,
+                             capacity: int) -> None:
+    with _timed("emb_bwd_apply_owner" + _width_tag(call)):
+        _lib.check(_lib.lib().ctr_emb_bwd_apply_p2p_unique(C.byref(call.struct), C.byref(shard), workspace.data_ptr(), C.byref(opt),
+                                                           peer_row_grads, capacity, None, _stream()), "ctr_emb_bwd_apply_p2p_unique")

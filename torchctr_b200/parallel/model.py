@@ -6,7 +6,7 @@ import torch.nn as nn
 from .sharded import ShardedTables, reduce_dense_grads
 
 
-def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=None):
+def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=None, dedup=None):
     """Every rank calls this with an identically initialised ``model`` (same seed).  The model's tables
     (and, for DeepFM, its first-order tables, which share the ids) are cut into this rank's rows, fused
     into one shard per width on ``device`` and the full tables are dropped; the dense part stays
@@ -26,7 +26,9 @@ def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=
         from .peer import IpcTransport, PeerShardedTables
         if transport is None:
             transport = IpcTransport(pg, device)
-        sharded = PeerShardedTables(groups[0].names, full, transport, device)
+        if dedup is None:                     # the requester-side sort pays off once most rows are remote
+            dedup = transport.world >= 4
+        sharded = PeerShardedTables(groups[0].names, full, transport, device, dedup=dedup)
     elif device is not None:
         # shards are built on the target device straight from the (host) full tables
         import torch

@@ -185,8 +185,13 @@ class PeerShardedTables(nn.Module):
     """The tables of one lookup group, row-sharded over the ranks of ``transport``.  ``dims`` lists the widths that
     share the ids (DeepFM: ``[emb_dim, 1]``); width ``w`` of table ``f`` is ``full_tables[w][f]`` (``[V_f, dims[w]]``)."""
 
-    def __init__(self, names, full_tables, transport, device=None):
+    def __init__(self, names, full_tables, transport, device=None, dedup: bool = False):
+        """``dedup``: every distinct row of this rank's batch crosses NVLink once per direction (the requester sorts
+        its slots, fetches the distinct rows into a staging matrix and pools from there; backward it reduces its own
+        duplicates before the owners pull) instead of once per id slot.  Pays a local sort on the forward path, saves
+        most of the NVLink traffic under Zipf ids; worth it from about four ranks on."""
         super().__init__()
+        self.dedup = bool(dedup)
         self.transport = transport
         self.world, self.rank = transport.world, transport.rank
         if self.world > _lib.MAX_WORLD:
@@ -269,6 +274,19 @@ class PeerShardedTables(nn.Module):
             self._grad_bufs.append(buf)
             self._peer_grads.append(ops.ptr_array(tr.share(buf)))
             self._strides.append(stride)
+        if self.dedup:
+            cap = max(S, 1)
+            self._uniq_buf = PeerBuffer(256 + 8 * cap, dev)            # [num_unique i64, pad][uniq_feature i32 S][uniq_row i32 S]
+            ptrs = tr.share(self._uniq_buf)
+            self._peer_nu = ops.ptr_array(ptrs)
+            self._peer_uf = ops.ptr_array([p + 256 for p in ptrs])
+            self._peer_ur = ops.ptr_array([p + 256 + 4 * cap for p in ptrs])
+            self._rowgrad_bufs, self._peer_rowgrads = [], []
+            for D in self.dims:
+                buf = PeerBuffer(cap * D * 4, dev)
+                self._rowgrad_bufs.append(buf)
+                self._peer_rowgrads.append(ops.ptr_array(tr.share(buf)))
+            self._one_id = torch.zeros(1, 1, dtype=torch.int64, device=dev)
         self._S = S
         self._B = (B, Ls)
 
@@ -279,7 +297,7 @@ class PeerShardedTables(nn.Module):
         return [ops.FeatureSpec(ids=ids, table=None, num_rows=v, D=D, out_col=f * D, index_kind=k, hash_seed=s)
                 for f, (ids, v, k, s) in enumerate(zip(ids_list, self.num_rows, self.index_kinds, self.hash_seeds))]
 
-    def _owner_specs(self, ids_list, w, with_state):
+    def _owner_specs(self, ids_list, w, with_state, dedup=False):
         D = self.dims[w]
         shard = self.shards[w].data
         specs = []
@@ -289,7 +307,7 @@ class PeerShardedTables(nn.Module):
             b = self.base[self.rank][f]
             s0 = self.opt_state0[w] if with_state else None
             s1 = self.opt_state1[w] if with_state else None
-            specs.append(ops.FeatureSpec(ids=ids, table=shard[b:b + n], num_rows=n, D=D, out_col=f * D,
+            specs.append(ops.FeatureSpec(ids=ids, table=shard[b:b + n], num_rows=n, D=D, out_col=0 if dedup else f * D,
                                          state0=None if s0 is None else s0[b:b + n],
                                          state1=None if s1 is None else s1[b:b + n]))
         return specs
@@ -313,6 +331,8 @@ class PeerShardedTables(nn.Module):
         if self.training:
             self._ensure_buffers(ids_list)
         self._ids = ids_list
+        if self.dedup:
+            return self._forward_dedup(ids_list, dense)
         dev = self.device
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         outs = []
@@ -342,9 +362,81 @@ class PeerShardedTables(nn.Module):
         self.status = status
         return outs
 
+    # ---- de-duplicated exchange ------------------------------------------------------------------------------------
+    def _forward_dedup(self, ids_list, dense):
+        B = ids_list[0].shape[0]
+        dev = self.device
+        S = sum(i.numel() for i in ids_list)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        # the plan of the single-GPU backward (sort + runs), on the requester's own slots, before the lookup
+        plan_call = ops.make_group(self._request_specs(ids_list, 0), B, None, self.num_features * self.dims[0], status=status)
+        ws = torch.empty(ops.emb_bwd_workspace_bytes(plan_call) + 256, dtype=torch.uint8, device=dev)
+        ops.emb_bwd_plan(plan_call, ws, runs=True)
+        uidx = torch.empty(S, dtype=torch.int64, device=dev)
+        views, off = [], 0
+        for ids in ids_list:
+            views.append(uidx[off:off + ids.numel()].view(ids.shape))
+            off += ids.numel()
+        outs = []
+        for w, D in enumerate(self.dims):
+            staging = torch.empty(max(S, 1), D, dtype=torch.float32, device=dev)
+            call = ops.make_group(self._request_specs(ids_list, w), B, None, self.num_features * D, status=status)
+            ops.unique_fetch(call, self._shard_struct, self._table_ptrs[w], ws, staging, uidx if w == 0 else None)
+            width = self.num_features * D + (self._dense_width if w == 0 else 0)
+            stride = (width + 3) // 4 * 4
+            out = torch.empty(B, stride, dtype=torch.float32, device=dev)
+            specs = [ops.FeatureSpec(ids=v, table=staging, num_rows=max(S, 1), D=D, out_col=f * D) for f, v in enumerate(views)]
+            pool = ops.make_group(specs, B, out, stride, dense=dense if w == 0 else None, dense_col=self.num_features * D,
+                                  zero_from=width if stride > width else -1, status=status)
+            ops.emb_pool_fwd(pool)
+            outs.append(out)
+        self._plan_local = ws
+        self.status = status
+        return outs
+
+    def _backward_dedup(self, grad_outs):
+        ids_list = self._ids
+        B = ids_list[0].shape[0]
+        dev = self.device
+        cap = max(self._S, 1)
+        live = [w for w, g in enumerate(grad_outs) if g is not None]
+        ub = self._uniq_buf
+        nu = ub.tensor(torch.int64, (1,))
+        uf = ub.tensor(torch.int32, (cap,), 256)
+        ur = ub.tensor(torch.int32, (cap,), 256 + 4 * cap)
+        none_opt = ops.make_opt("none")
+        for w in live:                                   # this rank's duplicates are summed here, once
+            g = grad_outs[w]
+            if g.stride(1) != 1 or g.stride(0) != g.shape[1]:
+                g = g.contiguous()
+            D = self.dims[w]
+            call = ops.make_group(self._request_specs(ids_list, w), B, g, g.shape[1])
+            rg = self._rowgrad_bufs[w].tensor(torch.float32, (cap, D))
+            ops.emb_bwd_apply(call, self._plan_local, none_opt, uf, ur, rg, nu)
+        self.transport.barrier()                         # every rank's distinct-row lists and gradients are in place
+        world_cap = self.world * cap
+        for w in live:
+            bind = self.bindings[w]
+            self._ensure_state(w, bind.kind, bind.initial_accumulator_value())
+        owner_ids = [self._one_id] * self.num_features
+        plan_call = ops.make_group(self._owner_specs(owner_ids, 0, False, dedup=True), 1, None, self.dims[0])
+        need = ops.emb_bwd_p2p_unique_workspace_bytes(plan_call, world_cap)
+        if self._plan_ws is None or self._plan_ws.numel() < need:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("run one eager step before capturing: the owner-side workspace is not sized yet")
+            self._plan_ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+        ops.emb_bwd_plan_p2p_unique(plan_call, self._shard_struct, self._peer_nu, self._peer_uf, self._peer_ur, world_cap, self._plan_ws)
+        for w in live:
+            call = ops.make_group(self._owner_specs(owner_ids, w, True, dedup=True), 1, None, self.dims[w])
+            ops.emb_bwd_apply_p2p_unique(call, self._shard_struct, self._plan_ws, self.bindings[w].next_opt(),
+                                         self._peer_rowgrads[w], world_cap)
+        self.transport.barrier()
+
     def _backward(self, grad_outs):
         if any(b is None for b in self.bindings):
             raise RuntimeError("sharded tables need bind_optimizer(): there is no dense or sparse .grad to hand back")
+        if self.dedup:
+            return self._backward_dedup(grad_outs)
         ids_list = self._ids
         B = ids_list[0].shape[0]
         live = [w for w, g in enumerate(grad_outs) if g is not None]
@@ -374,7 +466,7 @@ class PeerShardedTables(nn.Module):
         """A callable returning this rank's peer-visible gradient matrix of width ``w`` as a tensor [B, stride]: whoever
         produces dL/d(pooled output) may write it there directly and hand it back through autograd."""
         def provider():
-            if self._B is None:
+            if self._B is None or self.dedup:
                 return None
             return self._grad_bufs[w].tensor(torch.float32, (self._B[0], self._strides[w]))
         return provider
