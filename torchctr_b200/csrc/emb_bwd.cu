@@ -1017,69 +1017,44 @@ __global__ void p2p_uniq_offsets_kernel(const __grid_constant__ PeerUniq pu, uin
     if (r == 31) counters[3] = incl;
 }
 
-// Owner side: only the (table, row) pairs this rank owns go into the sort.  Peer r's list is cut into chunks of
-// kUniqChunk entries, one block each: a count pass, a device scan of the chunk counts, and a compaction pass that
-// keeps the (rank, index) order -- so the order of every sum is fixed.
-constexpr int kUniqChunk = 2048;   // 256 threads x 8 consecutive entries
-
-__device__ __forceinline__ uint32_t owned_key(const PeerUniq &pu, int r, uint32_t j) {
-    const uint32_t fi = (uint32_t)pu.uniq_feature[r][j];
-    const uint32_t rr = (uint32_t)pu.uniq_row[r][j] + fi;
-    if ((int)(rr % (uint32_t)pu.world) != pu.rank) return kInvalidKey;
-    return (uint32_t)(__ldg(pu.adj + (size_t)pu.rank * pu.num_features + fi) + (long long)(rr / (uint32_t)pu.world));
-}
-
+// grid (bx, world): every distinct (table, row) of peer r becomes a pair; the ones this rank does not own get the
+// invalid key (they sort behind everything and the sweep skips them), so the input order -- and with it the order
+// of every sum -- is fixed by (rank, index).  (An ordered compaction of the owned pairs was tried: its two extra
+// passes over the peers' lists cost more than sorting the invalid keys along, 232 vs 154 us at 8 GPUs.)
 __global__ void __launch_bounds__(256)
-    p2p_uniq_count_kernel(const __grid_constant__ PeerUniq pu, const uint32_t *__restrict__ counters, uint32_t *__restrict__ chunk_count) {
-    __shared__ uint32_t scratch[33];
-    const int r = blockIdx.y;
-    const uint32_t n = counters[kMetaCnt + r];
-    const uint32_t j0 = blockIdx.x * kUniqChunk + threadIdx.x * 8;
-    uint32_t c = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        if (j0 + i < n && owned_key(pu, r, j0 + i) != kInvalidKey) ++c;
-    uint32_t total;
-    block_exclusive_256(c, scratch, &total);
-    if (threadIdx.x == 0) chunk_count[(size_t)r * gridDim.x + blockIdx.x] = total;
-}
-
-__global__ void __launch_bounds__(256)
-    p2p_uniq_compact_kernel(const __grid_constant__ PeerUniq pu, uint32_t *counters, const uint32_t *__restrict__ chunk_offset,
-                            const uint32_t *__restrict__ scan_total, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
-                            uint32_t *__restrict__ hist, int passes, int bits) {
+    p2p_uniq_gather_kernel(const __grid_constant__ PeerUniq pu, const uint32_t *__restrict__ counters, uint32_t *__restrict__ keys,
+                           uint32_t *__restrict__ vals, uint32_t *__restrict__ hist, int passes, int bits) {
     __shared__ uint32_t sh[kMaxPasses][kMaxRadix];
-    __shared__ uint32_t scratch[33];
     for (int i = threadIdx.x; i < kMaxPasses * kMaxRadix; i += blockDim.x) (&sh[0][0])[i] = 0;
     __syncthreads();
     const int r = blockIdx.y;
-    if (blockIdx.x == 0 && r == 0 && threadIdx.x == 0) counters[3] = *scan_total;      // pairs to sort
     const uint32_t n = counters[kMetaCnt + r];
-    const uint32_t j0 = blockIdx.x * kUniqChunk + threadIdx.x * 8;
-    uint32_t key[8];
-    uint32_t c = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        key[i] = j0 + i < n ? owned_key(pu, r, j0 + i) : kInvalidKey;
-        c += key[i] != kInvalidKey;
-    }
-    uint32_t total;
-    uint32_t pos = chunk_offset[(size_t)r * gridDim.x + blockIdx.x] + block_exclusive_256(c, scratch, &total);
+    const uint32_t dst = counters[kMetaDst + r];
+    const int lane = threadIdx.x & 31;
     const uint32_t dmask = (1u << bits) - 1u;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        if (key[i] != kInvalidKey) {
-            keys[pos] = key[i];
-            vals[pos] = (j0 + i) | ((uint32_t)r << 28);
-            ++pos;
-            for (int p = 0; p < passes; ++p) atomicAdd(&sh[p][(key[i] >> (p * bits)) & dmask], 1u);
+    const uint32_t nround = (n + 31u) / 32u * 32u;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += gridDim.x * blockDim.x) {
+        const bool valid = j < n;
+        uint32_t key = kInvalidKey;
+        if (valid) {
+            const uint32_t fi = (uint32_t)pu.uniq_feature[r][j];
+            const uint32_t rr = (uint32_t)pu.uniq_row[r][j] + fi;
+            if ((int)(rr % (uint32_t)pu.world) == pu.rank)
+                key = (uint32_t)(__ldg(pu.adj + (size_t)pu.rank * pu.num_features + fi) + (long long)(rr / (uint32_t)pu.world));
+            keys[dst + j] = key;
+            vals[dst + j] = j | ((uint32_t)r << 28);
+        }
+        for (int p = 0; p < passes; ++p) {
+            const uint32_t d = (key >> (p * bits)) & dmask;
+            const uint32_t peers = __match_any_sync(kFull, valid ? d : (uint32_t)(kMaxRadix + lane));
+            if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[p][d], (uint32_t)__popc(peers));
         }
     }
     __syncthreads();
     const int radix = 1 << bits;
     for (int i = threadIdx.x; i < passes * radix; i += blockDim.x) {
-        const uint32_t cc = sh[i / radix][i % radix];
-        if (cc) atomicAdd(&hist[(i / radix) * kMaxRadix + (i % radix)], cc);
+        const uint32_t c = sh[i / radix][i % radix];
+        if (c) atomicAdd(&hist[(i / radix) * kMaxRadix + (i % radix)], c);
     }
 }
 
@@ -1164,19 +1139,12 @@ extern "C" int ctr_emb_bwd_plan_p2p_unique(const ctr_group_t *group, const ctr_s
     uint32_t *scratch = reinterpret_cast<uint32_t *>(ws + p.counts);
     rc = radix_sort_prepare(scratch, p.S, p.key_bits, stream);
     if (rc != CTR_OK) return rc;
-    // chunks of a peer's list (capacity / world entries at most), counts and offsets in the (unused) run_start region
-    const int64_t chunks = (capacity / shard->world + kUniqChunk - 1) / kUniqChunk;
-    const int64_t m = chunks * shard->world;
-    CTR_REQUIRE(2 * m + 2 <= p.S + 2, "capacity too small for the chunk table");
-    uint32_t *chunk_count = reinterpret_cast<uint32_t *>(ws + p.run_start);
-    uint32_t *chunk_offset = chunk_count + m;
-    uint32_t *spine = reinterpret_cast<uint32_t *>(ws + p.spine);
-    note_launch(), p2p_uniq_count_kernel<<<dim3((unsigned)chunks, shard->world), 256, 0, stream>>>(pu, counters, chunk_count);
-    rc = exclusive_scan_u32_to(chunk_count, chunk_offset, m, spine, stream);          // total lands in spine[scan_num_blocks(m)]
-    if (rc != CTR_OK) return rc;
-    note_launch(), p2p_uniq_compact_kernel<<<dim3((unsigned)chunks, shard->world), 256, 0, stream>>>(
-        pu, counters, chunk_offset, spine + scan_num_blocks(m), keys_a, vals_a, sort_hist(scratch), sort_num_passes(p.key_bits),
-        sort_digit_bits(p.key_bits));
+    int64_t bx = (capacity / shard->world / 4 + 2047) / 2048;
+    const int64_t per_peer = ((int64_t)kNumSMs * 4 + shard->world - 1) / shard->world;
+    if (bx > per_peer) bx = per_peer;
+    if (bx < 1) bx = 1;
+    note_launch(), p2p_uniq_gather_kernel<<<dim3((unsigned)bx, shard->world), 256, 0, stream>>>(
+        pu, counters, keys_a, vals_a, sort_hist(scratch), sort_num_passes(p.key_bits), sort_digit_bits(p.key_bits));
     CTR_CUDA_OK(cudaGetLastError());
     rc = radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, p.S, p.key_bits, scratch, reinterpret_cast<uint32_t *>(ws + p.spine),
                           stream, /*hist_ready=*/true, /*n_dev=*/counters + 3);
