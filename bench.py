@@ -455,7 +455,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--roofline-only", action="store_true", help="only time the embedding entry points (ncu target)")
     ap.add_argument("--dedup", default="auto", choices=["auto", "on", "off"],
-                    help="N > 1: fetch / send every distinct row once (auto: from 4 GPUs on)")
+                    help="N > 1: fetch / send every distinct row once (auto: above 4 GPUs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
