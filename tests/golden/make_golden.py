@@ -13,6 +13,7 @@ of SURVEY.md section 8c, the only missing dependency) and scikit-learn's
   ``torch.optim.Adagrad`` step and a short ``torchctr.trainer.Trainer.fit`` loss trace
 * ``dynamic_golden.pt``    -- ``torchctr.nn.DynamicEmbedding`` growth and state-dict merge
 * ``optim_golden.pt``      -- ``torch.optim.{Adagrad,SparseAdam,SGD}`` on an embedding table
+* ``collate_golden.pt``    -- ``torchctr.dataset.get_dataloader`` batches (padding / truncation / weights)
 
 The fixtures are small and committed; tests never import the reference.
 """
@@ -212,9 +213,50 @@ def golden_optim():
     print("optim_golden.pt")
 
 
+def golden_collate(torchctr):
+    """``torchctr.dataset.get_dataloader`` (dataset.py:5-82) on a small in-memory datasets.Dataset: the raw columns and
+    the batches its collate_fn produces (padding, truncation, weights, dtypes, key order)."""
+    import datasets
+    from torchctr.dataset import get_dataloader
+    rng = np.random.default_rng(7)
+    n = 23
+    lens = rng.integers(0, 9, n)
+    lens[3] = 0
+    lens[5] = 8
+    cols = {
+        "price": [float(x) for x in rng.normal(size=n)],
+        "age": [float(x) for x in rng.integers(18, 80, n)],
+        "user": [int(x) for x in rng.integers(0, 1000, n)],
+        "cat": [int(x) for x in rng.integers(0, 50, n)],
+        "hist": [[int(x) for x in rng.integers(0, 500, l)] for l in lens],
+        "hist_w": [[float(x) for x in rng.random(l)] for l in lens],
+        "tags": [[int(x) for x in rng.integers(0, 30, max(1, l // 2))] for l in lens],
+        "click": [float(x) for x in rng.integers(0, 2, n)],
+        "buy": [float(x) for x in rng.integers(0, 2, n)],
+    }
+    feat_configs = [
+        {"name": "price", "type": "dense"}, {"name": "user", "type": "sparse", "num_embeddings": 1000, "emb_dim": 16},
+        {"name": "hist", "type": "sparse", "islist": True, "maxlen": 6, "weight": "hist_w", "num_embeddings": 500, "emb_dim": 16},
+        {"name": "age", "type": "dense"}, {"name": "cat", "type": "sparse", "num_embeddings": 50, "emb_dim": 16},
+        {"name": "tags", "type": "sparse", "islist": True, "padding_value": -1, "num_embeddings": 30, "emb_dim": 16},
+    ]
+    target_cols = ["click", "buy"]
+    ds = datasets.Dataset.from_dict(cols)
+    out = {"columns": cols, "feat_configs": feat_configs, "target_cols": target_cols, "runs": []}
+    for kw in (dict(list_padding_maxlen=5), dict(list_padding_value=-7, list_padding_maxlen=12)):
+        dl = get_dataloader(ds, feat_configs, target_cols, batch_size=8, shuffle=False, **kw)
+        out["runs"].append({"kwargs": kw, "batches": [(dict(f), l) for f, l in dl]})
+    torch.save(out, os.path.join(HERE, "collate_golden.pt"))
+    print("collate_golden.pt", [len(r["batches"]) for r in out["runs"]])
+
+
 if __name__ == "__main__":
     ref = import_reference()
+    if "--only-collate" in sys.argv:
+        golden_collate(ref)
+        sys.exit(0)
     golden_hash(ref)
     golden_dnn(ref)
     golden_dynamic(ref)
     golden_optim()
+    golden_collate(ref)
