@@ -121,6 +121,15 @@ def _rank_main(rank, world, shared, prob, kind, errors, steps, dedup=False):
                     assert _close(rows, expect), \
                         f"update width {w} table {f} step {step}: max abs err {float((rows.cpu() - expect).abs().max()):.3e}"
             assert int(st.status.item()) == 0
+        # checkpoint round trip in the reference's unsharded format: export == the oracle's tables, load restores them
+        for w, ws in enumerate((w16, w1)):
+            full = st.export_full_tables(w)
+            for f in range(len(Vs)):
+                assert _close(full[f], ws[f]), f"export width {w} table {f}"
+            st.load_full_tables([t * 0.5 for t in full], w)
+            again = st.export_full_tables(w)
+            for f in range(len(Vs)):
+                assert torch.equal(again[f], full[f] * 0.5), f"load width {w} table {f}"
     except BaseException as e:          # noqa: BLE001 -- reported by the main thread
         errors.append((rank, repr(e)[:600]))
         try:

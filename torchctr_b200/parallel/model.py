@@ -49,4 +49,22 @@ def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=
         else:
             reduce_dense_grads(model.dense_parameters(), pg)
     model.reduce_dense_grads = _reduce
+
+    table_prefix = []
+    for g in groups:                       # 'embeddings', 'linear_embeddings': the ModuleDicts the tables lived in
+        table_prefix.append(next((n for n, m in model.named_children() if m is g.tables), None))
+
+    def full_state_dict():
+        """Collective.  The state dict of the UNSHARDED model -- every table gathered back to ``[V, D]`` under its
+        original key -- so that ``Trainer.save_ckpt`` output (``torchctr/trainer.py:353-496``) written from it loads
+        into the reference ``DNN`` or into an unsharded model of this package."""
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items() if not k.startswith("_sharded.")}
+        if hasattr(sharded, "export_full_tables"):
+            for w, prefix in enumerate(table_prefix):
+                if prefix is None:
+                    continue
+                for name, t in zip(sharded.names, sharded.export_full_tables(w)):
+                    sd[f"{prefix}.{name}.weight"] = t
+        return sd
+    model.full_state_dict = full_state_dict
     return model

@@ -104,6 +104,11 @@ class IpcTransport:
         through the peer mappings).  A 4-byte NCCL all-reduce: capturable into a CUDA graph."""
         dist.all_reduce(self._token, group=self.pg)
 
+    def all_gather_object(self, obj):
+        out = [None] * self.world
+        dist.all_gather_object(out, obj, group=self.pg)
+        return out
+
 
 class ThreadTransport:
     """Test transport: the ranks are threads of one process on ONE device; 'peer' pointers are plain device pointers."""
@@ -132,6 +137,16 @@ class ThreadTransport:
     def barrier(self):
         torch.cuda.synchronize(self.device)
         self.shared.barrier.wait()
+
+    def all_gather_object(self, obj):
+        key = ("obj", self._seq)
+        self._seq += 1
+        with self.shared.lock:
+            self.shared.slots.setdefault(key, {})[self.rank] = obj
+        self.shared.barrier.wait()
+        out = [self.shared.slots[key][r] for r in range(self.world)]
+        self.shared.barrier.wait()
+        return out
 
 
 def owned_rows(num_rows: int, table: int, rank: int, world: int):
@@ -470,6 +485,38 @@ class PeerShardedTables(nn.Module):
                 return None
             return self._grad_bufs[w].tensor(torch.float32, (self._B[0], self._strides[w]))
         return provider
+
+    # ---- checkpoints in the reference's (unsharded) format ------------------------------------------------------------
+    def export_full_tables(self, w: int = 0):
+        """Collective.  Every rank gets the full ``[V_f, dims[w]]`` table of every feature (CPU tensors), i.e. what
+        ``model.embeddings[name].weight`` holds in the reference and in an unsharded model: a checkpoint written from
+        them loads into ``torchctr.models.DNN`` (``torchctr/trainer.py:353-496``, ``nn/embedding.py:89-95``)."""
+        torch.cuda.synchronize(self.device)
+        mine = [self.local_rows_of(w, f)[1].detach().cpu() for f in range(self.num_features)]
+        parts = self.transport.all_gather_object(mine)
+        full = []
+        for f, v in enumerate(self.num_rows):
+            t = torch.empty(v, self.dims[w], dtype=torch.float32)
+            for r in range(self.world):
+                fr, n = owned_rows(v, f, r, self.world)
+                if n:
+                    t[fr::self.world] = parts[r][f]
+            full.append(t)
+        return full
+
+    def load_full_tables(self, full, w: int = 0) -> None:
+        """Scatter full tables (one ``[V_f, dims[w]]`` tensor per feature, e.g. from a reference checkpoint) into
+        this rank's shard.  Every rank calls it with the same tensors; optimizer state of the width is reset."""
+        with torch.no_grad():
+            for f, t in enumerate(full):
+                if tuple(t.shape) != (self.num_rows[f], self.dims[w]):
+                    raise ValueError(f"table {f}: expected {(self.num_rows[f], self.dims[w])}, got {tuple(t.shape)}")
+                fr, rows = self.local_rows_of(w, f)
+                if rows.shape[0]:
+                    rows.copy_(t[fr::self.world].to(self.device))
+        self.opt_state0[w] = None
+        self.opt_state1[w] = None
+        self.transport.barrier()
 
     # ---- inspection (tests, checkpoints): this rank's rows of table f, width w ------------------------------------------
     def local_rows_of(self, w, f):
