@@ -130,3 +130,22 @@ def test_peer_shard_geometry_is_a_bijection():
                 assert (o, vr) not in seen
                 seen.add((o, vr))
             assert len(seen) == v
+
+
+def test_fused_adagrad_on_cpu_parameters_is_torch_adagrad():
+    """Off the GPU (or with lr_decay / weight decay / sparse gradients) FusedAdagrad must take torch's own code path."""
+    from torchctr_b200.optim import FusedAdagrad
+    gen = torch.Generator().manual_seed(0)
+    p1 = [torch.randn(5, 3, generator=gen, requires_grad=True), torch.randn(4, generator=gen, requires_grad=True)]
+    p2 = [p.detach().clone().requires_grad_(True) for p in p1]
+    o1 = FusedAdagrad(p1, lr=0.1, lr_decay=0.01)
+    o2 = torch.optim.Adagrad(p2, lr=0.1, lr_decay=0.01)
+    for _ in range(3):
+        for a, b in zip(p1, p2):
+            g = torch.randn(a.shape, generator=gen)
+            a.grad, b.grad = g.clone(), g.clone()
+        o1.step()
+        o2.step()
+    for a, b in zip(p1, p2):
+        assert torch.equal(a, b)
+        assert torch.equal(o1.state[a]["sum"], o2.state[b]["sum"]) and float(o1.state[a]["step"]) == float(o2.state[b]["step"])

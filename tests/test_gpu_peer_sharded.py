@@ -144,7 +144,7 @@ def test_peer_sharded_threads(world, kind, hashed, dedup):
     import faulthandler
     import sys
     from torchctr_b200.parallel.peer import ThreadTransport
-    faulthandler.dump_traceback_later(100, exit=True, file=sys.stderr)      # a stuck rank must not hang the suite
+    faulthandler.dump_traceback_later(300, exit=True, file=sys.stderr)      # a stuck rank must not hang the suite
     shared = ThreadTransport.Shared(world)
     prob = _problem(world, hashed=hashed)
     errors = []
@@ -152,7 +152,7 @@ def test_peer_sharded_threads(world, kind, hashed, dedup):
     for t in threads:
         t.start()
     for t in threads:
-        t.join(timeout=90)
+        t.join(timeout=240)
     faulthandler.cancel_dump_traceback_later()
     assert not errors, errors
     assert all(not t.is_alive() for t in threads)
