@@ -280,6 +280,10 @@ class _LookupCall:
                 # kernels that leaves most of the machine idle, so the overlap is nearly free.
                 link.ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
                 side = _side_stream(dev)
+                if not torch.cuda.is_current_stream_capturing():
+                    link.ws.record_stream(side)      # a forward without backward must not hand the block back too early
+                    for _, ids, _ in self.entries:
+                        ids.record_stream(side)
                 side.wait_stream(torch.cuda.current_stream(dev))
                 with torch.cuda.stream(side):
                     ops.emb_bwd_plan(call, link.ws, runs=False)

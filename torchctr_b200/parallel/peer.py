@@ -368,6 +368,9 @@ class PeerShardedTables(nn.Module):
                 self._route_ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
             if self._side is None:
                 self._side = torch.cuda.Stream(device=dev)
+            if not torch.cuda.is_current_stream_capturing():
+                for t in ids_list:
+                    t.record_stream(self._side)      # the ids are read on the side stream
             main = torch.cuda.current_stream(dev)
             self._side.wait_stream(main)
             rp = self._route_buf.ptr
