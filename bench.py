@@ -361,8 +361,13 @@ def run_ours(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    for i in range(25):                                  # keeps the GPU under load while nvidia-smi samples
-        step(resident[i % nb], i)
+    t_load = time.perf_counter()                         # ~0.8 s of the same steps: the GPU is under the benchmark's load while
+    i = 0                                                # nvidia-smi (100 ms period) samples clocks and throttle reasons
+    while time.perf_counter() - t_load < 0.8:
+        for _ in range(25):
+            step(resident[i % nb], i)
+            i += 1
+        torch.cuda.synchronize()
     launches0 = ops.kernel_launches()
     ms = timed(resident, args.steps, read_loss=False)
     launches = ops.kernel_launches() - launches0 if launches_per_step is None else launches_per_step * args.steps
@@ -403,7 +408,7 @@ def run_ours(args):
                        + ("; requester-side de-duplication: every distinct row crosses NVLink once per direction"
                           if getattr(getattr(model, "_sharded", None), "dedup", False) else ""),
         "clocks": clock_info,
-        "tower_matmul": "torch F.linear, TF32 tensor cores, fp32 accumulate",
+        "tower_matmul": "tcgen05 TF32 kernels (ctr_linear_fwd forward / dgrad, ctr_linear_wgrad), fp32 accumulate in TMEM",
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
