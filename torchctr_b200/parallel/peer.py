@@ -198,7 +198,13 @@ class _PeerLookupFn(torch.autograd.Function):
 
 class PeerShardedTables(nn.Module):
     """The tables of one lookup group, row-sharded over the ranks of ``transport``.  ``dims`` lists the widths that
-    share the ids (DeepFM: ``[emb_dim, 1]``); width ``w`` of table ``f`` is ``full_tables[w][f]`` (``[V_f, dims[w]]``)."""
+    share the ids (DeepFM: ``[emb_dim, 1]``); width ``w`` of table ``f`` is ``full_tables[w][f]`` (``[V_f, dims[w]]``).
+
+    One training lookup is in flight per module at a time: the routing lists, gradient buffers and the requester-side
+    plan are per-module peer buffers that every rank reads between the two barriers of ``backward``, so a second
+    training ``forward`` must come after the ``backward`` of the first (forward / backward / forward / backward, as
+    the reference loop ``torchctr/trainer.py:291-303`` and gradient accumulation over micro-batches do).  All ranks
+    must call ``forward`` / ``backward`` the same number of times with the same batch size."""
 
     def __init__(self, names, full_tables, transport, device=None, dedup: bool = False):
         """``dedup``: every distinct row of this rank's batch crosses NVLink once per direction (the requester sorts
