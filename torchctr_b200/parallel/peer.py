@@ -252,6 +252,8 @@ class PeerShardedTables(nn.Module):
         self.bindings = [None] * len(self.dims)
         self._side = None           # side stream of the owner bucketing
         self._route_pending = False
+        self._owner_planned = False
+        self.early_owner_plan = True    # direct mode: meet the other ranks and sort on the side stream during the tower
         self._B = None              # batch geometry the peer buffers were sized for
         self._route_ws = None
         self._plan_ws = None
@@ -380,8 +382,23 @@ class PeerShardedTables(nn.Module):
             main = torch.cuda.current_stream(dev)
             self._side.wait_stream(main)
             rp = self._route_buf.ptr
+            # the owner-side plan needs the routing lists of every rank, which depend on the ids only: build them,
+            # meet the other ranks and sort -- all on the side stream, next to the tower, as the single-GPU path does
+            # with its early sort.  backward() then only waits for the gradients.
+            plan_call = ops.make_group(self._owner_specs(ids_list, 0, False), B, None, self._strides[0])
+            need_plan = ops.emb_bwd_p2p_workspace_bytes(plan_call, self.world)
+            if self._plan_ws is None or self._plan_ws.numel() < need_plan:
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("run one eager step before capturing: the owner-side workspace is not sized yet")
+                self._plan_ws = torch.empty(need_plan + 256, dtype=torch.uint8, device=dev)
+                self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 ops.route_p2p_build(call, self._shard_struct, rp, rp + 256, rp + 256 + 4 * max(self._S, 1), self._route_ws)
+                if self.early_owner_plan:
+                    self.transport.barrier()             # every rank's routing lists are in place
+                    ops.emb_bwd_plan_p2p(plan_call, self._shard_struct, self._peer_counts, self._peer_keys, self._peer_slots,
+                                         self._plan_ws)
+                    self._owner_planned = True
             self._route_pending = True
         self.status = status
         return outs
@@ -472,13 +489,15 @@ class PeerShardedTables(nn.Module):
             if g.data_ptr() != self._grad_bufs[w].ptr:   # (the tower's first block may have written it in place)
                 self._grad_bufs[w].tensor(torch.float32, (B, self._strides[w])).copy_(g)
         self.transport.barrier()                         # every rank's routing lists and gradients are in place
-        plan_call = ops.make_group(self._owner_specs(ids_list, 0, False), B, None, self._strides[0])
-        need = ops.emb_bwd_p2p_workspace_bytes(plan_call, self.world)
-        if self._plan_ws is None or self._plan_ws.numel() < need:
-            if torch.cuda.is_current_stream_capturing():
-                raise RuntimeError("run one eager step before capturing: the owner-side workspace is not sized yet")
-            self._plan_ws = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
-        ops.emb_bwd_plan_p2p(plan_call, self._shard_struct, self._peer_counts, self._peer_keys, self._peer_slots, self._plan_ws)
+        if not self._owner_planned:                      # (no early plan was started in forward)
+            plan_call = ops.make_group(self._owner_specs(ids_list, 0, False), B, None, self._strides[0])
+            need = ops.emb_bwd_p2p_workspace_bytes(plan_call, self.world)
+            if self._plan_ws is None or self._plan_ws.numel() < need:
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("run one eager step before capturing: the owner-side workspace is not sized yet")
+                self._plan_ws = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+            ops.emb_bwd_plan_p2p(plan_call, self._shard_struct, self._peer_counts, self._peer_keys, self._peer_slots, self._plan_ws)
+        self._owner_planned = False
         for w in live:
             bind = self.bindings[w]
             self._ensure_state(w, bind.kind, bind.initial_accumulator_value())
