@@ -149,3 +149,10 @@ def test_fused_adagrad_on_cpu_parameters_is_torch_adagrad():
     for a, b in zip(p1, p2):
         assert torch.equal(a, b)
         assert torch.equal(o1.state[a]["sum"], o2.state[b]["sum"]) and float(o1.state[a]["step"]) == float(o2.state[b]["step"])
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md must say, for every symbol of the header, which reference lines it stands in for."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in declared_in_header() if n not in doc]
+    assert not missing, missing
