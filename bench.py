@@ -266,8 +266,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
+    from torchctr_b200.nn import set_matmul_precision
     torch.backends.cuda.matmul.allow_tf32 = True        # tower GEMMs on tensor cores (TF32 in, fp32 accumulate)
     torch.backends.cudnn.allow_tf32 = True
+    set_matmul_precision(args.precision)                # "tf32" (headline) | "tf32x3" (error-compensated, fp32-grade)
 
     torch.manual_seed(0)
     fc = feat_configs()
@@ -380,6 +382,22 @@ def run_ours(args):
     value = B * world * args.steps / (ms / 1e3)
     e2e = B * world * args.steps / (ms_e2e / 1e3)
 
+    # the same step with the tower GEMMs in the exact mode (3xTF32 on the same tcgen05 kernels): the configuration the
+    # 1e-5 parity tests run in, timed the same way
+    exact = None
+    if world == 1 and args.precision == "tf32" and not args.no_graph and not args.no_exact:
+        from torchctr_b200.graph import GraphedTrainStep
+        set_matmul_precision("tf32x3")
+        graphed_x3 = GraphedTrainStep(model, opt, resident[0], warmup=1)
+        step_tf32, step = step, (lambda batch, i: graphed_x3(batch))
+        for i in range(3):
+            step(resident[i % nb], i)
+        ms_x3 = timed(resident, args.steps, read_loss=False)
+        step = step_tf32
+        set_matmul_precision(args.precision)
+        exact = {"value": B * args.steps / (ms_x3 / 1e3), "unit": "samples/s", "ms_per_step": ms_x3 / args.steps,
+                 "dtype": "f32 tables / interaction / BatchNorm + 3xTF32 (error-compensated, fp32-grade) tower GEMMs on tcgen05"}
+
     # ---- kernel roofline: each embedding entry point timed alone, CUDA events on the launching stream,
     # L2 flushed (1 GiB written) before every launch, on the step's real tensors
     kern, roofline = kernel_roofline(model, resident, B, dev) if (rank == 0 and world == 1) else ({}, None)
@@ -397,7 +415,10 @@ def run_ours(args):
     line = {
         "metric": "train samples/s, Criteo-shape DeepFM", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, world),
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 tables / interaction / BatchNorm + " + ("tf32" if args.precision == "tf32" else "3xTF32 (fp32-grade)")
+                 + " tower GEMMs (tcgen05, fp32 accumulate)",
+        "data": "synthetic", "config": workload_config(B, world), "exact_mode": exact,
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "cuda_graph": not args.no_graph, "kernels": kern, "kernels_in_step": in_step,
@@ -408,7 +429,8 @@ def run_ours(args):
                        + ("; requester-side de-duplication: every distinct row crosses NVLink once per direction"
                           if getattr(getattr(model, "_sharded", None), "dedup", False) else ""),
         "clocks": clock_info,
-        "tower_matmul": "tcgen05 TF32 kernels (ctr_linear_fwd forward / dgrad, ctr_linear_wgrad), fp32 accumulate in TMEM",
+        "tower_matmul": "tcgen05 kernels (ctr_linear_fwd forward / dgrad, ctr_linear_wgrad), fp32 accumulate in TMEM; precision "
+                        + args.precision + " (parity: tests/test_gpu_precision.py)",
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
@@ -459,6 +481,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--roofline-only", action="store_true", help="only time the embedding entry points (ncu target)")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3"], help="tower GEMM precision of the headline run")
+    ap.add_argument("--no-exact", action="store_true", help="skip the extra timing of the 3xTF32 mode")
     ap.add_argument("--dedup", default="auto", choices=["auto", "on", "off"],
                     help="N > 1: fetch / send every distinct row once (auto: above 4 GPUs)")
     args = ap.parse_args()

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CTR_B200_ABI_VERSION 2
+#define CTR_B200_ABI_VERSION 3
 #define CTR_MAX_FEATURES 40 /* features per launch group (kernel-parameter budget) */
 
 /* status codes */
@@ -221,6 +221,18 @@ int ctr_linear_fwd(const float *A, int64_t lda, const float *W, int64_t ldw, con
 int64_t ctr_linear_wgrad_workspace_bytes(int32_t B, int32_t N, int32_t K);
 int ctr_linear_wgrad(const float *G, int64_t ldg, const float *X, int64_t ldx, int32_t B, int32_t N, int32_t K, float *dW,
                      int64_t lddw, void *workspace, int64_t workspace_bytes, void *stream);
+
+/* Error-compensated TF32 ("3xTF32"): the exact-fp32 mode of the two GEMMs above (parity bound 1e-5 of the tower,
+ * torchctr/models/dnn.py:35-46).  Splits x f32 [rows, cols] into TF32-representable parts hi = rna(x), lo = rna(x - hi)
+ * and writes three segments along the reduction axis of the GEMM that will consume them:
+ *   role 0 (left operand) hi | lo | hi,   role 1 (right operand) hi | hi | lo;
+ *   axis 1: out [rows, >= 3 * seg], segment k in columns [k * seg, k * seg + cols), seg = cols rounded up to 4 (tail = 0)
+ *           -> ctr_linear_fwd(A3, W3, K = 3 * seg);
+ *   axis 0: out [3 * rows, >= seg], segment k in rows [k * rows, (k + 1) * rows)
+ *           -> ctr_linear_wgrad(G3, X3, B = 3 * rows).
+ * A3 . W3^T = hi.hi + lo.hi + hi.lo with fp32 accumulation: error ~2^-21 relative per product. */
+int ctr_split_tf32(const float *x, int64_t ldx, int32_t rows, int32_t cols, float *out, int64_t ldo, int32_t axis,
+                   int32_t role, void *stream);
 
 /* ---- tower block: BatchNorm1d (training) + ReLU + Dropout around a Linear, fused --------------------------
  * Replaces the BatchNorm1d / ReLU / Dropout modules of torchctr/models/dnn.py:39-45 in training mode and the

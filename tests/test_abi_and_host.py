@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in names:
         assert hasattr(handle, name), f"{name} declared in ctr_b200.h but not exported"
     assert set(_lib.declared_symbols()) == set(names), "ctypes signature table out of sync with the header"
-    assert _lib.lib().ctr_abi_version() == 2
+    assert _lib.lib().ctr_abi_version() == _lib.ABI_VERSION
 
 
 def test_struct_layouts_match_the_header(tmp_path):

@@ -13,6 +13,7 @@ import torch
 from . import build as _build
 
 MAX_FEATURES = 40
+ABI_VERSION = 3          # CTR_B200_ABI_VERSION of include/ctr_b200.h
 
 OK = 0
 STATUS_INDEX_OOB = 1
@@ -98,6 +99,7 @@ _SIGNATURES = {
     "ctr_cross_combine_bwd": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, C.c_int32, _P]),
     "ctr_linear_fwd": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int32, _P]),
+    "ctr_split_tf32": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "ctr_route_workspace_bytes": (C.c_int64, [C.POINTER(Group), C.c_int32]),
     "ctr_route_build": (C.c_int, [C.POINTER(Group), C.c_int32, _P, _P, _P, _P, _P, C.c_int64, _P]),
     "ctr_route_grad_gather": (C.c_int, [C.POINTER(Group), C.c_int32, _P, C.c_int64, C.c_int32, _P, _P]),

@@ -154,9 +154,9 @@ class CTRModelBase(nn.Module):
 
     @staticmethod
     def _linear(x, weight, bias):
-        """Linear layer: the hand-written tcgen05 TF32 kernel when torch is allowed to use TF32 for matmuls
-        (``torch.backends.cuda.matmul.allow_tf32``), exact fp32 cuBLAS otherwise (the parity mode)."""
-        if torch.backends.cuda.matmul.allow_tf32:
+        """Linear layer on the hand-written tcgen05 kernel: TF32 when torch is allowed to use TF32 for matmuls
+        (``torch.backends.cuda.matmul.allow_tf32``), error-compensated 3xTF32 otherwise (the exact / parity mode)."""
+        if x.is_cuda:
             return linear_tc(x, weight, bias)
         return F.linear(x, weight, bias)
 

@@ -2,7 +2,7 @@ from .embedding import EmbeddingTable, PooledLookupGroup, SparseOptimizerBinding
 from .dynamic import DynamicEmbedding
 from .vocab import VocabIndex
 from .interaction import CrossLayer, fm_interaction
-from .linear import linear_tc
+from .linear import linear_tc, matmul_precision, set_matmul_precision
 
 __all__ = ["EmbeddingTable", "DynamicEmbedding", "VocabIndex", "PooledLookupGroup", "SparseOptimizerBinding",
-           "pooled_lookup", "CrossLayer", "fm_interaction"]
+           "pooled_lookup", "CrossLayer", "fm_interaction", "linear_tc", "matmul_precision", "set_matmul_precision"]

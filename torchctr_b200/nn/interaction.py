@@ -101,6 +101,6 @@ class CrossLayer(nn.Linear):
         pad = x.shape[1] - self.in_features
         w = F.pad(self.weight, (0, pad, 0, pad)) if pad else self.weight
         b = F.pad(self.bias, (0, pad)) if pad else self.bias
-        # dense contraction: tcgen05 TF32 kernel when TF32 matmuls are allowed, fp32 cuBLAS otherwise
-        u = linear_tc(x, w, None) if torch.backends.cuda.matmul.allow_tf32 else x @ w.t()
+        # dense contraction on the tcgen05 kernel: TF32 when TF32 matmuls are allowed, 3xTF32 (fp32-grade) otherwise
+        u = linear_tc(x, w, None)
         return _CrossFn.apply(x0, x, u, b)

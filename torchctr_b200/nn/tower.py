@@ -1,7 +1,7 @@
 """One block of the reference tower -- Linear, BatchNorm1d, ReLU, Dropout (``torchctr/models/dnn.py:39-45``) -- as a
 single autograd node in training mode (host side of kernels K6 / K6b).
 
-forward   z = x W^T + b (tcgen05 TF32 kernel, or exact fp32 ``addmm`` when TF32 matmuls are not allowed)
+forward   z = x W^T + b (tcgen05 kernel: TF32, or error-compensated 3xTF32 when TF32 matmuls are not allowed)
           -> batch statistics + running-statistics update (``ctr_bn_stats``)
           -> y = dropout(relu(batchnorm(z))) in one pass (``ctr_bn_relu_dropout_fwd``)
 backward  one reduction pass + one apply pass give dL/dz, dgamma, dbeta and the bias gradient
@@ -15,28 +15,28 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .linear import tc_eligible, wgrad_eligible
+from .linear import gemm_nt, gemm_wgrad, matmul_precision, tc_eligible, wgrad_eligible
 
 
 class _TowerBlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, bn, p_drop, seed_dev, layer_id, use_tc, gx_provider=None):
+    def forward(ctx, x, weight, bias, gamma, beta, bn, p_drop, seed_dev, layer_id, precision, gx_provider=None):
         w = weight.contiguous()
-        tc = bool(use_tc and tc_eligible(x, w))
-        z = ops.linear_fwd(x, w, bias) if tc else torch.addmm(bias, x, w.t())
+        tc = tc_eligible(x, w, precision)
+        z = gemm_nt(x, w, bias, precision=precision) if tc else torch.addmm(bias, x, w.t())
         track = bn.track_running_stats and bn.running_mean is not None
         mean, rstd = ops.bn_stats(z, bn.eps, bn.momentum, bn.running_mean if track else None,
                                   bn.running_var if track else None, bn.num_batches_tracked if track else None)
         y = ops.bn_relu_dropout_fwd(z, mean, rstd, gamma, beta, p_drop, seed_dev, layer_id)
         ctx.save_for_backward(x, w, z, mean, rstd, gamma, beta)
-        ctx.meta = (p_drop, seed_dev, layer_id, tc)
+        ctx.meta = (p_drop, seed_dev, layer_id, tc, precision)
         ctx.gx_provider = gx_provider
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, w, z, mean, rstd, gamma, beta = ctx.saved_tensors
-        p_drop, seed_dev, layer_id, tc = ctx.meta
+        p_drop, seed_dev, layer_id, tc, precision = ctx.meta
         if gy.stride(1) != 1 or gy.stride(0) % 4 != 0 or gy.data_ptr() % 16 != 0:
             gy = gy.contiguous()
         gz, dgamma, dbeta, dbias = ops.bn_relu_dropout_bwd(gy, z, mean, rstd, gamma, beta, p_drop, seed_dev, layer_id)
@@ -46,9 +46,9 @@ class _TowerBlockFn(torch.autograd.Function):
             out = ctx.gx_provider() if (tc and ctx.gx_provider is not None) else None
             if out is not None and tuple(out.shape) != tuple(x.shape):
                 out = None
-            gx = ops.linear_fwd(gz, w.t().contiguous(), out=out) if tc else gz @ w
+            gx = gemm_nt(gz, w.t().contiguous(), out=out, precision=precision) if tc else gz @ w
         if ctx.needs_input_grad[1]:
-            gw = ops.linear_wgrad(gz, x) if tc and wgrad_eligible(gz, x) else gz.t() @ x
+            gw = gemm_wgrad(gz, x, precision) if tc and wgrad_eligible(gz, x, precision) else gz.t() @ x
         return gx, gw, dbias, dgamma, dbeta, None, None, None, None, None, None
 
 
@@ -64,4 +64,4 @@ def tower_block(x, linear: nn.Linear, bn: nn.BatchNorm1d, drop: nn.Dropout, seed
     (the first layer reads a zero-padded copy, see ``CTRModelBase._first_linear``)."""
     w = linear.weight if weight is None else weight
     return _TowerBlockFn.apply(x, w, linear.bias, bn.weight, bn.bias, bn, float(drop.p), seed_dev, layer_id,
-                               torch.backends.cuda.matmul.allow_tf32, gx_provider)
+                               matmul_precision(), gx_provider)

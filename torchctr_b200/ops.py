@@ -387,6 +387,22 @@ def linear_fwd(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor | None = Non
     return out
 
 
+def split_tf32(x: torch.Tensor, axis: int, role: int) -> torch.Tensor:
+    """3xTF32 operand of ``x`` f32 [rows, cols] (``ctr_split_tf32``): hi / lo TF32 parts laid out as three segments along
+    the reduction axis of the GEMM that consumes them -- axis 1: [rows, 3 * seg] (seg = cols rounded up to 4) for
+    ``linear_fwd``; axis 0: [3 * rows, seg] for ``linear_wgrad``.  role 0 = left operand (hi, lo, hi), 1 = right (hi, hi, lo)."""
+    _lib.require_cuda(x, "x")
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be f32 [rows, cols] with unit inner stride")
+    rows, cols = x.shape
+    seg = (cols + 3) // 4 * 4
+    out = torch.empty((rows, 3 * seg) if axis == 1 else (3 * rows, seg), dtype=torch.float32, device=x.device)
+    with _timed("split_tf32"):
+        _lib.check(_lib.lib().ctr_split_tf32(x.data_ptr(), x.stride(0), rows, cols, out.data_ptr(), out.stride(0), axis, role,
+                                             _stream(x)), "ctr_split_tf32")
+    return out
+
+
 # ---- row-sharded tables over peer memory -----------------------------------------------------------------------
 def ptr_array(ptrs):
     """ctypes array of device pointers (one per rank)."""
