@@ -225,12 +225,12 @@ int ctr_linear_wgrad(const float *G, int64_t ldg, const float *X, int64_t ldx, i
 /* Error-compensated TF32 ("3xTF32"): the exact-fp32 mode of the two GEMMs above (parity bound 1e-5 of the tower,
  * torchctr/models/dnn.py:35-46).  Splits x f32 [rows, cols] into TF32-representable parts hi = rna(x), lo = rna(x - hi)
  * and writes three segments along the reduction axis of the GEMM that will consume them:
- *   role 0 (left operand) hi | lo | hi,   role 1 (right operand) hi | hi | lo;
+ *   role 0 (left operand) lo | hi | hi,   role 1 (right operand) hi | lo | hi   (small terms first, see split_tf32.cu);
  *   axis 1: out [rows, >= 3 * seg], segment k in columns [k * seg, k * seg + cols), seg = cols rounded up to 4 (tail = 0)
  *           -> ctr_linear_fwd(A3, W3, K = 3 * seg);
  *   axis 0: out [3 * rows, >= seg], segment k in rows [k * rows, (k + 1) * rows)
  *           -> ctr_linear_wgrad(G3, X3, B = 3 * rows).
- * A3 . W3^T = hi.hi + lo.hi + hi.lo with fp32 accumulation: error ~2^-21 relative per product. */
+ * A3 . W3^T = lo.hi + hi.lo + hi.hi with fp32 accumulation: error ~2^-21 relative per product. */
 int ctr_split_tf32(const float *x, int64_t ldx, int32_t rows, int32_t cols, float *out, int64_t ldo, int32_t axis,
                    int32_t role, void *stream);
 

@@ -3,10 +3,13 @@
 // The tensor cores read fp32 operands as TF32 (10-bit mantissa), which cannot meet the 1e-5 parity bound of the
 // tower of torchctr/models/dnn.py:35-46.  Every fp32 value is therefore split into two TF32-representable parts
 //     hi = rna_tf32(x),   lo = rna_tf32(x - hi)          (x - hi is exact in fp32)
-// and the product A.W^T is formed as  hi_a.hi_w + lo_a.hi_w + hi_a.lo_w  (the dropped lo.lo term is 2^-22 relative)
-// with fp32 accumulation in TMEM.  Rather than a second GEMM kernel, the three terms are laid out as ONE GEMM with a
-// three times longer reduction dimension: this kernel writes the segments
-//     role 0 (left operand):  [hi | lo | hi]        role 1 (right operand): [hi | hi | lo]
+// and the product A.W^T is formed as  lo_a.hi_w + hi_a.lo_w + hi_a.hi_w  (the dropped lo.lo term is 2^-22 relative)
+// with fp32 accumulation in TMEM.  The two small correction terms come FIRST: the tensor core truncates when it adds
+// into the accumulator (measured: the error grows linearly with the number of accumulation steps), so corrections added
+// to an already large accumulator would each lose up to one ulp of it; added from zero they lose an ulp of themselves.
+// Rather than a second GEMM kernel, the three terms are laid out as ONE GEMM with a three times longer reduction
+// dimension: this kernel writes the segments
+//     role 0 (left operand):  [lo | hi | hi]        role 1 (right operand): [hi | lo | hi]
 // side by side along the reduction axis -- along the columns for the K-major operands of ctr_linear_fwd (axis 1) or
 // stacked along the rows for the batch-reduced operands of ctr_linear_wgrad (axis 0) -- and the unchanged tcgen05
 // kernels contract over them.  Both parts have their low 13 mantissa bits clear, so the result does not depend on how
@@ -42,9 +45,9 @@ __global__ void __launch_bounds__(256)
         hi.x = rna_tf32(v.x); hi.y = rna_tf32(v.y); hi.z = rna_tf32(v.z); hi.w = rna_tf32(v.w);
         lo.x = rna_tf32(v.x - hi.x); lo.y = rna_tf32(v.y - hi.y); lo.z = rna_tf32(v.z - hi.z); lo.w = rna_tf32(v.w - hi.w);
         float *dst = out + (int64_t)r * ldo + c;
-        *reinterpret_cast<float4 *>(dst) = hi;
-        *reinterpret_cast<float4 *>(dst + seg_stride) = role == 0 ? lo : hi;
-        *reinterpret_cast<float4 *>(dst + 2 * seg_stride) = role == 0 ? hi : lo;
+        *reinterpret_cast<float4 *>(dst) = role == 0 ? lo : hi;
+        *reinterpret_cast<float4 *>(dst + seg_stride) = role == 0 ? hi : lo;
+        *reinterpret_cast<float4 *>(dst + 2 * seg_stride) = hi;
     }
 }
 
@@ -58,7 +61,7 @@ extern "C" int ctr_split_tf32(const float *x, int64_t ldx, int32_t rows, int32_t
     if (rows == 0) return CTR_OK;
     CTR_REQUIRE(x != nullptr && out != nullptr, "null pointer");
     CTR_REQUIRE(axis == 0 || axis == 1, "axis must be 0 (segments stacked along rows) or 1 (along columns)");
-    CTR_REQUIRE(role == 0 || role == 1, "role must be 0 (hi, lo, hi) or 1 (hi, hi, lo)");
+    CTR_REQUIRE(role == 0 || role == 1, "role must be 0 (lo, hi, hi) or 1 (hi, lo, hi)");
     const int cols4 = (cols + 3) / 4;
     const int64_t seg = (int64_t)cols4 * 4;
     CTR_REQUIRE(ldx >= cols, "ldx smaller than the row length");

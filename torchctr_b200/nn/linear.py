@@ -6,7 +6,7 @@ tcgen05 kernels (``ctr_linear_fwd`` / ``ctr_linear_wgrad``) in one of two precis
 ``"tf32"``    operands read as TF32 (10-bit mantissa), fp32 accumulate in TMEM -- the numerics of
               ``torch.backends.cuda.matmul.allow_tf32 = True``; chosen when that flag is on.
 ``"tf32x3"``  error-compensated: every operand is split into two TF32 parts (``ctr_split_tf32``) and the same kernels
-              contract over hi.hi + lo.hi + hi.lo -- fp32-grade results (~1e-6 relative), the exact mode the 1e-5
+              contract over lo.hi + hi.lo + hi.hi -- fp32-grade results (~1e-6 relative), the exact mode the 1e-5
               parity bound of the tower (``torchctr/models/dnn.py:35-46``) is tested in; chosen when ``allow_tf32`` is off.
 
 ``set_matmul_precision`` overrides the choice.  There is no library GEMM on this path: shapes the kernels cannot take
@@ -70,8 +70,8 @@ def gemm_nt(a: torch.Tensor, w: torch.Tensor, bias=None, act: int = 0, out=None,
 
 def gemm_wgrad(g: torch.Tensor, x: torch.Tensor, precision: str = "tf32") -> torch.Tensor:
     """``g.T @ x`` -> [N, K] on tcgen05: g [B, N], x [B, K]."""
-    if precision == "tf32x3":
-        return ops.linear_wgrad(ops.split_tf32(g, 0, 0), ops.split_tf32(x, 0, 1))
+    if precision == "tf32x3":      # the split pads the rows to a multiple of 4 floats: hand the kernel views of the real width
+        return ops.linear_wgrad(ops.split_tf32(g, 0, 0)[:, :g.shape[1]], ops.split_tf32(x, 0, 1)[:, :x.shape[1]])
     return ops.linear_wgrad(g, x)
 
 

@@ -390,7 +390,7 @@ def linear_fwd(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor | None = Non
 def split_tf32(x: torch.Tensor, axis: int, role: int) -> torch.Tensor:
     """3xTF32 operand of ``x`` f32 [rows, cols] (``ctr_split_tf32``): hi / lo TF32 parts laid out as three segments along
     the reduction axis of the GEMM that consumes them -- axis 1: [rows, 3 * seg] (seg = cols rounded up to 4) for
-    ``linear_fwd``; axis 0: [3 * rows, seg] for ``linear_wgrad``.  role 0 = left operand (hi, lo, hi), 1 = right (hi, hi, lo)."""
+    ``linear_fwd``; axis 0: [3 * rows, seg] for ``linear_wgrad``.  role 0 = left operand (lo, hi, hi), 1 = right (hi, lo, hi)."""
     _lib.require_cuda(x, "x")
     if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
         raise ValueError("x must be f32 [rows, cols] with unit inner stride")
