@@ -90,6 +90,12 @@ typedef struct ctr_feature {
     int32_t pooling;         /* CTR_POOL_*                                                   */
     int32_t index_kind;      /* CTR_INDEX_*                                                  */
     uint32_t hash_seed;
+    /* optional twin: a second, ONE-column table indexed by the same ids -- DeepFM's first-order weights
+     * w1_f[id] (oracle/models.py OracleDeepFM.linear_embeddings).  Its pooled value is added to
+     * group->extra[bag]; the fused update moves it with the main row (same optimizer, same hyper-parameters). */
+    float *twin_table;       /* [num_rows] fp32 or NULL                                      */
+    float *twin_state0;      /* optimizer state of the twin, same kinds as state0, [num_rows] */
+    float *twin_state1;      /* Adam v of the twin [num_rows] or NULL                        */
 } ctr_feature_t;
 
 /* A launch group: up to CTR_MAX_FEATURES features pooled for the same B bags into one
@@ -106,6 +112,15 @@ typedef struct ctr_group {
     int32_t dense_col;
     int32_t zero_from;       /* fwd: columns [zero_from, out_stride) are zero-filled; <0 = none */
     uint32_t *status;        /* device status word (CTR_STATUS_*), may be NULL               */
+    /* optional per-bag scalar fused into the lookup / update (single-id groups of one width only, i.e. Criteo-shaped
+     * DeepFM):  extra[b] = sum_f twin_f[id_bf]  +  (fm ? 0.5 * sum_d[(sum_f v_bfd)^2 - sum_f v_bfd^2] : 0)
+     * -- the first-order and FM second-order logit terms.  fwd writes extra and, when fm is set,
+     * fm_sum[b, :] = sum_f v_bf (f32 [B, D]); bwd reads extra as dL/d extra[b] and fm_sum, adds
+     * extra[b] * (fm_sum[b, :] - v_bf) to the row gradients and extra[b] to the twin gradients.  NULL = off. */
+    float *extra;            /* [B]                                                          */
+    float *fm_sum;           /* [B, D], needed when fm != 0                                  */
+    int32_t fm;
+    int32_t reserved;
 } ctr_group_t;
 
 /* Per-step scalars of the row update as the kernels consume them (fp32). */

@@ -39,6 +39,7 @@ class Feature(C.Structure):
         ("num_rows", C.c_int64),
         ("L", C.c_int32), ("D", C.c_int32), ("out_col", C.c_int32), ("pooling", C.c_int32),
         ("index_kind", C.c_int32), ("hash_seed", C.c_uint32),
+        ("twin_table", C.c_void_p), ("twin_state0", C.c_void_p), ("twin_state1", C.c_void_p),
     ]
 
 
@@ -49,6 +50,7 @@ class Group(C.Structure):
         ("dense", C.c_void_p), ("dense_width", C.c_int32), ("dense_col", C.c_int32),
         ("zero_from", C.c_int32),
         ("status", C.c_void_p),
+        ("extra", C.c_void_p), ("fm_sum", C.c_void_p), ("fm", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

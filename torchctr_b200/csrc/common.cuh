@@ -53,6 +53,9 @@ struct DevFeature {
     int32_t vec;       // 4: float4 lanes, 1: scalar lanes
     int32_t G;         // lanes that cover one row (power of two)
     int32_t aligned;   // 1 when float4 access to the pooled / grad matrix is 16-byte aligned
+    float *twin_table;   // one-column twin table (DeepFM first-order weights) or null
+    float *twin_state0;
+    float *twin_state1;
 };
 
 struct DevGroup {
@@ -66,6 +69,10 @@ struct DevGroup {
     int32_t dense_col;
     int32_t zero_from;
     uint32_t *status;
+    float *extra;        // [B] per-bag scalar: sum of twins (+ FM term) forward, its gradient backward; or null
+    float *fm_sum;       // [B, D] sum over the features of the pooled vectors (FM), or null
+    int32_t fm;
+    int32_t has_twin;    // some feature has a twin table
     // row-sharded tables (world > 1): row r of table f lives on rank (r + f) % world, at row
     // shard_adj[owner * num_features + f] + (r + f) / world of that rank's fused shard peer_tables[owner]
     int32_t world;

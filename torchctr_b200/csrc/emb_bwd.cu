@@ -16,6 +16,7 @@
 //          range order and updates those rows.  Summation order is fixed by the layout, so the
 //          result is deterministic.
 #include <stdlib.h>
+#include <string.h>
 
 #include "sort.cuh"
 
@@ -61,14 +62,21 @@ static PlanLayout plan_layout(const DevGroup &g, int scale = 1, int64_t capacity
     while ((rows >> bits) != 0) ++bits;  // bit_length(rows): 2^bits - 1 > every valid key
     p.key_bits = bits < 1 ? 1 : bits;
     const int passes = sort_num_passes(p.key_bits);
-    p.sorted_in_b = passes & 1;
+    const bool segmented = scale == 1 && capacity == 0;   // the single-GPU plan: one independent sort per table
+    p.sorted_in_b = segmented ? 1 : (passes & 1);
     int64_t off = 0;
     p.counters = off; off = align256(off + kCounterWords * 4);
     p.keys_a = off; off = align256(off + (S + 1) * 4);
     p.keys_b = off; off = align256(off + (S + 1) * 4);
     p.vals_a = off; off = align256(off + S * 4);
     p.vals_b = off; off = align256(off + S * 4);
-    const int64_t counts = sort_counts_elems(S);
+    int64_t counts = sort_counts_elems(S);
+    if (segmented) {
+        int64_t tiles = 0;
+        for (int i = 0; i < g.num_features; ++i) tiles += sort_num_tiles((int64_t)g.B * g.f[i].L);
+        const int64_t seg = seg_counts_elems(tiles, g.num_features);
+        if (seg > counts) counts = seg;
+    }
     p.counts = off; off = align256(off + counts * 4);
     const int64_t spine = scan_spine_elems(counts > S ? counts : S) + 8;
     p.spine = off; off = align256(off + spine * 4);
@@ -87,20 +95,22 @@ static PlanLayout plan_layout(const DevGroup &g, int scale = 1, int64_t capacity
 }
 
 // ---- keygen -------------------------------------------------------------------------------
-// Also builds the digit histograms of every radix pass (the sort then needs no pass of its own over the keys).
+// Also builds the digit histograms of every pass of the table's sort (the sort then needs no pass of its own over the
+// keys): hist[table][pass][digit], digits taken from the table-local row (sort.cuh, segmented variant).
 __global__ void __launch_bounds__(256)
-    emb_keygen_kernel(const __grid_constant__ DevGroup g, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
-                      uint32_t *__restrict__ hist, int passes, int bits) {
-    __shared__ uint32_t sh[kMaxPasses][kMaxRadix];
-    for (int i = threadIdx.x; i < kMaxPasses * kMaxRadix; i += blockDim.x) (&sh[0][0])[i] = 0;
-    __syncthreads();
+    emb_keygen_kernel(const __grid_constant__ DevGroup g, const __grid_constant__ SegSortDesc sd, uint32_t *__restrict__ keys,
+                      uint32_t *__restrict__ vals, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t sh[kSegMaxPasses][kMaxRadix];
     const int fi = blockIdx.y;
     const DevFeature &f = g.f[fi];
-    int64_t slot_base = 0;
-    for (int i = 0; i < fi; ++i) slot_base += (int64_t)g.B * g.f[i].L;
+    const int passes = sd.passes[fi], bits = sd.digit_bits[fi], kb = sd.key_bits[fi];
+    const int radix = 1 << bits;
+    for (int i = threadIdx.x; i < passes * kMaxRadix; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t slot_base = sd.slot_base[fi];
     const int64_t n = (int64_t)g.B * f.L;
     const int lane = threadIdx.x & 31;
-    const uint32_t dmask = (1u << bits) - 1u;
+    const uint32_t dmask = (uint32_t)radix - 1u;
     const int64_t nround = (n + 31) / 32 * 32;   // whole warps iterate together (match.any below)
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += (int64_t)gridDim.x * blockDim.x) {
         const bool valid = j < n;
@@ -111,18 +121,46 @@ __global__ void __launch_bounds__(256)
             keys[slot_base + j] = key;
             vals[slot_base + j] = (uint32_t)j;
         }
+        const uint32_t local = seg_local_key(key, f.row_base, kb);
         for (int p = 0; p < passes; ++p) {
-            const uint32_t d = (key >> (p * bits)) & dmask;
+            const uint32_t d = (local >> (p * bits)) & dmask;
             const uint32_t peers = __match_any_sync(kFull, valid ? d : (uint32_t)(kMaxRadix + lane));
             if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[p][d], (uint32_t)__popc(peers));
         }
     }
     __syncthreads();
-    const int radix = 1 << bits;
+    uint32_t *dst = hist + (size_t)fi * kSegMaxPasses * kMaxRadix;
     for (int i = threadIdx.x; i < passes * radix; i += blockDim.x) {
         const uint32_t c = sh[i / radix][i % radix];
-        if (c) atomicAdd(&hist[(i / radix) * kMaxRadix + (i % radix)], c);
+        if (c) atomicAdd(&dst[(i / radix) * kMaxRadix + (i % radix)], c);
     }
+}
+
+// the per-table sort layout of a group (host)
+static void seg_desc(const DevGroup &g, SegSortDesc *sd) {
+    memset(sd, 0, sizeof(*sd));
+    sd->num_tables = g.num_features;
+    uint32_t tile = 0, slot = 0;
+    int maxp = 1;
+    for (int i = 0; i < g.num_features; ++i) {
+        const int64_t n = (int64_t)g.B * g.f[i].L;
+        sd->tile_base[i] = tile;
+        sd->slot_base[i] = slot;
+        sd->row_base[i] = g.f[i].row_base;
+        int bits = 0;
+        while (((uint64_t)g.f[i].num_rows >> bits) != 0) ++bits;       // bit_length(V): 2^bits - 1 >= V > every valid row
+        if (bits < 1) bits = 1;
+        const int passes = seg_num_passes(bits);
+        sd->key_bits[i] = (uint8_t)bits;
+        sd->passes[i] = (uint8_t)passes;
+        sd->digit_bits[i] = (uint8_t)((bits + passes - 1) / passes);
+        if (passes > maxp) maxp = passes;
+        tile += (uint32_t)sort_num_tiles(n);
+        slot += (uint32_t)n;
+    }
+    sd->tile_base[g.num_features] = tile;
+    sd->slot_base[g.num_features] = slot;
+    sd->max_passes = maxp;
 }
 
 __global__ void reset_counters_kernel(uint32_t *counters, uint32_t runs_built) {
@@ -549,7 +587,8 @@ __global__ void __launch_bounds__(kApplyThreads, 3)
         uint32_t lo = 0, hi = w - 1;
         while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (a.keys[(mid + 1) * a.range - 1] >= first_key) hi = mid; else lo = mid + 1;
+            // padding keys (0xffffffff) sit at the end of every table's segment: "+ 1" wraps them to 0, below every valid key
+            if (a.keys[(mid + 1) * a.range - 1] + 1u >= first_key + 1u) hi = mid; else lo = mid + 1;
         }
         // wait until every range the run passed through has published, fence ONCE, then read the partial sums
         for (uint32_t j = lo + lane; j < w; j += kWarp)
@@ -631,18 +670,15 @@ extern "C" int ctr_emb_bwd_plan_ex(const ctr_group_t *group, void *workspace, in
         if (bx > per_feature) bx = per_feature;
         if (bx < 1) bx = 1;
         uint32_t *scratch = reinterpret_cast<uint32_t *>(ws + p.counts);
-        rc = radix_sort_prepare(scratch, p.S, p.key_bits, stream);
+        static thread_local SegSortDesc sd;
+        seg_desc(dg, &sd);
+        rc = seg_sort_prepare(scratch, sd, stream);
         if (rc != CTR_OK) return rc;
-        note_launch(), emb_keygen_kernel<<<dim3((unsigned)bx, dg.num_features), 256, 0, stream>>>(
-            dg, keys_a, vals_a, sort_hist(scratch), sort_num_passes(p.key_bits), sort_digit_bits(p.key_bits));
+        note_launch(), emb_keygen_kernel<<<dim3((unsigned)bx, dg.num_features), 256, 0, stream>>>(dg, sd, keys_a, vals_a,
+                                                                                                  seg_hist(scratch));
         CTR_CUDA_OK(cudaGetLastError());
-    }
-    rc = radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, p.S, p.key_bits, reinterpret_cast<uint32_t *>(ws + p.counts),
-                          reinterpret_cast<uint32_t *>(ws + p.spine), stream, /*hist_ready=*/true);
-    if (rc < 0) return rc;
-    if (p.S > 0 && rc != p.sorted_in_b) {
-        set_error("internal: sort parity mismatch");
-        return CTR_E_CUDA;
+        rc = seg_sort_pairs(sd, keys_a, vals_a, keys_b, vals_b, scratch, stream);
+        if (rc < 0) return rc;
     }
     if (!want_runs) return CTR_OK;
     const uint32_t *sorted_keys = p.sorted_in_b ? keys_b : keys_a;

@@ -39,6 +39,10 @@ int lower_group(const ctr_group_t *g, DevGroup *out, bool need_tables, bool need
     out->dense_width = g->dense_width;
     out->dense_col = g->dense_col;
     out->status = g->status;
+    out->extra = g->extra;
+    out->fm_sum = g->fm_sum;
+    out->fm = g->fm ? 1 : 0;
+    CTR_REQUIRE(!g->fm || (g->extra != nullptr && g->fm_sum != nullptr), "fm needs extra [B] and fm_sum [B, D]");
     out->zero_from = (g->zero_from >= 0 && g->zero_from < g->out_stride) ? g->zero_from : -1;
     CTR_REQUIRE(g->dense_width == 0 || (g->dense_col >= 0 && g->dense_col + (int64_t)g->dense_width <= g->out_stride),
                 "dense block [%d, %d) outside out_stride=%lld", g->dense_col, g->dense_col + g->dense_width,
@@ -72,6 +76,13 @@ int lower_group(const ctr_group_t *g, DevGroup *out, bool need_tables, bool need
         d.pooling = s.pooling;
         d.index_kind = s.index_kind;
         d.hash_seed = s.hash_seed;
+        d.twin_table = s.twin_table;
+        d.twin_state0 = s.twin_state0;
+        d.twin_state1 = s.twin_state1;
+        if (s.twin_table != nullptr) {
+            CTR_REQUIRE(g->extra != nullptr, "feature %d: a twin table needs group->extra [B]", i);
+            out->has_twin = 1;
+        }
         if (s.index_kind == CTR_INDEX_REMAP) {
             CTR_REQUIRE(s.map != nullptr && s.map->keys != nullptr && s.map->rows != nullptr,
                         "feature %d: REMAP needs a vocabulary map", i);

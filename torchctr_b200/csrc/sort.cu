@@ -12,10 +12,11 @@ struct ArrayIn {
     const uint32_t *p;
     __device__ __forceinline__ uint32_t operator()(int64_t i) const { return p[i]; }
 };
-struct HeadIn {  // 1 where a run of equal keys starts
+struct HeadIn {  // 1 where a run of equal VALID keys starts (padding, 0xffffffff, may sit at the end of every table)
     const uint32_t *keys;
     __device__ __forceinline__ uint32_t operator()(int64_t i) const {
-        return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+        const uint32_t k = keys[i];
+        return (k != 0xffffffffu && (i == 0 || k != keys[i - 1])) ? 1u : 0u;
     }
 };
 struct ArrayOut {
@@ -36,7 +37,7 @@ struct RunsOut {
     __device__ __forceinline__ void finish(uint32_t total) const {
         run_start[total] = (uint32_t)n;
         counters[0] = total;
-        counters[1] = total - ((n > 0 && keys[n - 1] == 0xffffffffu) ? 1u : 0u);
+        counters[1] = total;
     }
 };
 
@@ -280,6 +281,158 @@ __global__ void __launch_bounds__(kSortThreads, 3)
             vals_out[dst] = v[r];
         }
     }
+}
+
+// One launch of the segmented sort (see sort.cuh): tile -> table by the static tile layout, digits from the table-local
+// row, look-back only over the tiles of the same table.  Tables whose passes have not started yet leave at once.
+__global__ void __launch_bounds__(kSortThreads, 3)
+    radix_seg_kernel(const __grid_constant__ SegSortDesc sd, const uint32_t *__restrict__ keys_in,
+                     const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                     int launch, const uint32_t *__restrict__ hist, uint32_t *status, uint32_t *ticket) {
+    constexpr int RADIX = kMaxRadix;
+    constexpr int DPT = RADIX / kSortThreads;   // digits per thread
+    constexpr int kWarps = kSortThreads / kWarp;
+    __shared__ uint32_t wh[kWarps][RADIX];
+    __shared__ uint32_t base[RADIX];
+    __shared__ uint32_t scratch[33];
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    int f = 0;
+    {
+        int lo = 0, hi = sd.num_tables - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (sd.tile_base[mid] <= tile) lo = mid; else hi = mid - 1;
+        }
+        f = lo;
+    }
+    const int first_launch = sd.max_passes - (int)sd.passes[f];
+    if (launch < first_launch) return;                       // block-uniform
+    const int pass = launch - first_launch;
+    const int w = sd.digit_bits[f], kb = sd.key_bits[f];
+    const int shift = pass * w;
+    const uint32_t dmask = (1u << w) - 1u;
+    const uint32_t rbase = sd.row_base[f];
+    const uint32_t tile0 = sd.tile_base[f];
+    const uint32_t seg_begin = sd.slot_base[f], seg_end = sd.slot_base[f + 1];
+    for (int i = threadIdx.x; i < kWarps * RADIX; i += kSortThreads) (&wh[0][0])[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t warp_base = seg_begin + (tile - tile0) * (uint32_t)kSortTile + (uint32_t)warp * (kWarp * kSortItems);
+    uint32_t k[kSortItems], v[kSortItems];
+    uint16_t rank[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t i = warp_base + r * kWarp + lane;
+        k[r] = i < seg_end ? keys_in[i] : 0xffffffffu;
+        v[r] = i < seg_end ? vals_in[i] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const bool valid = warp_base + r * kWarp + lane < seg_end;
+        const uint32_t d = (seg_local_key(k[r], rbase, kb) >> shift) & dmask;
+        const uint32_t peers = __match_any_sync(kFull, valid ? d : (uint32_t)(RADIX + lane));
+        const int leader = __ffs(peers) - 1;
+        uint32_t pre = 0;
+        if (valid && lane == leader) {
+            pre = wh[warp][d];
+            wh[warp][d] = pre + (uint32_t)__popc(peers);
+        }
+        pre = __shfl_sync(kFull, pre, leader);
+        rank[r] = (uint16_t)(pre + (uint32_t)__popc(peers & ((1u << lane) - 1u)));
+        __syncwarp();
+    }
+    __syncthreads();
+    const uint32_t *ghist = hist + ((size_t)f * kSegMaxPasses + pass) * RADIX;
+    uint32_t *st = status + (size_t)launch * sd.tile_base[sd.num_tables] * RADIX;
+    uint32_t gsum = 0, gh[DPT];
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) {
+        gh[j] = ghist[threadIdx.x * DPT + j];
+        gsum += gh[j];
+    }
+    uint32_t total;
+    uint32_t gbase = seg_begin + block_exclusive_256(gsum, scratch, &total);
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) {
+        const int d = threadIdx.x * DPT + j;
+        uint32_t count = 0;
+#pragma unroll
+        for (int ww = 0; ww < kWarps; ++ww) {
+            const uint32_t c = wh[ww][d];
+            wh[ww][d] = count;          // exclusive over the warps of this tile
+            count += c;
+        }
+        uint32_t prefix = 0;
+        if ((uint32_t)d <= dmask) {     // digits this table does not have are never looked up
+            uint32_t *mine = st + (size_t)tile * RADIX + d;
+            if (tile == tile0) {
+                st_status(mine, count | kFlagInc);
+            } else {
+                st_status(mine, count | kFlagAgg);
+                constexpr int kLook = 8;
+                int64_t prev = (int64_t)tile - 1;
+                bool done = false;
+                while (!done) {
+                    uint32_t sv[kLook];
+#pragma unroll
+                    for (int i = 0; i < kLook; ++i)
+                        sv[i] = prev - i >= (int64_t)tile0 ? ld_status(st + (size_t)(prev - i) * RADIX + d) : kFlagInc;
+#pragma unroll
+                    for (int i = 0; i < kLook; ++i) {
+                        if (!done) {
+                            while ((sv[i] & (kFlagAgg | kFlagInc)) == 0u) sv[i] = ld_status(st + (size_t)(prev - i) * RADIX + d);
+                            prefix += sv[i] & kValMask;
+                            done = (sv[i] & kFlagInc) != 0u;
+                        }
+                    }
+                    prev -= kLook;
+                }
+                st_status(mine, (prefix + count) | kFlagInc);
+            }
+        }
+        base[d] = gbase + prefix;
+        gbase += gh[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        if (warp_base + r * kWarp + lane < seg_end) {
+            const uint32_t d = (seg_local_key(k[r], rbase, kb) >> shift) & dmask;
+            const uint32_t dst = base[d] + wh[warp][d] + rank[r];
+            keys_out[dst] = k[r];
+            vals_out[dst] = v[r];
+        }
+    }
+}
+
+int seg_sort_prepare(uint32_t *counts, const SegSortDesc &sd, cudaStream_t stream) {
+    const size_t total_tiles = sd.tile_base[sd.num_tables];
+    const size_t zero_elems = 8 + (size_t)seg_hist_elems(sd.num_tables) + (size_t)sd.max_passes * total_tiles * kMaxRadix;
+    cudaError_t e = cudaMemsetAsync(counts, 0, zero_elems * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return cuda_fail(e, "segmented sort scratch memset");
+    return CTR_OK;
+}
+
+int seg_sort_pairs(const SegSortDesc &sd, uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
+                   uint32_t *counts, cudaStream_t stream) {
+    const uint32_t total_tiles = sd.tile_base[sd.num_tables];
+    if (total_tiles == 0) return CTR_OK;
+    uint32_t *tickets = counts;
+    const uint32_t *hist = seg_hist(counts);
+    uint32_t *status = counts + 8 + seg_hist_elems(sd.num_tables);
+    uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
+    for (int l = 0; l < sd.max_passes; ++l) {
+        note_launch(), radix_seg_kernel<<<total_tiles, kSortThreads, 0, stream>>>(sd, kin, vin, kout, vout, l, hist, status,
+                                                                                  tickets + l);
+        uint32_t *t = kin; kin = kout; kout = t;
+        t = vin; vin = vout; vout = t;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "seg_sort_pairs");
+    return CTR_OK;
 }
 
 template <int BITS>

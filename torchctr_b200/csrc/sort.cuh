@@ -48,6 +48,44 @@ int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint3
 int radix_sort_prepare(uint32_t *counts, int64_t n, int key_bits, cudaStream_t stream);
 inline uint32_t *sort_hist(uint32_t *counts) { return counts + 8; }
 
+// ---- segmented variant: one independent sort per table of a launch group --------------------------------------------
+// The id slots of a group are laid out table after table, so the pairs are ALREADY partitioned by table: what is left
+// is to sort each table's segment by row.  Doing that as independent sorts (instead of one global 26-bit sort) gives
+//   * digits sized to the table: ceil(bit_length(V) / passes) bits, 1 pass for V < 512, 3 up to 2^27 rows, 5 beyond
+//     (always odd, and a table's passes are the LAST launches, so every table ends in the b buffers);
+//   * look-back chains that span one table's tiles (16 for a 65536-bag batch) instead of all ~400 tiles of the launch:
+//     the chain, not bandwidth, is what a single-wave onesweep pass costs.
+// Keys stay global (row_base + row, or 0xffffffff for padding, which sorts to the end of ITS table); digits are taken
+// from the table-local row.
+constexpr int kSegMaxPasses = 5;
+struct SegSortDesc {
+    int32_t num_tables;
+    int32_t max_passes;                                // launches: the largest passes[] (odd)
+    uint32_t tile_base[CTR_MAX_FEATURES + 1];          // first tile of every table, [num_tables] = total tiles
+    uint32_t slot_base[CTR_MAX_FEATURES + 1];          // first slot (sorted position) of every table
+    uint32_t row_base[CTR_MAX_FEATURES];
+    uint8_t key_bits[CTR_MAX_FEATURES];                // bit_length(num_rows): 2^bits - 1 > every valid local row
+    uint8_t digit_bits[CTR_MAX_FEATURES];
+    uint8_t passes[CTR_MAX_FEATURES];
+};
+inline int seg_num_passes(int key_bits) { return key_bits <= kMaxRadixBits ? 1 : (key_bits <= 3 * kMaxRadixBits ? 3 : 5); }
+// scratch, in u32 elements: [tickets 8][histograms tables x kSegMaxPasses x kMaxRadix][tile status launches x tiles x kMaxRadix]
+inline int64_t seg_hist_elems(int num_tables) { return (int64_t)num_tables * kSegMaxPasses * kMaxRadix; }
+inline int64_t seg_counts_elems(int64_t total_tiles, int num_tables) {
+    return 8 + seg_hist_elems(num_tables) + (int64_t)kSegMaxPasses * total_tiles * kMaxRadix;
+}
+inline uint32_t *seg_hist(uint32_t *counts) { return counts + 8; }
+// zeroes the scratch (tickets, histograms, the tile status of the launches that will run)
+int seg_sort_prepare(uint32_t *counts, const SegSortDesc &sd, cudaStream_t stream);
+// histograms must have been filled by the caller ([table][pass][digit], pass 0 = least significant digit); the
+// sorted pairs end in (keys_b, vals_b).
+int seg_sort_pairs(const SegSortDesc &sd, uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
+                   uint32_t *counts, cudaStream_t stream);
+// table-local sort key of a global key
+__device__ __forceinline__ uint32_t seg_local_key(uint32_t key, uint32_t row_base, int key_bits) {
+    return key == 0xffffffffu ? ((1u << key_bits) - 1u) : key - row_base;
+}
+
 // Given sorted keys: run_start[r] = first position of the r-th run of equal keys, run_start[R] = n,
 // counters[0] = R (all runs), counters[1] = number of runs whose key != 0xffffffff.
 // spine: scan_spine_elems(n) u32.
