@@ -348,3 +348,92 @@ def test_sort_only_plan_counts_unique_rows_and_updates():
     ref = table.cuda().index_add(0, ids.cuda()[:, 0], gout.cuda(), alpha=-0.5)
     close(t, ref, rtol=2e-5)
     assert int(nu.item()) == int(torch.unique(ids).numel())
+
+
+@pytest.mark.parametrize("D,F,opt_kind", [(16, 26, "adagrad"), (16, 5, "sgd"), (32, 7, "adam"), (64, 3, "rowwise_adagrad"), (16, 9, "adagrad")])
+def test_fused_twin_and_fm_terms_match_the_separate_kernels(D, F, opt_kind):
+    """ctr_group_t.extra: the first-order (twin) tables and the FM second-order term folded into the single-id lookup
+    and into the fused update must equal the oracle's definitions: extra[b] = sum_f w1_f[id] + FM2(v_b), row gradients
+    = grad_out slice + g_extra[b] * (sum_f v_bf - v_bf), twin gradients = sum of g_extra over the run -- then the same
+    optimizer arithmetic as torch.optim on the touched rows (1e-5)."""
+    from oracle import embedding as oe
+    from oracle import optim as oo
+    from oracle.models import fm_second_order
+    from torchctr_b200 import ops
+    gen = torch.Generator().manual_seed(D * F)
+    B = 3000
+    Vs = [37 + 11 * i if i % 2 else 5000 + i for i in range(F)]
+    hashed = F == 9                                             # raw ids through the in-kernel murmur3 as well
+    tables = [torch.randn(V, D, generator=gen) for V in Vs]
+    twins = [torch.randn(V, generator=gen) for V in Vs]
+    if hashed:
+        raw = [torch.randint(0, 2 ** 40, (B, 1), generator=gen) for _ in Vs]
+        from oracle import hashing as oh
+        rows = [torch.from_numpy(oh.hash_bucket_ids(r.numpy(), V, 7)).long() for r, V in zip(raw, Vs)]
+    else:
+        # Zipf-like: long runs of the hot rows cross many sweep ranges
+        rows = [((V ** torch.rand(B, 1, generator=gen)) - 1).long().clamp_(0, V - 1) for V in Vs]
+        raw = rows
+    stride = (F * D + 3 + 3) // 4 * 4
+    dense = torch.randn(B, 3, generator=gen)
+    dev = "cuda"
+    t_dev = [t.clone().to(dev) for t in tables]
+    w_dev = [t.clone().to(dev) for t in twins]
+    kind_states = {"sgd": 0, "adagrad": 1, "rowwise_adagrad": 1, "adam": 2}[opt_kind]
+    def state_like(t, rowwise):
+        return torch.zeros(t.shape[0] if rowwise else t.shape, device=dev)
+    s0 = [state_like(t, opt_kind == "rowwise_adagrad") for t in t_dev] if kind_states >= 1 else [None] * F
+    s1 = [torch.zeros_like(t) for t in t_dev] if kind_states == 2 else [None] * F
+    ws0 = [torch.zeros_like(t) for t in w_dev] if kind_states >= 1 else [None] * F
+    ws1 = [torch.zeros_like(t) for t in w_dev] if kind_states == 2 else [None] * F
+    ids_dev = [r.to(dev) for r in raw]
+    out = torch.empty(B, stride, device=dev)
+    extra = torch.empty(B, device=dev)
+    fm_sum = torch.empty(B, D, device=dev)
+    def specs(with_state):
+        return [ops.FeatureSpec(ids=ids_dev[i], table=t_dev[i], num_rows=Vs[i], D=D, out_col=i * D,
+                                index_kind="hash" if hashed else "direct", hash_seed=7, twin_table=w_dev[i],
+                                state0=s0[i] if with_state else None, state1=s1[i] if with_state else None,
+                                twin_state0=ws0[i] if with_state else None, twin_state1=ws1[i] if with_state else None)
+                for i in range(F)]
+    fwd = ops.make_group(specs(False), B, out, stride, dense=dense.to(dev), dense_col=F * D, zero_from=F * D + 3,
+                         extra=extra, fm_sum=fm_sum, fm=True)
+    ops.emb_pool_fwd(fwd)
+    pooled = [t[r[:, 0]] for t, r in zip(tables, rows)]
+    ref_out = torch.zeros(B, stride)
+    ref_out[:, :F * D] = torch.cat(pooled, 1)
+    ref_out[:, F * D:F * D + 3] = dense
+    ref_extra = sum(w[r[:, 0]] for w, r in zip(twins, rows)) + fm_second_order(torch.stack(pooled, 1))[:, 0]
+    assert torch.equal(out.cpu(), ref_out)                       # single-id lookups are copies: bit-exact
+    close(extra.cpu(), ref_extra, 1e-5)
+    close(fm_sum.cpu(), torch.stack(pooled, 1).sum(1), 1e-5)
+    # backward + fused update
+    gout = torch.randn(B, stride, generator=gen) * 0.1
+    gextra = torch.randn(B, generator=gen) * 0.1
+    bwd = ops.make_group(specs(True), B, gout.to(dev), stride, extra=gextra.to(dev), fm_sum=fm_sum, fm=True)
+    ws = torch.empty(ops.emb_bwd_workspace_bytes(bwd) + 256, dtype=torch.uint8, device=dev)
+    ops.emb_bwd_plan(bwd, ws, runs=False)
+    lr = 0.05
+    ops.emb_bwd_apply(bwd, ws, ops.make_opt(opt_kind, lr=lr, eps=1e-8 if opt_kind == "adam" else 1e-10, step=1))
+    torch.cuda.synchronize()
+    ssum = torch.stack(pooled, 1).sum(1)
+    for i in range(F):
+        slot_grad = gout[:, i * D:(i + 1) * D] + gextra[:, None] * (ssum - pooled[i])
+        g_rows = torch.zeros(Vs[i], D).index_add_(0, rows[i][:, 0], slot_grad)
+        g_twin = torch.zeros(Vs[i]).index_add_(0, rows[i][:, 0], gextra)
+        touched = torch.zeros(Vs[i], dtype=torch.bool)
+        touched[rows[i][:, 0]] = True
+        for tab, grad, got, wide in ((tables[i], g_rows, t_dev[i], True), (twins[i][:, None], g_twin[:, None], w_dev[i][:, None], False)):
+            ref = tab.clone()
+            g = grad[touched]
+            if opt_kind == "sgd":
+                ref[touched] -= lr * g
+            elif opt_kind == "adagrad" or (opt_kind == "rowwise_adagrad" and not wide):
+                ref[touched] -= lr * g / (g.pow(2).sqrt() + 1e-10)
+            elif opt_kind == "rowwise_adagrad":
+                ref[touched] -= lr * g / (g.pow(2).mean(1, keepdim=True).sqrt() + 1e-10)
+            else:                                                   # lazy Adam, step 1: m = (1-b1) g, v = (1-b2) g^2
+                m, v = 0.1 * g, 0.001 * g * g
+                ref[touched] -= (lr * (1 - 0.999) ** 0.5 / (1 - 0.9)) * m / (v.sqrt() + 1e-8)
+            close(got.cpu(), ref, 2e-5 if opt_kind != "sgd" else 1e-5)
+            assert torch.equal(got.cpu()[~touched], tab[~touched])      # untouched rows do not move

@@ -88,6 +88,7 @@ static PlanLayout plan_layout(const DevGroup &g, int scale = 1, int64_t capacity
     // partial sums of runs that cross a range boundary: [range][team lane] float4
     int row_floats = 4;
     for (int i = 0; i < g.num_features; ++i) row_floats = max(row_floats, g.f[i].G * 4);
+    row_floats += 4;      // one more float4 slot: the summed per-bag coefficient of the fused DeepFM terms
     p.row_floats = row_floats;
     p.tail_part = off; off = align256(off + p.max_ranges * row_floats * 4);
     p.total = off;
@@ -193,6 +194,8 @@ struct ApplyArgs {
     const ctr_hyper_t *hyper_dev;  // device copy read at run time (CUDA-graph replays see new values)
     int team;                   // lanes per sorted position (max G of the group), power of two
     uint32_t *status;           // group status word (may be null)
+    const float *extra_grad;    // [B] dL/d extra[bag] (twin tables + FM term), or null
+    const float *fm_sum;        // [B, D] sum over the fields of the pooled vectors, or null
 };
 
 // last feature whose row_base <= key.  sf is the kernel's parameter copy of the features: sorted positions
@@ -390,8 +393,8 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 // the range started is finished by the warp that sees its end, which adds the partial sums the earlier ranges
 // published (in range order) -- no second kernel.
 // VEC = 4: lanes hold float4 pieces of the rows (some feature has D % 4 == 0); VEC = 1: every feature is scalar-laned.
-// SIMPLE: every table has D % 4 == 0, 16-byte aligned gradient slices, L == 1, no per-id weight, sum pooling.
-template <int VEC, bool SIMPLE, bool INL>
+// (Single-id groups of one width take emb_bwd_sweep_l1_kernel below instead.)
+template <int VEC>
 __global__ void __launch_bounds__(kApplyThreads, 3)
     emb_bwd_sweep_kernel(const __grid_constant__ DevGroup g, const __grid_constant__ ApplyArgs a_in) {
     __shared__ ApplyArgs sa;
@@ -491,10 +494,7 @@ __global__ void __launch_bounds__(kApplyThreads, 3)
                         f_hi = f_lo + sf[fi].num_rows;
                     }
                     const DevFeature &f = sf[fi];
-                    if (SIMPLE) {   // every table: D % 4 == 0, aligned slices, single-id bags, plain sum
-                        if (t < f.G)
-                            v[u] = __ldg(reinterpret_cast<const float4 *>(gout + (int64_t)sl * gstride + f.out_col) + t);
-                    } else if (t < f.G && t * f.vec < f.D) {
+                    if (t < f.G && t * f.vec < f.D) {
                         const uint32_t bag = f.L == 1 ? sl : sl / (uint32_t)f.L;
                         const float4 x = load_grad_part(gout, gstride, f, bag, t);
                         if (f.id_weight != nullptr || f.pooling == CTR_POOL_MEAN) {
@@ -552,8 +552,7 @@ __global__ void __launch_bounds__(kApplyThreads, 3)
                             f_hi = f_lo + sf[fi].num_rows;
                         }
                         const DevFeature &f = sf[fi];
-                        if (INL) update_row(f, a, p0 + idx, fi, key - f.row_base, t, t < f.G && t * f.vec < f.D, acc, tmask, TG);
-                        else update_row_call(f, a, p0 + idx, fi, key - f.row_base, t, t < f.G && t * f.vec < f.D, acc, tmask, TG);
+                        update_row_call(f, a, p0 + idx, fi, key - f.row_base, t, t < f.G && t * f.vec < f.D, acc, tmask, TG);
                     }
                     acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
@@ -610,6 +609,309 @@ __global__ void __launch_bounds__(kApplyThreads, 3)
             const DevFeature &f = sf[hf];
             update_row_call(f, a, first, hf, first_key - f.row_base, t, t < f.G && t * f.vec < f.D, sum,
                             TG == kWarp ? kFull : ((1u << TG) - 1u), TG);
+        }
+    }
+}
+
+
+// ---- the sweep for Criteo-shaped groups: single-id bags, one width D = 4 * TG, aligned slices, sum pooling ----------
+// Same algorithm as emb_bwd_sweep_kernel with everything about the lane layout known at compile time (P = 32 / TG teams,
+// U = 4 positions per team, Q = P * U positions per outer iteration: no local-memory arrays, no runtime divisions), and,
+// with EXTRA, the DeepFM terms folded in: every position also carries c = dL/d extra[bag]; the gradient of its row is
+//     grad_out[bag, cols] + c * (fm_sum[bag, :] - row)        (FM second order; the "- row * sum c" part is applied once
+// per run, when the row has been loaded for its update anyway) and the gradient of its twin (first-order weight) is
+// sum c.  That removes the FM backward pass over [B, F * D] and the whole D = 1 launch group of DeepFM.
+template <bool EXTRA>
+__device__ __forceinline__ void update_row_l1(const DevFeature &f, const ApplyArgs &a, uint32_t pos, int fi, uint32_t row, int t,
+                                              float4 gr, float cs, bool fm, unsigned mask, int team_lanes) {
+    if (!EXTRA) {
+        update_row(f, a, pos, fi, row, t, true, gr, mask, team_lanes);
+        return;
+    }
+    const size_t off = (size_t)row * f.D + (size_t)t * 4;
+    float4 w = *reinterpret_cast<float4 *>(f.table + off);
+    if (fm) {
+        gr.x = fmaf(-cs, w.x, gr.x); gr.y = fmaf(-cs, w.y, gr.y); gr.z = fmaf(-cs, w.z, gr.z); gr.w = fmaf(-cs, w.w, gr.w);
+    }
+    if (a.kind == CTR_OPT_SGD) {
+        w.x -= a.h.lr * gr.x; w.y -= a.h.lr * gr.y; w.z -= a.h.lr * gr.z; w.w -= a.h.lr * gr.w;
+    } else if (a.kind == CTR_OPT_ADAGRAD) {
+        float4 s = *reinterpret_cast<float4 *>(f.state0 + off);
+        w.x = adagrad_elem(w.x, s.x, gr.x, a.h.lr, a.h.eps);
+        w.y = adagrad_elem(w.y, s.y, gr.y, a.h.lr, a.h.eps);
+        w.z = adagrad_elem(w.z, s.z, gr.z, a.h.lr, a.h.eps);
+        w.w = adagrad_elem(w.w, s.w, gr.w, a.h.lr, a.h.eps);
+        *reinterpret_cast<float4 *>(f.state0 + off) = s;
+    } else if (a.kind == CTR_OPT_ROWWISE_ADAGRAD) {
+        float sq = gr.x * gr.x + gr.y * gr.y + gr.z * gr.z + gr.w * gr.w;
+        for (int o = 1; o < team_lanes; o <<= 1) sq += __shfl_xor_sync(mask, sq, o);
+        const float acc = f.state0[row] + sq / (float)f.D;
+        const float den = __fsqrt_rn(acc) + a.h.eps;
+        __syncwarp(mask);
+        if (t == 0) f.state0[row] = acc;
+        w.x -= a.h.lr * __fdiv_rn(gr.x, den); w.y -= a.h.lr * __fdiv_rn(gr.y, den);
+        w.z -= a.h.lr * __fdiv_rn(gr.z, den); w.w -= a.h.lr * __fdiv_rn(gr.w, den);
+    } else {  // CTR_OPT_ADAM
+        float4 m = *reinterpret_cast<float4 *>(f.state0 + off);
+        float4 v = *reinterpret_cast<float4 *>(f.state1 + off);
+        w.x = adam_elem(w.x, m.x, v.x, gr.x, a);
+        w.y = adam_elem(w.y, m.y, v.y, gr.y, a);
+        w.z = adam_elem(w.z, m.z, v.z, gr.z, a);
+        w.w = adam_elem(w.w, m.w, v.w, gr.w, a);
+        *reinterpret_cast<float4 *>(f.state0 + off) = m;
+        *reinterpret_cast<float4 *>(f.state1 + off) = v;
+    }
+    *reinterpret_cast<float4 *>(f.table + off) = w;
+    if (t == 0 && f.twin_table != nullptr) {     // the first-order weight of the same id: gradient = sum of c over the run
+        float tw = f.twin_table[row];
+        if (a.kind == CTR_OPT_SGD) {
+            tw -= a.h.lr * cs;
+        } else if (a.kind == CTR_OPT_ADAGRAD || a.kind == CTR_OPT_ROWWISE_ADAGRAD) {   // one column: the two coincide
+            float s = f.twin_state0[row];
+            tw = adagrad_elem(tw, s, cs, a.h.lr, a.h.eps);
+            f.twin_state0[row] = s;
+        } else {
+            float m = f.twin_state0[row], v = f.twin_state1[row];
+            tw = adam_elem(tw, m, v, cs, a);
+            f.twin_state0[row] = m;
+            f.twin_state1[row] = v;
+        }
+        f.twin_table[row] = tw;
+    }
+}
+
+template <int TG, bool EXTRA, int MINB>
+__global__ void __launch_bounds__(kApplyThreads, MINB)
+    emb_bwd_sweep_l1_kernel(const __grid_constant__ DevGroup g, const __grid_constant__ ApplyArgs a_in) {
+    constexpr int P = kWarp / TG, U = 4, Q = P * U;
+    constexpr int D = 4 * TG;
+    constexpr unsigned umask = (1u << U) - 1u;
+    __shared__ ApplyArgs sa;
+    __shared__ uint32_t s_first_range;
+    if (threadIdx.x == 0) {
+        sa = a_in;
+        if (a_in.hyper_dev != nullptr) sa.h = *a_in.hyper_dev;
+        s_first_range = atomicAdd(a_in.ticket, (uint32_t)kApplyWarps);
+    }
+    __syncthreads();
+    const ApplyArgs &a = sa;
+    const DevFeature *sf = g.f;
+    const int lane = threadIdx.x & 31;
+    const uint32_t w = s_first_range + (threadIdx.x >> 5);
+    if (w >= a.num_ranges) return;
+    const int nf = g.num_features;
+    const float *gout_local = g.out;
+    const int64_t gstride = g.out_stride;
+    const int team = lane / TG;
+    const int t = lane % TG;
+    const unsigned tmask = TG == kWarp ? kFull : (((1u << TG) - 1u) << (team * TG));
+    const bool fm = EXTRA && a.fm_sum != nullptr;
+    const uint32_t S = a.S_dev != nullptr ? min(*a.S_dev, a.S) : a.S;
+    const uint32_t first = w * a.range;
+    if (first >= S) {
+        if (lane == 0) st_relaxed_u32(a.range_flags + w, 1u);
+        return;
+    }
+    const uint32_t end = min(first + a.range, S);
+    const uint32_t first_key = a.keys[first];
+    bool head_pending = first > 0 && first_key != kInvalidKey && a.keys[first - 1] == first_key;
+    bool have_head = false;
+    float4 head_acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float head_c = 0.f;
+    bool carry_open = false;
+    float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
+    float carry_c = 0.f;
+    int fi = 0;
+    uint32_t f_lo = 1, f_hi = 0;
+    uint32_t closed = 0;
+
+    uint32_t k = kInvalidKey, nk = kInvalidKey, slot = 0;
+    if (lane < Q && first + lane < end) {
+        k = a.keys[first + lane];
+        slot = a.vals[first + lane];
+        if (first + lane + 1 < S) nk = a.keys[first + lane + 1];
+    }
+    for (uint32_t p0 = first; p0 < end; p0 += Q) {
+        uint32_t k_next = kInvalidKey, nk_next = kInvalidKey, slot_next = 0;
+        const uint32_t pn = p0 + Q + lane;
+        if (lane < Q && pn < end) {
+            k_next = a.keys[pn];
+            slot_next = a.vals[pn];
+            if (pn + 1 < S) nk_next = a.keys[pn + 1];
+        }
+        const bool is_tail = k != kInvalidKey && nk != k;
+        const unsigned tails = __ballot_sync(kFull, is_tail);
+        if (is_tail && a.kind != CTR_OPT_NONE) {     // pull the row (and its optimizer state) towards L2 now
+            if (k < f_lo || k >= f_hi) {
+                fi = find_feature(sf, nf, k);
+                f_lo = sf[fi].row_base;
+                f_hi = f_lo + sf[fi].num_rows;
+            }
+            const DevFeature &f = sf[fi];
+            const size_t off = (size_t)(k - f_lo) * D;
+#pragma unroll
+            for (int b = 0; b < D; b += 32) {
+                prefetch_l2(f.table + off + b);
+                if (a.kind == CTR_OPT_ADAGRAD || a.kind == CTR_OPT_ADAM) prefetch_l2(f.state0 + off + b);
+                if (a.kind == CTR_OPT_ADAM) prefetch_l2(f.state1 + off + b);
+            }
+            if (EXTRA && f.twin_table != nullptr) {
+                prefetch_l2(f.twin_table + (k - f_lo));
+                if (a.kind != CTR_OPT_SGD) prefetch_l2(f.twin_state0 + (k - f_lo));
+            }
+        }
+        float4 v[U];
+        float c[U];
+        uint32_t kk[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            c[u] = 0.f;
+            const int src = team * U + u;
+            kk[u] = __shfl_sync(kFull, k, src);
+            uint32_t sl = __shfl_sync(kFull, slot, src);
+            const float *gout = gout_local;
+            if (a.p2p) {               // the gradient lives on the rank that sent this slot
+                gout = a.peer_grads[sl >> 28];
+                sl &= 0x0fffffffu;
+            }
+            if (kk[u] != kInvalidKey) {
+                if (kk[u] < f_lo || kk[u] >= f_hi) {
+                    fi = find_feature(sf, nf, kk[u]);
+                    f_lo = sf[fi].row_base;
+                    f_hi = f_lo + sf[fi].num_rows;
+                }
+                v[u] = __ldg(reinterpret_cast<const float4 *>(gout + (int64_t)sl * gstride + sf[fi].out_col) + t);
+                if (EXTRA) {
+                    c[u] = __ldg(a.extra_grad + sl);
+                    if (fm) {
+                        const float4 s4 = __ldg(reinterpret_cast<const float4 *>(a.fm_sum + (size_t)sl * D) + t);
+                        v[u].x = fmaf(c[u], s4.x, v[u].x); v[u].y = fmaf(c[u], s4.y, v[u].y);
+                        v[u].z = fmaf(c[u], s4.z, v[u].z); v[u].w = fmaf(c[u], s4.w, v[u].w);
+                    }
+                }
+            }
+        }
+        const unsigned m = (tails >> (team * U)) & umask;
+        const bool single = (m & (umask >> 1)) == 0u;
+        const bool prev_open = team > 0 ? ((tails >> (team * U - 1)) & 1u) == 0u : carry_open;
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+        float oc = 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            add4(out, v[u]);
+            oc += c[u];
+            if (u < U - 1 && ((m >> u) & 1u)) {
+                out = make_float4(0.f, 0.f, 0.f, 0.f);
+                oc = 0.f;
+            }
+        }
+        if (team == 0 && single && carry_open) {
+            add4(out, carry);
+            oc += carry_c;
+        }
+        const unsigned starts = __ballot_sync(kFull, t == 0 && !(single && prev_open));
+#pragma unroll
+        for (int d = 1; d < P; d <<= 1) {
+            const float4 o = shfl_up4<4>(out, d * TG);
+            const float o_c = EXTRA ? __shfl_up_sync(kFull, oc, d * TG) : 0.f;
+            const unsigned span = team >= d ? ((d * TG == kWarp ? kFull : ((1u << (d * TG)) - 1u)) << ((team - d + 1) * TG)) : kFull;
+            if (team >= d && (starts & span) == 0u) {
+                add4(out, o);
+                oc += o_c;
+            }
+        }
+        float4 acc = shfl_up4<4>(out, TG);
+        float acc_c = EXTRA ? __shfl_up_sync(kFull, oc, TG) : 0.f;
+        if (team == 0) {
+            acc = carry;
+            acc_c = carry_c;
+        }
+        if (!prev_open) {
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            acc_c = 0.f;
+        }
+        carry = shfl_idx4<4>(out, (P - 1) * TG + t);
+        carry_c = EXTRA ? __shfl_sync(kFull, oc, (P - 1) * TG + t) : 0.f;
+        carry_open = ((tails >> (Q - 1)) & 1u) == 0u;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            add4(acc, v[u]);
+            acc_c += c[u];
+            if ((m >> u) & 1u) {
+                const int idx = team * U + u;
+                if (head_pending && (tails & ((1u << idx) - 1u)) == 0u) {   // first end of a run in this range
+                    have_head = true;
+                    head_acc = acc;
+                    head_c = acc_c;
+                } else {
+                    const uint32_t key = kk[u];
+                    if (key < f_lo || key >= f_hi) {
+                        fi = find_feature(sf, nf, key);
+                        f_lo = sf[fi].row_base;
+                        f_hi = f_lo + sf[fi].num_rows;
+                    }
+                    update_row_l1<EXTRA>(sf[fi], a, p0 + idx, fi, key - f_lo, t, acc, acc_c, fm, tmask, TG);
+                }
+                acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                acc_c = 0.f;
+            }
+        }
+        if (tails != 0u) head_pending = false;
+        closed += (uint32_t)__popc(tails);
+        k = k_next; nk = nk_next; slot = slot_next;
+    }
+    uint32_t flag = 1u;
+    if (end < S) {
+        const uint32_t kl = a.keys[end - 1];
+        if (kl != kInvalidKey && a.keys[end] == kl) {
+            if (team == 0) {
+                reinterpret_cast<float4 *>(a.tail_part + (size_t)w * a.row_floats)[t] = carry;
+                if (EXTRA && t == 0) a.tail_part[(size_t)w * a.row_floats + D] = carry_c;
+            }
+            flag = 3u;
+            __threadfence();
+            __syncwarp();
+        }
+    }
+    if (lane == 0) {
+        st_relaxed_u32(a.range_flags + w, flag);
+        if (a.num_unique != nullptr && closed != 0) atomicAdd(a.num_unique, (unsigned long long)closed);
+    }
+    const unsigned head_lanes = __ballot_sync(kFull, have_head);
+    if (head_lanes != 0u) {
+        const int src_team = (__ffs(head_lanes) - 1) / TG;
+        const float4 hv = shfl_idx4<4>(head_acc, src_team * TG + t);
+        const float hc = __shfl_sync(kFull, head_c, src_team * TG + t);
+        uint32_t lo = 0, hi = w - 1;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (a.keys[(mid + 1) * a.range - 1] + 1u >= first_key + 1u) hi = mid; else lo = mid + 1;
+        }
+        for (uint32_t j = lo + lane; j < w; j += kWarp)
+            while (ld_relaxed_u32(a.range_flags + j) == 0u) { }
+        __syncwarp();
+        __threadfence();
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        float sum_c = 0.f;
+        for (uint32_t j = lo + team; j < w; j += P) {
+            add4(sum, __ldcg(reinterpret_cast<const float4 *>(a.tail_part + (size_t)j * a.row_floats) + t));
+            if (EXTRA) sum_c += __ldcg(a.tail_part + (size_t)j * a.row_floats + D);
+        }
+#pragma unroll
+        for (int off = TG; off < kWarp; off <<= 1) {
+            float4 o;
+            o.x = __shfl_xor_sync(kFull, sum.x, off); o.y = __shfl_xor_sync(kFull, sum.y, off);
+            o.z = __shfl_xor_sync(kFull, sum.z, off); o.w = __shfl_xor_sync(kFull, sum.w, off);
+            add4(sum, o);
+            if (EXTRA) sum_c += __shfl_xor_sync(kFull, sum_c, off);
+        }
+        add4(sum, hv);
+        sum_c += hc;
+        if (team == 0) {
+            const int hf = find_feature(sf, nf, first_key);
+            update_row_l1<EXTRA>(sf[hf], a, first, hf, first_key - sf[hf].row_base, t, sum, sum_c, fm,
+                                 TG == kWarp ? kFull : ((1u << TG) - 1u), TG);
         }
     }
 }
@@ -763,21 +1065,53 @@ static int apply_impl(DevGroup &dg, const PlanLayout &p, void *workspace, const 
     a.S = (uint32_t)p.S;
     a.range = (uint32_t)range;
     a.num_ranges = (uint32_t)((p.S + range - 1) / range);
-    bool any_vec4 = false, simple = true;
+    bool any_vec4 = false, l1 = dg.num_features > 0;
     for (int i = 0; i < dg.num_features; ++i) {
         const DevFeature &f = dg.f[i];
         any_vec4 |= f.vec == 4;
-        simple &= f.vec == 4 && f.aligned && f.L == 1 && f.id_weight == nullptr && f.pooling == CTR_POOL_SUM;
+        l1 &= f.vec == 4 && f.aligned && f.L == 1 && f.id_weight == nullptr && f.pooling == CTR_POOL_SUM && f.D == dg.f[0].D &&
+              (f.D == 16 || f.D == 32 || f.D == 64);
+    }
+    const bool extra = dg.extra != nullptr;
+    if (extra) {
+        if (!l1 || peer_grads != nullptr || !updates || uniq_row != nullptr) {
+            set_error("group->extra (twin tables / FM term) needs an unsharded single-id group of one width (D = 16, 32 or 64), "
+                      "sum pooling, a fused optimizer and no unique-row outputs");
+            return CTR_E_UNSUPPORTED;
+        }
+        a.extra_grad = dg.extra;
+        a.fm_sum = dg.fm ? dg.fm_sum : nullptr;
+        if (dg.fm) CTR_REQUIRE((reinterpret_cast<uintptr_t>(dg.fm_sum) & 15u) == 0, "fm_sum must be 16-byte aligned");
+        for (int i = 0; i < dg.num_features; ++i) {
+            const DevFeature &f = dg.f[i];
+            if (f.twin_table == nullptr) continue;
+            if (opt->kind != CTR_OPT_SGD) CTR_REQUIRE(f.twin_state0 != nullptr, "feature %d: twin_state0 is null", i);
+            if (opt->kind == CTR_OPT_ADAM) CTR_REQUIRE(f.twin_state1 != nullptr, "feature %d: twin_state1 is null", i);
+        }
     }
     if (num_unique != nullptr) CTR_CUDA_OK(cudaMemsetAsync(num_unique, 0, sizeof(int64_t), stream));
     CTR_CUDA_OK(cudaMemsetAsync(a.ticket, 0, (64 + (size_t)a.num_ranges) * sizeof(uint32_t), stream));
     const unsigned blocks = (a.num_ranges + kApplyWarps - 1) / kApplyWarps;
     note_launch();
-    static const int inl = getenv("CTR_SWEEP_INLINE") ? atoi(getenv("CTR_SWEEP_INLINE")) : 1;   // tuning knob: the inlined update measured ~8 % faster
-    if (simple && inl) emb_bwd_sweep_kernel<4, true, true><<<blocks, kApplyThreads, 0, stream>>>(dg, a);
-    else if (simple) emb_bwd_sweep_kernel<4, true, false><<<blocks, kApplyThreads, 0, stream>>>(dg, a);
-    else if (any_vec4) emb_bwd_sweep_kernel<4, false, false><<<blocks, kApplyThreads, 0, stream>>>(dg, a);
-    else emb_bwd_sweep_kernel<1, false, false><<<blocks, kApplyThreads, 0, stream>>>(dg, a);
+    if (l1) {
+        const int tg = dg.f[0].D / 4;
+        // resident blocks per SM the kernel is compiled for: 3 (80 registers, a few spilled words) or 2 (no spills)
+        static const int occ = getenv("CTR_SWEEP_OCC") ? atoi(getenv("CTR_SWEEP_OCC")) : 3;
+#define CTR_L1_SWEEP(TG_, EX_)                                                                                    \
+    do {                                                                                                          \
+        if (occ == 2) emb_bwd_sweep_l1_kernel<TG_, EX_, 2><<<blocks, kApplyThreads, 0, stream>>>(dg, a);          \
+        else emb_bwd_sweep_l1_kernel<TG_, EX_, 3><<<blocks, kApplyThreads, 0, stream>>>(dg, a);                   \
+    } while (0)
+        if (tg == 4 && extra) CTR_L1_SWEEP(4, true);
+        else if (tg == 4) CTR_L1_SWEEP(4, false);
+        else if (tg == 8 && extra) CTR_L1_SWEEP(8, true);
+        else if (tg == 8) CTR_L1_SWEEP(8, false);
+        else if (extra) CTR_L1_SWEEP(16, true);
+        else CTR_L1_SWEEP(16, false);
+#undef CTR_L1_SWEEP
+    }
+    else if (any_vec4) emb_bwd_sweep_kernel<4><<<blocks, kApplyThreads, 0, stream>>>(dg, a);
+    else emb_bwd_sweep_kernel<1><<<blocks, kApplyThreads, 0, stream>>>(dg, a);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }

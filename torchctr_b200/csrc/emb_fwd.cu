@@ -184,15 +184,20 @@ __global__ void __launch_bounds__(kFwdThreads) emb_pool_fwd_kernel(const __grid_
 // walks the tables four at a time -- four id loads, then four independent row loads, then four stores -- so
 // there is no per-feature block row, no shuffle and ~2 instructions per id instead of ~20; the dense block and
 // the zero padding of the same bag are written by the same team.
-template <int G, int VEC, bool SHARDED>
+// EXTRA (DeepFM): the team holds every field of its bag, so the FM second-order term 0.5 * sum_d[(sum_f v)^2 - sum_f v^2]
+// and the sum of the one-column twin tables (first-order weights) cost a few FMAs and one 4-byte load per field here,
+// instead of two more passes over the [B, F * D] matrix: extra[bag] = sum_f twin_f[row] + FM, fm_sum[bag, :] = sum_f v.
+template <int G, int VEC, bool SHARDED, bool EXTRA>
 __global__ void __launch_bounds__(kFwdThreads) emb_pool_fwd_l1_kernel(const __grid_constant__ DevGroup g) {
     constexpr int kTeams = kFwdThreads / G;
     constexpr int D = G * VEC;
     const int t = threadIdx.x % G;
     const int F = g.num_features;
-    const int extra_from = g.dense_col + g.dense_width;
+    const unsigned team_mask = G >= 32 ? kFull : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
     for (int bag = blockIdx.x * kTeams + threadIdx.x / G; bag < g.B; bag += gridDim.x * kTeams) {
         float *out_row = g.out + (size_t)bag * g.out_stride;
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float twin_sum = 0.f;
         for (int f0 = 0; f0 < F; f0 += 4) {
             int32_t row[4];
 #pragma unroll
@@ -205,14 +210,17 @@ __global__ void __launch_bounds__(kFwdThreads) emb_pool_fwd_l1_kernel(const __gr
                 }
             }
             float4 v[4];
+            float tw[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                tw[j] = 0.f;
                 if (row[j] >= 0) {
                     const float *src = SHARDED ? table_row(g, g.f[f0 + j], f0 + j, row[j]) + t * VEC
                                                : g.f[f0 + j].table + (size_t)(uint32_t)row[j] * D + t * VEC;
                     if (VEC == 4) v[j] = __ldg(reinterpret_cast<const float4 *>(src));
                     else v[j].x = __ldg(src);
+                    if (EXTRA && t == 0 && g.f[f0 + j].twin_table != nullptr) tw[j] = __ldg(g.f[f0 + j].twin_table + (uint32_t)row[j]);
                 }
             }
 #pragma unroll
@@ -222,14 +230,29 @@ __global__ void __launch_bounds__(kFwdThreads) emb_pool_fwd_l1_kernel(const __gr
                     if (VEC == 4) *reinterpret_cast<float4 *>(dst) = v[j];
                     else *dst = v[j].x;
                     if (t == 0 && g.f[f0 + j].pooling == CTR_POOL_MEAN) g.f[f0 + j].bag_scale[bag] = 1.f;
+                    if (EXTRA) {
+                        s4.x += v[j].x; s4.y += v[j].y; s4.z += v[j].z; s4.w += v[j].w;
+                        q4.x = fmaf(v[j].x, v[j].x, q4.x); q4.y = fmaf(v[j].y, v[j].y, q4.y);
+                        q4.z = fmaf(v[j].z, v[j].z, q4.z); q4.w = fmaf(v[j].w, v[j].w, q4.w);
+                        twin_sum += tw[j];
+                    }
                 }
             }
         }
         for (int c = t; c < g.dense_width; c += G) out_row[g.dense_col + c] = __ldg(g.dense + (size_t)bag * g.dense_width + c);
         if (g.zero_from >= 0)
             for (int c = g.zero_from + t; c < (int)g.out_stride; c += G) out_row[c] = 0.f;
+        if (EXTRA) {
+            float e = 0.f;
+            if (g.fm) {
+                *reinterpret_cast<float4 *>(g.fm_sum + (size_t)bag * D + t * 4) = s4;
+                e = 0.5f * ((s4.x * s4.x - q4.x) + (s4.y * s4.y - q4.y) + (s4.z * s4.z - q4.z) + (s4.w * s4.w - q4.w));
+#pragma unroll
+                for (int off = 1; off < G; off <<= 1) e += __shfl_xor_sync(team_mask, e, off);
+            }
+            if (t == 0) g.extra[bag] = e + twin_sum;
+        }
     }
-    (void)extra_from;
 }
 
 // 0 when the group does not qualify, else the lane count G (VEC reported through *vec)
@@ -358,16 +381,31 @@ static int launch_pool_fwd(const DevGroup &dg, void *stream) {
         cudaStream_t st = (cudaStream_t)stream;
         note_launch();
         const bool sh = dg.world > 1;
-        if (vec == 1 && sh) emb_pool_fwd_l1_kernel<1, 1, true><<<blocks, kFwdThreads, 0, st>>>(dg);
-        else if (vec == 1) emb_pool_fwd_l1_kernel<1, 1, false><<<blocks, kFwdThreads, 0, st>>>(dg);
-        else if (fastG == 4 && sh) emb_pool_fwd_l1_kernel<4, 4, true><<<blocks, kFwdThreads, 0, st>>>(dg);
-        else if (fastG == 4) emb_pool_fwd_l1_kernel<4, 4, false><<<blocks, kFwdThreads, 0, st>>>(dg);
-        else if (fastG == 8 && sh) emb_pool_fwd_l1_kernel<8, 4, true><<<blocks, kFwdThreads, 0, st>>>(dg);
-        else if (fastG == 8) emb_pool_fwd_l1_kernel<8, 4, false><<<blocks, kFwdThreads, 0, st>>>(dg);
-        else if (sh) emb_pool_fwd_l1_kernel<16, 4, true><<<blocks, kFwdThreads, 0, st>>>(dg);
-        else emb_pool_fwd_l1_kernel<16, 4, false><<<blocks, kFwdThreads, 0, st>>>(dg);
+        const bool ex = dg.extra != nullptr;
+        if (ex) {
+            if (sh || vec != 4) {
+                set_error("group->extra (twin tables / FM term) needs an unsharded single-id group of one width, D %% 4 == 0");
+                return CTR_E_UNSUPPORTED;
+            }
+            if (dg.fm) CTR_REQUIRE((reinterpret_cast<uintptr_t>(dg.fm_sum) & 15u) == 0, "fm_sum must be 16-byte aligned");
+            if (fastG == 4) emb_pool_fwd_l1_kernel<4, 4, false, true><<<blocks, kFwdThreads, 0, st>>>(dg);
+            else if (fastG == 8) emb_pool_fwd_l1_kernel<8, 4, false, true><<<blocks, kFwdThreads, 0, st>>>(dg);
+            else emb_pool_fwd_l1_kernel<16, 4, false, true><<<blocks, kFwdThreads, 0, st>>>(dg);
+        }
+        else if (vec == 1 && sh) emb_pool_fwd_l1_kernel<1, 1, true, false><<<blocks, kFwdThreads, 0, st>>>(dg);
+        else if (vec == 1) emb_pool_fwd_l1_kernel<1, 1, false, false><<<blocks, kFwdThreads, 0, st>>>(dg);
+        else if (fastG == 4 && sh) emb_pool_fwd_l1_kernel<4, 4, true, false><<<blocks, kFwdThreads, 0, st>>>(dg);
+        else if (fastG == 4) emb_pool_fwd_l1_kernel<4, 4, false, false><<<blocks, kFwdThreads, 0, st>>>(dg);
+        else if (fastG == 8 && sh) emb_pool_fwd_l1_kernel<8, 4, true, false><<<blocks, kFwdThreads, 0, st>>>(dg);
+        else if (fastG == 8) emb_pool_fwd_l1_kernel<8, 4, false, false><<<blocks, kFwdThreads, 0, st>>>(dg);
+        else if (sh) emb_pool_fwd_l1_kernel<16, 4, true, false><<<blocks, kFwdThreads, 0, st>>>(dg);
+        else emb_pool_fwd_l1_kernel<16, 4, false, false><<<blocks, kFwdThreads, 0, st>>>(dg);
         CTR_CUDA_OK(cudaGetLastError());
         return CTR_OK;
+    }
+    if (dg.extra != nullptr) {
+        set_error("group->extra (twin tables / FM term) needs a single-id group of one width, D %% 4 == 0, no per-id weights");
+        return CTR_E_UNSUPPORTED;
     }
     int64_t max_warps = 1;
     for (int i = 0; i < dg.num_features; ++i) {

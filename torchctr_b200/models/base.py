@@ -206,7 +206,10 @@ class CTRModelBase(nn.Module):
         for name in self._names:
             table = self.embeddings[name]
             if table.index_kind == "vocab":
-                table.vocab.fit_and_grow(feats[name], table)
+                n = table.vocab.fit_and_grow(feats[name], table)
+                twins = getattr(self, "linear_embeddings", None)
+                if twins is not None and name in twins:   # DeepFM's first-order weights share the vocabulary
+                    twins[name].grow_to(n)
 
     # ---- step protocol: dnn.py:72-82 ----------------------------------------------------------
     def hidden_and_extra(self, input_feats):

@@ -6,7 +6,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from ..nn.embedding import EmbeddingTable, PooledLookupGroup
+from ..nn.embedding import EmbeddingTable, PlanLink, PooledLookupGroup
 from ..nn.interaction import fm_interaction_passthrough
 from .base import CTRModelBase, make_tower
 
@@ -33,9 +33,17 @@ class DeepFM(CTRModelBase):
         """(tower input x, the logit terms outside the tower: FM second order + first order (+ Linear on dense))"""
         self._grow_vocabularies(input_feats)
         dense = self.dense_block(input_feats)
-        x, first = self._lookup_all(input_feats, dense)       # [B, pad4(F*D + Nd)], [B, pad4(F)]; one backward sort
-        nf = len(self._names)
-        x, extra = fm_interaction_passthrough(x, nf, self._dim, first, nf)
+        twins = [self.linear_embeddings[n] for n in self._names]
+        if self._sharded is None and self._lookup.fused_extra_eligible(input_feats, twins, self.training):
+            # Criteo-shaped (single-id, one width): the first-order weights and the FM term ride inside the lookup
+            # kernel, their gradients inside the fused update -- no D = 1 launch group, no pass over [B, F * D] for FM
+            link = PlanLink() if self.training else None
+            x, extra = self._lookup(input_feats, dense, self.training, link, twins=twins, fm=True)
+            extra = extra.unsqueeze(1)
+        else:
+            x, first = self._lookup_all(input_feats, dense)   # [B, pad4(F*D + Nd)], [B, pad4(F)]; one backward sort
+            nf = len(self._names)
+            x, extra = fm_interaction_passthrough(x, nf, self._dim, first, nf)
         if self.linear_dense is not None:
             # the dense block itself, not the slice of x: same numbers, but no third gradient stream into x (autograd
             # would sum it with the tower's out of place: a zero-fill and an add over [B, F*D + Nd] per step)

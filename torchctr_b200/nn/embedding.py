@@ -229,12 +229,46 @@ class _PooledLookupFn(torch.autograd.Function):
         return (None, gdense, *wgrads)
 
 
+class _PooledLookupExtraFn(torch.autograd.Function):
+    """The lookup with the fused per-bag scalar (twin tables + FM term): two outputs, (pooled [B, stride], extra [B])."""
+
+    @staticmethod
+    def forward(ctx, call, dense, *weights):
+        ctx.call = call
+        ctx.has_dense = dense is not None
+        out = call.run_forward(dense, weights)
+        # hand `extra` out WITHOUT keeping it on the call: an output of this node that the node's own ctx also held would be
+        # a reference cycle, and the autograd graph (AccumulateGrad nodes bound to the stream of that step included) would
+        # outlive the step -- which breaks the next CUDA-graph capture
+        extra, call.extra = call.extra, None
+        ctx.device = out.device
+        return out, extra
+
+    @staticmethod
+    def backward(ctx, grad_out, grad_extra):
+        call = ctx.call
+        B = call.B
+        if grad_out is None:
+            grad_out = torch.zeros(B, call.stride, dtype=torch.float32, device=ctx.device)
+        if grad_extra is None:
+            grad_extra = torch.zeros(B, dtype=torch.float32, device=ctx.device)
+        wgrads = call.run_backward(grad_out, grad_extra.reshape(-1).contiguous())
+        gdense = None
+        if ctx.has_dense and ctx.needs_input_grad[1]:
+            gdense = grad_out[:, call.dense_col: call.dense_col + call.dense_width]
+        return (None, gdense, *wgrads)
+
+
 class _LookupCall:
     """One forward/backward of a group of tables over one batch."""
 
-    def __init__(self, entries, dense_width, layout, binding, training, plan_link=None):
+    def __init__(self, entries, dense_width, layout, binding, training, plan_link=None, twins=None, fm=False):
         # entries: [(table module, ids [B, L] i64, id_weight or None)]
         self.entries = entries
+        self.twins = twins              # one-column twin tables (same ids) or None; fm: add the FM term to `extra`
+        self.fm = bool(fm)
+        self.extra = None               # f32 [B]: sum of the twins (+ FM term), written by the lookup kernel
+        self.fm_sum = None
         self.plan_link = plan_link
         self.layout = layout            # (out_cols, width, stride, dense_col)
         self.out_cols, self.width, self.stride, self.dense_col = layout
@@ -246,11 +280,17 @@ class _LookupCall:
         self.status = None
         self.grad_enabled = torch.is_grad_enabled()   # read outside the autograd Function (inside, grad mode is off)
 
-    def _specs(self, tables_data, with_state):
+    def _specs(self, tables_data, with_state, twin_data=None):
         specs = []
         for i, (mod, ids, wgt) in enumerate(self.entries):
             vocab = mod.vocab.handle() if mod.index_kind == "vocab" else None
-            specs.append(ops.FeatureSpec(
+            tw = {}
+            if twin_data is not None:
+                tm = self.twins[i]
+                tw = dict(twin_table=twin_data[i],
+                          twin_state0=getattr(tm, "opt_state0", None) if with_state else None,
+                          twin_state1=getattr(tm, "opt_state1", None) if with_state else None)
+            specs.append(ops.FeatureSpec(**tw, 
                 ids=ids, table=tables_data[i], num_rows=mod.num_embeddings, D=mod.embedding_dim,
                 out_col=self.out_cols[i], pooling=mod.pooling, index_kind=mod.index_kind, hash_seed=mod.hash_seed,
                 id_weight=wgt, vocab=vocab,
@@ -267,8 +307,15 @@ class _LookupCall:
                            for m, _, _ in self.entries]
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         zero_from = self.width if self.stride > self.width else -1
-        call = ops.make_group(self._specs([w.detach() for w in weights], False), B, out, self.stride,
-                              dense=dense, dense_col=self.dense_col, zero_from=zero_from, status=self.status)
+        n = len(self.entries)
+        twin_data = [w.detach() for w in weights[n:]] if self.twins is not None else None
+        if self.twins is not None or self.fm:
+            self.extra = torch.empty(B, dtype=torch.float32, device=dev)
+            if self.fm:
+                self.fm_sum = torch.empty(B, self.entries[0][0].embedding_dim, dtype=torch.float32, device=dev)
+        call = ops.make_group(self._specs([w.detach() for w in weights[:n]], False, twin_data), B, out, self.stride,
+                              dense=dense, dense_col=self.dense_col, zero_from=zero_from, status=self.status,
+                              extra=self.extra, fm_sum=self.fm_sum, fm=self.fm)
         ops.emb_pool_fwd(call)
         link = self.plan_link
         if link is not None and self.training:               # every linked forward runs before any backward
@@ -290,20 +337,25 @@ class _LookupCall:
                 link.pending = side
         return out
 
-    def run_backward(self, grad_out):
+    def run_backward(self, grad_out, grad_extra=None):
         mods = [m for m, _, _ in self.entries]
         needs = [m.weight.requires_grad for m in mods]
+        nw = len(mods) + (len(self.twins) if self.twins is not None else 0)
         if not any(needs):
-            return [None] * len(mods)
+            return [None] * nw
         if grad_out.stride(1) != 1 or grad_out.stride(0) != grad_out.shape[1]:
             grad_out = grad_out.contiguous()
         dev = grad_out.device
         fused = self.binding is not None and self.training
+        if (self.twins is not None or self.fm) and not fused:
+            raise RuntimeError("the fused twin / FM lookup needs a bound optimizer in training (bind_optimizer)")
         if fused:
-            for m in mods:
+            for m in mods + (list(self.twins) if self.twins is not None else []):
                 m._ensure_state(self.binding.kind, self.binding.initial_accumulator_value())
         tables = [m.weight.data for m in mods]
-        call = ops.make_group(self._specs(tables, fused), self.B, grad_out, grad_out.shape[1])
+        twin_data = [t.weight.data for t in self.twins] if self.twins is not None else None
+        call = ops.make_group(self._specs(tables, fused, twin_data), self.B, grad_out, grad_out.shape[1],
+                              extra=grad_extra, fm_sum=self.fm_sum, fm=self.fm)
         link = self.plan_link
         if link is None:
             ws = _Workspace.get(dev, ops.emb_bwd_workspace_bytes(call))
@@ -323,7 +375,7 @@ class _LookupCall:
             ws = link.ws
         if fused:
             ops.emb_bwd_apply(call, ws, self.binding.next_opt())
-            return [None] * len(mods)
+            return [None] * nw
         # no optimizer bound: hand autograd sparse gradients (torch.optim SGD / Adagrad / SparseAdam accept them)
         S = sum(ids.numel() for _, ids, _ in self.entries)
         dmax = max(m.embedding_dim for m in mods)
@@ -368,12 +420,38 @@ class PlanLink:
         self.has_runs = False    # the plan in ws lists the runs (needed for unique-row outputs only)
 
 
+def fused_extra_eligible(tables, twins, feats_L, binding, training: bool) -> bool:
+    """Can the twin tables / FM term ride inside the lookup and update kernels (``ctr_group_t.extra``)?  Single-id bags,
+    one width of 16 / 32 / 64, sum pooling, no per-id weights, direct / hashed / vocabulary ids alike -- and, when a
+    gradient will be asked for, a bound optimizer (the fused update is the only consumer of the twin gradients)."""
+    if len(tables) == 0 or len(tables) > _lib.MAX_FEATURES:
+        return False
+    D = tables[0].embedding_dim
+    if D not in (16, 32, 64) or any(L != 1 for L in feats_L):
+        return False
+    for t in tables:
+        if t.embedding_dim != D or t.pooling != "sum" or t.use_id_weight:
+            return False
+    if twins is not None:
+        for t, tw in zip(tables, twins):
+            if tw.embedding_dim != 1 or tw.num_embeddings != t.num_embeddings or tw.weight.device != t.weight.device:
+                return False
+    if training and torch.is_grad_enabled() and binding is None:
+        return False
+    return True
+
+
 def pooled_lookup(entries, dense: torch.Tensor | None = None, binding: SparseOptimizerBinding | None = None,
-                  training: bool = False, plan_link: PlanLink | None = None) -> torch.Tensor:
+                  training: bool = False, plan_link: PlanLink | None = None, twins=None, fm: bool = False):
     """Pools every (table, ids [B, L], id_weight) entry and concatenates them with ``dense``.
 
     Returns f32 ``[B, stride]`` with ``stride`` = total width rounded up to 4 floats; columns past
     the width are zero.  This is ``torchctr/models/dnn.py:53-67`` as one launch.
+
+    ``twins`` (one ``EmbeddingTable(V, 1)`` per entry, indexed by the same ids) and / or ``fm=True`` ask for the fused
+    per-bag scalar of ``ctr_group_t.extra``: the call then returns ``(pooled, extra [B])`` with
+    ``extra[b] = sum_f twin_f[id] + (FM second-order term of the pooled vectors if fm)`` -- DeepFM's logit terms outside
+    the tower -- and backward folds their gradients into the one fused update (``fused_extra_eligible`` says when).
     """
     if not entries:
         raise ValueError("pooled_lookup needs at least one table")
@@ -398,6 +476,14 @@ def pooled_lookup(entries, dense: torch.Tensor | None = None, binding: SparseOpt
         dense_width = dense.shape[1]
     # a launch group carries at most MAX_FEATURES tables and a 32-bit key space
     if len(prepared) <= _lib.MAX_FEATURES and sum(m.num_embeddings for m, _, _ in prepared) < 2 ** 32 - 1:
+        if twins is not None or fm:
+            twins = list(twins) if twins else None
+            if twins is not None and len(twins) != len(prepared):
+                raise ValueError("one twin table per entry")
+            call = _LookupCall(prepared, dense_width, _layout(prepared, dense_width), binding, training, plan_link,
+                               twins=twins, fm=fm)
+            weights = [m.weight for m, _, _ in prepared] + [t.weight for t in (twins or [])]
+            return _PooledLookupExtraFn.apply(call, dense, *weights)
         call = _LookupCall(prepared, dense_width, _layout(prepared, dense_width), binding, training, plan_link)
         return _PooledLookupFn.apply(call, dense, *[m.weight for m, _, _ in prepared])
     raise NotImplementedError("split the features into several pooled_lookup calls "
@@ -416,7 +502,12 @@ class PooledLookupGroup:
         self.binding = SparseOptimizerBinding(optimizer, [self.tables[n] for n in self.names], kind)
         return self.binding
 
-    def __call__(self, feats: dict, dense: torch.Tensor | None, training: bool, plan_link: PlanLink | None = None) -> torch.Tensor:
+    def __call__(self, feats: dict, dense: torch.Tensor | None, training: bool, plan_link: PlanLink | None = None,
+                 twins=None, fm: bool = False):
         entries = [(self.tables[n], feats[n], feats.get(n + "_weight") if self.tables[n].use_id_weight else None)
                    for n in self.names]
-        return pooled_lookup(entries, dense, self.binding, training, plan_link)
+        return pooled_lookup(entries, dense, self.binding, training, plan_link, twins=twins, fm=fm)
+
+    def fused_extra_eligible(self, feats: dict, twins, training: bool) -> bool:
+        Ls = [feats[n].shape[1] if feats[n].dim() == 2 else 1 for n in self.names]
+        return fused_extra_eligible([self.tables[n] for n in self.names], twins, Ls, self.binding, training)

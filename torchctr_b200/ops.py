@@ -60,6 +60,9 @@ class FeatureSpec:
     state0: torch.Tensor | None = None
     state1: torch.Tensor | None = None
     bag_scale: torch.Tensor | None = None   # f32 [B]
+    twin_table: torch.Tensor | None = None  # f32 [V] / [V, 1]: one-column twin indexed by the same ids (DeepFM first order)
+    twin_state0: torch.Tensor | None = None
+    twin_state1: torch.Tensor | None = None
 
 
 @dataclass
@@ -70,12 +73,16 @@ class GroupCall:
 
 
 def make_group(features, B: int, out: torch.Tensor | None, out_stride: int, dense: torch.Tensor | None = None,
-               dense_col: int = 0, zero_from: int = -1, status: torch.Tensor | None = None) -> GroupCall:
+               dense_col: int = 0, zero_from: int = -1, status: torch.Tensor | None = None,
+               extra: torch.Tensor | None = None, fm_sum: torch.Tensor | None = None, fm: bool = False) -> GroupCall:
+    """``extra`` f32 [B] (+ ``fm_sum`` f32 [B, D] when ``fm``): the fused per-bag scalar of ``ctr_group_t`` -- sum of the
+    features' twin tables plus, with ``fm``, the FM second-order term; forward writes them, backward reads ``extra`` as
+    dL/d extra."""
     n = len(features)
     if n > _lib.MAX_FEATURES:
         raise ValueError(f"a launch group holds at most {_lib.MAX_FEATURES} features, got {n}")
     arr = (_lib.Feature * max(n, 1))()
-    keep = [arr, out, dense, status]
+    keep = [arr, out, dense, status, extra, fm_sum]
     for i, f in enumerate(features):
         _chk(f.ids, f"feature {i} ids", torch.int64)
         if f.ids.dim() != 2 or f.ids.shape[0] != B:
@@ -104,6 +111,13 @@ def make_group(features, B: int, out: torch.Tensor | None, out_stride: int, dens
         s.pooling = _POOLINGS[f.pooling]
         s.index_kind = _INDEX_KINDS[f.index_kind]
         s.hash_seed = f.hash_seed & 0xFFFFFFFF
+        for name in ("twin_table", "twin_state0", "twin_state1"):
+            t = getattr(f, name)
+            _chk(t, f"feature {i} {name}", torch.float32)
+            if t is not None and t.numel() != f.num_rows:
+                raise ValueError(f"feature {i}: {name} must hold num_rows={f.num_rows} floats, got {tuple(t.shape)}")
+            setattr(s, name, _lib.ptr(t))
+        keep.append((f.twin_table, f.twin_state0, f.twin_state1))
         keep.append((f.ids, f.id_weight, f.table, f.state0, f.state1, f.bag_scale, f.vocab))
     _chk(out, "out", torch.float32)
     _chk(dense, "dense", torch.float32)
@@ -120,6 +134,15 @@ def make_group(features, B: int, out: torch.Tensor | None, out_stride: int, dens
     g.dense_col = dense_col
     g.zero_from = zero_from
     g.status = _lib.ptr(status)
+    _chk(extra, "extra", torch.float32)
+    _chk(fm_sum, "fm_sum", torch.float32)
+    if extra is not None and extra.numel() != B:
+        raise ValueError(f"extra must hold B={B} floats")
+    if fm and (extra is None or fm_sum is None or fm_sum.shape[0] != B):
+        raise ValueError("fm needs extra [B] and fm_sum [B, D]")
+    g.extra = _lib.ptr(extra)
+    g.fm_sum = _lib.ptr(fm_sum)
+    g.fm = 1 if fm else 0
     return GroupCall(g, keep)
 
 
