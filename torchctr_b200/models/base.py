@@ -97,6 +97,25 @@ class CTRModelBase(nn.Module):
             g.bind_optimizer(optimizer, kind)
         return self
 
+    def table_optimizer_state_dict(self):
+        """Fused-update state that is NOT inside the torch optimizer (tables kept out of its parameters, row-wise Adagrad):
+        {table module name: {"state0": tensor, "state1": tensor | None}}; plain tensors, ``weights_only`` safe.  State of
+        tables that ARE parameters of the torch optimizer travels in ``optimizer.state_dict()`` instead."""
+        from ..nn.embedding import EmbeddingTable
+        out = {}
+        for name, m in self.named_modules():
+            if isinstance(m, EmbeddingTable) and m._state_owner is None and m._opt_state0 is not None:
+                out[name] = {"state0": m._opt_state0.detach().clone(),
+                             "state1": None if m._opt_state1 is None else m._opt_state1.detach().clone()}
+        return out
+
+    def load_table_optimizer_state_dict(self, state):
+        mods = dict(self.named_modules())
+        for name, st in state.items():
+            m = mods[name]
+            m._opt_state0 = st["state0"].to(m.weight.device).clone()
+            m._opt_state1 = None if st.get("state1") is None else st["state1"].to(m.weight.device).clone()
+
     def table_parameters(self):
         """Parameters updated by the fused sparse optimizer (every EmbeddingTable weight)."""
         from ..nn.embedding import EmbeddingTable

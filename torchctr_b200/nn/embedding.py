@@ -45,16 +45,39 @@ class EmbeddingTable(nn.Embedding):
         self.use_id_weight = bool(use_id_weight)  # multiply rows by feats['<name>_weight'] (dataset.py:59-67)
         self._opt_kind = None
 
-    # -- optimizer state lives with the table so that it is checkpointed with the model ------
-    def _ensure_state(self, kind: str, initial_accumulator_value: float = 0.0):
+    # -- optimizer state of the fused row update ---------------------------------------------------------------------
+    # Where it lives decides how it is checkpointed by the UNMODIFIED reference Trainer (torchctr/trainer.py:353-381 saves
+    # model.state_dict() and optimizer.state_dict()):
+    #   * the table's weight is one of the torch optimizer's parameters (the reference way: optim.Adagrad(model.parameters()))
+    #     -> the state IS the optimizer's own state for that parameter (Adagrad 'sum', Adam 'exp_avg' / 'exp_avg_sq'), so
+    #     optimizer.state_dict() carries it in torch's format and a checkpoint moves freely between this model and the
+    #     reference's nn.Embedding + torch.optim;
+    #   * otherwise (tables kept out of the dense optimizer, row-wise Adagrad, grown tables) -> non-persistent module buffers,
+    #     saved / restored with table_optimizer_state_dict() / load_table_optimizer_state_dict().
+    # Either way model.state_dict() has exactly the reference's keys.
+    _TORCH_STATE_KEYS = {"adagrad": ("sum", None), "adam": ("exp_avg", "exp_avg_sq")}
+
+    def _ensure_state(self, kind: str, initial_accumulator_value: float = 0.0, optimizer=None):
         w = self.weight
-        if kind in ("adagrad", "adam") and getattr(self, "opt_state0", None) is None:
-            self.register_buffer("opt_state0", torch.full_like(w.data, initial_accumulator_value if kind == "adagrad" else 0.0))
-        if kind == "rowwise_adagrad" and getattr(self, "opt_state0", None) is None:
-            self.register_buffer("opt_state0", torch.full((w.shape[0],), initial_accumulator_value, device=w.device))
-        if kind == "adam" and getattr(self, "opt_state1", None) is None:
-            self.register_buffer("opt_state1", torch.zeros_like(w.data))
-        for name in ("opt_state0", "opt_state1"):          # follow the table if it grew / moved
+        keys = self._TORCH_STATE_KEYS.get(kind)
+        self._state_owner = None
+        if optimizer is not None and keys is not None and any(w is p for g in optimizer.param_groups for p in g["params"]):
+            st = optimizer.state[w]
+            for key in keys:
+                if key is not None and (key not in st or st[key].shape != w.shape or st[key].device != w.device):
+                    st[key] = torch.full_like(w.data, initial_accumulator_value if key == "sum" else 0.0)
+            if "step" not in st:
+                st["step"] = torch.tensor(0.0, dtype=torch.float32)
+            self._state_owner = (optimizer, keys)
+            self._opt_kind = kind
+            return
+        if kind in ("adagrad", "adam") and getattr(self, "_opt_state0", None) is None:
+            self._opt_state0 = torch.full_like(w.data, initial_accumulator_value if kind == "adagrad" else 0.0)
+        if kind == "rowwise_adagrad" and getattr(self, "_opt_state0", None) is None:
+            self._opt_state0 = torch.full((w.shape[0],), initial_accumulator_value, device=w.device)
+        if kind == "adam" and getattr(self, "_opt_state1", None) is None:
+            self._opt_state1 = torch.zeros_like(w.data)
+        for name in ("_opt_state0", "_opt_state1"):          # follow the table if it grew / moved
             buf = getattr(self, name, None)
             if buf is not None and (buf.shape[0] != w.shape[0] or buf.device != w.device):
                 new = torch.zeros((w.shape[0],) + tuple(buf.shape[1:]), device=w.device)
@@ -62,6 +85,35 @@ class EmbeddingTable(nn.Embedding):
                 new[:n] = buf[:n].to(w.device)
                 setattr(self, name, new)
         self._opt_kind = kind
+
+    _state_owner = None
+    _opt_state0 = None
+    _opt_state1 = None
+
+    def _state(self, which: int):
+        owner = self._state_owner
+        if owner is not None:
+            key = owner[1][which]
+            return None if key is None else owner[0].state[self.weight].get(key)
+        return self._opt_state0 if which == 0 else self._opt_state1
+
+    @property
+    def opt_state0(self):
+        """Adagrad sum [V, D] | row-wise accumulator [V] | Adam exp_avg -- wherever it currently lives."""
+        return self._state(0)
+
+    @property
+    def opt_state1(self):
+        """Adam exp_avg_sq [V, D]."""
+        return self._state(1)
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        for name in ("_opt_state0", "_opt_state1"):           # module-held state follows .to() / .cuda()
+            buf = getattr(self, name, None)
+            if buf is not None:
+                setattr(self, name, fn(buf))
+        return out
 
     # -- growth (DynamicEmbedding._expand_embeddings, torchctr/nn/embedding.py:69-78) -----------
     def grow_to(self, new_num_embeddings: int, std: float = 0.01) -> None:
@@ -91,13 +143,11 @@ class EmbeddingTable(nn.Embedding):
             destination[key] = destination[key].clone()      # a view would drag the whole store into torch.save
 
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
-        for name in ("opt_state0", "opt_state1"):           # optional keys: absent in reference checkpoints
+        for which, name in enumerate(("opt_state0", "opt_state1")):   # round-1 checkpoints carried the state as buffers
             key = prefix + name
-            if key in state_dict and getattr(self, name, None) is None:
-                self.register_buffer(name, torch.empty_like(state_dict[key], device=self.weight.device))
-        before = len(missing_keys)
+            if key in state_dict:
+                setattr(self, "_" + name, state_dict.pop(key).to(self.weight.device).clone())
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
-        missing_keys[before:] = [k for k in missing_keys[before:] if not k.endswith(("opt_state0", "opt_state1"))]
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
         """``nn.Embedding.forward``: ids of any shape (all >= 0) -> [..., D]."""
@@ -351,7 +401,7 @@ class _LookupCall:
             raise RuntimeError("the fused twin / FM lookup needs a bound optimizer in training (bind_optimizer)")
         if fused:
             for m in mods + (list(self.twins) if self.twins is not None else []):
-                m._ensure_state(self.binding.kind, self.binding.initial_accumulator_value())
+                m._ensure_state(self.binding.kind, self.binding.initial_accumulator_value(), self.binding.optimizer)
         tables = [m.weight.data for m in mods]
         twin_data = [t.weight.data for t in self.twins] if self.twins is not None else None
         call = ops.make_group(self._specs(tables, fused, twin_data), self.B, grad_out, grad_out.shape[1],
@@ -490,6 +540,21 @@ def pooled_lookup(entries, dense: torch.Tensor | None = None, binding: SparseOpt
                               f"(more than {_lib.MAX_FEATURES} tables or >= 2^32 rows in one group)")
 
 
+def discover_optimizer(weights):
+    """The live ``torch.optim.Optimizer`` that holds any of ``weights`` among its parameters, or None.  The reference loop
+    hands the optimizer to the Trainer, never to the model (``torchctr/trainer.py:28-31``), so a model dropped into it is
+    not told which optimizer steps it; one scan of the garbage collector's objects at the first training step finds out."""
+    import gc
+    ids = {id(w) for w in weights}
+    for obj in gc.get_objects():
+        try:
+            if isinstance(obj, torch.optim.Optimizer) and any(id(p) in ids for g in obj.param_groups for p in g["params"]):
+                return obj
+        except ReferenceError:
+            continue
+    return None
+
+
 class PooledLookupGroup:
     """The sparse half of a model: tables in ``feat_configs`` order + the dense block."""
 
@@ -497,6 +562,23 @@ class PooledLookupGroup:
         self.names = list(names)
         self.tables = tables
         self.binding: SparseOptimizerBinding | None = None
+        self._autobind_tried = False
+
+    def autobind(self) -> None:
+        """Drop-in behaviour under the unmodified reference Trainer: no ``bind_optimizer`` call was made, so look for the
+        optimizer that steps these tables and fuse their update into backward when it is one the fused update can follow
+        (SGD / Adagrad / Adam without weight decay or momentum).  Otherwise the tables keep handing autograd sparse
+        gradients, which torch's SGD / Adagrad / SparseAdam accept."""
+        if self.binding is not None or self._autobind_tried:
+            return
+        self._autobind_tried = True
+        opt = discover_optimizer([self.tables[n].weight for n in self.names])
+        if opt is None:
+            return
+        try:
+            self.bind_optimizer(opt)
+        except ValueError as e:
+            warnings.warn(f"torchctr_b200: table update not fused ({e}); backward will emit sparse gradients", stacklevel=3)
 
     def bind_optimizer(self, optimizer, kind: str | None = None):
         self.binding = SparseOptimizerBinding(optimizer, [self.tables[n] for n in self.names], kind)
@@ -504,6 +586,8 @@ class PooledLookupGroup:
 
     def __call__(self, feats: dict, dense: torch.Tensor | None, training: bool, plan_link: PlanLink | None = None,
                  twins=None, fm: bool = False):
+        if training and self.binding is None and torch.is_grad_enabled():
+            self.autobind()
         entries = [(self.tables[n], feats[n], feats.get(n + "_weight") if self.tables[n].use_id_weight else None)
                    for n in self.names]
         return pooled_lookup(entries, dense, self.binding, training, plan_link, twins=twins, fm=fm)
