@@ -28,16 +28,45 @@ sys.path.insert(0, ROOT)
 CRITEO_VOCABS = [10_000_000, 10_000_000, 10_000_000, 2_000_000, 1_000_000, 1_000_000, 500_000, 300_000,
                  100_000, 100_000, 50_000, 20_000, 10_000, 10_000, 5_000, 5_000, 2_000, 2_000, 1_000, 1_000,
                  1_000, 500, 100, 50, 20, 10]
+# Amazon-review-shaped (BASELINE configs[0]): 8 categorical + 1 item sequence + 4 numerical
+AMAZON_VOCABS = [1_000_000, 500_000, 300_000, 200_000, 100_000, 100_000, 100_000, 100_000]
 NUM_DENSE = 13
 EMB_DIM = 16
 HIDDEN = [256, 128, 64]
 ZIPF_A = 1.05
 LR = 0.01
 
+CONFIGS = {
+    # BASELINE.json configs[1] -- the headline (what the driver runs)
+    "cfg2": dict(model="deepfm", vocabs=CRITEO_VOCABS, dim=16, num_dense=13, seq=None, batch=65536,
+                 workload="BASELINE configs[1]: DeepFM, 26 sparse (Zipf(1.05) ids, Criteo-like cardinalities, {rows} rows total) "
+                          "+ 13 dense, emb dim 16, tower 256-128-64, Adagrad"),
+    # configs[2]: DCN-v2, 3 cross layers of 845 x 845 (tensor-core cross matmul), emb dim 32
+    "cfg3": dict(model="dcnv2", vocabs=CRITEO_VOCABS, dim=32, num_dense=13, seq=None, batch=65536,
+                 workload="BASELINE configs[2]: DCN-v2 (stacked), 3 cross layers d = 26 x 32 + 13 = 845, same Criteo-shape ids "
+                          "({rows} rows total), emb dim 32, tower 256-128-64, Adagrad"),
+    # configs[0]: the reference's own CPU-runnable case, DNN under the unmodified reference Trainer
+    "cfg1": dict(model="dnn", vocabs=AMAZON_VOCABS, dim=16, num_dense=4, seq=dict(vocab=500_000, maxlen=50), batch=4096,
+                 workload="BASELINE configs[0]: DNN, Amazon-review-shaped: 8 categorical ({rows} rows total) + 1 item sequence "
+                          "(<= 50 ids, padded with -100) + 4 numerical, emb dim 16, tower 256-128-64, Adagrad"),
+}
 
-def feat_configs(vocabs=CRITEO_VOCABS, dim=EMB_DIM, num_dense=NUM_DENSE):
-    fc = [{"name": f"C{i + 1}", "type": "sparse", "num_embeddings": v, "emb_dim": dim} for i, v in enumerate(vocabs)]
-    fc += [{"name": f"I{i + 1}", "type": "dense"} for i in range(num_dense)]
+
+def get_cfg(name):
+    cfg = dict(CONFIGS[name])
+    cfg["name"] = name
+    cfg["rows"] = sum(cfg["vocabs"]) + (cfg["seq"]["vocab"] if cfg["seq"] else 0)
+    cfg["workload"] = cfg["workload"].format(rows=cfg["rows"])
+    cfg["metric"] = {"deepfm": "train samples/s, Criteo-shape DeepFM", "dcnv2": "train samples/s, Criteo-shape DCN-v2",
+                     "dnn": "train samples/s, Amazon-shape DNN"}[cfg["model"]]
+    return cfg
+
+
+def feat_configs(cfg):
+    fc = [{"name": f"C{i + 1}", "type": "sparse", "num_embeddings": v, "emb_dim": cfg["dim"]} for i, v in enumerate(cfg["vocabs"])]
+    if cfg["seq"]:
+        fc.append({"name": "hist", "type": "sparse", "num_embeddings": cfg["seq"]["vocab"], "emb_dim": cfg["dim"], "islist": True})
+    fc += [{"name": f"I{i + 1}", "type": "dense"} for i in range(cfg["num_dense"])]
     return fc
 
 
@@ -49,17 +78,32 @@ def zipf_ids(gen, n, V, a=ZIPF_A):
     return (x.floor().long() - 1).clamp_(0, V - 1)
 
 
-def make_batch(seed, B, vocabs=CRITEO_VOCABS, num_dense=NUM_DENSE, pin=False):
+def make_batch(cfg, seed, B, pin=False):
     gen = torch.Generator().manual_seed(seed)
     feats = {}
-    for i, V in enumerate(vocabs):
+    for i, V in enumerate(cfg["vocabs"]):
         feats[f"C{i + 1}"] = zipf_ids(gen, B, V).reshape(B, 1)
-    feats["dense_features"] = torch.randn(B, num_dense, generator=gen)
+    if cfg["seq"]:
+        L = cfg["seq"]["maxlen"]
+        ids = zipf_ids(gen, B * L, cfg["seq"]["vocab"]).reshape(B, L)
+        lens = torch.randint(0, L + 1, (B, 1), generator=gen)
+        ids[torch.arange(L)[None, :] >= lens] = -100                 # the collate's padding (torchctr/dataset.py:9)
+        feats["hist"] = ids
+    feats["dense_features"] = torch.randn(B, cfg["num_dense"], generator=gen)
     labels = (torch.rand(B, 1, generator=gen) < 0.25).float()
     if pin:
         feats = {k: v.pin_memory() for k, v in feats.items()}
         labels = labels.pin_memory()
     return feats, labels
+
+
+def build_model(cfg, oracle=False):
+    fc = feat_configs(cfg)
+    if oracle:
+        from oracle import models as om
+        return {"deepfm": om.OracleDeepFM, "dcnv2": om.OracleDCNv2, "dnn": om.OracleDNN}[cfg["model"]](fc, HIDDEN)
+    from torchctr_b200 import models as m
+    return {"deepfm": m.DeepFM, "dcnv2": m.DCNv2, "dnn": m.DNN}[cfg["model"]](fc, HIDDEN)
 
 
 def batch_bytes(batch):
@@ -117,25 +161,7 @@ def measured_peak_hbm():
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, B, budget_s):
-    """The reference arithmetic (oracle.models.OracleDeepFM == nn.Embedding + dense autograd +
-    dense torch.optim.Adagrad, the path torchctr/trainer.py:291-303 drives) on the host cores."""
-    from oracle import models as om
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    fc = feat_configs()
-    torch.manual_seed(0)
-    model = om.OracleDeepFM(fc, HIDDEN).train()
-    opt = torch.optim.Adagrad(model.parameters(), lr=LR)
-    batches = [make_batch(100 + i, B) for i in range(2)]
-
-    def step(i):
-        opt.zero_grad()
-        loss = model.training_step(batches[i % len(batches)], i)
-        loss.backward()
-        opt.step()
-        return loss.item()
-
+def _timed_cpu_steps(step, steps, warmup, budget_s):
     t0 = time.perf_counter()
     step(0)
     first = time.perf_counter() - t0
@@ -147,61 +173,129 @@ def cpu_reference_run(steps, warmup, B, budget_s):
     t1 = time.perf_counter()
     for i in range(k):
         step(warm_done + i)
-    dt = time.perf_counter() - t1
+    return k, warm_done, time.perf_counter() - t1, first
+
+
+def cpu_reference_run(cfg, steps, warmup, B, budget_s):
+    """The reference's CPU path on the host cores.  cfg1: the UNMODIFIED reference -- torchctr.models.DNN stepped by the
+    loop body of torchctr.trainer.Trainer.fit (baseline/_ref) -- kind "reference".  cfg2 / cfg3: DeepFM / DCN-v2 do not
+    exist upstream, so it is the oracle port of the reference arithmetic (nn.Embedding + dense autograd + dense
+    torch.optim.Adagrad, the path torchctr/trainer.py:291-303 drives) -- kind "port"."""
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    kind = "port"
+    torch.manual_seed(0)
+    model = None
+    if cfg["model"] == "dnn":
+        try:
+            from baseline import refshim
+            ref = refshim.load_reference()
+            model = ref.models.DNN(feat_configs(cfg), HIDDEN)
+            kind = "reference"
+        except ImportError:
+            model = None
+    if model is None:
+        model = build_model(cfg, oracle=True)
+    model.train()
+    opt = torch.optim.Adagrad(model.parameters(), lr=LR)
+    batches = [make_batch(cfg, 100 + i, B) for i in range(2)]
+
+    def step(i):                                 # trainer.py:292-303
+        opt.zero_grad()
+        loss = model.training_step(batches[i % len(batches)], i)
+        item = loss.item()                       # collect_loss, trainer.py:153-154
+        loss.backward()
+        opt.step()
+        return item
+
+    k, warm_done, dt, first = _timed_cpu_steps(step, steps, warmup, budget_s)
     return {"value": B * k / dt, "steps": k, "warmup": warm_done, "ms_per_step": 1e3 * dt / k, "cores": threads,
-            "first_step_s": first, "B": B}
+            "first_step_s": first, "B": B, "kind": kind}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = args.batch
-    r = cpu_reference_run(args.steps, args.warmup, B, budget_s=150.0)
+    cfg = get_cfg(args.config)
+    B = args.batch or cfg["batch"]
+    r = cpu_reference_run(cfg, args.steps, args.warmup, B, budget_s=150.0)
+    what = ("the unmodified torchctr.models.DNN (baseline/_ref) under the loop body of torchctr.trainer.Trainer.fit"
+            if r["kind"] == "reference" else "oracle port of the reference arithmetic (absent upstream): nn.Embedding + dense autograd")
     sample = (f"{r['steps']} steps (after {r['warmup']} warm-up) of B={B} samples each, full-size tables "
-              f"({sum(CRITEO_VOCABS)} rows x {EMB_DIM}), dense autograd + dense torch.optim.Adagrad, eager fp32 on CPU")
+              f"({cfg['rows']} rows x {cfg['dim']}), {what}, dense torch.optim.Adagrad, eager fp32 on CPU")
     line = {
-        "impl": "reference", "metric": "train samples/s, Criteo-shape DeepFM", "value": r["value"], "unit": "samples/s",
+        "impl": "reference", "metric": cfg["metric"], "value": r["value"], "unit": "samples/s",
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(B, 1),
-        "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": sample},
+        "config": workload_config(cfg, B, 1),
+        "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
         "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
 
-def workload_config(B, n_gpus):
-    return {"workload": "BASELINE configs[1]: DeepFM, 26 sparse (Zipf(1.05) ids, Criteo-like cardinalities, "
-                        f"{sum(CRITEO_VOCABS)} rows total) + 13 dense, emb dim 16, tower 256-128-64, Adagrad",
-            "batch_per_gpu": B, "global_batch": B * n_gpus, "emb_dim": EMB_DIM, "num_sparse": len(CRITEO_VOCABS),
-            "num_dense": NUM_DENSE, "table_rows": sum(CRITEO_VOCABS),
-            "l2": "inputs larger than L2: 2.4 GB of tables + 2.4 GB optimizer state, 4 distinct batches cycled"}
+def workload_config(cfg, B, n_gpus):
+    table_gb = cfg["rows"] * cfg["dim"] * 4 / 1e9
+    return {"workload": cfg["workload"], "name": cfg["name"],
+            "batch_per_gpu": B, "global_batch": B * n_gpus, "emb_dim": cfg["dim"], "num_sparse": len(cfg["vocabs"]) + (1 if cfg["seq"] else 0),
+            "num_dense": cfg["num_dense"], "table_rows": cfg["rows"],
+            "l2": f"inputs larger than L2: {table_gb:.1f} GB of tables + {table_gb:.1f} GB optimizer state, 4 distinct batches cycled"}
 
 
-def kernel_roofline(model, resident, B, dev, iters=12):
-    """Times ctr_emb_pool_fwd / ctr_emb_bwd_plan / ctr_emb_bwd_apply (fused Adagrad) of the D=16 table group one
-    launch at a time.  Algorithmic bytes per SURVEY.md 8(d): fwd 8S + 4DN + 4DB*F; update 8S + 4DB*F + 16DU."""
+def committed_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the ncu --set full capture summarised in
+    profiles/r2_traffic.json (written by profiles/summarise_ncu.py from a capture of THIS code; None when absent)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            t = json.load(f)
+        e = t["kernels"].get(kernel_key)
+        return (e["dram_bytes"], t["source"]) if e else (None, None)
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
+def measured_peak_tf32():
+    """Dense TF32 tensor peak: half of the measured cuBLAS bf16 burst figure (B200_PROFILING.md: tf32 = bf16 / 2)."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops"]) / 2.0, "measured (MEASURED_PEAKS.json bf16_tflops / 2: dense TF32 runs at half the bf16 rate)"
+    except (OSError, KeyError, ValueError):
+        return 1590.0 / 2.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s bf16 / 2)"
+
+
+def kernel_roofline(cfg, model, resident, B, dev, iters=12):
+    """Times the embedding entry points of the step's table group one launch at a time -- ctr_emb_pool_fwd /
+    ctr_emb_bwd_plan / ctr_emb_bwd_apply (fused Adagrad), with DeepFM's twin tables and FM term fused in exactly as the
+    step runs them -- behind a 1 GiB L2 flush.  Algorithmic bytes per SURVEY.md 8(d) (S id slots, N valid ids, U distinct
+    rows, F tables, D dim):  lookup 8S + 4DN + 4DBF (+ 4N twin reads + 4DB + 4B FM outputs);  plan 8S ids in + 8S sorted
+    (row, slot) pairs out;  update 8S + 4DBF + 16DU (+ 4DB + 4B + 16U for the fused terms)."""
     from torchctr_b200 import ops
     from torchctr_b200.nn.embedding import _layout
     names = model._names
     tables = [model.embeddings[n] for n in names]
-    D = EMB_DIM
-    S = B * len(names)
+    fused = cfg["model"] == "deepfm"
+    twins = [model.linear_embeddings[n] for n in names] if fused else None
+    D, F = cfg["dim"], len(names)
     flush = torch.empty(1 << 30, dtype=torch.uint8, device=dev)   # > L2; its fill also hides the host launch latency
     peak, peak_src = measured_peak_hbm()
     acc = {"emb_pool_fwd": 0.0, "emb_bwd_plan": 0.0, "emb_bwd_apply": 0.0}
-    uniq_total = 0
+    uniq_total = slots = valid = 0
     for it in range(iters + 2):
         feats, _ = resident[it % len(resident)]
         entries = [(t, feats[n], None) for t, n in zip(tables, names)]
-        cols, width, stride, dense_col = _layout(entries, NUM_DENSE)
+        cols, width, stride, dense_col = _layout(entries, cfg["num_dense"])
         out = torch.empty(B, stride, device=dev)
         gout = torch.randn(B, stride, device=dev)
-        specs = [ops.FeatureSpec(ids=feats[n], table=t.weight.data, num_rows=t.num_embeddings, D=D, out_col=c,
-                                 state0=t.opt_state0) for t, n, c in zip(tables, names, cols)]
-        fwd = ops.make_group(specs, B, out, stride, dense=feats["dense_features"], dense_col=dense_col, zero_from=width)
-        bwd = ops.make_group(specs, B, gout, stride)
+        extra = torch.empty(B, device=dev) if fused else None
+        gextra = torch.randn(B, device=dev) if fused else None
+        fm_sum = torch.empty(B, D, device=dev) if fused else None
+        specs = [ops.FeatureSpec(ids=feats[n], table=t.weight.data, num_rows=t.num_embeddings, D=D, out_col=c, state0=t.opt_state0,
+                                 twin_table=tw.weight.data if fused else None, twin_state0=tw.opt_state0 if fused else None)
+                 for t, tw, n, c in zip(tables, twins or tables, names, cols)]
+        fwd = ops.make_group(specs, B, out, stride, dense=feats["dense_features"], dense_col=dense_col, zero_from=width,
+                             extra=extra, fm_sum=fm_sum, fm=fused)
+        bwd = ops.make_group(specs, B, gout, stride, extra=gextra, fm_sum=fm_sum, fm=fused)
         ws = torch.empty(ops.emb_bwd_workspace_bytes(bwd) + 256, dtype=torch.uint8, device=dev)
         opt = ops.make_opt("adagrad", lr=LR, eps=1e-10)
         for name, fn in (("emb_pool_fwd", lambda: ops.emb_pool_fwd(fwd)), ("emb_bwd_plan", lambda: ops.emb_bwd_plan(bwd, ws, runs=False)),
@@ -213,28 +307,66 @@ def kernel_roofline(model, resident, B, dev, iters=12):
             if it >= 2:
                 acc[name] += e0.elapsed_time(e1)
         if it >= 2:
-            uniq_total += sum(int(torch.unique(feats[n]).numel()) for n in names)
-    U = uniq_total / iters
-    bytes_ = {"emb_pool_fwd": 8 * S + 4 * D * S + 4 * D * S, "emb_bwd_apply": 8 * S + 4 * D * S + 16 * D * U}
+            for n in names:
+                v = feats[n][feats[n] >= 0]
+                uniq_total += int(torch.unique(v).numel())
+                slots += feats[n].numel()
+                valid += v.numel()
+    U, S, N = uniq_total / iters, slots / iters, valid / iters
+    fx = (4 * N + 4 * D * B + 4 * B) if fused else 0
+    bx = (4 * D * B + 4 * B + 16 * U) if fused else 0
+    bytes_ = {"emb_pool_fwd": 8 * S + 4 * D * N + 4 * D * B * F + fx, "emb_bwd_plan": 16 * S,
+              "emb_bwd_apply": 8 * S + 4 * D * B * F + 16 * D * U + bx}
     kern = {}
     for name, total in acc.items():
         ms = total / iters
-        kern[name] = {"ms_per_launch": ms}
-        if name in bytes_:
-            kern[name]["algorithmic_bytes"] = bytes_[name]
-            kern[name]["achieved_GBs"] = bytes_[name] / (ms * 1e-3) / 1e9
-            kern[name]["frac_of_peak"] = kern[name]["achieved_GBs"] / peak
-    dom = "emb_bwd_apply" if kern["emb_bwd_apply"]["ms_per_launch"] >= kern["emb_pool_fwd"]["ms_per_launch"] else "emb_pool_fwd"
+        kern[name] = {"ms_per_launch": ms, "algorithmic_bytes": bytes_[name], "achieved_GBs": bytes_[name] / (ms * 1e-3) / 1e9}
+        kern[name]["frac_of_peak"] = kern[name]["achieved_GBs"] / peak
+    tot_ms = sum(k["ms_per_launch"] for k in kern.values())
+    tot_bytes = sum(bytes_.values())
+    kern["lookup+plan+update"] = {"ms_per_launch": tot_ms, "algorithmic_bytes": tot_bytes, "achieved_GBs": tot_bytes / (tot_ms * 1e-3) / 1e9,
+                                  "frac_of_peak": tot_bytes / (tot_ms * 1e-3) / 1e9 / peak}
+    dom = max(acc, key=lambda k: kern[k]["ms_per_launch"])
     k = kern[dom]
-    roofline = {"bound": "hbm", "kernel": dom + (" (sparse gradient reduce + fused Adagrad row update, 26 tables x D=16)"
-                                                 if dom == "emb_bwd_apply" else " (gather + pool + concat, 26 tables x D=16)"),
+    what = {"emb_bwd_apply": "sparse gradient reduce + fused Adagrad row update" + (" + FM / first-order gradients" if fused else ""),
+            "emb_pool_fwd": "gather + pool + concat" + (" + FM / first-order terms" if fused else ""),
+            "emb_bwd_plan": "key generation + per-table radix sort of the (row, slot) pairs"}[dom]
+    traffic, traffic_src = committed_traffic(dom + ("_fused" if fused else ""))
+    roofline = {"bound": "hbm", "kernel": f"{dom} ({what}, {F} tables x D={D})",
                 "achieved": k["achieved_GBs"], "peak": peak, "unit": "GB/s", "frac": k["frac_of_peak"],
-                "traffic": 234.1e6 if dom == "emb_bwd_apply" else 109.1e6,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel in profiles/r1_final_kernels_full.summary.txt (ncu --set full)",
+                "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": k["algorithmic_bytes"],
                 "ms_per_launch": k["ms_per_launch"], "unique_rows_per_launch": U,
+                "combined_lookup_plan_update": kern["lookup+plan+update"],
                 "timing": f"CUDA events around each launch on the launching stream, 1 GiB L2 flush before each, {iters} launches"}
-    return kern, roofline
+    return kern, roofline, dom
+
+
+def cross_gemm_roofline(cfg, B, dev, iters=12):
+    """cfg3: the DCN-v2 cross matmul x W^T, [B, 848] x [848, 848] (d = 845 padded to 16-byte rows), on ctr_linear_fwd
+    (tcgen05 kind::tf32).  Tensor-bound: 2 B d^2 FLOP against the dense TF32 peak."""
+    from torchctr_b200 import ops
+    d = len(cfg["vocabs"]) * cfg["dim"] + cfg["num_dense"]
+    dp = (d + 3) // 4 * 4
+    x = torch.randn(B, dp, device=dev)
+    w = torch.randn(dp, dp, device=dev) / d ** 0.5
+    flush = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    tot = 0.0
+    for it in range(iters + 2):
+        flush.fill_(it & 0xff)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); ops.linear_fwd(x, w); e1.record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            tot += e0.elapsed_time(e1)
+    ms = tot / iters
+    peak, src = measured_peak_tf32()
+    flops = 2.0 * B * d * d
+    traffic, traffic_src = committed_traffic("linear_tf32_cross")
+    return {"bound": "tensor", "kernel": f"linear_tf32_kernel<256> (DCN-v2 cross matmul [{B}, {dp}] x [{dp}, {dp}]^T, tcgen05 kind::tf32)",
+            "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / peak,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": src, "algorithmic_flops_per_launch": flops,
+            "ms_per_launch": ms, "timing": f"CUDA events around each launch, 1 GiB L2 flush before each, {iters} launches"}
 
 
 def kernels_in_step(eager_step, resident, steps=6, sleep_cycles=16_000_000):
@@ -253,11 +385,37 @@ def kernels_in_step(eager_step, resident, steps=6, sleep_cycles=16_000_000):
 
 
 # ---------------------------------------------------------------------------------------------
+def trainer_fit_leg(cfg, model, opt, host_batches, steps):
+    """samples/s INSIDE an unmodified ``torchctr.trainer.Trainer.fit`` (baseline/_ref) driving our model:
+    pinned host batches in, ``loss.item()`` every step (trainer.py:153-154), eager launches.  One epoch of ``steps``
+    batches plus the one evaluation batch ``fit`` insists on (trainer.py:332-333); wall clock around ``fit``."""
+    try:
+        from baseline import refshim
+        ref = refshim.load_reference()
+    except ImportError:
+        return None
+    import logging
+    train = [host_batches[i % len(host_batches)] for i in range(steps)]
+    evalb = [host_batches[0]]
+    quiet = logging.getLogger("bench.quiet")
+    quiet.setLevel(logging.ERROR)
+    tr = ref.trainer.Trainer(model, optimizer=opt, max_epochs=1, use_accelerate=False, log_steps=10 ** 9, logger=quiet)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tr.fit(train, evalb)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    B = train[0][1].shape[0]
+    return {"value": B * steps / dt, "unit": "samples/s", "ms_per_step": 1e3 * dt / steps, "steps": steps,
+            "how": "unmodified torchctr.trainer.Trainer.fit (baseline/_ref) over torchctr_b200's model: pinned host batches in, "
+                   "loss.item() per step, eager launches, one evaluation batch included in the wall time"}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from torchctr_b200 import ops
-    from torchctr_b200.models import DeepFM
 
+    cfg = get_cfg(args.config)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -265,17 +423,16 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
+    B = args.batch or cfg["batch"]
     from torchctr_b200.nn import set_matmul_precision
     torch.backends.cuda.matmul.allow_tf32 = True        # tower GEMMs on tensor cores (TF32 in, fp32 accumulate)
     torch.backends.cudnn.allow_tf32 = True
     set_matmul_precision(args.precision)                # "tf32" (headline) | "tf32x3" (error-compensated, fp32-grade)
 
     torch.manual_seed(0)
-    fc = feat_configs()
     if world > 1:
         from torchctr_b200.parallel import shard_model
-    model = DeepFM(fc, HIDDEN)                            # identical on every rank (same seed)
+    model = build_model(cfg)                              # identical on every rank (same seed)
     if world > 1:
         dedup = {"auto": None, "on": True, "off": False}[args.dedup]
         model = shard_model(model, None, device=dev, dedup=dedup)    # keep this rank's rows of every table, drop the rest
@@ -287,7 +444,7 @@ def run_ours(args):
     model.bind_optimizer(opt, kind="adagrad")
 
     nb = 4
-    host = [make_batch(1000 * rank + i, B, pin=True) for i in range(nb)]
+    host = [make_batch(cfg, 1000 * rank + i, B, pin=True) for i in range(nb)]
     resident = [({k: v.to(dev) for k, v in f.items()}, l.to(dev)) for f, l in host]
     h2d = batch_bytes(host[0])
 
@@ -298,7 +455,7 @@ def run_ours(args):
             opt.zero_grad(set_to_none=True)
         loss = model.training_step(batch, i)
         if world > 1:
-            (loss / world).backward()                   # tables: all-to-all of gradients + owner-side fused update
+            (loss / world).backward()                   # tables: owners pull the gradients + owner-side fused update
             model.reduce_dense_grads()                  # tower: one flat all-reduce
         else:
             loss.backward()
@@ -310,15 +467,32 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    first_losses = []
     for i in range(max(args.warmup, 3)):                 # eager warm-up (also sizes workspaces / optimizer state)
-        eager_step(resident[i % nb], i)
+        loss = eager_step(resident[i % nb], i)
+        if i < 2:
+            first_losses.append(loss.detach().clone())
+        del loss        # a live loss keeps its autograd graph (and AccumulateGrad nodes bound to THIS stream) alive into the capture
+    # N > 1: the global-batch loss of the first two steps (mean over the ranks' losses), printed so that runs at different
+    # N -- and the N = 1 run on the same global batch -- can be compared
+    loss_trace = None
+    if world > 1:
+        t = torch.stack(first_losses)
+        dist.all_reduce(t)
+        loss_trace = (t / world).tolist()
+    else:
+        loss_trace = [float(x) for x in first_losses]
     launches_per_step = None
     in_step = kernels_in_step(eager_step, resident)      # at N > 1: this rank's kernels, peers' rows over NVLink included
     if args.roofline_only:                               # profiling hook: just the embedding entry points
-        kern, roofline = kernel_roofline(model, resident, B, dev, iters=args.steps)
-        emit({"kernels": kern, "roofline": roofline, "kernels_in_step": in_step})
+        kern, roofline, _ = kernel_roofline(cfg, model, resident, B, dev, iters=args.steps)
+        out = {"kernels": kern, "roofline": roofline, "kernels_in_step": in_step}
+        if cfg["model"] == "dcnv2":
+            out["roofline_tensor"] = cross_gemm_roofline(cfg, B, dev, iters=args.steps)
+        emit(out)
         return
     graphed_holder = [None]
+    packed = None
     if args.no_graph:
         step = eager_step
     else:
@@ -333,6 +507,7 @@ def run_ours(args):
         launches_per_step = (ops.kernel_launches() - l0) // 2      # one eager warm-up + one captured step
         graphed_holder[0] = graphed
         step = lambda batch, i: graphed(batch)           # noqa: E731
+        packed = [graphed.pack(b) for b in resident]     # resident leg: one device-to-device copy per step, like the e2e leg
 
     def timed(batches, steps, read_loss):
         barrier()
@@ -360,6 +535,7 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
+    res_batches = packed if packed is not None else resident
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -367,11 +543,11 @@ def run_ours(args):
     i = 0                                                # nvidia-smi (100 ms period) samples clocks and throttle reasons
     while time.perf_counter() - t_load < 0.8:
         for _ in range(25):
-            step(resident[i % nb], i)
+            step(res_batches[i % nb], i)
             i += 1
         torch.cuda.synchronize()
     launches0 = ops.kernel_launches()
-    ms = timed(resident, args.steps, read_loss=False)
+    ms = timed(res_batches, args.steps, read_loss=False)
     launches = ops.kernel_launches() - launches0 if launches_per_step is None else launches_per_step * args.steps
     # end to end: pinned host buffers in, loss out, every step
     for i in range(3):
@@ -391,8 +567,8 @@ def run_ours(args):
         graphed_x3 = GraphedTrainStep(model, opt, resident[0], warmup=1)
         step_tf32, step = step, (lambda batch, i: graphed_x3(batch))
         for i in range(3):
-            step(resident[i % nb], i)
-        ms_x3 = timed(resident, args.steps, read_loss=False)
+            step(res_batches[i % nb], i)
+        ms_x3 = timed(res_batches, args.steps, read_loss=False)
         step = step_tf32
         set_matmul_precision(args.precision)
         exact = {"value": B * args.steps / (ms_x3 / 1e3), "unit": "samples/s", "ms_per_step": ms_x3 / args.steps,
@@ -400,29 +576,37 @@ def run_ours(args):
 
     # ---- kernel roofline: each embedding entry point timed alone, CUDA events on the launching stream,
     # L2 flushed (1 GiB written) before every launch, on the step's real tensors
-    kern, roofline = kernel_roofline(model, resident, B, dev) if (rank == 0 and world == 1) else ({}, None)
+    kern, roofline, dom = kernel_roofline(cfg, model, resident, B, dev) if (rank == 0 and world == 1) else ({}, None, None)
     if roofline is not None:
         # the same kernel inside the real step (caches as the step leaves them): CUDA events, eager step behind a device sleep
-        name = roofline["kernel"].split(" ")[0] + f"_d{EMB_DIM}"
+        name = dom + f"_d{cfg['dim']}" if dom != "emb_bwd_plan" else dom
         if name in in_step:
             us = in_step[name]["us_per_step"] / max(in_step[name]["calls_per_step"], 1)
             roofline["in_step"] = {"us_per_launch": us, "achieved": roofline["algorithmic_bytes_per_launch"] / (us * 1e-6) / 1e9,
                                    "frac": roofline["algorithmic_bytes_per_launch"] / (us * 1e-6) / 1e9 / roofline["peak"]}
         roofline["random_access_ceiling"] = ("B200 random 64-byte row reads top out at 2.2 TB/s (34 G rows/s), read-modify-write of "
-                                             "64-byte rows at 17 G rows/s (profiles/micro/random_access.cu): this kernel's gathers "
-                                             "are 64-byte rows, so ~0.35 of the copy peak is its hardware ceiling")
+                                             "64-byte rows at 17 G rows/s (profiles/micro/random_access.cu): the gathers of these "
+                                             "kernels are 64-byte rows, so ~0.35 of the copy peak is the hardware ceiling of the update")
+    roofline_tensor = cross_gemm_roofline(cfg, B, dev) if (rank == 0 and world == 1 and cfg["model"] == "dcnv2") else None
+
+    # cfg1: the number SURVEY.md 8(d) asks for -- samples/s inside the reference's own, unmodified Trainer.fit
+    trainer_leg = None
+    if world == 1 and cfg["model"] == "dnn" and not args.no_trainer_leg:
+        trainer_leg = trainer_fit_leg(cfg, model, opt, host, max(args.steps, 20))
 
     line = {
-        "metric": "train samples/s, Criteo-shape DeepFM", "value": value, "unit": "samples/s", "n_gpus": world,
+        "metric": cfg["metric"], "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 tables / interaction / BatchNorm + " + ("tf32" if args.precision == "tf32" else "3xTF32 (fp32-grade)")
                  + " tower GEMMs (tcgen05, fp32 accumulate)",
-        "data": "synthetic", "config": workload_config(B, world), "exact_mode": exact,
+        "data": "synthetic", "config": workload_config(cfg, B, world), "exact_mode": exact,
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "cuda_graph": not args.no_graph, "kernels": kern, "kernels_in_step": in_step,
-        "roofline": roofline,
+        "roofline": roofline_tensor if roofline_tensor is not None else roofline,
+        "roofline_embedding": roofline if roofline_tensor is not None else None,
+        "trainer_fit": trainer_leg, "loss_first_steps": loss_trace,
         "parallelism": "single GPU" if world == 1 else f"tables row-sharded over {world} GPUs (owner = (row + table) mod P); rows read "
                        "and gradients pulled through NVLink peer mappings inside the lookup / update kernels (no all-to-all), "
                        "batch data-parallel, tower replicated + one NCCL all-reduce"
@@ -434,11 +618,13 @@ def run_ours(args):
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_run(3, 1, B, budget_s=40.0)
+            r = cpu_reference_run(cfg, 3, 1, B, budget_s=40.0 if cfg["model"] != "dnn" else 15.0)
+            what = ("unmodified torchctr.models.DNN (baseline/_ref), loop body of Trainer.fit" if r["kind"] == "reference"
+                    else "oracle port of the reference arithmetic")
             line["cpu_baseline"] = {
-                "value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                "value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
                 "sample": f"{r['steps']} steps of B={r['B']} samples, full-size tables, dense autograd + dense Adagrad "
-                          f"(oracle.models.OracleDeepFM, eager fp32 CPU)"}
+                          f"({what}, eager fp32 CPU)"}
         emit(line)
     if world > 1:
         # the measurement is done and printed: tear down without letting a slow NCCL / IPC teardown hold the job
@@ -474,10 +660,12 @@ def main():
     _stdout_to_stderr()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json configs: cfg2 DeepFM (headline), cfg3 DCN-v2, cfg1 DNN")
+    ap.add_argument("--no-trainer-leg", action="store_true", help="cfg1: skip the run inside the unmodified reference Trainer.fit")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--roofline-only", action="store_true", help="only time the embedding entry points (ncu target)")

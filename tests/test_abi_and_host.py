@@ -156,3 +156,16 @@ def test_integration_doc_names_every_entry_point():
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     missing = [n for n in declared_in_header() if n not in doc]
     assert not missing, missing
+
+
+def test_dropout_seed_is_snapshotted_per_forward():
+    """backward must see the seed value ITS forward used (fwd, fwd, bwd orders): every training forward gets its own
+    copy of the device counter instead of a reference to the tensor that the next forward increments in place."""
+    import torch
+    from torchctr_b200.models import DNN
+    m = DNN([{"name": "a", "type": "sparse", "num_embeddings": 10, "emb_dim": 16}, {"name": "d", "type": "dense"}], [16])
+    s1 = m._step_seed(torch.device("cpu"))
+    s2 = m._step_seed(torch.device("cpu"))
+    assert s1.data_ptr() != s2.data_ptr() and int(s2) == int(s1) + 1
+    m._step_seed(torch.device("cpu"))
+    assert int(s2) == int(s1) + 1                      # later forwards do not change what earlier ones hold

@@ -371,3 +371,27 @@ def test_cfg5_long_sequences_with_growing_vocab(pooling):
         # optimizer, not of the kernel (sum pooling holds 1e-5)
         close(table.weight.detach().cpu(), table_ref, 1e-5 if pooling == "sum" else 3e-4)
         close(table.opt_state0.detach().cpu()[:n], acc_ref, 5e-5)      # sums of squares: twice the relative error of the gradients
+
+
+def test_model_on_a_device_that_is_not_current():
+    """every launch runs under the device (and on the stream) of its tensors, not of torch's current device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from oracle import models as om
+    from torchctr_b200.models import DeepFM
+    gen = torch.Generator().manual_seed(2)
+    fc, feats, labels = _criteo_like(gen, 256, 4, 50, 16, 3)
+    torch.manual_seed(0)
+    ref = no_dropout(om.OracleDeepFM(fc, [32, 16])).train()
+    ours = no_dropout(DeepFM(fc, [32, 16])).to("cuda:1").train()
+    ours.load_state_dict(ref.state_dict())
+    assert torch.cuda.current_device() == 0
+    opt_ref = torch.optim.SGD(ref.parameters(), lr=0.1)
+    opt = torch.optim.SGD(ours.parameters(), lr=0.1)
+    ours.bind_optimizer(opt)
+    l_ref = ref.training_step((feats, labels), 0); l = ours.training_step((feats, labels), 0)
+    close(l, l_ref, TOWER_RTOL)
+    l_ref.backward(); l.backward(); opt_ref.step(); opt.step()
+    torch.cuda.synchronize("cuda:1")
+    for k, v in ref.state_dict().items():
+        close(ours.state_dict()[k], v, 5e-4)

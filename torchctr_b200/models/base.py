@@ -217,7 +217,9 @@ class CTRModelBase(nn.Module):
             seed = torch.full((1,), torch.initial_seed() & 0x7fffffffffff, dtype=torch.int64, device=device)
             self._drop_seed = seed
         seed += 1
-        return seed
+        # a snapshot, not the counter itself: backward recomputes the dropout mask from the value ITS forward used, even
+        # when another training forward ran in between (two losses summed, fwd-fwd-bwd orders)
+        return seed.clone()
 
     def _grow_vocabularies(self, feats):
         if not self.training or self._sharded is not None:

@@ -350,6 +350,14 @@ class _LookupCall:
         return specs
 
     def run_forward(self, dense, weights):
+        with torch.cuda.device(weights[0].device):       # the model may live on a device that is not the current one
+            return self._run_forward(dense, weights)
+
+    def run_backward(self, grad_out, grad_extra=None):
+        with torch.cuda.device(grad_out.device):
+            return self._run_backward(grad_out, grad_extra)
+
+    def _run_forward(self, dense, weights):
         dev = weights[0].device
         B = self.B
         out = torch.empty(B, self.stride, dtype=torch.float32, device=dev)
@@ -387,7 +395,7 @@ class _LookupCall:
                 link.pending = side
         return out
 
-    def run_backward(self, grad_out, grad_extra=None):
+    def _run_backward(self, grad_out, grad_extra=None):
         mods = [m for m, _, _ in self.entries]
         needs = [m.weight.requires_grad for m in mods]
         nw = len(mods) + (len(self.twins) if self.twins is not None else 0)

@@ -70,6 +70,7 @@ class GroupCall:
     """A lowered ``ctr_group_t`` plus the Python objects that keep its pointers alive."""
     struct: _lib.Group
     keep: list = field(default_factory=list)
+    device: torch.device | None = None      # where the group's tensors live: launches run under this device and on ITS stream
 
 
 def make_group(features, B: int, out: torch.Tensor | None, out_stride: int, dense: torch.Tensor | None = None,
@@ -143,11 +144,46 @@ def make_group(features, B: int, out: torch.Tensor | None, out_stride: int, dens
     g.extra = _lib.ptr(extra)
     g.fm_sum = _lib.ptr(fm_sum)
     g.fm = 1 if fm else 0
-    return GroupCall(g, keep)
+    dev = None
+    for t in [out, dense] + [f.ids for f in features] + [f.table for f in features]:
+        if t is not None and t.is_cuda:
+            dev = t.device
+            break
+    return GroupCall(g, keep, dev)
 
 
-def _stream(t: torch.Tensor | None = None):
-    return _lib.stream_ptr(t.device if t is not None else None)
+def _stream(t=None):
+    """Raw handle of the current torch stream of the device ``t`` (a tensor, a GroupCall or None = current device) lives on."""
+    dev = getattr(t, "device", None)
+    return _lib.stream_ptr(dev)
+
+
+def _device_of(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, (list, tuple)) and a and isinstance(a[0], torch.Tensor):
+            a = a[0]
+        if isinstance(a, GroupCall) and a.device is not None:
+            return a.device
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a.device
+        if isinstance(a, VocabMapHandle):
+            return a.keys.device
+    return None
+
+
+def _guarded(fn):
+    """Runs ``fn`` with the CUDA device of its first tensor / group argument current: a kernel launched from another
+    device's context onto this device's stream (or pointers) is an error or, worse, an unordered access."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = _device_of(args, kwargs)
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 class KernelTimer:
@@ -198,22 +234,25 @@ def _width_tag(call: GroupCall) -> str:
     return f"_d{call.struct.features[0].D}" if call.struct.num_features > 0 else ""
 
 
+@_guarded
 def emb_pool_fwd(call: GroupCall) -> None:
     with _timed("emb_pool_fwd" + _width_tag(call)):
-        _lib.check(_lib.lib().ctr_emb_pool_fwd(C.byref(call.struct), _stream()), "ctr_emb_pool_fwd")
+        _lib.check(_lib.lib().ctr_emb_pool_fwd(C.byref(call.struct), _stream(call)), "ctr_emb_pool_fwd")
 
 
+@_guarded
 def emb_bwd_workspace_bytes(call: GroupCall) -> int:
     return _lib.check(_lib.lib().ctr_emb_bwd_workspace_bytes(C.byref(call.struct)), "ctr_emb_bwd_workspace_bytes")
 
 
+@_guarded
 def emb_bwd_plan(call: GroupCall, workspace: torch.Tensor, runs: bool = True) -> None:
     """Sort the (row, slot) pairs of the group; ``runs=False`` skips the run list, which only the unique-row
     outputs of ``emb_bwd_apply`` need (a fused training step does not ask for them)."""
     _chk(workspace, "workspace", torch.uint8)
     with _timed("emb_bwd_plan"):
         _lib.check(_lib.lib().ctr_emb_bwd_plan_ex(C.byref(call.struct), workspace.data_ptr(), workspace.numel(),
-                                                  0 if runs else _lib.PLAN_NO_RUNS, _stream()), "ctr_emb_bwd_plan")
+                                                  0 if runs else _lib.PLAN_NO_RUNS, _stream(call)), "ctr_emb_bwd_plan")
 
 
 def make_opt(kind: str = "none", lr: float = 0.0, eps: float = 1e-10, betas=(0.9, 0.999), step: int = 1,
@@ -230,6 +269,7 @@ def opt_hyper(opt: _lib.Opt):
     return [h.lr, h.eps, h.one_minus_beta1, h.one_minus_beta2, h.adam_step_size]
 
 
+@_guarded
 def emb_bwd_apply(call: GroupCall, workspace: torch.Tensor, opt: _lib.Opt, uniq_feature=None, uniq_row=None,
                   row_grad=None, num_unique=None) -> None:
     _chk(uniq_feature, "uniq_feature", torch.int32)
@@ -240,9 +280,10 @@ def emb_bwd_apply(call: GroupCall, workspace: torch.Tensor, opt: _lib.Opt, uniq_
     with _timed("emb_bwd_apply" + _width_tag(call)):
         _lib.check(_lib.lib().ctr_emb_bwd_apply(C.byref(call.struct), workspace.data_ptr(), C.byref(opt),
                                                 _lib.ptr(uniq_feature), _lib.ptr(uniq_row), _lib.ptr(row_grad), stride,
-                                                _lib.ptr(num_unique), _stream()), "ctr_emb_bwd_apply")
+                                                _lib.ptr(num_unique), _stream(call)), "ctr_emb_bwd_apply")
 
 
+@_guarded
 def hash_bucket(ids: torch.Tensor, buckets: int, seed: int = 0) -> torch.Tensor:
     """``torchctr.utils.hash_bucket`` (utils.py:103-119) on a tensor of integer ids -> int32 buckets."""
     _chk(ids, "ids", torch.int64)
@@ -256,6 +297,7 @@ def hash_bucket(ids: torch.Tensor, buckets: int, seed: int = 0) -> torch.Tensor:
     return out
 
 
+@_guarded
 def rows_gather(ids: torch.Tensor, table: torch.Tensor, status: torch.Tensor | None = None) -> torch.Tensor:
     _chk(ids, "ids", torch.int64)
     _chk(table, "table", torch.float32)
@@ -265,6 +307,7 @@ def rows_gather(ids: torch.Tensor, table: torch.Tensor, status: torch.Tensor | N
     return out
 
 
+@_guarded
 def normal_fill_rows(table: torch.Tensor, row0: int, n: int, mean: float, std: float, seed: int) -> None:
     _chk(table, "table", torch.float32)
     if row0 < 0 or row0 + n > table.shape[0]:
@@ -273,6 +316,7 @@ def normal_fill_rows(table: torch.Tensor, row0: int, n: int, mean: float, std: f
                                                seed & 0xFFFFFFFFFFFFFFFF, _stream(table)), "ctr_normal_fill_rows")
 
 
+@_guarded
 def ids_minmax(ids: torch.Tensor) -> torch.Tensor:
     """Device tensor i64 [2] = (min, max) of ids."""
     _chk(ids, "ids", torch.int64)
@@ -281,6 +325,7 @@ def ids_minmax(ids: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_guarded
 def vocab_fit(vmap: VocabMapHandle, keys: torch.Tensor, next_row: torch.Tensor, min_freq: int = 0,
               counts: torch.Tensor | None = None, status: torch.Tensor | None = None) -> None:
     _chk(keys, "keys", torch.int64)
@@ -294,6 +339,7 @@ def vocab_fit(vmap: VocabMapHandle, keys: torch.Tensor, next_row: torch.Tensor, 
                "ctr_vocab_fit")
 
 
+@_guarded
 def vocab_transform(vmap: VocabMapHandle, keys: torch.Tensor, oov_row: int = 0) -> torch.Tensor:
     _chk(keys, "keys", torch.int64)
     rows = torch.empty(keys.shape, dtype=torch.int32, device=keys.device)
@@ -302,6 +348,7 @@ def vocab_transform(vmap: VocabMapHandle, keys: torch.Tensor, oov_row: int = 0) 
     return rows
 
 
+@_guarded
 def vocab_insert(vmap: VocabMapHandle, keys: torch.Tensor, rows: torch.Tensor, status: torch.Tensor | None = None) -> None:
     _chk(keys, "keys", torch.int64)
     _chk(rows, "rows", torch.int32)
@@ -309,10 +356,12 @@ def vocab_insert(vmap: VocabMapHandle, keys: torch.Tensor, rows: torch.Tensor, s
                                            _lib.ptr(status), _stream(keys)), "ctr_vocab_insert")
 
 
+@_guarded
 def vocab_clear(vmap: VocabMapHandle) -> None:
     _lib.check(_lib.lib().ctr_vocab_clear(C.byref(vmap.struct), _stream(vmap.keys)), "ctr_vocab_clear")
 
 
+@_guarded
 def fm_fwd(x: torch.Tensor, F: int, D: int, first: torch.Tensor | None = None, out: torch.Tensor | None = None,
            accumulate: bool = False) -> torch.Tensor:
     """x f32 [B, stride>=F*D] -> out f32 [B, 1] = FM second-order term (+ row sums of ``first`` [B, n])."""
@@ -332,6 +381,7 @@ def fm_fwd(x: torch.Tensor, F: int, D: int, first: torch.Tensor | None = None, o
     return out
 
 
+@_guarded
 def fm_bwd(x: torch.Tensor, F: int, D: int, gout: torch.Tensor, gx: torch.Tensor, accumulate: bool,
            gfirst: torch.Tensor | None = None) -> None:
     B = x.shape[0]
@@ -342,6 +392,7 @@ def fm_bwd(x: torch.Tensor, F: int, D: int, gout: torch.Tensor, gx: torch.Tensor
                                          0 if gfirst is None else gfirst.stride(0), _stream(x)), "ctr_fm_bwd")
 
 
+@_guarded
 def cross_combine_fwd(x0, x, u, bias) -> torch.Tensor:
     for name, t in (("x0", x0), ("x", x), ("u", u)):
         _chk(t, name, torch.float32)
@@ -353,6 +404,7 @@ def cross_combine_fwd(x0, x, u, bias) -> torch.Tensor:
     return y
 
 
+@_guarded
 def cross_combine_bwd(x0, u, bias, gy, gx0: torch.Tensor, accumulate: bool) -> torch.Tensor:
     for name, t in (("x0", x0), ("u", u), ("gy", gy), ("gx0", gx0)):
         _chk(t, name, torch.float32)
@@ -364,6 +416,7 @@ def cross_combine_bwd(x0, u, bias, gy, gx0: torch.Tensor, accumulate: bool) -> t
     return gu
 
 
+@_guarded
 def route_build(call: GroupCall, world: int, base: torch.Tensor, S: int):
     """Buckets the id slots of ``call`` by owner rank.  Returns (counts i64 [world+1], send_rows i64 [S],
     inv i64 [S], workspace) -- see ``ctr_route_build``."""
@@ -381,6 +434,7 @@ def route_build(call: GroupCall, world: int, base: torch.Tensor, S: int):
     return counts, send_rows, inv, ws
 
 
+@_guarded
 def route_grad_gather(call: GroupCall, world: int, workspace: torch.Tensor, n: int, D: int) -> torch.Tensor:
     g_send = torch.empty(n, D, dtype=torch.float32, device=workspace.device)
     with _timed("route_grad_gather"):
@@ -389,6 +443,7 @@ def route_grad_gather(call: GroupCall, world: int, workspace: torch.Tensor, n: i
     return g_send
 
 
+@_guarded
 def linear_fwd(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor | None = None, act: int = 0,
                out: torch.Tensor | None = None) -> torch.Tensor:
     """``act(A @ W.T + bias)`` on tcgen05 tensor cores (TF32 inputs, fp32 accumulate).  A f32 [M, K] with unit
@@ -410,6 +465,7 @@ def linear_fwd(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor | None = Non
     return out
 
 
+@_guarded
 def split_tf32(x: torch.Tensor, axis: int, role: int) -> torch.Tensor:
     """3xTF32 operand of ``x`` f32 [rows, cols] (``ctr_split_tf32``): hi / lo TF32 parts laid out as three segments along
     the reduction axis of the GEMM that consumes them -- axis 1: [rows, 3 * seg] (seg = cols rounded up to 4) for
@@ -437,39 +493,45 @@ def make_shard(world: int, rank: int, adj: torch.Tensor) -> _lib.Shard:
     return _lib.Shard(world, rank, adj.data_ptr())
 
 
+@_guarded
 def emb_pool_fwd_sharded(call: GroupCall, shard: _lib.Shard, tables) -> None:
     with _timed("emb_pool_fwd" + _width_tag(call)):
-        _lib.check(_lib.lib().ctr_emb_pool_fwd_sharded(C.byref(call.struct), C.byref(shard), tables, _stream()),
+        _lib.check(_lib.lib().ctr_emb_pool_fwd_sharded(C.byref(call.struct), C.byref(shard), tables, _stream(call)),
                    "ctr_emb_pool_fwd_sharded")
 
 
+@_guarded
 def route_p2p_workspace_bytes(call: GroupCall) -> int:
     return _lib.check(_lib.lib().ctr_route_p2p_workspace_bytes(C.byref(call.struct)), "ctr_route_p2p_workspace_bytes")
 
 
+@_guarded
 def route_p2p_build(call: GroupCall, shard: _lib.Shard, counts_ptr: int, keys_ptr: int, slots_ptr: int,
                     workspace: torch.Tensor) -> None:
     with _timed("route_p2p_build"):
         _lib.check(_lib.lib().ctr_route_p2p_build(C.byref(call.struct), C.byref(shard), counts_ptr, keys_ptr, slots_ptr,
-                                                  workspace.data_ptr(), workspace.numel(), _stream()), "ctr_route_p2p_build")
+                                                  workspace.data_ptr(), workspace.numel(), _stream(call)), "ctr_route_p2p_build")
 
 
+@_guarded
 def emb_bwd_p2p_workspace_bytes(call: GroupCall, world: int) -> int:
     return _lib.check(_lib.lib().ctr_emb_bwd_p2p_workspace_bytes(C.byref(call.struct), world), "ctr_emb_bwd_p2p_workspace_bytes")
 
 
+@_guarded
 def emb_bwd_plan_p2p(call: GroupCall, shard: _lib.Shard, counts, keys, slots, workspace: torch.Tensor) -> None:
     with _timed("emb_bwd_plan"):
         _lib.check(_lib.lib().ctr_emb_bwd_plan_p2p(C.byref(call.struct), C.byref(shard), counts, keys, slots,
-                                                   workspace.data_ptr(), workspace.numel(), _stream()), "ctr_emb_bwd_plan_p2p")
+                                                   workspace.data_ptr(), workspace.numel(), _stream(call)), "ctr_emb_bwd_plan_p2p")
 
 
+@_guarded
 def emb_bwd_apply_p2p(call: GroupCall, shard: _lib.Shard, workspace: torch.Tensor, opt: _lib.Opt, grads,
                       num_unique: torch.Tensor | None = None) -> None:
     _chk(num_unique, "num_unique", torch.int64)
     with _timed("emb_bwd_apply" + _width_tag(call)):
         _lib.check(_lib.lib().ctr_emb_bwd_apply_p2p(C.byref(call.struct), C.byref(shard), workspace.data_ptr(), C.byref(opt),
-                                                    grads, _lib.ptr(num_unique), _stream()), "ctr_emb_bwd_apply_p2p")
+                                                    grads, _lib.ptr(num_unique), _stream(call)), "ctr_emb_bwd_apply_p2p")
 
 
 # ---- tower block (BatchNorm1d + ReLU + Dropout around a Linear) ------------------------------------------------------
@@ -491,6 +553,7 @@ def _rows2d(t, name):
         raise ValueError(f"{name} must be f32 [B, N] with unit inner stride")
 
 
+@_guarded
 def bn_stats(z, eps: float, momentum: float, running_mean=None, running_var=None, num_batches_tracked=None):
     """Batch statistics of z [B, N] -> (mean [N], rstd [N]); updates the running statistics in place."""
     _rows2d(z, "z")
@@ -504,6 +567,7 @@ def bn_stats(z, eps: float, momentum: float, running_mean=None, running_var=None
     return mean, rstd
 
 
+@_guarded
 def bn_relu_dropout_fwd(z, mean, rstd, gamma, beta, p_drop: float, seed_dev, seed_offset: int):
     _rows2d(z, "z")
     B, N = z.shape
@@ -515,6 +579,7 @@ def bn_relu_dropout_fwd(z, mean, rstd, gamma, beta, p_drop: float, seed_dev, see
     return y
 
 
+@_guarded
 def bn_relu_dropout_bwd(gy, z, mean, rstd, gamma, beta, p_drop: float, seed_dev, seed_offset: int, want_dbias: bool = True):
     """-> (gz [B, N], dgamma [N], dbeta [N], dbias [N] or None)"""
     _rows2d(gy, "gy")
@@ -537,6 +602,7 @@ def bn_relu_dropout_bwd(gy, z, mean, rstd, gamma, beta, p_drop: float, seed_dev,
 _wgrad_ws: dict = {}
 
 
+@_guarded
 def linear_wgrad(gz: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     """``gz.T @ x`` -> [N, K]: the weight gradient of ``y = x W^T`` on tcgen05 (TF32 in, fp32 accumulate, split over
     the batch).  gz f32 [B, N], x f32 [B, K], unit inner stride, row pitches multiples of 4 floats."""
@@ -559,6 +625,7 @@ def linear_wgrad(gz: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
 
 
 # ---- logit head + dense optimizer ----------------------------------------------------------------------------------
+@_guarded
 def logit_bce_fwd(h, w, bias, extra, labels, want_logits: bool = False):
     """h [B, H], w [H], bias [1] | None, extra [B, *] | None (column 0), labels [B, *] (column 0)
     -> (loss [] mean BCE-with-logits, dz [B], logits [B] | None)"""
@@ -576,6 +643,7 @@ def logit_bce_fwd(h, w, bias, extra, labels, want_logits: bool = False):
     return loss, dz, logits
 
 
+@_guarded
 def logit_bce_bwd(h, w, dz, gscale, want_gh: bool, want_gextra: bool):
     """-> (gh [B, H] | None, gw [H], gb [1], gextra [B, 1] | None) for the upstream scalar gradient ``gscale`` (device)."""
     B, H = h.shape
@@ -592,6 +660,7 @@ def logit_bce_bwd(h, w, dz, gscale, want_gh: bool, want_gextra: bool):
     return gh, gw, gb, gextra
 
 
+@_guarded
 def dense_adagrad(params, grads, sums, lr: float, eps: float) -> None:
     """One launch of torch.optim.Adagrad's update (lr_decay = weight_decay = 0) over up to 48 dense fp32 tensors."""
     n = len(params)
@@ -606,30 +675,34 @@ def dense_adagrad(params, grads, sums, lr: float, eps: float) -> None:
 
 
 # ---- de-duplicated exchange -------------------------------------------------------------------------------------------
+@_guarded
 def unique_fetch(call: GroupCall, shard: _lib.Shard, tables, plan_ws: torch.Tensor, staging: torch.Tensor,
                  uidx: torch.Tensor | None) -> None:
     _chk(staging, "staging", torch.float32)
     _chk(uidx, "uidx", torch.int64)
     with _timed("unique_fetch" + _width_tag(call)):
         _lib.check(_lib.lib().ctr_unique_fetch(C.byref(call.struct), C.byref(shard), tables, plan_ws.data_ptr(), staging.data_ptr(),
-                                               _lib.ptr(uidx), _stream()), "ctr_unique_fetch")
+                                               _lib.ptr(uidx), _stream(call)), "ctr_unique_fetch")
 
 
+@_guarded
 def emb_bwd_p2p_unique_workspace_bytes(call: GroupCall, capacity: int) -> int:
     return _lib.check(_lib.lib().ctr_emb_bwd_p2p_unique_workspace_bytes(C.byref(call.struct), capacity),
                       "ctr_emb_bwd_p2p_unique_workspace_bytes")
 
 
+@_guarded
 def emb_bwd_plan_p2p_unique(call: GroupCall, shard: _lib.Shard, peer_nu, peer_uf, peer_ur, capacity: int,
                             workspace: torch.Tensor) -> None:
     with _timed("emb_bwd_plan_owner"):
         _lib.check(_lib.lib().ctr_emb_bwd_plan_p2p_unique(C.byref(call.struct), C.byref(shard), peer_nu, peer_uf, peer_ur, capacity,
-                                                          workspace.data_ptr(), workspace.numel(), _stream()),
+                                                          workspace.data_ptr(), workspace.numel(), _stream(call)),
                    "ctr_emb_bwd_plan_p2p_unique")
 
 
+@_guarded
 def emb_bwd_apply_p2p_unique(call: GroupCall, shard: _lib.Shard, workspace: torch.Tensor, opt: _lib.Opt, peer_row_grads,
                              capacity: int) -> None:
     with _timed("emb_bwd_apply_owner" + _width_tag(call)):
         _lib.check(_lib.lib().ctr_emb_bwd_apply_p2p_unique(C.byref(call.struct), C.byref(shard), workspace.data_ptr(), C.byref(opt),
-                                                           peer_row_grads, capacity, None, _stream()), "ctr_emb_bwd_apply_p2p_unique")
+                                                           peer_row_grads, capacity, None, _stream(call)), "ctr_emb_bwd_apply_p2p_unique")
