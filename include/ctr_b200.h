@@ -154,6 +154,11 @@ int ctr_emb_pool_fwd(const ctr_group_t *group, void *stream);
 int ctr_hash_bucket_i64(const int64_t *ids, int64_t n, uint32_t buckets, uint32_t seed, int32_t *out,
                         void *stream);
 
+/* the same for string categories: string i = data[offsets[i], offsets[i + 1]) (utf-8 bytes of the canonical form of
+ * torchctr/transformer.py:367-401), offsets i64 [n + 1]; out i32 [n] = murmur3_32(bytes, seed) % buckets */
+int ctr_hash_bucket_bytes(const uint8_t *data, const int64_t *offsets, int64_t n, uint32_t buckets, uint32_t seed,
+                          int32_t *out, void *stream);
+
 /* plain row gather out[i, :] = table[ids[i], :] (ids >= 0), used by DynamicEmbedding */
 int ctr_rows_gather(const int64_t *ids, int64_t n, const float *table, int64_t num_rows, int32_t D,
                     float *out, uint32_t *status, void *stream);
@@ -215,6 +220,18 @@ int ctr_fm_fwd(const float *x, int64_t x_stride, int32_t B, int32_t F, int32_t D
 int ctr_fm_bwd(const float *x, int64_t x_stride, int32_t B, int32_t F, int32_t D, const float *gout,
                int64_t gout_stride, float *gx, int64_t gx_stride, int32_t accumulate, float *gfirst,
                int32_t nfirst, int64_t gfirst_stride, void *stream);
+
+/* Target-attention pooling over a candidate sequence, torchctr/nn/functional.py:46-74 (target_attention):
+ * out[b] = sum_n softmax_n(cand[b, n] . target[b]) cand[b, n];  target f32 [B, E], cand f32 [B, N, E] (contiguous), mask f32
+ * [B, N] or NULL, E a power of two in [4, 128].  honor_mask = 0 reproduces the reference, whose masked_fill is not in
+ * place (functional.py:63) so the mask has no effect; honor_mask = 1 gives masked candidates weight 0 (the intended
+ * semantics; a row with every candidate masked yields zeros).  scores [B, N], row_max [B], row_sum [B] are kept for bwd.
+ * bwd: gtarget [B, E], gcand [B, N, E] from gout [B, E]. */
+int ctr_target_attention_fwd(const float *target, const float *cand, const float *mask, int32_t B, int32_t N, int32_t E,
+                             int32_t honor_mask, float *out, float *scores, float *row_max, float *row_sum, void *stream);
+int ctr_target_attention_bwd(const float *target, const float *cand, const float *mask, int32_t B, int32_t N, int32_t E,
+                             int32_t honor_mask, const float *out, const float *scores, const float *row_max,
+                             const float *row_sum, const float *gout, float *gtarget, float *gcand, void *stream);
 
 /* DCN-v2 cross epilogue: y = x0 * (u + bias) + x   (u = x W^T from the GEMM), all [B, d] */
 int ctr_cross_combine_fwd(const float *x0, const float *x, const float *u, const float *bias, int32_t B,

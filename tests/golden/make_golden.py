@@ -250,13 +250,42 @@ def golden_collate(torchctr):
     print("collate_golden.pt", [len(r["batches"]) for r in out["runs"]])
 
 
+def golden_attention(torchctr):
+    """torchctr.nn.functional.target_attention (nn/functional.py:46-74) incl. its gradients, with and without a mask: the
+    reference's ``masked_fill`` is not in place (:63), so the mask has NO effect -- the fixture records exactly that."""
+    from torchctr.nn.functional import target_attention
+    gen = torch.Generator().manual_seed(11)
+    cases = []
+    for B, N, E in ((7, 5, 16), (16, 50, 16), (2, 200, 64), (9, 3, 4), (5, 17, 32)):
+        tgt = torch.randn(B, E, generator=gen).requires_grad_(True)
+        cand = torch.randn(B, N, E, generator=gen).requires_grad_(True)
+        lens = torch.randint(0, N + 1, (B, 1), generator=gen)
+        mask = (torch.arange(N)[None, :] < lens).float()
+        gout = torch.randn(B, E, generator=gen)
+        outs = {}
+        for name, m in (("nomask", None), ("mask", mask)):
+            tgt.grad = cand.grad = None
+            out = target_attention(tgt, cand, m)
+            out.backward(gout)
+            outs[name] = {"out": out.detach().clone(), "gtarget": tgt.grad.clone(), "gcand": cand.grad.clone()}
+        same = all(torch.equal(outs["mask"][k], outs["nomask"][k]) for k in outs["mask"])      # the reference ignores its mask
+        cases.append({"target": tgt.detach().clone(), "cand": cand.detach().clone(), "mask": mask, "gout": gout,
+                      "mask_ignored_by_reference": same, **outs["nomask"]})
+    torch.save(cases, os.path.join(HERE, "attention_golden.pt"))
+    print("attention_golden.pt", len(cases))
+
+
 if __name__ == "__main__":
     ref = import_reference()
     if "--only-collate" in sys.argv:
         golden_collate(ref)
+        sys.exit(0)
+    if "--only-attention" in sys.argv:
+        golden_attention(ref)
         sys.exit(0)
     golden_hash(ref)
     golden_dnn(ref)
     golden_dynamic(ref)
     golden_optim()
     golden_collate(ref)
+    golden_attention(ref)

@@ -81,6 +81,7 @@ _SIGNATURES = {
     "ctr_opt_hyper": (None, [C.POINTER(Opt), C.POINTER(Hyper)]),
     "ctr_emb_pool_fwd": (C.c_int, [C.POINTER(Group), _P]),
     "ctr_hash_bucket_i64": (C.c_int, [_P, C.c_int64, C.c_uint32, C.c_uint32, _P, _P]),
+    "ctr_hash_bucket_bytes": (C.c_int, [_P, _P, C.c_int64, C.c_uint32, C.c_uint32, _P, _P]),
     "ctr_rows_gather": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P, _P]),
     "ctr_normal_fill_rows": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_uint64, _P]),
     "ctr_ids_minmax": (C.c_int, [_P, C.c_int64, _P, _P]),
@@ -97,6 +98,8 @@ _SIGNATURES = {
                              C.c_int64, C.c_int32, _P]),
     "ctr_fm_bwd": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P, C.c_int64,
                              C.c_int32, _P, C.c_int32, C.c_int64, _P]),
+    "ctr_target_attention_fwd": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
+    "ctr_target_attention_bwd": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ctr_cross_combine_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P]),
     "ctr_cross_combine_bwd": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, C.c_int32, _P]),
     "ctr_linear_fwd": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32,

@@ -278,6 +278,30 @@ __global__ void hash_bucket_kernel(const int64_t *__restrict__ ids, int64_t n, u
         out[i] = (int32_t)(murmur3_decimal(ids[i], seed) % buckets);
 }
 
+// MurmurHash3_x86_32 over arbitrary byte strings (string categories: after torchctr/transformer.py:367-401 a category that
+// is not an int32 number keeps its own characters, e.g. Amazon's "B001NPEBGU"): string i = data[offsets[i], offsets[i + 1]).
+__global__ void hash_bucket_bytes_kernel(const uint8_t *__restrict__ data, const int64_t *__restrict__ offsets, int64_t n,
+                                         uint32_t buckets, uint32_t seed, int32_t *__restrict__ out) {
+    const uint32_t c1 = 0xcc9e2d51u, c2 = 0x1b873593u;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint8_t *p = data + offsets[i];
+        const int64_t len = offsets[i + 1] - offsets[i];
+        uint32_t h = seed;
+        int64_t j = 0;
+        for (; j + 4 <= len; j += 4) {
+            uint32_t k = (uint32_t)p[j] | ((uint32_t)p[j + 1] << 8) | ((uint32_t)p[j + 2] << 16) | ((uint32_t)p[j + 3] << 24);
+            k *= c1; k = rotl32(k, 15); k *= c2;
+            h ^= k; h = rotl32(h, 13); h = h * 5u + 0xe6546b64u;
+        }
+        uint32_t k = 0;
+        for (int t = 0; j + t < len; ++t) k |= (uint32_t)p[j + t] << (8 * t);
+        if (j < len) { k *= c1; k = rotl32(k, 15); k *= c2; h ^= k; }
+        h ^= (uint32_t)len;
+        h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+        out[i] = (int32_t)(h % buckets);
+    }
+}
+
 __global__ void rows_gather_kernel(const int64_t *__restrict__ ids, int64_t n, const float *__restrict__ table,
                                    int64_t num_rows, int D, float *__restrict__ out, uint32_t *status) {
     // one thread per (row, 4-float piece) when D % 4 == 0, else per element
@@ -439,6 +463,16 @@ extern "C" int ctr_hash_bucket_i64(const int64_t *ids, int64_t n, uint32_t bucke
     if (n == 0) return CTR_OK;
     CTR_REQUIRE(ids != nullptr && out != nullptr, "null pointer");
     note_launch(), hash_bucket_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(ids, n, buckets, seed, out);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int ctr_hash_bucket_bytes(const uint8_t *data, const int64_t *offsets, int64_t n, uint32_t buckets, uint32_t seed,
+                                     int32_t *out, void *stream) {
+    CTR_REQUIRE(n >= 0 && buckets > 0, "n=%lld buckets=%u", (long long)n, buckets);
+    if (n == 0) return CTR_OK;
+    CTR_REQUIRE(offsets != nullptr && out != nullptr, "null pointer");
+    note_launch(), hash_bucket_bytes_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(data, offsets, n, buckets, seed, out);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }

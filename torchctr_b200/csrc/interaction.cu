@@ -237,6 +237,123 @@ static int ew_grid(int64_t total) {
     return blocks < 1 ? 1 : (int)blocks;
 }
 
+
+// ---- target attention pooling (torchctr/nn/functional.py:46-74) --------------------------------------------------------
+// out[b, :] = sum_n softmax_n(cand[b, n, :] . target[b, :]) cand[b, n, :].  The reference materialises scores, weights and a
+// second [B, N, E] tensor; here a warp owns a row b, G = E / 4 lanes hold one candidate (float4 each, R = 32 / G candidates per
+// trip), the softmax is computed online (running max / sum per candidate slot, slots merged with xor shuffles at the end),
+// so cand is read once forward and once backward.  The scores and the row's (max, sum) are kept for the backward pass.
+// honor_mask = 0 reproduces the reference exactly: its masked_fill is not in place (functional.py:63), so the mask has no
+// effect; honor_mask = 1 is the intended semantics (masked candidates get weight 0; a row with no candidate gives 0).
+struct AttnArgs {
+    const float *target;   // [B, E]
+    const float *cand;     // [B, N, E]
+    const float *mask;     // [B, N] or null (0 = masked)
+    float *scores;         // [B, N]
+    float *row_max;        // [B]
+    float *row_sum;        // [B]
+    int B, N, E, G, honor_mask;
+};
+
+__device__ __forceinline__ float dot4(const float4 a, const float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+
+__global__ void __launch_bounds__(256) attn_pool_fwd_kernel(const AttnArgs a, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int G = a.G, R = 32 / G;
+    const int t = lane % G, r = lane / G;
+    for (int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < a.B; b += gridDim.x * (blockDim.x >> 5)) {
+        const float4 tg = __ldg(reinterpret_cast<const float4 *>(a.target + (size_t)b * a.E) + t);
+        float m = -INFINITY, l = 0.f;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int n0 = 0; n0 < a.N; n0 += R) {
+            const int n = n0 + r;
+            const bool in = n < a.N;
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in) c = __ldg(reinterpret_cast<const float4 *>(a.cand + ((size_t)b * a.N + n) * a.E) + t);
+            float s = dot4(c, tg);
+            for (int off = 1; off < G; off <<= 1) s += __shfl_xor_sync(kFull, s, off);
+            bool valid = in;
+            if (in && a.honor_mask && a.mask != nullptr) valid = __ldg(a.mask + (size_t)b * a.N + n) != 0.f;
+            if (in && t == 0) a.scores[(size_t)b * a.N + n] = s;
+            if (valid) {
+                const float mn = fmaxf(m, s);
+                const float sc = m == -INFINITY ? 0.f : __expf(m - mn);
+                const float p = __expf(s - mn);
+                l = l * sc + p;
+                acc.x = acc.x * sc + p * c.x; acc.y = acc.y * sc + p * c.y; acc.z = acc.z * sc + p * c.z; acc.w = acc.w * sc + p * c.w;
+                m = mn;
+            }
+        }
+        for (int off = G; off < 32; off <<= 1) {       // merge the candidate slots
+            const float m2 = __shfl_xor_sync(kFull, m, off), l2 = __shfl_xor_sync(kFull, l, off);
+            float4 a2;
+            a2.x = __shfl_xor_sync(kFull, acc.x, off); a2.y = __shfl_xor_sync(kFull, acc.y, off);
+            a2.z = __shfl_xor_sync(kFull, acc.z, off); a2.w = __shfl_xor_sync(kFull, acc.w, off);
+            const float mn = fmaxf(m, m2);
+            const float s1 = m == -INFINITY ? 0.f : __expf(m - mn), s2 = m2 == -INFINITY ? 0.f : __expf(m2 - mn);
+            l = l * s1 + l2 * s2;
+            acc.x = acc.x * s1 + a2.x * s2; acc.y = acc.y * s1 + a2.y * s2; acc.z = acc.z * s1 + a2.z * s2; acc.w = acc.w * s1 + a2.w * s2;
+            m = mn;
+        }
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        if (r == 0) reinterpret_cast<float4 *>(out + (size_t)b * a.E)[t] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+        if (lane == 0) {
+            a.row_max[b] = m;
+            a.row_sum[b] = l;
+        }
+    }
+}
+
+// d cand_n = w_n gout + ds_n target, d target = sum_n ds_n cand_n, ds_n = w_n (gout . cand_n - gout . out), w_n = exp(s_n - max) / sum
+__global__ void __launch_bounds__(256)
+    attn_pool_bwd_kernel(const AttnArgs a, const float *__restrict__ out, const float *__restrict__ gout, float *__restrict__ gtarget,
+                         float *__restrict__ gcand) {
+    const int lane = threadIdx.x & 31;
+    const int G = a.G, R = 32 / G;
+    const int t = lane % G, r = lane / G;
+    for (int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < a.B; b += gridDim.x * (blockDim.x >> 5)) {
+        const float4 tg = __ldg(reinterpret_cast<const float4 *>(a.target + (size_t)b * a.E) + t);
+        const float4 go = __ldg(reinterpret_cast<const float4 *>(gout + (size_t)b * a.E) + t);
+        const float4 o = __ldg(reinterpret_cast<const float4 *>(out + (size_t)b * a.E) + t);
+        float gdo = dot4(go, o);
+        for (int off = 1; off < G; off <<= 1) gdo += __shfl_xor_sync(kFull, gdo, off);
+        const float m = a.row_max[b], l = a.row_sum[b];
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        float4 gt = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int n0 = 0; n0 < a.N; n0 += R) {
+            const int n = n0 + r;
+            const bool in = n < a.N;
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in) c = __ldg(reinterpret_cast<const float4 *>(a.cand + ((size_t)b * a.N + n) * a.E) + t);
+            float gc = dot4(go, c);
+            for (int off = 1; off < G; off <<= 1) gc += __shfl_xor_sync(kFull, gc, off);
+            bool valid = in;
+            if (in && a.honor_mask && a.mask != nullptr) valid = __ldg(a.mask + (size_t)b * a.N + n) != 0.f;
+            const float w = valid ? __expf(__ldg(a.scores + (size_t)b * a.N + n) - m) * inv : 0.f;
+            const float ds = w * (gc - gdo);
+            if (in)
+                reinterpret_cast<float4 *>(gcand + ((size_t)b * a.N + n) * a.E)[t] =
+                    make_float4(w * go.x + ds * tg.x, w * go.y + ds * tg.y, w * go.z + ds * tg.z, w * go.w + ds * tg.w);
+            gt.x += ds * c.x; gt.y += ds * c.y; gt.z += ds * c.z; gt.w += ds * c.w;
+        }
+        for (int off = G; off < 32; off <<= 1) {
+            gt.x += __shfl_xor_sync(kFull, gt.x, off); gt.y += __shfl_xor_sync(kFull, gt.y, off);
+            gt.z += __shfl_xor_sync(kFull, gt.z, off); gt.w += __shfl_xor_sync(kFull, gt.w, off);
+        }
+        if (r == 0) reinterpret_cast<float4 *>(gtarget + (size_t)b * a.E)[t] = gt;
+    }
+}
+
+static int attn_args(AttnArgs *a, const float *target, const float *cand, const float *mask, float *scores, float *row_max,
+                     float *row_sum, int B, int N, int E, int honor_mask) {
+    CTR_REQUIRE(B >= 0 && N >= 0, "bad shape B=%d N=%d", B, N);
+    CTR_REQUIRE(E >= 4 && E <= 128 && (E & (E - 1)) == 0, "E=%d unsupported (a power of two in [4, 128])", E);
+    CTR_REQUIRE(target && (cand || N == 0 || B == 0) && scores && row_max && row_sum, "null pointer");
+    CTR_REQUIRE(((reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(cand)) & 15u) == 0, "target / cand must be 16-byte aligned");
+    *a = AttnArgs{target, cand, mask, scores, row_max, row_sum, B, N, E, E / 4, honor_mask ? 1 : 0};
+    return CTR_OK;
+}
+
 }  // namespace ctr
 
 using namespace ctr;
@@ -313,6 +430,39 @@ extern "C" int ctr_cross_combine_bwd(const float *x0, const float *u, const floa
     CTR_REQUIRE(x0 && u && bias && gy && gu && gx0, "null pointer");
     note_launch(), cross_combine_bwd_kernel<<<ew_grid((int64_t)B * d), 256, 0, (cudaStream_t)stream>>>(x0, u, bias, gy, B, d, stride, gu,
                                                                                      gx0, accumulate_gx0);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+
+extern "C" int ctr_target_attention_fwd(const float *target, const float *cand, const float *mask, int32_t B, int32_t N, int32_t E,
+                                        int32_t honor_mask, float *out, float *scores, float *row_max, float *row_sum, void *stream) {
+    AttnArgs a;
+    int rc = attn_args(&a, target, cand, mask, scores, row_max, row_sum, B, N, E, honor_mask);
+    if (rc != CTR_OK) return rc;
+    CTR_REQUIRE(out != nullptr && (reinterpret_cast<uintptr_t>(out) & 15u) == 0, "out is null or not 16-byte aligned");
+    if (B == 0) return CTR_OK;
+    int blocks = (B + 7) / 8;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    note_launch(), attn_pool_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, out);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int ctr_target_attention_bwd(const float *target, const float *cand, const float *mask, int32_t B, int32_t N, int32_t E,
+                                        int32_t honor_mask, const float *out, const float *scores, const float *row_max,
+                                        const float *row_sum, const float *gout, float *gtarget, float *gcand, void *stream) {
+    AttnArgs a;
+    int rc = attn_args(&a, target, cand, mask, const_cast<float *>(scores), const_cast<float *>(row_max), const_cast<float *>(row_sum), B,
+                       N, E, honor_mask);
+    if (rc != CTR_OK) return rc;
+    CTR_REQUIRE(out && gout && gtarget && (gcand || N == 0), "null pointer");
+    CTR_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(gtarget) |
+                  reinterpret_cast<uintptr_t>(gcand)) & 15u) == 0, "operands must be 16-byte aligned");
+    if (B == 0) return CTR_OK;
+    int blocks = (B + 7) / 8;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    note_launch(), attn_pool_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, out, gout, gtarget, gcand);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }

@@ -298,6 +298,22 @@ def hash_bucket(ids: torch.Tensor, buckets: int, seed: int = 0) -> torch.Tensor:
 
 
 @_guarded
+def hash_bucket_bytes(data: torch.Tensor, offsets: torch.Tensor, buckets: int, seed: int = 0) -> torch.Tensor:
+    """``hash_bucket`` of n byte strings packed back to back: data u8 [total], offsets i64 [n + 1] -> int32 [n]."""
+    _chk(data, "data", torch.uint8)
+    _chk(offsets, "offsets", torch.int64)
+    if not 0 <= seed <= 0xFFFFFFFF:
+        raise OverflowError("seed must fit uint32")
+    if not 0 < buckets < 2 ** 31:
+        raise ValueError("buckets must be in [1, 2^31)")
+    n = offsets.numel() - 1
+    out = torch.empty(max(n, 0), dtype=torch.int32, device=offsets.device)
+    _lib.check(_lib.lib().ctr_hash_bucket_bytes(data.data_ptr(), offsets.data_ptr(), n, buckets, seed, out.data_ptr(), _stream(offsets)),
+               "ctr_hash_bucket_bytes")
+    return out
+
+
+@_guarded
 def rows_gather(ids: torch.Tensor, table: torch.Tensor, status: torch.Tensor | None = None) -> torch.Tensor:
     _chk(ids, "ids", torch.int64)
     _chk(table, "table", torch.float32)
@@ -390,6 +406,38 @@ def fm_bwd(x: torch.Tensor, F: int, D: int, gout: torch.Tensor, gx: torch.Tensor
         _lib.check(_lib.lib().ctr_fm_bwd(x.data_ptr(), x.stride(0), B, F, D, gout.data_ptr(), gout.stride(0), gx.data_ptr(),
                                          gx.stride(0), int(accumulate), _lib.ptr(gfirst), nfirst,
                                          0 if gfirst is None else gfirst.stride(0), _stream(x)), "ctr_fm_bwd")
+
+
+@_guarded
+def target_attention_fwd(target, cand, mask, honor_mask: bool):
+    """-> (out [B, E], scores [B, N], row_max [B], row_sum [B]); see ``ctr_target_attention_fwd``."""
+    _chk(target, "target", torch.float32)
+    _chk(cand, "cand", torch.float32)
+    _chk(mask, "mask", torch.float32)
+    B, N, E = cand.shape
+    dev = cand.device
+    out = torch.empty(B, E, dtype=torch.float32, device=dev)
+    scores = torch.empty(B, N, dtype=torch.float32, device=dev)
+    row_max = torch.empty(B, dtype=torch.float32, device=dev)
+    row_sum = torch.empty(B, dtype=torch.float32, device=dev)
+    with _timed("target_attention_fwd"):
+        _lib.check(_lib.lib().ctr_target_attention_fwd(target.data_ptr(), cand.data_ptr(), _lib.ptr(mask), B, N, E, int(honor_mask),
+                                                       out.data_ptr(), scores.data_ptr(), row_max.data_ptr(), row_sum.data_ptr(),
+                                                       _stream(cand)), "ctr_target_attention_fwd")
+    return out, scores, row_max, row_sum
+
+
+@_guarded
+def target_attention_bwd(target, cand, mask, honor_mask: bool, out, scores, row_max, row_sum, gout):
+    B, N, E = cand.shape
+    gtarget = torch.empty_like(target)
+    gcand = torch.empty_like(cand)
+    with _timed("target_attention_bwd"):
+        _lib.check(_lib.lib().ctr_target_attention_bwd(target.data_ptr(), cand.data_ptr(), _lib.ptr(mask), B, N, E, int(honor_mask),
+                                                       out.data_ptr(), scores.data_ptr(), row_max.data_ptr(), row_sum.data_ptr(),
+                                                       gout.data_ptr(), gtarget.data_ptr(), gcand.data_ptr(), _stream(cand)),
+                   "ctr_target_attention_bwd")
+    return gtarget, gcand
 
 
 @_guarded
