@@ -45,6 +45,11 @@ CONFIGS = {
     "cfg3": dict(model="dcnv2", vocabs=CRITEO_VOCABS, dim=32, num_dense=13, seq=None, batch=65536,
                  workload="BASELINE configs[2]: DCN-v2 (stacked), 3 cross layers d = 26 x 32 + 13 = 845, same Criteo-shape ids "
                           "({rows} rows total), emb dim 32, tower 256-128-64, Adagrad"),
+    # configs[3]: hash-embedding tables totalling 2^30 rows x dim 64, row-sharded; raw ids hashed (murmur3) inside the kernels
+    "cfg4": dict(model="dnn", vocabs=[1 << 26] * 16, dim=64, num_dense=13, seq=None, batch=65536, hashed=True,
+                 workload="BASELINE configs[3]: DNN over 16 hashed tables totalling {rows} rows x dim 64 (raw 31-bit Zipf(1.05) ids, "
+                          "murmur3 bucketing inside the lookup / update kernels), tables created shard by shard (never replicated), "
+                          "tower 256-128-64, Adagrad"),
     # configs[0]: the reference's own CPU-runnable case, DNN under the unmodified reference Trainer
     "cfg1": dict(model="dnn", vocabs=AMAZON_VOCABS, dim=16, num_dense=4, seq=dict(vocab=500_000, maxlen=50), batch=4096,
                  workload="BASELINE configs[0]: DNN, Amazon-review-shaped: 8 categorical ({rows} rows total) + 1 item sequence "
@@ -52,18 +57,23 @@ CONFIGS = {
 }
 
 
-def get_cfg(name):
+def get_cfg(name, rows_log2=None):
     cfg = dict(CONFIGS[name])
     cfg["name"] = name
+    if rows_log2 and cfg.get("hashed"):
+        cfg["vocabs"] = [(1 << rows_log2) // len(cfg["vocabs"])] * len(cfg["vocabs"])
     cfg["rows"] = sum(cfg["vocabs"]) + (cfg["seq"]["vocab"] if cfg["seq"] else 0)
     cfg["workload"] = cfg["workload"].format(rows=cfg["rows"])
-    cfg["metric"] = {"deepfm": "train samples/s, Criteo-shape DeepFM", "dcnv2": "train samples/s, Criteo-shape DCN-v2",
-                     "dnn": "train samples/s, Amazon-shape DNN"}[cfg["model"]]
+    cfg["metric"] = {"cfg2": "train samples/s, Criteo-shape DeepFM", "cfg3": "train samples/s, Criteo-shape DCN-v2",
+                     "cfg1": "train samples/s, Amazon-shape DNN", "cfg4": "train samples/s, DNN over row-sharded hashed tables"}[name]
     return cfg
 
 
 def feat_configs(cfg):
     fc = [{"name": f"C{i + 1}", "type": "sparse", "num_embeddings": v, "emb_dim": cfg["dim"]} for i, v in enumerate(cfg["vocabs"])]
+    if cfg.get("hashed") and not cfg.get("_oracle_rows"):
+        for i, c in enumerate(fc):                      # raw ids in the batch; row = murmur3_32(str(id), seed) % hash_buckets
+            c.update(raw_ids=True, hash_buckets=c["num_embeddings"], seed=i)
     if cfg["seq"]:
         fc.append({"name": "hist", "type": "sparse", "num_embeddings": cfg["seq"]["vocab"], "emb_dim": cfg["dim"], "islist": True})
     fc += [{"name": f"I{i + 1}", "type": "dense"} for i in range(cfg["num_dense"])]
@@ -82,7 +92,14 @@ def make_batch(cfg, seed, B, pin=False):
     gen = torch.Generator().manual_seed(seed)
     feats = {}
     for i, V in enumerate(cfg["vocabs"]):
-        feats[f"C{i + 1}"] = zipf_ids(gen, B, V).reshape(B, 1)
+        if cfg.get("hashed"):
+            raw = zipf_ids(gen, B, 1 << 31)             # raw category ids; the kernels hash them
+            if cfg.get("_oracle_rows"):                 # the CPU reference indexes with the buckets (transformer.py:487-490)
+                from oracle import hashing as oh
+                raw = torch.from_numpy(oh.hash_bucket_ids(raw.numpy(), V, i)).long()
+            feats[f"C{i + 1}"] = raw.reshape(B, 1)
+        else:
+            feats[f"C{i + 1}"] = zipf_ids(gen, B, V).reshape(B, 1)
     if cfg["seq"]:
         L = cfg["seq"]["maxlen"]
         ids = zipf_ids(gen, B * L, cfg["seq"]["vocab"]).reshape(B, L)
@@ -97,8 +114,11 @@ def make_batch(cfg, seed, B, pin=False):
     return feats, labels
 
 
-def build_model(cfg, oracle=False):
+def build_model(cfg, oracle=False, table_device=None):
     fc = feat_configs(cfg)
+    if table_device is not None:
+        from torchctr_b200 import models as m
+        return {"deepfm": m.DeepFM, "dcnv2": m.DCNv2, "dnn": m.DNN}[cfg["model"]](fc, HIDDEN, table_device=table_device)
     if oracle:
         from oracle import models as om
         return {"deepfm": om.OracleDeepFM, "dcnv2": om.OracleDCNv2, "dnn": om.OracleDNN}[cfg["model"]](fc, HIDDEN)
@@ -186,6 +206,11 @@ def cpu_reference_run(cfg, steps, warmup, B, budget_s):
     kind = "port"
     torch.manual_seed(0)
     model = None
+    if cfg.get("hashed"):
+        # a dense [V, D] table + gradient + Adagrad state of 2^30 x 64 does not exist on any host: the CPU leg runs the same
+        # arithmetic on tables bounded to 2^24 rows in total (the bucketing is done on the host, as the reference does)
+        cfg = dict(cfg, vocabs=[(1 << 24) // len(cfg["vocabs"])] * len(cfg["vocabs"]), _oracle_rows=True)
+        cfg["rows"] = sum(cfg["vocabs"])
     if cfg["model"] == "dnn":
         try:
             from baseline import refshim
@@ -210,20 +235,21 @@ def cpu_reference_run(cfg, steps, warmup, B, budget_s):
 
     k, warm_done, dt, first = _timed_cpu_steps(step, steps, warmup, budget_s)
     return {"value": B * k / dt, "steps": k, "warmup": warm_done, "ms_per_step": 1e3 * dt / k, "cores": threads,
-            "first_step_s": first, "B": B, "kind": kind}
+            "first_step_s": first, "B": B, "kind": kind, "rows": cfg["rows"]}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = get_cfg(args.config)
+    cfg = get_cfg(args.config, args.rows_log2)
     B = args.batch or cfg["batch"]
     r = cpu_reference_run(cfg, args.steps, args.warmup, B, budget_s=150.0)
     what = ("the unmodified torchctr.models.DNN (baseline/_ref) under the loop body of torchctr.trainer.Trainer.fit"
             if r["kind"] == "reference" else "oracle port of the reference arithmetic (absent upstream): nn.Embedding + dense autograd")
-    sample = (f"{r['steps']} steps (after {r['warmup']} warm-up) of B={B} samples each, full-size tables "
-              f"({cfg['rows']} rows x {cfg['dim']}), {what}, dense torch.optim.Adagrad, eager fp32 on CPU")
+    sample = (f"{r['steps']} steps (after {r['warmup']} warm-up) of B={B} samples each, "
+              + ("full-size tables" if r["rows"] == cfg["rows"] else "tables bounded to") +
+              f" ({r['rows']} rows x {cfg['dim']}), {what}, dense torch.optim.Adagrad, eager fp32 on CPU")
     line = {
         "impl": "reference", "metric": cfg["metric"], "value": r["value"], "unit": "samples/s",
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
@@ -415,8 +441,11 @@ def run_ours(args):
     import torch.distributed as dist
     from torchctr_b200 import ops
 
-    cfg = get_cfg(args.config)
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    rows_log2 = args.rows_log2
+    if args.config == "cfg4" and not rows_log2:
+        rows_log2 = 30 if world >= 4 else 27          # 2^30 rows x 64 x (table + Adagrad sum) = 512 GiB needs >= 4 x 180 GB
+    cfg = get_cfg(args.config, rows_log2)
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -432,10 +461,13 @@ def run_ours(args):
     torch.manual_seed(0)
     if world > 1:
         from torchctr_b200.parallel import shard_model
-    model = build_model(cfg)                              # identical on every rank (same seed)
+    native = bool(cfg.get("hashed"))                      # cfg4: tables declared on the meta device, created shard by shard
+    model = build_model(cfg, table_device="meta" if native else None)      # identical on every rank (same seed)
     if world > 1:
         dedup = {"auto": None, "on": True, "off": False}[args.dedup]
-        model = shard_model(model, None, device=dev, dedup=dedup)    # keep this rank's rows of every table, drop the rest
+        model = shard_model(model, None, device=dev, dedup=dedup, init_seed=0)   # this rank's rows of every table only
+    elif native:
+        model.materialize_tables(dev, seed=0)
     model = model.to(dev).train()
     if world > 1:
         model.enable_flat_dense_grads()                   # dense gradients live in one buffer: all-reduce without cat / copies
@@ -617,6 +649,17 @@ def run_ours(args):
                         + args.precision + " (parity: tests/test_gpu_precision.py)",
     }
     if rank == 0:
+        if world > 1 and cfg.get("hashed"):
+            # the exchange this configuration is about: every slot's row crosses NVLink once forward and its
+            # gradient slice once backward unless the owner is the requester -- 4 D B F (P - 1) / P bytes each way per GPU
+            nbytes = 4.0 * cfg["dim"] * B * len(cfg["vocabs"]) * (world - 1) / world
+            floor_ms = 2 * nbytes / 770e9 * 1e3
+            line["roofline_nvlink"] = {"bound": "nvlink", "bytes_each_way_per_gpu_per_step": nbytes, "peak": 770.0, "unit": "GB/s",
+                                       "peak_source": "B200_PROFILING.md: measured peer copy 770 GB/s per direction per GPU",
+                                       "floor_ms_per_step": floor_ms, "ms_per_step": ms / args.steps,
+                                       "achieved": 2 * nbytes / (ms / args.steps * 1e-3) / 1e9 / 2,
+                                       "frac": floor_ms / (ms / args.steps),
+                                       "note": "whole step (tower and HBM work included) against the two one-way NVLink transfers"}
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(cfg, 3, 1, B, budget_s=40.0 if cfg["model"] != "dnn" else 15.0)
             what = ("unmodified torchctr.models.DNN (baseline/_ref), loop body of Trainer.fit" if r["kind"] == "reference"
@@ -662,6 +705,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json configs: cfg2 DeepFM (headline), cfg3 DCN-v2, cfg1 DNN")
+    ap.add_argument("--rows-log2", type=int, default=0, help="cfg4: log2 of the total number of table rows (default 30 on >= 4 GPUs, else 27)")
     ap.add_argument("--no-trainer-leg", action="store_true", help="cfg1: skip the run inside the unmodified reference Trainer.fit")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

@@ -167,6 +167,12 @@ int ctr_rows_gather(const int64_t *ids, int64_t n, const float *table, int64_t n
 int ctr_normal_fill_rows(float *table, int64_t row0, int64_t n, int32_t D, float mean, float std,
                          uint64_t seed, void *stream);
 
+/* the same generator for a SHARD: local rows [row0, row0 + n) of `table` stand for the global rows global_first,
+ * global_first + global_stride, ...; they get exactly the values ctr_normal_fill_rows gives those rows of the whole
+ * table (shard-native initialisation: no rank ever holds a full table) */
+int ctr_normal_fill_rows_strided(float *table, int64_t row0, int64_t n, int32_t D, float mean, float std, uint64_t seed,
+                                 int64_t global_first, int64_t global_stride, void *stream);
+
 /* min and max of an id tensor, written to out[0], out[1] (device) */
 int ctr_ids_minmax(const int64_t *ids, int64_t n, int64_t *out, void *stream);
 

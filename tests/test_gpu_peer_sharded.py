@@ -74,6 +74,8 @@ def _rank_main(rank, world, shared, prob, kind, errors, steps, dedup=False):
         opt = torch.optim.SGD(list(st.shards), lr=0.5) if kind == "sgd" else torch.optim.Adagrad(list(st.shards), lr=0.5)
         st.bind_optimizer(opt, kind=kind)
         feats = {n: t for n, t in zip(names, raw_all[rank] if hashed else ids_all[rank])}
+        B = ids_all[rank][0].shape[0]                    # ranks may hold batches of different sizes (uneven last batch)
+        dense = dense[:B]
         w16 = [w.clone() for w in full16]
         w1 = [w.clone() for w in full1]
         acc16 = [torch.zeros_like(w) for w in full16]
@@ -121,6 +123,15 @@ def _rank_main(rank, world, shared, prob, kind, errors, steps, dedup=False):
                     assert _close(rows, expect), \
                         f"update width {w} table {f} step {step}: max abs err {float((rows.cpu() - expect).abs().max()):.3e}"
             assert int(st.status.item()) == 0
+        if kind == "adagrad":                            # the fused-update state gathers to the oracle's accumulators too
+            for w, accs in enumerate((acc16, acc1)):
+                s0, s1 = st.export_full_optimizer_state(w)
+                assert s1 is None
+                for f in range(len(Vs)):
+                    assert _close(s0[f], accs[f]), f"optimizer state width {w} table {f}"
+                st.load_full_optimizer_state(([t * 2 for t in s0], None), w)
+                again0, _ = st.export_full_optimizer_state(w)
+                assert all(torch.equal(a, t * 2) for a, t in zip(again0, s0))
         # checkpoint round trip in the reference's unsharded format: export == the oracle's tables, load restores them
         for w, ws in enumerate((w16, w1)):
             full = st.export_full_tables(w)
@@ -156,3 +167,71 @@ def test_peer_sharded_threads(world, kind, hashed, dedup):
     faulthandler.cancel_dump_traceback_later()
     assert not errors, errors
     assert all(not t.is_alive() for t in threads)
+
+
+def test_uneven_batches_share_buffers_sized_for_the_largest():
+    """the ranks agree on the buffer geometry collectively (sized for the largest batch any rank holds), a
+    smaller batch -- the uneven last batch of an epoch -- reuses them, and a batch that does not fit raises instead of
+    entering a collective alone."""
+    import faulthandler
+    import sys
+    from torchctr_b200.parallel.peer import ThreadTransport
+    faulthandler.dump_traceback_later(300, exit=True, file=sys.stderr)
+    world = 3
+    shared = ThreadTransport.Shared(world)
+    prob = list(_problem(world))
+    for r in range(world):                               # rank r holds B - 37 r samples
+        n = prob[3] - 37 * r
+        prob[6][r] = [t[:n] for t in prob[6][r]]
+        prob[7][r] = prob[7][r][:n]
+        prob[8][r] = prob[8][r][:n]
+    errors = []
+    threads = [threading.Thread(target=_rank_main, args=(r, world, shared, tuple(prob), "adagrad", errors, 2, False)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=240)
+    faulthandler.cancel_dump_traceback_later()
+    assert not errors, errors
+
+
+def _native_init_rank(rank, world, shared, Vs, D, seed, out, errors):
+    try:
+        from torchctr_b200.nn.embedding import EmbeddingTable
+        from torchctr_b200.parallel.peer import PeerShardedTables, ThreadTransport
+        dev = torch.device("cuda", 0)
+        tr = ThreadTransport(shared, rank, dev)
+        tabs = [EmbeddingTable(v, D, device="meta") for v in Vs]                  # declared, never allocated
+        tabs1 = [EmbeddingTable(v, 1, device="meta") for v in Vs]
+        st = PeerShardedTables([f"f{i}" for i in range(len(Vs))], [tabs, tabs1], tr, dev, init_seed=seed)
+        out[rank] = (st.export_full_tables(0), st.export_full_tables(1))
+    except BaseException as e:          # noqa: BLE001
+        errors.append((rank, repr(e)[:600]))
+        try:
+            shared.barrier.abort()
+        except Exception:
+            pass
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_shard_native_init_equals_unsharded_init(world):
+    """BASELINE config 4 (2^30 rows x 64: no rank can hold a full table): tables declared on the meta device are created
+    shard by shard with the counter-based generator keyed by the GLOBAL row, so ANY world size gives the table an unsharded
+    model gets from ``counter_init_`` with the same seed -- bit for bit."""
+    from torchctr_b200.nn.embedding import EmbeddingTable
+    from torchctr_b200.parallel.peer import ThreadTransport
+    Vs, D, seed = [37, 1000, 5, 4099], 64, 1234
+    shared = ThreadTransport.Shared(world)
+    out, errors = {}, []
+    threads = [threading.Thread(target=_native_init_rank, args=(r, world, shared, Vs, D, seed, out, errors)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors, errors
+    for w, Dw in enumerate((D, 1)):
+        for f, v in enumerate(Vs):
+            ref = EmbeddingTable(v, Dw).cuda().counter_init_(EmbeddingTable.counter_seed(seed, f, w)).weight.detach().cpu()
+            assert 0.8 < float(ref.std()) < 1.2 or v * Dw < 200
+            for r in range(world):
+                assert torch.equal(out[r][w][f], ref), (w, f, r)

@@ -84,6 +84,8 @@ _SIGNATURES = {
     "ctr_hash_bucket_bytes": (C.c_int, [_P, _P, C.c_int64, C.c_uint32, C.c_uint32, _P, _P]),
     "ctr_rows_gather": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P, _P]),
     "ctr_normal_fill_rows": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_uint64, _P]),
+    "ctr_normal_fill_rows_strided": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_uint64, C.c_int64,
+                                               C.c_int64, _P]),
     "ctr_ids_minmax": (C.c_int, [_P, C.c_int64, _P, _P]),
     "ctr_emb_bwd_workspace_bytes": (C.c_int64, [C.POINTER(Group)]),
     "ctr_emb_bwd_plan": (C.c_int, [C.POINTER(Group), _P, C.c_int64, _P]),

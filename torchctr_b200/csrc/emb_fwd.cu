@@ -325,18 +325,21 @@ __global__ void rows_gather_kernel(const int64_t *__restrict__ ids, int64_t n, c
 
 // Counter-based normal generator: Philox-free, two rounds of mix64 -> Box-Muller.  Row/col
 // addressed so that growing a table in several steps gives the same rows as growing it once.
+// (row_first, row_stride): the GLOBAL row that local row i stands for is row_first + i * row_stride -- a rank that owns every
+// P-th row of a table draws exactly the values the unsharded table holds in those rows.
 __global__ void normal_fill_rows_kernel(float *table, int64_t row0, int64_t n, int D, float mean, float stdv,
-                                        uint64_t seed) {
+                                        uint64_t seed, int64_t row_first, int64_t row_stride) {
     const int64_t total = n * D;
+    table += row0 * D;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = row0 + i / D;
+        const int64_t r = row_first + (i / D) * row_stride;
         const int c = (int)(i % D);
         const uint64_t ctr = mix64(seed ^ mix64((uint64_t)r * 0x9e3779b97f4a7c15ull + (uint64_t)c + 1ull));
         const uint32_t a = (uint32_t)(ctr >> 32), b = (uint32_t)ctr;
         const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0, 1)
         const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
         const float z = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
-        table[r * D + c] = mean + stdv * z;
+        table[i] = mean + stdv * z;
     }
 }
 
@@ -495,7 +498,18 @@ extern "C" int ctr_normal_fill_rows(float *table, int64_t row0, int64_t n, int32
     if (n == 0) return CTR_OK;
     CTR_REQUIRE(table != nullptr, "null pointer");
     note_launch(), normal_fill_rows_kernel<<<grid_for(n * D, 256, kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(table, row0, n, D, mean,
-                                                                                              stdv, seed);
+                                                                                              stdv, seed, row0, 1);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+extern "C" int ctr_normal_fill_rows_strided(float *table, int64_t row0, int64_t n, int32_t D, float mean, float stdv, uint64_t seed,
+                                            int64_t global_first, int64_t global_stride, void *stream) {
+    CTR_REQUIRE(n >= 0 && D >= 1 && row0 >= 0 && global_first >= 0 && global_stride >= 1, "bad sizes");
+    if (n == 0) return CTR_OK;
+    CTR_REQUIRE(table != nullptr, "null pointer");
+    note_launch(), normal_fill_rows_kernel<<<grid_for(n * D, 256, kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(
+        table, row0, n, D, mean, stdv, seed, global_first, global_stride);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }

@@ -44,7 +44,7 @@ def make_tower(input_dim: int, hidden_units, p_drop: float = 0.5) -> nn.Sequenti
     return nn.Sequential(*layers)
 
 
-def table_from_config(cfg) -> EmbeddingTable:
+def table_from_config(cfg, device=None) -> EmbeddingTable:
     """Table for one sparse feature.  ``raw_ids: True`` (extension) means the batch carries raw
     category ids rather than rows: with ``hash_buckets`` the murmur3 bucket of
     ``torchctr/transformer.py:487-490`` is computed inside the lookup, without it the ids go
@@ -56,19 +56,24 @@ def table_from_config(cfg) -> EmbeddingTable:
         else:
             kind = "vocab"
             vocab = VocabIndex(capacity=cfg.get("vocab_capacity", 1 << 16), min_freq=cfg.get("min_freq", 0))
+    kw = {} if device is None else {"device": device}
     return EmbeddingTable(cfg["num_embeddings"], cfg["emb_dim"], pooling=cfg.get("pooling", "sum"), index_kind=kind,
-                          hash_seed=cfg.get("seed", 0), vocab=vocab, use_id_weight=bool(cfg.get("use_weight", False)))
+                          hash_seed=cfg.get("seed", 0), vocab=vocab, use_id_weight=bool(cfg.get("use_weight", False)), **kw)
 
 
 class CTRModelBase(nn.Module):
     """Holds ``feat_configs``, ``embeddings`` (ModuleDict of tables keyed by feature name) and the
     fused lookup; subclasses add the interaction and the tower."""
 
-    def __init__(self, feat_configs):
+    def __init__(self, feat_configs, table_device=None):
+        """``table_device='meta'``: the tables are declared but not allocated -- for models whose tables only ever exist as
+        row shards (``parallel.shard_model`` fills every rank's rows in place, BASELINE config 4: 2^30 rows x 64) or that are
+        materialised on the device with ``materialize_tables``."""
         super().__init__()
         self.feat_configs = feat_configs
         self._sparse, self._dense_width = split_feature_configs(feat_configs)
-        self.embeddings = nn.ModuleDict({c["name"]: table_from_config(c) for c in self._sparse})
+        self._table_device = table_device
+        self.embeddings = nn.ModuleDict({c["name"]: table_from_config(c, table_device) for c in self._sparse})
         self._names = [c["name"] for c in self._sparse]
         self._sparse_width = sum(c["emb_dim"] for c in self._sparse)
         self._lookup = PooledLookupGroup(self._names, self.embeddings)
@@ -95,6 +100,20 @@ class CTRModelBase(nn.Module):
             return self
         for g in self._groups:
             g.bind_optimizer(optimizer, kind)
+        return self
+
+    def materialize_tables(self, device, seed: int | None = None, std: float = 1.0):
+        """Allocate meta tables on ``device`` and fill them with the counter-based generator (the values a row-sharded copy
+        of the model gets for the same ``seed``)."""
+        from ..nn.embedding import EmbeddingTable
+        seed = torch.initial_seed() if seed is None else seed
+        groups = [g.tables for g in self._groups]
+        for w, tables in enumerate(groups):
+            for f, name in enumerate(self._names):
+                t = tables[name]
+                if t.weight.is_meta:
+                    t.weight = nn.Parameter(torch.empty(t.num_embeddings, t.embedding_dim, dtype=torch.float32, device=device))
+                t.counter_init_(EmbeddingTable.counter_seed(seed, f, w), std)
         return self
 
     def table_optimizer_state_dict(self):

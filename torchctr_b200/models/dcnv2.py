@@ -9,8 +9,8 @@ from .base import CTRModelBase, make_tower
 
 
 class DCNv2(CTRModelBase):
-    def __init__(self, feat_configs, hidden_units=[256, 128, 64], num_cross_layers: int = 3):
-        super().__init__(feat_configs)
+    def __init__(self, feat_configs, hidden_units=[256, 128, 64], num_cross_layers: int = 3, table_device=None):
+        super().__init__(feat_configs, table_device)
         width = self._sparse_width + self._dense_width
         self.cross = nn.ModuleList([CrossLayer(width, width) for _ in range(num_cross_layers)])
         self.tower = make_tower(width, list(hidden_units))

@@ -12,8 +12,8 @@ from .base import CTRModelBase, make_tower
 
 
 class DeepFM(CTRModelBase):
-    def __init__(self, feat_configs, hidden_units=[256, 128, 64]):
-        super().__init__(feat_configs)
+    def __init__(self, feat_configs, hidden_units=[256, 128, 64], table_device=None):
+        super().__init__(feat_configs, table_device)
         dims = {c["emb_dim"] for c in self._sparse}
         if len(dims) != 1:
             raise ValueError("DeepFM needs one common emb_dim for the FM term")
@@ -23,7 +23,7 @@ class DeepFM(CTRModelBase):
             src = self.embeddings[c["name"]]
             self.linear_embeddings[c["name"]] = EmbeddingTable(
                 c["num_embeddings"], 1, pooling=src.pooling, index_kind=src.index_kind, hash_seed=src.hash_seed,
-                vocab=src.vocab, use_id_weight=src.use_id_weight)
+                vocab=src.vocab, use_id_weight=src.use_id_weight, **({} if table_device is None else {"device": table_device}))
         self._linear_lookup = PooledLookupGroup(self._names, self.linear_embeddings)
         self._groups.append(self._linear_lookup)
         self.linear_dense = nn.Linear(self._dense_width, 1) if self._dense_width else None

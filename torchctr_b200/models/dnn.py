@@ -5,8 +5,8 @@ from .base import CTRModelBase, make_tower
 
 
 class DNN(CTRModelBase):
-    def __init__(self, feat_configs, hidden_units=[256, 128, 64]):
-        super().__init__(feat_configs)
+    def __init__(self, feat_configs, hidden_units=[256, 128, 64], table_device=None):
+        super().__init__(feat_configs, table_device)
         self.tower = make_tower(self._sparse_width + self._dense_width, list(hidden_units))
 
     def forward(self, input_feats):

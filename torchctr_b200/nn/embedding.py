@@ -115,6 +115,19 @@ class EmbeddingTable(nn.Embedding):
                 setattr(self, name, fn(buf))
         return out
 
+    # -- counter-based initialisation: the same table whatever the sharding ------------------------------------------------
+    @staticmethod
+    def counter_seed(base_seed: int, table_index: int, width_index: int = 0) -> int:
+        return (int(base_seed) * 1000003 + width_index * 4099 + table_index) & 0x7FFFFFFFFFFFFFFF
+
+    def counter_init_(self, seed: int, std: float = 1.0):
+        """weight[r, c] := N(0, std) drawn from a counter-based generator keyed by (seed, r, c) (``ctr_normal_fill_rows``)
+        instead of torch's sequential stream: any rank can then create just ITS rows of the table
+        (``ctr_normal_fill_rows_strided``) and the union equals this table -- row-sharded models need no full copy anywhere."""
+        with torch.no_grad():
+            ops.normal_fill_rows(self.weight.data, 0, self.num_embeddings, 0.0, std, seed)
+        return self
+
     # -- growth (DynamicEmbedding._expand_embeddings, torchctr/nn/embedding.py:69-78) -----------
     def grow_to(self, new_num_embeddings: int, std: float = 0.01) -> None:
         """Append rows ~ N(0, std) up to ``new_num_embeddings``; existing rows keep their values.

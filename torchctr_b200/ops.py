@@ -333,6 +333,18 @@ def normal_fill_rows(table: torch.Tensor, row0: int, n: int, mean: float, std: f
 
 
 @_guarded
+def normal_fill_rows_strided(table: torch.Tensor, row0: int, n: int, mean: float, std: float, seed: int, global_first: int,
+                             global_stride: int) -> None:
+    """Rows [row0, row0 + n) of a shard := the values ``normal_fill_rows`` gives global rows first, first + stride, ..."""
+    _chk(table, "table", torch.float32)
+    if row0 < 0 or row0 + n > table.shape[0]:
+        raise ValueError("row range outside the table")
+    _lib.check(_lib.lib().ctr_normal_fill_rows_strided(table.data_ptr(), row0, n, table.shape[1], mean, std,
+                                                       seed & 0xFFFFFFFFFFFFFFFF, global_first, global_stride, _stream(table)),
+               "ctr_normal_fill_rows_strided")
+
+
+@_guarded
 def ids_minmax(ids: torch.Tensor) -> torch.Tensor:
     """Device tensor i64 [2] = (min, max) of ids."""
     _chk(ids, "ids", torch.int64)

@@ -6,7 +6,7 @@ import torch.nn as nn
 from .sharded import ShardedTables, reduce_dense_grads
 
 
-def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=None, dedup=None):
+def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=None, dedup=None, init_seed=None):
     """Every rank calls this with an identically initialised ``model`` (same seed).  The model's tables
     (and, for DeepFM, its first-order tables, which share the ids) are cut into this rank's rows, fused
     into one shard per width on ``device`` and the full tables are dropped; the dense part stays
@@ -28,7 +28,8 @@ def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=
             transport = IpcTransport(pg, device)
         if dedup is None:                     # the requester-side sort pays off once nearly all rows are remote: measured
             dedup = transport.world > 4       # -10 % at 2 GPUs, +6 % at 8
-        sharded = PeerShardedTables(groups[0].names, full, transport, device, dedup=dedup)
+        # tables declared on the meta device (model built with table_device='meta') are created shard by shard, in place
+        sharded = PeerShardedTables(groups[0].names, full, transport, device, dedup=dedup, init_seed=init_seed)
     elif device is not None:
         # shards are built on the target device straight from the (host) full tables
         import torch
@@ -58,13 +59,48 @@ def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=
         """Collective.  The state dict of the UNSHARDED model -- every table gathered back to ``[V, D]`` under its
         original key -- so that ``Trainer.save_ckpt`` output (``torchctr/trainer.py:353-496``) written from it loads
         into the reference ``DNN`` or into an unsharded model of this package."""
+        if not hasattr(sharded, "export_full_tables"):
+            raise NotImplementedError("full_state_dict(): the all-to-all formulation (ShardedTables) cannot gather its tables; "
+                                      "use the peer-memory mode (mode='peer') for checkpoints in the reference's format")
         sd = {k: v.detach().cpu() for k, v in model.state_dict().items() if not k.startswith("_sharded.")}
-        if hasattr(sharded, "export_full_tables"):
-            for w, prefix in enumerate(table_prefix):
-                if prefix is None:
-                    continue
-                for name, t in zip(sharded.names, sharded.export_full_tables(w)):
-                    sd[f"{prefix}.{name}.weight"] = t
+        for w, prefix in enumerate(table_prefix):
+            if prefix is None:
+                continue
+            for name, t in zip(sharded.names, sharded.export_full_tables(w)):
+                sd[f"{prefix}.{name}.weight"] = t
         return sd
+
+    def full_table_optimizer_state():
+        """Collective.  The fused-update state of the sharded tables gathered to full ``[V, D]`` tensors, keyed like
+        ``CTRModelBase.table_optimizer_state_dict`` ({'embeddings.<name>': {'state0', 'state1'}}): together with
+        ``full_state_dict()`` a complete, sharding-independent checkpoint."""
+        out = {}
+        for w, prefix in enumerate(table_prefix):
+            if prefix is None:
+                continue
+            s0, s1 = sharded.export_full_optimizer_state(w)
+            if s0 is None:
+                continue
+            for f, name in enumerate(sharded.names):
+                out[f"{prefix}.{name}"] = {"state0": s0[f], "state1": None if s1 is None else s1[f]}
+        return out
+
+    def load_full_state(state_dict, table_optimizer_state=None):
+        """Collective inverse: every rank passes the same full state dict (reference format) and optional optimizer state."""
+        import torch
+        dense = {k: v for k, v in state_dict.items() if not any(k.startswith(p + ".") for p in table_prefix if p)}
+        own = model.state_dict()
+        model.load_state_dict({**{k: v for k, v in own.items() if k.startswith("_sharded.")}, **dense}, strict=False)
+        for w, prefix in enumerate(table_prefix):
+            if prefix is None:
+                continue
+            sharded.load_full_tables([state_dict[f"{prefix}.{n}.weight"] for n in sharded.names], w)
+            if table_optimizer_state:
+                ent = [table_optimizer_state.get(f"{prefix}.{n}") for n in sharded.names]
+                if all(e is not None for e in ent):
+                    s1 = None if ent[0]["state1"] is None else [e["state1"] for e in ent]
+                    sharded.load_full_optimizer_state(([e["state0"] for e in ent], s1), w)
+    model.full_table_optimizer_state = full_table_optimizer_state
+    model.load_full_state = load_full_state
     model.full_state_dict = full_state_dict
     return model

@@ -206,7 +206,8 @@ class PeerShardedTables(nn.Module):
     the reference loop ``torchctr/trainer.py:291-303`` and gradient accumulation over micro-batches do).  All ranks
     must call ``forward`` / ``backward`` the same number of times with the same batch size."""
 
-    def __init__(self, names, full_tables, transport, device=None, dedup: bool = False):
+    def __init__(self, names, full_tables, transport, device=None, dedup: bool = False, init_seed: int | None = None,
+                 init_std: float = 1.0):
         """``dedup``: every distinct row of this rank's batch crosses NVLink once per direction (the requester sorts
         its slots, fetches the distinct rows into a staging matrix and pools from there; backward it reduces its own
         duplicates before the owners pull) instead of once per id slot.  Pays a local sort on the forward path, saves
@@ -236,14 +237,21 @@ class PeerShardedTables(nn.Module):
         self._shard_bufs, self._table_ptrs = [], []
         self.shards = nn.ParameterList()
         rows = self.total[self.rank]
-        for tabs, D in zip(full_tables, self.dims):
+        from ..nn.embedding import EmbeddingTable
+        seed0 = torch.initial_seed() if init_seed is None else init_seed
+        for wi, (tabs, D) in enumerate(zip(full_tables, self.dims)):
             buf = PeerBuffer(rows * D * 4, dev)
             w = buf.tensor(torch.float32, (rows, D))
             for f, t in enumerate(tabs):
                 fr, n = owned_rows(self.num_rows[f], f, self.rank, self.world)
                 if n:
                     b = self.base[self.rank][f]
-                    w[b:b + n] = t.weight.detach()[fr::self.world].to(dev)
+                    if t.weight.is_meta:
+                        # shard-native: this rank draws ITS rows of the table with the counter-based generator; no rank ever
+                        # holds the full table (BASELINE config 4: 2^30 rows x 64 floats = 256 GiB)
+                        ops.normal_fill_rows_strided(w, b, n, 0.0, init_std, EmbeddingTable.counter_seed(seed0, f, wi), fr, self.world)
+                    else:
+                        w[b:b + n] = t.weight.detach()[fr::self.world].to(dev)
             self._shard_bufs.append(buf)
             self.shards.append(nn.Parameter(w, requires_grad=True))
             self._table_ptrs.append(ops.ptr_array(transport.share(buf)))
@@ -276,12 +284,24 @@ class PeerShardedTables(nn.Module):
 
     # ---- per-batch peer buffers ----------------------------------------------------------------------------------
     def _ensure_buffers(self, ids_list):
+        """Peer buffers (routing lists, gradient matrices) are sized ONCE, collectively, for the largest batch any rank has
+        seen in this call -- every rank enters the exchange together on the first training forward -- and later batches
+        that fit (an uneven last batch, a smaller micro-batch) reuse them without any collective.  A batch that does not
+        fit raises on that rank instead of silently entering a collective the other ranks are not in."""
         B = ids_list[0].shape[0]
         Ls = tuple(i.shape[1] for i in ids_list) + (self._dense_width,)
-        if self._B == (B, Ls):
-            return
+        if self._B is not None:
+            capB, capLs = self._B
+            if Ls == capLs and B <= capB:
+                return
+            raise RuntimeError(f"sharded lookup: batch geometry {(B, Ls)} does not fit the peer buffers sized for {self._B}; "
+                               "all ranks must call reserve(max_batch) together before a larger batch is used")
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("peer buffers must be sized (one eager step) before the step is captured into a CUDA graph")
+        geoms = self.transport.all_gather_object((B, Ls))
+        if any(g[1] != Ls for g in geoms):
+            raise RuntimeError(f"sharded lookup: ranks disagree on the feature layout: {geoms}")
+        B = max(g[0] for g in geoms)
         S = B * sum(Ls[:-1])
         dev = self.device
         tr = self.transport
@@ -310,6 +330,9 @@ class PeerShardedTables(nn.Module):
                 self._rowgrad_bufs.append(buf)
                 self._peer_rowgrads.append(ops.ptr_array(tr.share(buf)))
             self._one_id = torch.zeros(1, 1, dtype=torch.int64, device=dev)
+        # owner-side groups are sized for the CAPACITY batch (a peer may send more slots than this rank's own batch holds);
+        # their ids are never read -- the owner pulls the peers' routing lists
+        self._owner_ids = [torch.zeros(B, L, dtype=torch.int64, device=dev) for L in Ls[:-1]]
         self._S = S
         self._B = (B, Ls)
 
@@ -385,7 +408,7 @@ class PeerShardedTables(nn.Module):
             # the owner-side plan needs the routing lists of every rank, which depend on the ids only: build them,
             # meet the other ranks and sort -- all on the side stream, next to the tower, as the single-GPU path does
             # with its early sort.  backward() then only waits for the gradients.
-            plan_call = ops.make_group(self._owner_specs(ids_list, 0, False), B, None, self._strides[0])
+            plan_call = ops.make_group(self._owner_specs(self._owner_ids, 0, False), self._B[0], None, self._strides[0])
             need_plan = ops.emb_bwd_p2p_workspace_bytes(plan_call, self.world)
             if self._plan_ws is None or self._plan_ws.numel() < need_plan:
                 if torch.cuda.is_current_stream_capturing():
@@ -490,7 +513,7 @@ class PeerShardedTables(nn.Module):
                 self._grad_bufs[w].tensor(torch.float32, (B, self._strides[w])).copy_(g)
         self.transport.barrier()                         # every rank's routing lists and gradients are in place
         if not self._owner_planned:                      # (no early plan was started in forward)
-            plan_call = ops.make_group(self._owner_specs(ids_list, 0, False), B, None, self._strides[0])
+            plan_call = ops.make_group(self._owner_specs(self._owner_ids, 0, False), self._B[0], None, self._strides[0])
             need = ops.emb_bwd_p2p_workspace_bytes(plan_call, self.world)
             if self._plan_ws is None or self._plan_ws.numel() < need:
                 if torch.cuda.is_current_stream_capturing():
@@ -501,7 +524,7 @@ class PeerShardedTables(nn.Module):
         for w in live:
             bind = self.bindings[w]
             self._ensure_state(w, bind.kind, bind.initial_accumulator_value())
-            call = ops.make_group(self._owner_specs(ids_list, w, True), B, None, self._strides[w])
+            call = ops.make_group(self._owner_specs(self._owner_ids, w, True), self._B[0], None, self._strides[w])
             ops.emb_bwd_apply_p2p(call, self._shard_struct, self._plan_ws, bind.next_opt(), self._peer_grads[w])
         self.transport.barrier()                         # nobody overwrites lists / gradients / reads rows too early
 
@@ -531,6 +554,50 @@ class PeerShardedTables(nn.Module):
                     t[fr::self.world] = parts[r][f]
             full.append(t)
         return full
+
+    def export_full_optimizer_state(self, w: int = 0):
+        """Collective.  The fused-update state of width ``w`` gathered like ``export_full_tables``: a list (one entry per
+        feature) of ``(state0, state1)`` full tensors or None when the width has no state yet."""
+        torch.cuda.synchronize(self.device)
+        out = []
+        for which, states in enumerate((self.opt_state0, self.opt_state1)):
+            st = states[w]
+            mine = None
+            if st is not None:
+                mine = []
+                for f in range(self.num_features):
+                    _, n = owned_rows(self.num_rows[f], f, self.rank, self.world)
+                    b = self.base[self.rank][f]
+                    mine.append(st[b:b + n].detach().cpu())
+            parts = self.transport.all_gather_object(mine)
+            if parts[0] is None:
+                out.append(None)
+                continue
+            full = []
+            for f, v in enumerate(self.num_rows):
+                t = torch.zeros((v,) + tuple(parts[0][f].shape[1:]), dtype=torch.float32)
+                for r in range(self.world):
+                    fr, n = owned_rows(v, f, r, self.world)
+                    if n:
+                        t[fr::self.world] = parts[r][f]
+                full.append(t)
+            out.append(full)
+        return out
+
+    def load_full_optimizer_state(self, state, w: int = 0) -> None:
+        """Inverse of ``export_full_optimizer_state`` (every rank passes the same full tensors)."""
+        for which, name in enumerate(("opt_state0", "opt_state1")):
+            full = state[which]
+            if full is None:
+                continue
+            rows = self.total[self.rank]
+            buf = torch.zeros((rows,) + tuple(full[0].shape[1:]), dtype=torch.float32, device=self.device)
+            for f, t in enumerate(full):
+                fr, n = owned_rows(self.num_rows[f], f, self.rank, self.world)
+                if n:
+                    b = self.base[self.rank][f]
+                    buf[b:b + n] = t[fr::self.world].to(self.device)
+            getattr(self, name)[w] = buf
 
     def load_full_tables(self, full, w: int = 0) -> None:
         """Scatter full tables (one ``[V_f, dims[w]]`` tensor per feature, e.g. from a reference checkpoint) into
