@@ -508,7 +508,8 @@ def run_ours(args):
     # N > 1: the global-batch loss of the first two steps (mean over the ranks' losses), printed so that runs at different
     # N -- and the N = 1 run on the same global batch -- can be compared
     loss_trace = None
-    if world > 1:
+    rank0_first = float(first_losses[0])          # forward of step 0 on rank 0's batch with the initial weights: the SAME number
+    if world > 1:                                  # at every N (sharded lookup == unsharded lookup at bench scale)
         t = torch.stack(first_losses)
         dist.all_reduce(t)
         loss_trace = (t / world).tolist()
@@ -541,7 +542,12 @@ def run_ours(args):
         step = lambda batch, i: graphed(batch)           # noqa: E731
         packed = [graphed.pack(b) for b in resident]     # resident leg: one device-to-device copy per step, like the e2e leg
 
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+
     def timed(batches, steps, read_loss):
+        """read_loss (the end-to-end leg): every step's loss is copied to pinned host memory and read by the host -- one step
+        late, i.e. while the next step already runs, so that the readback does not leave the GPU idle between steps."""
         barrier()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
@@ -549,12 +555,21 @@ def run_ours(args):
         prefetch = getattr(graphed_holder[0], "prefetch", None) if read_loss else None
         if prefetch is not None:
             prefetch(batches[0])
+        seen = 0
         for i in range(steps):
             loss = step(batches[i % nb], i)
             if read_loss:
+                loss_host[i % 2].copy_(loss.detach(), non_blocking=True)     # device -> host copy of this step's result
+                loss_ev[i % 2].record()
                 if prefetch is not None and i + 1 < steps:
                     prefetch(batches[(i + 1) % nb])      # next batch's host -> device copy runs under this step
-                loss.item()                              # device -> host read of the step's result
+                if i > 0:
+                    loss_ev[(i - 1) % 2].synchronize()
+                    seen += float(loss_host[(i - 1) % 2]) == float(loss_host[(i - 1) % 2])
+        if read_loss:
+            loss_ev[(steps - 1) % 2].synchronize()
+            seen += float(loss_host[(steps - 1) % 2]) == float(loss_host[(steps - 1) % 2])
+            assert seen == steps, "a loss read back from the device was NaN"
         t1.record()
         barrier()
         wall = time.perf_counter() - w0
@@ -638,7 +653,7 @@ def run_ours(args):
         "gpu_launches": launches, "cuda_graph": not args.no_graph, "kernels": kern, "kernels_in_step": in_step,
         "roofline": roofline_tensor if roofline_tensor is not None else roofline,
         "roofline_embedding": roofline if roofline_tensor is not None else None,
-        "trainer_fit": trainer_leg, "loss_first_steps": loss_trace,
+        "trainer_fit": trainer_leg, "loss_first_steps": loss_trace, "loss_step0_rank0": rank0_first,
         "parallelism": "single GPU" if world == 1 else f"tables row-sharded over {world} GPUs (owner = (row + table) mod P); rows read "
                        "and gradients pulled through NVLink peer mappings inside the lookup / update kernels (no all-to-all), "
                        "batch data-parallel, tower replicated + one NCCL all-reduce"

@@ -235,3 +235,56 @@ def test_shard_native_init_equals_unsharded_init(world):
             assert 0.8 < float(ref.std()) < 1.2 or v * Dw < 200
             for r in range(world):
                 assert torch.equal(out[r][w][f], ref), (w, f, r)
+
+
+def _sharded_model_rank(rank, world, shared, fc, state, feats, out, errors):
+    try:
+        from torchctr_b200.models import DeepFM
+        from torchctr_b200.parallel import shard_model
+        from torchctr_b200.parallel.peer import ThreadTransport
+        dev = torch.device("cuda", 0)
+        tr = ThreadTransport(shared, rank, dev)
+        model = DeepFM(fc, [32, 16])
+        model.load_state_dict(state)
+        model = shard_model(model, transport=tr, device=dev).to(dev).eval()
+        with torch.no_grad():
+            out[rank] = model(feats).cpu()
+        sd = model.full_state_dict()                     # collective: the reference-format state dict, tables gathered
+        assert set(sd) == set(state), set(sd) ^ set(state)
+        for k, v in state.items():
+            assert torch.equal(sd[k].cpu(), v), k
+    except BaseException as e:          # noqa: BLE001
+        errors.append((rank, repr(e)[:600]))
+        try:
+            shared.barrier.abort()
+        except Exception:
+            pass
+
+
+def test_sharded_deepfm_model_forward_and_full_state_dict():
+    """Model level: ``shard_model`` on a DeepFM (two table widths sharing the ids, FM + first-order terms outside the fused
+    single-GPU path) gives the logits of the unsharded model, and ``full_state_dict()`` returns exactly the unsharded keys
+    and values."""
+    from torchctr_b200.models import DeepFM
+    from torchctr_b200.parallel.peer import ThreadTransport
+    world = 2
+    gen = torch.Generator().manual_seed(4)
+    fc = [{"name": f"c{i}", "type": "sparse", "num_embeddings": 50 + 9 * i, "emb_dim": 16} for i in range(5)]
+    fc += [{"name": f"d{i}", "type": "dense"} for i in range(3)]
+    feats = {f"c{i}": torch.randint(0, 50 + 9 * i, (200, 1), generator=gen) for i in range(5)}
+    feats["dense_features"] = torch.randn(200, 3, generator=gen)
+    torch.manual_seed(0)
+    ref = DeepFM(fc, [32, 16]).cuda().eval()
+    state = {k: v.detach().cpu().clone() for k, v in ref.state_dict().items()}
+    with torch.no_grad():
+        expect = ref(feats).cpu()
+    shared = ThreadTransport.Shared(world)
+    out, errors = {}, []
+    threads = [threading.Thread(target=_sharded_model_rank, args=(r, world, shared, fc, state, feats, out, errors)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors, errors
+    for r in range(world):
+        assert _close(out[r], expect), r

@@ -300,10 +300,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 template <int BN>
 static int launch_linear(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs g, cudaStream_t stream) {
     constexpr int smem = 4 * (kTileABytes + BN * kBK * 4) + 1024 + 256 + 4 * 4096;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};            // the attribute is per device: a process may drive several
+    int dev = 0;
+    CTR_CUDA_OK(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
         CTR_CUDA_OK(cudaFuncSetAttribute(linear_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured[dev & 63] = true;
     }
     g.tiles_m = (g.M + kBM - 1) / kBM;
     g.tiles_n = (g.N + BN - 1) / BN;
@@ -569,10 +571,12 @@ extern "C" int ctr_linear_wgrad(const float *G, int64_t ldg, const float *X, int
     if (rc != CTR_OK) return rc;
     rc = make_map(&mx, X, B, K, ldx, kWgRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc != CTR_OK) return rc;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    int dev = 0;
+    CTR_CUDA_OK(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
         CTR_CUDA_OK(cudaFuncSetAttribute(wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
-        configured = true;
+        configured[dev & 63] = true;
     }
     WgradArgs a{static_cast<float *>(workspace), B, N, K, tn, rps};
     note_launch(), wgrad_tf32_kernel<<<dim3(tm * tn, sp), kGemmThreads, kWgSmem, stream>>>(mg, mx, a);

@@ -33,11 +33,13 @@ class DeepFM(CTRModelBase):
         """(tower input x, the logit terms outside the tower: FM second order + first order (+ Linear on dense))"""
         self._grow_vocabularies(input_feats)
         dense = self.dense_block(input_feats)
-        twins = [self.linear_embeddings[n] for n in self._names]
-        if self.training and self._sharded is None and torch.is_grad_enabled():
-            for g in self._groups:
-                g.autobind()
-        if self._sharded is None and self._lookup.fused_extra_eligible(input_feats, twins, self.training):
+        twins = None
+        if self._sharded is None:                             # (sharded: the tables live in the shards, not in the ModuleDicts)
+            twins = [self.linear_embeddings[n] for n in self._names]
+            if self.training and torch.is_grad_enabled():
+                for g in self._groups:
+                    g.autobind()
+        if twins is not None and self._lookup.fused_extra_eligible(input_feats, twins, self.training):
             # Criteo-shaped (single-id, one width): the first-order weights and the FM term ride inside the lookup
             # kernel, their gradients inside the fused update -- no D = 1 launch group, no pass over [B, F * D] for FM
             link = PlanLink() if self.training else None

@@ -35,4 +35,6 @@ def target_attention(target_emb: torch.Tensor, candidate_embs: torch.Tensor, mas
     if candidate_embs.dim() != 3 or target_emb.dim() != 2 or candidate_embs.shape[0] != target_emb.shape[0] \
             or candidate_embs.shape[2] != target_emb.shape[1]:
         raise ValueError(f"shapes: target {tuple(target_emb.shape)} vs candidates {tuple(candidate_embs.shape)}")
+    if candidate_embs.shape[1] == 0 or candidate_embs.shape[0] == 0:      # no candidates: the sum over an empty sequence
+        return target_emb.float() * 0.0 + candidate_embs.float().sum(dim=1)
     return _TargetAttentionFn.apply(target_emb.float(), candidate_embs.float(), mask, bool(honor_mask))
