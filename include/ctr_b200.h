@@ -253,6 +253,14 @@ int ctr_cross_combine_bwd(const float *x0, const float *u, const float *bias, co
 int ctr_linear_fwd(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias, float *C,
                    int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t act, void *stream);
 
+/* The same GEMM (no activation) that also leaves, per block of 32 output rows, the column sums of C and of C^2 in
+ * stats f32 [ctr_linear_stats_blocks(M)][2][N]: the batch statistics of the BatchNorm1d that follows the Linear in
+ * torchctr/models/dnn.py:39-41 come out of the GEMM epilogue instead of a second pass over C
+ * (-> ctr_bn_stats_from_partials).  N % 4 == 0; ctr_linear_stats_blocks returns 0 when M is too small for this path. */
+int32_t ctr_linear_stats_blocks(int32_t M);
+int ctr_linear_fwd_stats(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias, float *C, int64_t ldc,
+                         int32_t M, int32_t N, int32_t K, float *stats, int64_t stats_floats, void *stream);
+
 /* Weight gradient of the same layers: dW[N, K] = sum_b G[b, N] . X[b, K] (G = dL/dz, X = the layer input), TF32 in,
  * fp32 accumulate, the batch split over the SMs and the slices added in order.  ldg, ldx multiples of 4 floats,
  * G, X, workspace 16-byte aligned; workspace: ctr_linear_wgrad_workspace_bytes(B, N, K). */
@@ -281,6 +289,9 @@ int64_t ctr_tower_workspace_bytes(int32_t N);
  * and num_batches_tracked (may be NULL) are updated as torch.nn.BatchNorm1d does with `momentum`. */
 int ctr_bn_stats(const float *z, int64_t ldz, int32_t B, int32_t N, float eps, float momentum, float *mean, float *rstd,
                  float *running_mean, float *running_var, int64_t *num_batches_tracked, void *workspace, void *stream);
+/* ctr_bn_stats on partial sums produced by ctr_linear_fwd_stats (blocks = ctr_linear_stats_blocks(B)) */
+int ctr_bn_stats_from_partials(const float *partial, int32_t blocks, int32_t B, int32_t N, float eps, float momentum, float *mean,
+                               float *rstd, float *running_mean, float *running_var, int64_t *num_batches_tracked, void *stream);
 /* y = dropout_p(relu((z - mean) * rstd * gamma + beta)).  The keep mask is a function of (*seed_dev, seed_offset,
  * element index) and is not stored; the backward call must get the same three values. */
 int ctr_bn_relu_dropout_fwd(const float *z, int64_t ldz, int32_t B, int32_t N, const float *mean, const float *rstd,

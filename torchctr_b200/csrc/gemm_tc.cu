@@ -27,6 +27,7 @@ namespace ctr {
 constexpr int kBM = 128, kBK = 32;               // tile; kBK floats = 128 bytes = one swizzle row
 constexpr int kUmmaK = 8;                       // tf32: 32 bytes per MMA along K
 constexpr int kGemmThreads = 192;
+constexpr int kPairThreads = 320;              // the CTA-pair kernel: producer + MMA + eight epilogue warps
 constexpr int kTileABytes = kBM * kBK * 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,6 +98,8 @@ struct GemmArgs {
     int tiles_m, tiles_n;
     const float *A;      // for the L2 prefetch of whole A tiles
     int64_t lda;
+    float *stats;        // optional (pair kernel): per 32-row block column sums of C and of C^2, [blocks][2][N] -- the batch
+                         // statistics of the BatchNorm that follows the Linear come out of the GEMM epilogue
 };
 
 // pull a contiguous global range towards L2 (no data comes back to the SM): 16-byte aligned, multiple of 16 bytes
@@ -129,6 +132,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // rows [tile_m * 128, +128) of A are one contiguous range: stream them into L2
 __device__ __forceinline__ void prefetch_a_rows(const GemmArgs &g, int tile_m) {
     const int r0 = tile_m * kBM;
+    if (r0 >= g.M) return;
     const int nr = g.M - r0 < kBM ? g.M - r0 : kBM;
     const char *p = reinterpret_cast<const char *>(g.A + (int64_t)r0 * g.lda);
     const int64_t bytes = ((int64_t)(nr - 1) * g.lda + g.K) * 4 / 16 * 16;
@@ -297,6 +301,243 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
 }
 
+
+// ---- the same GEMM on CTA PAIRS (tcgen05.mma.cta_group::2) --------------------------------------------------------------
+// Measured on the 1-CTA kernel above: the tensor pipe is ~25 % busy and the kernel runs at the speed of the L2 -> SM operand
+// stream, because every 128-row CTA streams its own copy of the W tile.  A pair of CTAs (a 2-CTA cluster = the two SMs of a
+// TPC) computes a 256 x BN tile instead: CTA r loads ITS 128 rows of A and only HALF of the W tile (rows r * BN/2 .. of it);
+// one thread of the leader CTA issues M = 256 MMAs that read A and W halves out of both CTAs' shared memory and write each
+// CTA's 128 accumulator rows into that CTA's TMEM.  Per 256 x BN x 32 step the pair moves 32 KB + 32 KB x BN / 256 instead of
+// 32 KB + 64 KB x BN / 256: the W stream halves, and the same shared memory holds 6 stages instead of 4.
+//   producer (warp 0, both CTAs)   cp.async.bulk.tensor ... .cta_group::2: the bytes of BOTH CTAs complete on the LEADER's
+//                                  `full` barrier; a CTA re-fills a stage when ITS `empty` barrier fires;
+//   MMA (warp 1, leader only)      waits `full`, issues, tcgen05.commit.multicast -> `empty` of both CTAs, finally `acc_full`
+//                                  of both;
+//   epilogue (warps 2-5, both)     drain their own TMEM half, then arrive on the LEADER's `acc_empty` (8 arrivals).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {     // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+    linear_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
+    constexpr int kSt = BN == 256 ? 5 : (BN == 128 ? 7 : 8);
+    constexpr int kHalfB = (BN / 2) * kBK * 4;                             // this CTA's half of the W tile
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_smem = base, b_smem = base + kSt * kTileABytes;
+    const uint32_t bars = b_smem + kSt * kHalfB;
+    const uint32_t full0 = bars, empty0 = bars + 8 * kSt, acc_full0 = bars + 16 * kSt, acc_empty0 = acc_full0 + 16;
+    const uint32_t tmem_slot = acc_empty0 + 16;
+    const uint32_t epi_smem = bars + 256;
+    uint8_t *gen_base = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(gen_base + (tmem_slot - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int num_kb = (g.K + kBK - 1) / kBK;
+    const int tiles_m2 = (g.M + 2 * kBM - 1) / (2 * kBM);
+    const int num_tiles = tiles_m2 * g.tiles_n;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kSt; ++s) {
+            mbar_init(full0 + 8 * s, 1);           // the leader's arrive.expect_tx; bytes of both CTAs land here
+            mbar_init(empty0 + 8 * s, 1);          // one multicast commit per use
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full0 + 8 * b, 1);
+            mbar_init(acc_empty0 + 8 * b, 16);     // eight epilogue warps of each CTA
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    cluster_sync_all();                            // barriers of both CTAs exist before anybody signals across
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- TMA producer (both CTAs)
+            int it = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                const int m0 = (tile / g.tiles_n) * 2 * kBM + (int)rank * kBM;
+                const int n0 = (tile % g.tiles_n) * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % kSt;
+                    if (it >= kSt) mbar_wait(empty0 + 8 * s, ((it / kSt) - 1) & 1);
+                    const uint32_t lead_full = mapa_rank(full0 + 8 * s, 0);
+                    if (leader) mbar_expect_tx(full0 + 8 * s, 2 * (kTileABytes + kHalfB));
+                    tma_load_2d_pair(a_smem + s * kTileABytes, &map_a, lead_full, kb * kBK, m0);
+                    tma_load_2d_pair(b_smem + s * kHalfB, &map_b, lead_full, kb * kBK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {  // ---- MMA issuer (leader CTA only)
+            const uint32_t idesc = umma_idesc_tf32(2 * kBM, BN);
+            int it = 0, tl = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++tl) {
+                const int buf = tl & 1;
+                if (tl >= 2) {
+                    mbar_wait(acc_empty0 + 8 * buf, ((tl >> 1) - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % kSt;
+                    mbar_wait(full0 + 8 * s, (it / kSt) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t da = umma_desc(a_smem + s * kTileABytes), db = umma_desc(b_smem + s * kHalfB);
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k)
+                        umma_tf32_pair(tmem_acc, da + (uint64_t)(k * kUmmaK * 4 >> 4), db + (uint64_t)(k * kUmmaK * 4 >> 4), idesc,
+                                       (kb | k) ? 1u : 0u);
+                    umma_commit_pair(empty0 + 8 * s);       // both CTAs may re-fill the stage
+                }
+                umma_commit_pair(acc_full0 + 8 * buf);      // both CTAs' epilogues may read their accumulator half
+            }
+        }
+    } else {  // ---- epilogue warps 2..9 of both CTAs: TMEM lane quarter = warp % 4, two warps per quarter taking alternate
+              //      32-column chunks (a lone warp per scheduler cannot hide its own TMEM / shared-memory latencies)
+        const int q = warp & 3, half = (warp - 2) >> 2, ew = warp - 2;
+        const bool vec_ok = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15u) == 0);
+        const bool bias_vec = g.bias != nullptr && (reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0;
+        int tl = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs, ++tl) {
+            const int buf = tl & 1;
+            const int m0 = (tile / g.tiles_n) * 2 * kBM + (int)rank * kBM, n0 = (tile % g.tiles_n) * BN;
+            // this tile's bias slice goes to shared memory ONCE (while the main loop still runs): the chunk loop below then
+            // reads it with broadcast LDS instead of eight dependent global loads per 32 columns (measured: those loads,
+            // serialised behind the TMEM load, made the epilogue -- not the tensor pipe -- the pace of the whole kernel)
+            float *bias_s = reinterpret_cast<float *>(gen_base + (epi_smem - base) + 8 * 4096) + ew * BN;
+            for (int j = lane; j < BN; j += 32) bias_s[j] = (g.bias != nullptr && n0 + j < g.N) ? __ldg(g.bias + n0 + j) : 0.f;
+            __syncwarp();
+            mbar_wait(acc_full0 + 8 * buf, (tl >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * BN);
+            float4 *stage = reinterpret_cast<float4 *>(gen_base + (epi_smem - base)) + ew * 256;
+#pragma unroll 1
+            for (int c = half * 32; c < BN; c += 64) {
+                if (n0 + c >= g.N) break;
+                float v[32];
+                tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+                const int col = n0 + c;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(bias_s + c + j);
+                    float4 o = make_float4(v[j] + b4.x, v[j + 1] + b4.y, v[j + 2] + b4.z, v[j + 3] + b4.w);
+                    if (g.act == 1) {
+                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                    }
+                    stage[lane * 8 + ((j >> 2) ^ (lane & 7))] = o;
+                }
+                __syncwarp();
+                float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const int r = i + (lane >> 3), slot = lane & 7;
+                    const float4 o = stage[r * 8 + (slot ^ (r & 7))];
+                    const int grow = m0 + q * 32 + r, gcol = col + 4 * slot;
+                    if (grow < g.M && gcol < g.N) {
+                        float *dst = g.C + (int64_t)grow * g.ldc + gcol;
+                        if (vec_ok && gcol + 4 <= g.N) {
+                            *reinterpret_cast<float4 *>(dst) = o;
+                        } else {
+                            dst[0] = o.x;
+                            if (gcol + 1 < g.N) dst[1] = o.y;
+                            if (gcol + 2 < g.N) dst[2] = o.z;
+                            if (gcol + 3 < g.N) dst[3] = o.w;
+                        }
+                        cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
+                        cq.x = fmaf(o.x, o.x, cq.x); cq.y = fmaf(o.y, o.y, cq.y); cq.z = fmaf(o.z, o.z, cq.z); cq.w = fmaf(o.w, o.w, cq.w);
+                    }
+                }
+                if (g.stats != nullptr) {      // column sums over this warp's 32 rows: lanes with the same slot hold rows 8 apart
+#pragma unroll
+                    for (int off = 8; off < 32; off <<= 1) {
+                        cs.x += __shfl_xor_sync(kFull, cs.x, off); cs.y += __shfl_xor_sync(kFull, cs.y, off);
+                        cs.z += __shfl_xor_sync(kFull, cs.z, off); cs.w += __shfl_xor_sync(kFull, cs.w, off);
+                        cq.x += __shfl_xor_sync(kFull, cq.x, off); cq.y += __shfl_xor_sync(kFull, cq.y, off);
+                        cq.z += __shfl_xor_sync(kFull, cq.z, off); cq.w += __shfl_xor_sync(kFull, cq.w, off);
+                    }
+                    const int gcol = col + 4 * lane;
+                    if (lane < 8 && gcol + 4 <= g.N) {
+                        float *dst = g.stats + ((size_t)((m0 >> 5) + q) * 2) * g.N + gcol;
+                        *reinterpret_cast<float4 *>(dst) = cs;
+                        *reinterpret_cast<float4 *>(dst + g.N) = cq;
+                    }
+                }
+                __syncwarp();
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_rank(acc_empty0 + 8 * buf, 0));     // the leader's MMA warp waits for all 8
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();                                  // the single-lane roles rejoin their warps (barrier.cluster is .aligned)
+    cluster_sync_all();                            // nobody frees TMEM / exits while the peer may still touch this CTA
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN));
+    }
+}
+
+template <int BN>
+static int launch_linear_pair(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs g, cudaStream_t stream) {
+    constexpr int kSt = BN == 256 ? 5 : (BN == 128 ? 7 : 8);
+    constexpr int smem = kSt * (kTileABytes + (BN / 2) * kBK * 4) + 1024 + 256 + 8 * 4096 + 8 * BN * 4;
+    static bool configured[64] = {};
+    int dev = 0;
+    CTR_CUDA_OK(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        CTR_CUDA_OK(cudaFuncSetAttribute(linear_tf32_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured[dev & 63] = true;
+    }
+    g.tiles_m = (g.M + 2 * kBM - 1) / (2 * kBM);
+    g.tiles_n = (g.N + BN - 1) / BN;
+    const int tiles = g.tiles_m * g.tiles_n;
+    const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
+    note_launch(), linear_tf32_pair_kernel<BN><<<2 * pairs, kPairThreads, smem, stream>>>(ma, mb, g);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
 template <int BN>
 static int launch_linear(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs g, cudaStream_t stream) {
     constexpr int smem = 4 * (kTileABytes + BN * kBK * 4) + 1024 + 256 + 4 * 4096;
@@ -344,9 +585,12 @@ static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int64_t co
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
     cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
+    // L2 promotion: a box takes 128 bytes from each of its rows; asking L2 to fetch 256 bytes per request halves the DRAM
+    // transactions of the A stream (the other half is the next k-block's data) -- tuning knob CTR_TMA_L2PROMO = 128 | 256
+    static const int promo_env = getenv("CTR_TMA_L2PROMO") ? atoi(getenv("CTR_TMA_L2PROMO")) : 256;
+    const CUtensorMapL2promotion promo = promo_env == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld ld=%lld)", (int)r, (long long)rows,
                   (long long)cols, (long long)ld);
@@ -524,8 +768,29 @@ static void wgrad_plan(int B, int N, int K, int *tiles_m, int *tiles_n, int *spl
 
 using namespace ctr;
 
+static int linear_fwd_impl(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias, float *C, int64_t ldc,
+                           int32_t M, int32_t N, int32_t K, int32_t act, float *stats, void *stream);
+
 extern "C" int ctr_linear_fwd(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias, float *C,
                               int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t act, void *stream) {
+    return linear_fwd_impl(A, lda, W, ldw, bias, C, ldc, M, N, K, act, nullptr, stream);
+}
+
+// number of 32-row blocks the statistics variant writes partial sums for (0: this M takes a path without them)
+extern "C" int32_t ctr_linear_stats_blocks(int32_t M) { return M > kBM ? ((M + 2 * kBM - 1) / (2 * kBM)) * 8 : 0; }
+
+extern "C" int ctr_linear_fwd_stats(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias, float *C,
+                                    int64_t ldc, int32_t M, int32_t N, int32_t K, float *stats, int64_t stats_floats, void *stream) {
+    const int64_t blocks = ctr_linear_stats_blocks(M);
+    CTR_REQUIRE(blocks > 0, "M=%d takes the single-CTA path, which does not produce statistics", M);
+    CTR_REQUIRE(stats != nullptr && stats_floats >= blocks * 2 * N, "stats buffer too small: %lld < %lld floats", (long long)stats_floats,
+                (long long)(blocks * 2 * N));
+    CTR_REQUIRE(N % 4 == 0 && (reinterpret_cast<uintptr_t>(stats) & 15u) == 0, "statistics need N %% 4 == 0 and a 16-byte aligned buffer");
+    return linear_fwd_impl(A, lda, W, ldw, bias, C, ldc, M, N, K, 0, stats, stream);
+}
+
+static int linear_fwd_impl(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias, float *C, int64_t ldc,
+                           int32_t M, int32_t N, int32_t K, int32_t act, float *stats, void *stream) {
     CTR_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad GEMM shape M=%d N=%d K=%d", M, N, K);
     if (M == 0) return CTR_OK;
     CTR_REQUIRE(A != nullptr && W != nullptr && C != nullptr, "null pointer");
@@ -536,12 +801,19 @@ extern "C" int ctr_linear_fwd(const float *A, int64_t lda, const float *W, int64
     CTR_REQUIRE(act == 0 || act == 1, "act must be 0 (none) or 1 (relu)");
     // widest tile the output needs: fewer passes over A (one per n tile)
     const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+    static const int pair_env = getenv("CTR_GEMM_2CTA") ? atoi(getenv("CTR_GEMM_2CTA")) : 1;
+    const bool pair = (pair_env != 0 || stats != nullptr) && M > kBM;   // CTA pairs (256-row tiles) unless there is a single 128-row tile
     CUtensorMap ma, mb;
     int rc = make_map(&ma, A, M, K, lda, kBM);
     if (rc != CTR_OK) return rc;
-    rc = make_map(&mb, W, N, K, ldw, bn);
+    rc = make_map(&mb, W, N, K, ldw, pair ? bn / 2 : bn);
     if (rc != CTR_OK) return rc;
-    GemmArgs g{C, bias, ldc, M, N, K, act, 0, 0, A, lda};
+    GemmArgs g{C, bias, ldc, M, N, K, act, 0, 0, A, lda, stats};
+    if (pair) {
+        if (bn == 256) return launch_linear_pair<256>(ma, mb, g, (cudaStream_t)stream);
+        if (bn == 128) return launch_linear_pair<128>(ma, mb, g, (cudaStream_t)stream);
+        return launch_linear_pair<64>(ma, mb, g, (cudaStream_t)stream);
+    }
     if (bn == 256) return launch_linear<256>(ma, mb, g, (cudaStream_t)stream);
     if (bn == 128) return launch_linear<128>(ma, mb, g, (cudaStream_t)stream);
     return launch_linear<64>(ma, mb, g, (cudaStream_t)stream);

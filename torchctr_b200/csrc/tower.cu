@@ -100,9 +100,10 @@ __global__ void __launch_bounds__(kTowerThreads)
 // blocks j, j + kFinLanes, ... in double, the lanes are then added in lane order (fixed order: deterministic).
 constexpr int kFinCols = 16, kFinLanes = 16;
 
-template <int NQ>
+template <int NQ, int LANES = kFinLanes>
 __device__ __forceinline__ bool column_totals(const float *__restrict__ partial, int blocks, int N, double (&tot)[NQ], int *col) {
-    __shared__ double sh[NQ][kFinLanes][kFinCols];
+    __shared__ double sh[NQ][LANES][kFinCols];
+    constexpr int kFinLanes = LANES;
     const int c = threadIdx.x % kFinCols, j = threadIdx.x / kFinCols;
     const int n = blockIdx.x * kFinCols + c;
     double acc[NQ];
@@ -129,15 +130,17 @@ __device__ __forceinline__ bool column_totals(const float *__restrict__ partial,
     return true;
 }
 
-// partials -> mean, rstd (+ running statistics, torch.nn.BatchNorm1d semantics)
-__global__ void __launch_bounds__(kFinCols * kFinLanes)
+// partials -> mean, rstd (+ running statistics, torch.nn.BatchNorm1d semantics).  LANES threads share a column's partials
+// (16 for the few hundred blocks of col_stats, 64 for the 32-row blocks that come out of the GEMM epilogue).
+template <int LANES>
+__global__ void __launch_bounds__(kFinCols * LANES)
     bn_finalize_fwd_kernel(const float *__restrict__ partial, int blocks, int B, int N, float eps, float momentum,
                            float *__restrict__ mean, float *__restrict__ rstd, float *running_mean, float *running_var,
                            long long *num_batches_tracked) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
     double tot[2];
     int n;
-    if (!column_totals<2>(partial, blocks, N, tot, &n)) return;
+    if (!column_totals<2, LANES>(partial, blocks, N, tot, &n)) return;
     const double s = tot[0], ss = tot[1];
     const double m = s / B;
     double var = ss / B - m * m;
@@ -451,9 +454,22 @@ extern "C" int ctr_bn_stats(const float *z, int64_t ldz, int32_t B, int32_t N, f
     const TowerGeom g = tower_geom(B, N);
     float *partial = static_cast<float *>(workspace);
     note_launch(), col_stats_kernel<<<g.blocks, kTowerThreads, 0, stream>>>(z, ldz, g, partial);
-    note_launch(), bn_finalize_fwd_kernel<<<(N + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, stream>>>(partial, g.blocks, B, N, eps, momentum, mean, rstd,
+    note_launch(), bn_finalize_fwd_kernel<kFinLanes><<<(N + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, stream>>>(partial, g.blocks, B, N, eps, momentum, mean, rstd,
                                                                               running_mean, running_var,
                                                                               reinterpret_cast<long long *>(num_batches_tracked));
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
+// the same finalisation on partial sums that came out of the GEMM epilogue (ctr_linear_fwd_stats): [blocks][2][N]
+extern "C" int ctr_bn_stats_from_partials(const float *partial, int32_t blocks, int32_t B, int32_t N, float eps, float momentum,
+                                          float *mean, float *rstd, float *running_mean, float *running_var,
+                                          int64_t *num_batches_tracked, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CTR_REQUIRE(partial && mean && rstd && blocks >= 1 && B >= 1 && N >= 1, "bad arguments");
+    CTR_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "running_mean and running_var go together");
+    note_launch(), bn_finalize_fwd_kernel<64><<<(N + kFinCols - 1) / kFinCols, kFinCols * 64, 0, stream>>>(
+        partial, blocks, B, N, eps, momentum, mean, rstd, running_mean, running_var, reinterpret_cast<long long *>(num_batches_tracked));
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }

@@ -80,32 +80,41 @@ class GraphedTrainStep:
         for v, t in zip(self._views, tensors):               # async from pinned host memory, D2D otherwise
             v.copy_(t, non_blocking=True)
 
-    def pack(self, batch) -> torch.Tensor:
-        """One device buffer holding ``batch`` in the layout of the graph's input block: ``step(packed)`` then needs a single
-        device-to-device copy instead of one per tensor (resident data sets: pack every batch once, up front)."""
+    def pack(self, batch, device=None) -> torch.Tensor:
+        """ONE buffer holding ``batch`` in the layout of the graph's input block.  On the device (``device=None``): a resident
+        data set is packed once, and ``step(packed)`` then needs a single device-to-device copy.  ``device='cpu'``: a pinned host
+        buffer -- what a collate function that writes its features into one pinned block produces -- so that the upload of a
+        batch is ONE host-to-device copy (``prefetch(packed)``) instead of one per feature."""
         feats, labels = batch
         tensors = [feats[k] for k in self._keys] + [labels]
-        packed = torch.empty_like(self._static)
+        if device is None:
+            packed = torch.empty_like(self._static)
+        else:
+            packed = torch.empty(self._nbytes, dtype=torch.uint8, device=device, pin_memory=(str(device) == "cpu"))
         for (o, n, dt, shape), t in zip(self._layout, tensors):
             packed[o:o + n].view(dt).view(shape).copy_(t, non_blocking=True)
         return packed
 
     def prefetch(self, batch) -> None:
-        """Start copying ``batch`` (pinned host tensors) to the device on a copy stream while the current step runs.  The next
-        ``__call__(batch)`` with the same batch object then only does one device-to-device move into the graph's input
-        buffers.  What a DataLoader's prefetching does for the reference loop (``torchctr/trainer.py:291``), one level down."""
+        """Start copying ``batch`` (pinned host tensors, or one pinned buffer made by ``pack(batch, 'cpu')``) to the device on a
+        copy stream while the current step runs.  The next ``__call__(batch)`` with the same batch object then only does one
+        device-to-device move into the graph's input buffers.  What a DataLoader's prefetching does for the reference loop
+        (``torchctr/trainer.py:291``), one level down."""
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._staging = torch.empty_like(self._static)
             self._staging_views = [self._staging[o:o + n].view(dt).view(shape) for o, n, dt, shape in self._layout]
-        feats, labels = batch
-        tensors = [feats[k] for k in self._keys] + [labels]
         cs = self._copy_stream
         if self._moved is not None:
             cs.wait_event(self._moved)          # only the previous staging -> static move, NOT the step that is running now
         with torch.cuda.stream(cs):
-            for v, t in zip(self._staging_views, tensors):
-                v.copy_(t, non_blocking=True)
+            if torch.is_tensor(batch):
+                self._staging.copy_(batch, non_blocking=True)
+            else:
+                feats, labels = batch
+                tensors = [feats[k] for k in self._keys] + [labels]
+                for v, t in zip(self._staging_views, tensors):
+                    v.copy_(t, non_blocking=True)
         self._prefetched = batch
 
     _copy_stream = None

@@ -68,6 +68,15 @@ def gemm_nt(a: torch.Tensor, w: torch.Tensor, bias=None, act: int = 0, out=None,
     return ops.linear_fwd(a, w, bias, act, out=out)
 
 
+def gemm_nt_bn_stats(a, w, bias, bn, precision: str = "tf32"):
+    """``z = a @ w.T + bias`` plus the BatchNorm1d batch statistics of ``z`` from the GEMM epilogue -> (z, mean, rstd) or None."""
+    track = bn.track_running_stats and bn.running_mean is not None
+    rm, rv, nbt = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if track else (None, None, None)
+    if precision == "tf32x3":
+        a, w = ops.split_tf32(a, 1, 0), ops.split_tf32(w, 1, 1)
+    return ops.linear_fwd_bn_stats(a, w, bias, bn.eps, bn.momentum, rm, rv, nbt)
+
+
 def gemm_wgrad(g: torch.Tensor, x: torch.Tensor, precision: str = "tf32") -> torch.Tensor:
     """``g.T @ x`` -> [N, K] on tcgen05: g [B, N], x [B, K]."""
     if precision == "tf32x3":      # the split pads the rows to a multiple of 4 floats: hand the kernel views of the real width

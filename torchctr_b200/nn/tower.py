@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .linear import gemm_nt, gemm_wgrad, matmul_precision, tc_eligible, wgrad_eligible
+from .linear import gemm_nt, gemm_nt_bn_stats, gemm_wgrad, matmul_precision, tc_eligible, wgrad_eligible
 
 
 class _TowerBlockFn(torch.autograd.Function):
@@ -23,10 +23,14 @@ class _TowerBlockFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, gamma, beta, bn, p_drop, seed_dev, layer_id, precision, gx_provider=None):
         w = weight.contiguous()
         tc = tc_eligible(x, w, precision)
-        z = gemm_nt(x, w, bias, precision=precision) if tc else torch.addmm(bias, x, w.t())
-        track = bn.track_running_stats and bn.running_mean is not None
-        mean, rstd = ops.bn_stats(z, bn.eps, bn.momentum, bn.running_mean if track else None,
-                                  bn.running_var if track else None, bn.num_batches_tracked if track else None)
+        fused = gemm_nt_bn_stats(x, w, bias, bn, precision) if tc else None    # statistics out of the GEMM epilogue
+        if fused is not None:
+            z, mean, rstd = fused
+        else:
+            z = gemm_nt(x, w, bias, precision=precision) if tc else torch.addmm(bias, x, w.t())
+            track = bn.track_running_stats and bn.running_mean is not None
+            mean, rstd = ops.bn_stats(z, bn.eps, bn.momentum, bn.running_mean if track else None,
+                                      bn.running_var if track else None, bn.num_batches_tracked if track else None)
         y = ops.bn_relu_dropout_fwd(z, mean, rstd, gamma, beta, p_drop, seed_dev, layer_id)
         ctx.save_for_backward(x, w, z, mean, rstd, gamma, beta)
         ctx.meta = (p_drop, seed_dev, layer_id, tc, precision)

@@ -542,6 +542,30 @@ def split_tf32(x: torch.Tensor, axis: int, role: int) -> torch.Tensor:
     return out
 
 
+@_guarded
+def linear_fwd_bn_stats(A, W, bias, eps: float, momentum: float, running_mean=None, running_var=None, num_batches_tracked=None):
+    """z = A @ W.T + bias together with the BatchNorm batch statistics of z, which come out of the GEMM epilogue
+    (``ctr_linear_fwd_stats`` + ``ctr_bn_stats_from_partials``) -> (z, mean [N], rstd [N]); None when this M has no such path."""
+    M, K = A.shape
+    N = W.shape[0]
+    blocks = int(_lib.lib().ctr_linear_stats_blocks(M))
+    if blocks == 0 or N % 4:
+        return None
+    dev = A.device
+    z = torch.empty(M, N, dtype=torch.float32, device=dev)
+    stats = torch.empty(blocks * 2 * N, dtype=torch.float32, device=dev)
+    mean = torch.empty(N, dtype=torch.float32, device=dev)
+    rstd = torch.empty(N, dtype=torch.float32, device=dev)
+    with _timed("linear_fwd"):
+        _lib.check(_lib.lib().ctr_linear_fwd_stats(A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), _lib.ptr(bias), z.data_ptr(),
+                                                   z.stride(0), M, N, K, stats.data_ptr(), stats.numel(), _stream(A)), "ctr_linear_fwd_stats")
+    with _timed("bn_stats"):
+        _lib.check(_lib.lib().ctr_bn_stats_from_partials(stats.data_ptr(), blocks, M, N, eps, momentum, mean.data_ptr(), rstd.data_ptr(),
+                                                         _lib.ptr(running_mean), _lib.ptr(running_var), _lib.ptr(num_batches_tracked),
+                                                         _stream(A)), "ctr_bn_stats_from_partials")
+    return z, mean, rstd
+
+
 # ---- row-sharded tables over peer memory -----------------------------------------------------------------------
 def ptr_array(ptrs):
     """ctypes array of device pointers (one per rank)."""
