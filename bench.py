@@ -50,6 +50,12 @@ CONFIGS = {
                  workload="BASELINE configs[3]: DNN over 16 hashed tables totalling {rows} rows x dim 64 (raw 31-bit Zipf(1.05) ids, "
                           "murmur3 bucketing inside the lookup / update kernels), tables created shard by shard (never replicated), "
                           "tower 256-128-64, Adagrad"),
+    # configs[4]: variable-length sequence pooling (<= 200 ids / row, Zipf keys from an unbounded key space) with a vocabulary
+    # that grows while training (fresh keys every step); eager launches (the table size is read on the host every step)
+    "cfg5": dict(model="dnn", vocabs=[], dim=16, num_dense=4, seq=dict(vocab=1, maxlen=200, growing=True), batch=2048,
+                 workload="BASELINE configs[4]: DNN over one sequence feature (<= 200 ids per row, Zipf(1.05) keys from an unbounded "
+                          "key space, fresh keys every step) pooled through a vocabulary that grows while training, emb dim 16, "
+                          "tower 256-128-64, Adagrad; eager launches"),
     # configs[0]: the reference's own CPU-runnable case, DNN under the unmodified reference Trainer
     "cfg1": dict(model="dnn", vocabs=AMAZON_VOCABS, dim=16, num_dense=4, seq=dict(vocab=500_000, maxlen=50), batch=4096,
                  workload="BASELINE configs[0]: DNN, Amazon-review-shaped: 8 categorical ({rows} rows total) + 1 item sequence "
@@ -65,7 +71,8 @@ def get_cfg(name, rows_log2=None):
     cfg["rows"] = sum(cfg["vocabs"]) + (cfg["seq"]["vocab"] if cfg["seq"] else 0)
     cfg["workload"] = cfg["workload"].format(rows=cfg["rows"])
     cfg["metric"] = {"cfg2": "train samples/s, Criteo-shape DeepFM", "cfg3": "train samples/s, Criteo-shape DCN-v2",
-                     "cfg1": "train samples/s, Amazon-shape DNN", "cfg4": "train samples/s, DNN over row-sharded hashed tables"}[name]
+                     "cfg1": "train samples/s, Amazon-shape DNN", "cfg4": "train samples/s, DNN over row-sharded hashed tables",
+                     "cfg5": "train samples/s, sequence pooling with a growing vocabulary"}[name]
     return cfg
 
 
@@ -75,7 +82,10 @@ def feat_configs(cfg):
         for i, c in enumerate(fc):                      # raw ids in the batch; row = murmur3_32(str(id), seed) % hash_buckets
             c.update(raw_ids=True, hash_buckets=c["num_embeddings"], seed=i)
     if cfg["seq"]:
-        fc.append({"name": "hist", "type": "sparse", "num_embeddings": cfg["seq"]["vocab"], "emb_dim": cfg["dim"], "islist": True})
+        c = {"name": "hist", "type": "sparse", "num_embeddings": cfg["seq"]["vocab"], "emb_dim": cfg["dim"], "islist": True}
+        if cfg["seq"].get("growing") and not cfg.get("_oracle_rows"):
+            c.update(raw_ids=True, vocab_capacity=1 << 27, vocab_max_rows=1 << 26)      # keys in the batch, rows assigned on the device
+        fc.append(c)
     fc += [{"name": f"I{i + 1}", "type": "dense"} for i in range(cfg["num_dense"])]
     return fc
 
@@ -102,8 +112,10 @@ def make_batch(cfg, seed, B, pin=False):
             feats[f"C{i + 1}"] = zipf_ids(gen, B, V).reshape(B, 1)
     if cfg["seq"]:
         L = cfg["seq"]["maxlen"]
-        ids = zipf_ids(gen, B * L, cfg["seq"]["vocab"]).reshape(B, L)
-        lens = torch.randint(0, L + 1, (B, 1), generator=gen)
+        ids = zipf_ids(gen, B * L, 10 ** 6 if cfg["seq"].get("growing") else cfg["seq"]["vocab"]).reshape(B, L)
+        if cfg["seq"].get("growing"):
+            ids = ids * 31                                # raw keys; eager_step shifts them by the step number (fresh keys every step)
+        lens = torch.randint(0 if not cfg["seq"].get("growing") else 1, L + 1, (B, 1), generator=gen)
         ids[torch.arange(L)[None, :] >= lens] = -100                 # the collate's padding (torchctr/dataset.py:9)
         feats["hist"] = ids
     feats["dense_features"] = torch.randn(B, cfg["num_dense"], generator=gen)
@@ -206,6 +218,11 @@ def cpu_reference_run(cfg, steps, warmup, B, budget_s):
     kind = "port"
     torch.manual_seed(0)
     model = None
+    if cfg["seq"] and cfg["seq"].get("growing"):
+        # the reference has no growing table inside a model (DynamicEmbedding is not wired into DNN, models/dnn.py:7,22): the CPU
+        # leg uses a table of fixed size (2^20 rows) indexed by keys folded into it, dense autograd + dense Adagrad as upstream
+        cfg = dict(cfg, seq=dict(cfg["seq"], vocab=1 << 20, growing=False), _oracle_rows=True)
+        cfg["rows"] = 1 << 20
     if cfg.get("hashed"):
         # a dense [V, D] table + gradient + Adagrad state of 2^30 x 64 does not exist on any host: the CPU leg runs the same
         # arithmetic on tables bounded to 2^24 rows in total (the bucketing is done on the host, as the reference does)
@@ -465,6 +482,8 @@ def run_ours(args):
     model = build_model(cfg, table_device="meta" if native else None)      # identical on every rank (same seed)
     if world > 1:
         dedup = {"auto": None, "on": True, "off": False}[args.dedup]
+        if cfg["seq"] and cfg["seq"].get("growing"):
+            dedup = False                                 # growing vocabularies run the direct exchange
         model = shard_model(model, None, device=dev, dedup=dedup, init_seed=0)   # this rank's rows of every table only
     elif native:
         model.materialize_tables(dev, seed=0)
@@ -480,7 +499,17 @@ def run_ours(args):
     resident = [({k: v.to(dev) for k, v in f.items()}, l.to(dev)) for f, l in host]
     h2d = batch_bytes(host[0])
 
+    growing = bool(cfg["seq"] and cfg["seq"].get("growing"))
+    step_no = [0]
+
     def eager_step(batch, i):
+        if growing:                                     # a fresh key range every step: the vocabulary (and the table) keeps growing
+            feats, labels = batch
+            h = feats["hist"]
+            step_no[0] += 1
+            # (256 distinct key ranges, then they repeat: growth is bounded to ~25 M rows however long the run is)
+            feats = dict(feats, hist=torch.where(h >= 0, h + (step_no[0] % 256) * 10 ** 9 + 1, h))
+            batch = (feats, labels)
         if world > 1:
             model.zero_dense_grads()
         else:
@@ -526,7 +555,7 @@ def run_ours(args):
         return
     graphed_holder = [None]
     packed = host_packed = None
-    if args.no_graph:
+    if args.no_graph or growing:
         step = eager_step
     else:
         from torchctr_b200.graph import GraphedTrainStep
@@ -612,7 +641,7 @@ def run_ours(args):
     # the same step with the tower GEMMs in the exact mode (3xTF32 on the same tcgen05 kernels): the configuration the
     # 1e-5 parity tests run in, timed the same way
     exact = None
-    if world == 1 and args.precision == "tf32" and not args.no_graph and not args.no_exact:
+    if world == 1 and args.precision == "tf32" and not args.no_graph and not args.no_exact and not growing:
         from torchctr_b200.graph import GraphedTrainStep
         set_matmul_precision("tf32x3")
         graphed_x3 = GraphedTrainStep(model, opt, resident[0], warmup=1)
@@ -627,7 +656,18 @@ def run_ours(args):
 
     # ---- kernel roofline: each embedding entry point timed alone, CUDA events on the launching stream,
     # L2 flushed (1 GiB written) before every launch, on the step's real tensors
-    kern, roofline, dom = kernel_roofline(cfg, model, resident, B, dev) if (rank == 0 and world == 1) else ({}, None, None)
+    kern, roofline, dom = kernel_roofline(cfg, model, resident, B, dev) if (rank == 0 and world == 1 and not growing) else ({}, None, None)
+    if growing and rank == 0 and "emb_pool_fwd_d16" in in_step:
+        # the vocabulary changes every step, so the lookup is timed inside the step only: 8S ids + 4DN rows + 4DB pooled output
+        feats0 = resident[0][0]
+        S_, N_ = feats0["hist"].numel(), int((feats0["hist"] >= 0).sum())
+        nbytes = 8 * S_ + 4 * cfg["dim"] * N_ + 4 * cfg["dim"] * B
+        us = in_step["emb_pool_fwd_d16"]["us_per_step"]
+        peak, peak_src = measured_peak_hbm()
+        roofline = {"bound": "hbm", "kernel": "emb_pool_fwd (vocabulary probe + gather + sum pool of <= 200 ids per row, D=16)",
+                    "achieved": nbytes / (us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s", "frac": nbytes / (us * 1e-6) / 1e9 / peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": us / 1e3,
+                    "timing": "CUDA events around the launch inside the eager step (behind a device-side sleep)"}
     if roofline is not None:
         # the same kernel inside the real step (caches as the step leaves them): CUDA events, eager step behind a device sleep
         name = dom + f"_d{cfg['dim']}" if dom != "emb_bwd_plan" else dom

@@ -288,3 +288,91 @@ def test_sharded_deepfm_model_forward_and_full_state_dict():
     assert not errors, errors
     for r in range(world):
         assert _close(out[r], expect), r
+
+
+def _vocab_rank(rank, world, shared, keys_all, ids_all, gouts, D, errors, report):
+    try:
+        from oracle import embedding as oe
+        from oracle.vocab import Vocab
+        from torchctr_b200.nn import VocabIndex
+        from torchctr_b200.nn.embedding import EmbeddingTable
+        from torchctr_b200.parallel.peer import PeerShardedTables, ThreadTransport
+        dev = torch.device("cuda", 0)
+        tr = ThreadTransport(shared, rank, dev)
+        torch.manual_seed(0)
+        seq = EmbeddingTable(1, D, index_kind="vocab", vocab=VocabIndex(capacity=256))         # one row so far: OOV
+        seq.vocab_max_rows = 4096
+        cat = EmbeddingTable(50, D)
+        st = PeerShardedTables(["seq", "cat"], [[seq, cat]], tr, dev, init_seed=7).train()
+        opt = torch.optim.SGD(list(st.shards), lr=0.5)
+        st.bind_optimizer(opt, kind="sgd")
+        ref_vocab = Vocab()
+        full_seq = st.export_full_tables(0)[0].clone()                   # [1, D]
+        full_cat = st.export_full_tables(0)[1].clone()
+        for step in range(len(keys_all)):
+            feats = {"seq": keys_all[step][rank], "cat": ids_all[step][rank]}
+            st.grow_vocabularies(feats)                                  # collective: the GLOBAL batch's new keys, rank order
+            glob = torch.cat([keys_all[step][r] for r in range(world)], 0).numpy()
+            n = ref_vocab.fit(glob[glob >= 0])
+            assert st.live_rows[0] == n, (st.live_rows[0], n)
+            exported = st.export_full_tables(0)[0]
+            assert exported.shape == (n, D)
+            assert torch.equal(exported[:full_seq.shape[0]], full_seq)   # existing rows untouched by growth
+            grown = exported[full_seq.shape[0]:]
+            if grown.numel():
+                assert 0.003 < float(grown.std()) < 0.03                 # N(0, 0.01), as DynamicEmbedding draws new rows
+            full_seq = exported.clone()
+            rows = {r: torch.from_numpy(ref_vocab.transform(keys_all[step][r].numpy())).long() for r in range(world)}
+            for r in range(world):
+                rows[r][keys_all[step][r] < 0] = -100
+            x, = st._forward([feats["seq"].to(dev), feats["cat"].to(dev)], None)
+            ref_x = torch.cat([oe.pooled_lookup(rows[rank], full_seq), oe.pooled_lookup(ids_all[step][rank], full_cat)], 1)
+            assert _close(x[:, :2 * D], ref_x), f"forward step {step}"
+            g = gouts[step][rank]
+            st._backward((g.to(dev),))
+            torch.cuda.synchronize()
+            dg_seq = sum(oe.dense_table_grad(rows[r], gouts[step][r][:, :D], n) for r in range(world))
+            dg_cat = sum(oe.dense_table_grad(ids_all[step][r], gouts[step][r][:, D:2 * D], 50) for r in range(world))
+            full_seq = full_seq - 0.5 * dg_seq
+            full_cat = full_cat - 0.5 * dg_cat
+            got = st.export_full_tables(0)
+            assert _close(got[0], full_seq) and _close(got[1], full_cat), f"update step {step}"
+            full_seq, full_cat = got[0].clone(), got[1].clone()
+        report[rank] = st.live_rows[0]
+    except BaseException as e:          # noqa: BLE001
+        errors.append((rank, repr(e)[:700]))
+        try:
+            shared.barrier.abort()
+        except Exception:
+            pass
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_growing_vocabulary(world):
+    """BASELINE config 5 at N > 1: a variable-length sequence feature over an unbounded key space, pooled through a vocabulary
+    that grows while training, with the table row-sharded.  The key -> row map is replicated and fitted on the all-gathered
+    global batch, so rows are bit-exact those of ``oracle.vocab`` on the concatenated batch (transformer.py:451-498); grown
+    rows appear on their owners only; pooled vectors and the SGD update match the single-table oracle."""
+    from torchctr_b200.parallel.peer import ThreadTransport
+    gen = torch.Generator().manual_seed(9)
+    B, L, D, steps = 96, 7, 16, 3
+    keys_all, ids_all, gouts = [], [], []
+    for step in range(steps):
+        ks, ids, gs = [], [], []
+        for r in range(world):
+            k = torch.randint(0, 400, (B, L), generator=gen) * 7919 + step * 10 ** 6      # fresh key range every step + repeats
+            k[:, 0] = torch.randint(0, 5, (B,), generator=gen) * 7919                       # hot keys shared by all ranks
+            k[torch.rand(B, L, generator=gen) < 0.3] = -100
+            ks.append(k)
+            ids.append(torch.randint(0, 50, (B, 1), generator=gen))
+            gs.append(torch.randn(B, 2 * D, generator=gen))
+        keys_all.append(ks); ids_all.append(ids); gouts.append(gs)
+    shared = ThreadTransport.Shared(world)
+    errors, report = [], {}
+    threads = [threading.Thread(target=_vocab_rank, args=(r, world, shared, keys_all, ids_all, gouts, D, errors, report)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=240)
+    assert not errors, errors
+    assert len(set(report.values())) == 1 and report[0] > 300

@@ -57,6 +57,13 @@ def table_from_config(cfg, device=None) -> EmbeddingTable:
             kind = "vocab"
             vocab = VocabIndex(capacity=cfg.get("vocab_capacity", 1 << 16), min_freq=cfg.get("min_freq", 0))
     kw = {} if device is None else {"device": device}
+    t = _make_table(cfg, kind, vocab, kw)
+    if kind == "vocab":
+        t.vocab_max_rows = int(cfg.get("vocab_max_rows", 1 << 20))      # row capacity of the table when it is row-sharded
+    return t
+
+
+def _make_table(cfg, kind, vocab, kw) -> EmbeddingTable:
     return EmbeddingTable(cfg["num_embeddings"], cfg["emb_dim"], pooling=cfg.get("pooling", "sum"), index_kind=kind,
                           hash_seed=cfg.get("seed", 0), vocab=vocab, use_id_weight=bool(cfg.get("use_weight", False)), **kw)
 
@@ -241,7 +248,12 @@ class CTRModelBase(nn.Module):
         return seed.clone()
 
     def _grow_vocabularies(self, feats):
-        if not self.training or self._sharded is not None:
+        if not self.training:
+            return
+        if self._sharded is not None:
+            grow = getattr(self._sharded, "grow_vocabularies", None)
+            if grow is not None and any(v is not None for v in getattr(self._sharded, "vocabs", [])):
+                grow(feats)
             return
         for name in self._names:
             table = self.embeddings[name]

@@ -109,6 +109,12 @@ class IpcTransport:
         dist.all_gather_object(out, obj, group=self.pg)
         return out
 
+    def all_gather_tensor(self, t: torch.Tensor) -> torch.Tensor:
+        """[n, ...] on every rank (same shape) -> [world * n, ...] in rank order (NCCL all-gather on the current stream)."""
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.pg)
+        return out
+
 
 class ThreadTransport:
     """Test transport: the ranks are threads of one process on ONE device; 'peer' pointers are plain device pointers."""
@@ -137,6 +143,10 @@ class ThreadTransport:
     def barrier(self):
         torch.cuda.synchronize(self.device)
         self.shared.barrier.wait()
+
+    def all_gather_tensor(self, t: torch.Tensor) -> torch.Tensor:
+        torch.cuda.synchronize(self.device)
+        return torch.cat(self.all_gather_object(t), 0)
 
     def all_gather_object(self, obj):
         key = ("obj", self._seq)
@@ -223,12 +233,20 @@ class PeerShardedTables(nn.Module):
         self.names = list(names)
         self.num_features = len(self.names)
         first = full_tables[0]
-        self.num_rows = [int(t.num_embeddings) for t in first]
+        # Vocabulary-indexed tables GROW while training (torchctr/transformer.py:451-498): their shard geometry is laid out for
+        # a fixed row capacity (``vocab_max_rows``) and ``live_rows`` says how many rows exist so far.  The key -> row map is
+        # REPLICATED: every step the ranks all-gather their batch keys and each fits the same global key sequence (rank 0's
+        # keys first), so all maps agree and the rows are exactly those a single process assigns to the global batch.
         self.index_kinds = [t.index_kind for t in first]
+        self.vocabs = [t.vocab if t.index_kind == "vocab" else None for t in first]
+        self.live_rows = [int(t.num_embeddings) for t in first]
+        self.num_rows = [int(getattr(t, "vocab_max_rows", 0) or (1 << 20)) if t.index_kind == "vocab" else int(t.num_embeddings)
+                         for t in first]
         self.hash_seeds = [t.hash_seed for t in first]
+        self._grow_seed = torch.initial_seed() if init_seed is None else init_seed
         for t in first:
-            if t.pooling != "sum" or t.use_id_weight or t.index_kind == "vocab":
-                raise NotImplementedError("sharded lookup: sum pooling, direct / hashed ids")
+            if t.pooling != "sum" or t.use_id_weight:
+                raise NotImplementedError("sharded lookup: sum pooling without per-id weights")
         self.dims = [int(tabs[0].embedding_dim) for tabs in full_tables]
         self.base, self.total, adj = shard_geometry(self.num_rows, self.world)
         self.register_buffer("adj", adj.to(dev), persistent=False)
@@ -246,7 +264,12 @@ class PeerShardedTables(nn.Module):
                 fr, n = owned_rows(self.num_rows[f], f, self.rank, self.world)
                 if n:
                     b = self.base[self.rank][f]
-                    if t.weight.is_meta:
+                    if self.index_kinds[f] == "vocab":       # the rows that exist so far; the rest of the capacity is filled as it grows
+                        live = self.live_rows[f]
+                        cnt = 0 if fr >= live else (live - fr + self.world - 1) // self.world
+                        if cnt and not t.weight.is_meta:
+                            w[b:b + cnt] = t.weight.detach()[fr:live:self.world].to(dev)
+                    elif t.weight.is_meta:
                         # shard-native: this rank draws ITS rows of the table with the counter-based generator; no rank ever
                         # holds the full table (BASELINE config 4: 2^30 rows x 64 floats = 256 GiB)
                         ops.normal_fill_rows_strided(w, b, n, 0.0, init_std, EmbeddingTable.counter_seed(seed0, f, wi), fr, self.world)
@@ -255,6 +278,7 @@ class PeerShardedTables(nn.Module):
             self._shard_bufs.append(buf)
             self.shards.append(nn.Parameter(w, requires_grad=True))
             self._table_ptrs.append(ops.ptr_array(transport.share(buf)))
+        self.vocab_modules = nn.ModuleList([v for v in self.vocabs if v is not None]).to(dev)   # checkpointed with the model
         self.opt_state0 = [None] * len(self.dims)
         self.opt_state1 = [None] * len(self.dims)
         self.bindings = [None] * len(self.dims)
@@ -340,8 +364,38 @@ class PeerShardedTables(nn.Module):
 
     def _request_specs(self, ids_list, w):
         D = self.dims[w]
-        return [ops.FeatureSpec(ids=ids, table=None, num_rows=v, D=D, out_col=f * D, index_kind=k, hash_seed=s)
-                for f, (ids, v, k, s) in enumerate(zip(ids_list, self.num_rows, self.index_kinds, self.hash_seeds))]
+        return [ops.FeatureSpec(ids=ids, table=None, num_rows=v, D=D, out_col=f * D, index_kind=k, hash_seed=s,
+                                vocab=None if vo is None else vo.handle())
+                for f, (ids, v, k, s, vo) in enumerate(zip(ids_list, self.num_rows, self.index_kinds, self.hash_seeds, self.vocabs))]
+
+    def grow_vocabularies(self, feats, std: float = 0.01) -> None:
+        """Collective, once per training step before ``forward``: admit the new keys of the GLOBAL batch into the
+        (replicated) vocabularies and create the rows they got -- N(0, std) from the counter-based generator keyed by the
+        global row, as ``DynamicEmbedding`` draws them (``torchctr/nn/embedding.py:74-78``) -- on the ranks that own them."""
+        from ..nn.embedding import EmbeddingTable
+        for f, (name, vo) in enumerate(zip(self.names, self.vocabs)):
+            if vo is None:
+                continue
+            keys = feats[name].to(self.device, dtype=torch.int64, non_blocking=True).contiguous()
+            vo.fit(self.transport.all_gather_tensor(keys.reshape(keys.shape[0], -1)))
+            n = vo.num_embeddings()
+            if int(vo._last_status.item()) & _lib.STATUS_MAP_FULL:
+                raise RuntimeError("vocabulary map overflow")
+            if n > self.num_rows[f]:
+                raise RuntimeError(f"table {name!r} outgrew its sharded capacity of {self.num_rows[f]} rows (vocab_max_rows)")
+            old = self.live_rows[f]
+            if n > old:
+                for wi in range(len(self.dims)):
+                    # rows r in [old, n) with (r + f) % world == rank, i.e. r = first_owned + k * world
+                    fr, _ = owned_rows(self.num_rows[f], f, self.rank, self.world)
+                    k0 = 0 if old <= fr else (old - fr + self.world - 1) // self.world
+                    k1 = 0 if n <= fr else (n - fr + self.world - 1) // self.world
+                    if k1 > k0:
+                        b = self.base[self.rank][f]
+                        ops.normal_fill_rows_strided(self.shards[wi].data, b + k0, k1 - k0, 0.0, std,
+                                                     EmbeddingTable.counter_seed(self._grow_seed, f, wi), fr + k0 * self.world, self.world)
+                self.live_rows[f] = n
+        self.transport.barrier()
 
     def _owner_specs(self, ids_list, w, with_state, dedup=False):
         D = self.dims[w]
@@ -552,7 +606,7 @@ class PeerShardedTables(nn.Module):
                 fr, n = owned_rows(v, f, r, self.world)
                 if n:
                     t[fr::self.world] = parts[r][f]
-            full.append(t)
+            full.append(t[:self.live_rows[f]] if self.vocabs[f] is not None else t)     # a growing table: the rows that exist
         return full
 
     def export_full_optimizer_state(self, w: int = 0):
@@ -604,11 +658,15 @@ class PeerShardedTables(nn.Module):
         this rank's shard.  Every rank calls it with the same tensors; optimizer state of the width is reset."""
         with torch.no_grad():
             for f, t in enumerate(full):
-                if tuple(t.shape) != (self.num_rows[f], self.dims[w]):
+                growing = self.vocabs[f] is not None
+                if t.shape[1] != self.dims[w] or (t.shape[0] != self.num_rows[f] and not (growing and t.shape[0] <= self.num_rows[f])):
                     raise ValueError(f"table {f}: expected {(self.num_rows[f], self.dims[w])}, got {tuple(t.shape)}")
                 fr, rows = self.local_rows_of(w, f)
-                if rows.shape[0]:
-                    rows.copy_(t[fr::self.world].to(self.device))
+                src = t[fr::self.world].to(self.device)
+                if src.shape[0]:
+                    rows[:src.shape[0]].copy_(src)
+                if growing:
+                    self.live_rows[f] = int(t.shape[0])
         self.opt_state0[w] = None
         self.opt_state1[w] = None
         self.transport.barrier()
