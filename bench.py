@@ -668,7 +668,7 @@ def run_ours(args):
                     "achieved": nbytes / (us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s", "frac": nbytes / (us * 1e-6) / 1e9 / peak,
                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": us / 1e3,
                     "timing": "CUDA events around the launch inside the eager step (behind a device-side sleep)"}
-    if roofline is not None:
+    if roofline is not None and dom is not None:
         # the same kernel inside the real step (caches as the step leaves them): CUDA events, eager step behind a device sleep
         name = dom + f"_d{cfg['dim']}" if dom != "emb_bwd_plan" else dom
         if name in in_step:

@@ -131,8 +131,9 @@ class CTRModelBase(nn.Module):
         out = {}
         for name, m in self.named_modules():
             if isinstance(m, EmbeddingTable) and m._state_owner is None and m._opt_state0 is not None:
-                out[name] = {"state0": m._opt_state0.detach().clone(),
-                             "state1": None if m._opt_state1 is None else m._opt_state1.detach().clone()}
+                n = m.num_embeddings                                  # (the buffers may be sized for the table's reservation)
+                out[name] = {"state0": m._opt_state0.detach()[:n].clone(),
+                             "state1": None if m._opt_state1 is None else m._opt_state1.detach()[:n].clone()}
         return out
 
     def load_table_optimizer_state_dict(self, state):

@@ -71,16 +71,18 @@ class EmbeddingTable(nn.Embedding):
             self._state_owner = (optimizer, keys)
             self._opt_kind = kind
             return
+        store = getattr(self, "_store", None)
+        rows = store.shape[0] if store is not None and store.data_ptr() == w.data_ptr() else w.shape[0]
         if kind in ("adagrad", "adam") and getattr(self, "_opt_state0", None) is None:
-            self._opt_state0 = torch.full_like(w.data, initial_accumulator_value if kind == "adagrad" else 0.0)
+            self._opt_state0 = torch.full((rows, w.shape[1]), initial_accumulator_value if kind == "adagrad" else 0.0, device=w.device)
         if kind == "rowwise_adagrad" and getattr(self, "_opt_state0", None) is None:
-            self._opt_state0 = torch.full((w.shape[0],), initial_accumulator_value, device=w.device)
+            self._opt_state0 = torch.full((rows,), initial_accumulator_value, device=w.device)
         if kind == "adam" and getattr(self, "_opt_state1", None) is None:
-            self._opt_state1 = torch.zeros_like(w.data)
-        for name in ("_opt_state0", "_opt_state1"):          # follow the table if it grew / moved
-            buf = getattr(self, name, None)
-            if buf is not None and (buf.shape[0] != w.shape[0] or buf.device != w.device):
-                new = torch.zeros((w.shape[0],) + tuple(buf.shape[1:]), device=w.device)
+            self._opt_state1 = torch.zeros((rows, w.shape[1]), device=w.device)
+        for name in ("_opt_state0", "_opt_state1"):          # follow the table if it grew / moved: sized like its reservation,
+            buf = getattr(self, name, None)                   # so that growth inside it costs nothing here either
+            if buf is not None and (buf.shape[0] < w.shape[0] or buf.device != w.device):
+                new = torch.zeros((rows,) + tuple(buf.shape[1:]), device=w.device)
                 n = min(buf.shape[0], w.shape[0])
                 new[:n] = buf[:n].to(w.device)
                 setattr(self, name, new)
@@ -138,7 +140,9 @@ class EmbeddingTable(nn.Embedding):
         w = self.weight
         store = getattr(self, "_store", None)
         if store is None or store.data_ptr() != w.data_ptr() or store.shape[0] < new_num_embeddings:
-            cap = max(new_num_embeddings, old + old // 2 + 1024)
+            # reserve once: the configured row capacity (vocab_max_rows, when the table belongs to a growing vocabulary) or
+            # 1.5x -- growth inside the reservation neither reallocates nor copies, it only fills the new rows
+            cap = max(new_num_embeddings, old + old // 2 + 1024, int(getattr(self, "vocab_max_rows", 0) or 0))
             store = torch.empty(cap, self.embedding_dim, dtype=w.dtype, device=w.device)
             store[:old] = w.data
             self._store = store
