@@ -317,6 +317,16 @@ int ctr_logit_bce_bwd(const float *h, int64_t ldh, int32_t B, int32_t H, const f
                       const float *gscale, float *gh, int64_t ldgh, float *gw, float *gb, float *gextra,
                       int64_t gextra_stride, void *workspace, void *stream);
 
+/* The same with a second linear term folded in: z += xe[b, :ne] . we + be (ne <= 32) -- DeepFM's Linear(Nd, 1) over the dense
+ * features -- and its weight gradient gwe[ne] (its bias gradient equals gb). */
+int ctr_logit_bce_fwd_ex(const float *h, int64_t ldh, int32_t B, int32_t H, const float *w, const float *bias, const float *extra,
+                         int64_t extra_stride, const float *xe, int64_t ldxe, int32_t ne, const float *we, const float *be,
+                         const float *labels, int64_t label_stride, float *logits, float *dz, float *loss, void *workspace,
+                         void *stream);
+int ctr_logit_bce_bwd_ex(const float *h, int64_t ldh, int32_t B, int32_t H, const float *w, const float *dz, const float *gscale,
+                         float *gh, int64_t ldgh, float *gw, float *gb, float *gextra, int64_t gextra_stride, const float *xe,
+                         int64_t ldxe, int32_t ne, float *gwe, void *workspace, void *stream);
+
 /* torch.optim.Adagrad (lr_decay = 0, weight_decay = 0) over `count` <= 48 dense fp32 tensors in ONE launch:
  * sum += g*g; p -= lr * g / (sqrt(sum) + eps).  params / grads / sums / sizes are HOST arrays of device pointers / sizes. */
 int ctr_dense_adagrad(int32_t count, float *const *params, const float *const *grads, float *const *sums,

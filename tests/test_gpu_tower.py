@@ -130,6 +130,30 @@ def test_logit_bce_head_matches_torch(B, H, with_extra):
             _close(g, r, rtol=2e-5)
 
 
+@pytest.mark.parametrize("B,H,ne", [(65536, 64, 13), (999, 32, 32), (300, 128, 1)])
+def test_logit_bce_head_second_linear_term(B, H, ne):
+    """The head with DeepFM's Linear(Nd, 1) over the dense block folded in vs torch ops."""
+    import torch.nn.functional as F
+    from torchctr_b200.nn.head import logit_bce, second_term_eligible
+    gen = torch.Generator().manual_seed(B + H + ne)
+    h = torch.randn(B, H, generator=gen).cuda().requires_grad_(True)
+    lin, lin_e = nn.Linear(H, 1).cuda(), nn.Linear(ne, 1).cuda()
+    extra = (torch.randn(B, 1, generator=gen) * 2).cuda().requires_grad_(True)
+    xe = torch.randn(B, ne, generator=gen).cuda()
+    labels = (torch.rand(B, 1, generator=gen) < 0.25).float().cuda()
+    assert second_term_eligible(xe, lin_e)
+    loss = logit_bce(h, lin, extra, labels, xe=xe, linear_e=lin_e)
+    (loss * 0.5).backward()
+    params = [h, lin.weight, lin.bias, extra, lin_e.weight, lin_e.bias]
+    got = [loss.detach()] + [p.grad.clone() for p in params]
+    for p in params:
+        p.grad = None
+    ref = F.binary_cross_entropy_with_logits(lin(h) + extra + lin_e(xe), labels)
+    (ref * 0.5).backward()
+    for g, r in zip(got, [ref.detach()] + [p.grad for p in params]):
+        _close(g, r, rtol=2e-5)
+
+
 def test_fused_adagrad_equals_torch_adagrad():
     from torchctr_b200.optim import FusedAdagrad
     gen = torch.Generator().manual_seed(1)

@@ -123,6 +123,10 @@ _SIGNATURES = {
                                           C.c_uint64, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "ctr_logit_bce_fwd": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "ctr_logit_bce_bwd": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_int64, _P, _P]),
+    "ctr_logit_bce_fwd_ex": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P, _P,
+                                       C.c_int64, _P, _P, _P, _P, _P]),
+    "ctr_logit_bce_bwd_ex": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_int64, _P,
+                                       C.c_int64, C.c_int32, _P, _P, _P]),
     "ctr_dense_adagrad": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_int64), C.c_float, C.c_float, _P]),
     "ctr_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(kTowerThreads)
         const uint64_t seed = (a.seed_dev != nullptr ? *a.seed_dev : 0ull) * 0x100000001b3ull + a.seed_offset;
         const int r0 = blockIdx.x * g.rows_per_block;
         const int r1 = min(r0 + g.rows_per_block, g.B);
-#pragma unroll 2
+#pragma unroll 4
         for (int r = r0 + rl; r < r1; r += g.RL) {
             float gq[4], zh[4];
             act_grad4(ld4(gy + (size_t)r * ldgy + 4 * cg), ld4(z + (size_t)r * ldz + 4 * cg), mu, rs, ga, be, drop, keep_scale,
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kTowerThreads)
         const uint64_t seed = (a.seed_dev != nullptr ? *a.seed_dev : 0ull) * 0x100000001b3ull + a.seed_offset;
         const int r0 = blockIdx.x * g.rows_per_block;
         const int r1 = min(r0 + g.rows_per_block, g.B);
-#pragma unroll 2
+#pragma unroll 4
         for (int r = r0 + rl; r < r1; r += g.RL) {
             float gq[4], zh[4], o[4];
             act_grad4(ld4(gy + (size_t)r * ldgy + 4 * cg), ld4(z + (size_t)r * ldz + 4 * cg), mu, rs, ga, be, drop, keep_scale,
@@ -302,6 +302,11 @@ struct HeadArgs {
     float *logits;         // [B] or null
     float *dz;             // [B]
     float inv_B;
+    const float *xe;       // optional second linear term over raw features (DeepFM's Linear(Nd, 1) on the dense block):
+    int64_t ldxe;          //   z += xe[r, :ne] . we + be
+    const float *we;       // [ne], ne <= 32
+    const float *be;       // [1] or null
+    int ne;
 };
 
 __global__ void __launch_bounds__(kTowerThreads)
@@ -327,6 +332,11 @@ __global__ void __launch_bounds__(kTowerThreads)
             if (ok && cg == 0) {
                 float z = d + b0;
                 if (a.extra != nullptr) z += __ldg(a.extra + (size_t)r * a.extra_stride);
+                if (a.xe != nullptr) {
+                    float e = a.be != nullptr ? __ldg(a.be) : 0.f;
+                    for (int j = 0; j < a.ne; ++j) e = fmaf(__ldg(a.xe + (size_t)r * a.ldxe + j), __ldg(a.we + j), e);
+                    z += e;
+                }
                 const float y = __ldg(a.labels + (size_t)r * a.label_stride);
                 // max(z, 0) - z y + log1p(exp(-|z|)): torch's stable form
                 loss_acc += fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));
@@ -360,13 +370,17 @@ __global__ void head_loss_finalize_kernel(const float *__restrict__ partial, int
 }
 
 // gh[r, :] = g dz[r] w;  partial (2 quantities): sum_r dz[r] h[r, :], and sum_r dz[r] (column 0 of quantity 1)
+// (xe, ldxe, ne, gwe_partial): the gradient of the optional second linear term: lane `cg` of a row team accumulates
+// sum_r dz[r] xe[r, j] for the columns j = cg, cg + CG, ... < ne <= 32 (at most 8 per lane as CG >= 4... one float4 pair)
 __global__ void __launch_bounds__(kTowerThreads)
     head_bwd_kernel(const float *__restrict__ h, int64_t ldh, const float *__restrict__ w, const float *__restrict__ dz,
                     const float *__restrict__ gscale, const TowerGeom g, float *__restrict__ gh, int64_t ldgh,
-                    float *__restrict__ gextra, int64_t gextra_stride, float *__restrict__ partial) {
+                    float *__restrict__ gextra, int64_t gextra_stride, float *__restrict__ partial,
+                    const float *__restrict__ xe, int64_t ldxe, int ne, float *__restrict__ xe_partial) {
     __shared__ float4 red[kTowerThreads];
     const int cg = threadIdx.x % g.CG, rl = threadIdx.x / g.CG;
     float4 acc[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
+    float xacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (rl < g.RL) {
         const float gs = __ldg(gscale);
         const float4 w4 = ld4(w + 4 * cg);
@@ -385,9 +399,41 @@ __global__ void __launch_bounds__(kTowerThreads)
                 acc[1].x += d;
                 if (gextra != nullptr) gextra[(size_t)r * gextra_stride] = gd;
             }
+            if (xe != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int j = cg + k * g.CG;
+                    if (j < ne) xacc[k] = fmaf(d, __ldg(xe + (size_t)r * ldxe + j), xacc[k]);
+                }
+            }
         }
     }
     reduce_rows_and_store<2>(acc, g, cg, rl, red, partial);
+    if (xe != nullptr) {      // per-block partial of the second term's weight gradient: [block][32], fixed order over the row lanes
+        float *sx = reinterpret_cast<float *>(red);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int j = cg + k * g.CG;
+            __syncthreads();
+            if (rl < g.RL && j < 32) sx[rl * 32 + j] = xacc[k];
+            __syncthreads();
+            if (rl == 0 && j < ne) {
+                float t = 0.f;
+                for (int r = 0; r < g.RL; ++r) t += sx[r * 32 + j];
+                xe_partial[(size_t)blockIdx.x * 32 + j] = t;
+            }
+        }
+    }
+}
+
+// gwe[j] = g sum over blocks of xe_partial[block][j]; gbe = g sum dz is the head's own bias gradient (same number)
+__global__ void head_xe_finalize_kernel(const float *__restrict__ xe_partial, int blocks, int ne, const float *__restrict__ gscale,
+                                        float *__restrict__ gwe) {
+    const int j = threadIdx.x;
+    if (j >= ne) return;
+    double t = 0.0;
+    for (int b = 0; b < blocks; ++b) t += (double)xe_partial[(size_t)b * 32 + j];
+    gwe[j] = (float)((double)__ldg(gscale) * t);
 }
 
 __global__ void __launch_bounds__(kFinCols * kFinLanes)
@@ -438,8 +484,9 @@ static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 using namespace ctr;
 
 extern "C" int64_t ctr_tower_workspace_bytes(int32_t N) {
-    // partials: up to kTowerMaxBlocks x 2 quantities x N floats, + 2 N floats (c1, c2)
-    return ((int64_t)kTowerMaxBlocks * 2 * N + 2 * N) * (int64_t)sizeof(float) + 256;
+    // partials: up to kTowerMaxBlocks x 2 quantities x N floats, + 2 N floats (c1, c2), + kTowerMaxBlocks x 32 floats (the
+    // logit head's second linear term)
+    return ((int64_t)kTowerMaxBlocks * 2 * N + 2 * N + (int64_t)kTowerMaxBlocks * 32) * (int64_t)sizeof(float) + 256;
 }
 
 extern "C" int ctr_bn_stats(const float *z, int64_t ldz, int32_t B, int32_t N, float eps, float momentum, float *mean,
@@ -524,13 +571,23 @@ extern "C" int ctr_bn_relu_dropout_bwd(const float *gy, int64_t ldgy, const floa
 extern "C" int ctr_logit_bce_fwd(const float *h, int64_t ldh, int32_t B, int32_t H, const float *w, const float *bias,
                                  const float *extra, int64_t extra_stride, const float *labels, int64_t label_stride,
                                  float *logits, float *dz, float *loss, void *workspace, void *stream_) {
+    return ctr_logit_bce_fwd_ex(h, ldh, B, H, w, bias, extra, extra_stride, nullptr, 0, 0, nullptr, nullptr, labels, label_stride,
+                                logits, dz, loss, workspace, stream_);
+}
+
+extern "C" int ctr_logit_bce_fwd_ex(const float *h, int64_t ldh, int32_t B, int32_t H, const float *w, const float *bias,
+                                    const float *extra, int64_t extra_stride, const float *xe, int64_t ldxe, int32_t ne,
+                                    const float *we, const float *be, const float *labels, int64_t label_stride, float *logits,
+                                    float *dz, float *loss, void *workspace, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    CTR_REQUIRE(xe == nullptr || (we != nullptr && ne >= 1 && ne <= 32 && ldxe >= ne && H >= 32),
+                "second linear term: 1 <= ne <= 32, H >= 32, we required");
     CTR_REQUIRE(B >= 1 && H >= 4 && H <= 128 && (H & (H - 1)) == 0, "head: B=%d, H=%d unsupported (H: power of two in [4, 128])", B, H);
     CTR_REQUIRE(ldh >= H && ldh % 4 == 0, "row pitch %lld must be a multiple of 4 and >= H", (long long)ldh);
     CTR_REQUIRE(h && w && labels && dz && loss && workspace, "null pointer");
     CTR_REQUIRE(aligned16(h) && aligned16(w), "h and w must be 16-byte aligned");
     const TowerGeom g = tower_geom(B, H);
-    HeadArgs a{h, ldh, w, bias, extra, extra_stride, labels, label_stride, logits, dz, 1.0f / (float)B};
+    HeadArgs a{h, ldh, w, bias, extra, extra_stride, labels, label_stride, logits, dz, 1.0f / (float)B, xe, ldxe, we, be, xe ? ne : 0};
     float *partial = static_cast<float *>(workspace);
     note_launch(), head_fwd_kernel<<<g.blocks, kTowerThreads, 0, stream>>>(a, g, partial);
     note_launch(), head_loss_finalize_kernel<<<1, 256, 0, stream>>>(partial, g.blocks, 1.0f / (float)B, loss);
@@ -541,15 +598,28 @@ extern "C" int ctr_logit_bce_fwd(const float *h, int64_t ldh, int32_t B, int32_t
 extern "C" int ctr_logit_bce_bwd(const float *h, int64_t ldh, int32_t B, int32_t H, const float *w, const float *dz,
                                  const float *gscale, float *gh, int64_t ldgh, float *gw, float *gb, float *gextra,
                                  int64_t gextra_stride, void *workspace, void *stream_) {
+    return ctr_logit_bce_bwd_ex(h, ldh, B, H, w, dz, gscale, gh, ldgh, gw, gb, gextra, gextra_stride, nullptr, 0, 0, nullptr, workspace,
+                                stream_);
+}
+
+extern "C" int ctr_logit_bce_bwd_ex(const float *h, int64_t ldh, int32_t B, int32_t H, const float *w, const float *dz,
+                                    const float *gscale, float *gh, int64_t ldgh, float *gw, float *gb, float *gextra,
+                                    int64_t gextra_stride, const float *xe, int64_t ldxe, int32_t ne, float *gwe, void *workspace,
+                                    void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    CTR_REQUIRE(xe == nullptr || (gwe != nullptr && ne >= 1 && ne <= 32 && ldxe >= ne && H >= 32),
+                "second linear term: 1 <= ne <= 32, H >= 32 (the block's row lanes stage [RL][32] partials), gwe required");
     CTR_REQUIRE(B >= 1 && H >= 4 && H <= 128 && (H & (H - 1)) == 0, "head: B=%d, H=%d unsupported (H: power of two in [4, 128])", B, H);
     CTR_REQUIRE(ldh >= H && ldh % 4 == 0 && (gh == nullptr || (ldgh >= H && ldgh % 4 == 0)), "row pitches must be multiples of 4 and >= H");
     CTR_REQUIRE(h && w && dz && gscale && gw && workspace, "null pointer");
     CTR_REQUIRE(aligned16(h) && aligned16(w) && aligned16(gh) && aligned16(workspace), "operands must be 16-byte aligned");
     const TowerGeom g = tower_geom(B, H);
     float *partial = static_cast<float *>(workspace);
-    note_launch(), head_bwd_kernel<<<g.blocks, kTowerThreads, 0, stream>>>(h, ldh, w, dz, gscale, g, gh, ldgh, gextra, gextra_stride, partial);
+    float *xe_partial = partial + (size_t)kTowerMaxBlocks * 2 * H;       // [blocks][32], behind the two-quantity partials
+    note_launch(), head_bwd_kernel<<<g.blocks, kTowerThreads, 0, stream>>>(h, ldh, w, dz, gscale, g, gh, ldgh, gextra, gextra_stride, partial,
+                                                                           xe, ldxe, xe ? ne : 0, xe_partial);
     note_launch(), head_bwd_finalize_kernel<<<(H + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, stream>>>(partial, g.blocks, H, gscale, gw, gb);
+    if (xe != nullptr) note_launch(), head_xe_finalize_kernel<<<1, 32, 0, stream>>>(xe_partial, g.blocks, ne, gscale, gwe);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }

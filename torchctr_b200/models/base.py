@@ -275,13 +275,23 @@ class CTRModelBase(nn.Module):
         last = self.tower[-1]
         if self.training and isinstance(last, nn.Linear) and len(self.tower) > 1:
             try:
-                h, extra = self.hidden_and_extra(features)
+                parts = self.hidden_and_extra(features)
             except NotImplementedError:
-                h = None
-            if h is not None:
+                parts = None
+            if parts is not None:
+                h, extra = parts[0], parts[1]
+                second = parts[2] if len(parts) > 2 else None    # (xe, Linear): a linear term over raw features (DeepFM)
                 labels = labels.to(h.device, non_blocking=True)
                 if head_eligible(h, last, labels):       # last Linear + logit terms + mean BCE as one autograd node
-                    return logit_bce(h, last, extra, labels)
+                    if second is None:
+                        return logit_bce(h, last, extra, labels)
+                    if h.shape[1] >= 32:
+                        return logit_bce(h, last, extra, labels, xe=second[0], linear_e=second[1])
+                    term = second[1](second[0])
+                    return logit_bce(h, last, term if extra is None else extra + term, labels)
+                if second is not None:
+                    term = second[1](second[0])
+                    extra = term if extra is None else extra + term
                 logits = self._linear(h, last.weight, last.bias)
                 if extra is not None:
                     logits = logits + extra

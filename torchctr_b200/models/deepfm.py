@@ -7,6 +7,7 @@ import torch
 import torch.nn as nn
 
 from ..nn.embedding import EmbeddingTable, PlanLink, PooledLookupGroup
+from ..nn.head import second_term_eligible
 from ..nn.interaction import fm_interaction_passthrough
 from .base import CTRModelBase, make_tower
 
@@ -29,8 +30,10 @@ class DeepFM(CTRModelBase):
         self.linear_dense = nn.Linear(self._dense_width, 1) if self._dense_width else None
         self.tower = make_tower(self._sparse_width + self._dense_width, list(hidden_units))
 
-    def _parts(self, input_feats):
-        """(tower input x, the logit terms outside the tower: FM second order + first order (+ Linear on dense))"""
+    def _parts(self, input_feats, defer_dense_linear: bool = False):
+        """(tower input x, the logit terms outside the tower: FM second order + first order (+ Linear on dense)).
+        ``defer_dense_linear``: leave Linear(dense) to the caller when the fused logit head can take it
+        (returns (x, extra, dense block | None))."""
         self._grow_vocabularies(input_feats)
         dense = self.dense_block(input_feats)
         twins = None
@@ -49,16 +52,21 @@ class DeepFM(CTRModelBase):
             x, first = self._lookup_all(input_feats, dense)   # [B, pad4(F*D + Nd)], [B, pad4(F)]; one backward sort
             nf = len(self._names)
             x, extra = fm_interaction_passthrough(x, nf, self._dim, first, nf)
+        if self.linear_dense is not None and defer_dense_linear:
+            xe = dense.to(x.device, non_blocking=True)
+            if second_term_eligible(xe, self.linear_dense):
+                return x, extra, xe
         if self.linear_dense is not None:
             # the dense block itself, not the slice of x: same numbers, but no third gradient stream into x (autograd
             # would sum it with the tower's out of place: a zero-fill and an add over [B, F*D + Nd] per step)
             extra = extra + self.linear_dense(dense.to(x.device, dtype=torch.float32, non_blocking=True))
-        return x, extra
+        return (x, extra, None) if defer_dense_linear else (x, extra)
 
     def forward(self, input_feats):
         x, extra = self._parts(input_feats)
         return extra + self._run_tower(x)
 
     def hidden_and_extra(self, input_feats):
-        x, extra = self._parts(input_feats)
-        return self._run_tower(x, stop_before_last=True), extra
+        """(h, extra, (dense block, its Linear) | None): the third item is the Linear(dense) term left to the head kernels"""
+        x, extra, xe = self._parts(input_feats, defer_dense_linear=True)
+        return self._run_tower(x, stop_before_last=True), extra, (None if xe is None else (xe, self.linear_dense))

@@ -710,8 +710,9 @@ def linear_wgrad(gz: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
 
 # ---- logit head + dense optimizer ----------------------------------------------------------------------------------
 @_guarded
-def logit_bce_fwd(h, w, bias, extra, labels, want_logits: bool = False):
+def logit_bce_fwd(h, w, bias, extra, labels, want_logits: bool = False, xe=None, we=None, be=None):
     """h [B, H], w [H], bias [1] | None, extra [B, *] | None (column 0), labels [B, *] (column 0)
+    (xe [B, ne <= 32], we [ne], be [1] | None): a second linear term ``xe @ we + be`` added to the logit
     -> (loss [] mean BCE-with-logits, dz [B], logits [B] | None)"""
     _rows2d(h, "h")
     B, H = h.shape
@@ -719,29 +720,39 @@ def logit_bce_fwd(h, w, bias, extra, labels, want_logits: bool = False):
     dz = torch.empty(B, dtype=torch.float32, device=dev)
     loss = torch.empty((), dtype=torch.float32, device=dev)
     logits = torch.empty(B, dtype=torch.float32, device=dev) if want_logits else None
+    ne = 0
+    if xe is not None:
+        _rows2d(xe, "xe")
+        ne = xe.shape[1]
     with _timed("head_fwd"):
-        _lib.check(_lib.lib().ctr_logit_bce_fwd(h.data_ptr(), h.stride(0), B, H, w.data_ptr(), _lib.ptr(bias), _lib.ptr(extra),
-                                                0 if extra is None else extra.stride(0), labels.data_ptr(), labels.stride(0),
-                                                _lib.ptr(logits), dz.data_ptr(), loss.data_ptr(),
-                                                tower_workspace(dev, H).data_ptr(), _stream(h)), "ctr_logit_bce_fwd")
+        _lib.check(_lib.lib().ctr_logit_bce_fwd_ex(h.data_ptr(), h.stride(0), B, H, w.data_ptr(), _lib.ptr(bias), _lib.ptr(extra),
+                                                   0 if extra is None else extra.stride(0), _lib.ptr(xe),
+                                                   0 if xe is None else xe.stride(0), ne, _lib.ptr(we), _lib.ptr(be),
+                                                   labels.data_ptr(), labels.stride(0), _lib.ptr(logits), dz.data_ptr(),
+                                                   loss.data_ptr(), tower_workspace(dev, H).data_ptr(), _stream(h)),
+                   "ctr_logit_bce_fwd_ex")
     return loss, dz, logits
 
 
 @_guarded
-def logit_bce_bwd(h, w, dz, gscale, want_gh: bool, want_gextra: bool):
-    """-> (gh [B, H] | None, gw [H], gb [1], gextra [B, 1] | None) for the upstream scalar gradient ``gscale`` (device)."""
+def logit_bce_bwd(h, w, dz, gscale, want_gh: bool, want_gextra: bool, xe=None):
+    """-> (gh [B, H] | None, gw [H], gb [1], gextra [B, 1] | None, gwe [ne] | None) for the upstream scalar gradient
+    ``gscale`` (device); the second linear term's bias gradient equals gb."""
     B, H = h.shape
     dev = h.device
     gh = torch.empty(B, H, dtype=torch.float32, device=dev) if want_gh else None
     gw = torch.empty(H, dtype=torch.float32, device=dev)
     gb = torch.empty(1, dtype=torch.float32, device=dev)
     gextra = torch.empty(B, 1, dtype=torch.float32, device=dev) if want_gextra else None
+    ne = 0 if xe is None else xe.shape[1]
+    gwe = torch.empty(ne, dtype=torch.float32, device=dev) if xe is not None else None
     with _timed("head_bwd"):
-        _lib.check(_lib.lib().ctr_logit_bce_bwd(h.data_ptr(), h.stride(0), B, H, w.data_ptr(), dz.data_ptr(), gscale.data_ptr(),
-                                                _lib.ptr(gh), 0 if gh is None else gh.stride(0), gw.data_ptr(), gb.data_ptr(),
-                                                _lib.ptr(gextra), 1, tower_workspace(dev, H).data_ptr(), _stream(h)),
-                   "ctr_logit_bce_bwd")
-    return gh, gw, gb, gextra
+        _lib.check(_lib.lib().ctr_logit_bce_bwd_ex(h.data_ptr(), h.stride(0), B, H, w.data_ptr(), dz.data_ptr(), gscale.data_ptr(),
+                                                   _lib.ptr(gh), 0 if gh is None else gh.stride(0), gw.data_ptr(), gb.data_ptr(),
+                                                   _lib.ptr(gextra), 1, _lib.ptr(xe), 0 if xe is None else xe.stride(0), ne,
+                                                   _lib.ptr(gwe), tower_workspace(dev, H).data_ptr(), _stream(h)),
+                   "ctr_logit_bce_bwd_ex")
+    return gh, gw, gb, gextra, gwe
 
 
 @_guarded
