@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CTR_B200_ABI_VERSION 3
+#define CTR_B200_ABI_VERSION 4
 #define CTR_MAX_FEATURES 40 /* features per launch group (kernel-parameter budget) */
 
 /* status codes */
@@ -65,6 +65,10 @@ extern "C" {
 #define CTR_OPT_ADAGRAD 2         /* torch.optim.Adagrad(lr, eps) element-wise              */
 #define CTR_OPT_ROWWISE_ADAGRAD 3 /* one accumulator per row, += mean(g*g)                  */
 #define CTR_OPT_ADAM 4            /* torch.optim.SparseAdam (lazy Adam)                     */
+#define CTR_OPT_GRAD_OUT 5        /* no update: state0[row, :] = summed gradient of the row (FM part included),
+                                     twin_state0[row] = gradient of the twin.  For tables REPLICATED on every rank of a
+                                     multi-GPU job: the caller zero-fills the buffers, all-reduces them and applies a
+                                     dense update (ctr_dense_adagrad), so every replica moves identically.          */
 
 /* Device-resident open-addressing hash map: raw key (int64) -> table row (int32). */
 typedef struct ctr_vocab_map {
@@ -198,6 +202,14 @@ int ctr_emb_bwd_plan_ex(const ctr_group_t *group, void *workspace, int64_t works
 int ctr_emb_bwd_apply(const ctr_group_t *group, void *workspace, const ctr_opt_t *opt,
                       int32_t *uniq_feature, int32_t *uniq_row, float *row_grad, int64_t row_grad_stride,
                       int64_t *num_unique, void *stream);
+
+/* Dense counterpart of the fused row update for tables REPLICATED on every rank (hybrid placement, see
+ * ctr_emb_pool_fwd_sharded): params / grads / state0 f32 [n] (n % 4 == 0, 16-byte aligned), grads = the buffer the
+ * CTR_OPT_GRAD_OUT sweep filled and the ranks all-reduced.  opt->kind: CTR_OPT_SGD or CTR_OPT_ADAGRAD, same arithmetic as
+ * ctr_emb_bwd_apply (optimizer.step() of torchctr/trainer.py:303 on the touched rows); zero gradients are skipped, and with
+ * clear_grads the buffer is zero again afterwards. */
+int ctr_rows_dense_apply(const ctr_opt_t *opt, float *params, float *grads, float *state0, int64_t n, int32_t clear_grads,
+                         void *stream);
 
 /* ---- vocabulary (dynamic growth) ---------------------------------------------------- */
 int64_t ctr_vocab_fit_workspace_bytes(int64_t n);
@@ -369,9 +381,16 @@ typedef struct ctr_shard {
 } ctr_shard_t;
 
 /* ctr_emb_pool_fwd with every row read from its owner: tables[o] = fused shard of rank o (device pointers, the
- * local one included).  The features' `table` fields are ignored; `num_rows` is the size of the FULL table. */
+ * local one included).  `num_rows` is the size of the FULL table.  A feature whose `table` is NULL is row-sharded; a
+ * feature that carries a `table` (and optionally a `twin_table`) is REPLICATED -- this rank holds all of it and reads it
+ * locally (hybrid placement: small tables replicated, large ones sharded; the reference replicates everything,
+ * torchctr/trainer.py:128-130).  shard->adj is indexed with the feature's position in THIS group. */
 int ctr_emb_pool_fwd_sharded(const ctr_group_t *group, const ctr_shard_t *shard, const float *const *tables,
                              void *stream);
+/* The same with the fused per-bag scalar (group->extra / fm_sum / fm, single-id groups of one width): twin_tables[o] =
+ * the one-column twin shard of rank o (same row geometry as tables[o]), or NULL when the sharded features have no twins. */
+int ctr_emb_pool_fwd_sharded_ex(const ctr_group_t *group, const ctr_shard_t *shard, const float *const *tables,
+                                const float *const *twin_tables, void *stream);
 
 /* Buckets this rank's id slots by owner (stable).  Outputs, to be placed in peer-visible memory:
  *   counts u32 [CTR_MAX_WORLD + 1]  slots per owner (entry `world` = padding / invalid),
@@ -394,6 +413,12 @@ int ctr_emb_bwd_plan_p2p(const ctr_group_t *group, const ctr_shard_t *shard, con
  * rank that sent it: peer_grads[r] f32 [B, group->out_stride] (group->out is ignored). */
 int ctr_emb_bwd_apply_p2p(const ctr_group_t *group, const ctr_shard_t *shard, void *workspace, const ctr_opt_t *opt,
                           const float *const *peer_grads, int64_t *num_unique, void *stream);
+/* The same with the fused DeepFM terms (see ctr_group_t.extra): peer_extra[r] f32 [B] = dL/d extra of rank r's bags,
+ * peer_fm_sum[r] f32 [B, D] = the fm_sum rank r's lookup wrote (NULL array = no FM term); the owner's features carry
+ * their twin shard slices (twin_table / twin_state0 / twin_state1).  group->extra must be non-NULL (it is not read). */
+int ctr_emb_bwd_apply_p2p_ex(const ctr_group_t *group, const ctr_shard_t *shard, void *workspace, const ctr_opt_t *opt,
+                             const float *const *peer_grads, const float *const *peer_extra,
+                             const float *const *peer_fm_sum, int64_t *num_unique, void *stream);
 
 /* ---- de-duplicated exchange (every distinct row of a rank's batch crosses NVLink once per direction) -----------
  * Requester, forward: plan the group with ctr_emb_bwd_plan (runs listed), then ctr_unique_fetch copies the row of every

@@ -13,7 +13,7 @@ import torch
 from . import build as _build
 
 MAX_FEATURES = 40
-ABI_VERSION = 3          # CTR_B200_ABI_VERSION of include/ctr_b200.h
+ABI_VERSION = 4          # CTR_B200_ABI_VERSION of include/ctr_b200.h
 
 OK = 0
 STATUS_INDEX_OOB = 1
@@ -23,7 +23,7 @@ PLAN_NO_RUNS = 1
 
 INDEX_DIRECT, INDEX_HASH, INDEX_REMAP = 0, 1, 2
 POOL_SUM, POOL_MEAN = 0, 1
-OPT_NONE, OPT_SGD, OPT_ADAGRAD, OPT_ROWWISE_ADAGRAD, OPT_ADAM = 0, 1, 2, 3, 4
+OPT_NONE, OPT_SGD, OPT_ADAGRAD, OPT_ROWWISE_ADAGRAD, OPT_ADAM, OPT_GRAD_OUT = 0, 1, 2, 3, 4, 5
 VOCAB_EMPTY = -(2 ** 63)
 
 
@@ -134,7 +134,9 @@ _SIGNATURES = {
     "ctr_peer_export": (C.c_int, [_P, _P]),
     "ctr_peer_open": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
     "ctr_peer_close": (C.c_int, [_P]),
+    "ctr_rows_dense_apply": (C.c_int, [C.POINTER(Opt), _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "ctr_emb_pool_fwd_sharded": (C.c_int, [C.POINTER(Group), C.POINTER(Shard), C.POINTER(C.c_void_p), _P]),
+    "ctr_emb_pool_fwd_sharded_ex": (C.c_int, [C.POINTER(Group), C.POINTER(Shard), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _P]),
     "ctr_route_p2p_workspace_bytes": (C.c_int64, [C.POINTER(Group)]),
     "ctr_route_p2p_build": (C.c_int, [C.POINTER(Group), C.POINTER(Shard), _P, _P, _P, _P, C.c_int64, _P]),
     "ctr_emb_bwd_p2p_workspace_bytes": (C.c_int64, [C.POINTER(Group), C.c_int32]),
@@ -147,6 +149,8 @@ _SIGNATURES = {
     "ctr_emb_bwd_apply_p2p_unique": (C.c_int, [C.POINTER(Group), C.POINTER(Shard), _P, C.POINTER(Opt), C.POINTER(C.c_void_p),
                                                C.c_int64, _P, _P]),
     "ctr_emb_bwd_apply_p2p": (C.c_int, [C.POINTER(Group), C.POINTER(Shard), _P, C.POINTER(Opt), C.POINTER(C.c_void_p), _P, _P]),
+    "ctr_emb_bwd_apply_p2p_ex": (C.c_int, [C.POINTER(Group), C.POINTER(Shard), _P, C.POINTER(Opt), C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _P, _P]),
 }
 
 _lib = None

@@ -79,6 +79,8 @@ struct DevGroup {
     int32_t rank;
     const int64_t *shard_adj;
     const float *peer_tables[CTR_MAX_WORLD];
+    // one-column twin shards (DeepFM first-order weights) of the sharded features, same geometry; null = none
+    const float *peer_twins[CTR_MAX_WORLD];
 };
 
 // Validates a ctr_shard_t and attaches it to a lowered group.
@@ -92,9 +94,10 @@ __device__ __forceinline__ int64_t shard_vrow(const DevGroup &g, int fi, uint32_
     return __ldg(g.shard_adj + (size_t)o * g.num_features + fi) + (int64_t)(r / (uint32_t)g.world);
 }
 
-// address of (table f, row): the local table, or the owner's shard through its peer mapping
+// address of (table f, row): the local table, or the owner's shard through its peer mapping.  In a sharded launch a
+// feature that carries its own `table` pointer is REPLICATED (every rank holds all of it): read locally.
 __device__ __forceinline__ const float *table_row(const DevGroup &g, const DevFeature &f, int fi, int32_t row) {
-    if (g.world <= 1) return f.table + (size_t)(uint32_t)row * f.D;
+    if (g.world <= 1 || f.table != nullptr) return f.table + (size_t)(uint32_t)row * f.D;
     uint32_t o;
     const int64_t v = shard_vrow(g, fi, (uint32_t)row, &o);
     return g.peer_tables[o] + v * f.D;

@@ -196,6 +196,8 @@ struct ApplyArgs {
     uint32_t *status;           // group status word (may be null)
     const float *extra_grad;    // [B] dL/d extra[bag] (twin tables + FM term), or null
     const float *fm_sum;        // [B, D] sum over the fields of the pooled vectors, or null
+    const float *peer_extra[CTR_MAX_WORLD];    // sharded owner side: extra_grad / fm_sum of the rank that sent the slot
+    const float *peer_fm_sum[CTR_MAX_WORLD];
 };
 
 // last feature whose row_base <= key.  sf is the kernel's parameter copy of the features: sorted positions
@@ -279,6 +281,14 @@ __device__ __forceinline__ void update_row(const DevFeature &f, const ApplyArgs 
         }
     }
     if (a.kind == CTR_OPT_NONE) return;
+    if (a.kind == CTR_OPT_GRAD_OUT) {          // replicated table: the summed gradient goes to the dense buffer behind state0
+        if (col_ok) {
+            float *dst = f.state0 + (size_t)row * f.D + (size_t)g_lane * f.vec;
+            if (f.vec == 4) *reinterpret_cast<float4 *>(dst) = gr;
+            else *dst = gr.x;
+        }
+        return;
+    }
     float rowwise_denominator = 0.f;
     if (a.kind == CTR_OPT_ROWWISE_ADAGRAD) {  // whole team takes part in the reduction
         float sq = col_ok ? (f.vec == 4 ? gr.x * gr.x + gr.y * gr.y + gr.z * gr.z + gr.w * gr.w : gr.x * gr.x) : 0.f;
@@ -633,6 +643,11 @@ __device__ __forceinline__ void update_row_l1(const DevFeature &f, const ApplyAr
     if (fm) {
         gr.x = fmaf(-cs, w.x, gr.x); gr.y = fmaf(-cs, w.y, gr.y); gr.z = fmaf(-cs, w.z, gr.z); gr.w = fmaf(-cs, w.w, gr.w);
     }
+    if (a.kind == CTR_OPT_GRAD_OUT) {          // replicated table: gradients out, no update (see ctr_b200.h)
+        *reinterpret_cast<float4 *>(f.state0 + off) = gr;
+        if (t == 0 && f.twin_table != nullptr) f.twin_state0[row] = cs;
+        return;
+    }
     if (a.kind == CTR_OPT_SGD) {
         w.x -= a.h.lr * gr.x; w.y -= a.h.lr * gr.y; w.z -= a.h.lr * gr.z; w.w -= a.h.lr * gr.w;
     } else if (a.kind == CTR_OPT_ADAGRAD) {
@@ -771,8 +786,14 @@ __global__ void __launch_bounds__(kApplyThreads, MINB)
             kk[u] = __shfl_sync(kFull, k, src);
             uint32_t sl = __shfl_sync(kFull, slot, src);
             const float *gout = gout_local;
+            const float *ex = a.extra_grad, *fs = a.fm_sum;
             if (a.p2p) {               // the gradient lives on the rank that sent this slot
-                gout = a.peer_grads[sl >> 28];
+                const uint32_t src_rank = sl >> 28;
+                gout = a.peer_grads[src_rank];
+                if (EXTRA) {
+                    ex = a.peer_extra[src_rank];
+                    fs = a.peer_fm_sum[src_rank];
+                }
                 sl &= 0x0fffffffu;
             }
             if (kk[u] != kInvalidKey) {
@@ -783,9 +804,9 @@ __global__ void __launch_bounds__(kApplyThreads, MINB)
                 }
                 v[u] = __ldg(reinterpret_cast<const float4 *>(gout + (int64_t)sl * gstride + sf[fi].out_col) + t);
                 if (EXTRA) {
-                    c[u] = __ldg(a.extra_grad + sl);
+                    c[u] = __ldg(ex + sl);
                     if (fm) {
-                        const float4 s4 = __ldg(reinterpret_cast<const float4 *>(a.fm_sum + (size_t)sl * D) + t);
+                        const float4 s4 = __ldg(reinterpret_cast<const float4 *>(fs + (size_t)sl * D) + t);
                         v[u].x = fmaf(c[u], s4.x, v[u].x); v[u].y = fmaf(c[u], s4.y, v[u].y);
                         v[u].z = fmaf(c[u], s4.z, v[u].z); v[u].w = fmaf(c[u], s4.w, v[u].w);
                     }
@@ -916,6 +937,33 @@ __global__ void __launch_bounds__(kApplyThreads, MINB)
     }
 }
 
+// ---- replicated tables: dense update from an (all-reduced) gradient buffer -------------------------------------------------
+// p / g / s hold n4 float4 each.  A float4 whose gradient is all zero is skipped (no read of p / s, no write): untouched rows
+// do not move, exactly as the fused sparse update leaves them (sgd / adagrad with g = 0 are the identity anyway).  The
+// gradient is cleared behind the read, so the buffer is zero again for the next step's CTR_OPT_GRAD_OUT sweep.
+__global__ void __launch_bounds__(256)
+    rows_dense_apply_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restrict__ s, long long n4, int kind,
+                            ctr_hyper_t h, const ctr_hyper_t *__restrict__ hd, int clear) {
+    if (hd != nullptr) h = *hd;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 gr = g[i];
+        if (gr.x == 0.f && gr.y == 0.f && gr.z == 0.f && gr.w == 0.f) continue;
+        float4 w = p[i];
+        if (kind == CTR_OPT_SGD) {
+            w.x -= h.lr * gr.x; w.y -= h.lr * gr.y; w.z -= h.lr * gr.z; w.w -= h.lr * gr.w;
+        } else {
+            float4 st = s[i];
+            w.x = adagrad_elem(w.x, st.x, gr.x, h.lr, h.eps);
+            w.y = adagrad_elem(w.y, st.y, gr.y, h.lr, h.eps);
+            w.z = adagrad_elem(w.z, st.z, gr.z, h.lr, h.eps);
+            w.w = adagrad_elem(w.w, st.w, gr.w, h.lr, h.eps);
+            s[i] = st;
+        }
+        p[i] = w;
+        if (clear) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 }  // namespace ctr
 
 using namespace ctr;
@@ -931,6 +979,28 @@ extern "C" void ctr_opt_hyper(const ctr_opt_t *opt, ctr_hyper_t *out) {
         const double bc2 = 1.0 - pow(opt->beta2, (double)opt->step);
         out->adam_step_size = (float)(opt->lr * sqrt(bc2) / bc1);
     }
+}
+
+extern "C" int ctr_rows_dense_apply(const ctr_opt_t *opt, float *params, float *grads, float *state0, int64_t n,
+                                    int32_t clear_grads, void *stream_) {
+    CTR_REQUIRE(opt != nullptr && params != nullptr && grads != nullptr, "null pointer");
+    CTR_REQUIRE(opt->kind == CTR_OPT_SGD || opt->kind == CTR_OPT_ADAGRAD,
+                "ctr_rows_dense_apply: sgd or element-wise adagrad (kind %d given)", opt->kind);
+    CTR_REQUIRE(opt->kind == CTR_OPT_SGD || state0 != nullptr, "adagrad needs state0");
+    CTR_REQUIRE(n >= 0 && n % 4 == 0, "n=%lld must be a multiple of 4", (long long)n);
+    CTR_REQUIRE(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(state0)) & 15u) == 0,
+                "params / grads / state0 must be 16-byte aligned");
+    if (n == 0) return CTR_OK;
+    ctr_hyper_t h;
+    ctr_opt_hyper(opt, &h);
+    const long long n4 = n / 4;
+    long long bx = (n4 + 1023) / 1024;
+    if (bx > kNumSMs * 8) bx = kNumSMs * 8;
+    note_launch(), rows_dense_apply_kernel<<<(unsigned)bx, 256, 0, (cudaStream_t)stream_>>>(
+        reinterpret_cast<float4 *>(params), reinterpret_cast<float4 *>(grads), reinterpret_cast<float4 *>(state0), n4, opt->kind, h,
+        opt->device_hyper, clear_grads);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
 }
 
 extern "C" int64_t ctr_emb_bwd_workspace_bytes(const ctr_group_t *group) {
@@ -995,19 +1065,23 @@ extern "C" int ctr_emb_bwd_plan(const ctr_group_t *group, void *workspace, int64
 // shared by the single-GPU apply and the sharded owner-side apply
 static int apply_impl(DevGroup &dg, const PlanLayout &p, void *workspace, const ctr_opt_t *opt, int32_t *uniq_feature,
                       int32_t *uniq_row, float *row_grad, int64_t row_grad_stride, int64_t *num_unique,
-                      const float *const *peer_grads, int world, cudaStream_t stream) {
+                      const float *const *peer_grads, int world, cudaStream_t stream,
+                      const float *const *peer_extra = nullptr, const float *const *peer_fm_sum = nullptr) {
     const bool updates = opt->kind != CTR_OPT_NONE;
     CTR_REQUIRE(workspace != nullptr, "workspace is null");
-    CTR_REQUIRE(opt->kind >= CTR_OPT_NONE && opt->kind <= CTR_OPT_ADAM, "bad optimizer kind %d", opt->kind);
+    CTR_REQUIRE(opt->kind >= CTR_OPT_NONE && opt->kind <= CTR_OPT_GRAD_OUT, "bad optimizer kind %d", opt->kind);
+    CTR_REQUIRE(opt->kind != CTR_OPT_GRAD_OUT || (uniq_row == nullptr && peer_grads == nullptr),
+                "CTR_OPT_GRAD_OUT: local (unsharded) apply without unique-row outputs");
     int team = 1;
     for (int i = 0; i < dg.num_features; ++i) {
         const DevFeature &f = dg.f[i];
         if (f.G > team) team = f.G;
-        if (opt->kind == CTR_OPT_ADAGRAD || opt->kind == CTR_OPT_ROWWISE_ADAGRAD || opt->kind == CTR_OPT_ADAM)
+        if (opt->kind == CTR_OPT_ADAGRAD || opt->kind == CTR_OPT_ROWWISE_ADAGRAD || opt->kind == CTR_OPT_ADAM ||
+            opt->kind == CTR_OPT_GRAD_OUT)
             CTR_REQUIRE(f.state0 != nullptr, "feature %d: optimizer state0 is null", i);
         if (opt->kind == CTR_OPT_ADAM) CTR_REQUIRE(f.state1 != nullptr, "feature %d: optimizer state1 is null", i);
         if (f.vec == 4 && updates) {
-            CTR_REQUIRE(f.state0 == nullptr || opt->kind == CTR_OPT_ROWWISE_ADAGRAD ||
+            CTR_REQUIRE(f.state0 == nullptr || opt->kind == CTR_OPT_ROWWISE_ADAGRAD || opt->kind == CTR_OPT_SGD ||
                             (reinterpret_cast<uintptr_t>(f.state0) & 15u) == 0,
                         "feature %d: state0 not 16-byte aligned", i);
             CTR_REQUIRE(f.state1 == nullptr || (reinterpret_cast<uintptr_t>(f.state1) & 15u) == 0,
@@ -1074,14 +1148,28 @@ static int apply_impl(DevGroup &dg, const PlanLayout &p, void *workspace, const 
     }
     const bool extra = dg.extra != nullptr;
     if (extra) {
-        if (!l1 || peer_grads != nullptr || !updates || uniq_row != nullptr) {
-            set_error("group->extra (twin tables / FM term) needs an unsharded single-id group of one width (D = 16, 32 or 64), "
-                      "sum pooling, a fused optimizer and no unique-row outputs");
+        if (!l1 || (peer_grads != nullptr && peer_extra == nullptr) || !updates || uniq_row != nullptr) {
+            set_error("group->extra (twin tables / FM term) needs a single-id group of one width (D = 16, 32 or 64), sum pooling, "
+                      "a fused optimizer and no unique-row outputs (sharded owner side: ctr_emb_bwd_apply_p2p_ex)");
             return CTR_E_UNSUPPORTED;
         }
-        a.extra_grad = dg.extra;
-        a.fm_sum = dg.fm ? dg.fm_sum : nullptr;
-        if (dg.fm) CTR_REQUIRE((reinterpret_cast<uintptr_t>(dg.fm_sum) & 15u) == 0, "fm_sum must be 16-byte aligned");
+        if (peer_grads != nullptr) {       // owner side: every slot reads the scalars of the rank that sent it
+            for (int r = 0; r < world; ++r) {
+                CTR_REQUIRE(peer_extra[r] != nullptr, "peer_extra[%d] is null", r);
+                a.peer_extra[r] = peer_extra[r];
+                if (peer_fm_sum != nullptr) {
+                    CTR_REQUIRE(peer_fm_sum[r] != nullptr && (reinterpret_cast<uintptr_t>(peer_fm_sum[r]) & 15u) == 0,
+                                "peer_fm_sum[%d] is null or not 16-byte aligned", r);
+                    a.peer_fm_sum[r] = peer_fm_sum[r];
+                }
+            }
+            a.extra_grad = peer_extra[0];
+            a.fm_sum = peer_fm_sum != nullptr ? peer_fm_sum[0] : nullptr;
+        } else {
+            a.extra_grad = dg.extra;
+            a.fm_sum = dg.fm ? dg.fm_sum : nullptr;
+            if (dg.fm) CTR_REQUIRE((reinterpret_cast<uintptr_t>(dg.fm_sum) & 15u) == 0, "fm_sum must be 16-byte aligned");
+        }
         for (int i = 0; i < dg.num_features; ++i) {
             const DevFeature &f = dg.f[i];
             if (f.twin_table == nullptr) continue;
@@ -1286,6 +1374,29 @@ extern "C" int ctr_emb_bwd_apply_p2p(const ctr_group_t *group, const ctr_shard_t
     }
     return apply_impl(dg, plan_layout(dg, shard->world), workspace, opt, nullptr, nullptr, nullptr, 0, num_unique, peer_grads,
                       shard->world, (cudaStream_t)stream_);
+}
+
+extern "C" int ctr_emb_bwd_apply_p2p_ex(const ctr_group_t *group, const ctr_shard_t *shard, void *workspace, const ctr_opt_t *opt,
+                                        const float *const *peer_grads, const float *const *peer_extra,
+                                        const float *const *peer_fm_sum, int64_t *num_unique, void *stream_) {
+    static thread_local DevGroup dg;
+    CTR_REQUIRE(opt != nullptr && peer_grads != nullptr && peer_extra != nullptr, "null pointer");
+    CTR_REQUIRE(group != nullptr && group->extra != nullptr, "group->extra must be set (marks the fused terms; it is not read)");
+    ctr_group_t gcopy = *group;
+    gcopy.fm = 0;                 // the FM sums come from the peers (peer_fm_sum), not from group->fm_sum
+    gcopy.fm_sum = nullptr;
+    int rc = lower_group(&gcopy, &dg, /*need_tables=*/opt->kind != CTR_OPT_NONE, /*need_out=*/false);
+    if (rc != CTR_OK) return rc;
+    rc = check_owner_group(dg, shard);
+    if (rc != CTR_OK) return rc;
+    for (int i = 0; i < dg.num_features; ++i) {
+        DevFeature &f = dg.f[i];
+        bool al = f.vec == 4 && f.out_col % 4 == 0 && dg.out_stride % 4 == 0;
+        for (int r = 0; r < shard->world && al; ++r) al = (reinterpret_cast<uintptr_t>(peer_grads[r]) & 15u) == 0;
+        f.aligned = al ? 1 : 0;
+    }
+    return apply_impl(dg, plan_layout(dg, shard->world), workspace, opt, nullptr, nullptr, nullptr, 0, num_unique, peer_grads,
+                      shard->world, (cudaStream_t)stream_, peer_extra, peer_fm_sum);
 }
 
 // ---- de-duplicated exchange: every rank fetches / sends each distinct row of its batch once ------------------------

@@ -216,11 +216,20 @@ __global__ void __launch_bounds__(kFwdThreads) emb_pool_fwd_l1_kernel(const __gr
                 v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 tw[j] = 0.f;
                 if (row[j] >= 0) {
-                    const float *src = SHARDED ? table_row(g, g.f[f0 + j], f0 + j, row[j]) + t * VEC
-                                               : g.f[f0 + j].table + (size_t)(uint32_t)row[j] * D + t * VEC;
+                    const DevFeature &ft = g.f[f0 + j];
+                    const float *src, *tsrc = nullptr;
+                    if (!SHARDED || ft.table != nullptr) {      // the local table (a sharded launch: a replicated feature)
+                        src = ft.table + (size_t)(uint32_t)row[j] * D + t * VEC;
+                        if (EXTRA && ft.twin_table != nullptr) tsrc = ft.twin_table + (uint32_t)row[j];
+                    } else {                                    // the owner's shard through its peer mapping
+                        uint32_t o;
+                        const int64_t vr = shard_vrow(g, f0 + j, (uint32_t)row[j], &o);
+                        src = g.peer_tables[o] + vr * D + t * VEC;
+                        if (EXTRA && g.peer_twins[o] != nullptr) tsrc = g.peer_twins[o] + vr;
+                    }
                     if (VEC == 4) v[j] = __ldg(reinterpret_cast<const float4 *>(src));
                     else v[j].x = __ldg(src);
-                    if (EXTRA && t == 0 && g.f[f0 + j].twin_table != nullptr) tw[j] = __ldg(g.f[f0 + j].twin_table + (uint32_t)row[j]);
+                    if (EXTRA && t == 0 && tsrc != nullptr) tw[j] = __ldg(tsrc);
                 }
             }
 #pragma unroll
@@ -397,6 +406,24 @@ extern "C" int ctr_emb_pool_fwd_sharded(const ctr_group_t *group, const ctr_shar
     return launch_pool_fwd(dg, stream);
 }
 
+extern "C" int ctr_emb_pool_fwd_sharded_ex(const ctr_group_t *group, const ctr_shard_t *shard, const float *const *tables,
+                                           const float *const *twin_tables, void *stream) {
+    static thread_local DevGroup dg;
+    int rc = lower_group(group, &dg, /*need_tables=*/false, /*need_out=*/true);
+    if (rc != CTR_OK) return rc;
+    CTR_REQUIRE(tables != nullptr, "tables is null");
+    rc = attach_shard(&dg, shard, tables);
+    if (rc != CTR_OK) return rc;
+    if (twin_tables != nullptr) {
+        CTR_REQUIRE(dg.extra != nullptr, "twin shards need group->extra [B]");
+        for (int o = 0; o < shard->world; ++o) {
+            CTR_REQUIRE(twin_tables[o] != nullptr, "twin_tables[%d] is null", o);
+            dg.peer_twins[o] = twin_tables[o];
+        }
+    }
+    return launch_pool_fwd(dg, stream);
+}
+
 static int launch_pool_fwd(const DevGroup &dg, void *stream) {
     const int extra_w = dg.dense_width + (dg.zero_from >= 0 ? (int)(dg.out_stride - dg.zero_from) : 0);
     if (dg.B == 0 || (dg.num_features == 0 && extra_w == 0)) return CTR_OK;
@@ -410,13 +437,16 @@ static int launch_pool_fwd(const DevGroup &dg, void *stream) {
         const bool sh = dg.world > 1;
         const bool ex = dg.extra != nullptr;
         if (ex) {
-            if (sh || vec != 4) {
-                set_error("group->extra (twin tables / FM term) needs an unsharded single-id group of one width, D %% 4 == 0");
+            if (vec != 4) {
+                set_error("group->extra (twin tables / FM term) needs a single-id group of one width, D %% 4 == 0");
                 return CTR_E_UNSUPPORTED;
             }
             if (dg.fm) CTR_REQUIRE((reinterpret_cast<uintptr_t>(dg.fm_sum) & 15u) == 0, "fm_sum must be 16-byte aligned");
-            if (fastG == 4) emb_pool_fwd_l1_kernel<4, 4, false, true><<<blocks, kFwdThreads, 0, st>>>(dg);
+            if (fastG == 4 && sh) emb_pool_fwd_l1_kernel<4, 4, true, true><<<blocks, kFwdThreads, 0, st>>>(dg);
+            else if (fastG == 4) emb_pool_fwd_l1_kernel<4, 4, false, true><<<blocks, kFwdThreads, 0, st>>>(dg);
+            else if (fastG == 8 && sh) emb_pool_fwd_l1_kernel<8, 4, true, true><<<blocks, kFwdThreads, 0, st>>>(dg);
             else if (fastG == 8) emb_pool_fwd_l1_kernel<8, 4, false, true><<<blocks, kFwdThreads, 0, st>>>(dg);
+            else if (sh) emb_pool_fwd_l1_kernel<16, 4, true, true><<<blocks, kFwdThreads, 0, st>>>(dg);
             else emb_pool_fwd_l1_kernel<16, 4, false, true><<<blocks, kFwdThreads, 0, st>>>(dg);
         }
         else if (vec == 1 && sh) emb_pool_fwd_l1_kernel<1, 1, true, false><<<blocks, kFwdThreads, 0, st>>>(dg);

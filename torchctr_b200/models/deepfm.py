@@ -13,6 +13,8 @@ from .base import CTRModelBase, make_tower
 
 
 class DeepFM(CTRModelBase):
+    _fm_term = True          # the lookup may produce the FM second-order term (parallel.shard_model reads this)
+
     def __init__(self, feat_configs, hidden_units=[256, 128, 64], table_device=None):
         super().__init__(feat_configs, table_device)
         dims = {c["emb_dim"] for c in self._sparse}
@@ -42,7 +44,11 @@ class DeepFM(CTRModelBase):
             if self.training and torch.is_grad_enabled():
                 for g in self._groups:
                     g.autobind()
-        if twins is not None and self._lookup.fused_extra_eligible(input_feats, twins, self.training):
+        if self._sharded is not None and getattr(self._sharded, "fused_extra", False):
+            # hybrid placement: the same fused terms, small tables replicated / large ones read over NVLink inside ONE lookup
+            x, extra = self._sharded(input_feats, dense)
+            extra = extra.unsqueeze(1)
+        elif twins is not None and self._lookup.fused_extra_eligible(input_feats, twins, self.training):
             # Criteo-shaped (single-id, one width): the first-order weights and the FM term ride inside the lookup
             # kernel, their gradients inside the fused update -- no D = 1 launch group, no pass over [B, F * D] for FM
             link = PlanLink() if self.training else None

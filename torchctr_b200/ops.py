@@ -11,13 +11,13 @@ from dataclasses import dataclass, field
 import torch
 
 from . import _lib
-from ._lib import (INDEX_DIRECT, INDEX_HASH, INDEX_REMAP, OPT_ADAGRAD, OPT_ADAM, OPT_NONE,  # noqa: F401
+from ._lib import (INDEX_DIRECT, INDEX_HASH, INDEX_REMAP, OPT_ADAGRAD, OPT_ADAM, OPT_GRAD_OUT, OPT_NONE,  # noqa: F401
                    OPT_ROWWISE_ADAGRAD, OPT_SGD, POOL_MEAN, POOL_SUM)
 
 _INDEX_KINDS = {"direct": INDEX_DIRECT, "hash": INDEX_HASH, "vocab": INDEX_REMAP, "remap": INDEX_REMAP}
 _POOLINGS = {"sum": POOL_SUM, "mean": POOL_MEAN}
 _OPT_KINDS = {"none": OPT_NONE, "sgd": OPT_SGD, "adagrad": OPT_ADAGRAD, "rowwise_adagrad": OPT_ROWWISE_ADAGRAD,
-              "adam": OPT_ADAM}
+              "adam": OPT_ADAM, "grad_out": OPT_GRAD_OUT}
 
 
 def _chk(t, name, dtype, cuda=True):
@@ -281,6 +281,20 @@ def emb_bwd_apply(call: GroupCall, workspace: torch.Tensor, opt: _lib.Opt, uniq_
         _lib.check(_lib.lib().ctr_emb_bwd_apply(C.byref(call.struct), workspace.data_ptr(), C.byref(opt),
                                                 _lib.ptr(uniq_feature), _lib.ptr(uniq_row), _lib.ptr(row_grad), stride,
                                                 _lib.ptr(num_unique), _stream(call)), "ctr_emb_bwd_apply")
+
+
+@_guarded
+def rows_dense_apply(params: torch.Tensor, grads: torch.Tensor, state0: torch.Tensor | None, opt: _lib.Opt, clear: bool = True) -> None:
+    """Dense sgd / adagrad update of a replicated table block from its (all-reduced) gradient buffer; zero gradients are
+    skipped and, with ``clear``, the buffer is zero again afterwards."""
+    _chk(params, "params", torch.float32)
+    _chk(grads, "grads", torch.float32)
+    _chk(state0, "state0", torch.float32)
+    if grads.numel() != params.numel() or (state0 is not None and state0.numel() != params.numel()):
+        raise ValueError("params / grads / state0 must hold the same number of elements")
+    with _timed("rows_dense_apply"):
+        _lib.check(_lib.lib().ctr_rows_dense_apply(C.byref(opt), params.data_ptr(), grads.data_ptr(), _lib.ptr(state0),
+                                                   params.numel(), 1 if clear else 0, _stream(params)), "ctr_rows_dense_apply")
 
 
 @_guarded
@@ -578,10 +592,15 @@ def make_shard(world: int, rank: int, adj: torch.Tensor) -> _lib.Shard:
 
 
 @_guarded
-def emb_pool_fwd_sharded(call: GroupCall, shard: _lib.Shard, tables) -> None:
+def emb_pool_fwd_sharded(call: GroupCall, shard: _lib.Shard, tables, twin_tables=None) -> None:
+    """``twin_tables``: per-rank pointers of the one-column twin shards (the fused DeepFM terms, ``make_group(extra=...)``)."""
     with _timed("emb_pool_fwd" + _width_tag(call)):
-        _lib.check(_lib.lib().ctr_emb_pool_fwd_sharded(C.byref(call.struct), C.byref(shard), tables, _stream(call)),
-                   "ctr_emb_pool_fwd_sharded")
+        if twin_tables is None and not call.struct.extra:
+            _lib.check(_lib.lib().ctr_emb_pool_fwd_sharded(C.byref(call.struct), C.byref(shard), tables, _stream(call)),
+                       "ctr_emb_pool_fwd_sharded")
+        else:
+            _lib.check(_lib.lib().ctr_emb_pool_fwd_sharded_ex(C.byref(call.struct), C.byref(shard), tables, twin_tables,
+                                                              _stream(call)), "ctr_emb_pool_fwd_sharded_ex")
 
 
 @_guarded
@@ -611,11 +630,18 @@ def emb_bwd_plan_p2p(call: GroupCall, shard: _lib.Shard, counts, keys, slots, wo
 
 @_guarded
 def emb_bwd_apply_p2p(call: GroupCall, shard: _lib.Shard, workspace: torch.Tensor, opt: _lib.Opt, grads,
-                      num_unique: torch.Tensor | None = None) -> None:
+                      num_unique: torch.Tensor | None = None, peer_extra=None, peer_fm_sum=None) -> None:
+    """``peer_extra`` (+ ``peer_fm_sum``): per-rank pointers of dL/d extra [B] (and fm_sum [B, D]) -- the fused DeepFM terms on
+    the owner side; the group then carries ``extra`` and the features their twin shard slices."""
     _chk(num_unique, "num_unique", torch.int64)
-    with _timed("emb_bwd_apply" + _width_tag(call)):
-        _lib.check(_lib.lib().ctr_emb_bwd_apply_p2p(C.byref(call.struct), C.byref(shard), workspace.data_ptr(), C.byref(opt),
-                                                    grads, _lib.ptr(num_unique), _stream(call)), "ctr_emb_bwd_apply_p2p")
+    with _timed("emb_bwd_apply_owner" + _width_tag(call)):
+        if peer_extra is None:
+            _lib.check(_lib.lib().ctr_emb_bwd_apply_p2p(C.byref(call.struct), C.byref(shard), workspace.data_ptr(), C.byref(opt),
+                                                        grads, _lib.ptr(num_unique), _stream(call)), "ctr_emb_bwd_apply_p2p")
+        else:
+            _lib.check(_lib.lib().ctr_emb_bwd_apply_p2p_ex(C.byref(call.struct), C.byref(shard), workspace.data_ptr(), C.byref(opt),
+                                                           grads, peer_extra, peer_fm_sum, _lib.ptr(num_unique), _stream(call)),
+                       "ctr_emb_bwd_apply_p2p_ex")
 
 
 # ---- tower block (BatchNorm1d + ReLU + Dropout around a Linear) ------------------------------------------------------

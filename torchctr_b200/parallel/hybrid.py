@@ -1,0 +1,498 @@
+"""Hybrid table placement for Criteo-shaped models: small tables replicated, large tables row-sharded.
+
+The reference is replicas-only (``Accelerator().prepare`` -> DDP, ``torchctr/trainer.py:128-130``): every rank holds every
+table and dense ``[V, D]`` gradients of ALL tables are all-reduced.  ``PeerShardedTables`` is the other extreme: every table
+row-sharded, every id slot crosses NVLink twice per step.  On a Criteo-shaped batch most slots belong to SMALL tables
+(18 of 26 tables have <= 1e5 rows and take 69 % of the slots), whose full gradient is a few MB -- cheaper to all-reduce
+than to route -- while the large tables' gradients are far too sparse for that.  So:
+
+  replicated  tables with <= ``replicate_max_rows`` rows live on every rank in one contiguous block.  The lookup reads them
+              locally; backward, the fused sweep runs in ``CTR_OPT_GRAD_OUT`` mode (summed row gradients into a zeroed dense
+              buffer, FM / first-order terms included), ONE NCCL all-reduce sums the buffer over the ranks and
+              ``ctr_rows_dense_apply`` gives every replica the same sgd / adagrad update (zero gradients skipped);
+  sharded     the other tables are cut as in ``PeerShardedTables`` (row r of the j-th sharded table on rank (r + j) mod P):
+              rows are read from the owner's shard through its NVLink peer mapping INSIDE the same lookup kernel, and the
+              owners pull the (row, slot) lists, sort them on a side stream during the tower and run the fused sweep reading
+              every slot's gradient (and, for DeepFM, its dL/d extra and FM sum) from the rank that produced it.
+
+One lookup launch and, per rank, two sweeps per step -- DeepFM's first-order tables and FM term ride inside them exactly as
+on one GPU (``ctr_group_t.extra``).  The all-reduce doubles as the closing barrier of the owner-side update.
+Single-id features of one width (D = 16, 32 or 64), direct or hashed ids, sum pooling, sgd / adagrad.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops
+from ..nn.embedding import SparseOptimizerBinding
+from .peer import PeerBuffer, _ShardHolder, owned_rows, shard_geometry
+
+
+def hybrid_eligible(tables, twins=None) -> bool:
+    """Can ``HybridShardedTables`` hold these tables?"""
+    if not tables:
+        return False
+    D = tables[0].embedding_dim
+    if D not in (16, 32, 64):
+        return False
+    for t in list(tables) + list(twins or []):
+        if t.pooling != "sum" or t.use_id_weight or t.index_kind not in ("direct", "hash"):
+            return False
+    if any(t.embedding_dim != D for t in tables) or any(t.embedding_dim != 1 for t in (twins or [])):
+        return False
+    return True
+
+
+class _HybridLookupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, st, ids_list, dense, *weights):
+        ctx.st = st
+        ctx.has_dense = dense is not None
+        ctx.dense_width = 0 if dense is None else dense.shape[1]
+        x, extra = st._forward(ids_list, dense)
+        if extra is None:
+            return (x,)
+        return x, extra
+
+    @staticmethod
+    def backward(ctx, gx, gextra=None):
+        st = ctx.st
+        st._backward(gx, gextra)
+        gdense = None
+        if ctx.has_dense and ctx.needs_input_grad[2] and gx is not None:
+            c0 = st.num_features * st.D
+            gdense = gx[:, c0:c0 + ctx.dense_width]
+        return (None, None, gdense) + (None,) * len(st.shards)
+
+
+class HybridShardedTables(nn.Module):
+    """``tables``: the full tables of the model in feature order (``twins``: DeepFM's one-column first-order tables, same
+    order, or None); ``fm``: also produce the FM second-order term.  ``forward(feats, dense)`` returns ``(x,)`` or, with
+    twins / fm, ``(x, extra)`` with ``extra`` f32 [B] = sum of the first-order weights (+ FM term).
+
+    One training lookup is in flight per module at a time (forward / backward / forward / backward); every rank calls
+    ``forward`` / ``backward`` the same number of times."""
+
+    def __init__(self, names, tables, twins, transport, device=None, fm: bool = False, replicate_max_rows: int = 1 << 17,
+                 init_seed: int | None = None, init_std: float = 1.0):
+        super().__init__()
+        if not hybrid_eligible(tables, twins):
+            raise NotImplementedError("hybrid placement: single-id sum-pooled tables of one width (16, 32 or 64), direct / hashed ids")
+        from ..nn.embedding import EmbeddingTable
+        self.transport = transport
+        self.world, self.rank = transport.world, transport.rank
+        if self.world > _lib.MAX_WORLD:
+            raise ValueError(f"at most {_lib.MAX_WORLD} ranks")
+        dev = torch.device(device if device is not None else transport.device)
+        self.device = dev
+        self.names = list(names)
+        F = self.num_features = len(self.names)
+        self.D = D = int(tables[0].embedding_dim)
+        self.has_twins = twins is not None
+        self.fm = bool(fm)
+        self.fused_extra = self.has_twins or self.fm
+        self.dims = [D, 1] if self.has_twins else [D]
+        self.num_rows = [int(t.num_embeddings) for t in tables]
+        self.index_kinds = [t.index_kind for t in tables]
+        self.hash_seeds = [t.hash_seed for t in tables]
+        self.vocabs = [None] * F
+        self.sh = [f for f in range(F) if self.num_rows[f] > replicate_max_rows]       # sharded features (original indices)
+        self.rp = [f for f in range(F) if self.num_rows[f] <= replicate_max_rows]      # replicated features
+        self.order = self.sh + self.rp                                                  # feature order of the lookup group
+        Fs = len(self.sh)
+        seed0 = torch.initial_seed() if init_seed is None else init_seed
+        widths = [tables] + ([twins] if self.has_twins else [])
+
+        # ---- sharded part: this rank's rows of the large tables, in peer-visible memory ----
+        self.base, self.total, adj_s = shard_geometry([self.num_rows[f] for f in self.sh], self.world) if Fs else ([], [1] * self.world, torch.zeros(0, dtype=torch.int64))
+        adj_l = torch.zeros(self.world * F, dtype=torch.int64)
+        for o in range(self.world):
+            for j in range(Fs):
+                adj_l[o * F + j] = adj_s[o * Fs + j]
+        self.register_buffer("adj_s", adj_s.to(dev) if Fs else torch.zeros(1, dtype=torch.int64, device=dev), persistent=False)
+        self.register_buffer("adj_l", adj_l.to(dev), persistent=False)
+        self._shard_s = ops.make_shard(self.world, self.rank, self.adj_s)
+        self._shard_l = ops.make_shard(self.world, self.rank, self.adj_l)
+        rows = max(self.total[self.rank], 1) if Fs else 1
+        self._shard_bufs, self._table_ptrs = [], []
+        params = []
+        for wi, (tabs, Dw) in enumerate(zip(widths, self.dims)):
+            buf = PeerBuffer(rows * Dw * 4, dev)
+            w = buf.tensor(torch.float32, (rows, Dw))
+            for j, f in enumerate(self.sh):
+                t = tabs[f]
+                fr, n = owned_rows(self.num_rows[f], j, self.rank, self.world)
+                if not n:
+                    continue
+                b = self.base[self.rank][j]
+                if t.weight.is_meta:       # shard-native: this rank draws ITS rows; no rank ever holds the full table
+                    ops.normal_fill_rows_strided(w, b, n, 0.0, init_std, EmbeddingTable.counter_seed(seed0, f, wi), fr, self.world)
+                else:
+                    w[b:b + n] = t.weight.detach()[fr::self.world].to(dev)
+            self._shard_bufs.append(buf)
+            params.append(nn.Parameter(w, requires_grad=True))
+            self._table_ptrs.append(ops.ptr_array(transport.share(buf)))
+
+        # ---- replicated part: the small tables, whole, in one block per width ----
+        self.rep_off, acc = {}, 0
+        for f in self.rp:
+            self.rep_off[f] = acc
+            acc += self.num_rows[f]
+        self.R = R = (acc + 3) // 4 * 4 if acc else 0
+        for wi, (tabs, Dw) in enumerate(zip(widths, self.dims)):
+            blk = torch.zeros(max(R, 4), Dw, dtype=torch.float32, device=dev)
+            for f in self.rp:
+                t, o, v = tabs[f], self.rep_off[f], self.num_rows[f]
+                if t.weight.is_meta:
+                    ops.normal_fill_rows_strided(blk, o, v, 0.0, init_std, EmbeddingTable.counter_seed(seed0, f, wi), 0, 1)
+                else:
+                    blk[o:o + v] = t.weight.detach().to(dev)
+            params.append(nn.Parameter(blk, requires_grad=True))
+        nw = len(self.dims)
+        # shards[0 .. nw): this rank's shard of every width; shards[nw .. 2 nw): the replicated block of every width
+        self.shards = nn.ParameterList(params)
+        # gradient buffer of the replicated block: [R, D] then [R] (twins), ONE flat tensor = one all-reduce
+        self._rep_grad = torch.zeros(max(R, 4) * (D + (1 if self.has_twins else 0)), dtype=torch.float32, device=dev)
+        self.opt_state = [None] * (2 * nw)      # adagrad sums, same shapes as self.shards
+        self.bindings = [None]
+        self.binding = None
+        self._side = None
+        self._route_pending = False
+        self._cap = None                        # (B, dense width) the peer buffers were sized for
+        self._route_ws = self._plan_ws = self._rep_ws = None
+        self._dense_width = 0
+        self.status = None
+
+    # ---- optimizer ---------------------------------------------------------------------------------------------
+    def bind_optimizer(self, optimizer, kind=None):
+        b = SparseOptimizerBinding(optimizer, [_ShardHolder(self.shards[0])], kind)
+        if b.kind not in ("sgd", "adagrad"):
+            raise NotImplementedError(f"hybrid placement updates its replicated tables densely: sgd / adagrad only, not {b.kind!r} "
+                                      "(use PeerShardedTables: shard_model(..., hybrid=False))")
+        self.binding = b
+        self.bindings = [b]
+
+    def _ensure_state(self):
+        if self.binding.kind != "adagrad" or self.opt_state[0] is not None:
+            return
+        init = self.binding.initial_accumulator_value()
+        self.opt_state = [torch.full_like(p.data, init) for p in self.shards]
+
+    # ---- per-batch peer buffers ----------------------------------------------------------------------------------
+    def _ensure_buffers(self, B):
+        key = self._dense_width
+        if self._cap is not None:
+            capB, capkey = self._cap
+            if key == capkey and B <= capB:
+                return
+            raise RuntimeError(f"hybrid lookup: batch geometry {(B, key)} does not fit the peer buffers sized for {self._cap}")
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("peer buffers must be sized (one eager step) before the step is captured into a CUDA graph")
+        geoms = self.transport.all_gather_object((B, key))
+        if any(g[1] != key for g in geoms):
+            raise RuntimeError(f"hybrid lookup: ranks disagree on the feature layout: {geoms}")
+        B = max(g[0] for g in geoms)
+        dev, tr, D, F = self.device, self.transport, self.D, self.num_features
+        Fs = len(self.sh)
+        S = max(B * Fs, 1)
+        self._S = S
+        self._route_buf = PeerBuffer(256 + 8 * S, dev)                  # [counts 64 words][keys S][slots S]
+        ptrs = tr.share(self._route_buf)
+        self._peer_counts = ops.ptr_array(ptrs)
+        self._peer_keys = ops.ptr_array([p + 256 for p in ptrs])
+        self._peer_slots = ops.ptr_array([p + 256 + 4 * S for p in ptrs])
+        self._stride = (F * D + self._dense_width + 3) // 4 * 4
+        self._grad_buf = PeerBuffer(B * self._stride * 4, dev)          # dL/dx of this rank's bags
+        self._peer_grads = ops.ptr_array(tr.share(self._grad_buf))
+        self._peer_extra = self._peer_fm = None
+        if self.fused_extra:
+            self._extra_buf = PeerBuffer(B * 4, dev)                    # dL/d extra of this rank's bags
+            self._peer_extra = ops.ptr_array(tr.share(self._extra_buf))
+            self._gextra = self._extra_buf.tensor(torch.float32, (B,))
+        if self.fm:
+            self._fm_buf = PeerBuffer(B * D * 4, dev)                   # sum over the fields of the pooled vectors
+            self._peer_fm = ops.ptr_array(tr.share(self._fm_buf))
+        self._owner_ids = torch.zeros(B, 1, dtype=torch.int64, device=dev)   # never read: the owner pulls the peers' lists
+        self._cap = (B, key)
+
+    # ---- feature specs ---------------------------------------------------------------------------------------------
+    def _rep_views(self, f, wi, src):
+        o, v = self.rep_off[f], self.num_rows[f]
+        return src[o:o + v]
+
+    def _lookup_specs(self, ids_list):
+        """Sharded features first (their position is the index the shard geometry uses), then the replicated ones."""
+        D, nw = self.D, len(self.dims)
+        rep_w = self.shards[nw].data
+        rep_t = self.shards[nw + 1].data if self.has_twins else None
+        specs = []
+        for j, f in enumerate(self.order):
+            kw = dict(ids=ids_list[j], num_rows=self.num_rows[f], D=D, out_col=f * D, index_kind=self.index_kinds[f],
+                      hash_seed=self.hash_seeds[f])
+            if j < len(self.sh):
+                specs.append(ops.FeatureSpec(table=None, **kw))
+            else:
+                o, v = self.rep_off[f], self.num_rows[f]
+                specs.append(ops.FeatureSpec(table=rep_w[o:o + v], twin_table=None if rep_t is None else rep_t[o:o + v], **kw))
+        return specs
+
+    def _rep_bwd_specs(self, ids_list, plan: bool = False):
+        """The replicated features for the GRAD_OUT sweep: state0 / twin_state0 are the dense gradient buffers
+        (``plan``: ids and row counts only, for the sort)."""
+        D, nw = self.D, len(self.dims)
+        R = max(self.R, 4)
+        rep_w = self.shards[nw].data
+        rep_t = self.shards[nw + 1].data if self.has_twins else None
+        g_main = self._rep_grad[:R * D].view(R, D)
+        g_twin = self._rep_grad[R * D:] if self.has_twins else None
+        specs = []
+        for j, f in enumerate(self.order):
+            if j < len(self.sh):
+                continue
+            o, v = self.rep_off[f], self.num_rows[f]
+            if plan:
+                specs.append(ops.FeatureSpec(ids=ids_list[j], table=None, num_rows=v, D=D, out_col=f * D,
+                                             index_kind=self.index_kinds[f], hash_seed=self.hash_seeds[f]))
+                continue
+            specs.append(ops.FeatureSpec(ids=ids_list[j], table=rep_w[o:o + v], num_rows=v, D=D, out_col=f * D,
+                                         index_kind=self.index_kinds[f], hash_seed=self.hash_seeds[f], state0=g_main[o:o + v],
+                                         twin_table=None if rep_t is None else rep_t[o:o + v],
+                                         twin_state0=None if g_twin is None else g_twin[o:o + v]))
+        return specs
+
+    def _route_specs(self, ids_list):
+        return [ops.FeatureSpec(ids=ids_list[j], table=None, num_rows=self.num_rows[f], D=self.D, out_col=f * self.D,
+                                index_kind=self.index_kinds[f], hash_seed=self.hash_seeds[f]) for j, f in enumerate(self.sh)]
+
+    def _owner_specs(self, with_state):
+        D = self.D
+        shard = self.shards[0].data
+        twin = self.shards[1].data.view(-1) if self.has_twins else None
+        s0 = self.opt_state[0] if with_state else None
+        t0 = self.opt_state[1].view(-1) if (with_state and self.has_twins and self.opt_state[1] is not None) else None
+        specs = []
+        for j, f in enumerate(self.sh):
+            _, n = owned_rows(self.num_rows[f], j, self.rank, self.world)
+            n = max(n, 1)
+            b = self.base[self.rank][j]
+            specs.append(ops.FeatureSpec(ids=self._owner_ids, table=shard[b:b + n], num_rows=n, D=D, out_col=f * D,
+                                         state0=None if s0 is None else s0[b:b + n],
+                                         twin_table=None if twin is None or not with_state else twin[b:b + n],
+                                         twin_state0=None if t0 is None else t0[b:b + n]))
+        return specs
+
+    # ---- forward / backward ----------------------------------------------------------------------------------------
+    def forward(self, feats, dense=None):
+        dev = self.device
+        ids = []
+        for f in self.order:
+            t = feats[self.names[f]]
+            if t.dim() == 1:
+                t = t.unsqueeze(1)
+            if t.shape[1] != 1:
+                raise ValueError(f"hybrid placement holds single-id features; {self.names[f]!r} has {t.shape[1]} ids per row")
+            ids.append(t.to(dev, dtype=torch.int64, non_blocking=True).contiguous())
+        if dense is not None:
+            dense = dense.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        return _HybridLookupFn.apply(self, ids, dense, *list(self.shards))
+
+    def _forward(self, ids_list, dense):
+        B = ids_list[0].shape[0]
+        dev, D, F = self.device, self.D, self.num_features
+        self._dense_width = 0 if dense is None else dense.shape[1]
+        train = self.training and torch.is_grad_enabled()
+        if train:
+            self._ensure_buffers(B)
+        self._ids = ids_list
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        width = F * D + self._dense_width
+        stride = (width + 3) // 4 * 4
+        x = torch.empty(B, stride, dtype=torch.float32, device=dev)
+        extra = torch.empty(B, dtype=torch.float32, device=dev) if self.fused_extra else None
+        fm_sum = None
+        if self.fm:
+            fm_sum = self._fm_buf.tensor(torch.float32, (B, D)) if train else torch.empty(B, D, dtype=torch.float32, device=dev)
+        call = ops.make_group(self._lookup_specs(ids_list), B, x, stride, dense=dense, dense_col=F * D,
+                              zero_from=width if stride > width else -1, status=status, extra=extra, fm_sum=fm_sum, fm=self.fm)
+        ops.emb_pool_fwd_sharded(call, self._shard_l, self._table_ptrs[0], self._table_ptrs[1] if self.has_twins else None)
+        if train:
+            # everything the backward needs that depends on the ids only runs on a side stream next to the tower: the sort of
+            # the replicated features' slots, the bucketing of the sharded features' slots by owner, the meeting with the other
+            # ranks and the owner-side gather + sort
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=dev)
+            if not torch.cuda.is_current_stream_capturing():
+                for t in ids_list:
+                    t.record_stream(self._side)
+            main = torch.cuda.current_stream(dev)
+            capturing = torch.cuda.is_current_stream_capturing()
+            route_call = plan_call = rep_call = None
+            if self.sh:
+                route_call = ops.make_group(self._route_specs(ids_list), B, None, stride, status=status)
+                need = ops.route_p2p_workspace_bytes(route_call)
+                if self._route_ws is None or self._route_ws.numel() < need:
+                    self._route_ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+                plan_call = ops.make_group(self._owner_specs(False), self._cap[0], None, self._stride)
+                need = ops.emb_bwd_p2p_workspace_bytes(plan_call, self.world)
+                if self._plan_ws is None or self._plan_ws.numel() < need:
+                    if capturing:
+                        raise RuntimeError("run one eager step before capturing: the owner-side workspace is not sized yet")
+                    self._plan_ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+            if self.rp:
+                rep_call = ops.make_group(self._rep_bwd_specs(ids_list, plan=True), B, None, stride, status=status)
+                need = ops.emb_bwd_workspace_bytes(rep_call)
+                if self._rep_ws is None or self._rep_ws.numel() < need:
+                    if capturing:
+                        raise RuntimeError("run one eager step before capturing: the plan workspace is not sized yet")
+                    self._rep_ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                if route_call is not None:
+                    rp = self._route_buf.ptr
+                    ops.route_p2p_build(route_call, self._shard_s, rp, rp + 256, rp + 256 + 4 * self._S, self._route_ws)
+                    self.transport.barrier()                 # every rank's routing lists are in place
+                    ops.emb_bwd_plan_p2p(plan_call, self._shard_s, self._peer_counts, self._peer_keys, self._peer_slots, self._plan_ws)
+                if rep_call is not None:
+                    ops.emb_bwd_plan(rep_call, self._rep_ws, runs=False)
+            self._route_pending = True
+        self.status = status
+        return x, extra
+
+    def _backward(self, gx, gextra):
+        if self.binding is None:
+            raise RuntimeError("hybrid tables need bind_optimizer(): there is no dense or sparse .grad to hand back")
+        dev, D = self.device, self.D
+        ids_list = self._ids
+        B = ids_list[0].shape[0]
+        if self._route_pending:
+            torch.cuda.current_stream(dev).wait_stream(self._side)
+            self._route_pending = False
+        gbuf = self._grad_buf.tensor(torch.float32, (B, self._stride))
+        if gx is None:
+            gbuf.zero_()
+        elif gx.data_ptr() != self._grad_buf.ptr:          # (the tower's first block may have written it in place)
+            gbuf.copy_(gx)
+        ge = None
+        if self.fused_extra:
+            ge = self._gextra[:B]
+            if gextra is None:
+                ge.zero_()
+            else:
+                ge.copy_(gextra.reshape(-1))
+        self._ensure_state()
+        opt = self.binding.next_opt()
+        nw = len(self.dims)
+        fm_sum = self._fm_buf.tensor(torch.float32, (B, D)) if self.fm else None
+        if self.rp:                                        # replicated tables: this rank's summed row gradients -> dense buffer
+            call = ops.make_group(self._rep_bwd_specs(ids_list), B, gbuf, self._stride, extra=ge, fm_sum=fm_sum, fm=self.fm)
+            ops.emb_bwd_apply(call, self._rep_ws, ops.make_opt("grad_out"))
+        if self.sh:
+            self.transport.barrier()                       # every rank's gradients (and routing lists) are in place
+            call = ops.make_group(self._owner_specs(True), self._cap[0], None, self._stride, extra=ge)
+            ops.emb_bwd_apply_p2p(call, self._shard_s, self._plan_ws, opt, self._peer_grads,
+                                  peer_extra=self._peer_extra, peer_fm_sum=self._peer_fm)
+        if self.rp:
+            self.transport.all_reduce(self._rep_grad)      # also the closing barrier: nobody overwrites what an owner still reads
+            R = max(self.R, 4)
+            st = self.opt_state
+            ops.rows_dense_apply(self.shards[nw].data, self._rep_grad[:R * D], None if st[nw] is None else st[nw], opt)
+            if self.has_twins:
+                ops.rows_dense_apply(self.shards[nw + 1].data, self._rep_grad[R * D:], None if st[nw + 1] is None else st[nw + 1], opt)
+        else:
+            self.transport.barrier()
+
+    def grad_buffer_provider(self, w):
+        """A callable returning this rank's peer-visible gradient matrix as a tensor [B, stride]: whoever produces
+        dL/d(pooled output) may write it there directly and hand it back through autograd."""
+        def provider():
+            if self._cap is None or w != 0:
+                return None
+            return self._grad_buf.tensor(torch.float32, (self._cap[0], self._stride))
+        return provider
+
+    # ---- checkpoints in the reference's (unsharded) format ------------------------------------------------------------
+    def _gather_width(self, sources, wi):
+        """Full per-feature tensors (CPU) of width ``wi`` from (shard-shaped tensor, replicated-block tensor)."""
+        torch.cuda.synchronize(self.device)
+        shard_t, rep_t = sources
+        mine = []
+        for j, f in enumerate(self.sh):
+            _, n = owned_rows(self.num_rows[f], j, self.rank, self.world)
+            b = self.base[self.rank][j]
+            mine.append(shard_t[b:b + n].detach().cpu())
+        parts = self.transport.all_gather_object(mine)
+        Dw = self.dims[wi]
+        full = [None] * self.num_features
+        for j, f in enumerate(self.sh):
+            v = self.num_rows[f]
+            t = torch.empty(v, Dw, dtype=torch.float32)
+            for r in range(self.world):
+                fr, n = owned_rows(v, j, r, self.world)
+                if n:
+                    t[fr::self.world] = parts[r][j].view(-1, Dw)
+            full[f] = t
+        for f in self.rp:
+            o, v = self.rep_off[f], self.num_rows[f]
+            full[f] = rep_t[o:o + v].detach().cpu().view(v, Dw).clone()
+        return full
+
+    def export_full_tables(self, w: int = 0):
+        """Collective.  Every rank gets the full ``[V_f, dims[w]]`` table of every feature (CPU tensors, feature order), i.e.
+        what ``model.embeddings[name].weight`` holds in the reference (``torchctr/trainer.py:353-496``)."""
+        nw = len(self.dims)
+        return self._gather_width((self.shards[w].data, self.shards[nw + w].data), w)
+
+    def export_full_optimizer_state(self, w: int = 0):
+        nw = len(self.dims)
+        if self.opt_state[w] is None:
+            self.transport.all_gather_object(None)
+            return None, None
+        return self._gather_width((self.opt_state[w], self.opt_state[nw + w]), w), None
+
+    def _scatter_width(self, full, shard_t, rep_t, wi):
+        Dw = self.dims[wi]
+        for j, f in enumerate(self.sh):
+            t = full[f]
+            if tuple(t.shape) != (self.num_rows[f], Dw):
+                raise ValueError(f"table {f}: expected {(self.num_rows[f], Dw)}, got {tuple(t.shape)}")
+            fr, n = owned_rows(self.num_rows[f], j, self.rank, self.world)
+            if n:
+                b = self.base[self.rank][j]
+                shard_t[b:b + n].copy_(t[fr::self.world].to(self.device).view(n, -1))
+        for f in self.rp:
+            t = full[f]
+            if tuple(t.shape) != (self.num_rows[f], Dw):
+                raise ValueError(f"table {f}: expected {(self.num_rows[f], Dw)}, got {tuple(t.shape)}")
+            o, v = self.rep_off[f], self.num_rows[f]
+            rep_t[o:o + v].copy_(t.to(self.device).view(v, -1))
+
+    def load_full_tables(self, full, w: int = 0) -> None:
+        """Scatter full tables (one ``[V_f, dims[w]]`` tensor per feature, e.g. from a reference checkpoint) into this rank's
+        shard and replicated block.  Every rank calls it with the same tensors; optimizer state is reset."""
+        nw = len(self.dims)
+        with torch.no_grad():
+            self._scatter_width(full, self.shards[w].data, self.shards[nw + w].data, w)
+        self.opt_state = [None] * (2 * nw)
+        self.transport.barrier()
+
+    def load_full_optimizer_state(self, state, w: int = 0) -> None:
+        full = state[0]
+        if full is None:
+            return
+        nw = len(self.dims)
+        if self.opt_state[0] is None:
+            self.opt_state = [torch.zeros_like(p.data) for p in self.shards]
+        self._scatter_width(full, self.opt_state[w], self.opt_state[nw + w], w)
+
+    def local_rows_of(self, w, f):
+        """(first global row, this rank's rows) of feature ``f``, width ``w``: a stride-``world`` slice for a sharded table,
+        the whole table (first row 0) for a replicated one."""
+        nw = len(self.dims)
+        if f in self.rep_off:
+            o, v = self.rep_off[f], self.num_rows[f]
+            return 0, self.shards[nw + w].data[o:o + v]
+        j = self.sh.index(f)
+        fr, n = owned_rows(self.num_rows[f], j, self.rank, self.world)
+        b = self.base[self.rank][j]
+        return fr, self.shards[w].data[b:b + n]

@@ -6,7 +6,8 @@ import torch.nn as nn
 from .sharded import ShardedTables, reduce_dense_grads
 
 
-def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=None, dedup=None, init_seed=None):
+def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=None, dedup=None, init_seed=None, hybrid=None,
+                replicate_max_rows: int = 1 << 17):
     """Every rank calls this with an identically initialised ``model`` (same seed).  The model's tables
     (and, for DeepFM, its first-order tables, which share the ids) are cut into this rank's rows, fused
     into one shard per width on ``device`` and the full tables are dropped; the dense part stays
@@ -16,6 +17,10 @@ def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=
         (loss / world).backward()            # tables are updated inside backward
         model.reduce_dense_grads()           # one all-reduce for the tower
         optimizer.step()
+
+    ``hybrid`` (peer mode; default: on when the model qualifies and has small tables or DeepFM's fused terms): tables with at
+    most ``replicate_max_rows`` rows stay replicated on every rank (their gradients are all-reduced densely), the others are
+    row-sharded -- ``parallel.hybrid.HybridShardedTables``.
     """
     groups = model._groups
     full = [[g.tables[n] for n in g.names] for g in groups]
@@ -28,8 +33,19 @@ def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=
             transport = IpcTransport(pg, device)
         if dedup is None:                     # the requester-side sort pays off once nearly all rows are remote: measured
             dedup = transport.world > 4       # -10 % at 2 GPUs, +6 % at 8
-        # tables declared on the meta device (model built with table_device='meta') are created shard by shard, in place
-        sharded = PeerShardedTables(groups[0].names, full, transport, device, dedup=dedup, init_seed=init_seed)
+        from .hybrid import HybridShardedTables, hybrid_eligible
+        twins = full[1] if len(full) == 2 and all(t.embedding_dim == 1 for t in full[1]) else None
+        can = len(full) <= 2 and (len(full) == 1 or twins is not None) and hybrid_eligible(full[0], twins)
+        if hybrid is None:
+            hybrid = can and dedup is not True and (twins is not None or any(t.num_embeddings <= replicate_max_rows for t in full[0]))
+        if hybrid and not can:
+            raise NotImplementedError("hybrid placement needs single-id sum-pooled tables of one width (16 / 32 / 64)")
+        if hybrid:
+            sharded = HybridShardedTables(groups[0].names, full[0], twins, transport, device, fm=bool(getattr(model, "_fm_term", False)),
+                                          replicate_max_rows=replicate_max_rows, init_seed=init_seed)
+        else:
+            # tables declared on the meta device (model built with table_device='meta') are created shard by shard, in place
+            sharded = PeerShardedTables(groups[0].names, full, transport, device, dedup=dedup, init_seed=init_seed)
     elif device is not None:
         # shards are built on the target device straight from the (host) full tables
         import torch

@@ -109,6 +109,10 @@ class IpcTransport:
         dist.all_gather_object(out, obj, group=self.pg)
         return out
 
+    def all_reduce(self, t: torch.Tensor) -> None:
+        """In-place sum over the ranks (NCCL, on the current stream; capturable)."""
+        dist.all_reduce(t, group=self.pg)
+
     def all_gather_tensor(self, t: torch.Tensor) -> torch.Tensor:
         """[n, ...] on every rank (same shape) -> [world * n, ...] in rank order (NCCL all-gather on the current stream)."""
         out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
@@ -147,6 +151,17 @@ class ThreadTransport:
     def all_gather_tensor(self, t: torch.Tensor) -> torch.Tensor:
         torch.cuda.synchronize(self.device)
         return torch.cat(self.all_gather_object(t), 0)
+
+    def all_reduce(self, t: torch.Tensor) -> None:
+        torch.cuda.synchronize(self.device)
+        parts = self.all_gather_object(t)
+        total = parts[0].clone()
+        for p in parts[1:]:                 # rank order on every rank: all replicas get bit-identical sums
+            total += p
+        torch.cuda.synchronize(self.device)
+        self.shared.barrier.wait()          # everybody has read everybody's input
+        t.copy_(total)
+        torch.cuda.synchronize(self.device)
 
     def all_gather_object(self, obj):
         key = ("obj", self._seq)
