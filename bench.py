@@ -454,6 +454,41 @@ def trainer_fit_leg(cfg, model, opt, host_batches, steps):
                    "loss.item() per step, eager launches, one evaluation batch included in the wall time"}
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this process (and first-touch its pinned buffers) on the CPUs NVML names as local to the GPU: a host-to-device
+    copy from the far socket of a two-socket box runs at half the PCIe rate.  Best effort."""
+    orig = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:       # noqa: BLE001 -- no NVML / no permission: keep the default placement
+        pass
+    return orig
+
+
+def parallelism_note(model, world):
+    if world == 1:
+        return "single GPU"
+    sh = getattr(model, "_sharded", None)
+    if hasattr(sh, "rp"):
+        rows_rep = sum(sh.num_rows[f] for f in sh.rp)
+        return (f"hybrid placement over {world} GPUs: {len(sh.rp)} tables ({rows_rep} rows) replicated -- read locally, their summed row "
+                f"gradients all-reduced densely ({sh._rep_grad.numel() * 4 / 1e6:.1f} MB, one NCCL all-reduce that also carries the tower's "
+                f"gradients) and applied by every replica -- and {len(sh.sh)} tables row-sharded (owner = (row + table) mod P): rows read "
+                "through NVLink peer mappings inside the lookup kernel, owners pull the (row, slot) lists and gradients inside the update "
+                "kernel (no all-to-all); batch data-parallel, tower replicated")
+    return (f"tables row-sharded over {world} GPUs (owner = (row + table) mod P); rows read and gradients pulled through NVLink peer "
+            "mappings inside the lookup / update kernels (no all-to-all), batch data-parallel, tower replicated + one NCCL all-reduce"
+            + ("; requester-side de-duplication: every distinct row crosses NVLink once per direction" if getattr(sh, "dedup", False) else ""))
+
+
 def run_ours(args):
     import torch.distributed as dist
     from torchctr_b200 import ops
@@ -467,6 +502,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = bind_to_gpu_numa_node(local)             # before any pinned allocation: host buffers on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch or cfg["batch"]
@@ -484,7 +520,10 @@ def run_ours(args):
         dedup = {"auto": None, "on": True, "off": False}[args.dedup]
         if cfg["seq"] and cfg["seq"].get("growing"):
             dedup = False                                 # growing vocabularies run the direct exchange
-        model = shard_model(model, None, device=dev, dedup=dedup, init_seed=0)   # this rank's rows of every table only
+        hybrid = {"auto": None, "on": True, "off": False}[args.hybrid]
+        # cfg2 / cfg3: hybrid placement (tables <= --replicate-max-rows rows replicated, the rest row-sharded); cfg4 / cfg5: every
+        # table row-sharded
+        model = shard_model(model, None, device=dev, dedup=dedup, init_seed=0, hybrid=hybrid, replicate_max_rows=args.replicate_max_rows)
     elif native:
         model.materialize_tables(dev, seed=0)
     model = model.to(dev).train()
@@ -531,7 +570,7 @@ def run_ours(args):
     first_losses = []
     for i in range(max(args.warmup, 3)):                 # eager warm-up (also sizes workspaces / optimizer state)
         loss = eager_step(resident[i % nb], i)
-        if i < 2:
+        if i < 5:
             first_losses.append(loss.detach().clone())
         del loss        # a live loss keeps its autograd graph (and AccumulateGrad nodes bound to THIS stream) alive into the capture
     # N > 1: the global-batch loss of the first two steps (mean over the ranks' losses), printed so that runs at different
@@ -572,12 +611,14 @@ def run_ours(args):
         packed = [graphed.pack(b) for b in resident]     # resident leg: one device-to-device copy per step, like the e2e leg
         host_packed = [graphed.pack(b, "cpu") for b in host]    # e2e leg: each batch is ONE pinned host block (one H2D copy)
 
-    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
-    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    LAG = 3                                   # the host reads step i's loss while steps i+1 .. i+LAG-1 are queued / running
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(LAG + 1)]
+    loss_ev = [torch.cuda.Event() for _ in range(LAG + 1)]
 
     def timed(batches, steps, read_loss):
-        """read_loss (the end-to-end leg): every step's loss is copied to pinned host memory and read by the host -- one step
-        late, i.e. while the next step already runs, so that the readback does not leave the GPU idle between steps."""
+        """read_loss (the end-to-end leg): every step's loss is copied to pinned host memory and read by the host -- up to LAG - 1
+        steps late, i.e. while the next steps already run, so that neither the readback nor a slow moment of the host leaves the
+        GPU idle between steps.  Every loss is read inside the timed region."""
         barrier()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
@@ -586,19 +627,22 @@ def run_ours(args):
         if prefetch is not None:
             prefetch(batches[0])
         seen = 0
+        nslot = LAG + 1
         for i in range(steps):
             loss = step(batches[i % nb], i)
             if read_loss:
-                loss_host[i % 2].copy_(loss.detach(), non_blocking=True)     # device -> host copy of this step's result
-                loss_ev[i % 2].record()
+                loss_host[i % nslot].copy_(loss.detach(), non_blocking=True)     # device -> host copy of this step's result
+                loss_ev[i % nslot].record()
                 if prefetch is not None and i + 1 < steps:
                     prefetch(batches[(i + 1) % nb])      # next batch's host -> device copy runs under this step
-                if i > 0:
-                    loss_ev[(i - 1) % 2].synchronize()
-                    seen += float(loss_host[(i - 1) % 2]) == float(loss_host[(i - 1) % 2])
+                j = i - (LAG - 1)
+                if j >= 0:
+                    loss_ev[j % nslot].synchronize()
+                    seen += float(loss_host[j % nslot]) == float(loss_host[j % nslot])
         if read_loss:
-            loss_ev[(steps - 1) % 2].synchronize()
-            seen += float(loss_host[(steps - 1) % 2]) == float(loss_host[(steps - 1) % 2])
+            for j in range(max(steps - (LAG - 1), 0), steps):
+                loss_ev[j % nslot].synchronize()
+                seen += float(loss_host[j % nslot]) == float(loss_host[j % nslot])
             assert seen == steps, "a loss read back from the device was NaN"
         t1.record()
         barrier()
@@ -634,6 +678,7 @@ def run_ours(args):
         step(e2e_batches[i % nb], i)
     ms_e2e = timed(e2e_batches, args.steps, read_loss=True)
     clock_info = clocks.stop() if rank == 0 else None
+    os.sched_setaffinity(0, all_cpus)                   # the CPU-baseline leg below uses every host core again
 
     value = B * world * args.steps / (ms / 1e3)
     e2e = B * world * args.steps / (ms_e2e / 1e3)
@@ -698,11 +743,7 @@ def run_ours(args):
         "roofline": roofline_tensor if roofline_tensor is not None else roofline,
         "roofline_embedding": roofline if roofline_tensor is not None else None,
         "trainer_fit": trainer_leg, "loss_first_steps": loss_trace, "loss_step0_rank0": rank0_first,
-        "parallelism": "single GPU" if world == 1 else f"tables row-sharded over {world} GPUs (owner = (row + table) mod P); rows read "
-                       "and gradients pulled through NVLink peer mappings inside the lookup / update kernels (no all-to-all), "
-                       "batch data-parallel, tower replicated + one NCCL all-reduce"
-                       + ("; requester-side de-duplication: every distinct row crosses NVLink once per direction"
-                          if getattr(getattr(model, "_sharded", None), "dedup", False) else ""),
+        "parallelism": parallelism_note(model, world),
         "clocks": clock_info,
         "tower_matmul": "tcgen05 kernels (ctr_linear_fwd forward / dgrad, ctr_linear_wgrad), fp32 accumulate in TMEM; precision "
                         + args.precision + " (parity: tests/test_gpu_precision.py)",
@@ -774,6 +815,9 @@ def main():
     ap.add_argument("--roofline-only", action="store_true", help="only time the embedding entry points (ncu target)")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3"], help="tower GEMM precision of the headline run")
     ap.add_argument("--no-exact", action="store_true", help="skip the extra timing of the 3xTF32 mode")
+    ap.add_argument("--hybrid", default="auto", choices=["auto", "on", "off"],
+                    help="N > 1: replicate small tables, shard large ones (auto: when the model qualifies: cfg2, cfg3)")
+    ap.add_argument("--replicate-max-rows", type=int, default=1 << 17, help="hybrid placement: tables up to this many rows are replicated")
     ap.add_argument("--dedup", default="auto", choices=["auto", "on", "off"],
                     help="N > 1: fetch / send every distinct row once (auto: above 4 GPUs)")
     args = ap.parse_args()

@@ -945,22 +945,33 @@ __global__ void __launch_bounds__(256)
     rows_dense_apply_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restrict__ s, long long n4, int kind,
                             ctr_hyper_t h, const ctr_hyper_t *__restrict__ hd, int clear) {
     if (hd != nullptr) h = *hd;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 gr = g[i];
-        if (gr.x == 0.f && gr.y == 0.f && gr.z == 0.f && gr.w == 0.f) continue;
-        float4 w = p[i];
-        if (kind == CTR_OPT_SGD) {
-            w.x -= h.lr * gr.x; w.y -= h.lr * gr.y; w.z -= h.lr * gr.z; w.w -= h.lr * gr.w;
-        } else {
-            float4 st = s[i];
-            w.x = adagrad_elem(w.x, st.x, gr.x, h.lr, h.eps);
-            w.y = adagrad_elem(w.y, st.y, gr.y, h.lr, h.eps);
-            w.z = adagrad_elem(w.z, st.z, gr.z, h.lr, h.eps);
-            w.w = adagrad_elem(w.w, st.w, gr.w, h.lr, h.eps);
-            s[i] = st;
+    constexpr int U = 4;                       // gradient loads in flight per thread
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += U * stride) {
+        float4 gr[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            gr[u] = i < n4 ? __ldcs(g + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        p[i] = w;
-        if (clear) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (gr[u].x == 0.f && gr[u].y == 0.f && gr[u].z == 0.f && gr[u].w == 0.f) continue;
+            float4 w = p[i];
+            if (kind == CTR_OPT_SGD) {
+                w.x -= h.lr * gr[u].x; w.y -= h.lr * gr[u].y; w.z -= h.lr * gr[u].z; w.w -= h.lr * gr[u].w;
+            } else {
+                float4 st = s[i];
+                w.x = adagrad_elem(w.x, st.x, gr[u].x, h.lr, h.eps);
+                w.y = adagrad_elem(w.y, st.y, gr[u].y, h.lr, h.eps);
+                w.z = adagrad_elem(w.z, st.z, gr[u].z, h.lr, h.eps);
+                w.w = adagrad_elem(w.w, st.w, gr[u].w, h.lr, h.eps);
+                s[i] = st;
+            }
+            p[i] = w;
+            if (clear) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
 }
 
@@ -994,7 +1005,7 @@ extern "C" int ctr_rows_dense_apply(const ctr_opt_t *opt, float *params, float *
     ctr_hyper_t h;
     ctr_opt_hyper(opt, &h);
     const long long n4 = n / 4;
-    long long bx = (n4 + 1023) / 1024;
+    long long bx = (n4 + 1023) / 1024;         // 4 float4 per thread
     if (bx > kNumSMs * 8) bx = kNumSMs * 8;
     note_launch(), rows_dense_apply_kernel<<<(unsigned)bx, 256, 0, (cudaStream_t)stream_>>>(
         reinterpret_cast<float4 *>(params), reinterpret_cast<float4 *>(grads), reinterpret_cast<float4 *>(state0), n4, opt->kind, h,

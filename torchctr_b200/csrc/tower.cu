@@ -327,16 +327,14 @@ __global__ void __launch_bounds__(kTowerThreads)
             if (ok) {
                 const float4 v = ld4(a.h + (size_t)r * a.ldh + 4 * cg);
                 d = v.x * w4.x + v.y * w4.y + v.z * w4.z + v.w * w4.w;
+                // second linear term: the row team's lanes share its ne columns (coalesced), the shuffle sum below adds them up
+                for (int j = cg; j < a.ne; j += g.CG) d = fmaf(__ldg(a.xe + (size_t)r * a.ldxe + j), __ldg(a.we + j), d);
             }
             for (int off = 1; off < g.CG; off <<= 1) d += __shfl_xor_sync(kFull, d, off);
             if (ok && cg == 0) {
                 float z = d + b0;
                 if (a.extra != nullptr) z += __ldg(a.extra + (size_t)r * a.extra_stride);
-                if (a.xe != nullptr) {
-                    float e = a.be != nullptr ? __ldg(a.be) : 0.f;
-                    for (int j = 0; j < a.ne; ++j) e = fmaf(__ldg(a.xe + (size_t)r * a.ldxe + j), __ldg(a.we + j), e);
-                    z += e;
-                }
+                if (a.xe != nullptr && a.be != nullptr) z += __ldg(a.be);
                 const float y = __ldg(a.labels + (size_t)r * a.label_stride);
                 // max(z, 0) - z y + log1p(exp(-|z|)): torch's stable form
                 loss_acc += fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));
@@ -380,7 +378,7 @@ __global__ void __launch_bounds__(kTowerThreads)
     __shared__ float4 red[kTowerThreads];
     const int cg = threadIdx.x % g.CG, rl = threadIdx.x / g.CG;
     float4 acc[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
-    float xacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float xacc[4] = {0.f, 0.f, 0.f, 0.f};      // ne <= 32 columns over CG >= 8 lanes (H >= 32): at most 4 per lane
     if (rl < g.RL) {
         const float gs = __ldg(gscale);
         const float4 w4 = ld4(w + 4 * cg);
@@ -401,7 +399,7 @@ __global__ void __launch_bounds__(kTowerThreads)
             }
             if (xe != nullptr) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < 4; ++k) {
                     const int j = cg + k * g.CG;
                     if (j < ne) xacc[k] = fmaf(d, __ldg(xe + (size_t)r * ldxe + j), xacc[k]);
                 }
@@ -412,7 +410,8 @@ __global__ void __launch_bounds__(kTowerThreads)
     if (xe != nullptr) {      // per-block partial of the second term's weight gradient: [block][32], fixed order over the row lanes
         float *sx = reinterpret_cast<float *>(red);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 4; ++k) {
+            if (k * g.CG >= ne) break;            // (block-uniform)
             const int j = cg + k * g.CG;
             __syncthreads();
             if (rl < g.RL && j < 32) sx[rl * 32 + j] = xacc[k];
@@ -427,13 +426,16 @@ __global__ void __launch_bounds__(kTowerThreads)
 }
 
 // gwe[j] = g sum over blocks of xe_partial[block][j]; gbe = g sum dz is the head's own bias gradient (same number)
-__global__ void head_xe_finalize_kernel(const float *__restrict__ xe_partial, int blocks, int ne, const float *__restrict__ gscale,
-                                        float *__restrict__ gwe) {
-    const int j = threadIdx.x;
+// (one warp per column: lane l adds the blocks l, l + 32, ... in double, then a shuffle tree -- a fixed order)
+__global__ void __launch_bounds__(1024)
+    head_xe_finalize_kernel(const float *__restrict__ xe_partial, int blocks, int ne, const float *__restrict__ gscale,
+                            float *__restrict__ gwe) {
+    const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (j >= ne) return;
     double t = 0.0;
-    for (int b = 0; b < blocks; ++b) t += (double)xe_partial[(size_t)b * 32 + j];
-    gwe[j] = (float)((double)__ldg(gscale) * t);
+    for (int b = lane; b < blocks; b += 32) t += (double)xe_partial[(size_t)b * 32 + j];
+    for (int off = 16; off; off >>= 1) t += __shfl_xor_sync(kFull, t, off);
+    if (lane == 0) gwe[j] = (float)((double)__ldg(gscale) * t);
 }
 
 __global__ void __launch_bounds__(kFinCols * kFinLanes)
@@ -619,7 +621,7 @@ extern "C" int ctr_logit_bce_bwd_ex(const float *h, int64_t ldh, int32_t B, int3
     note_launch(), head_bwd_kernel<<<g.blocks, kTowerThreads, 0, stream>>>(h, ldh, w, dz, gscale, g, gh, ldgh, gextra, gextra_stride, partial,
                                                                            xe, ldxe, xe ? ne : 0, xe_partial);
     note_launch(), head_bwd_finalize_kernel<<<(H + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, stream>>>(partial, g.blocks, H, gscale, gw, gb);
-    if (xe != nullptr) note_launch(), head_xe_finalize_kernel<<<1, 32, 0, stream>>>(xe_partial, g.blocks, ne, gscale, gwe);
+    if (xe != nullptr) note_launch(), head_xe_finalize_kernel<<<1, 32 * ((ne + 0) > 0 ? ne : 1), 0, stream>>>(xe_partial, g.blocks, ne, gscale, gwe);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }

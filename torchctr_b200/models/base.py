@@ -164,7 +164,13 @@ class CTRModelBase(nn.Module):
         ``optimizer.zero_grad(set_to_none=True)`` afterwards, which would drop the views."""
         params = [p for p in self.dense_parameters() if p.requires_grad]
         total = sum(p.numel() for p in params)
-        flat = torch.zeros(total, dtype=torch.float32, device=params[0].device)
+        flat = None
+        adopt = getattr(self._sharded, "adopt_dense_grads", None)
+        if adopt is not None:                 # hybrid placement: the buffer rides in the all-reduce of the replicated tables'
+            flat = adopt(total)               # gradients at the end of backward; reduce_dense_grads() is then a no-op
+            self._dense_grads_reduced_in_backward = flat is not None
+        if flat is None:
+            flat = torch.zeros(total, dtype=torch.float32, device=params[0].device)
         off = 0
         for p in params:
             p.grad = flat[off:off + p.numel()].view_as(p)

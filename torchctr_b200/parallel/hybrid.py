@@ -153,7 +153,8 @@ class HybridShardedTables(nn.Module):
         # shards[0 .. nw): this rank's shard of every width; shards[nw .. 2 nw): the replicated block of every width
         self.shards = nn.ParameterList(params)
         # gradient buffer of the replicated block: [R, D] then [R] (twins), ONE flat tensor = one all-reduce
-        self._rep_grad = torch.zeros(max(R, 4) * (D + (1 if self.has_twins else 0)), dtype=torch.float32, device=dev)
+        self._rep_elems = max(R, 4) * (D + (1 if self.has_twins else 0))
+        self._rep_grad = torch.zeros(self._rep_elems, dtype=torch.float32, device=dev)
         self.opt_state = [None] * (2 * nw)      # adagrad sums, same shapes as self.shards
         self.bindings = [None]
         self.binding = None
@@ -245,7 +246,7 @@ class HybridShardedTables(nn.Module):
         rep_w = self.shards[nw].data
         rep_t = self.shards[nw + 1].data if self.has_twins else None
         g_main = self._rep_grad[:R * D].view(R, D)
-        g_twin = self._rep_grad[R * D:] if self.has_twins else None
+        g_twin = self._rep_grad[R * D:R * D + R] if self.has_twins else None
         specs = []
         for j, f in enumerate(self.order):
             if j < len(self.sh):
@@ -295,13 +296,17 @@ class HybridShardedTables(nn.Module):
             ids.append(t.to(dev, dtype=torch.int64, non_blocking=True).contiguous())
         if dense is not None:
             dense = dense.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        self._want_backward = self.training and torch.is_grad_enabled()      # (grad mode is off inside Function.forward)
         return _HybridLookupFn.apply(self, ids, dense, *list(self.shards))
+
+    _want_backward = None
 
     def _forward(self, ids_list, dense):
         B = ids_list[0].shape[0]
         dev, D, F = self.device, self.D, self.num_features
         self._dense_width = 0 if dense is None else dense.shape[1]
-        train = self.training and torch.is_grad_enabled()
+        train = self._want_backward if self._want_backward is not None else (self.training and torch.is_grad_enabled())
+        self._want_backward = None
         if train:
             self._ensure_buffers(B)
         self._ids = ids_list
@@ -384,23 +389,49 @@ class HybridShardedTables(nn.Module):
         opt = self.binding.next_opt()
         nw = len(self.dims)
         fm_sum = self._fm_buf.tensor(torch.float32, (B, D)) if self.fm else None
-        if self.rp:                                        # replicated tables: this rank's summed row gradients -> dense buffer
-            call = ops.make_group(self._rep_bwd_specs(ids_list), B, gbuf, self._stride, extra=ge, fm_sum=fm_sum, fm=self.fm)
-            ops.emb_bwd_apply(call, self._rep_ws, ops.make_opt("grad_out"))
+        main = torch.cuda.current_stream(dev)
         if self.sh:
             self.transport.barrier()                       # every rank's gradients (and routing lists) are in place
-            call = ops.make_group(self._owner_specs(True), self._cap[0], None, self._stride, extra=ge)
+        if self.rp:
+            # replicated tables, on a second stream NEXT TO the owner-side update of the sharded tables: this rank's summed row
+            # gradients -> dense buffer, all-reduce (the tower's flat gradient buffer rides along), dense update of every replica
+            side = self._side2 if self.sh else main
+            if self.sh and side is None:
+                side = self._side2 = torch.cuda.Stream(device=dev)
+            if side is not main:
+                side.wait_stream(main)
+            with torch.cuda.stream(side):
+                call = ops.make_group(self._rep_bwd_specs(ids_list), B, gbuf, self._stride, extra=ge, fm_sum=fm_sum, fm=self.fm)
+                ops.emb_bwd_apply(call, self._rep_ws, ops.make_opt("grad_out"))
+                self.transport.all_reduce(self._rep_grad)
+                R = max(self.R, 4)
+                st = self.opt_state
+                ops.rows_dense_apply(self.shards[nw].data, self._rep_grad[:R * D], None if st[nw] is None else st[nw], opt)
+                if self.has_twins:
+                    ops.rows_dense_apply(self.shards[nw + 1].data, self._rep_grad[R * D:R * D + R],
+                                         None if st[nw + 1] is None else st[nw + 1], opt)
+        if self.sh:
+            call = ops.make_group(self._owner_specs(True), self._cap[0], None, self._stride, extra=self._gextra if self.fused_extra else None)
             ops.emb_bwd_apply_p2p(call, self._shard_s, self._plan_ws, opt, self._peer_grads,
                                   peer_extra=self._peer_extra, peer_fm_sum=self._peer_fm)
-        if self.rp:
-            self.transport.all_reduce(self._rep_grad)      # also the closing barrier: nobody overwrites what an owner still reads
-            R = max(self.R, 4)
-            st = self.opt_state
-            ops.rows_dense_apply(self.shards[nw].data, self._rep_grad[:R * D], None if st[nw] is None else st[nw], opt)
-            if self.has_twins:
-                ops.rows_dense_apply(self.shards[nw + 1].data, self._rep_grad[R * D:], None if st[nw + 1] is None else st[nw + 1], opt)
-        else:
-            self.transport.barrier()
+            if self.rp and side is not main:
+                main.wait_stream(side)
+            self.transport.barrier()                       # closing: nobody overwrites what an owner still reads / reads rows too early
+        # (no sharded table: the all-reduce above is the only collective, and it is on this stream)
+
+    _side2 = None
+
+    def adopt_dense_grads(self, numel: int):
+        """Room for ``numel`` more floats behind the replicated tables' gradients: the model's flat dense-gradient buffer
+        (``CTRModelBase.enable_flat_dense_grads``) then travels in the same all-reduce, which runs at the end of backward -- the
+        lookup is the first node of the graph, so every dense gradient has been accumulated by then.  Returns the view, or
+        None when there is no replicated table (no all-reduce here)."""
+        if not self.rp:
+            return None
+        flat = torch.zeros(self._rep_elems + (numel + 3) // 4 * 4, dtype=torch.float32, device=self.device)
+        flat[:self._rep_elems].copy_(self._rep_grad)
+        self._rep_grad = flat
+        return flat[self._rep_elems:self._rep_elems + numel]
 
     def grad_buffer_provider(self, w):
         """A callable returning this rank's peer-visible gradient matrix as a tensor [B, stride]: whoever produces

@@ -59,6 +59,8 @@ def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=
             del g.tables[n]
     model._pg = pg
     def _reduce():
+        if getattr(model, "_dense_grads_reduced_in_backward", False):
+            return                              # hybrid placement: already summed with the replicated tables' gradients
         flat = getattr(model, "_flat_dense_grad", None)
         if flat is not None:                    # one all-reduce over the flat gradient buffer, nothing to copy
             import torch.distributed as dist
