@@ -419,6 +419,13 @@ int ctr_emb_bwd_apply_p2p(const ctr_group_t *group, const ctr_shard_t *shard, vo
 int ctr_emb_bwd_apply_p2p_ex(const ctr_group_t *group, const ctr_shard_t *shard, void *workspace, const ctr_opt_t *opt,
                              const float *const *peer_grads, const float *const *peer_extra,
                              const float *const *peer_fm_sum, int64_t *num_unique, void *stream);
+/* Requester side of the same: packed[b, j * D .. (j + 1) * D) = gx[b, cols[j] .. cols[j] + D) + extra_grad[b] * fm_sum[b, :]
+ * for the J sharded features of a bag (cols: HOST array of their first columns in gx; fm_sum NULL = plain copy).  With the
+ * gradients packed like this the owners call ctr_emb_bwd_apply_p2p_ex with peer_grads = the packed matrices (out_col = j * D,
+ * out_stride = J * D), peer_fm_sum = NULL and group->fm = 1: one D-float piece per slot crosses NVLink instead of the
+ * gradient slice plus the bag's fm_sum row; only the "- row * sum(extra_grad)" part of the FM gradient is left to the owner. */
+int ctr_fm_pack_grads(const float *gx, int64_t gx_stride, const float *extra_grad, const float *fm_sum, int32_t B, int32_t D,
+                      const int32_t *cols, int32_t J, float *packed, void *stream);
 
 /* ---- de-duplicated exchange (every distinct row of a rank's batch crosses NVLink once per direction) -----------
  * Requester, forward: plan the group with ctr_emb_bwd_plan (runs listed), then ctr_unique_fetch copies the row of every

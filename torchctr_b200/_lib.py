@@ -134,6 +134,7 @@ _SIGNATURES = {
     "ctr_peer_export": (C.c_int, [_P, _P]),
     "ctr_peer_open": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
     "ctr_peer_close": (C.c_int, [_P]),
+    "ctr_fm_pack_grads": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, _P, _P]),
     "ctr_rows_dense_apply": (C.c_int, [C.POINTER(Opt), _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "ctr_emb_pool_fwd_sharded": (C.c_int, [C.POINTER(Group), C.POINTER(Shard), C.POINTER(C.c_void_p), _P]),
     "ctr_emb_pool_fwd_sharded_ex": (C.c_int, [C.POINTER(Group), C.POINTER(Shard), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _P]),

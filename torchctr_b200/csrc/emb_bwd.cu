@@ -198,6 +198,8 @@ struct ApplyArgs {
     const float *fm_sum;        // [B, D] sum over the fields of the pooled vectors, or null
     const float *peer_extra[CTR_MAX_WORLD];    // sharded owner side: extra_grad / fm_sum of the rank that sent the slot
     const float *peer_fm_sum[CTR_MAX_WORLD];
+    int fm_row_only;            // FM term with the "c * fm_sum" part already folded into the gradients (ctr_fm_pack_grads):
+                                // only "- row * sum c" is left to do here
 };
 
 // last feature whose row_base <= key.  sf is the kernel's parameter copy of the features: sorted positions
@@ -720,7 +722,8 @@ __global__ void __launch_bounds__(kApplyThreads, MINB)
     const int team = lane / TG;
     const int t = lane % TG;
     const unsigned tmask = TG == kWarp ? kFull : (((1u << TG) - 1u) << (team * TG));
-    const bool fm = EXTRA && a.fm_sum != nullptr;
+    const bool fm_gather = EXTRA && a.fm_sum != nullptr;          // add c * fm_sum[bag] to every slot's gradient
+    const bool fm = fm_gather || (EXTRA && a.fm_row_only != 0);    // subtract row * sum c once per row
     const uint32_t S = a.S_dev != nullptr ? min(*a.S_dev, a.S) : a.S;
     const uint32_t first = w * a.range;
     if (first >= S) {
@@ -805,7 +808,7 @@ __global__ void __launch_bounds__(kApplyThreads, MINB)
                 v[u] = __ldg(reinterpret_cast<const float4 *>(gout + (int64_t)sl * gstride + sf[fi].out_col) + t);
                 if (EXTRA) {
                     c[u] = __ldg(ex + sl);
-                    if (fm) {
+                    if (fm_gather) {
                         const float4 s4 = __ldg(reinterpret_cast<const float4 *>(fs + (size_t)sl * D) + t);
                         v[u].x = fmaf(c[u], s4.x, v[u].x); v[u].y = fmaf(c[u], s4.y, v[u].y);
                         v[u].z = fmaf(c[u], s4.z, v[u].z); v[u].w = fmaf(c[u], s4.w, v[u].w);
@@ -937,6 +940,32 @@ __global__ void __launch_bounds__(kApplyThreads, MINB)
     }
 }
 
+// ---- hybrid placement, requester side: per-slot gradients of the SHARDED features, FM part folded in, packed densely ------
+// packed[b, j * D .. (j + 1) * D) = gx[b, cols[j] .. + D) + c[b] * fm_sum[b, :]: the owner then pulls ONE 64-byte (D = 16) piece
+// per slot over NVLink instead of the gradient slice plus the bag's fm_sum row.
+struct PackCols {
+    int32_t col[CTR_MAX_FEATURES];
+};
+
+template <int G>
+__global__ void __launch_bounds__(256)
+    fm_pack_grads_kernel(const float *__restrict__ gx, int64_t gx_stride, const float *__restrict__ c, const float *__restrict__ fm_sum,
+                         int B, int J, const __grid_constant__ PackCols pc, float *__restrict__ packed) {
+    constexpr int D = 4 * G;
+    const int t = threadIdx.x % G;
+    const long long total = (long long)B * J;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G; i < total; i += (long long)gridDim.x * blockDim.x / G) {
+        const int b = (int)(i / J), j = (int)(i - (long long)b * J);
+        float4 v = __ldg(reinterpret_cast<const float4 *>(gx + (size_t)b * gx_stride + pc.col[j]) + t);
+        if (fm_sum != nullptr) {
+            const float cb = __ldg(c + b);
+            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(fm_sum + (size_t)b * D) + t);
+            v.x = fmaf(cb, s4.x, v.x); v.y = fmaf(cb, s4.y, v.y); v.z = fmaf(cb, s4.z, v.z); v.w = fmaf(cb, s4.w, v.w);
+        }
+        reinterpret_cast<float4 *>(packed + (size_t)i * D)[t] = v;
+    }
+}
+
 // ---- replicated tables: dense update from an (all-reduced) gradient buffer -------------------------------------------------
 // p / g / s hold n4 float4 each.  A float4 whose gradient is all zero is skipped (no read of p / s, no write): untouched rows
 // do not move, exactly as the fused sparse update leaves them (sgd / adagrad with g = 0 are the identity anyway).  The
@@ -990,6 +1019,31 @@ extern "C" void ctr_opt_hyper(const ctr_opt_t *opt, ctr_hyper_t *out) {
         const double bc2 = 1.0 - pow(opt->beta2, (double)opt->step);
         out->adam_step_size = (float)(opt->lr * sqrt(bc2) / bc1);
     }
+}
+
+extern "C" int ctr_fm_pack_grads(const float *gx, int64_t gx_stride, const float *extra_grad, const float *fm_sum, int32_t B,
+                                 int32_t D, const int32_t *cols, int32_t J, float *packed, void *stream_) {
+    CTR_REQUIRE(gx != nullptr && packed != nullptr && cols != nullptr, "null pointer");
+    CTR_REQUIRE(fm_sum == nullptr || extra_grad != nullptr, "fm_sum needs extra_grad");
+    CTR_REQUIRE(B >= 0 && J >= 1 && J <= CTR_MAX_FEATURES && (D == 16 || D == 32 || D == 64), "B=%d J=%d D=%d unsupported", B, J, D);
+    CTR_REQUIRE(gx_stride % 4 == 0 && ((reinterpret_cast<uintptr_t>(gx) | reinterpret_cast<uintptr_t>(packed) |
+                                        reinterpret_cast<uintptr_t>(fm_sum)) & 15u) == 0, "operands must be 16-byte aligned");
+    if (B == 0) return CTR_OK;
+    PackCols pc{};
+    for (int j = 0; j < J; ++j) {
+        CTR_REQUIRE(cols[j] >= 0 && cols[j] % 4 == 0 && cols[j] + D <= gx_stride, "cols[%d]=%d outside the gradient row", j, cols[j]);
+        pc.col[j] = cols[j];
+    }
+    const int G = D / 4;
+    long long blocks = ((long long)B * J * G + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    note_launch();
+    if (G == 4) fm_pack_grads_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(gx, gx_stride, extra_grad, fm_sum, B, J, pc, packed);
+    else if (G == 8) fm_pack_grads_kernel<8><<<(unsigned)blocks, 256, 0, stream>>>(gx, gx_stride, extra_grad, fm_sum, B, J, pc, packed);
+    else fm_pack_grads_kernel<16><<<(unsigned)blocks, 256, 0, stream>>>(gx, gx_stride, extra_grad, fm_sum, B, J, pc, packed);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
 }
 
 extern "C" int ctr_rows_dense_apply(const ctr_opt_t *opt, float *params, float *grads, float *state0, int64_t n,
@@ -1077,7 +1131,8 @@ extern "C" int ctr_emb_bwd_plan(const ctr_group_t *group, void *workspace, int64
 static int apply_impl(DevGroup &dg, const PlanLayout &p, void *workspace, const ctr_opt_t *opt, int32_t *uniq_feature,
                       int32_t *uniq_row, float *row_grad, int64_t row_grad_stride, int64_t *num_unique,
                       const float *const *peer_grads, int world, cudaStream_t stream,
-                      const float *const *peer_extra = nullptr, const float *const *peer_fm_sum = nullptr) {
+                      const float *const *peer_extra = nullptr, const float *const *peer_fm_sum = nullptr,
+                      bool fm_row_only = false) {
     const bool updates = opt->kind != CTR_OPT_NONE;
     CTR_REQUIRE(workspace != nullptr, "workspace is null");
     CTR_REQUIRE(opt->kind >= CTR_OPT_NONE && opt->kind <= CTR_OPT_GRAD_OUT, "bad optimizer kind %d", opt->kind);
@@ -1176,6 +1231,7 @@ static int apply_impl(DevGroup &dg, const PlanLayout &p, void *workspace, const 
             }
             a.extra_grad = peer_extra[0];
             a.fm_sum = peer_fm_sum != nullptr ? peer_fm_sum[0] : nullptr;
+            a.fm_row_only = (fm_row_only && peer_fm_sum == nullptr) ? 1 : 0;
         } else {
             a.extra_grad = dg.extra;
             a.fm_sum = dg.fm ? dg.fm_sum : nullptr;
@@ -1394,6 +1450,7 @@ extern "C" int ctr_emb_bwd_apply_p2p_ex(const ctr_group_t *group, const ctr_shar
     CTR_REQUIRE(opt != nullptr && peer_grads != nullptr && peer_extra != nullptr, "null pointer");
     CTR_REQUIRE(group != nullptr && group->extra != nullptr, "group->extra must be set (marks the fused terms; it is not read)");
     ctr_group_t gcopy = *group;
+    const bool fm_row_only = group->fm != 0 && peer_fm_sum == nullptr;   // gradients pre-combined by ctr_fm_pack_grads
     gcopy.fm = 0;                 // the FM sums come from the peers (peer_fm_sum), not from group->fm_sum
     gcopy.fm_sum = nullptr;
     int rc = lower_group(&gcopy, &dg, /*need_tables=*/opt->kind != CTR_OPT_NONE, /*need_out=*/false);
@@ -1407,7 +1464,7 @@ extern "C" int ctr_emb_bwd_apply_p2p_ex(const ctr_group_t *group, const ctr_shar
         f.aligned = al ? 1 : 0;
     }
     return apply_impl(dg, plan_layout(dg, shard->world), workspace, opt, nullptr, nullptr, nullptr, 0, num_unique, peer_grads,
-                      shard->world, (cudaStream_t)stream_, peer_extra, peer_fm_sum);
+                      shard->world, (cudaStream_t)stream_, peer_extra, peer_fm_sum, fm_row_only);
 }
 
 // ---- de-duplicated exchange: every rank fetches / sends each distinct row of its batch once ------------------------

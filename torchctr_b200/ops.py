@@ -284,6 +284,22 @@ def emb_bwd_apply(call: GroupCall, workspace: torch.Tensor, opt: _lib.Opt, uniq_
 
 
 @_guarded
+def fm_pack_grads(gx: torch.Tensor, extra_grad, fm_sum, cols, D: int, packed: torch.Tensor) -> None:
+    """packed[b, j*D:(j+1)*D] = gx[b, cols[j]:cols[j]+D] + extra_grad[b] * fm_sum[b, :] (hybrid placement, requester side)."""
+    _rows2d(gx, "gx")
+    _chk(extra_grad, "extra_grad", torch.float32)
+    _chk(fm_sum, "fm_sum", torch.float32)
+    _chk(packed, "packed", torch.float32)
+    B, J = gx.shape[0], len(cols)
+    if packed.numel() < B * J * D:
+        raise ValueError("packed is too small")
+    arr = (C.c_int32 * J)(*[int(c) for c in cols])
+    with _timed("fm_pack_grads"):
+        _lib.check(_lib.lib().ctr_fm_pack_grads(gx.data_ptr(), gx.stride(0), _lib.ptr(extra_grad), _lib.ptr(fm_sum), B, D, arr, J,
+                                                packed.data_ptr(), _stream(gx)), "ctr_fm_pack_grads")
+
+
+@_guarded
 def rows_dense_apply(params: torch.Tensor, grads: torch.Tensor, state0: torch.Tensor | None, opt: _lib.Opt, clear: bool = True) -> None:
     """Dense sgd / adagrad update of a replicated table block from its (all-reduced) gradient buffer; zero gradients are
     skipped and, with ``clear``, the buffer is zero again afterwards."""

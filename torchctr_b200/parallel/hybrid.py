@@ -206,14 +206,19 @@ class HybridShardedTables(nn.Module):
         self._stride = (F * D + self._dense_width + 3) // 4 * 4
         self._grad_buf = PeerBuffer(B * self._stride * 4, dev)          # dL/dx of this rank's bags
         self._peer_grads = ops.ptr_array(tr.share(self._grad_buf))
-        self._peer_extra = self._peer_fm = None
+        self._peer_extra = None
         if self.fused_extra:
             self._extra_buf = PeerBuffer(B * 4, dev)                    # dL/d extra of this rank's bags
             self._peer_extra = ops.ptr_array(tr.share(self._extra_buf))
             self._gextra = self._extra_buf.tensor(torch.float32, (B,))
+        self._peer_pack = None
         if self.fm:
-            self._fm_buf = PeerBuffer(B * D * 4, dev)                   # sum over the fields of the pooled vectors
-            self._peer_fm = ops.ptr_array(tr.share(self._fm_buf))
+            self._fm_buf = PeerBuffer(B * D * 4, dev)                   # sum over the fields of the pooled vectors (local use)
+            if Fs:
+                # the sharded features' gradients with the "c * fm_sum" part of the FM gradient folded in, packed [B, Fs * D]: what
+                # the owners pull (one D-float piece per slot instead of the gradient slice plus the bag's fm_sum row)
+                self._pack_buf = PeerBuffer(B * Fs * D * 4, dev)
+                self._peer_pack = ops.ptr_array(tr.share(self._pack_buf))
         self._owner_ids = torch.zeros(B, 1, dtype=torch.int64, device=dev)   # never read: the owner pulls the peers' lists
         self._cap = (B, key)
 
@@ -266,7 +271,9 @@ class HybridShardedTables(nn.Module):
         return [ops.FeatureSpec(ids=ids_list[j], table=None, num_rows=self.num_rows[f], D=self.D, out_col=f * self.D,
                                 index_kind=self.index_kinds[f], hash_seed=self.hash_seeds[f]) for j, f in enumerate(self.sh)]
 
-    def _owner_specs(self, with_state):
+    def _owner_specs(self, with_state, packed: bool = False):
+        """This rank's rows of the sharded tables.  ``packed``: the gradients come from the peers' packed matrices
+        ([B, Fs * D], feature j at column j * D) instead of their full dL/dx matrices."""
         D = self.D
         shard = self.shards[0].data
         twin = self.shards[1].data.view(-1) if self.has_twins else None
@@ -277,7 +284,7 @@ class HybridShardedTables(nn.Module):
             _, n = owned_rows(self.num_rows[f], j, self.rank, self.world)
             n = max(n, 1)
             b = self.base[self.rank][j]
-            specs.append(ops.FeatureSpec(ids=self._owner_ids, table=shard[b:b + n], num_rows=n, D=D, out_col=f * D,
+            specs.append(ops.FeatureSpec(ids=self._owner_ids, table=shard[b:b + n], num_rows=n, D=D, out_col=j * D if packed else f * D,
                                          state0=None if s0 is None else s0[b:b + n],
                                          twin_table=None if twin is None or not with_state else twin[b:b + n],
                                          twin_state0=None if t0 is None else t0[b:b + n]))
@@ -390,6 +397,9 @@ class HybridShardedTables(nn.Module):
         nw = len(self.dims)
         fm_sum = self._fm_buf.tensor(torch.float32, (B, D)) if self.fm else None
         main = torch.cuda.current_stream(dev)
+        packed = self._peer_pack is not None
+        if packed:
+            ops.fm_pack_grads(gbuf, ge, fm_sum, [f * D for f in self.sh], D, self._pack_buf.tensor(torch.float32, (B, len(self.sh) * D)))
         if self.sh:
             self.transport.barrier()                       # every rank's gradients (and routing lists) are in place
         if self.rp:
@@ -411,9 +421,15 @@ class HybridShardedTables(nn.Module):
                     ops.rows_dense_apply(self.shards[nw + 1].data, self._rep_grad[R * D:R * D + R],
                                          None if st[nw + 1] is None else st[nw + 1], opt)
         if self.sh:
-            call = ops.make_group(self._owner_specs(True), self._cap[0], None, self._stride, extra=self._gextra if self.fused_extra else None)
-            ops.emb_bwd_apply_p2p(call, self._shard_s, self._plan_ws, opt, self._peer_grads,
-                                  peer_extra=self._peer_extra, peer_fm_sum=self._peer_fm)
+            if packed:
+                capB = self._cap[0]
+                call = ops.make_group(self._owner_specs(True, packed=True), capB, None, len(self.sh) * D, extra=self._gextra,
+                                      fm_sum=self._fm_buf.tensor(torch.float32, (capB, D)), fm=True)     # (fm_sum: a marker, not read)
+                ops.emb_bwd_apply_p2p(call, self._shard_s, self._plan_ws, opt, self._peer_pack, peer_extra=self._peer_extra)
+            else:
+                call = ops.make_group(self._owner_specs(True), self._cap[0], None, self._stride,
+                                      extra=self._gextra if self.fused_extra else None)
+                ops.emb_bwd_apply_p2p(call, self._shard_s, self._plan_ws, opt, self._peer_grads, peer_extra=self._peer_extra)
             if self.rp and side is not main:
                 main.wait_stream(side)
             self.transport.barrier()                       # closing: nobody overwrites what an owner still reads / reads rows too early
