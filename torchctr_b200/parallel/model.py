@@ -31,13 +31,13 @@ def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=
         from .peer import IpcTransport, PeerShardedTables
         if transport is None:
             transport = IpcTransport(pg, device)
-        if dedup is None:                     # the requester-side sort pays off once nearly all rows are remote: measured
-            dedup = transport.world > 4       # -10 % at 2 GPUs, +6 % at 8
         from .hybrid import HybridShardedTables, hybrid_eligible
         twins = full[1] if len(full) == 2 and all(t.embedding_dim == 1 for t in full[1]) else None
         can = len(full) <= 2 and (len(full) == 1 or twins is not None) and hybrid_eligible(full[0], twins)
-        if hybrid is None:
+        if hybrid is None:                    # (an explicit dedup=True asks for the fully sharded, de-duplicated exchange)
             hybrid = can and dedup is not True and (twins is not None or any(t.num_embeddings <= replicate_max_rows for t in full[0]))
+        if dedup is None:                     # fully sharded: the requester-side sort pays off once nearly all rows are remote:
+            dedup = transport.world > 4       # measured -10 % at 2 GPUs, +6 % at 8
         if hybrid and not can:
             raise NotImplementedError("hybrid placement needs single-id sum-pooled tables of one width (16 / 32 / 64)")
         if hybrid:
