@@ -478,10 +478,13 @@ def parallelism_note(model, world):
         return "single GPU"
     sh = getattr(model, "_sharded", None)
     if hasattr(sh, "rp"):
-        rows_rep = sum(sh.num_rows[f] for f in sh.rp)
-        return (f"hybrid placement over {world} GPUs: {len(sh.rp)} tables ({rows_rep} rows) replicated -- read locally, their summed row "
+        rows_rep = sum(sh.parts[p][2] for p in sh.rp)
+        heads = sum(1 for p in sh.rp if sh.parts[p][3] == "window")
+        return (f"hybrid placement over {world} GPUs: {len(sh.rp) - heads} small tables"
+                + (f" and the first {sh.parts[[p for p in sh.rp if sh.parts[p][3] == 'window'][0]][2]} (hot) rows of {heads} large tables" if heads else "")
+                + f" ({rows_rep} rows) replicated -- read locally, their summed row "
                 f"gradients all-reduced densely ({sh._rep_grad.numel() * 4 / 1e6:.1f} MB, one NCCL all-reduce that also carries the tower's "
-                f"gradients) and applied by every replica -- and {len(sh.sh)} tables row-sharded (owner = (row + table) mod P): rows read "
+                f"gradients) and applied by every replica -- and {len(sh.sh)} tables" + (" (their tails)" if heads else "") + " row-sharded (owner = (row + table) mod P): rows read "
                 "through NVLink peer mappings inside the lookup kernel, owners pull the (row, slot) lists and gradients inside the update "
                 "kernel (no all-to-all); batch data-parallel, tower replicated")
     return (f"tables row-sharded over {world} GPUs (owner = (row + table) mod P); rows read and gradients pulled through NVLink peer "
@@ -523,7 +526,8 @@ def run_ours(args):
         hybrid = {"auto": None, "on": True, "off": False}[args.hybrid]
         # cfg2 / cfg3: hybrid placement (tables <= --replicate-max-rows rows replicated, the rest row-sharded); cfg4 / cfg5: every
         # table row-sharded
-        model = shard_model(model, None, device=dev, dedup=dedup, init_seed=0, hybrid=hybrid, replicate_max_rows=args.replicate_max_rows)
+        model = shard_model(model, None, device=dev, dedup=dedup, init_seed=0, hybrid=hybrid, replicate_max_rows=args.replicate_max_rows,
+                            hot_rows=args.hot_rows)
     elif native:
         model.materialize_tables(dev, seed=0)
     model = model.to(dev).train()
@@ -818,6 +822,8 @@ def main():
     ap.add_argument("--hybrid", default="auto", choices=["auto", "on", "off"],
                     help="N > 1: replicate small tables, shard large ones (auto: when the model qualifies: cfg2, cfg3)")
     ap.add_argument("--replicate-max-rows", type=int, default=1 << 17, help="hybrid placement: tables up to this many rows are replicated")
+    ap.add_argument("--hot-rows", type=int, default=16384,
+                    help="hybrid placement: the first this-many rows of every large direct-id table are replicated too (0 = off)")
     ap.add_argument("--dedup", default="auto", choices=["auto", "on", "off"],
                     help="N > 1: fetch / send every distinct row once (auto: above 4 GPUs)")
     args = ap.parse_args()

@@ -54,6 +54,12 @@ extern "C" {
 #define CTR_INDEX_DIRECT 0 /* ids are table rows                                          */
 #define CTR_INDEX_HASH 1   /* row = murmur3_32(decimal(id), seed) % num_rows               */
 #define CTR_INDEX_REMAP 2  /* row = vocab[id], unknown -> 0 (OOV)                          */
+#define CTR_INDEX_WINDOW 3 /* row = id - first for ids in [first, first + num_rows), every other id is padding;
+                              `first` travels in hash_seed.  One table cut into a head [0, K) and a tail [K, V) that
+                              live in different places (hybrid placement: hot rows replicated, the rest row-sharded):
+                              the two parts are two features over the SAME ids and the same output columns -- in a
+                              single-id group exactly one of them writes the bag's slice (the head also writes the
+                              zeros of a negative id) */
 
 /* ctr_feature_t.pooling */
 #define CTR_POOL_SUM 0

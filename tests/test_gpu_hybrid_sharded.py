@@ -80,7 +80,7 @@ def _oracle_step(Vs, D, W, W1, acc, acc1, ids_all, gx_all, ge_all, dense, twins,
     return outs
 
 
-def _rank_main(rank, world, shared, prob, kind, twins, fm, errors, steps):
+def _rank_main(rank, world, shared, prob, kind, twins, fm, errors, steps, hot_rows=0):
     try:
         from torchctr_b200.nn.embedding import EmbeddingTable
         from torchctr_b200.parallel.hybrid import HybridShardedTables
@@ -92,8 +92,13 @@ def _rank_main(rank, world, shared, prob, kind, twins, fm, errors, steps):
         kw = [dict(index_kind="hash", hash_seed=7 + f) if hashed and f in (1, 5) else {} for f in range(len(Vs))]
         tabs = [EmbeddingTable(v, D, _weight=w.clone(), **k) for v, w, k in zip(Vs, full, kw)]
         tabs1 = [EmbeddingTable(v, 1, _weight=w.clone(), **k) for v, w, k in zip(Vs, full1, kw)] if twins else None
-        st = HybridShardedTables(names, tabs, tabs1, tr, dev, fm=fm, replicate_max_rows=200).train()
-        assert st.sh == [1, 3, 4] and st.rp == [0, 2, 5, 6]
+        st = HybridShardedTables(names, tabs, tabs1, tr, dev, fm=fm, replicate_max_rows=200, hot_rows=hot_rows).train()
+        assert sorted({st.parts[p][0] for p in st.sh}) == [1, 3, 4]
+        if hot_rows:      # large direct-id tables: a replicated head [0, hot_rows) + a sharded tail; hashed ones stay whole
+            split = [f for f in (1, 3, 4) if not (hashed and f == 1)]
+            assert sorted(st.parts[p][0] for p in st.rp if st.parts[p][3] == "window") == split
+        else:
+            assert sorted(st.parts[p][0] for p in st.rp) == [0, 2, 5, 6]
         lr = 0.5
         opt = torch.optim.SGD(list(st.shards), lr=lr) if kind == "sgd" else torch.optim.Adagrad(list(st.shards), lr=lr)
         st.bind_optimizer(opt, kind=kind)
@@ -104,7 +109,7 @@ def _rank_main(rank, world, shared, prob, kind, twins, fm, errors, steps):
         feats = {n: t for n, t in zip(names, raw_all[rank])}
         for step in range(steps):
             # (threads cannot meet at a barrier inside autograd's backward: drive the two halves of the Function directly)
-            ids_dev = [feats[names[f]].to(dev) for f in st.order]
+            ids_dev = st._ids_in_order(feats)
             x, extra = st._forward(ids_dev, dense.to(dev))
             outs = _oracle_step(Vs, D, W, W1, acc, acc1, ids_all, gx_all, ge_all, dense, twins, fm, kind, lr)
             ref_x, ref_e = outs[rank]
@@ -120,23 +125,20 @@ def _rank_main(rank, world, shared, prob, kind, twins, fm, errors, steps):
             st._backward(gx.to(dev), ge_all[rank].to(dev) if (twins or fm) else None)
             torch.cuda.synchronize()
             for w, ws in enumerate((W, W1) if twins else (W,)):
+                got = st.export_full_tables(w)               # collective: every table gathered back to [V, D]
                 for f in range(len(Vs)):
-                    fr, rows = st.local_rows_of(w, f)
-                    expect = ws[f][fr::world] if f in st.sh else ws[f]
+                    rows, expect = got[f], ws[f]
                     assert rows.shape == expect.shape, (rows.shape, expect.shape)
                     # element-wise Adagrad moves an element by lr g / sqrt(sum g^2): where an element's gradients all but
                     # cancel (g = gy + c (fm_sum - v) is a sum of O(10) terms) the step is ill-conditioned in g, so the bound
                     # is 1e-5 of the table's scale plus the step's sensitivity to an fp32 rounding error of the gradient
                     tol = torch.full_like(expect, RTOL * float(expect.abs().max()))
                     if kind == "adagrad":
-                        a = (acc, acc1)[w][f]
-                        a = a[fr::world] if f in st.sh else a
-                        tol = tol + lr * 2e-5 / (a.sqrt() + 1e-12)
-                    err = (rows.cpu() - expect).abs()
+                        tol = tol + lr * 2e-5 / ((acc, acc1)[w][f].sqrt() + 1e-12)
+                    err = (rows - expect).abs()
                     if bool((err > tol).any()):
                         bad = torch.nonzero((err > tol).any(1)).reshape(-1)[:8].tolist()
-                        raise AssertionError(f"update width {w} table {f} step {step}: max abs err {float(err.max()):.3e}, "
-                                             f"local rows {bad} (first global row {fr}, stride {world if f in st.sh else 1}), "
+                        raise AssertionError(f"update width {w} table {f} step {step}: max abs err {float(err.max()):.3e}, rows {bad}, "
                                              f"errs {[round(float(err[i].max()), 6) for i in bad]}")
             assert int(st.status.item()) == 0
         # checkpoints in the reference's unsharded format
@@ -149,8 +151,6 @@ def _rank_main(rank, world, shared, prob, kind, twins, fm, errors, steps):
             fullw = st.export_full_tables(w)
             for f in range(len(Vs)):
                 assert _close(fullw[f], ws[f], rtol=1e-3), f"export width {w} table {f}"      # (values were checked row by row above)
-                fr, rows = st.local_rows_of(w, f)
-                assert torch.equal(fullw[f][fr::world] if f in st.sh else fullw[f], rows.cpu()), f"export width {w} table {f}: not this rank's rows"
             st.load_full_tables([t * 0.5 for t in fullw], w)
             again = st.export_full_tables(w)
             for f in range(len(Vs)):
@@ -164,10 +164,11 @@ def _rank_main(rank, world, shared, prob, kind, twins, fm, errors, steps):
             pass
 
 
-@pytest.mark.parametrize("world,kind,D,twins,fm,hashed", [
-    (2, "sgd", 16, True, True, False), (3, "sgd", 16, True, True, False), (3, "adagrad", 16, True, True, False), (4, "adagrad", 16, True, True, True),
-    (2, "adagrad", 32, False, False, False), (3, "sgd", 64, False, False, True), (2, "adagrad", 16, True, False, False)])
-def test_hybrid_sharded_threads(world, kind, D, twins, fm, hashed):
+@pytest.mark.parametrize("world,kind,D,twins,fm,hashed,hot_rows", [
+    (2, "sgd", 16, True, True, False, 0), (3, "sgd", 16, True, True, False, 100), (3, "adagrad", 16, True, True, False, 0),
+    (4, "adagrad", 16, True, True, True, 100), (2, "adagrad", 32, False, False, False, 100), (3, "sgd", 64, False, False, True, 0),
+    (2, "adagrad", 16, True, False, False, 0), (2, "sgd", 16, True, True, False, 100)])
+def test_hybrid_sharded_threads(world, kind, D, twins, fm, hashed, hot_rows):
     import faulthandler
     import sys
     from torchctr_b200.parallel.peer import ThreadTransport
@@ -175,7 +176,7 @@ def test_hybrid_sharded_threads(world, kind, D, twins, fm, hashed):
     shared = ThreadTransport.Shared(world)
     prob = _problem(world, D, hashed=hashed)
     errors = []
-    threads = [threading.Thread(target=_rank_main, args=(r, world, shared, prob, kind, twins, fm, errors, 2)) for r in range(world)]
+    threads = [threading.Thread(target=_rank_main, args=(r, world, shared, prob, kind, twins, fm, errors, 2, hot_rows)) for r in range(world)]
     for t in threads:
         t.start()
     for t in threads:
@@ -195,8 +196,9 @@ def _model_rank(rank, world, shared, fc, state, batches, out, errors):
         tr = ThreadTransport(shared, rank, dev)
         model = DeepFM(fc, [32, 16])
         model.load_state_dict(state)
-        model = shard_model(model, transport=tr, device=dev, replicate_max_rows=100).to(dev).eval()
+        model = shard_model(model, transport=tr, device=dev, replicate_max_rows=100, hot_rows=32).to(dev).eval()
         assert isinstance(model._sharded, HybridShardedTables) and model._sharded.sh and model._sharded.rp
+        assert any(part[3] == "window" for part in model._sharded.parts)          # hot rows of the large tables replicated
         with torch.no_grad():
             out[rank] = model(batches[rank]).cpu()
         sd = model.full_state_dict()

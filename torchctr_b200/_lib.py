@@ -21,7 +21,7 @@ STATUS_MAP_FULL = 2
 STATUS_NO_RUNS = 4
 PLAN_NO_RUNS = 1
 
-INDEX_DIRECT, INDEX_HASH, INDEX_REMAP = 0, 1, 2
+INDEX_DIRECT, INDEX_HASH, INDEX_REMAP, INDEX_WINDOW = 0, 1, 2, 3
 POOL_SUM, POOL_MEAN = 0, 1
 OPT_NONE, OPT_SGD, OPT_ADAGRAD, OPT_ROWWISE_ADAGRAD, OPT_ADAM, OPT_GRAD_OUT = 0, 1, 2, 3, 4, 5
 VOCAB_EMPTY = -(2 ** 63)

@@ -176,6 +176,9 @@ __device__ __forceinline__ int32_t map_index(const DevFeature &f, int64_t id) {
         return id < (int64_t)f.num_rows ? (int32_t)id : -2;
     } else if (f.index_kind == CTR_INDEX_HASH) {
         return (int32_t)(murmur3_decimal(id, f.hash_seed) % f.num_rows);
+    } else if (f.index_kind == CTR_INDEX_WINDOW) {      // a part [first, first + num_rows) of a table; ids outside are not ours
+        const int64_t r = id - (int64_t)f.hash_seed;
+        return (r >= 0 && r < (int64_t)f.num_rows) ? (int32_t)r : -1;
     } else {
         const int32_t r = map_find(f.map_keys, f.map_rows, f.map_mask, id, 0);
         return (uint32_t)r < f.num_rows ? r : -2;

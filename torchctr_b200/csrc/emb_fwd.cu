@@ -200,13 +200,17 @@ __global__ void __launch_bounds__(kFwdThreads) emb_pool_fwd_l1_kernel(const __gr
         float twin_sum = 0.f;
         for (int f0 = 0; f0 < F; f0 += 4) {
             int32_t row[4];
+            bool writes[4];          // false: a WINDOW part whose id belongs to the table's other part (which writes the slice)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 row[j] = -1;
+                writes[j] = f0 + j < F;
                 if (f0 + j < F) {
                     const DevFeature &f = g.f[f0 + j];
-                    row[j] = map_index(f, __ldg(f.ids + bag));
+                    const int64_t id = __ldg(f.ids + bag);
+                    row[j] = map_index(f, id);
                     if (row[j] == -2) flag_status(g.status, CTR_STATUS_INDEX_OOB);
+                    if (f.index_kind == CTR_INDEX_WINDOW && row[j] < 0) writes[j] = id < 0 && f.hash_seed == 0u;
                 }
             }
             float4 v[4];
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(kFwdThreads) emb_pool_fwd_l1_kernel(const __gr
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (f0 + j < F) {
+                if (writes[j]) {
                     float *dst = out_row + g.f[f0 + j].out_col + t * VEC;
                     if (VEC == 4) *reinterpret_cast<float4 *>(dst) = v[j];
                     else *dst = v[j].x;

@@ -92,7 +92,7 @@ int lower_group(const ctr_group_t *g, DevGroup *out, bool need_tables, bool need
             d.map_rows = s.map->rows;
             d.map_mask = s.map->capacity - 1;
         } else {
-            CTR_REQUIRE(s.index_kind == CTR_INDEX_DIRECT || s.index_kind == CTR_INDEX_HASH,
+            CTR_REQUIRE(s.index_kind == CTR_INDEX_DIRECT || s.index_kind == CTR_INDEX_HASH || s.index_kind == CTR_INDEX_WINDOW,
                         "feature %d: bad index_kind %d", i, s.index_kind);
         }
         CTR_REQUIRE(s.pooling != CTR_POOL_MEAN || s.bag_scale != nullptr || g->B == 0,

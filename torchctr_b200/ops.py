@@ -11,10 +11,11 @@ from dataclasses import dataclass, field
 import torch
 
 from . import _lib
-from ._lib import (INDEX_DIRECT, INDEX_HASH, INDEX_REMAP, OPT_ADAGRAD, OPT_ADAM, OPT_GRAD_OUT, OPT_NONE,  # noqa: F401
+from ._lib import (INDEX_DIRECT, INDEX_HASH, INDEX_REMAP, INDEX_WINDOW, OPT_ADAGRAD, OPT_ADAM, OPT_GRAD_OUT, OPT_NONE,  # noqa: F401
                    OPT_ROWWISE_ADAGRAD, OPT_SGD, POOL_MEAN, POOL_SUM)
 
-_INDEX_KINDS = {"direct": INDEX_DIRECT, "hash": INDEX_HASH, "vocab": INDEX_REMAP, "remap": INDEX_REMAP}
+_INDEX_KINDS = {"direct": INDEX_DIRECT, "hash": INDEX_HASH, "vocab": INDEX_REMAP, "remap": INDEX_REMAP,
+                "window": INDEX_WINDOW}      # window: rows [hash_seed, hash_seed + num_rows) of a table, other ids are padding
 _POOLINGS = {"sum": POOL_SUM, "mean": POOL_MEAN}
 _OPT_KINDS = {"none": OPT_NONE, "sgd": OPT_SGD, "adagrad": OPT_ADAGRAD, "rowwise_adagrad": OPT_ROWWISE_ADAGRAD,
               "adam": OPT_ADAM, "grad_out": OPT_GRAD_OUT}

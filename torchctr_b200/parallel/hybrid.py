@@ -15,6 +15,11 @@ than to route -- while the large tables' gradients are far too sparse for that. 
               owners pull the (row, slot) lists, sort them on a side stream during the tower and run the fused sweep reading
               every slot's gradient (and, for DeepFM, its dL/d extra and FM sum) from the rank that produced it.
 
+  hot rows    a large table with direct ids is cut in two: its first ``hot_rows`` rows (the hot ones of a frequency-ordered
+              vocabulary: 16 K rows of a 1e7-row Zipf(1.05) table take 69 % of its slots) are replicated like a small table, only
+              the tail is sharded.  Both parts are features over the same ids and the same output columns
+              (``CTR_INDEX_WINDOW``); a slot belongs to exactly one of them.
+
 One lookup launch and, per rank, two sweeps per step -- DeepFM's first-order tables and FM term ride inside them exactly as
 on one GPU (``ctr_group_t.extra``).  The all-reduce doubles as the closing barrier of the owner-side update.
 Single-id features of one width (D = 16, 32 or 64), direct or hashed ids, sum pooling, sgd / adagrad.
@@ -75,7 +80,7 @@ class HybridShardedTables(nn.Module):
     ``forward`` / ``backward`` the same number of times."""
 
     def __init__(self, names, tables, twins, transport, device=None, fm: bool = False, replicate_max_rows: int = 1 << 17,
-                 init_seed: int | None = None, init_std: float = 1.0):
+                 init_seed: int | None = None, init_std: float = 1.0, hot_rows: int = 0):
         super().__init__()
         if not hybrid_eligible(tables, twins):
             raise NotImplementedError("hybrid placement: single-id sum-pooled tables of one width (16, 32 or 64), direct / hashed ids")
@@ -94,23 +99,36 @@ class HybridShardedTables(nn.Module):
         self.fused_extra = self.has_twins or self.fm
         self.dims = [D, 1] if self.has_twins else [D]
         self.num_rows = [int(t.num_embeddings) for t in tables]
-        self.index_kinds = [t.index_kind for t in tables]
-        self.hash_seeds = [t.hash_seed for t in tables]
         self.vocabs = [None] * F
-        self.sh = [f for f in range(F) if self.num_rows[f] > replicate_max_rows]       # sharded features (original indices)
-        self.rp = [f for f in range(F) if self.num_rows[f] <= replicate_max_rows]      # replicated features
-        self.order = self.sh + self.rp                                                  # feature order of the lookup group
-        Fs = len(self.sh)
+        # parts: (feature, first row, rows, index kind, hash seed | window start).  A table is one part, or -- a large table
+        # with direct ids and hot_rows > 0 -- a replicated head [0, hot_rows) and a sharded tail [hot_rows, V)
+        self.parts, self.sh, self.rp = [], [], []
+        for f, t in enumerate(tables):
+            V, kind = self.num_rows[f], t.index_kind
+            if V <= replicate_max_rows:
+                self.rp.append(len(self.parts)); self.parts.append((f, 0, V, kind, t.hash_seed))
+            elif kind == "direct" and 0 < hot_rows < V:
+                self.rp.append(len(self.parts)); self.parts.append((f, 0, hot_rows, "window", 0))
+                self.sh.append(len(self.parts)); self.parts.append((f, hot_rows, V - hot_rows, "window", hot_rows))
+            else:
+                self.sh.append(len(self.parts)); self.parts.append((f, 0, V, kind, t.hash_seed))
+        if len(self.parts) > _lib.MAX_FEATURES:
+            raise ValueError(f"{len(self.parts)} table parts exceed the {_lib.MAX_FEATURES} features of a launch group; use hot_rows=0")
+        self.order = self.sh + self.rp            # part order of the lookup group: sharded parts first (= the shard geometry's index)
+        P, Fs = len(self.parts), len(self.sh)
         seed0 = torch.initial_seed() if init_seed is None else init_seed
         widths = [tables] + ([twins] if self.has_twins else [])
 
-        # ---- sharded part: this rank's rows of the large tables, in peer-visible memory ----
-        self.base, self.total, adj_s = shard_geometry([self.num_rows[f] for f in self.sh], self.world) if Fs else ([], [1] * self.world, torch.zeros(0, dtype=torch.int64))
-        adj_l = torch.zeros(self.world * F, dtype=torch.int64)
+        # ---- sharded parts: this rank's rows (row r of the j-th sharded part on rank (r + j) mod P), in peer-visible memory ----
+        if Fs:
+            self.base, self.total, adj_s = shard_geometry([self.parts[p][2] for p in self.sh], self.world)
+        else:
+            self.base, self.total, adj_s = [], [1] * self.world, torch.zeros(1, dtype=torch.int64)
+        adj_l = torch.zeros(self.world * P, dtype=torch.int64)           # the same for the lookup group (P features)
         for o in range(self.world):
             for j in range(Fs):
-                adj_l[o * F + j] = adj_s[o * Fs + j]
-        self.register_buffer("adj_s", adj_s.to(dev) if Fs else torch.zeros(1, dtype=torch.int64, device=dev), persistent=False)
+                adj_l[o * P + j] = adj_s[o * Fs + j]
+        self.register_buffer("adj_s", adj_s.to(dev), persistent=False)
         self.register_buffer("adj_l", adj_l.to(dev), persistent=False)
         self._shard_s = ops.make_shard(self.world, self.rank, self.adj_s)
         self._shard_l = ops.make_shard(self.world, self.rank, self.adj_l)
@@ -120,42 +138,43 @@ class HybridShardedTables(nn.Module):
         for wi, (tabs, Dw) in enumerate(zip(widths, self.dims)):
             buf = PeerBuffer(rows * Dw * 4, dev)
             w = buf.tensor(torch.float32, (rows, Dw))
-            for j, f in enumerate(self.sh):
+            for j, p in enumerate(self.sh):
+                f, first, cnt = self.parts[p][:3]
                 t = tabs[f]
-                fr, n = owned_rows(self.num_rows[f], j, self.rank, self.world)
+                fr, n = owned_rows(cnt, j, self.rank, self.world)
                 if not n:
                     continue
                 b = self.base[self.rank][j]
                 if t.weight.is_meta:       # shard-native: this rank draws ITS rows; no rank ever holds the full table
-                    ops.normal_fill_rows_strided(w, b, n, 0.0, init_std, EmbeddingTable.counter_seed(seed0, f, wi), fr, self.world)
+                    ops.normal_fill_rows_strided(w, b, n, 0.0, init_std, EmbeddingTable.counter_seed(seed0, f, wi), first + fr, self.world)
                 else:
-                    w[b:b + n] = t.weight.detach()[fr::self.world].to(dev)
+                    w[b:b + n] = t.weight.detach()[first + fr:first + cnt:self.world].to(dev)
             self._shard_bufs.append(buf)
             params.append(nn.Parameter(w, requires_grad=True))
             self._table_ptrs.append(ops.ptr_array(transport.share(buf)))
 
-        # ---- replicated part: the small tables, whole, in one block per width ----
+        # ---- replicated parts: whole, in one block per width ----
         self.rep_off, acc = {}, 0
-        for f in self.rp:
-            self.rep_off[f] = acc
-            acc += self.num_rows[f]
+        for p in self.rp:
+            self.rep_off[p] = acc
+            acc += self.parts[p][2]
         self.R = R = (acc + 3) // 4 * 4 if acc else 0
         for wi, (tabs, Dw) in enumerate(zip(widths, self.dims)):
             blk = torch.zeros(max(R, 4), Dw, dtype=torch.float32, device=dev)
-            for f in self.rp:
-                t, o, v = tabs[f], self.rep_off[f], self.num_rows[f]
+            for p in self.rp:
+                f, first, cnt = self.parts[p][:3]
+                t, o = tabs[f], self.rep_off[p]
                 if t.weight.is_meta:
-                    ops.normal_fill_rows_strided(blk, o, v, 0.0, init_std, EmbeddingTable.counter_seed(seed0, f, wi), 0, 1)
+                    ops.normal_fill_rows_strided(blk, o, cnt, 0.0, init_std, EmbeddingTable.counter_seed(seed0, f, wi), first, 1)
                 else:
-                    blk[o:o + v] = t.weight.detach().to(dev)
+                    blk[o:o + cnt] = t.weight.detach()[first:first + cnt].to(dev)
             params.append(nn.Parameter(blk, requires_grad=True))
-        nw = len(self.dims)
         # shards[0 .. nw): this rank's shard of every width; shards[nw .. 2 nw): the replicated block of every width
         self.shards = nn.ParameterList(params)
         # gradient buffer of the replicated block: [R, D] then [R] (twins), ONE flat tensor = one all-reduce
         self._rep_elems = max(R, 4) * (D + (1 if self.has_twins else 0))
         self._rep_grad = torch.zeros(self._rep_elems, dtype=torch.float32, device=dev)
-        self.opt_state = [None] * (2 * nw)      # adagrad sums, same shapes as self.shards
+        self.opt_state = [None] * (2 * len(self.dims))      # adagrad sums, same shapes as self.shards
         self.bindings = [None]
         self.binding = None
         self._side = None
@@ -213,9 +232,9 @@ class HybridShardedTables(nn.Module):
             self._gextra = self._extra_buf.tensor(torch.float32, (B,))
         self._peer_pack = None
         if self.fm:
-            self._fm_buf = PeerBuffer(B * D * 4, dev)                   # sum over the fields of the pooled vectors (local use)
+            self._fm_sum = torch.empty(B, D, dtype=torch.float32, device=dev)   # sum over the fields of the pooled vectors
             if Fs:
-                # the sharded features' gradients with the "c * fm_sum" part of the FM gradient folded in, packed [B, Fs * D]: what
+                # the sharded parts' gradients with the "c * fm_sum" part of the FM gradient folded in, packed [B, Fs * D]: what
                 # the owners pull (one D-float piece per slot instead of the gradient slice plus the bag's fm_sum row)
                 self._pack_buf = PeerBuffer(B * Fs * D * 4, dev)
                 self._peer_pack = ops.ptr_array(tr.share(self._pack_buf))
@@ -223,65 +242,66 @@ class HybridShardedTables(nn.Module):
         self._cap = (B, key)
 
     # ---- feature specs ---------------------------------------------------------------------------------------------
-    def _rep_views(self, f, wi, src):
-        o, v = self.rep_off[f], self.num_rows[f]
-        return src[o:o + v]
+    def _part_kw(self, p, ids_list_pos, ids_list):
+        f, first, cnt, kind, seed = self.parts[p]
+        return dict(ids=ids_list[ids_list_pos], num_rows=cnt, D=self.D, out_col=f * self.D, index_kind=kind, hash_seed=seed)
 
-    def _lookup_specs(self, ids_list):
-        """Sharded features first (their position is the index the shard geometry uses), then the replicated ones."""
-        D, nw = self.D, len(self.dims)
+    def _rep_slices(self, p):
+        """(table rows, twin rows | None) of replicated part ``p`` inside the replicated blocks."""
+        nw = len(self.dims)
+        o, cnt = self.rep_off[p], self.parts[p][2]
         rep_w = self.shards[nw].data
         rep_t = self.shards[nw + 1].data if self.has_twins else None
+        return rep_w[o:o + cnt], (None if rep_t is None else rep_t[o:o + cnt])
+
+    def _lookup_specs(self, ids_list):
+        """Sharded parts first (their position is the index the shard geometry uses), then the replicated ones."""
         specs = []
-        for j, f in enumerate(self.order):
-            kw = dict(ids=ids_list[j], num_rows=self.num_rows[f], D=D, out_col=f * D, index_kind=self.index_kinds[f],
-                      hash_seed=self.hash_seeds[f])
+        for j, p in enumerate(self.order):
+            kw = self._part_kw(p, j, ids_list)
             if j < len(self.sh):
                 specs.append(ops.FeatureSpec(table=None, **kw))
             else:
-                o, v = self.rep_off[f], self.num_rows[f]
-                specs.append(ops.FeatureSpec(table=rep_w[o:o + v], twin_table=None if rep_t is None else rep_t[o:o + v], **kw))
+                w, tw = self._rep_slices(p)
+                specs.append(ops.FeatureSpec(table=w, twin_table=tw, **kw))
         return specs
 
     def _rep_bwd_specs(self, ids_list, plan: bool = False):
-        """The replicated features for the GRAD_OUT sweep: state0 / twin_state0 are the dense gradient buffers
+        """The replicated parts for the GRAD_OUT sweep: state0 / twin_state0 are the dense gradient buffers
         (``plan``: ids and row counts only, for the sort)."""
-        D, nw = self.D, len(self.dims)
+        D = self.D
         R = max(self.R, 4)
-        rep_w = self.shards[nw].data
-        rep_t = self.shards[nw + 1].data if self.has_twins else None
         g_main = self._rep_grad[:R * D].view(R, D)
         g_twin = self._rep_grad[R * D:R * D + R] if self.has_twins else None
         specs = []
-        for j, f in enumerate(self.order):
+        for j, p in enumerate(self.order):
             if j < len(self.sh):
                 continue
-            o, v = self.rep_off[f], self.num_rows[f]
+            kw = self._part_kw(p, j, ids_list)
             if plan:
-                specs.append(ops.FeatureSpec(ids=ids_list[j], table=None, num_rows=v, D=D, out_col=f * D,
-                                             index_kind=self.index_kinds[f], hash_seed=self.hash_seeds[f]))
+                specs.append(ops.FeatureSpec(table=None, **kw))
                 continue
-            specs.append(ops.FeatureSpec(ids=ids_list[j], table=rep_w[o:o + v], num_rows=v, D=D, out_col=f * D,
-                                         index_kind=self.index_kinds[f], hash_seed=self.hash_seeds[f], state0=g_main[o:o + v],
-                                         twin_table=None if rep_t is None else rep_t[o:o + v],
-                                         twin_state0=None if g_twin is None else g_twin[o:o + v]))
+            o, cnt = self.rep_off[p], self.parts[p][2]
+            w, tw = self._rep_slices(p)
+            specs.append(ops.FeatureSpec(table=w, state0=g_main[o:o + cnt], twin_table=tw,
+                                         twin_state0=None if g_twin is None else g_twin[o:o + cnt], **kw))
         return specs
 
     def _route_specs(self, ids_list):
-        return [ops.FeatureSpec(ids=ids_list[j], table=None, num_rows=self.num_rows[f], D=self.D, out_col=f * self.D,
-                                index_kind=self.index_kinds[f], hash_seed=self.hash_seeds[f]) for j, f in enumerate(self.sh)]
+        return [ops.FeatureSpec(table=None, **self._part_kw(p, j, ids_list)) for j, p in enumerate(self.sh)]
 
     def _owner_specs(self, with_state, packed: bool = False):
-        """This rank's rows of the sharded tables.  ``packed``: the gradients come from the peers' packed matrices
-        ([B, Fs * D], feature j at column j * D) instead of their full dL/dx matrices."""
+        """This rank's rows of the sharded parts.  ``packed``: the gradients come from the peers' packed matrices
+        ([B, Fs * D], part j at column j * D) instead of their full dL/dx matrices."""
         D = self.D
         shard = self.shards[0].data
         twin = self.shards[1].data.view(-1) if self.has_twins else None
         s0 = self.opt_state[0] if with_state else None
         t0 = self.opt_state[1].view(-1) if (with_state and self.has_twins and self.opt_state[1] is not None) else None
         specs = []
-        for j, f in enumerate(self.sh):
-            _, n = owned_rows(self.num_rows[f], j, self.rank, self.world)
+        for j, p in enumerate(self.sh):
+            f, first, cnt = self.parts[p][:3]
+            _, n = owned_rows(cnt, j, self.rank, self.world)
             n = max(n, 1)
             b = self.base[self.rank][j]
             specs.append(ops.FeatureSpec(ids=self._owner_ids, table=shard[b:b + n], num_rows=n, D=D, out_col=j * D if packed else f * D,
@@ -291,18 +311,25 @@ class HybridShardedTables(nn.Module):
         return specs
 
     # ---- forward / backward ----------------------------------------------------------------------------------------
-    def forward(self, feats, dense=None):
+    def _ids_in_order(self, feats):
         dev = self.device
-        ids = []
-        for f in self.order:
-            t = feats[self.names[f]]
-            if t.dim() == 1:
-                t = t.unsqueeze(1)
-            if t.shape[1] != 1:
-                raise ValueError(f"hybrid placement holds single-id features; {self.names[f]!r} has {t.shape[1]} ids per row")
-            ids.append(t.to(dev, dtype=torch.int64, non_blocking=True).contiguous())
+        cache, ids = {}, []
+        for p in self.order:
+            f = self.parts[p][0]
+            if f not in cache:
+                t = feats[self.names[f]]
+                if t.dim() == 1:
+                    t = t.unsqueeze(1)
+                if t.shape[1] != 1:
+                    raise ValueError(f"hybrid placement holds single-id features; {self.names[f]!r} has {t.shape[1]} ids per row")
+                cache[f] = t.to(dev, dtype=torch.int64, non_blocking=True).contiguous()
+            ids.append(cache[f])
+        return ids
+
+    def forward(self, feats, dense=None):
+        ids = self._ids_in_order(feats)
         if dense is not None:
-            dense = dense.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+            dense = dense.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
         self._want_backward = self.training and torch.is_grad_enabled()      # (grad mode is off inside Function.forward)
         return _HybridLookupFn.apply(self, ids, dense, *list(self.shards))
 
@@ -324,21 +351,21 @@ class HybridShardedTables(nn.Module):
         extra = torch.empty(B, dtype=torch.float32, device=dev) if self.fused_extra else None
         fm_sum = None
         if self.fm:
-            fm_sum = self._fm_buf.tensor(torch.float32, (B, D)) if train else torch.empty(B, D, dtype=torch.float32, device=dev)
+            fm_sum = self._fm_sum[:B] if train else torch.empty(B, D, dtype=torch.float32, device=dev)
         call = ops.make_group(self._lookup_specs(ids_list), B, x, stride, dense=dense, dense_col=F * D,
                               zero_from=width if stride > width else -1, status=status, extra=extra, fm_sum=fm_sum, fm=self.fm)
         ops.emb_pool_fwd_sharded(call, self._shard_l, self._table_ptrs[0], self._table_ptrs[1] if self.has_twins else None)
         if train:
             # everything the backward needs that depends on the ids only runs on a side stream next to the tower: the sort of
-            # the replicated features' slots, the bucketing of the sharded features' slots by owner, the meeting with the other
+            # the replicated parts' slots, the bucketing of the sharded parts' slots by owner, the meeting with the other
             # ranks and the owner-side gather + sort
             if self._side is None:
                 self._side = torch.cuda.Stream(device=dev)
-            if not torch.cuda.is_current_stream_capturing():
+            capturing = torch.cuda.is_current_stream_capturing()
+            if not capturing:
                 for t in ids_list:
                     t.record_stream(self._side)
             main = torch.cuda.current_stream(dev)
-            capturing = torch.cuda.is_current_stream_capturing()
             route_call = plan_call = rep_call = None
             if self.sh:
                 route_call = ops.make_group(self._route_specs(ids_list), B, None, stride, status=status)
@@ -395,20 +422,22 @@ class HybridShardedTables(nn.Module):
         self._ensure_state()
         opt = self.binding.next_opt()
         nw = len(self.dims)
-        fm_sum = self._fm_buf.tensor(torch.float32, (B, D)) if self.fm else None
+        fm_sum = self._fm_sum[:B] if self.fm else None
         main = torch.cuda.current_stream(dev)
         packed = self._peer_pack is not None
         if packed:
-            ops.fm_pack_grads(gbuf, ge, fm_sum, [f * D for f in self.sh], D, self._pack_buf.tensor(torch.float32, (B, len(self.sh) * D)))
+            ops.fm_pack_grads(gbuf, ge, fm_sum, [self.parts[p][0] * D for p in self.sh], D,
+                              self._pack_buf.tensor(torch.float32, (B, len(self.sh) * D)))
         if self.sh:
             self.transport.barrier()                       # every rank's gradients (and routing lists) are in place
+        side = main
         if self.rp:
-            # replicated tables, on a second stream NEXT TO the owner-side update of the sharded tables: this rank's summed row
+            # replicated parts, on a second stream NEXT TO the owner-side update of the sharded parts: this rank's summed row
             # gradients -> dense buffer, all-reduce (the tower's flat gradient buffer rides along), dense update of every replica
-            side = self._side2 if self.sh else main
-            if self.sh and side is None:
-                side = self._side2 = torch.cuda.Stream(device=dev)
-            if side is not main:
+            if self.sh:
+                if self._side2 is None:
+                    self._side2 = torch.cuda.Stream(device=dev)
+                side = self._side2
                 side.wait_stream(main)
             with torch.cuda.stream(side):
                 call = ops.make_group(self._rep_bwd_specs(ids_list), B, gbuf, self._stride, extra=ge, fm_sum=fm_sum, fm=self.fm)
@@ -421,19 +450,18 @@ class HybridShardedTables(nn.Module):
                     ops.rows_dense_apply(self.shards[nw + 1].data, self._rep_grad[R * D:R * D + R],
                                          None if st[nw + 1] is None else st[nw + 1], opt)
         if self.sh:
+            capB = self._cap[0]
             if packed:
-                capB = self._cap[0]
                 call = ops.make_group(self._owner_specs(True, packed=True), capB, None, len(self.sh) * D, extra=self._gextra,
-                                      fm_sum=self._fm_buf.tensor(torch.float32, (capB, D)), fm=True)     # (fm_sum: a marker, not read)
+                                      fm_sum=self._fm_sum, fm=True)           # (fm_sum: a marker here, the owner does not read it)
                 ops.emb_bwd_apply_p2p(call, self._shard_s, self._plan_ws, opt, self._peer_pack, peer_extra=self._peer_extra)
             else:
-                call = ops.make_group(self._owner_specs(True), self._cap[0], None, self._stride,
-                                      extra=self._gextra if self.fused_extra else None)
+                call = ops.make_group(self._owner_specs(True), capB, None, self._stride, extra=self._gextra if self.fused_extra else None)
                 ops.emb_bwd_apply_p2p(call, self._shard_s, self._plan_ws, opt, self._peer_grads, peer_extra=self._peer_extra)
-            if self.rp and side is not main:
+            if side is not main:
                 main.wait_stream(side)
             self.transport.barrier()                       # closing: nobody overwrites what an owner still reads / reads rows too early
-        # (no sharded table: the all-reduce above is the only collective, and it is on this stream)
+        # (no sharded part: the all-reduce above is the only collective, and it is on this stream)
 
     _side2 = None
 
@@ -459,60 +487,57 @@ class HybridShardedTables(nn.Module):
         return provider
 
     # ---- checkpoints in the reference's (unsharded) format ------------------------------------------------------------
-    def _gather_width(self, sources, wi):
-        """Full per-feature tensors (CPU) of width ``wi`` from (shard-shaped tensor, replicated-block tensor)."""
+    def _gather_width(self, shard_t, rep_t, wi):
+        """Full per-feature tensors (CPU) of width ``wi`` from a shard-shaped and a replicated-block-shaped tensor."""
         torch.cuda.synchronize(self.device)
-        shard_t, rep_t = sources
+        Dw = self.dims[wi]
         mine = []
-        for j, f in enumerate(self.sh):
-            _, n = owned_rows(self.num_rows[f], j, self.rank, self.world)
+        for j, p in enumerate(self.sh):
+            _, n = owned_rows(self.parts[p][2], j, self.rank, self.world)
             b = self.base[self.rank][j]
             mine.append(shard_t[b:b + n].detach().cpu())
-        parts = self.transport.all_gather_object(mine)
-        Dw = self.dims[wi]
-        full = [None] * self.num_features
-        for j, f in enumerate(self.sh):
-            v = self.num_rows[f]
-            t = torch.empty(v, Dw, dtype=torch.float32)
+        gathered = self.transport.all_gather_object(mine)
+        full = [torch.empty(v, Dw, dtype=torch.float32) for v in self.num_rows]
+        for j, p in enumerate(self.sh):
+            f, first, cnt = self.parts[p][:3]
             for r in range(self.world):
-                fr, n = owned_rows(v, j, r, self.world)
+                fr, n = owned_rows(cnt, j, r, self.world)
                 if n:
-                    t[fr::self.world] = parts[r][j].view(-1, Dw)
-            full[f] = t
-        for f in self.rp:
-            o, v = self.rep_off[f], self.num_rows[f]
-            full[f] = rep_t[o:o + v].detach().cpu().view(v, Dw).clone()
+                    full[f][first + fr:first + cnt:self.world] = gathered[r][j].view(-1, Dw)
+        for p in self.rp:
+            f, first, cnt = self.parts[p][:3]
+            o = self.rep_off[p]
+            full[f][first:first + cnt] = rep_t[o:o + cnt].detach().cpu().view(cnt, Dw)
         return full
 
     def export_full_tables(self, w: int = 0):
         """Collective.  Every rank gets the full ``[V_f, dims[w]]`` table of every feature (CPU tensors, feature order), i.e.
         what ``model.embeddings[name].weight`` holds in the reference (``torchctr/trainer.py:353-496``)."""
         nw = len(self.dims)
-        return self._gather_width((self.shards[w].data, self.shards[nw + w].data), w)
+        return self._gather_width(self.shards[w].data, self.shards[nw + w].data, w)
 
     def export_full_optimizer_state(self, w: int = 0):
         nw = len(self.dims)
         if self.opt_state[w] is None:
             self.transport.all_gather_object(None)
             return None, None
-        return self._gather_width((self.opt_state[w], self.opt_state[nw + w]), w), None
+        return self._gather_width(self.opt_state[w], self.opt_state[nw + w], w), None
 
     def _scatter_width(self, full, shard_t, rep_t, wi):
         Dw = self.dims[wi]
-        for j, f in enumerate(self.sh):
-            t = full[f]
+        for f, t in enumerate(full):
             if tuple(t.shape) != (self.num_rows[f], Dw):
                 raise ValueError(f"table {f}: expected {(self.num_rows[f], Dw)}, got {tuple(t.shape)}")
-            fr, n = owned_rows(self.num_rows[f], j, self.rank, self.world)
+        for j, p in enumerate(self.sh):
+            f, first, cnt = self.parts[p][:3]
+            fr, n = owned_rows(cnt, j, self.rank, self.world)
             if n:
                 b = self.base[self.rank][j]
-                shard_t[b:b + n].copy_(t[fr::self.world].to(self.device).view(n, -1))
-        for f in self.rp:
-            t = full[f]
-            if tuple(t.shape) != (self.num_rows[f], Dw):
-                raise ValueError(f"table {f}: expected {(self.num_rows[f], Dw)}, got {tuple(t.shape)}")
-            o, v = self.rep_off[f], self.num_rows[f]
-            rep_t[o:o + v].copy_(t.to(self.device).view(v, -1))
+                shard_t[b:b + n].copy_(full[f][first + fr:first + cnt:self.world].to(self.device).view(n, -1))
+        for p in self.rp:
+            f, first, cnt = self.parts[p][:3]
+            o = self.rep_off[p]
+            rep_t[o:o + cnt].copy_(full[f][first:first + cnt].to(self.device).view(cnt, -1))
 
     def load_full_tables(self, full, w: int = 0) -> None:
         """Scatter full tables (one ``[V_f, dims[w]]`` tensor per feature, e.g. from a reference checkpoint) into this rank's
@@ -531,15 +556,3 @@ class HybridShardedTables(nn.Module):
         if self.opt_state[0] is None:
             self.opt_state = [torch.zeros_like(p.data) for p in self.shards]
         self._scatter_width(full, self.opt_state[w], self.opt_state[nw + w], w)
-
-    def local_rows_of(self, w, f):
-        """(first global row, this rank's rows) of feature ``f``, width ``w``: a stride-``world`` slice for a sharded table,
-        the whole table (first row 0) for a replicated one."""
-        nw = len(self.dims)
-        if f in self.rep_off:
-            o, v = self.rep_off[f], self.num_rows[f]
-            return 0, self.shards[nw + w].data[o:o + v]
-        j = self.sh.index(f)
-        fr, n = owned_rows(self.num_rows[f], j, self.rank, self.world)
-        b = self.base[self.rank][j]
-        return fr, self.shards[w].data[b:b + n]

@@ -7,7 +7,7 @@ from .sharded import ShardedTables, reduce_dense_grads
 
 
 def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=None, dedup=None, init_seed=None, hybrid=None,
-                replicate_max_rows: int = 1 << 17):
+                replicate_max_rows: int = 1 << 17, hot_rows: int = 0):
     """Every rank calls this with an identically initialised ``model`` (same seed).  The model's tables
     (and, for DeepFM, its first-order tables, which share the ids) are cut into this rank's rows, fused
     into one shard per width on ``device`` and the full tables are dropped; the dense part stays
@@ -20,7 +20,8 @@ def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=
 
     ``hybrid`` (peer mode; default: on when the model qualifies and has small tables or DeepFM's fused terms): tables with at
     most ``replicate_max_rows`` rows stay replicated on every rank (their gradients are all-reduced densely), the others are
-    row-sharded -- ``parallel.hybrid.HybridShardedTables``.
+    row-sharded -- ``parallel.hybrid.HybridShardedTables``.  ``hot_rows`` > 0 additionally replicates the first ``hot_rows``
+    rows of every large direct-id table (the hot rows of a frequency-ordered vocabulary); only the tails are sharded.
     """
     groups = model._groups
     full = [[g.tables[n] for n in g.names] for g in groups]
@@ -42,7 +43,7 @@ def shard_model(model, pg=None, device=None, backend=None, transport=None, mode=
             raise NotImplementedError("hybrid placement needs single-id sum-pooled tables of one width (16 / 32 / 64)")
         if hybrid:
             sharded = HybridShardedTables(groups[0].names, full[0], twins, transport, device, fm=bool(getattr(model, "_fm_term", False)),
-                                          replicate_max_rows=replicate_max_rows, init_seed=init_seed)
+                                          replicate_max_rows=replicate_max_rows, init_seed=init_seed, hot_rows=hot_rows)
         else:
             # tables declared on the meta device (model built with table_device='meta') are created shard by shard, in place
             sharded = PeerShardedTables(groups[0].names, full, transport, device, dedup=dedup, init_seed=init_seed)
