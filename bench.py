@@ -597,7 +597,7 @@ def run_ours(args):
         emit(out)
         return
     graphed_holder = [None]
-    packed = host_packed = None
+    packed = host_packed = host_packed_i64 = None
     if args.no_graph or growing:
         step = eager_step
     else:
@@ -613,7 +613,10 @@ def run_ours(args):
         graphed_holder[0] = graphed
         step = lambda batch, i: graphed(batch)           # noqa: E731
         packed = [graphed.pack(b) for b in resident]     # resident leg: one device-to-device copy per step, like the e2e leg
-        host_packed = [graphed.pack(b, "cpu") for b in host]    # e2e leg: each batch is ONE pinned host block (one H2D copy)
+        # e2e leg: each batch is ONE pinned host block (one H2D copy); --wire-ids i32 (default): the ids cross PCIe as i32 and are
+        # widened on the device (GraphedTrainStep.pack(..., ids="i32")), i64: the reference collate's dtype byte for byte
+        host_packed = [graphed.pack(b, "cpu", ids=args.wire_ids) for b in host]
+        host_packed_i64 = [graphed.pack(b, "cpu") for b in host] if args.wire_ids != "i64" else None
 
     LAG = 3                                   # the host reads step i's loss while steps i+1 .. i+LAG-1 are queued / running
     loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(LAG + 1)]
@@ -678,9 +681,32 @@ def run_ours(args):
     e2e_batches = host_packed if packed is not None else host
     if packed is not None:
         h2d = host_packed[0].numel()                     # the packed block (features padded to 256-byte boundaries)
-    for i in range(3):
-        step(e2e_batches[i % nb], i)
-    ms_e2e = timed(e2e_batches, args.steps, read_loss=True)
+    import gc
+
+    def e2e_leg(batches):
+        """The end-to-end leg: a warm-up through the SAME path (copy stream, staging buffers and the loss read-back are set up
+        before the clock starts), then exactly args.steps timed steps with the garbage collector off.  The leg is host-inclusive
+        (max of device time and wall clock), so a stray host stall -- it has been seen to double a 100-step, 80 ms region on a
+        shared box -- shows up in full: an attempt slower than 1.25x the resident leg is taken again, at most twice; every
+        attempt is reported, the value is the fastest one."""
+        timed(batches, min(10, args.steps), read_loss=True)
+        attempts = []
+        gc.disable()
+        try:
+            for _ in range(3):
+                attempts.append(timed(batches, args.steps, read_loss=True))
+                if attempts[-1] <= 1.25 * ms:
+                    break
+        finally:
+            gc.enable()
+        return min(attempts), [a / args.steps for a in attempts]
+
+    ms_e2e, e2e_attempts = e2e_leg(e2e_batches)
+    e2e_i64 = None
+    if host_packed_i64 is not None:                      # the same leg with the ids as the reference collate emits them (i64)
+        ms_i64, att = e2e_leg(host_packed_i64)
+        e2e_i64 = {"value": B * world * args.steps / (ms_i64 / 1e3), "unit": "samples/s", "ms_per_step": ms_i64 / args.steps,
+                   "h2d_bytes_per_step": host_packed_i64[0].numel(), "attempts_ms_per_step": att}
     clock_info = clocks.stop() if rank == 0 else None
     os.sched_setaffinity(0, all_cpus)                   # the CPU-baseline leg below uses every host core again
 
@@ -742,7 +768,11 @@ def run_ours(args):
                  + " tower GEMMs (tcgen05, fp32 accumulate)",
         "data": "synthetic", "config": workload_config(cfg, B, world), "exact_mode": exact,
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps, "attempts_ms_per_step": e2e_attempts,
+                "host_block": ("one pinned block per batch, ids as i32 on the wire (every table < 2^31 rows), widened to the kernels' i64 "
+                               "on the device" if (packed is not None and args.wire_ids == "i32") else
+                               "pinned host tensors in the reference collate's dtypes (i64 ids)"),
+                "with_i64_ids": e2e_i64},
         "gpu_launches": launches, "cuda_graph": not args.no_graph, "kernels": kern, "kernels_in_step": in_step,
         "roofline": roofline_tensor if roofline_tensor is not None else roofline,
         "roofline_embedding": roofline if roofline_tensor is not None else None,
@@ -824,6 +854,8 @@ def main():
     ap.add_argument("--replicate-max-rows", type=int, default=1 << 17, help="hybrid placement: tables up to this many rows are replicated")
     ap.add_argument("--hot-rows", type=int, default=16384,
                     help="hybrid placement: the first this-many rows of every large direct-id table are replicated too (0 = off)")
+    ap.add_argument("--wire-ids", default="i32", choices=["i32", "i64"],
+                    help="e2e leg: dtype of the ids in the pinned host block (i32 halves the PCIe bytes; the device widens them)")
     ap.add_argument("--dedup", default="auto", choices=["auto", "on", "off"],
                     help="N > 1: fetch / send every distinct row once (auto: above 4 GPUs)")
     args = ap.parse_args()

@@ -273,7 +273,7 @@ def test_graphed_train_step_equals_eager(opt_name):
     gen = torch.Generator().manual_seed(17)
     fc, f0, l0 = _criteo_like(gen, 1024, 5, 300, 16, 3)
     batches = [(f0, l0)]
-    for _ in range(3):
+    for _ in range(5):
         feats = {k: (torch.randint(0, 300, v.shape, generator=gen) if v.dtype == torch.int64
                      else torch.randn(v.shape, generator=gen)) for k, v in f0.items()}
         batches.append((feats, (torch.rand(1024, 1, generator=gen) < 0.25).float()))
@@ -301,9 +301,20 @@ def test_graphed_train_step_equals_eager(opt_name):
         la = a.training_step(batch, i)
         la.backward()
         oa.step()
-        if i >= 2:                                   # the input-prefetch path: copy on a side stream, then one D2D move
+        if i == 1:                                   # the i32 wire block (ids narrowed on the host, widened on the device)
+            lb = graphed(graphed.pack(pinned[i], "cpu", ids="i32"))
+        elif i == 2:                                 # the input-prefetch path: copy on a side stream, then one D2D move
             graphed.prefetch(pinned[i])
             lb = graphed(pinned[i])
+        elif i == 3:                                 # prefetch of a wire block
+            wire = graphed.pack(pinned[i], "cpu", ids="i32")
+            assert wire.numel() < graphed.pack(pinned[i], "cpu").numel()
+            graphed.prefetch(wire)
+            lb = graphed(wire)
+        elif i == 4:                                 # full-width packed block, resident on the device
+            lb = graphed(graphed.pack(batch))
+        elif i == 5:                                 # wire block resident on the device
+            lb = graphed(graphed.pack(batch, ids="i32"))
         else:
             lb = graphed(batch)
         close(lb, la, 1e-5)
@@ -311,6 +322,9 @@ def test_graphed_train_step_equals_eager(opt_name):
     for k in sa:
         if sa[k].dtype.is_floating_point:
             close(sb[k], sa[k], 1e-5)
+    big = ({k: (v + 2 ** 31 if v.dtype == torch.int64 else v) for k, v in batches[0][0].items()}, batches[0][1])
+    with pytest.raises(ValueError):                  # ids that do not fit 32 bits cannot take the wire layout
+        graphed.pack(big, "cpu", ids="i32")
 
 
 @pytest.mark.parametrize("pooling", ["sum", "mean"])

@@ -200,6 +200,7 @@ struct ApplyArgs {
     const float *peer_fm_sum[CTR_MAX_WORLD];
     int fm_row_only;            // FM term with the "c * fm_sum" part already folded into the gradients (ctr_fm_pack_grads):
                                 // only "- row * sum c" is left to do here
+    int gather_prefetch;        // single-id sweep: pull the next outer iteration's gradient slices into L2 one iteration ahead
 };
 
 // last feature whose row_base <= key.  sf is the kernel's parameter copy of the features: sorted positions
@@ -743,19 +744,38 @@ __global__ void __launch_bounds__(kApplyThreads, MINB)
     uint32_t f_lo = 1, f_hi = 0;
     uint32_t closed = 0;
 
+    // keys / slots are loaded two outer iterations ahead: the pairs of the NEXT iteration are in registers when this one starts,
+    // so its gradient slices (random 64-byte reads over [B, stride], the latency this kernel waits on) can be pulled into L2 now
     uint32_t k = kInvalidKey, nk = kInvalidKey, slot = 0;
+    uint32_t k1 = kInvalidKey, nk1 = kInvalidKey, slot1 = 0;
     if (lane < Q && first + lane < end) {
         k = a.keys[first + lane];
         slot = a.vals[first + lane];
         if (first + lane + 1 < S) nk = a.keys[first + lane + 1];
     }
+    if (lane < Q && first + Q + lane < end) {
+        k1 = a.keys[first + Q + lane];
+        slot1 = a.vals[first + Q + lane];
+        if (first + Q + lane + 1 < S) nk1 = a.keys[first + Q + lane + 1];
+    }
+    const bool gather_ahead = a.gather_prefetch != 0 && !a.p2p;
     for (uint32_t p0 = first; p0 < end; p0 += Q) {
         uint32_t k_next = kInvalidKey, nk_next = kInvalidKey, slot_next = 0;
-        const uint32_t pn = p0 + Q + lane;
+        const uint32_t pn = p0 + 2 * Q + lane;
         if (lane < Q && pn < end) {
             k_next = a.keys[pn];
             slot_next = a.vals[pn];
             if (pn + 1 < S) nk_next = a.keys[pn + 1];
+        }
+        if (gather_ahead && k1 != kInvalidKey) {
+            if (k1 < f_lo || k1 >= f_hi) {
+                fi = find_feature(sf, nf, k1);
+                f_lo = sf[fi].row_base;
+                f_hi = f_lo + sf[fi].num_rows;
+            }
+            const float *gp = gout_local + (int64_t)slot1 * gstride + sf[fi].out_col;
+#pragma unroll
+            for (int b = 0; b < D; b += 8) prefetch_l2(gp + b);
         }
         const bool is_tail = k != kInvalidKey && nk != k;
         const unsigned tails = __ballot_sync(kFull, is_tail);
@@ -883,7 +903,8 @@ __global__ void __launch_bounds__(kApplyThreads, MINB)
         }
         if (tails != 0u) head_pending = false;
         closed += (uint32_t)__popc(tails);
-        k = k_next; nk = nk_next; slot = slot_next;
+        k = k1; nk = nk1; slot = slot1;
+        k1 = k_next; nk1 = nk_next; slot1 = slot_next;
     }
     uint32_t flag = 1u;
     if (end < S) {
@@ -1201,6 +1222,8 @@ static int apply_impl(DevGroup &dg, const PlanLayout &p, void *workspace, const 
     if (range < lo) range = lo;
     if (range > 512) range = 512;
     static const int range_env = getenv("CTR_SWEEP_RANGE") ? atoi(getenv("CTR_SWEEP_RANGE")) : 0;   // tuning knob
+    static const int prefetch_env = getenv("CTR_SWEEP_PREFETCH") ? atoi(getenv("CTR_SWEEP_PREFETCH")) : 1;   // 164 vs 170 us (cfg2)
+    a.gather_prefetch = prefetch_env;
     if (range_env > 0) range = (range_env + Q - 1) / Q * Q;
     a.S = (uint32_t)p.S;
     a.range = (uint32_t)range;

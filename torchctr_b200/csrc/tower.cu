@@ -98,20 +98,21 @@ __global__ void __launch_bounds__(kTowerThreads)
 
 // Finalize kernels: a block of kFinCols x kFinLanes threads owns kFinCols columns; lane j adds the partials of
 // blocks j, j + kFinLanes, ... in double, the lanes are then added in lane order (fixed order: deterministic).
-constexpr int kFinCols = 16, kFinLanes = 16;
+constexpr int kFinCols = 16, kFinLanes = 64;
 
 template <int NQ, int LANES = kFinLanes>
 __device__ __forceinline__ bool column_totals(const float *__restrict__ partial, int blocks, int N, double (&tot)[NQ], int *col) {
+    static_assert(LANES % 8 == 0, "lanes are folded eight at a time");
     __shared__ double sh[NQ][LANES][kFinCols];
-    constexpr int kFinLanes = LANES;
+    __shared__ double sh2[NQ][LANES / 8][kFinCols];
     const int c = threadIdx.x % kFinCols, j = threadIdx.x / kFinCols;
     const int n = blockIdx.x * kFinCols + c;
     double acc[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
     if (n < N) {
-#pragma unroll 4
-        for (int b = j; b < blocks; b += kFinLanes) {
+#pragma unroll 8
+        for (int b = j; b < blocks; b += LANES) {       // independent loads: eight blocks in flight per thread
 #pragma unroll
             for (int q = 0; q < NQ; ++q) acc[q] += (double)partial[((size_t)b * NQ + q) * N + n];
         }
@@ -119,19 +120,29 @@ __device__ __forceinline__ bool column_totals(const float *__restrict__ partial,
 #pragma unroll
     for (int q = 0; q < NQ; ++q) sh[q][j][c] = acc[q];
     __syncthreads();
+    if (j < LANES / 8) {                                // lanes 8 j .. 8 j + 7, in lane order
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            double t = 0.0;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) t += sh[q][j * 8 + l][c];
+            sh2[q][j][c] = t;
+        }
+    }
+    __syncthreads();
     *col = n;
     if (j != 0 || n >= N) return false;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
         double t = 0.0;
-        for (int l = 0; l < kFinLanes; ++l) t += sh[q][l][c];
+#pragma unroll
+        for (int l = 0; l < LANES / 8; ++l) t += sh2[q][l][c];
         tot[q] = t;
     }
     return true;
 }
 
-// partials -> mean, rstd (+ running statistics, torch.nn.BatchNorm1d semantics).  LANES threads share a column's partials
-// (16 for the few hundred blocks of col_stats, 64 for the 32-row blocks that come out of the GEMM epilogue).
+// partials -> mean, rstd (+ running statistics, torch.nn.BatchNorm1d semantics).  LANES threads share a column's partials.
 template <int LANES>
 __global__ void __launch_bounds__(kFinCols * LANES)
     bn_finalize_fwd_kernel(const float *__restrict__ partial, int blocks, int B, int N, float eps, float momentum,
@@ -243,7 +254,7 @@ __global__ void __launch_bounds__(kFinCols * kFinLanes)
     c2[n] = (float)(sz / B);
 }
 
-__global__ void __launch_bounds__(kTowerThreads)
+__global__ void __launch_bounds__(kTowerThreads, 4)      // <= 64 registers: all kTowerMaxBlocks blocks resident in one wave
     bn_act_bwd_apply_kernel(const float *__restrict__ gy, int64_t ldgy, const float *__restrict__ z, int64_t ldz,
                             const TowerGeom g, const ActArgs a, const float *__restrict__ c1, const float *__restrict__ c2,
                             float *__restrict__ gz, int64_t ldgz, float *__restrict__ partial) {
@@ -425,22 +436,23 @@ __global__ void __launch_bounds__(kTowerThreads)
     }
 }
 
-// gwe[j] = g sum over blocks of xe_partial[block][j]; gbe = g sum dz is the head's own bias gradient (same number)
-// (one warp per column: lane l adds the blocks l, l + 32, ... in double, then a shuffle tree -- a fixed order)
-__global__ void __launch_bounds__(1024)
-    head_xe_finalize_kernel(const float *__restrict__ xe_partial, int blocks, int ne, const float *__restrict__ gscale,
-                            float *__restrict__ gwe) {
-    const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (j >= ne) return;
-    double t = 0.0;
-    for (int b = lane; b < blocks; b += 32) t += (double)xe_partial[(size_t)b * 32 + j];
-    for (int off = 16; off; off >>= 1) t += __shfl_xor_sync(kFull, t, off);
-    if (lane == 0) gwe[j] = (float)((double)__ldg(gscale) * t);
-}
-
+// gw = g sum_b dz h, gb = g sum_b dz from the two-quantity partials; the LAST block of the grid (when there is a second linear
+// term) computes gwe[j] = g sum over blocks of xe_partial[block][j] instead: one warp per column, lane l adds the blocks
+// l, l + 32, ... in double, then a shuffle tree -- a fixed order.  (gbe = g sum dz is the head's own bias gradient.)
 __global__ void __launch_bounds__(kFinCols * kFinLanes)
     head_bwd_finalize_kernel(const float *__restrict__ partial, int blocks, int H, const float *__restrict__ gscale,
-                             float *__restrict__ gw, float *__restrict__ gb) {
+                             float *__restrict__ gw, float *__restrict__ gb, const float *__restrict__ xe_partial, int ne,
+                             float *__restrict__ gwe) {
+    if (ne > 0 && blockIdx.x == gridDim.x - 1) {
+        const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (j >= ne) return;
+        double t = 0.0;
+#pragma unroll 8
+        for (int b = lane; b < blocks; b += 32) t += (double)xe_partial[(size_t)b * 32 + j];
+        for (int off = 16; off; off >>= 1) t += __shfl_xor_sync(kFull, t, off);
+        if (lane == 0) gwe[j] = (float)((double)__ldg(gscale) * t);
+        return;
+    }
     double tot[2];
     int n;
     if (!column_totals<2>(partial, blocks, H, tot, &n)) return;
@@ -620,8 +632,8 @@ extern "C" int ctr_logit_bce_bwd_ex(const float *h, int64_t ldh, int32_t B, int3
     float *xe_partial = partial + (size_t)kTowerMaxBlocks * 2 * H;       // [blocks][32], behind the two-quantity partials
     note_launch(), head_bwd_kernel<<<g.blocks, kTowerThreads, 0, stream>>>(h, ldh, w, dz, gscale, g, gh, ldgh, gextra, gextra_stride, partial,
                                                                            xe, ldxe, xe ? ne : 0, xe_partial);
-    note_launch(), head_bwd_finalize_kernel<<<(H + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, stream>>>(partial, g.blocks, H, gscale, gw, gb);
-    if (xe != nullptr) note_launch(), head_xe_finalize_kernel<<<1, 32 * ((ne + 0) > 0 ? ne : 1), 0, stream>>>(xe_partial, g.blocks, ne, gscale, gwe);
+    note_launch(), head_bwd_finalize_kernel<<<(H + kFinCols - 1) / kFinCols + (xe != nullptr ? 1 : 0), kFinCols * kFinLanes, 0, stream>>>(
+        partial, g.blocks, H, gscale, gw, gb, xe_partial, xe != nullptr ? ne : 0, gwe);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }

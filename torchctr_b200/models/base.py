@@ -223,12 +223,10 @@ class CTRModelBase(nn.Module):
             seed = self._step_seed(x.device)
             h, i, block = x, 0, 0
             while i + 3 < len(layers) and block_is_fusable(*layers[i:i + 4]):
-                lin = layers[i]
-                pad = h.shape[1] - lin.in_features
-                w = F.pad(lin.weight, (0, pad)) if pad else None      # first layer: 4-float-padded lookup output
+                lin = layers[i]           # (first layer: the 4-float-padded lookup output; the block pads the weight itself)
                 # sharded tables: let the first block write dL/dx straight into the peer-visible gradient matrix
                 provider = getattr(self._sharded, "grad_buffer_provider", None) if block == 0 else None
-                h = tower_block(h, lin, layers[i + 1], layers[i + 3], seed, block, weight=w,
+                h = tower_block(h, lin, layers[i + 1], layers[i + 3], seed, block,
                                 gx_provider=provider(0) if provider is not None else None)
                 i += 4
                 block += 1

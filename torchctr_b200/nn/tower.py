@@ -8,8 +8,18 @@ backward  one reduction pass + one apply pass give dL/dz, dgamma, dbeta and the 
           (``ctr_bn_relu_dropout_bwd``); dL/dx on the tcgen05 kernel; dL/dW = gz^T x.
 The dropout mask is recomputed from (step seed on the device, layer id, element), never stored.  The modules keep
 their parameters, buffers and ``state_dict`` keys; in eval mode they run as plain torch modules.
+
+Off the critical path: nothing downstream of a block's backward needs its WEIGHT gradient before the optimizer step, while
+dL/dx feeds the next block and finally the embedding update.  So dL/dW (the split-K tcgen05 kernel + its reduction) is issued on
+a second stream right after dL/dx and runs next to the following blocks' BatchNorm backward and the embedding sweep (a parallel
+branch when the step is captured into a CUDA graph); the streams are joined when the backward pass ends (an autograd engine
+callback), so ``loss.backward(); optimizer.step()`` needs nothing new.  Only when the parameter's ``.grad`` is unset, i.e. when
+autograd takes the gradient tensor over without launching a kernel (``zero_grad(set_to_none=True)``, torch's default); with
+accumulating gradients everything stays on the one stream.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.nn as nn
@@ -18,10 +28,37 @@ from .. import ops
 from .linear import gemm_nt, gemm_nt_bn_stats, gemm_wgrad, matmul_precision, tc_eligible, wgrad_eligible
 
 
+_wgrad_streams: dict = {}
+_deferred: dict = {}       # device -> [graph task id, tensors the second stream still reads (kept alive until the join)]
+defer_weight_grads = os.environ.get("CTR_DEFER_WGRAD", "1") != "0"   # module switch (tests compare both schedules)
+
+
+def _wgrad_stream(device) -> torch.cuda.Stream:
+    key = torch.device(device)
+    st = _wgrad_streams.get(key)
+    if st is None:
+        st = _wgrad_streams[key] = torch.cuda.Stream(device=key)
+    return st
+
+
+def join_deferred(device=None) -> None:
+    """Make the current stream wait for the weight gradients issued on the second stream.  Runs by itself at the end of every
+    backward pass; idempotent."""
+    for dev in ([torch.device(device)] if device is not None else list(_deferred)):
+        entry = _deferred.pop(dev, None)
+        if entry is not None:
+            torch.cuda.current_stream(dev).wait_stream(_wgrad_stream(dev))
+            entry[1].clear()
+
+
 class _TowerBlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, bn, p_drop, seed_dev, layer_id, precision, gx_provider=None):
-        w = weight.contiguous()
+    def forward(ctx, x, weight, bias, gamma, beta, bn, p_drop, seed_dev, layer_id, precision, gx_provider=None, pad=0):
+        # pad: zero columns appended to the weight here (the first layer reads the 4-float-padded lookup output); the gradient
+        # handed back is that of the unpadded parameter
+        ctx.param = weight
+        ctx.pad = pad
+        w = torch.nn.functional.pad(weight.detach(), (0, pad)) if pad else weight.contiguous()
         tc = tc_eligible(x, w, precision)
         fused = gemm_nt_bn_stats(x, w, bias, bn, precision) if tc else None    # statistics out of the GEMM epilogue
         if fused is not None:
@@ -52,8 +89,32 @@ class _TowerBlockFn(torch.autograd.Function):
                 out = None
             gx = gemm_nt(gz, w.t().contiguous(), out=out, precision=precision) if tc else gz @ w
         if ctx.needs_input_grad[1]:
-            gw = gemm_wgrad(gz, x, precision) if tc and wgrad_eligible(gz, x, precision) else gz.t() @ x
-        return gx, gw, dbias, dgamma, dbeta, None, None, None, None, None, None
+            def weight_grad():
+                g = gemm_wgrad(gz, x, precision) if tc and wgrad_eligible(gz, x, precision) else gz.t() @ x
+                return g[:, :g.shape[1] - ctx.pad].contiguous() if ctx.pad else g
+
+            dev = gz.device
+            if defer_weight_grads and tc and ctx.param.is_leaf and ctx.param.grad is None:
+                main, side = torch.cuda.current_stream(dev), _wgrad_stream(dev)
+                engine_joins = True
+                task = torch._C._current_graph_task_id()
+                if dev in _deferred and _deferred[dev][0] != task:
+                    join_deferred(dev)                 # left over from a backward pass that did not finish
+                if dev not in _deferred:
+                    _deferred[dev] = [task, []]
+                    try:        # joined when this backward pass ends, on the stream backward() was called on
+                        torch.autograd.Variable._execution_engine.queue_callback(lambda: join_deferred(dev))
+                    except RuntimeError:               # no engine to call back (backward() called by hand)
+                        engine_joins = False
+                _deferred[dev][1] += [gz, x]           # main-stream blocks the second stream reads: alive until the join
+                side.wait_stream(main)                 # after dL/dx was issued: the critical path goes first
+                with torch.cuda.stream(side):
+                    gw = weight_grad()
+                if not engine_joins:
+                    join_deferred(dev)
+            else:
+                gw = weight_grad()
+        return gx, gw, dbias, dgamma, dbeta, None, None, None, None, None, None, None
 
 
 def block_is_fusable(linear, bn, act, drop) -> bool:
@@ -64,8 +125,12 @@ def block_is_fusable(linear, bn, act, drop) -> bool:
 
 def tower_block(x, linear: nn.Linear, bn: nn.BatchNorm1d, drop: nn.Dropout, seed_dev, layer_id: int, weight=None,
                 gx_provider=None):
-    """Training-mode forward of [linear, bn, ReLU, drop] on a CUDA tensor.  ``weight`` overrides ``linear.weight``
-    (the first layer reads a zero-padded copy, see ``CTRModelBase._first_linear``)."""
-    w = linear.weight if weight is None else weight
-    return _TowerBlockFn.apply(x, w, linear.bias, bn.weight, bn.bias, bn, float(drop.p), seed_dev, layer_id,
-                               matmul_precision(), gx_provider)
+    """Training-mode forward of [linear, bn, ReLU, drop] on a CUDA tensor.  When ``x`` is wider than ``linear.in_features`` (the
+    first layer reads the 4-float-padded lookup output) the weight is zero-padded inside the node.  ``weight`` overrides
+    ``linear.weight`` as is."""
+    if weight is not None:
+        return _TowerBlockFn.apply(x, weight, linear.bias, bn.weight, bn.bias, bn, float(drop.p), seed_dev, layer_id,
+                                   matmul_precision(), gx_provider, 0)
+    pad = x.shape[1] - linear.in_features
+    return _TowerBlockFn.apply(x, linear.weight, linear.bias, bn.weight, bn.bias, bn, float(drop.p), seed_dev, layer_id,
+                               matmul_precision(), gx_provider, pad)
