@@ -618,6 +618,28 @@ def run_ours(args):
         host_packed = [graphed.pack(b, "cpu", ids=args.wire_ids) for b in host]
         host_packed_i64 = [graphed.pack(b, "cpu") for b in host] if args.wire_ids != "i64" else None
 
+    if args.trace:                            # diagnostic: kernel timeline of graph replays (CUPTI through torch.profiler)
+        from torch.profiler import ProfilerActivity, profile
+        batches = packed if packed is not None else resident
+        for i in range(5):
+            step(batches[i % nb], i)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(3):
+                step(batches[i % nb], i)
+            torch.cuda.synchronize()
+        evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+        t0 = evs[0].time_range.start if evs else 0
+        if rank == 0:
+            with open(args.trace, "w") as f:
+                f.write("# start_us | dur_us | stream | kernel\n")
+                for e in evs:
+                    f.write(f"{e.time_range.start - t0:.1f} | {e.time_range.end - e.time_range.start:.1f} | {getattr(e, 'device_resource_id', '?')} | {e.name[:90]}\n")
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+        return
     LAG = 3                                   # the host reads step i's loss while steps i+1 .. i+LAG-1 are queued / running
     loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(LAG + 1)]
     loss_ev = [torch.cuda.Event() for _ in range(LAG + 1)]
@@ -854,6 +876,7 @@ def main():
     ap.add_argument("--replicate-max-rows", type=int, default=1 << 17, help="hybrid placement: tables up to this many rows are replicated")
     ap.add_argument("--hot-rows", type=int, default=16384,
                     help="hybrid placement: the first this-many rows of every large direct-id table are replicated too (0 = off)")
+    ap.add_argument("--trace", default="", help="diagnostic: write the kernel timeline of three steps to this file and exit")
     ap.add_argument("--wire-ids", default="i32", choices=["i32", "i64"],
                     help="e2e leg: dtype of the ids in the pinned host block (i32 halves the PCIe bytes; the device widens them)")
     ap.add_argument("--dedup", default="auto", choices=["auto", "on", "off"],

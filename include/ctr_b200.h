@@ -321,6 +321,11 @@ int ctr_bn_relu_dropout_bwd(const float *gy, int64_t ldgy, const float *z, int64
                             const float *mean, const float *rstd, const float *gamma, const float *beta, float p_drop,
                             const uint64_t *seed_dev, uint64_t seed_offset, float *gz, int64_t ldgz, float *dgamma,
                             float *dbeta, float *dbias, void *workspace, void *stream);
+/* dbias[N] of a ctr_bn_relu_dropout_bwd(..., dbias = NULL, workspace) call, from the per-block partials that call left in
+ * `workspace` (same B, N).  Nothing on the way to dL/dx needs the bias gradient (torchctr/trainer.py:301-303: it is read by
+ * optimizer.step() only), so it may be issued on another stream, ordered after that call and before the next use of the
+ * workspace. */
+int ctr_bn_bias_grad_from_partials(const void *workspace, int32_t B, int32_t N, float *dbias, void *stream);
 
 /* ---- logit head: the last Linear(H -> 1) of the tower (dnn.py:46) + extra logit terms + the mean
  * binary_cross_entropy_with_logits of dnn.py:75, forward and backward.  h f32 [B, H] (H a power of two in [4, 128],
@@ -344,6 +349,12 @@ int ctr_logit_bce_fwd_ex(const float *h, int64_t ldh, int32_t B, int32_t H, cons
 int ctr_logit_bce_bwd_ex(const float *h, int64_t ldh, int32_t B, int32_t H, const float *w, const float *dz, const float *gscale,
                          float *gh, int64_t ldgh, float *gw, float *gb, float *gextra, int64_t gextra_stride, const float *xe,
                          int64_t ldxe, int32_t ne, float *gwe, void *workspace, void *stream);
+/* ctr_logit_bce_bwd / _bwd_ex accept gw = NULL: only gh / gextra are produced and the per-block partials stay in `workspace`;
+ * this call turns them into gw[H], gb[1] (may be NULL) and gwe[ne] (ne = 0: none) -- the parameter gradients of the last
+ * Linear (dnn.py:46), needed by optimizer.step() only, so it may run on another stream (ordered after the bwd call, before the
+ * next use of the workspace). */
+int ctr_logit_bce_bwd_finalize(int32_t B, int32_t H, const float *gscale, float *gw, float *gb, int32_t ne, float *gwe,
+                               const void *workspace, void *stream);
 
 /* torch.optim.Adagrad (lr_decay = 0, weight_decay = 0) over `count` <= 48 dense fp32 tensors in ONE launch:
  * sum += g*g; p -= lr * g / (sqrt(sum) + eps).  params / grads / sums / sizes are HOST arrays of device pointers / sizes. */

@@ -30,7 +30,6 @@ TRAFFIC_KEYS = [
     ("emb_bwd_sweep", "emb_bwd_apply"),
     ("emb_pool_fwd_l1_kernel<4, 4, 0, 1", "emb_pool_fwd_fused"),
     ("emb_pool_fwd", "emb_pool_fwd"),
-    ("linear_tf32_pair", "linear_tf32_cross"),
 ]
 
 

@@ -178,3 +178,58 @@ def test_fused_adagrad_equals_torch_adagrad():
     sd = o1.state_dict()
     o3 = torch.optim.Adagrad([p.detach().clone().requires_grad_(True) for p in p1], lr=0.05)
     o3.load_state_dict(sd)                          # same state layout as torch.optim.Adagrad
+
+
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+def test_deferred_weight_gradients_equal_the_single_stream_schedule(precision):
+    """nn/tower.py issues the weight / bias gradients of the tower and of the logit head on a second stream (joined when the
+    backward pass ends) when autograd takes the gradient tensors over as they are.  Same kernels, same order of every sum:
+    the gradients and the updated parameters are bit-identical to the single-stream schedule -- also when ``.grad`` is already
+    set (accumulation), where everything stays on the one stream."""
+    from torchctr_b200.models import DeepFM
+    from torchctr_b200.nn import set_matmul_precision, tower
+    gen = torch.Generator().manual_seed(5)
+    B, F, D, nd = 2048, 5, 16, 3           # 5 * 16 + 3 = 83 -> padded to 84: the first layer's weight is padded inside the node
+    fc = [{"name": f"c{i}", "type": "sparse", "num_embeddings": 200 + i, "emb_dim": D} for i in range(F)]
+    fc += [{"name": f"d{i}", "type": "dense"} for i in range(nd)]
+    batches = []
+    for _ in range(3):
+        feats = {f"c{i}": torch.randint(0, 200 + i, (B, 1), generator=gen).cuda() for i in range(F)}
+        feats["dense_features"] = torch.randn(B, nd, generator=gen).cuda()
+        batches.append((feats, (torch.rand(B, 1, generator=gen) < 0.25).float().cuda()))
+    set_matmul_precision(precision)
+    old = tower.defer_weight_grads
+    try:
+        results = []
+        for defer, flat in ((False, False), (True, False), (True, True)):
+            # flat: every dense .grad is a view of one buffer (the multi-GPU all-reduce layout): the second stream adds into it
+            tower.defer_weight_grads = defer
+            torch.manual_seed(3)
+            m = DeepFM(fc, [64, 32]).cuda().train()
+            opt = torch.optim.Adagrad(m.dense_parameters(), lr=0.05)
+            m.bind_optimizer(opt, kind="adagrad")
+            if flat:
+                m.enable_flat_dense_grads()
+            grads = []
+            for i, batch in enumerate(batches):
+                if i != 2 and flat:
+                    m.zero_dense_grads()
+                elif i != 2:
+                    opt.zero_grad(set_to_none=True)      # step 2 accumulates on top of step 1's gradients
+                m.training_step(batch, i).backward()
+                grads.append({k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+                opt.step()
+            torch.cuda.synchronize()
+            assert not tower._deferred, "the second stream was not joined at the end of backward"
+            results.append((grads, {k: v.clone() for k, v in m.state_dict().items()}))
+        g0, s0 = results[0]
+        for g1, s1 in results[1:]:
+            for a, b in zip(g0, g1):
+                assert a.keys() == b.keys() and len(a) >= 10
+                for k in a:
+                    assert torch.equal(a[k], b[k]), k
+            for k in s0:
+                assert torch.equal(s0[k], s1[k]), k
+    finally:
+        tower.defer_weight_grads = old
+        set_matmul_precision(None)

@@ -121,6 +121,8 @@ _SIGNATURES = {
                                           _P, C.c_int64, _P]),
     "ctr_bn_relu_dropout_bwd": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_float, _P,
                                           C.c_uint64, _P, C.c_int64, _P, _P, _P, _P, _P]),
+    "ctr_bn_bias_grad_from_partials": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
+    "ctr_logit_bce_bwd_finalize": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P]),
     "ctr_logit_bce_fwd": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "ctr_logit_bce_bwd": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_int64, _P, _P]),
     "ctr_logit_bce_fwd_ex": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P, _P,

@@ -582,6 +582,21 @@ extern "C" int ctr_bn_relu_dropout_bwd(const float *gy, int64_t ldgy, const floa
     return CTR_OK;
 }
 
+// the bias gradient left out of a ctr_bn_relu_dropout_bwd(..., dbias = NULL, workspace) call: column sums of gz from the
+// per-block partials that call left in `workspace`.  Nothing on the path to dL/dx needs it, so the caller may issue it on
+// another stream (ordered after that call, and before the next call that uses the same workspace).
+extern "C" int ctr_bn_bias_grad_from_partials(const void *workspace, int32_t B, int32_t N, float *dbias, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_tower_shape(B, N, N);
+    if (rc != CTR_OK) return rc;
+    CTR_REQUIRE(workspace != nullptr && dbias != nullptr, "null pointer");
+    const TowerGeom g = tower_geom(B, N);
+    note_launch(), col_sum_finalize_kernel<<<(N + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, stream>>>(
+        static_cast<const float *>(workspace), g.blocks, N, dbias);
+    CTR_CUDA_OK(cudaGetLastError());
+    return CTR_OK;
+}
+
 extern "C" int ctr_logit_bce_fwd(const float *h, int64_t ldh, int32_t B, int32_t H, const float *w, const float *bias,
                                  const float *extra, int64_t extra_stride, const float *labels, int64_t label_stride,
                                  float *logits, float *dz, float *loss, void *workspace, void *stream_) {
@@ -621,19 +636,36 @@ extern "C" int ctr_logit_bce_bwd_ex(const float *h, int64_t ldh, int32_t B, int3
                                     int64_t gextra_stride, const float *xe, int64_t ldxe, int32_t ne, float *gwe, void *workspace,
                                     void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    CTR_REQUIRE(xe == nullptr || (gwe != nullptr && ne >= 1 && ne <= 32 && ldxe >= ne && H >= 32),
+    CTR_REQUIRE(xe == nullptr || ((gwe != nullptr || gw == nullptr) && ne >= 1 && ne <= 32 && ldxe >= ne && H >= 32),
                 "second linear term: 1 <= ne <= 32, H >= 32 (the block's row lanes stage [RL][32] partials), gwe required");
     CTR_REQUIRE(B >= 1 && H >= 4 && H <= 128 && (H & (H - 1)) == 0, "head: B=%d, H=%d unsupported (H: power of two in [4, 128])", B, H);
     CTR_REQUIRE(ldh >= H && ldh % 4 == 0 && (gh == nullptr || (ldgh >= H && ldgh % 4 == 0)), "row pitches must be multiples of 4 and >= H");
-    CTR_REQUIRE(h && w && dz && gscale && gw && workspace, "null pointer");
+    CTR_REQUIRE(h && w && dz && gscale && workspace, "null pointer");
     CTR_REQUIRE(aligned16(h) && aligned16(w) && aligned16(gh) && aligned16(workspace), "operands must be 16-byte aligned");
     const TowerGeom g = tower_geom(B, H);
     float *partial = static_cast<float *>(workspace);
     float *xe_partial = partial + (size_t)kTowerMaxBlocks * 2 * H;       // [blocks][32], behind the two-quantity partials
     note_launch(), head_bwd_kernel<<<g.blocks, kTowerThreads, 0, stream>>>(h, ldh, w, dz, gscale, g, gh, ldgh, gextra, gextra_stride, partial,
                                                                            xe, ldxe, xe ? ne : 0, xe_partial);
-    note_launch(), head_bwd_finalize_kernel<<<(H + kFinCols - 1) / kFinCols + (xe != nullptr ? 1 : 0), kFinCols * kFinLanes, 0, stream>>>(
-        partial, g.blocks, H, gscale, gw, gb, xe_partial, xe != nullptr ? ne : 0, gwe);
+    CTR_CUDA_OK(cudaGetLastError());
+    if (gw == nullptr) return CTR_OK;        // the parameter gradients are finalised later: ctr_logit_bce_bwd_finalize
+    return ctr_logit_bce_bwd_finalize(B, H, gscale, gw, gb, xe != nullptr ? ne : 0, gwe, workspace, stream_);
+}
+
+// gw[H], gb[1] (may be NULL) and gwe[ne] (ne = 0: none) from the partials a ctr_logit_bce_bwd(_ex)(..., gw = NULL, ...) call left
+// in `workspace`.  dL/dh does not depend on them, so the caller may issue this on another stream (ordered after that call,
+// and before the next call that uses the same workspace).
+extern "C" int ctr_logit_bce_bwd_finalize(int32_t B, int32_t H, const float *gscale, float *gw, float *gb, int32_t ne, float *gwe,
+                                          const void *workspace, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CTR_REQUIRE(B >= 1 && H >= 4 && H <= 128 && (H & (H - 1)) == 0, "head: B=%d, H=%d unsupported (H: power of two in [4, 128])", B, H);
+    CTR_REQUIRE(gscale && gw && workspace, "null pointer");
+    CTR_REQUIRE(ne >= 0 && ne <= 32 && (ne == 0 || gwe != nullptr), "second linear term: 0 <= ne <= 32, gwe required");
+    const TowerGeom g = tower_geom(B, H);
+    const float *partial = static_cast<const float *>(workspace);
+    const float *xe_partial = partial + (size_t)kTowerMaxBlocks * 2 * H;
+    note_launch(), head_bwd_finalize_kernel<<<(H + kFinCols - 1) / kFinCols + (ne > 0 ? 1 : 0), kFinCols * kFinLanes, 0, stream>>>(
+        partial, g.blocks, H, gscale, gw, gb, xe_partial, ne, gwe);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }

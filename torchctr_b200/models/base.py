@@ -174,6 +174,7 @@ class CTRModelBase(nn.Module):
         off = 0
         for p in params:
             p.grad = flat[off:off + p.numel()].view_as(p)
+            p._ctr_direct_grad = True       # nn/tower.py: gradients made on the second stream are added into the view there
             off += p.numel()
         self._flat_dense_grad = flat
         return flat
@@ -183,6 +184,7 @@ class CTRModelBase(nn.Module):
         if flat is None:
             for p in self.dense_parameters():
                 p.grad = None
+                p._ctr_direct_grad = False
         else:
             flat.zero_()
 

@@ -9,6 +9,8 @@ bound), so neither a ``[B, L, D]`` activation nor a dense ``[V, D]`` gradient ex
 """
 from __future__ import annotations
 
+import os
+
 import warnings
 
 import torch
@@ -269,6 +271,17 @@ class _Workspace:
 
 
 _side_streams: dict = {}
+PLAN_START = os.environ.get("CTR_PLAN_START", "after")      # where the backward plan (the sort) is issued: before | after | head
+_late_starts: list = []
+
+
+def run_late_starts() -> None:
+    """Issue the backward plans whose start was left for later (PLAN_START = "head": the fused logit head calls this)."""
+    while _late_starts:
+        link = _late_starts.pop()
+        fn, link.late = link.late, None
+        if fn is not None:
+            fn()
 
 
 def _side_stream(device) -> torch.cuda.Stream:
@@ -391,25 +404,36 @@ class _LookupCall:
         call = ops.make_group(self._specs([w.detach() for w in weights[:n]], False, twin_data), B, out, self.stride,
                               dense=dense, dense_col=self.dense_col, zero_from=zero_from, status=self.status,
                               extra=self.extra, fm_sum=self.fm_sum, fm=self.fm)
-        ops.emb_pool_fwd(call)
         link = self.plan_link
+        early = None
         if link is not None and self.training:               # every linked forward runs before any backward
             need = ops.emb_bwd_workspace_bytes(call)
             link.nbytes = max(link.nbytes, need)
             if link.ws is None and self.binding is not None and self.grad_enabled:
-                # The sort depends on the ids only: start it NOW on a side stream, next to the tower's forward and
-                # backward (in a captured CUDA graph: a parallel branch).  It is a chain of small latency-bound
-                # kernels that leaves most of the machine idle, so the overlap is nearly free.
+                # The sort depends on the ids only: it runs on a side stream, next to the lookup / the tower (in a captured
+                # CUDA graph: a parallel branch).  It is a chain of small latency-bound kernels that leaves most of the
+                # machine idle -- but its blocks do hold SM slots the tower's GEMM CTAs (~200 KB of shared memory each) wait
+                # for, so WHERE it starts matters (PLAN_START): "before" the lookup kernel, "after" it, or at the logit "head".
                 link.ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
-                side = _side_stream(dev)
-                if not torch.cuda.is_current_stream_capturing():
-                    link.ws.record_stream(side)      # a forward without backward must not hand the block back too early
-                    for _, ids, _ in self.entries:
-                        ids.record_stream(side)
-                side.wait_stream(torch.cuda.current_stream(dev))
-                with torch.cuda.stream(side):
-                    ops.emb_bwd_plan(call, link.ws, runs=False)
-                link.pending = side
+
+                def early(link=link, call=call):
+                    side = _side_stream(dev)
+                    if not torch.cuda.is_current_stream_capturing():
+                        link.ws.record_stream(side)      # a forward without backward must not hand the block back too early
+                        for _, ids, _ in self.entries:
+                            ids.record_stream(side)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):
+                        ops.emb_bwd_plan(call, link.ws, runs=False)
+                    link.pending = side
+        if early is not None and PLAN_START == "before":
+            early()
+        ops.emb_pool_fwd(call)
+        if early is not None and PLAN_START == "head":
+            link.late = early
+            _late_starts.append(link)
+        elif early is not None and PLAN_START != "before":
+            early()
         return out
 
     def _run_backward(self, grad_out, grad_extra=None):
@@ -440,6 +464,8 @@ class _LookupCall:
             # weights next to its embeddings) share one plan per step
             need = ops.emb_bwd_workspace_bytes(call)
             link.nbytes = max(link.nbytes, need)
+            if link.late is not None:                         # nobody started the sort yet (PLAN_START = "head", no fused head)
+                run_late_starts()
             if link.pending is not None:                      # the early sort of run_forward
                 torch.cuda.current_stream(dev).wait_stream(link.pending)
                 link.pending = None
@@ -492,6 +518,7 @@ class PlanLink:
         self.ws = None
         self.nbytes = nbytes
         self.pending = None      # side stream an early sort is running on
+        self.late = None         # the launch of that sort, when it has been left to run_late_starts()
         self.has_runs = False    # the plan in ws lists the runs (needed for unique-row outputs only)
 
 

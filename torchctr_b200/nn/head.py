@@ -12,6 +12,8 @@ from .. import ops
 class _LogitBceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, weight, bias, extra, labels, xe, we, be):
+        from .embedding import run_late_starts
+        run_late_starts()                   # backward plans left to start here (embedding.PLAN_START = "head")
         w = weight.reshape(-1).contiguous()
         we_flat = None if we is None else we.reshape(-1).contiguous()
         loss, dz, _ = ops.logit_bce_fwd(h, w, bias, extra, labels, xe=xe, we=we_flat, be=be)
@@ -20,17 +22,43 @@ class _LogitBceFn(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.has_be = be is not None
         ctx.wshape = tuple(weight.shape)
+        ctx.params = (weight, bias, we, be)
         ctx.weshape = None if we is None else tuple(we.shape)
         return loss
 
     @staticmethod
     def backward(ctx, gloss):
+        from . import tower as _tower
         h, w, dz, xe = ctx.saved_tensors
         g = gloss.reshape(1).to(torch.float32).contiguous()
+        params = [p for p in ctx.params if p is not None]
+        # the parameter gradients (last Linear, Linear(dense)) are read by optimizer.step() only: their finalisation runs on the
+        # second stream (nn/tower.py) when autograd takes the tensors over as they are
+        defer = _tower.defer_weight_grads and all(_tower._takes_over(p) for p in params)
         gh, gw, gb, gextra, gwe = ops.logit_bce_bwd(h, w, dz, g, ctx.needs_input_grad[0],
-                                                    ctx.has_extra and ctx.needs_input_grad[3], xe=xe)
+                                                    ctx.has_extra and ctx.needs_input_grad[3], xe=xe,
+                                                    defer_params_tag="head" if defer else None)
+        gbe = None
+        if defer:
+            dev = h.device
+            main, side, engine_joins = _tower._defer_begin(dev)
+            _tower._deferred[dev][1] += [g, h]
+            side.wait_stream(main)
+            weight, bias, we, be = ctx.params
+            with torch.cuda.stream(side):
+                gw, gb, gwe = ops.logit_bce_bwd_params(h, g, 0 if xe is None else xe.shape[1], "head")
+                if ctx.has_be:
+                    gbe = _tower._deliver(be, gb.clone())
+                gw = _tower._deliver(weight, gw.view(ctx.wshape))
+                gb = _tower._deliver(bias, gb) if ctx.has_bias else None
+                gwe = _tower._deliver(we, gwe.view(ctx.weshape)) if gwe is not None else None
+            if not engine_joins:
+                _tower.join_deferred(dev)
+            return gh, gw, gb, gextra, None, None, gwe, gbe
+        if ctx.has_be:
+            gbe = gb.clone()
         return (gh, gw.view(ctx.wshape), (gb if ctx.has_bias else None), gextra, None, None,
-                (gwe.view(ctx.weshape) if gwe is not None else None), (gb.clone() if ctx.has_be else None))
+                (gwe.view(ctx.weshape) if gwe is not None else None), gbe)
 
 
 def head_eligible(h: torch.Tensor, linear: torch.nn.Linear, labels: torch.Tensor) -> bool:

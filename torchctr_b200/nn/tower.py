@@ -37,18 +37,67 @@ def _wgrad_stream(device) -> torch.cuda.Stream:
     key = torch.device(device)
     st = _wgrad_streams.get(key)
     if st is None:
-        st = _wgrad_streams[key] = torch.cuda.Stream(device=key)
+        st = _wgrad_streams[key] = torch.cuda.Stream(device=key, priority=-1 if os.environ.get("CTR_WGRAD_PRIO", "0") == "1" else 0)
     return st
 
 
 def join_deferred(device=None) -> None:
-    """Make the current stream wait for the weight gradients issued on the second stream.  Runs by itself at the end of every
-    backward pass; idempotent."""
+    """Make the current stream wait for the weight gradients issued on the second stream and let go of the tensors that
+    stream was reading.  Runs by itself at the end of every backward pass (on the stream backward() was called on); idempotent."""
     for dev in ([torch.device(device)] if device is not None else list(_deferred)):
         entry = _deferred.pop(dev, None)
         if entry is not None:
             torch.cuda.current_stream(dev).wait_stream(_wgrad_stream(dev))
             entry[1].clear()
+
+
+def wait_deferred(device) -> None:
+    """Make the CURRENT stream wait for the second stream without ending the deferral: for a consumer that reads the dense
+    gradients inside the backward pass (the all-reduce of the hybrid placement, issued from the lookup's backward node)."""
+    dev = torch.device(device)
+    if dev in _deferred:
+        torch.cuda.current_stream(dev).wait_stream(_wgrad_stream(dev))
+
+
+def _defer_begin(dev):
+    """-> (main stream, second stream, engine_joins).  Registers the end-of-backward join once per backward pass."""
+    main, side = torch.cuda.current_stream(dev), _wgrad_stream(dev)
+    engine_joins = True
+    task = torch._C._current_graph_task_id()
+    if dev in _deferred and _deferred[dev][0] != task:
+        join_deferred(dev)                 # left over from a backward pass that did not finish
+    if dev not in _deferred:
+        _deferred[dev] = [task, []]
+        try:        # joined when this backward pass ends, on the stream backward() was called on
+            torch.autograd.Variable._execution_engine.queue_callback(lambda: join_deferred(dev))
+        except RuntimeError:               # no engine to call back (backward() called by hand)
+            engine_joins = False
+    return main, side, engine_joins
+
+
+def _grad_mode(param) -> str:
+    """How the gradient of ``param`` can leave the second stream:
+    "steal"   ``.grad`` is unset: autograd takes the tensor over as it is (no kernel on its own stream);
+    "direct"  ``.grad`` is a view of the model's flat gradient buffer (``CTRModelBase.enable_flat_dense_grads`` marks those
+              parameters): the second stream adds into it and autograd gets None;
+    "main"    anything else (plain accumulation): autograd adds on its own stream, so the gradient is made there too."""
+    if param is None or not param.is_leaf:
+        return "main"
+    if param.grad is None:
+        return "steal"
+    return "direct" if getattr(param, "_ctr_direct_grad", False) else "main"
+
+
+def _takes_over(param) -> bool:
+    return _grad_mode(param) != "main"
+
+
+def _deliver(param, g):
+    """(on the second stream) hand ``g`` to autograd, or add it into the flat buffer and hand None"""
+    if g is not None and _grad_mode(param) == "direct":
+        param.grad.add_(g.view_as(param.grad))
+        return None
+    return g
 
 
 class _TowerBlockFn(torch.autograd.Function):
@@ -57,9 +106,24 @@ class _TowerBlockFn(torch.autograd.Function):
         # pad: zero columns appended to the weight here (the first layer reads the 4-float-padded lookup output); the gradient
         # handed back is that of the unpadded parameter
         ctx.param = weight
+        ctx.bias_param = bias
+        ctx.bn_params = (gamma, beta)
         ctx.pad = pad
         w = torch.nn.functional.pad(weight.detach(), (0, pad)) if pad else weight.contiguous()
         tc = tc_eligible(x, w, precision)
+        ctx.wt = ctx.wt_ready = None
+        if tc and defer_weight_grads and ctx.needs_input_grad[0] and precision == "tf32":
+            # W^T for the input-gradient GEMM of backward, made NOW on the second stream (next to this block's forward)
+            # instead of on the critical path of backward
+            dev = x.device
+            main, side = torch.cuda.current_stream(dev), _wgrad_stream(dev)
+            wt = torch.empty(w.shape[1], w.shape[0], dtype=w.dtype, device=dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                wt.copy_(w.t())
+                ctx.wt_ready = torch.cuda.Event()
+                ctx.wt_ready.record(side)
+            ctx.wt = wt
         fused = gemm_nt_bn_stats(x, w, bias, bn, precision) if tc else None    # statistics out of the GEMM epilogue
         if fused is not None:
             z, mean, rstd = fused
@@ -80,40 +144,54 @@ class _TowerBlockFn(torch.autograd.Function):
         p_drop, seed_dev, layer_id, tc, precision = ctx.meta
         if gy.stride(1) != 1 or gy.stride(0) % 4 != 0 or gy.data_ptr() % 16 != 0:
             gy = gy.contiguous()
-        gz, dgamma, dbeta, dbias = ops.bn_relu_dropout_bwd(gy, z, mean, rstd, gamma, beta, p_drop, seed_dev, layer_id)
+        dev = gy.device
+        want_dbias = ctx.needs_input_grad[2]
+        defer_dbias = defer_weight_grads and want_dbias and _takes_over(ctx.bias_param)
+        gz, dgamma, dbeta, dbias = ops.bn_relu_dropout_bwd(gy, z, mean, rstd, gamma, beta, p_drop, seed_dev, layer_id,
+                                                           want_dbias=want_dbias,
+                                                           defer_dbias_tag=("block", layer_id) if defer_dbias else None)
         gx = gw = None
         if ctx.needs_input_grad[0]:
             # gx_provider: a buffer the caller wants dL/dx in (the peer-visible gradient matrix of the sharded tables)
             out = ctx.gx_provider() if (tc and ctx.gx_provider is not None) else None
             if out is not None and tuple(out.shape) != tuple(x.shape):
                 out = None
-            gx = gemm_nt(gz, w.t().contiguous(), out=out, precision=precision) if tc else gz @ w
-        if ctx.needs_input_grad[1]:
-            def weight_grad():
-                g = gemm_wgrad(gz, x, precision) if tc and wgrad_eligible(gz, x, precision) else gz.t() @ x
-                return g[:, :g.shape[1] - ctx.pad].contiguous() if ctx.pad else g
-
-            dev = gz.device
-            if defer_weight_grads and tc and ctx.param.is_leaf and ctx.param.grad is None:
-                main, side = torch.cuda.current_stream(dev), _wgrad_stream(dev)
-                engine_joins = True
-                task = torch._C._current_graph_task_id()
-                if dev in _deferred and _deferred[dev][0] != task:
-                    join_deferred(dev)                 # left over from a backward pass that did not finish
-                if dev not in _deferred:
-                    _deferred[dev] = [task, []]
-                    try:        # joined when this backward pass ends, on the stream backward() was called on
-                        torch.autograd.Variable._execution_engine.queue_callback(lambda: join_deferred(dev))
-                    except RuntimeError:               # no engine to call back (backward() called by hand)
-                        engine_joins = False
-                _deferred[dev][1] += [gz, x]           # main-stream blocks the second stream reads: alive until the join
-                side.wait_stream(main)                 # after dL/dx was issued: the critical path goes first
-                with torch.cuda.stream(side):
-                    gw = weight_grad()
-                if not engine_joins:
-                    join_deferred(dev)
+            if tc:
+                wt = ctx.wt
+                if wt is not None:
+                    torch.cuda.current_stream(dev).wait_event(ctx.wt_ready)
+                else:
+                    wt = w.t().contiguous()
+                gx = gemm_nt(gz, wt, out=out, precision=precision)
             else:
-                gw = weight_grad()
+                gx = gz @ w
+        want_gw = ctx.needs_input_grad[1]
+        defer_gw = defer_weight_grads and want_gw and tc and _takes_over(ctx.param)
+
+        def weight_grad():
+            g = gemm_wgrad(gz, x, precision) if tc and wgrad_eligible(gz, x, precision) else gz.t() @ x
+            return g[:, :g.shape[1] - ctx.pad].contiguous() if ctx.pad else g
+
+        if want_gw and not defer_gw:
+            gw = weight_grad()
+        if defer_gw or defer_dbias:
+            main, side, engine_joins = _defer_begin(dev)
+            _deferred[dev][1] += [gz, x]           # main-stream blocks the second stream reads: alive until the join
+            direct_bn = [defer_weight_grads and _grad_mode(p) == "direct" for p in ctx.bn_params]
+            if any(direct_bn):
+                _deferred[dev][1] += [dgamma, dbeta]
+            side.wait_stream(main)                 # after dL/dx was issued: the critical path goes first
+            with torch.cuda.stream(side):
+                if defer_gw:
+                    gw = _deliver(ctx.param, weight_grad())
+                if defer_dbias:
+                    dbias = _deliver(ctx.bias_param, ops.bn_bias_grad_deferred(gz, ("block", layer_id)))
+                if direct_bn[0]:
+                    dgamma = _deliver(ctx.bn_params[0], dgamma)
+                if direct_bn[1]:
+                    dbeta = _deliver(ctx.bn_params[1], dbeta)
+            if not engine_joins:
+                join_deferred(dev)
         return gx, gw, dbias, dgamma, dbeta, None, None, None, None, None, None, None
 
 

@@ -665,8 +665,10 @@ def emb_bwd_apply_p2p(call: GroupCall, shard: _lib.Shard, workspace: torch.Tenso
 _tower_ws: dict = {}
 
 
-def tower_workspace(device, N: int) -> torch.Tensor:
-    key = (device, N)
+def tower_workspace(device, N: int, tag=None) -> torch.Tensor:
+    """Scratch of the tower / head kernels for width N.  ``tag``: a workspace of its own (the calls whose per-block partials
+    are finalised later on another stream must not share theirs with the kernels that run in between)."""
+    key = (device, N, tag)
     ws = _tower_ws.get(key)
     if ws is None:
         ws = torch.empty(_lib.check(_lib.lib().ctr_tower_workspace_bytes(N)), dtype=torch.uint8, device=device)
@@ -707,8 +709,10 @@ def bn_relu_dropout_fwd(z, mean, rstd, gamma, beta, p_drop: float, seed_dev, see
 
 
 @_guarded
-def bn_relu_dropout_bwd(gy, z, mean, rstd, gamma, beta, p_drop: float, seed_dev, seed_offset: int, want_dbias: bool = True):
-    """-> (gz [B, N], dgamma [N], dbeta [N], dbias [N] or None)"""
+def bn_relu_dropout_bwd(gy, z, mean, rstd, gamma, beta, p_drop: float, seed_dev, seed_offset: int, want_dbias: bool = True,
+                        defer_dbias_tag=None):
+    """-> (gz [B, N], dgamma [N], dbeta [N], dbias [N] or None).  ``defer_dbias_tag``: leave the bias gradient's per-block
+    partials in a workspace of that tag and return ``dbias = None``; ``bn_bias_grad_deferred`` finishes it (on any stream)."""
     _rows2d(gy, "gy")
     _rows2d(z, "z")
     B, N = z.shape
@@ -716,14 +720,29 @@ def bn_relu_dropout_bwd(gy, z, mean, rstd, gamma, beta, p_drop: float, seed_dev,
     gz = torch.empty(B, N, dtype=torch.float32, device=dev)
     dgamma = torch.empty(N, dtype=torch.float32, device=dev)
     dbeta = torch.empty(N, dtype=torch.float32, device=dev)
-    dbias = torch.empty(N, dtype=torch.float32, device=dev) if want_dbias else None
+    deferred = want_dbias and defer_dbias_tag is not None
+    dbias = torch.empty(N, dtype=torch.float32, device=dev) if (want_dbias and not deferred) else None
+    ws = tower_workspace(dev, N, defer_dbias_tag if deferred else None)
     with _timed("bn_act_bwd"):
         _lib.check(_lib.lib().ctr_bn_relu_dropout_bwd(gy.data_ptr(), gy.stride(0), z.data_ptr(), z.stride(0), B, N, mean.data_ptr(),
                                                       rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), p_drop,
                                                       _lib.ptr(seed_dev), seed_offset, gz.data_ptr(), gz.stride(0),
                                                       dgamma.data_ptr(), dbeta.data_ptr(), _lib.ptr(dbias),
-                                                      tower_workspace(dev, N).data_ptr(), _stream(z)), "ctr_bn_relu_dropout_bwd")
+                                                      ws.data_ptr(), _stream(z)), "ctr_bn_relu_dropout_bwd")
     return gz, dgamma, dbeta, dbias
+
+
+@_guarded
+def bn_bias_grad_deferred(gz: torch.Tensor, tag) -> torch.Tensor:
+    """dbias [N] of the ``bn_relu_dropout_bwd(..., defer_dbias_tag=tag)`` call that produced ``gz`` [B, N] (the last one on
+    (device, N, tag)); launched on the CURRENT stream, which the caller has ordered after that call."""
+    B, N = gz.shape
+    device = gz.device
+    dbias = torch.empty(N, dtype=torch.float32, device=device)
+    with _timed("bn_bias_grad"):
+        _lib.check(_lib.lib().ctr_bn_bias_grad_from_partials(tower_workspace(device, N, tag).data_ptr(), B, N, dbias.data_ptr(),
+                                                             _stream(dbias)), "ctr_bn_bias_grad_from_partials")
+    return dbias
 
 
 _wgrad_ws: dict = {}
@@ -778,24 +797,42 @@ def logit_bce_fwd(h, w, bias, extra, labels, want_logits: bool = False, xe=None,
 
 
 @_guarded
-def logit_bce_bwd(h, w, dz, gscale, want_gh: bool, want_gextra: bool, xe=None):
+def logit_bce_bwd(h, w, dz, gscale, want_gh: bool, want_gextra: bool, xe=None, defer_params_tag=None):
     """-> (gh [B, H] | None, gw [H], gb [1], gextra [B, 1] | None, gwe [ne] | None) for the upstream scalar gradient
-    ``gscale`` (device); the second linear term's bias gradient equals gb."""
+    ``gscale`` (device); the second linear term's bias gradient equals gb.  ``defer_params_tag``: gw / gb / gwe come back as
+    None, their per-block partials stay in a workspace of that tag for ``logit_bce_bwd_params``."""
     B, H = h.shape
     dev = h.device
+    deferred = defer_params_tag is not None
     gh = torch.empty(B, H, dtype=torch.float32, device=dev) if want_gh else None
-    gw = torch.empty(H, dtype=torch.float32, device=dev)
-    gb = torch.empty(1, dtype=torch.float32, device=dev)
+    gw = None if deferred else torch.empty(H, dtype=torch.float32, device=dev)
+    gb = None if deferred else torch.empty(1, dtype=torch.float32, device=dev)
     gextra = torch.empty(B, 1, dtype=torch.float32, device=dev) if want_gextra else None
     ne = 0 if xe is None else xe.shape[1]
-    gwe = torch.empty(ne, dtype=torch.float32, device=dev) if xe is not None else None
+    gwe = torch.empty(ne, dtype=torch.float32, device=dev) if (xe is not None and not deferred) else None
     with _timed("head_bwd"):
         _lib.check(_lib.lib().ctr_logit_bce_bwd_ex(h.data_ptr(), h.stride(0), B, H, w.data_ptr(), dz.data_ptr(), gscale.data_ptr(),
-                                                   _lib.ptr(gh), 0 if gh is None else gh.stride(0), gw.data_ptr(), gb.data_ptr(),
+                                                   _lib.ptr(gh), 0 if gh is None else gh.stride(0), _lib.ptr(gw), _lib.ptr(gb),
                                                    _lib.ptr(gextra), 1, _lib.ptr(xe), 0 if xe is None else xe.stride(0), ne,
-                                                   _lib.ptr(gwe), tower_workspace(dev, H).data_ptr(), _stream(h)),
+                                                   _lib.ptr(gwe), tower_workspace(dev, H, defer_params_tag).data_ptr(), _stream(h)),
                    "ctr_logit_bce_bwd_ex")
     return gh, gw, gb, gextra, gwe
+
+
+@_guarded
+def logit_bce_bwd_params(h: torch.Tensor, gscale, ne: int, tag):
+    """(gw [H], gb [1], gwe [ne] | None) of the ``logit_bce_bwd(h, ..., defer_params_tag=tag)`` call that ran last on
+    (device, H, tag); launched on the CURRENT stream, which the caller has ordered after that call."""
+    B, H = h.shape
+    device = h.device
+    gw = torch.empty(H, dtype=torch.float32, device=device)
+    gb = torch.empty(1, dtype=torch.float32, device=device)
+    gwe = torch.empty(ne, dtype=torch.float32, device=device) if ne else None
+    with _timed("head_bwd_params"):
+        _lib.check(_lib.lib().ctr_logit_bce_bwd_finalize(B, H, gscale.data_ptr(), gw.data_ptr(), gb.data_ptr(), ne, _lib.ptr(gwe),
+                                                         tower_workspace(device, H, tag).data_ptr(), _stream(gw)),
+                   "ctr_logit_bce_bwd_finalize")
+    return gw, gb, gwe
 
 
 @_guarded

@@ -442,6 +442,8 @@ class HybridShardedTables(nn.Module):
             with torch.cuda.stream(side):
                 call = ops.make_group(self._rep_bwd_specs(ids_list), B, gbuf, self._stride, extra=ge, fm_sum=fm_sum, fm=self.fm)
                 ops.emb_bwd_apply(call, self._rep_ws, ops.make_opt("grad_out"))
+                from ..nn.tower import wait_deferred
+                wait_deferred(dev)              # the tower's weight gradients (second stream) ride in this all-reduce
                 self.transport.all_reduce(self._rep_grad)
                 R = max(self.R, 4)
                 st = self.opt_state
