@@ -322,6 +322,8 @@ def kernel_roofline(cfg, model, resident, B, dev, iters=12):
     D, F = cfg["dim"], len(names)
     flush = torch.empty(1 << 30, dtype=torch.uint8, device=dev)   # > L2; its fill also hides the host launch latency
     peak, peak_src = measured_peak_hbm()
+    from torchctr_b200.nn import embedding as _emb
+    blocked = bool(_emb.BLOCKED_GRAD and cfg["model"] in ("deepfm", "dnn") and not cfg["seq"] and D in (16, 32, 64))
     acc = {"emb_pool_fwd": 0.0, "emb_bwd_plan": 0.0, "emb_bwd_apply": 0.0}
     uniq_total = slots = valid = 0
     for it in range(iters + 2):
@@ -338,7 +340,9 @@ def kernel_roofline(cfg, model, resident, B, dev, iters=12):
                  for t, tw, n, c in zip(tables, twins or tables, names, cols)]
         fwd = ops.make_group(specs, B, out, stride, dense=feats["dense_features"], dense_col=dense_col, zero_from=width,
                              extra=extra, fm_sum=fm_sum, fm=fused)
-        bwd = ops.make_group(specs, B, gout, stride, extra=gextra, fm_sum=fm_sum, fm=fused)
+        # the layout the step hands dL/dx to the update in: column-blocked (feature by feature) when the tower's first block
+        # writes it that way (nn.embedding.BlockedGrad: DNN / DeepFM over single-id tables of one width), else row-major
+        bwd = ops.make_group(specs, B, gout, stride, extra=gextra, fm_sum=fm_sum, fm=fused, grad_blocked=blocked)
         ws = torch.empty(ops.emb_bwd_workspace_bytes(bwd) + 256, dtype=torch.uint8, device=dev)
         opt = ops.make_opt("adagrad", lr=LR, eps=1e-10)
         for name, fn in (("emb_pool_fwd", lambda: ops.emb_pool_fwd(fwd)), ("emb_bwd_plan", lambda: ops.emb_bwd_plan(bwd, ws, runs=False)),
@@ -381,7 +385,8 @@ def kernel_roofline(cfg, model, resident, B, dev, iters=12):
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": k["algorithmic_bytes"],
                 "ms_per_launch": k["ms_per_launch"], "unique_rows_per_launch": U,
                 "combined_lookup_plan_update": kern["lookup+plan+update"],
-                "timing": f"CUDA events around each launch on the launching stream, 1 GiB L2 flush before each, {iters} launches"}
+                "timing": f"CUDA events around each launch on the launching stream, 1 GiB L2 flush before each, {iters} launches",
+                "gradient_layout": "column-blocked (one [B, D] block per table)" if blocked else "row-major [B, stride]"}
     return kern, roofline, dom
 
 

@@ -130,7 +130,12 @@ typedef struct ctr_group {
     float *extra;            /* [B]                                                          */
     float *fm_sum;           /* [B, D], needed when fm != 0                                  */
     int32_t fm;
-    int32_t reserved;
+    /* backward only (ctr_emb_bwd_apply): `out` holds the gradient COLUMN-BLOCKED instead of row-major -- the columns
+     * [out_col, out_col + D) of feature i are the contiguous matrix out + out_col * B, f32 [B, D] -- which is what
+     * ctr_linear_fwd_blocked(block_cols = D, block_stride = B * D) writes.  A table's gradient slices are then one dense
+     * 4 D B-byte block that stays in L2 while its rows are swept, instead of D-float pieces strided over [B, out_stride].
+     * Single-id, sum-pooled features of one width (D % 4 == 0), out_col multiples of D. */
+    int32_t grad_blocked;
 } ctr_group_t;
 
 /* Per-step scalars of the row update as the kernels consume them (fp32). */
@@ -270,6 +275,12 @@ int ctr_cross_combine_bwd(const float *x0, const float *u, const float *bias, co
  * layers of torchctr/models/dnn.py:35-46 and the x.W^T of the DCN-v2 cross layer. */
 int ctr_linear_fwd(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias, float *C,
                    int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t act, void *stream);
+/* the same with C stored column-blocked: columns [j * block_cols, (j + 1) * block_cols) are the contiguous matrix
+ * C + j * block_stride, f32 [M, block_cols] row-major (block_cols a multiple of 4 that divides N; M > 128).  Used for the
+ * input gradient of the tower's first Linear (autograd of torchctr/models/dnn.py:68), which the embedding update consumes
+ * feature by feature (ctr_group_t.grad_blocked). */
+int ctr_linear_fwd_blocked(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias, float *C,
+                           int32_t block_cols, int64_t block_stride, int32_t M, int32_t N, int32_t K, int32_t act, void *stream);
 
 /* The same GEMM (no activation) that also leaves, per block of 32 output rows, the column sums of C and of C^2 in
  * stats f32 [ctr_linear_stats_blocks(M)][2][N]: the batch statistics of the BatchNorm1d that follows the Linear in

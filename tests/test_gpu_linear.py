@@ -75,3 +75,21 @@ def test_wgrad_matches_fp32_matmul(B, N, K):
     xp[:, :K] = x
     got2 = ops.linear_wgrad(gz, xp[:, :K])
     assert torch.equal(got, got2)
+
+
+@pytest.mark.parametrize("M,N,K,D", [(4096, 416, 256, 16), (1000, 128, 64, 32), (300, 192, 40, 64), (513, 64, 128, 16)])
+def test_linear_column_blocked_output_equals_row_major(M, N, K, D):
+    """ctr_linear_fwd_blocked: the same numbers as ctr_linear_fwd, columns [j D, (j + 1) D) stored as their own contiguous
+    [M, D] matrix -- the layout the embedding update reads dL/d(pooled output) in (ctr_group_t.grad_blocked)."""
+    from torchctr_b200 import ops
+    gen = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=gen).cuda()
+    w = torch.randn(N, K, generator=gen).cuda()
+    ref = ops.linear_fwd(a, w)
+    buf = torch.full((M * N + 64,), float("nan"), device="cuda")
+    ops.linear_fwd(a, w, out=buf, out_block=D)
+    got = buf[:M * N].view(N // D, M, D).permute(1, 0, 2).reshape(M, N)
+    assert torch.equal(got, ref)
+    assert torch.isnan(buf[M * N:]).all()
+    with pytest.raises(ValueError):
+        ops.linear_fwd(a[:100], w, out=buf, out_block=D)          # needs M > 128 (the CTA-pair kernel)

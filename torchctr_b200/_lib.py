@@ -50,7 +50,7 @@ class Group(C.Structure):
         ("dense", C.c_void_p), ("dense_width", C.c_int32), ("dense_col", C.c_int32),
         ("zero_from", C.c_int32),
         ("status", C.c_void_p),
-        ("extra", C.c_void_p), ("fm_sum", C.c_void_p), ("fm", C.c_int32), ("reserved", C.c_int32),
+        ("extra", C.c_void_p), ("fm_sum", C.c_void_p), ("fm", C.c_int32), ("grad_blocked", C.c_int32),
     ]
 
 
@@ -109,6 +109,8 @@ _SIGNATURES = {
     "ctr_linear_stats_blocks": (C.c_int32, [C.c_int32]),
     "ctr_linear_fwd_stats": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "ctr_bn_stats_from_partials": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P]),
+    "ctr_linear_fwd_blocked": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, _P, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32, _P]),
     "ctr_split_tf32": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "ctr_route_workspace_bytes": (C.c_int64, [C.POINTER(Group), C.c_int32]),
     "ctr_route_build": (C.c_int, [C.POINTER(Group), C.c_int32, _P, _P, _P, _P, _P, C.c_int64, _P]),

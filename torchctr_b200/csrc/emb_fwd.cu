@@ -394,6 +394,7 @@ static int launch_pool_fwd(const DevGroup &dg, void *stream);
 
 extern "C" int ctr_emb_pool_fwd(const ctr_group_t *group, void *stream) {
     static thread_local DevGroup dg;
+    CTR_REQUIRE(group == nullptr || !group->grad_blocked, "grad_blocked describes a gradient layout: backward (ctr_emb_bwd_apply) only");
     int rc = lower_group(group, &dg, /*need_tables=*/true, /*need_out=*/true);
     if (rc != CTR_OK) return rc;
     return launch_pool_fwd(dg, stream);
@@ -402,6 +403,7 @@ extern "C" int ctr_emb_pool_fwd(const ctr_group_t *group, void *stream) {
 extern "C" int ctr_emb_pool_fwd_sharded(const ctr_group_t *group, const ctr_shard_t *shard, const float *const *tables,
                                         void *stream) {
     static thread_local DevGroup dg;
+    CTR_REQUIRE(group == nullptr || !group->grad_blocked, "grad_blocked describes a gradient layout: backward (ctr_emb_bwd_apply) only");
     int rc = lower_group(group, &dg, /*need_tables=*/false, /*need_out=*/true);
     if (rc != CTR_OK) return rc;
     CTR_REQUIRE(tables != nullptr, "tables is null");
@@ -413,6 +415,7 @@ extern "C" int ctr_emb_pool_fwd_sharded(const ctr_group_t *group, const ctr_shar
 extern "C" int ctr_emb_pool_fwd_sharded_ex(const ctr_group_t *group, const ctr_shard_t *shard, const float *const *tables,
                                            const float *const *twin_tables, void *stream) {
     static thread_local DevGroup dg;
+    CTR_REQUIRE(group == nullptr || !group->grad_blocked, "grad_blocked describes a gradient layout: backward (ctr_emb_bwd_apply) only");
     int rc = lower_group(group, &dg, /*need_tables=*/false, /*need_out=*/true);
     if (rc != CTR_OK) return rc;
     CTR_REQUIRE(tables != nullptr, "tables is null");

@@ -100,6 +100,8 @@ struct GemmArgs {
     int64_t lda;
     float *stats;        // optional (pair kernel): per 32-row block column sums of C and of C^2, [blocks][2][N] -- the batch
                          // statistics of the BatchNorm that follows the Linear come out of the GEMM epilogue
+    int block_cols;      // > 0 (pair kernel): C is stored column-BLOCKED -- columns [j * block_cols, (j + 1) * block_cols) are the
+    int64_t block_stride;//     contiguous matrix C + j * block_stride, [M, block_cols] row-major (ctr_linear_fwd_blocked)
 };
 
 // pull a contiguous global range towards L2 (no data comes back to the SM): 16-byte aligned, multiple of 16 bytes
@@ -475,7 +477,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
                     const float4 o = stage[r * 8 + (slot ^ (r & 7))];
                     const int grow = m0 + q * 32 + r, gcol = col + 4 * slot;
                     if (grow < g.M && gcol < g.N) {
-                        float *dst = g.C + (int64_t)grow * g.ldc + gcol;
+                        // (blocked: block_cols is a multiple of 4 that divides N, so a float4 never straddles two blocks)
+                        float *dst = g.block_cols > 0
+                                         ? g.C + (int64_t)(gcol / g.block_cols) * g.block_stride + (int64_t)grow * g.block_cols + gcol % g.block_cols
+                                         : g.C + (int64_t)grow * g.ldc + gcol;
                         if (vec_ok && gcol + 4 <= g.N) {
                             *reinterpret_cast<float4 *>(dst) = o;
                         } else {
@@ -769,7 +774,23 @@ static void wgrad_plan(int B, int N, int K, int *tiles_m, int *tiles_n, int *spl
 using namespace ctr;
 
 static int linear_fwd_impl(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias, float *C, int64_t ldc,
-                           int32_t M, int32_t N, int32_t K, int32_t act, float *stats, void *stream);
+                           int32_t M, int32_t N, int32_t K, int32_t act, float *stats, void *stream, int32_t block_cols = 0,
+                           int64_t block_stride = 0);
+
+// C = act(A W^T + bias) stored column-blocked: columns [j * block_cols, (j + 1) * block_cols) form the contiguous matrix
+// C + j * block_stride, [M, block_cols] row-major.  What the embedding update wants dL/d(pooled output) in: feature j's
+// gradient slices are then a dense [B, D] block (L2-sized) instead of 64-byte pieces strided over a [B, F * D] matrix.
+extern "C" int ctr_linear_fwd_blocked(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias, float *C,
+                                      int32_t block_cols, int64_t block_stride, int32_t M, int32_t N, int32_t K, int32_t act,
+                                      void *stream) {
+    CTR_REQUIRE(block_cols >= 4 && block_cols % 4 == 0 && N % block_cols == 0, "block_cols=%d must be a multiple of 4 that divides N=%d",
+                block_cols, N);
+    CTR_REQUIRE(block_stride >= (int64_t)M * block_cols && block_stride % 4 == 0, "block_stride=%lld must be >= M * block_cols and a multiple of 4",
+                (long long)block_stride);
+    CTR_REQUIRE(M > kBM, "the column-blocked output needs M > %d (the CTA-pair kernel)", kBM);
+    CTR_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15u) == 0, "C must be 16-byte aligned");
+    return linear_fwd_impl(A, lda, W, ldw, bias, C, N, M, N, K, act, nullptr, stream, block_cols, block_stride);
+}
 
 extern "C" int ctr_linear_fwd(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias, float *C,
                               int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t act, void *stream) {
@@ -790,7 +811,8 @@ extern "C" int ctr_linear_fwd_stats(const float *A, int64_t lda, const float *W,
 }
 
 static int linear_fwd_impl(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias, float *C, int64_t ldc,
-                           int32_t M, int32_t N, int32_t K, int32_t act, float *stats, void *stream) {
+                           int32_t M, int32_t N, int32_t K, int32_t act, float *stats, void *stream, int32_t block_cols,
+                           int64_t block_stride) {
     CTR_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad GEMM shape M=%d N=%d K=%d", M, N, K);
     if (M == 0) return CTR_OK;
     CTR_REQUIRE(A != nullptr && W != nullptr && C != nullptr, "null pointer");
@@ -802,13 +824,13 @@ static int linear_fwd_impl(const float *A, int64_t lda, const float *W, int64_t 
     // widest tile the output needs: fewer passes over A (one per n tile)
     const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
     static const int pair_env = getenv("CTR_GEMM_2CTA") ? atoi(getenv("CTR_GEMM_2CTA")) : 1;
-    const bool pair = (pair_env != 0 || stats != nullptr) && M > kBM;   // CTA pairs (256-row tiles) unless there is a single 128-row tile
+    const bool pair = (pair_env != 0 || stats != nullptr || block_cols > 0) && M > kBM;   // CTA pairs (256-row tiles) unless there is a single 128-row tile
     CUtensorMap ma, mb;
     int rc = make_map(&ma, A, M, K, lda, kBM);
     if (rc != CTR_OK) return rc;
     rc = make_map(&mb, W, N, K, ldw, pair ? bn / 2 : bn);
     if (rc != CTR_OK) return rc;
-    GemmArgs g{C, bias, ldc, M, N, K, act, 0, 0, A, lda, stats};
+    GemmArgs g{C, bias, ldc, M, N, K, act, 0, 0, A, lda, stats, block_cols, block_stride};
     if (pair) {
         if (bn == 256) return launch_linear_pair<256>(ma, mb, g, (cudaStream_t)stream);
         if (bn == 128) return launch_linear_pair<128>(ma, mb, g, (cudaStream_t)stream);

@@ -34,7 +34,7 @@ int lower_group(const ctr_group_t *g, DevGroup *out, bool need_tables, bool need
     out->num_features = g->num_features;
     out->B = g->B;
     out->out = g->out;
-    out->out_stride = g->out_stride;
+    out->out_stride = (g->grad_blocked && g->num_features > 0) ? g->features[0].D : g->out_stride;
     out->dense = g->dense;
     out->dense_width = g->dense_width;
     out->dense_col = g->dense_col;
@@ -63,6 +63,16 @@ int lower_group(const ctr_group_t *g, DevGroup *out, bool need_tables, bool need
         CTR_REQUIRE(s.out_col >= 0 && s.out_col + (int64_t)s.D <= g->out_stride,
                     "feature %d: columns [%d, %d) outside out_stride=%lld", i, s.out_col, s.out_col + s.D,
                     (long long)g->out_stride);
+        if (g->grad_blocked) {
+            // backward only: the columns of feature i are their own contiguous [B, D] matrix at out + out_col * B (what
+            // ctr_linear_fwd_blocked writes with block_cols = D, block_stride = B * D): lowered to row pitch D and a
+            // per-feature offset, which is all the sweep kernels address the gradient by
+            CTR_REQUIRE(s.L == 1 && s.D % 4 == 0 && s.D == g->features[0].D && s.out_col % s.D == 0 && s.id_weight == nullptr &&
+                            s.pooling == CTR_POOL_SUM,
+                        "feature %d: grad_blocked needs single-id, sum-pooled features of one width D %% 4 == 0 at columns that are "
+                        "multiples of D", i);
+            CTR_REQUIRE((int64_t)s.out_col * g->B + (int64_t)g->B * s.D < (1ll << 31), "feature %d: blocked gradient offset does not fit 31 bits", i);
+        }
         d.ids = s.ids;
         d.id_weight = s.id_weight;
         d.table = s.table;
@@ -72,7 +82,7 @@ int lower_group(const ctr_group_t *g, DevGroup *out, bool need_tables, bool need
         d.num_rows = (uint32_t)s.num_rows;
         d.L = s.L;
         d.D = s.D;
-        d.out_col = s.out_col;
+        d.out_col = g->grad_blocked ? (int32_t)((int64_t)s.out_col * g->B) : s.out_col;
         d.pooling = s.pooling;
         d.index_kind = s.index_kind;
         d.hash_seed = s.hash_seed;
@@ -99,7 +109,7 @@ int lower_group(const ctr_group_t *g, DevGroup *out, bool need_tables, bool need
                     "feature %d: mean pooling needs bag_scale [B]", i);
         d.vec = (s.D % 4 == 0) ? 4 : 1;
         d.G = pow2_ceil(s.D / d.vec);
-        d.aligned = (d.vec == 4 && s.out_col % 4 == 0 && g->out_stride % 4 == 0 &&
+        d.aligned = (d.vec == 4 && s.out_col % 4 == 0 && out->out_stride % 4 == 0 &&
                      (reinterpret_cast<uintptr_t>(g->out) & 15u) == 0)
                         ? 1
                         : 0;

@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ..nn.embedding import EmbeddingTable, PlanLink, PooledLookupGroup
+from ..nn.embedding import EmbeddingTable, PlanLink, PooledLookupGroup, take_blocked_offer
 from ..nn.linear import linear_tc
 from ..nn.head import head_eligible, logit_bce
 from ..nn.tower import block_is_fusable, tower_block
@@ -214,9 +214,11 @@ class CTRModelBase(nn.Module):
             return linear_tc(x, weight, bias)
         return F.linear(x, weight, bias)
 
-    def _run_tower(self, x: torch.Tensor, stop_before_last: bool = False) -> torch.Tensor:
+    def _run_tower(self, x: torch.Tensor, stop_before_last: bool = False, blocked_ok: bool = False) -> torch.Tensor:
         """The tower of dnn.py:35-46 on the lookup output.  ``stop_before_last``: return the input of the final
-        ``Linear(., 1)`` instead of the logits (the fused logit + loss head of ``training_step`` takes it from there)."""
+        ``Linear(., 1)`` instead of the logits (the fused logit + loss head of ``training_step`` takes it from there).
+        ``blocked_ok``: the caller states that ``x`` is the fused lookup's output and that NOTHING but this tower consumes it, so
+        the first block may hand dL/dx back column-blocked (``nn.embedding.BlockedGrad``)."""
         layers = list(self.tower)
         if stop_before_last:
             layers = layers[:-1]
@@ -228,8 +230,11 @@ class CTRModelBase(nn.Module):
                 lin = layers[i]           # (first layer: the 4-float-padded lookup output; the block pads the weight itself)
                 # sharded tables: let the first block write dL/dx straight into the peer-visible gradient matrix
                 provider = getattr(self._sharded, "grad_buffer_provider", None) if block == 0 else None
-                h = tower_block(h, lin, layers[i + 1], layers[i + 3], seed, block,
-                                gx_provider=provider(0) if provider is not None else None)
+                gx_provider = provider(0) if provider is not None else None
+                if block == 0 and self._sharded is None:
+                    offer = take_blocked_offer(x)          # (always taken, so that a stale offer never outlives its step)
+                    gx_provider = offer if blocked_ok else None
+                h = tower_block(h, lin, layers[i + 1], layers[i + 3], seed, block, gx_provider=gx_provider)
                 i += 4
                 block += 1
             if i > 0:

@@ -39,6 +39,7 @@ class DeepFM(CTRModelBase):
         self._grow_vocabularies(input_feats)
         dense = self.dense_block(input_feats)
         twins = None
+        self._x_tower_only = False
         if self._sharded is None:                             # (sharded: the tables live in the shards, not in the ModuleDicts)
             twins = [self.linear_embeddings[n] for n in self._names]
             if self.training and torch.is_grad_enabled():
@@ -54,6 +55,7 @@ class DeepFM(CTRModelBase):
             link = PlanLink() if self.training else None
             x, extra = self._lookup(input_feats, dense, self.training, link, twins=twins, fm=True)
             extra = extra.unsqueeze(1)
+            self._x_tower_only = True                         # the FM term came out of the lookup: only the tower reads x
         else:
             x, first = self._lookup_all(input_feats, dense)   # [B, pad4(F*D + Nd)], [B, pad4(F)]; one backward sort
             nf = len(self._names)
@@ -70,9 +72,10 @@ class DeepFM(CTRModelBase):
 
     def forward(self, input_feats):
         x, extra = self._parts(input_feats)
-        return extra + self._run_tower(x)
+        return extra + self._run_tower(x, blocked_ok=self._x_tower_only)
 
     def hidden_and_extra(self, input_feats):
         """(h, extra, (dense block, its Linear) | None): the third item is the Linear(dense) term left to the head kernels"""
         x, extra, xe = self._parts(input_feats, defer_dense_linear=True)
-        return self._run_tower(x, stop_before_last=True), extra, (None if xe is None else (xe, self.linear_dense))
+        return (self._run_tower(x, stop_before_last=True, blocked_ok=self._x_tower_only), extra,
+                (None if xe is None else (xe, self.linear_dense)))

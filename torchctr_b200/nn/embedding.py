@@ -292,11 +292,54 @@ def _side_stream(device) -> torch.cuda.Stream:
     return st
 
 
+# Off by default: measured on cfg2 (B200), the sweep takes 163.8 us with the blocked handover and 164.7 us with the row-major
+# one -- its long-scoreboard stalls are dependent-latency chains (gather -> reduce -> row read-modify-write), not DRAM
+# efficiency of the gathers, so where the slices come from does not matter.  Kept as a tested option (CTR_BLOCKED_GRAD=1).
+BLOCKED_GRAD = os.environ.get("CTR_BLOCKED_GRAD", "0") == "1"
+
+
+class BlockedGrad:
+    """dL/d(pooled output) handed over COLUMN-BLOCKED (``ctr_group_t.grad_blocked``): feature j's gradient slices are the
+    contiguous matrix ``buffer[j * B * D:]`` viewed [B, D] instead of D-float pieces strided over [B, stride].  The sweep then
+    gathers a table's slices from one dense 4 D B-byte block that sits in L2 while that table's rows are swept, instead of
+    random 64-byte DRAM reads over the whole gradient matrix.
+
+    Protocol: the lookup offers it (``take_blocked_offer``) to the ONE consumer of its output, the tower's first block, as
+    that block's ``gx_provider``; the block's input-gradient GEMM writes the blocked layout (``ctr_linear_fwd_blocked``), sets
+    ``marked`` and returns ``buffer`` viewed [B, stride] as the gradient autograd carries back; the lookup's backward checks
+    that what arrives IS that buffer and reads it blocked.  Anything else that touched the gradient on the way would have read
+    a scrambled matrix, hence the check -- and the opt-in by the model (``CTRModelBase._run_tower(blocked_ok=True)``)."""
+
+    def __init__(self, B: int, stride: int, cols: int, block: int, device):
+        self.B, self.stride, self.cols, self.block, self.device = B, stride, cols, block, device
+        self.buffer = None
+        self.marked = False
+
+    def __call__(self):
+        if self.buffer is None:
+            self.buffer = torch.empty(self.B * self.stride, dtype=torch.float32, device=self.device)
+        return self
+
+
+blocked_backwards = 0      # how many lookups read their gradient column-blocked (tests, diagnostics)
+_blocked_offer = None      # (data_ptr of the lookup output, BlockedGrad) of the most recent eligible lookup
+
+
+def take_blocked_offer(x: torch.Tensor):
+    """The ``BlockedGrad`` of the lookup that produced ``x`` (only if ``x`` IS that lookup's output), or None."""
+    global _blocked_offer
+    offer, _blocked_offer = _blocked_offer, None
+    if offer is not None and offer[0] == x.data_ptr() and tuple(x.shape) == (offer[1].B, offer[1].stride):
+        return offer[1]
+    return None
+
+
 class _PooledLookupFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, call, dense, *weights):
         ctx.call = call
         ctx.has_dense = dense is not None
+        call.dense_needs_grad = bool(ctx.needs_input_grad[1])
         return call.run_forward(dense, weights)
 
     @staticmethod
@@ -316,6 +359,7 @@ class _PooledLookupExtraFn(torch.autograd.Function):
     def forward(ctx, call, dense, *weights):
         ctx.call = call
         ctx.has_dense = dense is not None
+        call.dense_needs_grad = bool(ctx.needs_input_grad[1])
         out = call.run_forward(dense, weights)
         # hand `extra` out WITHOUT keeping it on the call: an output of this node that the node's own ctx also held would be
         # a reference cycle, and the autograd graph (AccumulateGrad nodes bound to the stream of that step included) would
@@ -359,6 +403,8 @@ class _LookupCall:
         self.bag_scales = None
         self.status = None
         self.grad_enabled = torch.is_grad_enabled()   # read outside the autograd Function (inside, grad mode is off)
+        self.dense_needs_grad = False
+        self.blocked = None             # BlockedGrad offered to the consumer of the output (see take_blocked_offer)
 
     def _specs(self, tables_data, with_state, twin_data=None):
         specs = []
@@ -378,6 +424,12 @@ class _LookupCall:
                 state1=getattr(mod, "opt_state1", None) if with_state else None,
                 bag_scale=self.bag_scales[i]))
         return specs
+
+    def _single_id_one_width(self) -> bool:
+        """the group the compile-time-layout sweep takes: single-id bags, one width of 16 / 32 / 64, sum pooling, no weights"""
+        D = self.entries[0][0].embedding_dim
+        return D in (16, 32, 64) and all(m.embedding_dim == D and m.pooling == "sum" and wgt is None and ids.shape[1] == 1
+                                         for m, ids, wgt in self.entries)
 
     def run_forward(self, dense, weights):
         with torch.cuda.device(weights[0].device):       # the model may live on a device that is not the current one
@@ -429,6 +481,13 @@ class _LookupCall:
         if early is not None and PLAN_START == "before":
             early()
         ops.emb_pool_fwd(call)
+        global _blocked_offer
+        _blocked_offer = None
+        if (BLOCKED_GRAD and self.training and self.grad_enabled and self.binding is not None and not self.dense_needs_grad
+                and B > 128 and self._single_id_one_width()):
+            D = self.entries[0][0].embedding_dim
+            self.blocked = BlockedGrad(B, self.stride, len(self.entries) * D, D, dev)
+            _blocked_offer = (out.data_ptr(), self.blocked)
         if early is not None and PLAN_START == "head":
             link.late = early
             _late_starts.append(link)
@@ -453,8 +512,15 @@ class _LookupCall:
                 m._ensure_state(self.binding.kind, self.binding.initial_accumulator_value(), self.binding.optimizer)
         tables = [m.weight.data for m in mods]
         twin_data = [t.weight.data for t in self.twins] if self.twins is not None else None
+        blocked = self.blocked is not None and self.blocked.marked
+        if blocked:
+            global blocked_backwards
+            blocked_backwards += 1
+        if blocked and (not fused or grad_out.data_ptr() != self.blocked.buffer.data_ptr()):
+            raise RuntimeError("the tower wrote dL/dx column-blocked (BlockedGrad) but a different tensor came back to the lookup: "
+                               "something else consumed the lookup's output; set CTR_BLOCKED_GRAD=0")
         call = ops.make_group(self._specs(tables, fused, twin_data), self.B, grad_out, grad_out.shape[1],
-                              extra=grad_extra, fm_sum=self.fm_sum, fm=self.fm)
+                              extra=grad_extra, fm_sum=self.fm_sum, fm=self.fm, grad_blocked=blocked)
         link = self.plan_link
         if link is None:
             ws = _Workspace.get(dev, ops.emb_bwd_workspace_bytes(call))

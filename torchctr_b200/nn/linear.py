@@ -61,11 +61,12 @@ def wgrad_eligible(gy: torch.Tensor, x: torch.Tensor, precision: str | None = No
     return ok(gy) and ok(x) and gy.shape[0] == x.shape[0] and gy.shape[0] >= 1
 
 
-def gemm_nt(a: torch.Tensor, w: torch.Tensor, bias=None, act: int = 0, out=None, precision: str = "tf32") -> torch.Tensor:
-    """``act(a @ w.T + bias)`` on tcgen05: a [M, K], w [N, K]."""
+def gemm_nt(a: torch.Tensor, w: torch.Tensor, bias=None, act: int = 0, out=None, precision: str = "tf32",
+            out_block: int = 0) -> torch.Tensor:
+    """``act(a @ w.T + bias)`` on tcgen05: a [M, K], w [N, K] (``out_block``: column-blocked result, ``ops.linear_fwd``)."""
     if precision == "tf32x3":
-        return ops.linear_fwd(ops.split_tf32(a, 1, 0), ops.split_tf32(w, 1, 1), bias, act, out=out)
-    return ops.linear_fwd(a, w, bias, act, out=out)
+        return ops.linear_fwd(ops.split_tf32(a, 1, 0), ops.split_tf32(w, 1, 1), bias, act, out=out, out_block=out_block)
+    return ops.linear_fwd(a, w, bias, act, out=out, out_block=out_block)
 
 
 def gemm_nt_bn_stats(a, w, bias, bn, precision: str = "tf32"):

@@ -25,6 +25,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from .embedding import BlockedGrad
 from .linear import gemm_nt, gemm_nt_bn_stats, gemm_wgrad, matmul_precision, tc_eligible, wgrad_eligible
 
 
@@ -154,6 +155,11 @@ class _TowerBlockFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             # gx_provider: a buffer the caller wants dL/dx in (the peer-visible gradient matrix of the sharded tables)
             out = ctx.gx_provider() if (tc and ctx.gx_provider is not None) else None
+            blocked = out if isinstance(out, BlockedGrad) else None
+            if blocked is not None:
+                out = None
+                if (blocked.B, blocked.stride) != tuple(x.shape) or blocked.cols > x.shape[1] or blocked.cols % blocked.block:
+                    blocked = None
             if out is not None and tuple(out.shape) != tuple(x.shape):
                 out = None
             if tc:
@@ -162,7 +168,14 @@ class _TowerBlockFn(torch.autograd.Function):
                     torch.cuda.current_stream(dev).wait_event(ctx.wt_ready)
                 else:
                     wt = w.t().contiguous()
-                gx = gemm_nt(gz, wt, out=out, precision=precision)
+                if blocked is not None:
+                    # the embedding update reads dL/dx feature by feature: write it column-blocked (and only the table columns:
+                    # the dense block and the padding behind them need no gradient)
+                    gemm_nt(gz, wt[:blocked.cols], out=blocked.buffer, precision=precision, out_block=blocked.block)
+                    blocked.marked = True
+                    gx = blocked.buffer.view(blocked.B, blocked.stride)
+                else:
+                    gx = gemm_nt(gz, wt, out=out, precision=precision)
             else:
                 gx = gz @ w
         want_gw = ctx.needs_input_grad[1]

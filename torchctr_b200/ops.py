@@ -76,10 +76,12 @@ class GroupCall:
 
 def make_group(features, B: int, out: torch.Tensor | None, out_stride: int, dense: torch.Tensor | None = None,
                dense_col: int = 0, zero_from: int = -1, status: torch.Tensor | None = None,
-               extra: torch.Tensor | None = None, fm_sum: torch.Tensor | None = None, fm: bool = False) -> GroupCall:
+               extra: torch.Tensor | None = None, fm_sum: torch.Tensor | None = None, fm: bool = False,
+               grad_blocked: bool = False) -> GroupCall:
     """``extra`` f32 [B] (+ ``fm_sum`` f32 [B, D] when ``fm``): the fused per-bag scalar of ``ctr_group_t`` -- sum of the
     features' twin tables plus, with ``fm``, the FM second-order term; forward writes them, backward reads ``extra`` as
-    dL/d extra."""
+    dL/d extra.  ``grad_blocked`` (backward): ``out`` holds the gradient column-blocked, feature by feature
+    (``ctr_group_t.grad_blocked``, written by ``linear_fwd(..., out_block=D)``)."""
     n = len(features)
     if n > _lib.MAX_FEATURES:
         raise ValueError(f"a launch group holds at most {_lib.MAX_FEATURES} features, got {n}")
@@ -136,6 +138,7 @@ def make_group(features, B: int, out: torch.Tensor | None, out_stride: int, dens
     g.dense_col = dense_col
     g.zero_from = zero_from
     g.status = _lib.ptr(status)
+    g.grad_blocked = 1 if grad_blocked else 0
     _chk(extra, "extra", torch.float32)
     _chk(fm_sum, "fm_sum", torch.float32)
     if extra is not None and extra.numel() != B:
@@ -536,9 +539,11 @@ def route_grad_gather(call: GroupCall, world: int, workspace: torch.Tensor, n: i
 
 @_guarded
 def linear_fwd(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor | None = None, act: int = 0,
-               out: torch.Tensor | None = None) -> torch.Tensor:
+               out: torch.Tensor | None = None, out_block: int = 0) -> torch.Tensor:
     """``act(A @ W.T + bias)`` on tcgen05 tensor cores (TF32 inputs, fp32 accumulate).  A f32 [M, K] with unit
-    inner stride and a row pitch that is a multiple of 4 floats, W f32 [N, K] likewise."""
+    inner stride and a row pitch that is a multiple of 4 floats, W f32 [N, K] likewise.  ``out_block = D > 0``: the result is
+    stored column-blocked into the flat buffer ``out`` (>= M * N floats): columns [j D, (j + 1) D) are the contiguous matrix
+    ``out[j * M * D:]`` viewed [M, D] (``ctr_linear_fwd_blocked``; needs M > 128)."""
     _lib.require_cuda(A, "A")
     for name, t in (("A", A), ("W", W)):
         if t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
@@ -548,6 +553,14 @@ def linear_fwd(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor | None = Non
     if W.shape[1] != K:
         raise ValueError(f"shape mismatch: A {tuple(A.shape)} vs W {tuple(W.shape)}")
     _chk(bias, "bias", torch.float32)
+    if out_block:
+        if out is None or not out.is_contiguous() or out.numel() < M * N or out.dtype != torch.float32:
+            raise ValueError("out_block needs a contiguous f32 `out` of at least M * N elements")
+        with _timed("linear_fwd"):
+            _lib.check(_lib.lib().ctr_linear_fwd_blocked(A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), _lib.ptr(bias),
+                                                         out.data_ptr(), out_block, M * out_block, M, N, K, act, _stream(A)),
+                       "ctr_linear_fwd_blocked")
+        return out
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=A.device)
     with _timed("linear_fwd"):
