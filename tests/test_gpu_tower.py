@@ -233,3 +233,59 @@ def test_deferred_weight_gradients_equal_the_single_stream_schedule(precision):
     finally:
         tower.defer_weight_grads = old
         set_matmul_precision(None)
+
+
+@pytest.mark.parametrize("model_name", ["DNN", "DeepFM", "DCNv2"])
+def test_first_block_prepared_next_to_the_lookup_is_bit_identical(model_name):
+    """``CTRModelBase._prepare_tower`` issues the first block's dropout-seed snapshot, zero-padded weight and its transpose on the
+    second stream BEFORE the lookup (``nn.tower.prepare_first_block``).  Same values, same kernels downstream: losses and
+    parameters after three steps (dropout on) are bit-identical to the in-line preparation, and the prepared path is the one
+    that ran from the second step on."""
+    import torchctr_b200.models as models
+    from torchctr_b200.nn import tower
+    gen = torch.Generator().manual_seed(9)
+    B, F, D, nd = 1024, 5, 16, 3
+    fc = [{"name": f"c{i}", "type": "sparse", "num_embeddings": 300 + i, "emb_dim": D} for i in range(F)]
+    fc += [{"name": f"d{i}", "type": "dense"} for i in range(nd)]
+    batches = []
+    for _ in range(3):
+        feats = {f"c{i}": torch.randint(0, 300 + i, (B, 1), generator=gen).cuda() for i in range(F)}
+        feats["dense_features"] = torch.randn(B, nd, generator=gen).cuda()
+        batches.append((feats, (torch.rand(B, 1, generator=gen) < 0.25).float().cuda()))
+    old = tower.prepare_early
+    real = tower._TowerBlockFn.forward
+    taken = []
+
+    def spy(ctx, *args):
+        taken.append(args[-1] is not None)           # the ``prepared`` argument
+        return real(ctx, *args)
+    try:
+        tower._TowerBlockFn.forward = staticmethod(spy)
+        results = []
+        for early in (False, True):
+            tower.prepare_early = early
+            taken.clear()
+            torch.manual_seed(3)
+            m = getattr(models, model_name)(fc, [64, 32]).cuda().train()
+            opt = torch.optim.Adagrad(m.dense_parameters(), lr=0.05)
+            m.bind_optimizer(opt, kind="adagrad")
+            losses = []
+            for i, batch in enumerate(batches):
+                opt.zero_grad(set_to_none=True)
+                loss = m.training_step(batch, i)
+                loss.backward()
+                opt.step()
+                losses.append(loss.detach().clone())
+            torch.cuda.synchronize()
+            assert not tower._deferred
+            # two fused blocks per step; the first one is prepared from the second step on (the padding is known by then)
+            assert taken == ([False, False] * 3 if not early else [False, False, True, False, True, False]), taken
+            results.append((losses, {k: v.clone() for k, v in m.state_dict().items()}))
+        (l0, s0), (l1, s1) = results
+        for a, b in zip(l0, l1):
+            assert torch.equal(a, b)
+        for k in s0:
+            assert torch.equal(s0[k], s1[k]), k
+    finally:
+        tower._TowerBlockFn.forward = real
+        tower.prepare_early = old

@@ -12,7 +12,9 @@ import torch.nn.functional as F
 from ..nn.embedding import EmbeddingTable, PlanLink, PooledLookupGroup, take_blocked_offer
 from ..nn.linear import linear_tc
 from ..nn.head import head_eligible, logit_bce
-from ..nn.tower import block_is_fusable, tower_block
+from ..nn import tower as _tower
+from ..nn.linear import matmul_precision
+from ..nn.tower import block_is_fusable, prepare_first_block, tower_block
 from ..nn.vocab import VocabIndex
 
 
@@ -224,7 +226,11 @@ class CTRModelBase(nn.Module):
             layers = layers[:-1]
         if self.training and x.is_cuda and x.dtype == torch.float32:
             # training mode: every [Linear, BatchNorm1d, ReLU, Dropout] block is one fused autograd node
-            seed = self._step_seed(x.device)
+            prepared = self._take_prepared(x, layers)
+            if prepared is not None:
+                seed, prepared = prepared[0], prepared[1:]
+            else:
+                seed = self._step_seed(x.device)
             h, i, block = x, 0, 0
             while i + 3 < len(layers) and block_is_fusable(*layers[i:i + 4]):
                 lin = layers[i]           # (first layer: the 4-float-padded lookup output; the block pads the weight itself)
@@ -234,7 +240,8 @@ class CTRModelBase(nn.Module):
                 if block == 0 and self._sharded is None:
                     offer = take_blocked_offer(x)          # (always taken, so that a stale offer never outlives its step)
                     gx_provider = offer if blocked_ok else None
-                h = tower_block(h, lin, layers[i + 1], layers[i + 3], seed, block, gx_provider=gx_provider)
+                h = tower_block(h, lin, layers[i + 1], layers[i + 3], seed, block, gx_provider=gx_provider,
+                                prepared=prepared if block == 0 else None)
                 i += 4
                 block += 1
             if i > 0:
@@ -248,12 +255,54 @@ class CTRModelBase(nn.Module):
             h = self._linear(h, layer.weight, layer.bias) if isinstance(layer, nn.Linear) else layer(h)
         return h
 
-    def _step_seed(self, device):
-        """Device-resident dropout seed, advanced once per training forward (inside a captured CUDA graph too)."""
+    def _seed_counter(self, device):
         seed = getattr(self, "_drop_seed", None)
         if seed is None or seed.device != device:
             seed = torch.full((1,), torch.initial_seed() & 0x7fffffffffff, dtype=torch.int64, device=device)
             self._drop_seed = seed
+        return seed
+
+    def _prepare_tower(self):
+        """Called by the models BEFORE they issue the lookup of a training forward: the first tower block's small preparatory
+        kernels (dropout seed advance + snapshot, zero-padded weight, its transpose) go to the second stream now, so that they
+        run next to the lookup instead of between it and the first GEMM (``nn.tower.prepare_first_block``).  Needs the padding
+        the first block saw on an earlier step (``_run_tower`` records it); whatever is prepared here is taken -- or, if it does
+        not fit, joined and dropped -- by the next ``_run_tower``."""
+        self._prepared = None
+        pad = getattr(self, "_first_block_pad", None)
+        tower = getattr(self, "tower", None)
+        if (pad is None or tower is None or not self.training or not torch.is_grad_enabled() or not _tower.prepare_early
+                or not _tower.defer_weight_grads or len(tower) < 5 or not block_is_fusable(*list(tower)[:4])):
+            return
+        lin = tower[0]
+        if not lin.weight.is_cuda or lin.weight.dtype != torch.float32:
+            return
+        precision = matmul_precision()
+        with torch.cuda.device(lin.weight.device):
+            made = prepare_first_block(lin, pad, self._seed_counter(lin.weight.device), want_wt=precision == "tf32")
+        self._prepared = (made, pad, precision, lin.weight._version, lin)
+
+    def _take_prepared(self, x, layers):
+        """-> (seed snapshot, padded weight, transpose | None, event) when ``_prepare_tower`` ran for exactly this tower input,
+        else None (anything prepared is joined first, so that no work is left dangling on the second stream)."""
+        entry, self._prepared = getattr(self, "_prepared", None), None
+        lin = layers[0] if layers else None
+        fits = isinstance(lin, nn.Linear) and len(layers) >= 4 and block_is_fusable(*layers[:4])
+        if fits:
+            self._first_block_pad = x.shape[1] - lin.in_features
+        if entry is None:
+            return None
+        made, pad, precision, version, prepared_lin = entry
+        if (fits and prepared_lin is lin and pad == x.shape[1] - lin.in_features and precision == matmul_precision()
+                and version == lin.weight._version and made[1].device == x.device):
+            return made
+        torch.cuda.current_stream(made[1].device).wait_event(made[3])
+        # the counter was advanced by the preparation; the block falls back to a snapshot of its own (one more advance: harmless)
+        return None
+
+    def _step_seed(self, device):
+        """Device-resident dropout seed, advanced once per training forward (inside a captured CUDA graph too)."""
+        seed = self._seed_counter(device)
         seed += 1
         # a snapshot, not the counter itself: backward recomputes the dropout mask from the value ITS forward used, even
         # when another training forward ran in between (two losses summed, fwd-fwd-bwd orders)

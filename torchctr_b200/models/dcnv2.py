@@ -17,6 +17,7 @@ class DCNv2(CTRModelBase):
 
     def _crossed(self, input_feats):
         self._grow_vocabularies(input_feats)
+        self._prepare_tower()
         (x0,) = self._lookup_all(input_feats, self.dense_block(input_feats))
         x = x0
         for layer in self.cross:

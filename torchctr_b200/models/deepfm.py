@@ -37,6 +37,7 @@ class DeepFM(CTRModelBase):
         ``defer_dense_linear``: leave Linear(dense) to the caller when the fused logit head can take it
         (returns (x, extra, dense block | None))."""
         self._grow_vocabularies(input_feats)
+        self._prepare_tower()
         dense = self.dense_block(input_feats)
         twins = None
         self._x_tower_only = False

@@ -11,10 +11,12 @@ class DNN(CTRModelBase):
 
     def forward(self, input_feats):
         self._grow_vocabularies(input_feats)
+        self._prepare_tower()
         (x,) = self._lookup_all(input_feats, self.dense_block(input_feats))          # dnn.py:53-67 in one launch
         return self._run_tower(x, blocked_ok=True)                                    # dnn.py:68 (x feeds the tower only)
 
     def hidden_and_extra(self, input_feats):
         self._grow_vocabularies(input_feats)
+        self._prepare_tower()
         (x,) = self._lookup_all(input_feats, self.dense_block(input_feats))
         return self._run_tower(x, stop_before_last=True, blocked_ok=True), None

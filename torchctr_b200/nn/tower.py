@@ -32,6 +32,7 @@ from .linear import gemm_nt, gemm_nt_bn_stats, gemm_wgrad, matmul_precision, tc_
 _wgrad_streams: dict = {}
 _deferred: dict = {}       # device -> [graph task id, tensors the second stream still reads (kept alive until the join)]
 defer_weight_grads = os.environ.get("CTR_DEFER_WGRAD", "1") != "0"   # module switch (tests compare both schedules)
+prepare_early = os.environ.get("CTR_PREPARE_EARLY", "1") != "0"      # first block's weight / seed preparation next to the lookup
 
 
 def _wgrad_stream(device) -> torch.cuda.Stream:
@@ -103,17 +104,27 @@ def _deliver(param, g):
 
 class _TowerBlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, bn, p_drop, seed_dev, layer_id, precision, gx_provider=None, pad=0):
+    def forward(ctx, x, weight, bias, gamma, beta, bn, p_drop, seed_dev, layer_id, precision, gx_provider=None, pad=0,
+                prepared=None):
         # pad: zero columns appended to the weight here (the first layer reads the 4-float-padded lookup output); the gradient
         # handed back is that of the unpadded parameter
+        # prepared: (padded weight, its transpose or None, event) made by ``prepare_first_block`` on the second stream BEFORE the
+        # lookup was issued -- the small copies then run next to the lookup instead of between it and the first GEMM
         ctx.param = weight
         ctx.bias_param = bias
         ctx.bn_params = (gamma, beta)
         ctx.pad = pad
-        w = torch.nn.functional.pad(weight.detach(), (0, pad)) if pad else weight.contiguous()
-        tc = tc_eligible(x, w, precision)
         ctx.wt = ctx.wt_ready = None
-        if tc and defer_weight_grads and ctx.needs_input_grad[0] and precision == "tf32":
+        if prepared is not None:
+            w, wt, ready = prepared
+            torch.cuda.current_stream(x.device).wait_event(ready)
+            tc = tc_eligible(x, w, precision)
+            if tc and ctx.needs_input_grad[0] and wt is not None:
+                ctx.wt, ctx.wt_ready = wt, ready
+        else:
+            w = torch.nn.functional.pad(weight.detach(), (0, pad)) if pad else weight.contiguous()
+            tc = tc_eligible(x, w, precision)
+        if prepared is None and tc and defer_weight_grads and ctx.needs_input_grad[0] and precision == "tf32":
             # W^T for the input-gradient GEMM of backward, made NOW on the second stream (next to this block's forward)
             # instead of on the critical path of backward
             dev = x.device
@@ -205,7 +216,7 @@ class _TowerBlockFn(torch.autograd.Function):
                     dbeta = _deliver(ctx.bn_params[1], dbeta)
             if not engine_joins:
                 join_deferred(dev)
-        return gx, gw, dbias, dgamma, dbeta, None, None, None, None, None, None, None
+        return gx, gw, dbias, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
 def block_is_fusable(linear, bn, act, drop) -> bool:
@@ -214,14 +225,45 @@ def block_is_fusable(linear, bn, act, drop) -> bool:
             and linear.out_features % 4 == 0 and 4 <= linear.out_features <= 1024)
 
 
+def prepare_first_block(linear: nn.Linear, pad: int, seed_counter: torch.Tensor, want_wt: bool = True):
+    """What the first block's forward needs besides its input, made on the SECOND stream before the lookup is issued: the step's
+    dropout seed (counter advanced, snapshot taken), the zero-padded weight and (TF32 mode) its transpose for the input-gradient
+    GEMM.  In a step captured from one stream these five tiny kernels otherwise sit, one after the other, between the lookup
+    and the first GEMM (~20 us of a 0.8 ms step); forked off before the lookup they run next to it.
+    -> (seed snapshot, padded weight [N, K + pad], transpose [K + pad, N] | None, event recorded on the second stream)."""
+    w0 = linear.weight.detach()
+    dev = w0.device
+    N, K = w0.shape
+    main, side = torch.cuda.current_stream(dev), _wgrad_stream(dev)
+    snap = torch.empty_like(seed_counter)            # allocated on the stream that will read them, written on the second one
+    w = torch.empty(N, K + pad, dtype=w0.dtype, device=dev) if pad else None
+    wt = torch.empty(K + pad, N, dtype=w0.dtype, device=dev) if want_wt else None
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        seed_counter += 1
+        snap.copy_(seed_counter)
+        if pad:
+            w[:, :K].copy_(w0)
+            w[:, K:].zero_()
+        else:
+            w = w0.contiguous()
+        if wt is not None:
+            wt[:K].copy_(w0.t())
+            if pad:
+                wt[K:].zero_()
+        ready = torch.cuda.Event()
+        ready.record(side)
+    return snap, w, wt, ready
+
+
 def tower_block(x, linear: nn.Linear, bn: nn.BatchNorm1d, drop: nn.Dropout, seed_dev, layer_id: int, weight=None,
-                gx_provider=None):
+                gx_provider=None, prepared=None):
     """Training-mode forward of [linear, bn, ReLU, drop] on a CUDA tensor.  When ``x`` is wider than ``linear.in_features`` (the
     first layer reads the 4-float-padded lookup output) the weight is zero-padded inside the node.  ``weight`` overrides
-    ``linear.weight`` as is."""
+    ``linear.weight`` as is.  ``prepared``: (padded weight, transpose | None, event) from ``prepare_first_block``."""
     if weight is not None:
         return _TowerBlockFn.apply(x, weight, linear.bias, bn.weight, bn.bias, bn, float(drop.p), seed_dev, layer_id,
-                                   matmul_precision(), gx_provider, 0)
+                                   matmul_precision(), gx_provider, 0, None)
     pad = x.shape[1] - linear.in_features
     return _TowerBlockFn.apply(x, linear.weight, linear.bias, bn.weight, bn.bias, bn, float(drop.p), seed_dev, layer_id,
-                               matmul_precision(), gx_provider, pad)
+                               matmul_precision(), gx_provider, pad, prepared)
