@@ -331,27 +331,48 @@ __global__ void __launch_bounds__(kTowerThreads)
         const int r0 = blockIdx.x * g.rows_per_block;
         const int r1 = min(r0 + g.rows_per_block, g.B);
         const int iters = (r1 - r0 + g.RL - 1) / g.RL;       // the same trip count for every lane of a row team
-        for (int it = 0; it < iters; ++it) {
-            const int r = r0 + rl + it * g.RL;
-            const bool ok = r < r1;
-            float d = 0.f;
-            if (ok) {
-                const float4 v = ld4(a.h + (size_t)r * a.ldh + 4 * cg);
-                d = v.x * w4.x + v.y * w4.y + v.z * w4.z + v.w * w4.w;
-                // second linear term: the row team's lanes share its ne columns (coalesced), the shuffle sum below adds them up
-                for (int j = cg; j < a.ne; j += g.CG) d = fmaf(__ldg(a.xe + (size_t)r * a.ldxe + j), __ldg(a.we + j), d);
+        // four rows per trip: every load of the four rows (h, the second term's columns, the extra term, the label) is issued
+        // before the first shuffle, so a thread has 4 x 16 bytes in flight instead of one dependent chain per row
+        for (int it = 0; it < iters; it += 4) {
+            float4 v[4];
+            float d[4], ex[4], y[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + rl + (it + u) * g.RL;
+                ok[u] = it + u < iters && r < r1;
+                v[u] = ok[u] ? ld4(a.h + (size_t)r * a.ldh + 4 * cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+                ex[u] = 0.f;
+                y[u] = 0.f;
+                if (ok[u] && cg == 0) {
+                    if (a.extra != nullptr) ex[u] = __ldg(a.extra + (size_t)r * a.extra_stride);
+                    y[u] = __ldg(a.labels + (size_t)r * a.label_stride);
+                }
             }
-            for (int off = 1; off < g.CG; off <<= 1) d += __shfl_xor_sync(kFull, d, off);
-            if (ok && cg == 0) {
-                float z = d + b0;
-                if (a.extra != nullptr) z += __ldg(a.extra + (size_t)r * a.extra_stride);
-                if (a.xe != nullptr && a.be != nullptr) z += __ldg(a.be);
-                const float y = __ldg(a.labels + (size_t)r * a.label_stride);
-                // max(z, 0) - z y + log1p(exp(-|z|)): torch's stable form
-                loss_acc += fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));
-                const float sg = 1.f / (1.f + expf(-z));
-                a.dz[r] = (sg - y) * a.inv_B;
-                if (a.logits != nullptr) a.logits[r] = z;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + rl + (it + u) * g.RL;
+                d[u] = v[u].x * w4.x + v[u].y * w4.y + v[u].z * w4.z + v[u].w * w4.w;
+                // second linear term: the row team's lanes share its ne columns (coalesced), the shuffle sum below adds them up
+                if (ok[u])
+                    for (int j = cg; j < a.ne; j += g.CG) d[u] = fmaf(__ldg(a.xe + (size_t)r * a.ldxe + j), __ldg(a.we + j), d[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                for (int off = 1; off < g.CG; off <<= 1) d[u] += __shfl_xor_sync(kFull, d[u], off);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (ok[u] && cg == 0) {
+                    const int r = r0 + rl + (it + u) * g.RL;
+                    float z = d[u] + b0;
+                    if (a.extra != nullptr) z += ex[u];
+                    if (a.xe != nullptr && a.be != nullptr) z += __ldg(a.be);
+                    // max(z, 0) - z y + log1p(exp(-|z|)): torch's stable form
+                    loss_acc += fmaxf(z, 0.f) - z * y[u] + log1pf(expf(-fabsf(z)));
+                    const float sg = 1.f / (1.f + expf(-z));
+                    a.dz[r] = (sg - y[u]) * a.inv_B;
+                    if (a.logits != nullptr) a.logits[r] = z;
+                }
             }
         }
     }
