@@ -99,14 +99,19 @@ __global__ void __launch_bounds__(kTowerThreads)
 // Finalize kernels: a block of kFinCols x kFinLanes threads owns kFinCols columns; lane j adds the partials of
 // blocks j, j + kFinLanes, ... in double, the lanes are then added in lane order (fixed order: deterministic).
 constexpr int kFinCols = 16, kFinLanes = 64;
+// The finalize kernels ON the critical path (BatchNorm statistics forward, dgamma / dbeta / means backward) own kFinColsFast
+// columns per block instead: 256-thread blocks find a free SM at once while the second stream's weight-gradient kernel or the
+// sort occupies the machine (the 1024-thread ones waited ~9 us for one, CUPTI timeline of round 2), and there are four times
+// as many of them.  Same lanes per column, same order of every sum: bit-identical results.
+constexpr int kFinColsFast = 4;
 
-template <int NQ, int LANES = kFinLanes>
+template <int NQ, int LANES = kFinLanes, int COLS = kFinCols>
 __device__ __forceinline__ bool column_totals(const float *__restrict__ partial, int blocks, int N, double (&tot)[NQ], int *col) {
     static_assert(LANES % 8 == 0, "lanes are folded eight at a time");
-    __shared__ double sh[NQ][LANES][kFinCols];
-    __shared__ double sh2[NQ][LANES / 8][kFinCols];
-    const int c = threadIdx.x % kFinCols, j = threadIdx.x / kFinCols;
-    const int n = blockIdx.x * kFinCols + c;
+    __shared__ double sh[NQ][LANES][COLS];
+    __shared__ double sh2[NQ][LANES / 8][COLS];
+    const int c = threadIdx.x % COLS, j = threadIdx.x / COLS;
+    const int n = blockIdx.x * COLS + c;
     double acc[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
@@ -144,14 +149,14 @@ __device__ __forceinline__ bool column_totals(const float *__restrict__ partial,
 
 // partials -> mean, rstd (+ running statistics, torch.nn.BatchNorm1d semantics).  LANES threads share a column's partials.
 template <int LANES>
-__global__ void __launch_bounds__(kFinCols * LANES)
+__global__ void __launch_bounds__(kFinColsFast * LANES)
     bn_finalize_fwd_kernel(const float *__restrict__ partial, int blocks, int B, int N, float eps, float momentum,
                            float *__restrict__ mean, float *__restrict__ rstd, float *running_mean, float *running_var,
                            long long *num_batches_tracked) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
     double tot[2];
     int n;
-    if (!column_totals<2, LANES>(partial, blocks, N, tot, &n)) return;
+    if (!column_totals<2, LANES, kFinColsFast>(partial, blocks, N, tot, &n)) return;
     const double s = tot[0], ss = tot[1];
     const double m = s / B;
     double var = ss / B - m * m;
@@ -241,12 +246,12 @@ __global__ void __launch_bounds__(kTowerThreads)
 }
 
 // dbeta = sum g, dgamma = sum g zhat; c1 = mean(g), c2 = mean(g zhat) for the apply pass
-__global__ void __launch_bounds__(kFinCols * kFinLanes)
+__global__ void __launch_bounds__(kFinColsFast * kFinLanes)
     bn_finalize_bwd_kernel(const float *__restrict__ partial, int blocks, int B, int N, float *__restrict__ dgamma,
                            float *__restrict__ dbeta, float *__restrict__ c1, float *__restrict__ c2) {
     double tot[2];
     int n;
-    if (!column_totals<2>(partial, blocks, N, tot, &n)) return;
+    if (!column_totals<2, kFinLanes, kFinColsFast>(partial, blocks, N, tot, &n)) return;
     const double s = tot[0], sz = tot[1];
     dbeta[n] = (float)s;
     dgamma[n] = (float)sz;
@@ -536,7 +541,7 @@ extern "C" int ctr_bn_stats(const float *z, int64_t ldz, int32_t B, int32_t N, f
     const TowerGeom g = tower_geom(B, N);
     float *partial = static_cast<float *>(workspace);
     note_launch(), col_stats_kernel<<<g.blocks, kTowerThreads, 0, stream>>>(z, ldz, g, partial);
-    note_launch(), bn_finalize_fwd_kernel<kFinLanes><<<(N + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, stream>>>(partial, g.blocks, B, N, eps, momentum, mean, rstd,
+    note_launch(), bn_finalize_fwd_kernel<kFinLanes><<<(N + kFinColsFast - 1) / kFinColsFast, kFinColsFast * kFinLanes, 0, stream>>>(partial, g.blocks, B, N, eps, momentum, mean, rstd,
                                                                               running_mean, running_var,
                                                                               reinterpret_cast<long long *>(num_batches_tracked));
     CTR_CUDA_OK(cudaGetLastError());
@@ -550,7 +555,7 @@ extern "C" int ctr_bn_stats_from_partials(const float *partial, int32_t blocks, 
     cudaStream_t stream = (cudaStream_t)stream_;
     CTR_REQUIRE(partial && mean && rstd && blocks >= 1 && B >= 1 && N >= 1, "bad arguments");
     CTR_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "running_mean and running_var go together");
-    note_launch(), bn_finalize_fwd_kernel<64><<<(N + kFinCols - 1) / kFinCols, kFinCols * 64, 0, stream>>>(
+    note_launch(), bn_finalize_fwd_kernel<64><<<(N + kFinColsFast - 1) / kFinColsFast, kFinColsFast * 64, 0, stream>>>(
         partial, blocks, B, N, eps, momentum, mean, rstd, running_mean, running_var, reinterpret_cast<long long *>(num_batches_tracked));
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
@@ -595,7 +600,7 @@ extern "C" int ctr_bn_relu_dropout_bwd(const float *gy, int64_t ldgy, const floa
     float *c1 = partial + (size_t)kTowerMaxBlocks * 2 * N;
     float *c2 = c1 + N;
     note_launch(), bn_act_bwd_reduce_kernel<<<g.blocks, kTowerThreads, 0, stream>>>(gy, ldgy, z, ldz, g, a, partial);
-    note_launch(), bn_finalize_bwd_kernel<<<(N + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, stream>>>(partial, g.blocks, B, N, dgamma, dbeta, c1, c2);
+    note_launch(), bn_finalize_bwd_kernel<<<(N + kFinColsFast - 1) / kFinColsFast, kFinColsFast * kFinLanes, 0, stream>>>(partial, g.blocks, B, N, dgamma, dbeta, c1, c2);
     note_launch(), bn_act_bwd_apply_kernel<<<g.blocks, kTowerThreads, 0, stream>>>(gy, ldgy, z, ldz, g, a, c1, c2, gz, ldgz, partial);
     if (dbias != nullptr)
         note_launch(), col_sum_finalize_kernel<<<(N + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, stream>>>(partial, g.blocks, N, dbias);
