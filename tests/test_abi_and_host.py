@@ -169,3 +169,59 @@ def test_dropout_seed_is_snapshotted_per_forward():
     assert s1.data_ptr() != s2.data_ptr() and int(s2) == int(s1) + 1
     m._step_seed(torch.device("cpu"))
     assert int(s2) == int(s1) + 1                      # later forwards do not change what earlier ones hold
+
+
+def test_first_block_preparation_host_logic(monkeypatch):
+    """``nn.tower.prepare_first_block`` / ``CTRModelBase._take_prepared`` with the CUDA stream calls stubbed out (CPU tensors):
+    the prepared tensors are exactly what the in-line path builds (F.pad of the weight, its transpose, counter + 1), and a
+    preparation that does not fit the tower input is joined and dropped, never used."""
+    import contextlib
+
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from torchctr_b200.models import DNN
+    from torchctr_b200.nn import tower as T
+
+    class FakeStream:
+        waited = None
+
+        def wait_stream(self, other):
+            pass
+
+        def wait_event(self, ev):
+            self.waited = ev
+
+    class FakeEvent:
+        def record(self, stream):
+            self.stream = stream
+
+    main, side = FakeStream(), FakeStream()
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: main)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(T, "_wgrad_stream", lambda device: side)
+    lin = nn.Linear(429, 256)
+    counter = torch.tensor([5])
+    snap, w, wt, ready = T.prepare_first_block(lin, 3, counter, want_wt=True)
+    assert counter.item() == 6 and snap.item() == 6 and ready.stream is side
+    assert torch.equal(w, F.pad(lin.weight.detach(), (0, 3))) and torch.equal(wt, w.t().contiguous())
+    snap, w, wt, _ = T.prepare_first_block(lin, 0, counter, want_wt=False)
+    assert wt is None and w.data_ptr() == lin.weight.data_ptr() and snap.item() == 7
+
+    fc = [{"name": "a", "type": "sparse", "num_embeddings": 10, "emb_dim": 4}, {"name": "d", "type": "dense"}]
+    m = DNN(fc, [8, 4])
+    layers = list(m.tower)[:-1]
+    x = torch.zeros(2, 8)                              # 4 + 1 columns padded to 8: the first block sees 3 padding columns
+    assert m._take_prepared(x, layers) is None and m._first_block_pad == 3
+    m._prepare_tower()                                 # tables / tower on the CPU: nothing is prepared
+    assert m._prepared is None
+    made = T.prepare_first_block(m.tower[0], 3, m._seed_counter(torch.device("cpu")), True)
+    entry = (made, 3, T.matmul_precision(), m.tower[0].weight._version, m.tower[0])
+    m._prepared = entry
+    assert m._take_prepared(x, layers) is made and m._prepared is None
+    m._prepared = entry
+    assert m._take_prepared(torch.zeros(2, 12), layers) is None and main.waited is made[3]      # other width: joined, dropped
+    m._prepared = entry
+    with torch.no_grad():
+        m.tower[0].weight.mul_(1.0)                    # an in-place update after the preparation (version bump): stale, dropped
+    assert m._take_prepared(x, layers) is None
