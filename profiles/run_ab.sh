@@ -9,7 +9,7 @@ i=0
 for envs in "$@"; do
   i=$((i+1))
   echo "== [$i] $envs"
-  env $envs timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-exact > $out/bench_${tag}_$i.json 2> $out/bench_${tag}_$i.err || tail -5 $out/bench_${tag}_$i.err
+  env $envs timeout 300 python bench.py --steps ${AB_STEPS:-100} --warmup 5 --no-cpu-baseline --no-exact > $out/bench_${tag}_$i.json 2> $out/bench_${tag}_$i.err || tail -5 $out/bench_${tag}_$i.err
   python - $out/bench_${tag}_$i.json <<'PY'
 import json, sys
 try:

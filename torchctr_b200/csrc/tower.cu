@@ -13,6 +13,8 @@
 // The dropout mask is never stored: both directions recompute it from a counter-based generator keyed by
 // (device-resident step seed, layer, element), so a captured CUDA graph draws a fresh mask every replay.
 // All of it is HBM-bound fp32 streaming work; the GEMMs on either side are in gemm_tc.cu.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ctr {
@@ -116,10 +118,23 @@ __device__ __forceinline__ bool column_totals(const float *__restrict__ partial,
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
     if (n < N) {
-#pragma unroll 8
-        for (int b = j; b < blocks; b += LANES) {       // independent loads: eight blocks in flight per thread
+        // all loads of a batch are issued before the first one is consumed (left to itself the compiler interleaves each
+        // load with the conversion + add of an earlier one, which serialises on the first miss); rows are added in ascending
+        // order as before, rows past the end contribute + 0.0
+        constexpr int UB = LANES == 128 ? 16 : 8;
+        for (int b0 = j; b0 < blocks; b0 += LANES * UB) {
+            float v[UB][NQ];
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) acc[q] += (double)partial[((size_t)b * NQ + q) * N + n];
+            for (int u = 0; u < UB; ++u) {
+                const int b = b0 + u * LANES;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) v[u][q] = b < blocks ? __ldg(partial + ((size_t)b * NQ + q) * N + n) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) acc[q] += (double)v[u][q];
+            }
         }
     }
 #pragma unroll
@@ -555,8 +570,18 @@ extern "C" int ctr_bn_stats_from_partials(const float *partial, int32_t blocks, 
     cudaStream_t stream = (cudaStream_t)stream_;
     CTR_REQUIRE(partial && mean && rstd && blocks >= 1 && B >= 1 && N >= 1, "bad arguments");
     CTR_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "running_mean and running_var go together");
-    note_launch(), bn_finalize_fwd_kernel<64><<<(N + kFinColsFast - 1) / kFinColsFast, kFinColsFast * 64, 0, stream>>>(
-        partial, blocks, B, N, eps, momentum, mean, rstd, running_mean, running_var, reinterpret_cast<long long *>(num_batches_tracked));
+    // lanes per column: the GEMM epilogue leaves B / 32 partial rows (2048 for a 65536-row batch), i.e. a chain of 32 dependent-free
+    // but latency-bound loads per quantity and lane at 64 lanes; more lanes shorten it (CTR_FIN_LANES = 64 | 128 | 256, tuning knob)
+    static const int lanes_env = getenv("CTR_FIN_LANES") ? atoi(getenv("CTR_FIN_LANES")) : 64;
+    const int grid = (N + kFinColsFast - 1) / kFinColsFast;
+    long long *nbt = reinterpret_cast<long long *>(num_batches_tracked);
+    note_launch();
+    if (lanes_env >= 256 && blocks >= 1024)
+        bn_finalize_fwd_kernel<256><<<grid, kFinColsFast * 256, 0, stream>>>(partial, blocks, B, N, eps, momentum, mean, rstd, running_mean, running_var, nbt);
+    else if (lanes_env >= 128 && blocks >= 512)
+        bn_finalize_fwd_kernel<128><<<grid, kFinColsFast * 128, 0, stream>>>(partial, blocks, B, N, eps, momentum, mean, rstd, running_mean, running_var, nbt);
+    else
+        bn_finalize_fwd_kernel<64><<<grid, kFinColsFast * 64, 0, stream>>>(partial, blocks, B, N, eps, momentum, mean, rstd, running_mean, running_var, nbt);
     CTR_CUDA_OK(cudaGetLastError());
     return CTR_OK;
 }
