@@ -25,7 +25,7 @@ def flush(title, header, rows, top):
     samp = next((i for i, h in enumerate(header) if h.startswith("Warp Stall Sampling (All")), None)
     if samp is None:
         samp = next((i for i, h in enumerate(header) if h.startswith("# Samples") or h == "Samples"), None)
-    stalls = [(i, h) for i, h in enumerate(header) if h.startswith("stall_")]
+    stalls = [(i, h) for i, h in enumerate(header) if h.startswith("stall_") and "(" not in h]      # (all samples, not the "(Not Issued)" twins)
     total = sum(fnum(r[samp]) for r in rows) if samp is not None else 0.0
     print(f"## {title}: total samples {total:.0f}, instructions {len(rows)}")
     by_reason = sorted(((sum(fnum(r[i]) for r in rows), h) for i, h in stalls), reverse=True)
